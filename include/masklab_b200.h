@@ -1,0 +1,237 @@
+/* masklab_b200.h — C ABI of the B200-native MaskLab post-backbone hot path.
+ *
+ * One shared library (libmasklab_b200.so, hand-written CUDA for sm_100a) replaces
+ * the TensorFlow op chain behind the reference's Keras custom layers
+ * (/root/reference/engine/layers/{detection,instance,misc}.py).  The reference is
+ * pure Python, so "the FFI a maintainer would bind" is ctypes; every entry point
+ * below names the reference interface (file:line) it replaces.  INTEGRATION.md
+ * shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain C: device pointers, sizes, scalars; no torch / TF types.
+ *   - every pointer named *_dev is DEVICE memory on the ctx's GPU, 16-byte aligned,
+ *     dense row-major ("C contiguous"); tensors are BORROWED for the duration of
+ *     the enqueued work, never freed by the library.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation except in functions documented as "[syncs]".
+ *   - return 0 (MLP_OK) or a negative MLP_E* code; mlp_last_error() gives the
+ *     thread-local message.
+ *   - data-dependent shapes (M = kept boxes per image, Mf = RoIs per level) are
+ *     produced ON THE DEVICE as int32 scalars and consumed by later stages from
+ *     device memory; the host reads them only when it has to materialise the
+ *     reference's dynamically shaped tensors.
+ *   - a ctx owns scratch (candidate lists, NMS work space); one ctx per
+ *     (GPU, stream); not thread-safe.
+ *   - padding sentinel is -1 everywhere, at least one slot per image
+ *     (engine/layers/misc.py:235-236, 275-286).
+ */
+#ifndef MASKLAB_B200_H_
+#define MASKLAB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLP_VERSION 100          /* 0.1.0 */
+
+#define MLP_OK          0
+#define MLP_EINVAL     -1        /* bad argument (shape, alignment, limits)          */
+#define MLP_ECUDA      -2        /* CUDA runtime error (message has the CUDA string) */
+#define MLP_ENOMEM     -3        /* scratch allocation failed                        */
+#define MLP_EDLPACK    -4        /* DLPack tensor rejected (dtype/device/strides)    */
+#define MLP_EBATCH     -5        /* B > 32: tf.dynamic_partition(...,32), misc.py:275 */
+
+#define MLP_MAX_LEVELS   8
+#define MLP_MAX_ANCHORS  32
+#define MLP_MAX_BATCH    32      /* engine/layers/misc.py:275                        */
+#define MLP_MAX_KEEP     2048    /* largest nms_max_output_size the NMS kernels hold */
+
+typedef struct mlp_ctx mlp_ctx;
+typedef void* mlp_stream_t;      /* cudaStream_t */
+
+/* ---- library / context ------------------------------------------------------ */
+int         mlp_version(void);
+const char* mlp_last_error(void);
+int         mlp_ctx_create(int device, mlp_ctx** out);
+void        mlp_ctx_destroy(mlp_ctx* ctx);
+int         mlp_ctx_device(const mlp_ctx* ctx);
+int         mlp_ctx_sm_count(const mlp_ctx* ctx);
+/* Bytes of scratch currently owned by the ctx. */
+int64_t     mlp_ctx_scratch_bytes(const mlp_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench `gpu_launches`). */
+int64_t     mlp_ctx_launch_count(const mlp_ctx* ctx);
+
+/* ---- DLPack handoff ---------------------------------------------------------
+ * Python passes PyCapsule("dltensor") -> DLManagedTensor*; this validates it and
+ * extracts the plain pointer/shape the stage functions take.  Layout of
+ * DLManagedTensor follows dlpack.h (v0.x legacy struct, what
+ * torch.utils.dlpack.to_dlpack produces).  The tensor stays owned by the caller.  */
+typedef struct {
+    void*   data;            /* device pointer incl. byte_offset */
+    int32_t device_id;
+    int32_t ndim;
+    int32_t dtype_code;      /* 0 int, 1 uint, 2 float */
+    int32_t dtype_bits;
+    int64_t shape[8];
+    int64_t numel;
+} mlp_tensor_view;
+
+#define MLP_F32 0
+#define MLP_I32 1
+#define MLP_U8  2
+#define MLP_I64 3
+/* expect_dtype: one of MLP_F32/I32/U8/I64, or -1 to accept any.  Rejects non-CUDA
+ * devices, a device other than the ctx's, non-dense strides, ndim > 8 and
+ * pointers not aligned to 16 bytes. */
+int mlp_dlpack_view(const mlp_ctx* ctx, const void* dl_managed_tensor, int expect_dtype,
+                    mlp_tensor_view* out);
+
+/* ---- a1/a2: prior (anchor) configuration ------------------------------------
+ * Output of PriorBoxes.setup (engine/prior.py:55-67) grouped by stride ascending
+ * as PriorLayer.__init__ does (engine/layers/detection.py:260-262).               */
+typedef struct {
+    int32_t num_levels;
+    int32_t padding_same;                               /* 1: ceil(H/s) ('same'); 0: floor */
+    int32_t stride[MLP_MAX_LEVELS];
+    int32_t num_anchors[MLP_MAX_LEVELS];
+    int32_t anchor_w[MLP_MAX_LEVELS][MLP_MAX_ANCHORS];
+    int32_t anchor_h[MLP_MAX_LEVELS][MLP_MAX_ANCHORS];
+} mlp_prior_config;
+
+/* N = sum_l Hf_l*Wf_l*A_l for an H x W image; negative on bad config. */
+int64_t mlp_prior_count(const mlp_prior_config* prior, int height, int width);
+
+/* PriorLayer.call (engine/layers/detection.py:269-298): out_dev int32 [B,N,4]
+ * (cx,cy,w,h), anchor order (stride asc, y, x, anchor), tiled over the batch.     */
+int mlp_prior_layer(mlp_ctx* ctx, const mlp_prior_config* prior, int batch, int height,
+                    int width, int32_t* out_dev, mlp_stream_t stream);
+
+/* ---- a3: RestoreBoxes.call (engine/layers/detection.py:325-344) --------------
+ * loc_dev f32 [rows,4], prior_dev [rows,4] int32 (prior_is_f32=0) or f32 (=1)
+ * -> out_dev f32 [rows,4] (cx,cy,w,h).  exp() is the correctly rounded f32 value. */
+int mlp_restore_boxes(mlp_ctx* ctx, const float* loc_dev, const void* prior_dev,
+                      int prior_is_f32, int64_t rows, float* out_dev, mlp_stream_t stream);
+/* Same, anchors generated in-kernel from the prior config (no [B,N,4] prior tensor). */
+int mlp_restore_boxes_from_prior(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                                 int batch, int height, int width, float* out_dev,
+                                 mlp_stream_t stream);
+
+/* ---- a4: NormalizeBoxes.call (engine/layers/detection.py:360-375) ------------
+ * boxes_dev f32 [rows,row_stride] (first 4 columns cx,cy,w,h) -> out_dev f32
+ * [rows,4] (y1,x1,y2,x2)/(H,W).                                                   */
+int mlp_normalize_boxes(mlp_ctx* ctx, const float* boxes_dev, int64_t rows, int row_stride,
+                        float image_h, float image_w, float* out_dev, mlp_stream_t stream);
+
+/* ---- a5-a8: DetectionProposal.call (engine/layers/detection.py:482-567) ------ */
+typedef struct {
+    float   min_confidence;        /* cls_pred >= min_confidence                     */
+    float   nms_iou_threshold;     /* per (image,class) NMS: suppress iff IoU > thr  */
+    float   post_iou_threshold;    /* per image cross-class NMS                      */
+    int32_t nms_max_output_size;   /* cap on kept boxes per NMS call, <= MLP_MAX_KEEP */
+    int32_t strict_batch;          /* 1: reject B > 32 like misc.py:275              */
+} mlp_detection_params;
+
+/* cls_dev f32 [B,N,C]; boxes_dev f32 [B,N,4] (cx,cy,w,h) as RestoreBoxes returns.
+ * Outputs (capacity K = nms_max_output_size rows per image):
+ *   det_dev    f32 [B,K,6]  (cx,cy,w,h,class,score), rows >= count[b] are -1
+ *   keep_dev   i32 [B,K,2]  (anchor index n, class c) of each kept row, -1 padded
+ *                           (may be NULL)
+ *   counts_dev i32 [B]      kept boxes per image
+ *   m_dev      i32 [1]      M = max(1, max_b counts[b])  -> reference output is
+ *                           det[:, :M, :] (MoldBatch, engine/layers/misc.py:231-286) */
+int mlp_detection_proposal(mlp_ctx* ctx, const float* cls_dev, const float* boxes_dev,
+                           int batch, int64_t num_boxes, int num_classes,
+                           const mlp_detection_params* params, float* det_dev,
+                           int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev,
+                           mlp_stream_t stream);
+
+/* Fused a2+a3+a4+a5-a8: boxes are decoded from loc_dev [B,N,4] and the prior
+ * config only for candidates that pass the score threshold; no [B,N,4] prior or
+ * restored-box tensor is materialised.  Same outputs as mlp_detection_proposal.    */
+int mlp_detect_from_heads(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                          const float* cls_dev, int batch, int height, int width,
+                          int num_classes, const mlp_detection_params* params,
+                          float* det_dev, int32_t* keep_dev, int32_t* counts_dev,
+                          int32_t* m_dev, mlp_stream_t stream);
+
+/* ---- a9: MaskDistribute.call (engine/layers/instance.py:52-66) ---------------
+ * det_dev f32 [rows,6] -> out_dev f32 [rows,7] (k,cx,cy,w,h,class,score).         */
+int mlp_mask_distribute(mlp_ctx* ctx, const float* det_dev, int64_t rows, int max_k,
+                        float base_size, float* out_dev, mlp_stream_t stream);
+
+/* ---- a10: PyramidRoiAlign.call (engine/layers/instance.py:109-139) -----------
+ * Plan: per level f and image b count rows of dist_dev [B,M,7] with k == f;
+ *   level_counts_dev i32 [L,B];  level_m_dev i32 [L+1]: [f] = Mf = max(1, max_b count),
+ *   [L] = sum_f Mf (R, written by mlp_roi_align_run; TrimInstances reads it as r_dev).
+ * dist row stride is m_stride rows per image (the capacity K when dist_dev is a
+ * capacity buffer); only the first *m_dev rows (or m_rows when m_dev is NULL) of
+ * each image are looked at.                                                       */
+int mlp_roi_align_plan(mlp_ctx* ctx, const float* dist_dev, int batch, int m_rows, int m_stride,
+                       const int32_t* m_dev, int num_levels, int32_t* level_counts_dev,
+                       int32_t* level_m_dev, mlp_stream_t stream);
+
+/* Run: fmaps_dev[f] f32 [B,fh[f],fw[f],Cf] (NHWC).  For each level f writes
+ *   crops_dev[f]   f32 [B,Mf,ch,cw,Cf] with Mf = level_m_dev[f] read ON DEVICE
+ *                  (caller allocates capacity >= B*m_rows slots, or exactly B*Mf
+ *                  after reading level_m_dev), -1 in padded slots;
+ *   roi_boxes_dev  f32 [B,sum_f Mf,6] (cx,cy,w,h,class,score), level-major, -1 pad.
+ * crop_and_resize arithmetic of TF (bilinear, extrapolation 0), boxes normalised
+ * by the model-input image size (image_h,image_w) at every level.                  */
+int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, const int32_t* fh,
+                      const int32_t* fw, int num_levels, int channels, const float* dist_dev,
+                      int batch, int m_rows, int m_stride, const int32_t* m_dev,
+                      float image_h, float image_w, int crop_h, int crop_w,
+                      const int32_t* level_counts_dev, int32_t* level_m_dev,
+                      float* const* crops_dev, float* roi_boxes_dev, mlp_stream_t stream);
+
+/* ---- a11: TrimInstances.call (engine/layers/instance.py:258-277) -------------
+ * roi_boxes_dev f32 [B,R,6], roi_masks_dev f32 [B,R,mh,mw,C].  R is read from
+ * r_dev (i32 [1], e.g. the sum of level_m_dev) when not NULL, else r_rows.
+ * Plan writes counts_dev i32 [B] (rows with class != -1) and m_dev i32 [1].
+ * Run writes out_boxes_dev f32 [B,M,6] and out_masks_dev f32 [B,M,mh,mw] (the class
+ * channel of each valid row), M read from m_dev on device, -1 padded.             */
+int mlp_trim_plan(mlp_ctx* ctx, const float* roi_boxes_dev, int batch, int r_rows,
+                  const int32_t* r_dev, int32_t* counts_dev, int32_t* m_dev, mlp_stream_t stream);
+int mlp_trim_run(mlp_ctx* ctx, const float* roi_boxes_dev, const float* roi_masks_dev, int batch,
+                 int r_rows, const int32_t* r_dev, int mask_h, int mask_w, int num_classes,
+                 const int32_t* m_dev, float* out_boxes_dev, float* out_masks_dev,
+                 mlp_stream_t stream);
+
+/* ---- a12: UpSampleOutput.call, instance part (engine/layers/misc.py:169-188) --
+ * det_dev f32 [rows,6] -> det_i32_dev [rows,6]; masks_dev f32 [mask_elems] ->
+ * masks_i32_dev (mask > 0.5).  ratio_h = PH/h_s, ratio_w = PW/w_s; cx,w use
+ * ratio_h and cy,h use ratio_w exactly as misc.py:180-183 does.                   */
+int mlp_upsample_output(mlp_ctx* ctx, const float* det_dev, int64_t rows, float ratio_h,
+                        float ratio_w, int32_t* det_i32_dev, const float* masks_dev,
+                        int64_t mask_elems, int32_t* masks_i32_dev, mlp_stream_t stream);
+
+/* ---- a13/a14: CropAndPadMask.call (engine/layers/misc.py:358-401) ------------ */
+#define MLP_PASTE_F32 0   /* drop-in: f32 bilinear values, [B,M,PH,PW]                  */
+#define MLP_PASTE_U8  1   /* canonical binary mask (value > 0.5, misc.py:457,:611-615) */
+/* det_i32_dev [B,M,6], masks_i32_dev i32 [B,M,mh,mw] -> out_dev [B,M,PH,PW].
+ * M is read from m_dev (i32 [1]) when not NULL, else m_rows; m_stride is the row
+ * stride of det/masks per image.  A box clipped to zero area gives an all-zero mask
+ * (TF raises InvalidArgument there).                                              */
+int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* masks_i32_dev,
+                          int batch, int m_rows, int m_stride, const int32_t* m_dev, int mask_h,
+                          int mask_w, int frame_h, int frame_w, int out_mode, void* out_dev,
+                          mlp_stream_t stream);
+
+/* ---- a8: MoldBatch.call (engine/layers/misc.py:231-286) as a standalone operator ----
+ * x_dev [K,row_elems] of 4-byte elements, batch_idx_dev i32 [K] (image id of each row).
+ * Plan: counts_dev i32 [B], m_dev i32 [1] = max(1, max_b count).  Run: out_dev
+ * [B,M,row_elems] (M read on device), input order kept per image, padded with -1
+ * (-1.0f when pad_is_float, else int -1).  Rows whose id is outside [0,B) are dropped
+ * (tf.dynamic_partition raises there).                                              */
+int mlp_mold_batch_plan(mlp_ctx* ctx, const int32_t* batch_idx_dev, int64_t rows, int batch,
+                        int32_t* counts_dev, int32_t* m_dev, mlp_stream_t stream);
+int mlp_mold_batch_run(mlp_ctx* ctx, const void* x_dev, const int32_t* counts_dev, int64_t rows,
+                       int64_t row_elems, int batch, int pad_is_float, const int32_t* m_dev,
+                       void* out_dev, mlp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASKLAB_B200_H_ */

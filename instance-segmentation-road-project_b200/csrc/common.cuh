@@ -1,0 +1,162 @@
+// common.cuh — shared host/device helpers for libmasklab_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "masklab_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmasklab_b200 is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------- context ----
+#define MLP_NUM_ARENAS 6
+struct mlp_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    // grow-only scratch arenas, one per stage family so that stages never alias each
+    // other's work space (cudaMalloc'd; regrown only between calls)
+    void* arena[MLP_NUM_ARENAS];
+    int64_t arena_bytes[MLP_NUM_ARENAS];
+    // small device block for counters / dims (always allocated)
+    int32_t* ctr;          // [MLP_CTR_WORDS]
+};
+
+#define MLP_CTR_WORDS 1024
+#define MLP_ARENA_DETECT 0
+#define MLP_ARENA_ROI    1
+#define MLP_ARENA_TRIM   2
+#define MLP_ARENA_PASTE  3
+#define MLP_ARENA_MOLD   4
+#define MLP_ARENA_FUSED  5
+
+void mlp_set_error(const char* fmt, ...);
+int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes);
+
+#define MLP_CHECK_ARG(cond, ...)                      \
+    do {                                              \
+        if (!(cond)) {                                \
+            mlp_set_error(__VA_ARGS__);               \
+            return MLP_EINVAL;                        \
+        }                                             \
+    } while (0)
+
+#define MLP_CUDA(call)                                                               \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            mlp_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                          __FILE__, __LINE__);                                       \
+            return MLP_ECUDA;                                                        \
+        }                                                                            \
+    } while (0)
+
+#define MLP_LAUNCH_CHECK(ctx)                                                        \
+    do {                                                                             \
+        (ctx)->launches++;                                                           \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            mlp_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                          __FILE__, __LINE__);                                       \
+            return MLP_ECUDA;                                                        \
+        }                                                                            \
+    } while (0)
+
+static inline bool mlp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------- device helpers ------
+// Streaming 128-bit global accesses: read-once inputs bypass L1, write-once
+// outputs do not allocate in L1 (guideline 13/14 of the Blackwell playbook).
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// Correctly rounded float32 exp / log (evaluate in fp64, round once).  The oracle
+// does the same (oracle/masklab_oracle.py exp_f32/log_f32), which makes the
+// decoded boxes and FPN levels agree bit for bit between CPU and GPU.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float log_cr(float x) { return (float)log((double)x); }
+
+// Order-preserving map float -> uint32 (ascending), -0.0 folded onto +0.0.
+__device__ __forceinline__ uint32_t float_ordered(float f) {
+    f = f + 0.0f;
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_ordered(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+
+// Anchor lookup table passed by value to kernels (built from mlp_prior_config
+// for one image size).
+struct PriorDev {
+    int num_levels;
+    int total;                            // N
+    int stride[MLP_MAX_LEVELS];
+    int hf[MLP_MAX_LEVELS];
+    int wf[MLP_MAX_LEVELS];
+    int na[MLP_MAX_LEVELS];
+    int start[MLP_MAX_LEVELS + 1];        // first anchor index of each level
+    short aw[MLP_MAX_LEVELS][MLP_MAX_ANCHORS];
+    short ah[MLP_MAX_LEVELS][MLP_MAX_ANCHORS];
+};
+
+int mlp_build_prior_dev(const mlp_prior_config* prior, int height, int width, PriorDev* out);
+
+// anchor n -> (cx, cy, w, h) as ints (engine/layers/detection.py:272-295)
+__device__ __forceinline__ int4 prior_anchor(const PriorDev& P, int n) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < MLP_MAX_LEVELS; ++i)
+        if (i < P.num_levels && n >= P.start[i]) l = i;
+    int r = n - P.start[l];
+    int A = P.na[l];
+    int cell = r / A;
+    int a = r - cell * A;
+    int y = cell / P.wf[l];
+    int x = cell - y * P.wf[l];
+    int s = P.stride[l];
+    return make_int4(s / 2 + x * s, s / 2 + y * s, (int)P.aw[l][a], (int)P.ah[l][a]);
+}
+
+// RestoreBoxes arithmetic (engine/layers/detection.py:333-341); compiled with
+// -fmad=false so multiply and add round separately like TF/NumPy.
+__device__ __forceinline__ float4 restore_box(const float4 loc, const int4 pr) {
+    float pcx = (float)pr.x, pcy = (float)pr.y, pw = (float)pr.z, ph = (float)pr.w;
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(loc.x, pw), pcx);
+    o.y = __fadd_rn(__fmul_rn(loc.y, ph), pcy);
+    o.z = __fmul_rn(exp_cr(loc.z), pw);
+    o.w = __fmul_rn(exp_cr(loc.w), ph);
+    return o;
+}

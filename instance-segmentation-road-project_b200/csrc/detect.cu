@@ -1,0 +1,665 @@
+// detect.cu — DetectionProposal (rows a5-a8 of SURVEY.md §8):
+//   K1 threshold_compact : one streaming pass over cls_pred [B,N,C] (128-bit loads),
+//                          candidates appended per (image,class) as 64-bit keys
+//                          (descending score | anchor index)  -> a total order, so the
+//                          append order does not matter.
+//   K2 nms_per_class     : one CTA per (image,class): sort keys in shared memory,
+//                          greedy NMS in chunks (kept list + intra-chunk bitmask), boxes
+//                          fetched (or decoded from loc_pred + anchors) only for candidates.
+//   K3 nms_cross_class   : one CTA per image over the concatenated per-class survivors
+//                          in tf.unique first-appearance order; writes the -1 padded
+//                          [B,K,6] rows, kept (n,c), counts and M.
+// Reference: /root/reference/engine/layers/detection.py:482-567; TF NonMaxSuppressionV3
+// semantics restated in oracle/tf_ops.py.  Compiled with -fmad=false: IoU and decode
+// round every multiply/add separately so kept indices match the CPU oracle bit for bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kClassThreads = 512;          // K2: several CTAs per SM (B*C CTAs in one wave)
+constexpr int kCrossThreads = 1024;         // K3: one CTA per image
+constexpr int kChunk = 256;                 // candidates resolved per round
+constexpr int kMaskWords = kChunk / 32;
+constexpr uint64_t kKeyPad = ~0ull;
+
+struct BoxC { float ymin, xmin, ymax, xmax, area; };
+
+// NormalizeBoxes with shape = ones (detection.py:367-374, :488) then the min/max
+// canonicalisation and area of TF's IOU().
+__device__ __forceinline__ BoxC corners_of(const float4 b) {
+    float hw = __fmul_rn(b.z, 0.5f), hh = __fmul_rn(b.w, 0.5f);
+    float y1 = __fsub_rn(b.y, hh), x1 = __fsub_rn(b.x, hw);
+    float y2 = __fadd_rn(b.y, hh), x2 = __fadd_rn(b.x, hw);
+    BoxC c;
+    c.ymin = fminf(y1, y2); c.xmin = fminf(x1, x2);
+    c.ymax = fmaxf(y1, y2); c.xmax = fmaxf(x1, x2);
+    c.area = __fmul_rn(__fsub_rn(c.ymax, c.ymin), __fsub_rn(c.xmax, c.xmin));
+    return c;
+}
+
+// IoU(a,b) > thr, TF operation order, true division.
+__device__ __forceinline__ bool iou_exceeds(float aymin, float axmin, float aymax, float axmax,
+                                            float aarea, float bymin, float bxmin, float bymax,
+                                            float bxmax, float barea, float thr) {
+    if (aarea <= 0.0f || barea <= 0.0f) return 0.0f > thr;
+    float ih = fmaxf(__fsub_rn(fminf(aymax, bymax), fmaxf(aymin, bymin)), 0.0f);
+    float iw = fmaxf(__fsub_rn(fminf(axmax, bxmax), fmaxf(axmin, bxmin)), 0.0f);
+    float inter = __fmul_rn(ih, iw);
+    if (inter == 0.0f) return 0.0f > thr;
+    float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+    return iou > thr;
+}
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t low) {
+    return ((uint64_t)(~float_ordered(score)) << 32) | low;
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+    return float_from_ordered(~(uint32_t)(key >> 32));
+}
+
+// ------------------------------------------------------------------ K1 -------
+// cand_keys [G][cap] (G = B*C), cand_count [G].
+__global__ void __launch_bounds__(256)
+threshold_compact_kernel(const float* __restrict__ cls, int64_t total, int N, int C, float thr,
+                         uint64_t* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
+                         int64_t cap, int32_t* __restrict__ m_dev) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && m_dev) *m_dev = 1;
+    const int64_t total4 = total >> 2;
+    const float4* cls4 = reinterpret_cast<const float4*>(cls);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto emit = [&](int64_t e, float s) {
+        int64_t bn = e / C;
+        int c = (int)(e - bn * C);
+        int b = (int)(bn / N);
+        int n = (int)(bn - (int64_t)b * N);
+        int g = b * C + c;
+        int pos = atomicAdd(cand_count + g, 1);
+        if (pos < cap) cand_keys[(int64_t)g * cap + pos] = make_key(s, (uint32_t)n);
+    };
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // 4 independent 128-bit loads in flight per thread
+    for (; i + 3 * stride < total4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(cls4 + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t e = (i + u * stride) << 2;
+            if (v[u].x >= thr) emit(e, v[u].x);
+            if (v[u].y >= thr) emit(e + 1, v[u].y);
+            if (v[u].z >= thr) emit(e + 2, v[u].z);
+            if (v[u].w >= thr) emit(e + 3, v[u].w);
+        }
+    }
+    for (; i < total4; i += stride) {
+        float4 v = ldg_stream_f4(cls4 + i);
+        int64_t e = i << 2;
+        if (v.x >= thr) emit(e, v.x);
+        if (v.y >= thr) emit(e + 1, v.y);
+        if (v.z >= thr) emit(e + 2, v.z);
+        if (v.w >= thr) emit(e + 3, v.w);
+    }
+    for (int64_t e = (total4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += stride) {
+        float s = cls[e];
+        if (s >= thr) emit(e, s);
+    }
+}
+
+// --------------------------------------------------------- sort helpers ------
+__device__ void bitonic_sort_smem(uint64_t* s, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t a = s[i], b = s[ixj];
+                    bool asc = (i & k) == 0;
+                    if ((a > b) == asc) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Smallest pivot P such that #{key in gkeys : lo_excl < key <= P (or any key when
+// !have_lo)} == want.  Keys are unique, 1 <= want <= number of such keys.  MSB-first
+// 8-bit radix select; hist is a 256-int shared array, bcast a 2-word shared array.
+__device__ uint64_t radix_select_pivot(const uint64_t* gkeys, int cnt, bool have_lo,
+                                       uint64_t lo_excl, int want, int* hist,
+                                       unsigned long long* bcast) {
+    uint64_t prefix = 0, prefix_mask = 0;
+    int remaining = want;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            uint64_t k = gkeys[i];
+            if ((!have_lo || k > lo_excl) && (k & prefix_mask) == prefix)
+                atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0, d = 0;
+            for (; d < 256; ++d) {
+                if (acc + hist[d] >= remaining) break;
+                acc += hist[d];
+            }
+            bcast[0] = (unsigned long long)d;
+            bcast[1] = (unsigned long long)acc;
+        }
+        __syncthreads();
+        int d = (int)bcast[0];
+        remaining -= (int)bcast[1];
+        prefix |= ((uint64_t)d) << shift;
+        prefix_mask |= 0xffull << shift;
+        __syncthreads();
+    }
+    return prefix;     // the want-th smallest qualifying key itself
+}
+
+// ------------------------------------------------------------ NMS core -------
+struct NmsSmem {
+    uint64_t* skeys;        // [sort_cap]
+    float* k_ymin; float* k_xmin; float* k_ymax; float* k_xmax; float* k_area;   // [max_out]
+    float* c_ymin; float* c_xmin; float* c_ymax; float* c_xmax; float* c_area;   // [kChunk]
+    float4* c_box;          // [kChunk] cx,cy,w,h of the chunk's candidates
+    uint32_t* c_mask;       // [kChunk][kMaskWords]
+    int* c_supp;            // [kChunk]
+    uint32_t* keptw;        // [kMaskWords]
+    int* hist;              // [256]
+    unsigned long long* bcast;   // [2]
+    int* misc;              // [4]: 0 kept, 1 gather counter
+};
+
+__host__ __device__ inline size_t nms_smem_bytes(int sort_cap, int max_out) {
+    size_t b = 0;
+    b += (size_t)sort_cap * 8;
+    b += (size_t)max_out * 4 * 5;
+    b += (size_t)kChunk * 4 * 5;
+    b += (size_t)kChunk * 16;
+    b += (size_t)kChunk * kMaskWords * 4;
+    b += (size_t)kChunk * 4;
+    b += kMaskWords * 4;
+    b += 256 * 4;
+    b += 2 * 8;
+    b += 4 * 4;
+    return b + 64;
+}
+
+__device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_out) {
+    NmsSmem S;
+    unsigned char* p = base;
+    S.skeys = reinterpret_cast<uint64_t*>(p); p += (size_t)sort_cap * 8;
+    S.c_box = reinterpret_cast<float4*>(p);   p += (size_t)kChunk * 16;
+    S.bcast = reinterpret_cast<unsigned long long*>(p); p += 16;
+    S.k_ymin = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.k_xmin = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.k_ymax = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.k_xmax = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.k_area = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.c_ymin = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_xmin = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_ymax = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_xmax = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_area = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_mask = reinterpret_cast<uint32_t*>(p); p += (size_t)kChunk * kMaskWords * 4;
+    S.c_supp = reinterpret_cast<int*>(p); p += kChunk * 4;
+    S.keptw = reinterpret_cast<uint32_t*>(p); p += kMaskWords * 4;
+    S.hist = reinterpret_cast<int*>(p); p += 256 * 4;
+    S.misc = reinterpret_cast<int*>(p); p += 16;
+    return S;
+}
+
+// Greedy NMS over `cnt` unique keys in global memory (any order).  Pops keys in
+// ascending key order (= descending score, ties -> lower low-word), suppresses a
+// candidate iff IoU > thr with an earlier kept box, stops at max_out.  fetch(low)
+// returns the (cx,cy,w,h) box of a key; emit(rank, key, box) is called once per kept
+// box by exactly one thread.  Returns the kept count (block-uniform).
+template <int kThreads, class Fetch, class Emit>
+__device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
+                        int max_out, const NmsSmem& S, Fetch fetch, Emit emit) {
+    constexpr int kLanesPerCand = kThreads / kChunk;   // threads that split the kept list
+    static_assert(kThreads % kChunk == 0 && kMaskWords % kLanesPerCand == 0, "bad NMS geometry");
+    const int tid = threadIdx.x;
+    if (tid == 0) S.misc[0] = 0;
+    __syncthreads();
+    int kept = 0;
+    int done = 0;                    // keys consumed so far (in sorted order)
+    uint64_t lo = 0;                 // largest key consumed so far
+    while (done < cnt && kept < max_out) {
+        // ---- stage a super-chunk of up to sort_cap smallest unconsumed keys ----
+        const int remaining = cnt - done;
+        const int sc = remaining < sort_cap ? remaining : sort_cap;
+        const bool have_lo = done > 0;
+        uint64_t pivot = kKeyPad;
+        if (remaining > sort_cap)
+            pivot = radix_select_pivot(gkeys, cnt, have_lo, lo, sc, S.hist, S.bcast);
+        if (tid == 0) S.misc[1] = 0;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += blockDim.x) {
+            uint64_t k = gkeys[i];
+            if ((!have_lo || k > lo) && k <= pivot) {
+                int pos = atomicAdd(&S.misc[1], 1);
+                if (pos < sort_cap) S.skeys[pos] = k;
+            }
+        }
+        int p2 = 1;
+        while (p2 < sc) p2 <<= 1;
+        __syncthreads();
+        for (int i = sc + tid; i < p2; i += blockDim.x) S.skeys[i] = kKeyPad;
+        __syncthreads();
+        bitonic_sort_smem(S.skeys, p2);
+        lo = S.skeys[sc - 1];
+        done += sc;
+
+        // ---- chunks of kChunk candidates ----
+        for (int base = 0; base < sc && kept < max_out; base += kChunk) {
+            const int m = (sc - base) < kChunk ? (sc - base) : kChunk;
+            if (tid < kChunk) {
+                if (tid < m) {
+                    uint64_t key = S.skeys[base + tid];
+                    float4 bx = fetch((uint32_t)key);
+                    BoxC c = corners_of(bx);
+                    S.c_box[tid] = bx;
+                    S.c_ymin[tid] = c.ymin; S.c_xmin[tid] = c.xmin;
+                    S.c_ymax[tid] = c.ymax; S.c_xmax[tid] = c.xmax; S.c_area[tid] = c.area;
+                    S.c_supp[tid] = 0;
+                } else {
+                    S.c_supp[tid] = 1;
+                }
+            }
+            if (tid < kMaskWords) S.keptw[tid] = 0;
+            __syncthreads();
+            const int t = tid % kChunk, r = tid / kChunk;
+            const float tymin = S.c_ymin[t], txmin = S.c_xmin[t], tymax = S.c_ymax[t],
+                        txmax = S.c_xmax[t], tarea = S.c_area[t];
+            // (b) against the kept list, split over kLanesPerCand threads per candidate
+            if (t < m) {
+                for (int j = r; j < kept; j += kLanesPerCand) {
+                    if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.k_ymin[j], S.k_xmin[j],
+                                    S.k_ymax[j], S.k_xmax[j], S.k_area[j], thr)) {
+                        S.c_supp[t] = 1;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            // (c) intra-chunk bitmask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
+            {
+                const bool t_alive = (t < m) && (S.c_supp[t] == 0);
+#pragma unroll
+                for (int wi = 0; wi < kMaskWords / kLanesPerCand; ++wi) {
+                    const int w = r * (kMaskWords / kLanesPerCand) + wi;
+                    uint32_t bits = 0;
+                    if (t_alive) {
+                        const int u0 = w * 32;
+                        const int u1 = (u0 + 32 < t) ? (u0 + 32) : t;
+                        for (int u = u0; u < u1; ++u) {
+                            if (S.c_supp[u] == 0 &&
+                                iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.c_ymin[u],
+                                            S.c_xmin[u], S.c_ymax[u], S.c_xmax[u], S.c_area[u], thr))
+                                bits |= 1u << (u - u0);
+                        }
+                    }
+                    S.c_mask[t * kMaskWords + w] = bits;
+                }
+            }
+            __syncthreads();
+            // (d) sequential resolve by warp 0: lane l owns kept word l
+            if (tid < 32) {
+                uint32_t myw = 0;
+                int k = kept;
+                for (int q = 0; q < m && k < max_out; ++q) {
+                    bool alive = S.c_supp[q] == 0;
+                    uint32_t hit = (tid < kMaskWords) ? (S.c_mask[q * kMaskWords + tid] & myw) : 0u;
+                    bool any = __any_sync(0xffffffffu, hit != 0);
+                    if (alive && !any) {
+                        if (tid == (q >> 5)) myw |= 1u << (q & 31);
+                        ++k;
+                    }
+                }
+                if (tid < kMaskWords) S.keptw[tid] = myw;
+                if (tid == 0) S.misc[0] = k;
+            }
+            __syncthreads();
+            // (e) append newly kept boxes in order and emit them
+            if (tid < m) {
+                uint32_t wv = S.keptw[tid >> 5];
+                if ((wv >> (tid & 31)) & 1u) {
+                    int rank = kept;
+                    for (int w = 0; w < (tid >> 5); ++w) rank += __popc(S.keptw[w]);
+                    rank += __popc(wv & ((1u << (tid & 31)) - 1u));
+                    S.k_ymin[rank] = S.c_ymin[tid]; S.k_xmin[rank] = S.c_xmin[tid];
+                    S.k_ymax[rank] = S.c_ymax[tid]; S.k_xmax[rank] = S.c_xmax[tid];
+                    S.k_area[rank] = S.c_area[tid];
+                    emit(rank, S.skeys[base + tid], S.c_box[tid]);
+                }
+            }
+            kept = S.misc[0];
+            __syncthreads();
+        }
+    }
+    return kept;
+}
+
+// ------------------------------------------------------------------ K2 -------
+struct FetchBoxes {
+    const float4* boxes;     // [N] of this image
+    __device__ float4 operator()(uint32_t n) const { return boxes[n]; }
+};
+struct FetchDecode {
+    const PriorDev* P;
+    const float4* loc;       // [N] of this image
+    __device__ float4 operator()(uint32_t n) const { return restore_box(loc[n], prior_anchor(*P, (int)n)); }
+};
+
+struct DetScratch {
+    uint64_t* cand_keys;     // [G][cap]
+    int32_t* cand_count;     // [G]
+    int32_t* cls_kept;       // [G]
+    int32_t* min_n;          // [G]
+    float4* rec_box;         // [G][max_out]
+    int2* rec_sn;            // [G][max_out] (score bits, n)
+    uint64_t* cat_keys;      // [B][C*max_out]
+    float4* cat_box;         // [B][C*max_out]
+    int2* cat_sn;            // [B][C*max_out] (score bits, n)
+    int32_t* cat_c;          // [B][C*max_out]
+    int64_t cap;
+};
+
+template <bool kDecode>
+__global__ void __launch_bounds__(kClassThreads, 2)
+nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restrict__ boxes_or_loc,
+                     int N, int C, float thr, int max_out, int sort_cap, DetScratch D) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
+    const int g = blockIdx.x;
+    const int b = g / C;
+    int cnt = D.cand_count[g];
+    if ((int64_t)cnt > D.cap) cnt = (int)D.cap;
+    const uint64_t* gkeys = D.cand_keys + (int64_t)g * D.cap;
+
+    // first anchor index at which this (image,class) appears: orders the groups like
+    // tf.unique does in the row-major (b,n,c) scan (detection.py:519-520)
+    {
+        int mn = 0x7fffffff;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            int n = (int)(uint32_t)gkeys[i];
+            mn = n < mn ? n : mn;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            int v = __shfl_xor_sync(0xffffffffu, mn, o);
+            mn = v < mn ? v : mn;
+        }
+        if (threadIdx.x == 0) S.hist[0] = 0x7fffffff;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) atomicMin(&S.hist[0], mn);
+        __syncthreads();
+        if (threadIdx.x == 0) D.min_n[g] = S.hist[0];
+        __syncthreads();
+    }
+    if (cnt == 0) {
+        if (threadIdx.x == 0) D.cls_kept[g] = 0;
+        return;
+    }
+    float4* rec_box = D.rec_box + (int64_t)g * max_out;
+    int2* rec_sn = D.rec_sn + (int64_t)g * max_out;
+    auto emit = [&](int rank, uint64_t key, const float4& bx) {
+        rec_box[rank] = bx;
+        rec_sn[rank] = make_int2(__float_as_int(key_score(key)), (int)(uint32_t)key);
+    };
+    int kept;
+    if (kDecode) {
+        FetchDecode f{&P, boxes_or_loc + (int64_t)b * N};
+        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit);
+    } else {
+        FetchBoxes f{boxes_or_loc + (int64_t)b * N};
+        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit);
+    }
+    if (threadIdx.x == 0) D.cls_kept[g] = kept;
+}
+
+// ------------------------------------------------------------------ K3 -------
+struct FetchCat {
+    const float4* box;
+    __device__ float4 operator()(uint32_t p) const { return box[p]; }
+};
+
+__global__ void __launch_bounds__(kCrossThreads)
+nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D,
+                       float* __restrict__ det, int32_t* __restrict__ keep,
+                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
+    __shared__ int s_order[256];
+    __shared__ int s_off[257];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    // groups of this image in first-appearance order: sort by (min_n, c)
+    if (tid == 0) {
+        int ng = 0;
+        for (int c = 0; c < C; ++c) {
+            if (D.cand_count[b * C + c] > 0) {
+                int mn = D.min_n[b * C + c];
+                int pos = ng++;
+                while (pos > 0 && D.min_n[b * C + s_order[pos - 1]] > mn) {
+                    s_order[pos] = s_order[pos - 1];
+                    --pos;
+                }
+                s_order[pos] = c;
+            }
+        }
+        int off = 0;
+        for (int i = 0; i < ng; ++i) {
+            s_off[i] = off;
+            off += D.cls_kept[b * C + s_order[i]];
+        }
+        s_off[ng] = off;
+        S.misc[2] = ng;
+        S.misc[3] = off;
+    }
+    __syncthreads();
+    const int ng = S.misc[2];
+    const int total = S.misc[3];
+    const int64_t cat_base = (int64_t)b * C * max_out;
+    uint64_t* cat_keys = D.cat_keys + cat_base;
+    float4* cat_box = D.cat_box + cat_base;
+    int2* cat_sn = D.cat_sn + cat_base;
+    int32_t* cat_c = D.cat_c + cat_base;
+    for (int gi = 0; gi < ng; ++gi) {
+        const int c = s_order[gi];
+        const int g = b * C + c;
+        const int n_g = s_off[gi + 1] - s_off[gi];
+        for (int i = tid; i < n_g; i += blockDim.x) {
+            const int p = s_off[gi] + i;
+            float4 bx = D.rec_box[(int64_t)g * max_out + i];
+            int2 sn = D.rec_sn[(int64_t)g * max_out + i];
+            cat_box[p] = bx;
+            cat_sn[p] = sn;
+            cat_c[p] = c;
+            cat_keys[p] = make_key(__int_as_float(sn.x), (uint32_t)p);
+        }
+    }
+    __syncthreads();
+    float* det_b = det + (int64_t)b * max_out * 6;
+    int32_t* keep_b = keep ? keep + (int64_t)b * max_out * 2 : nullptr;
+    auto emit = [&](int rank, uint64_t key, const float4& bx) {
+        const uint32_t p = (uint32_t)key;
+        const int2 sn = cat_sn[p];
+        const int c = cat_c[p];
+        float* o = det_b + rank * 6;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = (float)c;
+        o[5] = __int_as_float(sn.x);
+        if (keep_b) { keep_b[rank * 2] = sn.y; keep_b[rank * 2 + 1] = c; }
+    };
+    int kept = 0;
+    if (total > 0) {
+        FetchCat f{cat_box};
+        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit);
+    }
+    // -1 padding of the unused rows (MoldBatch, misc.py:276-283)
+    for (int i = kept * 6 + tid; i < max_out * 6; i += blockDim.x) det_b[i] = -1.0f;
+    if (keep_b)
+        for (int i = kept * 2 + tid; i < max_out * 2; i += blockDim.x) keep_b[i] = -1;
+    if (tid == 0) {
+        counts[b] = kept;
+        if (m_dev) atomicMax(m_dev, kept > 1 ? kept : 1);
+    }
+}
+
+// ------------------------------------------------------------ host side ------
+struct DetPlan {
+    DetScratch D;
+    int64_t bytes;
+};
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int plan_scratch(mlp_ctx* ctx, int B, int64_t N, int C, int max_out, DetScratch* out) {
+    const int64_t G = (int64_t)B * C;
+    const int64_t cap = align_up(N, 2);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 256); return o; };
+    const int64_t o_keys = take(G * cap * 8);
+    const int64_t o_count = take(G * 4);
+    const int64_t o_kept = take(G * 4);
+    const int64_t o_minn = take(G * 4);
+    const int64_t o_rbox = take(G * max_out * 16);
+    const int64_t o_rsn = take(G * max_out * 8);
+    const int64_t o_ckeys = take(G * max_out * 8);
+    const int64_t o_cbox = take(G * max_out * 16);
+    const int64_t o_csn = take(G * max_out * 8);
+    const int64_t o_cc = take(G * max_out * 4);
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_DETECT, off);
+    if (rc) return rc;
+    char* base = static_cast<char*>(ctx->arena[MLP_ARENA_DETECT]);
+    out->cand_keys = reinterpret_cast<uint64_t*>(base + o_keys);
+    out->cand_count = reinterpret_cast<int32_t*>(base + o_count);
+    out->cls_kept = reinterpret_cast<int32_t*>(base + o_kept);
+    out->min_n = reinterpret_cast<int32_t*>(base + o_minn);
+    out->rec_box = reinterpret_cast<float4*>(base + o_rbox);
+    out->rec_sn = reinterpret_cast<int2*>(base + o_rsn);
+    out->cat_keys = reinterpret_cast<uint64_t*>(base + o_ckeys);
+    out->cat_box = reinterpret_cast<float4*>(base + o_cbox);
+    out->cat_sn = reinterpret_cast<int2*>(base + o_csn);
+    out->cat_c = reinterpret_cast<int32_t*>(base + o_cc);
+    out->cap = cap;
+    return MLP_OK;
+}
+
+int pick_sort_cap(int want_items, int max_out, size_t smem_limit) {
+    int cap = 256;
+    while (cap < want_items && cap < 16384 && nms_smem_bytes(cap * 2, max_out) <= smem_limit) cap <<= 1;
+    return cap;
+}
+
+int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int width,
+                   const float* cls_dev, const float* boxes_or_loc_dev, int B, int64_t N, int C,
+                   const mlp_detection_params* p, float* det_dev, int32_t* keep_dev,
+                   int32_t* counts_dev, int32_t* m_dev, cudaStream_t stream, const char* who) {
+    MLP_CHECK_ARG(ctx && cls_dev && boxes_or_loc_dev && p && det_dev && counts_dev,
+                  "%s: NULL argument", who);
+    MLP_CHECK_ARG(B >= 1 && N >= 1 && C >= 1, "%s: bad shape B=%d N=%lld C=%d", who, B, (long long)N, C);
+    MLP_CHECK_ARG(C <= 256, "%s: num_classes=%d > 256 not supported", who, C);
+    MLP_CHECK_ARG(N < (1ll << 30) && (int64_t)B * N * C < (1ll << 40), "%s: problem too large", who);
+    if (p->strict_batch && B > MLP_MAX_BATCH) {
+        mlp_set_error("%s: batch %d > 32; the reference's MoldBatch uses tf.dynamic_partition(.., 32) "
+                      "(engine/layers/misc.py:275). Pass strict_batch=0 to lift the limit.", who, B);
+        return MLP_EBATCH;
+    }
+    MLP_CHECK_ARG(p->nms_max_output_size >= 1 && p->nms_max_output_size <= MLP_MAX_KEEP,
+                  "%s: nms_max_output_size=%d out of range [1,%d]", who, p->nms_max_output_size,
+                  MLP_MAX_KEEP);
+    MLP_CHECK_ARG(mlp_aligned16(cls_dev) && mlp_aligned16(boxes_or_loc_dev) && mlp_aligned16(det_dev),
+                  "%s: pointers must be 16-byte aligned", who);
+    PriorDev P;
+    memset(&P, 0, sizeof(P));
+    if (prior) {
+        int rc = mlp_build_prior_dev(prior, height, width, &P);
+        if (rc) return rc;
+        MLP_CHECK_ARG(P.total == N, "%s: prior config gives %d anchors, tensors have %lld", who, P.total,
+                      (long long)N);
+    }
+    DeviceGuard g(ctx->device);
+    const int max_out = p->nms_max_output_size;
+    DetScratch D;
+    int rc = plan_scratch(ctx, B, N, C, max_out, &D);
+    if (rc) return rc;
+    const int G = B * C;
+    MLP_CUDA(cudaMemsetAsync(D.cand_count, 0, (size_t)G * 4, stream));
+
+    // K1: stream cls_pred once
+    {
+        const int64_t total = (int64_t)B * N * C;
+        int64_t blocks = (total / 4 + 255) / 256;
+        int64_t capb = (int64_t)ctx->sm_count * 8;
+        int grid = (int)(blocks < capb ? (blocks < 1 ? 1 : blocks) : capb);
+        threshold_compact_kernel<<<grid, 256, 0, stream>>>(cls_dev, total, (int)N, C,
+                                                          p->min_confidence, D.cand_keys,
+                                                          D.cand_count, D.cap, m_dev);
+        MLP_LAUNCH_CHECK(ctx);
+    }
+    // K2: per (image,class) NMS.  512-thread CTAs, <= 72 KB smem -> 3 CTAs per SM, so all
+    // B*C groups (160-192 at batch 32) are resident in a single wave on 148 SMs.
+    {
+        const int sort_cap = pick_sort_cap(4096, max_out, 72 * 1024);
+        const size_t smem = nms_smem_bytes(sort_cap, max_out);
+        if (prior) {
+            MLP_CUDA(cudaFuncSetAttribute(nms_per_class_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nms_per_class_kernel<true><<<G, kClassThreads, smem, stream>>>(
+                P, reinterpret_cast<const float4*>(boxes_or_loc_dev), (int)N, C, p->nms_iou_threshold,
+                max_out, sort_cap, D);
+        } else {
+            MLP_CUDA(cudaFuncSetAttribute(nms_per_class_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nms_per_class_kernel<false><<<G, kClassThreads, smem, stream>>>(
+                P, reinterpret_cast<const float4*>(boxes_or_loc_dev), (int)N, C, p->nms_iou_threshold,
+                max_out, sort_cap, D);
+        }
+        MLP_LAUNCH_CHECK(ctx);
+    }
+    // K3: cross-class NMS per image; sort buffer sized for C*max_out survivors when it fits.
+    {
+        const int sort_cap = pick_sort_cap(C * max_out, max_out, 200 * 1024);
+        const size_t smem = nms_smem_bytes(sort_cap, max_out);
+        MLP_CUDA(cudaFuncSetAttribute(nms_cross_class_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_cross_class_kernel<<<B, kCrossThreads, smem, stream>>>(C, p->post_iou_threshold, max_out,
+                                                                sort_cap, D, det_dev, keep_dev,
+                                                                counts_dev, m_dev);
+        MLP_LAUNCH_CHECK(ctx);
+    }
+    return MLP_OK;
+}
+
+}  // namespace
+
+extern "C" int mlp_detection_proposal(mlp_ctx* ctx, const float* cls_dev, const float* boxes_dev,
+                                      int batch, int64_t num_boxes, int num_classes,
+                                      const mlp_detection_params* params, float* det_dev,
+                                      int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev,
+                                      mlp_stream_t stream) {
+    return detection_impl(ctx, nullptr, 0, 0, cls_dev, boxes_dev, batch, num_boxes, num_classes, params,
+                          det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream,
+                          "mlp_detection_proposal");
+}
+
+extern "C" int mlp_detect_from_heads(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                                     const float* cls_dev, int batch, int height, int width,
+                                     int num_classes, const mlp_detection_params* params,
+                                     float* det_dev, int32_t* keep_dev, int32_t* counts_dev,
+                                     int32_t* m_dev, mlp_stream_t stream) {
+    if (!prior) {
+        mlp_set_error("mlp_detect_from_heads: prior config is NULL");
+        return MLP_EINVAL;
+    }
+    int64_t N = mlp_prior_count(prior, height, width);
+    if (N < 0) return (int)N;
+    return detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,
+                          det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream,
+                          "mlp_detect_from_heads");
+}

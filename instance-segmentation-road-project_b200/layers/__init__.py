@@ -1,0 +1,5 @@
+"""Drop-in mirror of /root/reference/engine/layers/ for the post-backbone hot path."""
+from .base import Layer, get_custom_objects                                    # noqa: F401
+from .detection import PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal   # noqa: F401
+from .instance import MaskDistribute, PyramidRoiAlign, TrimInstances          # noqa: F401
+from .misc import MoldBatch, UpSampleOutput, CropAndPadMask                   # noqa: F401

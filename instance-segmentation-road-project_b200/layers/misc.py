@@ -1,0 +1,118 @@
+"""Misc layers of the hot path — mirror of /root/reference/engine/layers/misc.py:
+MoldBatch (:213-293), UpSampleOutput (:164-196, instance part), CropAndPadMask (:354-401).
+"""
+import torch
+
+from .. import runtime as rt
+from .base import Layer, ctx_of, i32_scalar, null, register
+
+
+@register
+class MoldBatch(Layer):
+    """x [K,...] + batch_indices [K] -> [B, max(1, max count), ...], -1 padded, input order
+    kept per image.  With max_batch_size not None the reference partitions into exactly 32
+    buckets (misc.py:275), so B > 32 is an error; None lifts the limit (misc.py:239-271)."""
+
+    def __init__(self, max_batch_size=None, **kwargs):
+        self.max_batch_size = max_batch_size
+        super().__init__(**kwargs)
+
+    def call(self, inputs, **kwargs):
+        batch_indices = kwargs.get("batch_indices")
+        batch_size = int(kwargs.get("batch_size"))
+        ctx = ctx_of(inputs)
+        if self.max_batch_size is not None and batch_size > rt.MLP_MAX_BATCH:
+            raise rt.InvalidArgumentError(
+                rt.MLP_EBATCH, "MoldBatch: batch > 32 (tf.dynamic_partition(..,32), misc.py:275)")
+        x = inputs
+        if x.dtype not in (torch.float32, torch.int32):
+            x = x.to(torch.float32)
+        x = x.contiguous()
+        if not x.is_cuda:
+            raise rt.InvalidArgumentError(rt.MLP_EDLPACK, "MoldBatch: tensor is not on a CUDA device")
+        bi = batch_indices.to(device=x.device, dtype=torch.int32).contiguous()   # tf.cast(.., int32)
+        K = int(x.shape[0])
+        row = 1
+        for d in x.shape[1:]:
+            row *= int(d)
+        counts = i32_scalar(ctx, batch_size)
+        m_dev = i32_scalar(ctx, 1)
+        rt.check(ctx.lib.mlp_mold_batch_plan(ctx.handle, ctx.view(bi), K, batch_size, ctx.view(counts),
+                                             ctx.view(m_dev), ctx.stream()))
+        M = int(m_dev.item())
+        out = ctx.empty((batch_size, M) + tuple(x.shape[1:]), x.dtype)
+        if row > 0:
+            rt.check(ctx.lib.mlp_mold_batch_run(ctx.handle, ctx.view(x), ctx.view(counts), K, row,
+                                                batch_size, 1 if x.dtype == torch.float32 else 0,
+                                                ctx.view(m_dev), ctx.view(out), ctx.stream()))
+        return out
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"max_batch_size": self.max_batch_size})
+        return config
+
+
+@register
+class UpSampleOutput(Layer):
+    """[roi_box [B,M,6] f32, roi_mask [B,M,mh,mw] f32, semantic [B,hs,ws,S]], target=frames
+    -> (int32 boxes, int32 {0,1} masks, semantic).
+
+    Boxes are scaled to the target frame with the reference's (swapped) ratios
+    (misc.py:180-183: cx,w by PH/hs and cy,h by PW/ws) and truncated to int32; masks are
+    thresholded at 0.5.  The semantic branch (resize + threshold, misc.py:190-195) is outside
+    this path: the semantic tensor is only read for its shape and returned unchanged."""
+
+    def call(self, inputs, **kwargs):
+        target = kwargs.get("target")
+        roi_box, roi_mask, semantic = inputs[0], inputs[1], inputs[2]
+        ctx = ctx_of(roi_box)
+        box = rt.as_device_f32(ctx, roi_box, "UpSampleOutput roi_box")
+        mask = rt.as_device_f32(ctx, roi_mask, "UpSampleOutput roi_mask")
+        src_h, src_w = (semantic.shape[1], semantic.shape[2]) if hasattr(semantic, "shape") else semantic
+        dst_h, dst_w = (target.shape[1], target.shape[2]) if hasattr(target, "shape") else target
+        # float32 division like tf.cast(shape, f32) / tf.cast(shape, f32)
+        ratio = (torch.tensor([float(dst_h), float(dst_w)], dtype=torch.float32)
+                 / torch.tensor([float(src_h), float(src_w)], dtype=torch.float32))
+        box_i = ctx.empty(tuple(box.shape), torch.int32)
+        mask_i = ctx.empty(tuple(mask.shape), torch.int32)
+        rt.check(ctx.lib.mlp_upsample_output(
+            ctx.handle, ctx.view(box), box.numel() // 6, float(ratio[0]), float(ratio[1]),
+            ctx.view(box_i), ctx.view(mask), mask.numel(), ctx.view(mask_i), ctx.stream()))
+        return box_i, mask_i, semantic
+
+
+@register
+class CropAndPadMask(Layer):
+    """[images [B,PH,PW,3] (shape only), det_outs int32 [B,M,6], ins_outs int32 [B,M,mh,mw], ...]
+    -> pasted masks [B,M,PH,PW].
+
+    output='float32' (default) is the reference's tensor: bilinear values of the resized
+    mask inside the clipped box, 0 elsewhere.  output='uint8' fuses the consumers'
+    `> 0.5` (misc.py:457, :611-615) and writes the binary mask, a quarter of the bytes."""
+
+    def __init__(self, output="float32", **kwargs):
+        if output not in ("float32", "uint8"):
+            raise ValueError("output must be 'float32' or 'uint8'")
+        self.output = output
+        super().__init__(**kwargs)
+
+    def call(self, inputs, **kwargs):
+        images, det_outs, ins_outs = inputs[0], inputs[1], inputs[2]
+        ctx = ctx_of(det_outs)
+        frame_h, frame_w = (images.shape[1], images.shape[2]) if hasattr(images, "shape") else images
+        det = det_outs.to(torch.int32).contiguous()
+        ins = ins_outs.to(torch.int32).contiguous()
+        B, M = int(det.shape[0]), int(det.shape[1])
+        mh, mw = int(ins.shape[2]), int(ins.shape[3])
+        u8 = self.output == "uint8"
+        out = ctx.empty((B, M, int(frame_h), int(frame_w)), torch.uint8 if u8 else torch.float32)
+        rt.check(ctx.lib.mlp_crop_and_pad_mask(
+            ctx.handle, ctx.view(det), ctx.view(ins), B, M, M, null(), mh, mw, int(frame_h),
+            int(frame_w), rt.MLP_PASTE_U8 if u8 else rt.MLP_PASTE_F32, ctx.view(out), ctx.stream()))
+        return out
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"output": self.output})
+        return config

@@ -1,0 +1,197 @@
+"""PostProcessPipeline — the whole post-backbone path as one sync-free device pipeline.
+
+It is the wiring of /root/reference/engine/retinamasklab.py:458-470 (RestoreBoxes ->
+DetectionProposal -> MaskDistribute -> PyramidRoiAlign), :615-616 (TrimInstances),
+:635-636 (UpSampleOutput) and /root/reference/road_project/setup/serving.py:30
+(CropAndPadMask), but on fixed-capacity device buffers: the data-dependent sizes
+(M kept boxes, Mf RoIs per level, R = sum Mf) stay on the device as int32 scalars that
+the next kernel reads, so a batch is enqueued without any host round trip.  The mask
+head (MaskSubNet, dense convolutions) is not part of this path: the caller runs it
+between `detect_and_align` and `trim_and_paste`.
+"""
+import ctypes
+from dataclasses import dataclass, field
+
+import torch
+
+from . import runtime as rt
+from .prior import PriorBoxes
+
+
+@dataclass
+class DetectionConfig:
+    """Hyper-parameters of the path; defaults are the reference's layer defaults
+    (engine/layers/detection.py:469-473, engine/layers/instance.py:47,104)."""
+    min_confidence: float = 0.05
+    nms_iou_threshold: float = 0.4
+    post_iou_threshold: float = 0.65
+    nms_max_output_size: int = 1000
+    max_k: int = 2
+    base_size: float = 64
+    crop_size: tuple = (14, 14)
+    mask_size: tuple = (28, 28)
+    padding: str = "same"
+    strict_batch: bool = True
+    paste_output: str = "uint8"          # 'uint8' (binary, > 0.5 fused) or 'float32' (drop-in)
+
+
+@dataclass
+class AlignedRois:
+    """Device-side result of the first half (everything MaskSubNet needs)."""
+    det: torch.Tensor             # [B,K,6] f32, -1 padded (K = nms_max_output_size capacity)
+    keep: torch.Tensor            # [B,K,2] i32 (anchor index, class), -1 padded
+    counts: torch.Tensor          # [B] i32
+    m_dev: torch.Tensor           # [1] i32  M = max(1, max counts)
+    dist: torch.Tensor            # [B,K,7] f32
+    level_counts: torch.Tensor    # [L,B] i32
+    level_m: torch.Tensor         # [L+1] i32: Mf per level, then R = sum Mf
+    crops: list = field(default_factory=list)   # per level flat capacity buffers, valid prefix [B,Mf,ch,cw,Cf]
+    roi_boxes: torch.Tensor = None               # flat capacity buffer, valid prefix [B,R,6]
+
+    def shapes(self):
+        """One D2H of L+1 ints: (Mf list, R)."""
+        v = self.level_m.tolist()
+        return v[:-1], v[-1]
+
+
+class PostProcessPipeline:
+    def __init__(self, prior, image_hw, frame_hw, num_classes, fpn_channels, batch,
+                 config=None, device=None):
+        self.cfg = config or DetectionConfig()
+        self.prior = prior if isinstance(prior, PriorBoxes) else PriorBoxes(**prior)
+        self.image_hw = (int(image_hw[0]), int(image_hw[1]))
+        self.frame_hw = (int(frame_hw[0]), int(frame_hw[1]))
+        self.C = int(num_classes)
+        self.Cf = int(fpn_channels)
+        self.B = int(batch)
+        self.ctx = rt.Context.get(device)
+        self.lib = self.ctx.lib
+        self.L = int(self.cfg.max_k) + 1
+        self.K = int(self.cfg.nms_max_output_size)
+        self.prior_c = self.prior.to_c(self.cfg.padding)
+        self.N = int(self.lib.mlp_prior_count(ctypes.byref(self.prior_c), *self.image_hw))
+        if self.N < 0:
+            rt.check(self.N)
+        groups = self.prior.grouped()
+        if self.L > len(groups):
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "max_k + 1 exceeds the number of pyramid levels")
+        same = self.cfg.padding == "same"
+        H, W = self.image_hw
+        self.fmap_hw = [((H + s - 1) // s if same else H // s, (W + s - 1) // s if same else W // s)
+                        for s, _ in groups[:self.L]]
+        self.params = rt.DetectionParamsC(
+            float(self.cfg.min_confidence), float(self.cfg.nms_iou_threshold),
+            float(self.cfg.post_iou_threshold), self.K, 1 if self.cfg.strict_batch else 0)
+        self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        c, B, K, L = self.ctx, self.B, self.K, self.L
+        ch, cw = self.cfg.crop_size
+        mh, mw = self.cfg.mask_size
+        f32, i32 = torch.float32, torch.int32
+        self.det = c.empty((B, K, 6), f32)
+        self.keep = c.empty((B, K, 2), i32)
+        self.counts = c.empty((B,), i32)
+        self.m_dev = c.empty((1,), i32)
+        self.dist = c.empty((B, K, 7), f32)
+        self.level_counts = c.empty((L, B), i32)
+        self.level_m = c.empty((L + 1,), i32)
+        self.crops = [c.empty((B * K * ch * cw * self.Cf,), f32) for _ in range(L)]
+        self.roi_boxes = c.empty((B * L * K * 6,), f32)
+        self.trim_counts = c.empty((B,), i32)
+        self.trim_m = c.empty((1,), i32)
+        self.trim_boxes = c.empty((B * K * 6,), f32)
+        self.trim_masks = c.empty((B * K * mh * mw,), f32)
+        self.det_i32 = c.empty((B * K * 6,), i32)
+        self.masks_i32 = c.empty((B * K * mh * mw,), i32)
+        PH, PW = self.frame_hw
+        u8 = self.cfg.paste_output == "uint8"
+        self.pasted = c.empty((B * K * PH * PW,), torch.uint8 if u8 else f32)
+        self._crop_ptrs = (ctypes.c_void_p * L)(*[c.view(t).value for t in self.crops])
+        self._fh = (ctypes.c_int32 * L)(*[h for h, _ in self.fmap_hw])
+        self._fw = (ctypes.c_int32 * L)(*[w for _, w in self.fmap_hw])
+
+    def device_bytes(self):
+        ts = [self.det, self.keep, self.dist, self.roi_boxes, self.trim_boxes, self.trim_masks,
+              self.det_i32, self.masks_i32, self.pasted] + self.crops
+        return sum(t.numel() * t.element_size() for t in ts) + self.ctx.scratch_bytes()
+
+    # --------------------------------------------------------------- first half
+    def detect_and_align(self, loc_pred, cls_pred, fmaps):
+        """loc_pred [B,N,4], cls_pred [B,N,C], fmaps: L tensors [B,Hf,Wf,Cf] (NHWC), all f32
+        CUDA.  Enqueues a2-a10; returns AlignedRois (device tensors, no host sync)."""
+        c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
+        st = c.stream()
+        if tuple(loc_pred.shape) != (B, self.N, 4) or tuple(cls_pred.shape) != (B, self.N, self.C):
+            raise rt.InvalidArgumentError(
+                rt.MLP_EINVAL, f"expected loc {(B, self.N, 4)} / cls {(B, self.N, self.C)}, got "
+                f"{tuple(loc_pred.shape)} / {tuple(cls_pred.shape)}")
+        if len(fmaps) < L:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"need {L} FPN maps, got {len(fmaps)}")
+        for f, (h, w) in zip(fmaps[:L], self.fmap_hw):
+            if tuple(f.shape) != (B, h, w, self.Cf):
+                raise rt.InvalidArgumentError(
+                    rt.MLP_EINVAL, f"FPN map {tuple(f.shape)} != {(B, h, w, self.Cf)}")
+        rt.check(lib.mlp_detect_from_heads(
+            c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
+            c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
+            ctypes.byref(self.params), c.view(self.det), c.view(self.keep), c.view(self.counts),
+            c.view(self.m_dev), st))
+        rt.check(lib.mlp_mask_distribute(c.handle, c.view(self.det), B * K, int(self.cfg.max_k),
+                                         float(self.cfg.base_size), c.view(self.dist), st))
+        rt.check(lib.mlp_roi_align_plan(c.handle, c.view(self.dist), B, K, K, c.view(self.m_dev), L,
+                                        c.view(self.level_counts), c.view(self.level_m), st))
+        fmap_ptrs = (ctypes.c_void_p * L)(*[c.view(f, torch.float32).value for f in fmaps[:L]])
+        ch, cw = self.cfg.crop_size
+        rt.check(lib.mlp_roi_align_run(
+            c.handle, fmap_ptrs, self._fh, self._fw, L, self.Cf, c.view(self.dist), B, K, K,
+            c.view(self.m_dev), float(self.image_hw[0]), float(self.image_hw[1]), int(ch), int(cw),
+            c.view(self.level_counts), c.view(self.level_m), self._crop_ptrs, c.view(self.roi_boxes),
+            st))
+        return AlignedRois(self.det, self.keep, self.counts, self.m_dev, self.dist, self.level_counts,
+                           self.level_m, self.crops, self.roi_boxes)
+
+    def roi_views(self, rois):
+        """Reference-shaped views ([B,Mf,ch,cw,Cf] per level, [B,R,6]) — one small D2H."""
+        mf, R = rois.shapes()
+        ch, cw = self.cfg.crop_size
+        crops = [t[:self.B * m * ch * cw * self.Cf].view(self.B, m, ch, cw, self.Cf)
+                 for t, m in zip(rois.crops, mf)]
+        boxes = rois.roi_boxes[:self.B * R * 6].view(self.B, R, 6)
+        return crops, boxes
+
+    # -------------------------------------------------------------- second half
+    def trim_and_paste(self, rois, roi_masks):
+        """roi_masks: mask-head output, f32, dense [B,R,mh,mw,C] (R = rois.level_m[-1]; a flat
+        buffer whose prefix has that layout is fine).  Enqueues a11-a14.  Returns
+        (det_i32 flat, pasted flat, m_dev): valid prefixes [B,M,6] and [B,M,PH,PW]."""
+        c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
+        st = c.stream()
+        mh, mw = self.cfg.mask_size
+        r_cap = L * K
+        r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
+        masks_ptr = c.view(roi_masks, torch.float32)
+        rt.check(lib.mlp_trim_plan(c.handle, c.view(rois.roi_boxes), B, r_cap, r_dev,
+                                   c.view(self.trim_counts), c.view(self.trim_m), st))
+        rt.check(lib.mlp_trim_run(c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw,
+                                  self.C, c.view(self.trim_m), c.view(self.trim_boxes),
+                                  c.view(self.trim_masks), st))
+        ratio = (torch.tensor([float(self.frame_hw[0]), float(self.frame_hw[1])], dtype=torch.float32)
+                 / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
+        rt.check(lib.mlp_upsample_output(
+            c.handle, c.view(self.trim_boxes), B * K, float(ratio[0]), float(ratio[1]),
+            c.view(self.det_i32), c.view(self.trim_masks), B * K * mh * mw, c.view(self.masks_i32), st))
+        mode = rt.MLP_PASTE_U8 if self.cfg.paste_output == "uint8" else rt.MLP_PASTE_F32
+        rt.check(lib.mlp_crop_and_pad_mask(
+            c.handle, c.view(self.det_i32), c.view(self.masks_i32), B, K, 0, c.view(self.trim_m), mh, mw,
+            self.frame_hw[0], self.frame_hw[1], mode, c.view(self.pasted), st))
+        return self.det_i32, self.pasted, self.trim_m
+
+    def result_views(self):
+        """Reference-shaped views of the last trim_and_paste (one D2H of M)."""
+        M = int(self.trim_m.item())
+        PH, PW = self.frame_hw
+        det = self.det_i32[:self.B * M * 6].view(self.B, M, 6)
+        masks = self.pasted[:self.B * M * PH * PW].view(self.B, M, PH, PW)
+        return det, masks

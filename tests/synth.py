@@ -1,0 +1,73 @@
+"""Seeded synthetic inputs of SURVEY.md §8(d), shared by the tests and bench.py (NumPy, CPU).
+
+Everything is float32 NHWC.  `head_tensors` follows the classification-head statistics of
+the reference (bias init -log(99), /root/reference/engine/layers/detection.py:200): scores
+are sigmoid(N(mu,1)); mu=-5.8 is the "realistic" setting (~0.21% of scores pass 0.05),
+mu=-5.0 the "stress" one (~2%).
+"""
+import numpy as np
+
+F32 = np.float32
+
+DEFAULT_STRIDES = (8, 16, 32, 64, 128)
+DEFAULT_SCALES = (2 ** 0, 2 ** (1 / 3), 2 ** (2 / 3))
+DEFAULT_RATIOS = (1 / 3, 1 / 2, 1, 2, 3)
+A9_RATIOS = (1 / 2, 1, 2)
+
+
+def prior_config(strides=DEFAULT_STRIDES, scales=DEFAULT_SCALES, ratios=DEFAULT_RATIOS):
+    strides = [int(s) for s in strides]
+    return dict(strides=strides, sizes=[4 * s for s in strides], pr_scales=list(scales),
+                pr_ratios=list(ratios))
+
+
+def num_anchors(prior_cfg, H, W, padding="same"):
+    A = len(prior_cfg["pr_scales"]) * len(prior_cfg["pr_ratios"])
+    n = 0
+    for s in prior_cfg["strides"]:
+        hf = -(-H // s) if padding == "same" else H // s
+        wf = -(-W // s) if padding == "same" else W // s
+        n += hf * wf * A
+    return n
+
+
+def head_tensors(B, N, C, mu=-5.8, seed=0):
+    """loc_pred [B,N,4] ~ N(0,0.5^2) clipped to +-2; cls_pred [B,N,C] = sigmoid(N(mu,1))."""
+    rng = np.random.default_rng(seed)
+    loc = np.clip(rng.standard_normal((B, N, 4), dtype=F32) * F32(0.5), -2, 2).astype(F32)
+    z = rng.standard_normal((B, N, C), dtype=F32) + F32(mu)
+    cls = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(F32)
+    return loc, cls
+
+
+def fpn_maps(B, H, W, Cf, strides=(8, 16, 32), seed=1, padding="same"):
+    rng = np.random.default_rng(seed)
+    out = []
+    for s in strides:
+        hf = -(-H // s) if padding == "same" else H // s
+        wf = -(-W // s) if padding == "same" else W // s
+        out.append(rng.standard_normal((B, hf, wf, Cf), dtype=F32))
+    return out
+
+
+def mask_probs(B, R, C, mask_hw=(28, 28), seed=2):
+    """Stand-in for the MaskSubNet output: U(0,1) [B,R,mh,mw,C]."""
+    rng = np.random.default_rng(seed)
+    return rng.random((B, R, mask_hw[0], mask_hw[1], C), dtype=F32)
+
+
+def detections(B, M, C, H, W, seed=3, lo=16.0, hi=400.0, pad_tail=0):
+    """Exactly M synthetic detections per image (cfg-4): w,h ~ logU(lo,hi), centres uniform
+    in-frame, classes uniform, scores U(0.5,1) sorted descending like NMS output; the last
+    `pad_tail` rows of every image are -1 padding."""
+    rng = np.random.default_rng(seed)
+    w = np.exp(rng.uniform(np.log(lo), np.log(hi), (B, M))).astype(F32)
+    h = np.exp(rng.uniform(np.log(lo), np.log(hi), (B, M))).astype(F32)
+    cx = rng.uniform(0, W, (B, M)).astype(F32)
+    cy = rng.uniform(0, H, (B, M)).astype(F32)
+    cls = rng.integers(0, C, (B, M)).astype(F32)
+    score = -np.sort(-rng.uniform(0.5, 1.0, (B, M)), axis=1)
+    det = np.stack([cx, cy, w, h, cls, score.astype(F32)], axis=-1).astype(F32)
+    if pad_tail:
+        det[:, M - pad_tail:] = -1
+    return det
