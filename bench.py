@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the MaskLab post-backbone path (decode -> NMS -> RoIAlign -> trim ->
+mask paste) on 1..8 B200, with the roofline of the dominant kernel and a CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|stress|cfg5]
+
+One "step" = one pass of the whole hot path over one synthetic batch of 32 frames per GPU
+(BASELINE.json configs[1]: 1024x512 frames, N=163,680 anchors, C=5, FPN Cf=128).  Frames are
+sharded by image: every rank runs its own batch on its own stream (weak scaling), the only
+collective is one NCCL all_gather of the fixed-capacity detection records at the end of the
+timed region.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / SURVEY §8 cfg-2: ResNeXt default ModelConfiguration shapes
+    # (engine/config.py:53,60-64,83-86,150) with the north-star score threshold 0.05.
+    "cfg2": dict(B=32, H=512, W=1024, PH=512, PW=1024, C=5, Cf=128, ratios="default", mu=-5.8,
+                 min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.6,
+                 nms_max_output_size=100, max_k=2, base_size=36),
+    # configs[2]+[3]: NMS/top-k stress + 1000 RoIs/image mask paste
+    "stress": dict(B=32, H=512, W=1024, PH=512, PW=1024, C=6, Cf=128, ratios="default", mu=-5.0,
+                   min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+                   nms_max_output_size=1000, max_k=2, base_size=64),
+    # configs[4]: 1080p frames, model at 540x960, paste at 1080x1920
+    "cfg5": dict(B=32, H=540, W=960, PH=1080, PW=1920, C=6, Cf=128, ratios="default", mu=-5.8,
+                 min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+                 nms_max_output_size=100, max_k=2, base_size=36),
+    # small variant for quick checks
+    "tiny": dict(B=4, H=128, W=256, PH=128, PW=256, C=5, Cf=32, ratios="default", mu=-5.0,
+                 min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.6,
+                 nms_max_output_size=50, max_k=2, base_size=36),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def kwargs_of(wl):
+    return {k: wl[k] for k in ("min_confidence", "nms_iou_threshold", "post_iou_threshold",
+                               "nms_max_output_size", "max_k", "base_size")}
+
+
+def make_inputs(wl, B, seed):
+    import synth
+    cfgp = synth.prior_config()
+    N = synth.num_anchors(cfgp, wl["H"], wl["W"])
+    loc, cls = synth.head_tensors(B, N, wl["C"], mu=wl["mu"], seed=seed)
+    fmaps = synth.fpn_maps(B, wl["H"], wl["W"], wl["Cf"], seed=seed + 1000)
+    return cfgp, N, loc, cls, fmaps
+
+
+# ------------------------------------------------------------------ clocks -----
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:          # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------- CPU baseline --
+def _cpu_one_frame(args):
+    """One frame through the oracle's whole path (the restated reference CPU path)."""
+    wl, seed = args
+    import synth
+    from oracle import masklab_oracle as mo
+    cfgp, N, loc, cls, fmaps = make_inputs(wl, 1, seed)
+    C = wl["C"]
+    t0 = time.perf_counter()
+    mo.full_path(loc, cls, fmaps, lambda f, b: synth.mask_probs(1, b.shape[1], C, seed=seed + 2),
+                 cfgp, (wl["H"], wl["W"]), (wl["PH"], wl["PW"]), **kwargs_of(wl))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, frames, procs):
+    """frames/s of the NumPy oracle ("port": restated CPU path, not TensorFlow) over `frames`
+    frames of the same workload, `procs` worker processes (one frame each at a time)."""
+    jobs = [(wl, 7000 + i) for i in range(frames)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        per = [_cpu_one_frame(j) for j in jobs]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            per = pool.map(_cpu_one_frame, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return frames / wall, wall, float(np.mean(per))
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.x is not
+    installable here, so this times the oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    frames_per_step = procs
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(wl, procs, procs)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(steps):
+        cpu_baseline(wl, frames_per_step, procs)
+        total += frames_per_step
+    wall = time.perf_counter() - t0
+    fps = total / wall
+    sample = f"{steps} step(s) x {frames_per_step} frames of workload {args.workload}, {procs} processes"
+    line = {
+        "impl": "reference", "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the reference path (NumPy, restated TF kernels); TensorFlow is absent",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl):
+    return {"workload": f"{args.workload}: B={wl['B']}/GPU {wl['W']}x{wl['H']} frames, C={wl['C']}, "
+                        f"Cf={wl['Cf']}, max_out={wl['nms_max_output_size']}, paste {wl['PW']}x{wl['PH']} uint8",
+            "batch_per_gpu": wl["B"], "parallelism": f"image-sharded x{args.gpus}",
+            "l2_policy": "inputs (>=365 MB) and outputs (>=1.6 GB) per step exceed the 126 MB L2",
+            "score_mu": wl["mu"]}
+
+
+# -------------------------------------------------------------------- ours -----
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import synth
+    import masklab_b200 as ml
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, C = wl["B"], wl["C"]
+    H, W, PH, PW = wl["H"], wl["W"], wl["PH"], wl["PW"]
+    cfgp, N, loc, cls, fmaps = make_inputs(wl, B, seed=100 + rank)
+    cfg = ml.DetectionConfig(paste_output="uint8", **kwargs_of(wl))
+    pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local)
+    ctx = pipe.ctx
+    K = pipe.K
+
+    # host (pinned) copies for the end-to-end leg, device copies for the kernel-only leg
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_loc, h_cls, h_fmaps = pin(loc), pin(cls), [pin(f) for f in fmaps]
+    d_loc, d_cls = h_loc.cuda(non_blocking=True), h_cls.cuda(non_blocking=True)
+    d_fmaps = [f.cuda(non_blocking=True) for f in h_fmaps]
+
+    # first pass: discover R (rows the mask head would produce) and make its synthetic output
+    rois = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+    mf, R = rois.shapes()
+    h_masks = pin(synth.mask_probs(B, R, C, seed=300 + rank))
+    d_masks = h_masks.cuda()
+    pipe.trim_and_paste(rois, d_masks)
+    M = int(pipe.trim_m.item())
+    counts = rois.counts.cpu().numpy()
+    torch.cuda.synchronize()
+
+    def step():
+        r = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+        pipe.trim_and_paste(r, d_masks)
+
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty_like(pipe.det) for _ in range(world)]
+        gathered_counts = [torch.empty_like(pipe.counts) for _ in range(world)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count()
+    ctx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        if world > 1:           # the one collective of the path: gather detections at the end
+            dist.all_gather(gathered, pipe.det)
+            dist.all_gather(gathered_counts, pipe.counts)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    stages = ctx.profile_read()
+    ctx.profile(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * B * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (mask paste): algorithmic bytes = B*M*PH*PW uint8
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    paste_ms, paste_n = stages.get("paste", (0.0, 0))
+    paste_bytes = B * M * PH * PW
+    achieved = (paste_bytes / (paste_ms / paste_n * 1e-3) / 1e9) if paste_n else None
+    step_bytes = algorithmic_bytes(wl, N, M)
+    roofline = {"bound": "hbm", "kernel": "paste_kernel<uint8> (CropAndPadMask + >0.5)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_kind": peak_kind, "bytes_per_launch": paste_bytes,
+                "avg_launch_ms": (paste_ms / paste_n) if paste_n else None,
+                "whole_step": {"algorithmic_bytes": step_bytes,
+                               "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()}}
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            procs = 1
+            frames = args.cpu_frames or 24
+            v, wall, per = cpu_baseline(wl, frames, procs)
+            cpu = {"value": v, "unit": "frames/s", "cores": procs, "kind": "port",
+                   "sample": f"{frames} frames of workload {args.workload} through the NumPy oracle "
+                             f"(whole path incl. f32 paste), {wall:.1f} s wall"}
+        line = {
+            "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "detections": {"M": M, "R": R, "Mf": mf, "kept_per_image_mean": float(counts.mean())},
+            "device_bytes": pipe.device_bytes(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def algorithmic_bytes(wl, N, M):
+    """read each required input once, write each required output once."""
+    B, C, Cf = wl["B"], wl["C"], wl["Cf"]
+    decode = B * N * 16 + B * N * C * 4
+    det = B * M * 24
+    fm = sum(B * (-(-wl["H"] // s)) * (-(-wl["W"] // s)) * Cf * 4 for s in (8, 16, 32)[:wl["max_k"] + 1])
+    crops = B * M * 14 * 14 * Cf * 4
+    trim = B * M * 28 * 28 * 4
+    paste = B * M * wl["PH"] * wl["PW"]
+    return decode + det + fm + crops + trim + paste
+
+
+def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier):
+    """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
+    from pinned host memory, runs the path and reads detections + binary masks back."""
+    import torch
+    import torch.distributed as dist
+    B, PH, PW = wl["B"], wl["PH"], wl["PW"]
+    d_loc = torch.empty_like(h_loc, device="cuda")
+    d_cls = torch.empty_like(h_cls, device="cuda")
+    d_fmaps = [torch.empty_like(f, device="cuda") for f in h_fmaps]
+    d_masks = torch.empty_like(h_masks, device="cuda")
+    out_det = torch.empty((B * M * 6,), dtype=torch.int32).pin_memory()
+    out_masks = torch.empty((B * M * PH * PW,), dtype=torch.uint8).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps)
+    d2h = out_det.numel() * 4 + out_masks.numel()
+
+    def step():
+        d_loc.copy_(h_loc, non_blocking=True)
+        d_cls.copy_(h_cls, non_blocking=True)
+        for d, h in zip(d_fmaps, h_fmaps):
+            d.copy_(h, non_blocking=True)
+        d_masks.copy_(h_masks, non_blocking=True)
+        r = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+        det_i32, pasted, _ = pipe.trim_and_paste(r, d_masks)
+        out_det.copy_(det_i32[:out_det.numel()], non_blocking=True)
+        out_masks.copy_(pasted[:out_masks.numel()], non_blocking=True)
+
+    step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.e2e_steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * B * args.e2e_steps / (ms * 1e-3), "unit": "frames/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+            "ms_per_step": ms / args.e2e_steps,
+            "api": "PostProcessPipeline.detect_and_align + trim_and_paste, pinned host in/out"}
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,16 @@ int64_t     mlp_ctx_scratch_bytes(const mlp_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench `gpu_launches`). */
 int64_t     mlp_ctx_launch_count(const mlp_ctx* ctx);
 
+/* ---- per-stage timing (bench.py roofline) -----------------------------------
+ * When enabled, every stage function brackets its kernels with a pair of CUDA events on
+ * the launching stream (no extra synchronisation).  mlp_ctx_profile_read [syncs] sums
+ * the elapsed milliseconds and the number of bracketed calls per stage.               */
+#define MLP_NUM_STAGES 16
+const char* mlp_stage_name(int stage);
+int mlp_ctx_profile_enable(mlp_ctx* ctx, int enable);
+int mlp_ctx_profile_read(mlp_ctx* ctx, double* ms_out /*[MLP_NUM_STAGES]*/,
+                         int64_t* count_out /*[MLP_NUM_STAGES]*/);
+
 /* ---- DLPack handoff ---------------------------------------------------------
  * Python passes PyCapsule("dltensor") -> DLManagedTensor*; this validates it and
  * extracts the plain pointer/shape the stage functions take.  Layout of

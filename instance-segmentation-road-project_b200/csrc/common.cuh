@@ -23,6 +23,34 @@ struct mlp_ctx {
     int64_t arena_bytes[MLP_NUM_ARENAS];
     // small device block for counters / dims (always allocated)
     int32_t* ctr;          // [MLP_CTR_WORDS]
+    // optional per-stage CUDA-event timing (bench.py roofline): pairs recorded on the
+    // launching stream around each stage's kernels
+    bool prof_on;
+    int prof_used;
+    cudaEvent_t* prof_ev;  // [2 * MLP_PROF_CAP]
+    int* prof_stage;       // [MLP_PROF_CAP]
+};
+
+#define MLP_PROF_CAP 16384
+enum {
+    MLP_ST_THRESHOLD = 0, MLP_ST_NMS_CLASS, MLP_ST_NMS_CROSS, MLP_ST_DISTRIBUTE, MLP_ST_ROI_PLAN,
+    MLP_ST_ROI_ALIGN, MLP_ST_TRIM, MLP_ST_UPSAMPLE, MLP_ST_PASTE_THR, MLP_ST_PASTE, MLP_ST_ELEMENTWISE,
+    MLP_ST_MOLD, MLP_ST_TAIL_FUSED
+};
+
+// RAII: records a start event now and a stop event when it goes out of scope.
+struct ProfScope {
+    mlp_ctx* c; cudaStream_t st; int slot;
+    ProfScope(mlp_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), st(stream), slot(-1) {
+        if (c->prof_on && c->prof_used < MLP_PROF_CAP) {
+            slot = c->prof_used++;
+            c->prof_stage[slot] = stage;
+            cudaEventRecord(c->prof_ev[2 * slot], st);
+        }
+    }
+    ~ProfScope() {
+        if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], st);
+    }
 };
 
 #define MLP_CTR_WORDS 1024

@@ -36,6 +36,10 @@ extern "C" int mlp_ctx_create(int device, mlp_ctx** out) {
     c->launches = 0;
     for (int i = 0; i < MLP_NUM_ARENAS; ++i) { c->arena[i] = nullptr; c->arena_bytes[i] = 0; }
     c->ctr = nullptr;
+    c->prof_on = false;
+    c->prof_used = 0;
+    c->prof_ev = nullptr;
+    c->prof_stage = nullptr;
     cudaError_t e = cudaMalloc(&c->ctr, MLP_CTR_WORDS * sizeof(int32_t));
     if (e != cudaSuccess) {
         mlp_set_error("mlp_ctx_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -53,6 +57,11 @@ extern "C" void mlp_ctx_destroy(mlp_ctx* ctx) {
     for (int i = 0; i < MLP_NUM_ARENAS; ++i)
         if (ctx->arena[i]) cudaFree(ctx->arena[i]);
     if (ctx->ctr) cudaFree(ctx->ctr);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * MLP_PROF_CAP; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        delete[] ctx->prof_ev;
+        delete[] ctx->prof_stage;
+    }
     delete ctx;
 }
 
@@ -65,6 +74,42 @@ extern "C" int64_t mlp_ctx_scratch_bytes(const mlp_ctx* ctx) {
     return t;
 }
 extern "C" int64_t mlp_ctx_launch_count(const mlp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static const char* kStageNames[MLP_NUM_STAGES] = {
+    "threshold_compact", "nms_per_class", "nms_cross_class", "mask_distribute", "roi_plan",
+    "roi_align", "trim", "upsample", "paste_threshold", "paste", "elementwise", "mold_batch",
+    "tail_fused", "", "", ""};
+
+extern "C" const char* mlp_stage_name(int stage) {
+    return (stage >= 0 && stage < MLP_NUM_STAGES) ? kStageNames[stage] : "";
+}
+
+extern "C" int mlp_ctx_profile_enable(mlp_ctx* ctx, int enable) {
+    MLP_CHECK_ARG(ctx != nullptr, "mlp_ctx_profile_enable: NULL ctx");
+    DeviceGuard g(ctx->device);
+    if (enable && !ctx->prof_ev) {
+        ctx->prof_ev = new cudaEvent_t[2 * MLP_PROF_CAP];
+        ctx->prof_stage = new int[MLP_PROF_CAP];
+        for (int i = 0; i < 2 * MLP_PROF_CAP; ++i) MLP_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    if (enable) ctx->prof_used = 0;
+    ctx->prof_on = enable != 0;
+    return MLP_OK;
+}
+
+extern "C" int mlp_ctx_profile_read(mlp_ctx* ctx, double* ms_out, int64_t* count_out) {
+    MLP_CHECK_ARG(ctx && ms_out && count_out, "mlp_ctx_profile_read: NULL argument");
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < MLP_NUM_STAGES; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+    MLP_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        float ms = 0.f;
+        MLP_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ms_out[ctx->prof_stage[i]] += ms;
+        count_out[ctx->prof_stage[i]] += 1;
+    }
+    return MLP_OK;
+}
 
 // Grow-only.  Regrowth frees the old arena after a device synchronise, so it must
 // not happen while earlier work of this ctx is still using it; callers size the

@@ -593,6 +593,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
 
     // K1: stream cls_pred once
     {
+        ProfScope prof(ctx, MLP_ST_THRESHOLD, stream);
         const int64_t total = (int64_t)B * N * C;
         int64_t blocks = (total / 4 + 255) / 256;
         int64_t capb = (int64_t)ctx->sm_count * 8;
@@ -605,6 +606,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     // K2: per (image,class) NMS.  512-thread CTAs, <= 72 KB smem -> 3 CTAs per SM, so all
     // B*C groups (160-192 at batch 32) are resident in a single wave on 148 SMs.
     {
+        ProfScope prof(ctx, MLP_ST_NMS_CLASS, stream);
         const int sort_cap = pick_sort_cap(4096, max_out, 72 * 1024);
         const size_t smem = nms_smem_bytes(sort_cap, max_out);
         if (prior) {
@@ -624,6 +626,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     }
     // K3: cross-class NMS per image; sort buffer sized for C*max_out survivors when it fits.
     {
+        ProfScope prof(ctx, MLP_ST_NMS_CROSS, stream);
         const int sort_cap = pick_sort_cap(C * max_out, max_out, 200 * 1024);
         const size_t smem = nms_smem_bytes(sort_cap, max_out);
         MLP_CUDA(cudaFuncSetAttribute(nms_cross_class_kernel,

@@ -160,6 +160,7 @@ extern "C" int mlp_prior_layer(mlp_ctx* ctx, const mlp_prior_config* prior, int 
     int rc = mlp_build_prior_dev(prior, height, width, &P);
     if (rc) return rc;
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_ELEMENTWISE, (cudaStream_t)stream);
     int64_t total = (int64_t)batch * P.total;
     prior_layer_kernel<<<grid_for(ctx, total), kThreads, 0, (cudaStream_t)stream>>>(
         P, batch, reinterpret_cast<int4*>(out_dev));
@@ -176,6 +177,7 @@ extern "C" int mlp_restore_boxes(mlp_ctx* ctx, const float* loc_dev, const void*
                   "mlp_restore_boxes: pointers must be 16-byte aligned");
     if (rows == 0) return MLP_OK;
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_ELEMENTWISE, (cudaStream_t)stream);
     int grid = grid_for(ctx, rows);
     if (prior_is_f32)
         restore_boxes_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
@@ -200,6 +202,7 @@ extern "C" int mlp_restore_boxes_from_prior(mlp_ctx* ctx, const mlp_prior_config
     int rc = mlp_build_prior_dev(prior, height, width, &P);
     if (rc) return rc;
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_ELEMENTWISE, (cudaStream_t)stream);
     int64_t total = (int64_t)batch * P.total;
     restore_from_prior_kernel<<<grid_for(ctx, total), kThreads, 0, (cudaStream_t)stream>>>(
         P, reinterpret_cast<const float4*>(loc_dev), batch, reinterpret_cast<float4*>(out_dev));
@@ -217,6 +220,7 @@ extern "C" int mlp_normalize_boxes(mlp_ctx* ctx, const float* boxes_dev, int64_t
                   "mlp_normalize_boxes: pointers must be 16-byte aligned");
     if (rows == 0) return MLP_OK;
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_ELEMENTWISE, (cudaStream_t)stream);
     normalize_boxes_kernel<<<grid_for(ctx, rows), kThreads, 0, (cudaStream_t)stream>>>(
         boxes_dev, rows, row_stride, image_h, image_w, reinterpret_cast<float4*>(out_dev));
     MLP_LAUNCH_CHECK(ctx);
@@ -230,6 +234,7 @@ extern "C" int mlp_mask_distribute(mlp_ctx* ctx, const float* det_dev, int64_t r
                   max_k);
     if (rows == 0) return MLP_OK;
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_DISTRIBUTE, (cudaStream_t)stream);
     float base_eps = (float)((double)base_size + 1e-7);      // python: base_size + K.epsilon()
     mask_distribute_kernel<<<grid_for(ctx, rows), kThreads, 0, (cudaStream_t)stream>>>(
         det_dev, rows, base_eps, (float)max_k, out_dev);
@@ -243,6 +248,7 @@ extern "C" int mlp_upsample_output(mlp_ctx* ctx, const float* det_dev, int64_t r
     MLP_CHECK_ARG(ctx, "mlp_upsample_output: NULL ctx");
     MLP_CHECK_ARG(rows >= 0 && mask_elems >= 0, "mlp_upsample_output: negative size");
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_UPSAMPLE, (cudaStream_t)stream);
     if (rows > 0) {
         MLP_CHECK_ARG(det_dev && det_i32_dev, "mlp_upsample_output: NULL det pointers");
         upsample_boxes_kernel<<<grid_for(ctx, rows), kThreads, 0, (cudaStream_t)stream>>>(

@@ -72,6 +72,7 @@ extern "C" int mlp_mold_batch_plan(mlp_ctx* ctx, const int32_t* batch_idx_dev, i
     int rc = mlp_ensure_scratch(ctx, MLP_ARENA_MOLD, (int64_t)batch * (rows > 0 ? rows : 1) * 4);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_MOLD, st);
     MLP_CUDA(cudaMemsetAsync(m_dev, 0, 4, st));
     mold_plan_kernel<<<batch, 32, 0, st>>>(batch_idx_dev, rows,
                                           static_cast<int32_t*>(ctx->arena[MLP_ARENA_MOLD]), counts_dev,
@@ -92,6 +93,7 @@ extern "C" int mlp_mold_batch_run(mlp_ctx* ctx, const void* x_dev, const int32_t
                       ctx->arena_bytes[MLP_ARENA_MOLD] >= (int64_t)batch * (rows > 0 ? rows : 1) * 4,
                   "mlp_mold_batch_run: call mlp_mold_batch_plan with the same shapes first");
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_MOLD, (cudaStream_t)stream);
     const float m1 = -1.0f;
     uint32_t pad = pad_is_float ? *reinterpret_cast<const uint32_t*>(&m1) : 0xffffffffu;
     mold_run_kernel<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(

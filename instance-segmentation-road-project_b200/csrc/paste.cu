@@ -218,8 +218,12 @@ extern "C" int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev,
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* thr_dev = ctx->ctr;        // ctr[0]: paste row-filter threshold
-    paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
-    MLP_LAUNCH_CHECK(ctx);
+    {
+        ProfScope prof(ctx, MLP_ST_PASTE_THR, st);
+        paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
+        MLP_LAUNCH_CHECK(ctx);
+    }
+    ProfScope prof(ctx, MLP_ST_PASTE, st);
     const bool u8 = out_mode == MLP_PASTE_U8;
     const int vec = u8 ? 16 : 4;
     // persistent grid, 8 CTAs of 256 threads per SM (write-only: occupancy hides store latency)

@@ -277,6 +277,7 @@ extern "C" int mlp_roi_align_plan(mlp_ctx* ctx, const float* dist_dev, int batch
     int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)num_levels * batch * m_rows * 4);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_ROI_PLAN, st);
     MLP_CUDA(cudaMemsetAsync(level_m_dev, 0, (size_t)(num_levels + 1) * 4, st));
     roi_plan_kernel<<<batch, 32 * MLP_MAX_LEVELS, 0, st>>>(
         dist_dev, batch, m_rows, m_stride, m_dev, num_levels,
@@ -319,6 +320,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
         lv.fw[f] = fw[f];
     }
     DeviceGuard g(ctx->device);
+    ProfScope prof(ctx, MLP_ST_ROI_ALIGN, (cudaStream_t)stream);
     // persistent grid: 4 CTAs of 256 threads per SM
     const int grid = ctx->sm_count * 4;
     roi_align_kernel<<<grid, kRoiThreads, 0, (cudaStream_t)stream>>>(
@@ -336,6 +338,7 @@ extern "C" int mlp_trim_plan(mlp_ctx* ctx, const float* roi_boxes_dev, int batch
     MLP_CHECK_ARG(batch >= 1 && r_rows >= 1, "mlp_trim_plan: bad shape B=%d R=%d", batch, r_rows);
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_TRIM, st);
     MLP_CUDA(cudaMemsetAsync(m_dev, 0, 4, st));
     trim_plan_kernel<<<batch, 256, 0, st>>>(roi_boxes_dev, r_rows, r_dev, counts_dev, m_dev);
     MLP_LAUNCH_CHECK(ctx);
@@ -355,6 +358,7 @@ extern "C" int mlp_trim_run(mlp_ctx* ctx, const float* roi_boxes_dev, const floa
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* trim_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_TRIM]);
+    ProfScope prof(ctx, MLP_ST_TRIM, st);
     trim_index_kernel<<<batch, 32, 0, st>>>(roi_boxes_dev, r_rows, r_dev, m_dev, trim_src, r_rows,
                                            out_boxes_dev);
     MLP_LAUNCH_CHECK(ctx);

@@ -65,6 +65,9 @@ SIGNATURES = {
     "mlp_ctx_sm_count": (_I, [_P]),
     "mlp_ctx_scratch_bytes": (_L, [_P]),
     "mlp_ctx_launch_count": (_L, [_P]),
+    "mlp_stage_name": (ctypes.c_char_p, [_I]),
+    "mlp_ctx_profile_enable": (_I, [_P, _I]),
+    "mlp_ctx_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "mlp_dlpack_view": (_I, [_P, _P, _I, ctypes.POINTER(TensorViewC)]),
     "mlp_prior_count": (_L, [ctypes.POINTER(PriorConfigC), _I, _I]),
     "mlp_prior_layer": (_I, [_P, ctypes.POINTER(PriorConfigC), _I, _I, _I, _P, _P]),
@@ -186,6 +189,21 @@ class Context:
 
     def sm_count(self):
         return int(self.lib.mlp_ctx_sm_count(self.handle))
+
+    def profile(self, enable=True):
+        check(self.lib.mlp_ctx_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{stage name: (total ms, bracketed calls)} since profile(True); synchronises."""
+        ms = (ctypes.c_double * 16)()
+        cnt = (ctypes.c_int64 * 16)()
+        check(self.lib.mlp_ctx_profile_read(self.handle, ms, cnt))
+        out = {}
+        for i in range(16):
+            name = self.lib.mlp_stage_name(i).decode()
+            if name and cnt[i]:
+                out[name] = (float(ms[i]), int(cnt[i]))
+        return out
 
     def view(self, tensor, dtype=None):
         """DLPack handoff: validate `tensor` in C and return its device pointer."""
