@@ -18,7 +18,7 @@ namespace {
 
 constexpr int kClassThreads = 512;          // K2: several CTAs per SM (B*C CTAs in one wave)
 constexpr int kCrossThreads = 1024;         // K3: one CTA per image
-constexpr int kChunk = 256;                 // candidates resolved per round
+constexpr int kChunk = 64;                  // candidates resolved per round (one 64-bit mask row each)
 constexpr int kMaskWords = kChunk / 32;
 constexpr uint64_t kKeyPad = ~0ull;
 
@@ -58,52 +58,83 @@ __device__ __forceinline__ float key_score(uint64_t key) {
 }
 
 // ------------------------------------------------------------------ K1 -------
-// cand_keys [G][cap] (G = B*C), cand_count [G].
-__global__ void __launch_bounds__(256)
-threshold_compact_kernel(const float* __restrict__ cls, int64_t total, int N, int C, float thr,
+// cand_keys [G][cap] (G = B*C), cand_count [G].  Every CTA streams one contiguous slice of
+// cls_pred with 4 independent 128-bit loads in flight per thread.  Hits (0.2-2 % of the
+// scores) are parked in a shared-memory queue as (flat index, score) and turned into
+// per-(image,class) appends once per CTA, so the streaming loop carries no global atomics,
+// no 64-bit divisions and almost no divergence.
+constexpr int kK1Threads = 256;
+constexpr int kK1Queue = 2048;
+
+__device__ __forceinline__ void k1_append(uint32_t e, float s, int N, int C, uint64_t* cand_keys,
+                                          int32_t* cand_count, int64_t cap) {
+    const uint32_t bn = e / (uint32_t)C;
+    const int c = (int)(e - bn * (uint32_t)C);
+    const uint32_t b = bn / (uint32_t)N;
+    const uint32_t n = bn - b * (uint32_t)N;
+    const int g = (int)b * C + c;
+    const int pos = atomicAdd(cand_count + g, 1);
+    if (pos < cap) cand_keys[(int64_t)g * cap + pos] = make_key(s, n);
+}
+
+__global__ void __launch_bounds__(kK1Threads)
+threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, int C, float thr,
                          uint64_t* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
                          int64_t cap, int32_t* __restrict__ m_dev) {
+    __shared__ uint2 s_q[kK1Queue];
+    __shared__ int s_qn;
     if (blockIdx.x == 0 && threadIdx.x == 0 && m_dev) *m_dev = 1;
-    const int64_t total4 = total >> 2;
-    const float4* cls4 = reinterpret_cast<const float4*>(cls);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    auto emit = [&](int64_t e, float s) {
-        int64_t bn = e / C;
-        int c = (int)(e - bn * C);
-        int b = (int)(bn / N);
-        int n = (int)(bn - (int64_t)b * N);
-        int g = b * C + c;
-        int pos = atomicAdd(cand_count + g, 1);
-        if (pos < cap) cand_keys[(int64_t)g * cap + pos] = make_key(s, (uint32_t)n);
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    auto hit = [&](uint32_t e, float s) {
+        const int pos = atomicAdd(&s_qn, 1);
+        if (pos < kK1Queue) s_q[pos] = make_uint2(e, __float_as_uint(s));
+        else k1_append(e, s, N, C, cand_keys, cand_count, cap);      // queue full: slow path
     };
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    // 4 independent 128-bit loads in flight per thread
-    for (; i + 3 * stride < total4; i += 4 * stride) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(cls4 + i + u * stride);
+    const uint32_t total4 = total >> 2;
+    const float4* cls4 = reinterpret_cast<const float4*>(cls);
+    const float kNaN = __int_as_float(0x7fc00000);     // NaN >= thr is false for every thr
+    // contiguous slice per CTA, rounded to whole tiles of kK1Threads*4 vectors
+    const uint32_t tile = kK1Threads * 4;
+    const uint32_t tiles = (total4 + tile - 1) / tile;
+    const uint32_t tiles_per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+    uint32_t v0 = blockIdx.x * tiles_per_cta * tile;
+    uint32_t v1 = v0 + tiles_per_cta * tile;
+    if (v1 > total4) v1 = total4;
+    // software pipeline: the next tile's four 128-bit loads are in flight while the current
+    // tile is compared against the threshold
+    float4 cur[4], nxt[4];
+    auto load_tile = [&](float4 (&v)[4], uint32_t base) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            int64_t e = (i + u * stride) << 2;
-            if (v[u].x >= thr) emit(e, v[u].x);
-            if (v[u].y >= thr) emit(e + 1, v[u].y);
-            if (v[u].z >= thr) emit(e + 2, v[u].z);
-            if (v[u].w >= thr) emit(e + 3, v[u].w);
+            const uint32_t i = base + u * kK1Threads + threadIdx.x;
+            v[u] = (i < v1) ? ldg_stream_f4(cls4 + i) : make_float4(kNaN, kNaN, kNaN, kNaN);
+        }
+    };
+    if (v0 < v1) load_tile(cur, v0);
+    for (uint32_t base = v0; base < v1; base += tile) {
+        if (base + tile < v1) load_tile(nxt, base + tile);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e = (base + u * kK1Threads + threadIdx.x) << 2;
+            if (cur[u].x >= thr) hit(e, cur[u].x);
+            if (cur[u].y >= thr) hit(e + 1, cur[u].y);
+            if (cur[u].z >= thr) hit(e + 2, cur[u].z);
+            if (cur[u].w >= thr) hit(e + 3, cur[u].w);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    }
+    if (blockIdx.x == gridDim.x - 1) {             // scalar tail (total not a multiple of 4)
+        for (uint32_t e = (total4 << 2) + threadIdx.x; e < total; e += kK1Threads) {
+            const float s = cls[e];
+            if (s >= thr) hit(e, s);
         }
     }
-    for (; i < total4; i += stride) {
-        float4 v = ldg_stream_f4(cls4 + i);
-        int64_t e = i << 2;
-        if (v.x >= thr) emit(e, v.x);
-        if (v.y >= thr) emit(e + 1, v.y);
-        if (v.z >= thr) emit(e + 2, v.z);
-        if (v.w >= thr) emit(e + 3, v.w);
-    }
-    for (int64_t e = (total4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
-         e += stride) {
-        float s = cls[e];
-        if (s >= thr) emit(e, s);
-    }
+    __syncthreads();
+    const int qn = s_qn < kK1Queue ? s_qn : kK1Queue;
+    for (int i = threadIdx.x; i < qn; i += kK1Threads)
+        k1_append(s_q[i].x, __uint_as_float(s_q[i].y), N, C, cand_keys, cand_count, cap);
 }
 
 // --------------------------------------------------------- sort helpers ------
@@ -221,7 +252,7 @@ template <int kThreads, class Fetch, class Emit>
 __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                         int max_out, const NmsSmem& S, Fetch fetch, Emit emit) {
     constexpr int kLanesPerCand = kThreads / kChunk;   // threads that split the kept list
-    static_assert(kThreads % kChunk == 0 && kMaskWords % kLanesPerCand == 0, "bad NMS geometry");
+    static_assert(kThreads % kChunk == 0 && kChunk % kLanesPerCand == 0 && kChunk == 64, "bad NMS geometry");
     const int tid = threadIdx.x;
     if (tid == 0) S.misc[0] = 0;
     __syncthreads();
@@ -254,7 +285,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
         lo = S.skeys[sc - 1];
         done += sc;
 
-        // ---- chunks of kChunk candidates ----
+        // ---- chunks of kChunk (= 64) candidates ----
         for (int base = 0; base < sc && kept < max_out; base += kChunk) {
             const int m = (sc - base) < kChunk ? (sc - base) : kChunk;
             if (tid < kChunk) {
@@ -269,8 +300,9 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 } else {
                     S.c_supp[tid] = 1;
                 }
+                S.c_mask[tid * 2] = 0u;
+                S.c_mask[tid * 2 + 1] = 0u;
             }
-            if (tid < kMaskWords) S.keptw[tid] = 0;
             __syncthreads();
             const int t = tid % kChunk, r = tid / kChunk;
             const float tymin = S.c_ymin[t], txmin = S.c_xmin[t], tymax = S.c_ymax[t],
@@ -286,50 +318,57 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 }
             }
             __syncthreads();
-            // (c) intra-chunk bitmask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
-            {
-                const bool t_alive = (t < m) && (S.c_supp[t] == 0);
-#pragma unroll
-                for (int wi = 0; wi < kMaskWords / kLanesPerCand; ++wi) {
-                    const int w = r * (kMaskWords / kLanesPerCand) + wi;
-                    uint32_t bits = 0;
-                    if (t_alive) {
-                        const int u0 = w * 32;
-                        const int u1 = (u0 + 32 < t) ? (u0 + 32) : t;
-                        for (int u = u0; u < u1; ++u) {
-                            if (S.c_supp[u] == 0 &&
-                                iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.c_ymin[u],
-                                            S.c_xmin[u], S.c_ymax[u], S.c_xmax[u], S.c_area[u], thr))
-                                bits |= 1u << (u - u0);
-                        }
+            // (c) intra-chunk mask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
+            if (t < m && S.c_supp[t] == 0) {
+                constexpr int kSlice = kChunk / kLanesPerCand;
+                const int u0 = r * kSlice;
+                const int u1 = (u0 + kSlice < t) ? (u0 + kSlice) : t;
+                uint32_t lo = 0, hi = 0;
+                for (int u = u0; u < u1; ++u) {
+                    if (S.c_supp[u] == 0 &&
+                        iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.c_ymin[u], S.c_xmin[u],
+                                    S.c_ymax[u], S.c_xmax[u], S.c_area[u], thr)) {
+                        if (u < 32) lo |= 1u << u; else hi |= 1u << (u - 32);
                     }
-                    S.c_mask[t * kMaskWords + w] = bits;
                 }
+                if (lo) atomicOr(&S.c_mask[t * 2], lo);
+                if (hi) atomicOr(&S.c_mask[t * 2 + 1], hi);
             }
             __syncthreads();
-            // (d) sequential resolve by warp 0: lane l owns kept word l
+            // (d) sequential resolve by warp 0.  Rows live in registers (lane l: candidates l
+            // and l+32) and reach every lane by shuffle, so the loop-carried chain is two ANDs,
+            // a compare and an OR per candidate - no shared-memory latency on it.
             if (tid < 32) {
-                uint32_t myw = 0;
+                const uint32_t alive_lo = __ballot_sync(0xffffffffu, S.c_supp[tid] == 0);
+                const uint32_t alive_hi = __ballot_sync(0xffffffffu, S.c_supp[tid + 32] == 0);
+                const uint32_t rowA_lo = S.c_mask[tid * 2];
+                const uint32_t rowB_lo = S.c_mask[(tid + 32) * 2];
+                const uint32_t rowB_hi = S.c_mask[(tid + 32) * 2 + 1];
+                uint32_t kept_lo = 0, kept_hi = 0;
                 int k = kept;
-                for (int q = 0; q < m && k < max_out; ++q) {
-                    bool alive = S.c_supp[q] == 0;
-                    uint32_t hit = (tid < kMaskWords) ? (S.c_mask[q * kMaskWords + tid] & myw) : 0u;
-                    bool any = __any_sync(0xffffffffu, hit != 0);
-                    if (alive && !any) {
-                        if (tid == (q >> 5)) myw |= 1u << (q & 31);
-                        ++k;
-                    }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const uint32_t rl = __shfl_sync(0xffffffffu, rowA_lo, q);
+                    const bool keep = ((alive_lo >> q) & 1u) && !(rl & kept_lo) && (k < max_out);
+                    if (keep) { kept_lo |= 1u << q; ++k; }
                 }
-                if (tid < kMaskWords) S.keptw[tid] = myw;
-                if (tid == 0) S.misc[0] = k;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const uint32_t rl = __shfl_sync(0xffffffffu, rowB_lo, q);
+                    const uint32_t rh = __shfl_sync(0xffffffffu, rowB_hi, q);
+                    const bool keep = ((alive_hi >> q) & 1u) && !((rl & kept_lo) | (rh & kept_hi)) &&
+                                      (k < max_out);
+                    if (keep) { kept_hi |= 1u << q; ++k; }
+                }
+                if (tid == 0) { S.keptw[0] = kept_lo; S.keptw[1] = kept_hi; S.misc[0] = k; }
             }
             __syncthreads();
             // (e) append newly kept boxes in order and emit them
             if (tid < m) {
-                uint32_t wv = S.keptw[tid >> 5];
+                const uint32_t w0 = S.keptw[0], w1 = S.keptw[1];
+                const uint32_t wv = (tid < 32) ? w0 : w1;
                 if ((wv >> (tid & 31)) & 1u) {
-                    int rank = kept;
-                    for (int w = 0; w < (tid >> 5); ++w) rank += __popc(S.keptw[w]);
+                    int rank = kept + ((tid < 32) ? 0 : __popc(w0));
                     rank += __popc(wv & ((1u << (tid & 31)) - 1u));
                     S.k_ymin[rank] = S.c_ymin[tid]; S.k_xmin[rank] = S.c_xmin[tid];
                     S.k_ymax[rank] = S.c_ymax[tid]; S.k_xmax[rank] = S.c_xmax[tid];
@@ -564,7 +603,8 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
                   "%s: NULL argument", who);
     MLP_CHECK_ARG(B >= 1 && N >= 1 && C >= 1, "%s: bad shape B=%d N=%lld C=%d", who, B, (long long)N, C);
     MLP_CHECK_ARG(C <= 256, "%s: num_classes=%d > 256 not supported", who, C);
-    MLP_CHECK_ARG(N < (1ll << 30) && (int64_t)B * N * C < (1ll << 40), "%s: problem too large", who);
+    MLP_CHECK_ARG(N < (1ll << 30) && (int64_t)B * N * C < (1ll << 32) - 4096,
+                  "%s: B*N*C must fit 32 bits", who);
     if (p->strict_batch && B > MLP_MAX_BATCH) {
         mlp_set_error("%s: batch %d > 32; the reference's MoldBatch uses tf.dynamic_partition(.., 32) "
                       "(engine/layers/misc.py:275). Pass strict_batch=0 to lift the limit.", who, B);
@@ -595,10 +635,12 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     {
         ProfScope prof(ctx, MLP_ST_THRESHOLD, stream);
         const int64_t total = (int64_t)B * N * C;
-        int64_t blocks = (total / 4 + 255) / 256;
-        int64_t capb = (int64_t)ctx->sm_count * 8;
-        int grid = (int)(blocks < capb ? (blocks < 1 ? 1 : blocks) : capb);
-        threshold_compact_kernel<<<grid, 256, 0, stream>>>(cls_dev, total, (int)N, C,
+        int64_t tiles = (total / 4 + kK1Threads * 4 - 1) / (kK1Threads * 4);
+        int occ = 0;
+        MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, threshold_compact_kernel, kK1Threads, 0));
+        int64_t capb = (int64_t)ctx->sm_count * (occ < 1 ? 1 : occ);      // one resident wave
+        int grid = (int)(tiles < capb ? (tiles < 1 ? 1 : tiles) : capb);
+        threshold_compact_kernel<<<grid, kK1Threads, 0, stream>>>(cls_dev, (uint32_t)total, (int)N, C,
                                                           p->min_confidence, D.cand_keys,
                                                           D.cand_count, D.cap, m_dev);
         MLP_LAUNCH_CHECK(ctx);

@@ -9,6 +9,8 @@
 // st.global per 16 uint8 pixels / 4 float pixels), only pixels inside the clipped box
 // evaluate the two-stage lerp from the mask tile held in shared memory, everything else
 // is written as zero without touching memory for reads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -49,7 +51,7 @@ struct PasteGeom {
 };
 
 // misc.py:373-386: box = max(box,1) -> float; ceil(c -/+ s/2) -> int -> clip.
-__device__ __forceinline__ PasteGeom paste_geometry(const int32_t* __restrict__ row, int thr, int mh,
+__device__ __forceinline__ PasteGeom paste_geometry(const int32_t* row, int thr, int mh,
                                                     int mw, int PH, int PW) {
     PasteGeom g;
     const int conf = row[5];
@@ -82,15 +84,22 @@ __device__ __forceinline__ float paste_value(const float* __restrict__ tile, int
     return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
 }
 
-// One work item = (image b, slot j, band of `band_rows` frame rows).  kU8: 16 pixels per
-// thread-store; else 4 float pixels per thread-store.  PW must be a multiple of the
-// vector width (host checks; the scalar kernel below handles everything else).
+// One work item = (image b, slot j, band of `band_rows` frame rows).  Every thread-store is
+// 128 bits: 16 uint8 pixels (kU8) or 4 float pixels.  PW must be a multiple of that vector
+// width (host checks; the scalar kernel below handles everything else).  The band is written
+// in three phases so that no warp mixes cheap and expensive lanes:
+//   A  rows of the band above/below the clipped box: one contiguous byte range, flat
+//      unrolled zero stores, no index arithmetic;
+//   B1 rows crossing the box: the 16-byte segments left and right of it (zeros);
+//   B2 the segments that intersect the box, flattened over ALL threads of the CTA: each
+//      evaluates the reference's two-stage lerp per pixel from the mask tile in smem.
 template <bool kU8>
 __global__ void __launch_bounds__(kPasteThreads)
 paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks, int B, int m_rows,
              int m_stride, const int32_t* __restrict__ m_dev, const int32_t* __restrict__ thr_dev,
              int mh, int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
     constexpr int kVec = kU8 ? 16 : 4;
+    constexpr int kPx = kU8 ? 1 : 4;               // bytes per pixel
     __shared__ float s_tile[kMaxTile];
     int M = m_dev ? *m_dev : m_rows;
     if (M > m_rows) M = m_rows;
@@ -98,63 +107,128 @@ paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks,
     const int thr = *thr_dev;
     const int bands = (PH + band_rows - 1) / band_rows;
     const int64_t items = (int64_t)B * M * bands;
-    const int segs_per_row = PW / kVec;
-    int tile_owner = -1;                       // instance whose mask is in s_tile
-
+    const int spr = PW / kVec;                     // 16-byte segments per frame row
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    // One CTA per (instance, band) item, NOT a persistent grid: on B200 a write-only stream
+    // of many short-lived CTAs, each owning one contiguous 32 KB band, reaches ~7.4 TB/s while
+    // persistent CTAs top out near 6.3 TB/s (tools/write_bw.cu, profiles/write_bw_r01.txt).
+    // The grid is sized for the capacity m_rows; CTAs past the device-side M exit at once.
+    constexpr int kTileRegs = 4;                   // covers tiles up to 32x32; larger ones load late
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int inst = (int)(item / bands);
         const int band = (int)(item - (int64_t)inst * bands);
         const int b = inst / M, j = inst - b * M;
-        const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
+        int row[6];
+        {
+            const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * m_stride + j) * 6);
+            const int2 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+            row[0] = a0.x; row[1] = a0.y; row[2] = a1.x; row[3] = a1.y; row[4] = a2.x; row[5] = a2.y;
+        }
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         const int y0 = band * band_rows;
         const int y1 = min(y0 + band_rows, PH);
-        const bool touches = g.active && y0 < g.ymax && y1 > g.ymin;
-        if (touches && tile_owner != inst) {
-            __syncthreads();
+        // rows of this band that cross the clipped box: [ya, yb)
+        int ya = y1, yb = y1;
+        if (g.active) { ya = min(max(g.ymin, y0), y1); yb = min(max(g.ymax, ya), y1); }
+        const bool touches = yb > ya;              // block-uniform
+        // the mask tile is only needed by phase B2: issue its loads now, park them in
+        // shared memory after the zero rows have been streamed out
+        int tile_regs[kTileRegs];
+        if (touches) {
             const int32_t* m = masks + ((int64_t)b * m_stride + j) * mh * mw;
-            for (int i = threadIdx.x; i < mh * mw; i += kPasteThreads) s_tile[i] = (float)m[i];
-            tile_owner = inst;
-            __syncthreads();
-        }
-        unsigned char* obase = static_cast<unsigned char*>(out) +
-                               ((int64_t)inst * PH + y0) * PW * (kU8 ? 1 : 4);
-        const int nseg = (y1 - y0) * segs_per_row;
-        for (int s = threadIdx.x; s < nseg; s += kPasteThreads) {
-            const int ry = s / segs_per_row;
-            const int x0 = (s - ry * segs_per_row) * kVec;
-            const int oy = y0 + ry;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (touches && oy >= g.ymin && oy < g.ymax && x0 < g.xmax && x0 + kVec > g.xmin) {
-                const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
-                const float fl = floorf(p);
-                const int ylo = max((int)fl, 0);
-                const int yhi = min((int)ceilf(p), mh - 1);
-                const float ly = __fsub_rn(p, fl);
-                if (kU8) {
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int ox = x0 + q;
-                        if (ox >= g.xmin && ox < g.xmax) {
-                            const float val = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
-                            if (val > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
-                        }
-                    }
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
-                } else {
-                    float f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int ox = x0 + q;
-                        if (ox >= g.xmin && ox < g.xmax)
-                            f[q] = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
-                    }
-                    v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                                   __float_as_uint(f[3]));
-                }
+            for (int q = 0; q < kTileRegs; ++q) {
+                const int i = tid + q * kPasteThreads;
+                tile_regs[q] = (i < mh * mw) ? __ldg(m + i) : 0;
             }
-            stg_stream_u4(reinterpret_cast<uint4*>(obase) + s, v);
+        }
+        uint4* band_base = reinterpret_cast<uint4*>(static_cast<unsigned char*>(out) +
+                                                    ((int64_t)inst * PH + y0) * PW * kPx);
+        // ---- phase A: zero rows [y0,ya) and [yb,y1)
+        {
+            const int n_top = (ya - y0) * spr;
+            int i = tid;
+            for (; i + 3 * kPasteThreads < n_top; i += 4 * kPasteThreads) {
+                stg_stream_u4(band_base + i, zero4);
+                stg_stream_u4(band_base + i + kPasteThreads, zero4);
+                stg_stream_u4(band_base + i + 2 * kPasteThreads, zero4);
+                stg_stream_u4(band_base + i + 3 * kPasteThreads, zero4);
+            }
+            for (; i < n_top; i += kPasteThreads) stg_stream_u4(band_base + i, zero4);
+            uint4* bot = band_base + (int64_t)(yb - y0) * spr;
+            const int n_bot = (y1 - yb) * spr;
+            i = tid;
+            for (; i + 3 * kPasteThreads < n_bot; i += 4 * kPasteThreads) {
+                stg_stream_u4(bot + i, zero4);
+                stg_stream_u4(bot + i + kPasteThreads, zero4);
+                stg_stream_u4(bot + i + 2 * kPasteThreads, zero4);
+                stg_stream_u4(bot + i + 3 * kPasteThreads, zero4);
+            }
+            for (; i < n_bot; i += kPasteThreads) stg_stream_u4(bot + i, zero4);
+        }
+        if (!touches) continue;
+        __syncthreads();                           // previous item's phase B2 done with s_tile
+#pragma unroll
+        for (int q = 0; q < kTileRegs; ++q) {
+            const int i = tid + q * kPasteThreads;
+            if (i < mh * mw) s_tile[i] = (float)tile_regs[q];
+        }
+        if (mh * mw > kTileRegs * kPasteThreads) {
+            const int32_t* m = masks + ((int64_t)b * m_stride + j) * mh * mw;
+            for (int i = tid + kTileRegs * kPasteThreads; i < mh * mw; i += kPasteThreads)
+                s_tile[i] = (float)__ldg(m + i);
+        }
+        const int sL = g.xmin / kVec;                       // first segment touching the box
+        const int sR = (g.xmax + kVec - 1) / kVec;          // one past the last
+        const int bw = sR - sL;
+        uint4* box_rows = band_base + (int64_t)(ya - y0) * spr;
+        // ---- phase B1: zero strips left/right of the box, one warp per row
+        {
+            const int nz = spr - bw;
+            for (int r = warp; r < yb - ya; r += kPasteThreads / 32) {
+                uint4* rp = box_rows + (int64_t)r * spr;
+                for (int k = lane; k < nz; k += 32) stg_stream_u4(rp + (k < sL ? k : k + bw), zero4);
+            }
+        }
+        __syncthreads();                           // s_tile ready
+        // ---- phase B2: segments intersecting the box, flattened over the CTA
+        const int nb = (yb - ya) * bw;
+        for (int i = tid; i < nb; i += kPasteThreads) {
+            const int r = i / bw;
+            const int seg = sL + (i - r * bw);
+            const int oy = ya + r;
+            const int x0 = seg * kVec;
+            const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
+            const float fl = floorf(p);
+            const int ylo = max((int)fl, 0);
+            const int yhi = min((int)ceilf(p), mh - 1);
+            const float ly = __fsub_rn(p, fl);
+            uint4 v;
+            if (kU8) {
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int ox = x0 + q;
+                    if (ox >= g.xmin && ox < g.xmax) {
+                        const float val = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
+                        if (val > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
+                    }
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ox = x0 + q;
+                    if (ox >= g.xmin && ox < g.xmax)
+                        f[q] = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
+                }
+                v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                               __float_as_uint(f[3]));
+            }
+            stg_stream_u4(box_rows + (int64_t)r * spr + seg, v);
         }
     }
 }
@@ -226,13 +300,25 @@ extern "C" int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev,
     ProfScope prof(ctx, MLP_ST_PASTE, st);
     const bool u8 = out_mode == MLP_PASTE_U8;
     const int vec = u8 ? 16 : 4;
-    // persistent grid, 8 CTAs of 256 threads per SM (write-only: occupancy hides store latency)
-    const int grid = ctx->sm_count * 8;
+    // persistent grid: exactly the resident CTA count, each CTA streams one contiguous slab
+    int occ = 0;
+    if (u8) MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_kernel<true>, kPasteThreads, 0));
+    else MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_kernel<false>, kPasteThreads, 0));
+    if (occ < 1) occ = 1;
+    int ctas_per_sm = 0;                          // 0: one CTA per item (default)
+    int band_kb = 64;
+    if (const char* e = getenv("MLP_PASTE_CTAS_PER_SM")) ctas_per_sm = atoi(e);     // tuning knobs
+    if (const char* e = getenv("MLP_PASTE_BAND_KB")) band_kb = atoi(e) > 0 ? atoi(e) : 64;
+    int grid = ctx->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : occ);
     if (frame_w % vec == 0) {
         // bands of ~64 KB of output keep >> grid items in flight even for one small batch
-        int band_rows = (64 * 1024) / (frame_w * (u8 ? 1 : 4));
+        int band_rows = (band_kb * 1024) / (frame_w * (u8 ? 1 : 4));
         if (band_rows < 1) band_rows = 1;
         if (band_rows > frame_h) band_rows = frame_h;
+        if (ctas_per_sm <= 0) {
+            const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
+            grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
+        }
         if (u8)
             paste_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, masks_i32_dev, batch, m_rows,
                                                               m_stride, m_dev, thr_dev, mask_h, mask_w,

@@ -54,47 +54,56 @@ roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
 }
 
 // ---- run ----------------------------------------------------------------------
+constexpr int kPixUnroll = 4;         // output pixels in flight per warp (16 corner loads)
+constexpr int kMaxPix = 1024;         // crop_h * crop_w <= 1024 (per-RoI pixel table in smem)
+
 __global__ void __launch_bounds__(kRoiThreads)
 roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ dist, int B,
                  int m_rows, int m_stride, float image_h, float image_w, int ch, int cw,
                  const int32_t* __restrict__ roi_src, const int32_t* __restrict__ counts,
                  int32_t* __restrict__ level_m, float* __restrict__ roi_boxes) {
+    // per-RoI tables, built once per RoI by ch+cw (coordinates) and ch*cw (pixels) threads so
+    // that the streaming loop below carries no divisions and no 64-bit address arithmetic
     __shared__ float s_iny[kMaxCrop], s_inx[kMaxCrop];
-    __shared__ int s_item[4];
-    int Mf[MLP_MAX_LEVELS], off[MLP_MAX_LEVELS + 1];
-    int64_t item_start[MLP_MAX_LEVELS + 1];
-    off[0] = 0;
-    item_start[0] = 0;
-#pragma unroll
-    for (int f = 0; f < MLP_MAX_LEVELS; ++f) {
-        Mf[f] = (f < L) ? level_m[f] : 0;
-        off[f + 1] = off[f] + Mf[f];
-        item_start[f + 1] = item_start[f] + (int64_t)B * Mf[f];
+    __shared__ int4 s_poff[kMaxPix];          // float offsets of TL,TR,BL,BR inside this image's map
+    __shared__ float2 s_pw[kMaxPix];          // (lx, ly); lx < 0 marks "outside -> 0"
+    __shared__ int s_mf[MLP_MAX_LEVELS], s_off[MLP_MAX_LEVELS + 1];
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int f = 0; f < L; ++f) {
+            const int m = level_m[f];
+            s_mf[f] = m; s_off[f] = off;
+            off += m;
+        }
+        s_off[L] = off;
+        if (blockIdx.x == 0) level_m[L] = off;               // R = sum of Mf, for TrimInstances
     }
-    const int R = off[L];
-    if (blockIdx.x == 0 && threadIdx.x == 0) level_m[L] = R;     // sum of Mf for TrimInstances
-    const int64_t items = item_start[L];
+    __syncthreads();
+    const int R = s_off[L];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = kRoiThreads / 32;
     const int npix = ch * cw;
     const int C4 = Cf >> 2;
+    const bool vec = (Cf & 3) == 0;
+    // One CTA per (level, image, slot) over the CAPACITY m_rows (not a persistent grid: the
+    // stage is write-dominated and short-lived CTAs stream best, see paste.cu); slots past the
+    // device-side Mf exit at once.
+    const int64_t items = (int64_t)L * B * m_rows;
 
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        int f = 0;
-#pragma unroll
-        for (int q = 1; q < MLP_MAX_LEVELS; ++q)
-            if (q < L && item >= item_start[q]) f = q;
-        const int64_t local = item - item_start[f];
-        const int b = (int)(local / Mf[f]);
-        const int slot = (int)(local - (int64_t)b * Mf[f]);
+        const int slot = (int)(item % m_rows);
+        const int fb = (int)(item / m_rows);
+        const int f = fb / B, b = fb - f * B;
+        const int mf = s_mf[f];
+        if (slot >= mf) continue;
         const int cnt = counts[f * B + b];
-        float* out = lv.crops[f] + ((int64_t)b * Mf[f] + slot) * npix * Cf;
-        float* rb = roi_boxes + ((int64_t)b * R + off[f] + slot) * 6;
+        float* out = lv.crops[f] + ((int64_t)b * mf + slot) * npix * Cf;
+        float* rb = roi_boxes + ((int64_t)b * R + s_off[f] + slot) * 6;
 
         if (slot >= cnt) {                                   // MoldBatch padding
             if (threadIdx.x < 6) rb[threadIdx.x] = -1.0f;
             const int64_t n = (int64_t)npix * Cf;
-            if ((Cf & 3) == 0) {
+            if (vec) {
                 float4* o4 = reinterpret_cast<float4*>(out);
                 const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
                 for (int64_t i = threadIdx.x; i < (n >> 2); i += kRoiThreads) stg_stream_f4(o4 + i, m1);
@@ -106,7 +115,7 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
         const int j = roi_src[((int64_t)f * B + b) * m_rows + slot];
         const float* row = dist + ((int64_t)b * m_stride + j) * 7;
         const int Hf = lv.fh[f], Wf = lv.fw[f];
-        __syncthreads();                                     // previous RoI done with s_in*
+        __syncthreads();                                     // previous RoI done with the tables
         if (threadIdx.x < 6) rb[threadIdx.x] = row[1 + threadIdx.x];
         if (threadIdx.x < ch + cw) {
             // NormalizeBoxes(shape=image) then crop_and_resize source coordinates
@@ -130,53 +139,81 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
             if (is_y) s_iny[idx] = in; else s_inx[idx] = in;
         }
         __syncthreads();
-        const float* img = lv.fmap[f] + (int64_t)b * Hf * Wf * Cf;
-        const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
-        for (int p = warp; p < npix; p += nwarps) {
-            const int y = p / cw, x = p - y * cw;
-            const float in_y = s_iny[y], in_x = s_inx[x];
-            float* o = out + (int64_t)p * Cf;
-            const bool inside = !(in_y < 0.0f || in_y > hm1) && !(in_x < 0.0f || in_x > wm1) &&
-                                (in_y == in_y) && (in_x == in_x);
-            if (!inside) {                                   // extrapolation_value = 0
-                if ((Cf & 3) == 0)
-                    for (int c4 = lane; c4 < C4; c4 += 32)
-                        stg_stream_f4(reinterpret_cast<float4*>(o) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
-                else
-                    for (int c = lane; c < Cf; c += 32) o[c] = 0.0f;
-                continue;
+        {
+            const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
+            for (int p = threadIdx.x; p < npix; p += kRoiThreads) {
+                const int y = p / cw, x = p - y * cw;
+                const float in_y = s_iny[y], in_x = s_inx[x];
+                int4 o = make_int4(0, 0, 0, 0);
+                float2 w = make_float2(-1.0f, 0.0f);
+                // TF: in < 0 || in > size-1 -> extrapolation value; NaN counts as outside
+                if (in_y >= 0.0f && in_y <= hm1 && in_x >= 0.0f && in_x <= wm1) {
+                    const float fy = floorf(in_y), fx = floorf(in_x);
+                    const int top = (int)fy, bot = (int)ceilf(in_y);
+                    const int left = (int)fx, right = (int)ceilf(in_x);
+                    w = make_float2(__fsub_rn(in_x, fx), __fsub_rn(in_y, fy));
+                    o = make_int4((top * Wf + left) * Cf, (top * Wf + right) * Cf,
+                                  (bot * Wf + left) * Cf, (bot * Wf + right) * Cf);
+                }
+                s_poff[p] = o;
+                s_pw[p] = w;
             }
-            const float fy = floorf(in_y), fx = floorf(in_x);
-            const int top = (int)fy, bot = (int)ceilf(in_y);
-            const int left = (int)fx, right = (int)ceilf(in_x);
-            const float ly = __fsub_rn(in_y, fy), lx = __fsub_rn(in_x, fx);
-            const float* ptl = img + ((int64_t)top * Wf + left) * Cf;
-            const float* ptr = img + ((int64_t)top * Wf + right) * Cf;
-            const float* pbl = img + ((int64_t)bot * Wf + left) * Cf;
-            const float* pbr = img + ((int64_t)bot * Wf + right) * Cf;
-            if ((Cf & 3) == 0) {
+        }
+        __syncthreads();
+        const float* img = lv.fmap[f] + (int64_t)b * Hf * Wf * Cf;
+        // each warp owns kPixUnroll consecutive output pixels per iteration
+        for (int p0 = warp * kPixUnroll; p0 < npix; p0 += nwarps * kPixUnroll) {
+            if (vec) {
                 for (int c4 = lane; c4 < C4; c4 += 32) {
-                    const float4 tl = __ldg(reinterpret_cast<const float4*>(ptl) + c4);
-                    const float4 tr = __ldg(reinterpret_cast<const float4*>(ptr) + c4);
-                    const float4 bl = __ldg(reinterpret_cast<const float4*>(pbl) + c4);
-                    const float4 br = __ldg(reinterpret_cast<const float4*>(pbr) + c4);
-                    float4 r;
-#define MLP_LERP2(F)                                                                      \
-    {                                                                                     \
-        const float t_ = __fadd_rn(tl.F, __fmul_rn(__fsub_rn(tr.F, tl.F), lx));           \
-        const float b_ = __fadd_rn(bl.F, __fmul_rn(__fsub_rn(br.F, bl.F), lx));           \
-        r.F = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly));                            \
+                    float4 tl[kPixUnroll], tr[kPixUnroll], bl[kPixUnroll], br[kPixUnroll];
+                    float2 w[kPixUnroll];
+                    const float* base = img + c4 * 4;
+#pragma unroll
+                    for (int u = 0; u < kPixUnroll; ++u) {            // 16 loads in flight
+                        const int p = min(p0 + u, npix - 1);
+                        const int4 o = s_poff[p];
+                        w[u] = s_pw[p];
+                        tl[u] = __ldg(reinterpret_cast<const float4*>(base + o.x));
+                        tr[u] = __ldg(reinterpret_cast<const float4*>(base + o.y));
+                        bl[u] = __ldg(reinterpret_cast<const float4*>(base + o.z));
+                        br[u] = __ldg(reinterpret_cast<const float4*>(base + o.w));
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPixUnroll; ++u) {
+                        if (p0 + u >= npix) continue;
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);  // extrapolation_value = 0
+                        if (w[u].x >= 0.0f) {
+                            const float lx = w[u].x, ly = w[u].y;
+#define MLP_LERP2(F)                                                                          \
+    {                                                                                         \
+        const float t_ = __fadd_rn(tl[u].F, __fmul_rn(__fsub_rn(tr[u].F, tl[u].F), lx));      \
+        const float b_ = __fadd_rn(bl[u].F, __fmul_rn(__fsub_rn(br[u].F, bl[u].F), lx));      \
+        r.F = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly));                                \
     }
-                    MLP_LERP2(x) MLP_LERP2(y) MLP_LERP2(z) MLP_LERP2(w)
+                            MLP_LERP2(x) MLP_LERP2(y) MLP_LERP2(z) MLP_LERP2(w)
 #undef MLP_LERP2
-                    stg_stream_f4(reinterpret_cast<float4*>(o) + c4, r);
+                        }
+                        stg_stream_f4(reinterpret_cast<float4*>(out + (p0 + u) * Cf) + c4, r);
+                    }
                 }
             } else {
-                for (int c = lane; c < Cf; c += 32) {
-                    const float tl = ptl[c], tr = ptr[c], bl = pbl[c], br = pbr[c];
-                    const float t_ = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-                    const float b_ = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-                    o[c] = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly));
+#pragma unroll
+                for (int u = 0; u < kPixUnroll; ++u) {
+                    const int p = p0 + u;
+                    if (p >= npix) continue;
+                    const int4 o = s_poff[p];
+                    const float2 w = s_pw[p];
+                    float* op = out + p * Cf;
+                    for (int c = lane; c < Cf; c += 32) {
+                        float r = 0.0f;
+                        if (w.x >= 0.0f) {
+                            const float tl = img[o.x + c], tr = img[o.y + c], bl = img[o.z + c], br = img[o.w + c];
+                            const float t_ = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), w.x));
+                            const float b_ = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), w.x));
+                            r = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), w.y));
+                        }
+                        op[c] = r;
+                    }
                 }
             }
         }
@@ -302,7 +339,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     MLP_CHECK_ARG(channels >= 1 && batch >= 1 && m_rows >= 1 && m_stride >= m_rows,
                   "mlp_roi_align_run: bad shape");
     MLP_CHECK_ARG(crop_h >= 1 && crop_w >= 1 && crop_h <= kMaxCrop && crop_w <= kMaxCrop &&
-                      crop_h + crop_w <= kRoiThreads,
+                      crop_h + crop_w <= kRoiThreads && crop_h * crop_w <= kMaxPix,
                   "mlp_roi_align_run: crop size %dx%d out of range [1,%d]", crop_h, crop_w, kMaxCrop);
     MLP_CHECK_ARG(ctx->arena[MLP_ARENA_ROI] &&
                       ctx->arena_bytes[MLP_ARENA_ROI] >= (int64_t)num_levels * batch * m_rows * 4,
@@ -314,6 +351,9 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
         MLP_CHECK_ARG(mlp_aligned16(fmaps_dev[f]) && mlp_aligned16(crops_dev[f]),
                       "mlp_roi_align_run: level %d pointers must be 16-byte aligned", f);
         MLP_CHECK_ARG(fh[f] >= 1 && fw[f] >= 1, "mlp_roi_align_run: level %d map is %dx%d", f, fh[f], fw[f]);
+        MLP_CHECK_ARG((int64_t)fh[f] * fw[f] * channels < (1ll << 31) &&
+                          (int64_t)crop_h * crop_w * channels < (1ll << 31),
+                      "mlp_roi_align_run: level %d map too large for 32-bit offsets", f);
         lv.fmap[f] = fmaps_dev[f];
         lv.crops[f] = crops_dev[f];
         lv.fh[f] = fh[f];
@@ -321,8 +361,8 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     }
     DeviceGuard g(ctx->device);
     ProfScope prof(ctx, MLP_ST_ROI_ALIGN, (cudaStream_t)stream);
-    // persistent grid: 4 CTAs of 256 threads per SM
-    const int grid = ctx->sm_count * 4;
+    const int64_t items = (int64_t)num_levels * batch * m_rows;
+    const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
     roi_align_kernel<<<grid, kRoiThreads, 0, (cudaStream_t)stream>>>(
         lv, num_levels, channels, dist_dev, batch, m_rows, m_stride, image_h, image_w, crop_h, crop_w,
         static_cast<const int32_t*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev,
