@@ -1,0 +1,116 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/masklab_b200.h declares, the ctypes table covers them all, and the product package
+never touches oracle/ (no compute call is made here - there is no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "masklab_b200.h")
+PKG = os.path.join(ROOT, "instance-segmentation-road-project_b200")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mlp_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    import masklab_b200
+    return masklab_b200.load_library()
+
+
+def test_header_declares_the_whole_path():
+    syms = declared_symbols()
+    for must in ("mlp_prior_layer", "mlp_restore_boxes", "mlp_normalize_boxes", "mlp_detection_proposal",
+                 "mlp_detect_from_heads", "mlp_mask_distribute", "mlp_roi_align_plan", "mlp_roi_align_run",
+                 "mlp_trim_plan", "mlp_trim_run", "mlp_upsample_output", "mlp_crop_and_pad_mask",
+                 "mlp_mold_batch_plan", "mlp_mold_batch_run", "mlp_dlpack_view", "mlp_ctx_create"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in masklab_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib):
+    from masklab_b200 import runtime as rt
+    assert sorted(rt.SIGNATURES) == declared_symbols()
+    assert lib.mlp_version() == 100
+    assert isinstance(lib.mlp_last_error(), bytes)
+    assert ctypes.sizeof(rt.PriorConfigC) == 4 * (2 + 8 + 8 + 2 * 8 * 32)
+    assert ctypes.sizeof(rt.DetectionParamsC) == 20
+
+
+def test_prior_count_is_host_side(lib):
+    import masklab_b200 as ml
+    import synth
+    pc = ml.PriorBoxes(**synth.prior_config()).to_c("same")
+    assert lib.mlp_prior_count(ctypes.byref(pc), 512, 1024) == 163680
+    assert lib.mlp_prior_count(ctypes.byref(pc), 540, 960) == 163275
+    pv = ml.PriorBoxes(**synth.prior_config()).to_c("valid")
+    assert lib.mlp_prior_count(ctypes.byref(pv), 20, 20) == 5 * 15
+    bad = ml.PriorBoxes(**synth.prior_config()).to_c("same")
+    bad.num_levels = 0
+    assert lib.mlp_prior_count(ctypes.byref(bad), 64, 64) < 0
+    assert b"num_levels" in lib.mlp_last_error()
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    import masklab_b200 as ml
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        ml.Context.get()
+    with pytest.raises((RuntimeError, ValueError)):
+        ml.DetectionProposal()([torch.zeros((1, 4, 2)), torch.zeros((1, 4, 4)), None])
+
+
+def test_product_never_imports_oracle():
+    offenders = []
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "oracle/" in text and f.endswith(".py") and "import" in text and re.search(r"import.*oracle", text):
+                    offenders.append(f)
+    assert not offenders, offenders
+
+
+def test_prior_boxes_mirror_matches_golden():
+    import json
+    import masklab_b200 as ml
+    with open(os.path.join(ROOT, "tests", "golden", "prior_tables.json")) as f:
+        golden = json.load(f)
+    for name, g in golden.items():
+        pb = ml.PriorBoxes(g["strides"], g["sizes"], g["pr_scales"], g["pr_ratios"])
+        assert pb.table.tolist() == g["rows"], name
+        assert len(pb) == g["num_anchors"]
+        assert pb.get_config() == {"strides": g["strides"], "sizes": g["sizes"],
+                                   "pr_scales": g["pr_scales"], "pr_ratios": g["pr_ratios"]}
+        assert list(pb.boxes.columns) == ["stride", "w", "h"] and pb.boxes.index[0] == 1
+
+
+def test_layer_configs_roundtrip_without_gpu():
+    import masklab_b200 as ml
+    import synth
+    objs = ml.get_custom_objects()
+    for name in ("PriorLayer", "RestoreBoxes", "NormalizeBoxes", "DetectionProposal", "MoldBatch",
+                 "MaskDistribute", "PyramidRoiAlign", "TrimInstances", "UpSampleOutput", "CropAndPadMask"):
+        assert name in objs
+    layers = [ml.PriorLayer(synth.prior_config(), padding="valid"), ml.DetectionProposal(0.3, 0.5, 0.7, 50, 8),
+              ml.MaskDistribute(3, 40), ml.PyramidRoiAlign((7, 7), 16), ml.TrimInstances(False, 4),
+              ml.MoldBatch(12), ml.RestoreBoxes(), ml.NormalizeBoxes(), ml.UpSampleOutput(),
+              ml.CropAndPadMask(output="uint8")]
+    for layer in layers:
+        clone = type(layer).from_config(layer.get_config())
+        assert clone.get_config() == layer.get_config()
+    assert layers[0].get_config()["trainable"] is False        # detection.py:264-266
