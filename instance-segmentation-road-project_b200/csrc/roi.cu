@@ -65,7 +65,7 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
     // per-RoI tables, built once per RoI by ch+cw (coordinates) and ch*cw (pixels) threads so
     // that the streaming loop below carries no divisions and no 64-bit address arithmetic
     __shared__ float s_iny[kMaxCrop], s_inx[kMaxCrop];
-    __shared__ int4 s_poff[kMaxPix];          // float offsets of TL,TR,BL,BR inside this image's map
+    __shared__ uint4 s_poff[kMaxPix];         // BYTE offsets of TL,TR,BL,BR inside this image's map
     __shared__ float2 s_pw[kMaxPix];          // (lx, ly); lx < 0 marks "outside -> 0"
     __shared__ int s_mf[MLP_MAX_LEVELS], s_off[MLP_MAX_LEVELS + 1];
     if (threadIdx.x == 0) {
@@ -144,7 +144,7 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
             for (int p = threadIdx.x; p < npix; p += kRoiThreads) {
                 const int y = p / cw, x = p - y * cw;
                 const float in_y = s_iny[y], in_x = s_inx[x];
-                int4 o = make_int4(0, 0, 0, 0);
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
                 float2 w = make_float2(-1.0f, 0.0f);
                 // TF: in < 0 || in > size-1 -> extrapolation value; NaN counts as outside
                 if (in_y >= 0.0f && in_y <= hm1 && in_x >= 0.0f && in_x <= wm1) {
@@ -152,8 +152,8 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                     const int top = (int)fy, bot = (int)ceilf(in_y);
                     const int left = (int)fx, right = (int)ceilf(in_x);
                     w = make_float2(__fsub_rn(in_x, fx), __fsub_rn(in_y, fy));
-                    o = make_int4((top * Wf + left) * Cf, (top * Wf + right) * Cf,
-                                  (bot * Wf + left) * Cf, (bot * Wf + right) * Cf);
+                    o = make_uint4((unsigned)((top * Wf + left) * Cf) * 4u, (unsigned)((top * Wf + right) * Cf) * 4u,
+                                   (unsigned)((bot * Wf + left) * Cf) * 4u, (unsigned)((bot * Wf + right) * Cf) * 4u);
                 }
                 s_poff[p] = o;
                 s_pw[p] = w;
@@ -167,33 +167,33 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                 for (int c4 = lane; c4 < C4; c4 += 32) {
                     float4 tl[kPixUnroll], tr[kPixUnroll], bl[kPixUnroll], br[kPixUnroll];
                     float2 w[kPixUnroll];
-                    const float* base = img + c4 * 4;
+                    // 64-bit lane base + 32-bit unsigned byte offsets: two adds per address
+                    const char* base = reinterpret_cast<const char*>(img) + c4 * 16;
 #pragma unroll
                     for (int u = 0; u < kPixUnroll; ++u) {            // 16 loads in flight
                         const int p = min(p0 + u, npix - 1);
-                        const int4 o = s_poff[p];
+                        const uint4 o = s_poff[p];
                         w[u] = s_pw[p];
                         tl[u] = __ldg(reinterpret_cast<const float4*>(base + o.x));
                         tr[u] = __ldg(reinterpret_cast<const float4*>(base + o.y));
                         bl[u] = __ldg(reinterpret_cast<const float4*>(base + o.z));
                         br[u] = __ldg(reinterpret_cast<const float4*>(base + o.w));
                     }
+                    float4* obase = reinterpret_cast<float4*>(out + (int64_t)p0 * Cf) + c4;
 #pragma unroll
                     for (int u = 0; u < kPixUnroll; ++u) {
-                        if (p0 + u >= npix) continue;
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);  // extrapolation_value = 0
-                        if (w[u].x >= 0.0f) {
-                            const float lx = w[u].x, ly = w[u].y;
+                        const float lx = w[u].x, ly = w[u].y;
+                        const bool inside = lx >= 0.0f;               // else extrapolation_value = 0
+                        float4 r;
 #define MLP_LERP2(F)                                                                          \
     {                                                                                         \
         const float t_ = __fadd_rn(tl[u].F, __fmul_rn(__fsub_rn(tr[u].F, tl[u].F), lx));      \
         const float b_ = __fadd_rn(bl[u].F, __fmul_rn(__fsub_rn(br[u].F, bl[u].F), lx));      \
-        r.F = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly));                                \
+        r.F = inside ? __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly)) : 0.0f;                \
     }
-                            MLP_LERP2(x) MLP_LERP2(y) MLP_LERP2(z) MLP_LERP2(w)
+                        MLP_LERP2(x) MLP_LERP2(y) MLP_LERP2(z) MLP_LERP2(w)
 #undef MLP_LERP2
-                        }
-                        stg_stream_f4(reinterpret_cast<float4*>(out + (p0 + u) * Cf) + c4, r);
+                        if (p0 + u < npix) stg_stream_f4(obase + (size_t)u * C4, r);
                     }
                 }
             } else {
@@ -201,13 +201,13 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                 for (int u = 0; u < kPixUnroll; ++u) {
                     const int p = p0 + u;
                     if (p >= npix) continue;
-                    const int4 o = s_poff[p];
+                    const uint4 o = s_poff[p];
                     const float2 w = s_pw[p];
                     float* op = out + p * Cf;
                     for (int c = lane; c < Cf; c += 32) {
                         float r = 0.0f;
                         if (w.x >= 0.0f) {
-                            const float tl = img[o.x + c], tr = img[o.y + c], bl = img[o.z + c], br = img[o.w + c];
+                            const float tl = img[(o.x >> 2) + c], tr = img[(o.y >> 2) + c], bl = img[(o.z >> 2) + c], br = img[(o.w >> 2) + c];
                             const float t_ = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), w.x));
                             const float b_ = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), w.x));
                             r = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), w.y));
@@ -351,7 +351,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
         MLP_CHECK_ARG(mlp_aligned16(fmaps_dev[f]) && mlp_aligned16(crops_dev[f]),
                       "mlp_roi_align_run: level %d pointers must be 16-byte aligned", f);
         MLP_CHECK_ARG(fh[f] >= 1 && fw[f] >= 1, "mlp_roi_align_run: level %d map is %dx%d", f, fh[f], fw[f]);
-        MLP_CHECK_ARG((int64_t)fh[f] * fw[f] * channels < (1ll << 31) &&
+        MLP_CHECK_ARG((int64_t)fh[f] * fw[f] * channels < (1ll << 29) &&
                           (int64_t)crop_h * crop_w * channels < (1ll << 31),
                       "mlp_roi_align_run: level %d map too large for 32-bit offsets", f);
         lv.fmap[f] = fmaps_dev[f];
