@@ -229,6 +229,39 @@ int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_
                           int mask_w, int frame_h, int frame_w, int out_mode, void* out_dev,
                           mlp_stream_t stream);
 
+/* ---- fused halves of the path (what PostProcessPipeline enqueues) -------------------------
+ * The mask head (MaskSubNet, dense convolutions) sits between them and is not part of this
+ * library.  Same results as the chain of stage functions above, fewer kernels and no
+ * intermediate tensors:
+ *
+ * mlp_detect_align = a2-a10, the wiring of engine/retinamasklab.py:458-469: boxes decoded from
+ *   loc_dev + the prior config for candidates only; MaskDistribute and the RoIAlign plan are folded
+ *   into the cross-class NMS epilogue; then the RoIAlign run.  4 kernel launches.
+ *   Outputs are capacity buffers (K = nms_max_output_size rows per image): det_dev [B,K,6],
+ *   keep_dev [B,K,2] (may be NULL), counts_dev [B], m_dev [1], dist_dev [B,K,7],
+ *   level_counts_dev [L,B], level_m_dev [L+1], crops_dev[f] (prefix [B,Mf,ch,cw,Cf] of a
+ *   B*K*ch*cw*Cf buffer), roi_boxes_dev (prefix [B,R,6] of a B*L*K*6 buffer); L = max_k+1.
+ *
+ * mlp_trim_paste = a11-a14, engine/retinamasklab.py:615-616, :635-636 and
+ *   road_project/setup/serving.py:30: valid rows of roi_boxes_dev [B,R,6] ranked per image, int32
+ *   boxes of UpSampleOutput written to det_i32_dev [B,K,6] (capacity rows, padding rows as the
+ *   reference produces them), and the paste kernel reads every instance's class channel of
+ *   roi_masks_dev [B,R,mh,mw,C] directly (> 0.5 on the fly).  R is read from r_dev (i32 [1], e.g.
+ *   level_m_dev + L) when not NULL, else r_rows.  counts_dev [B], m_dev [1] = M;
+ *   out_dev [B,M,PH,PW] (uint8 or f32, M on device).  2 kernel launches.                     */
+int mlp_detect_align(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                     const float* cls_dev, int batch, int height, int width, int num_classes,
+                     const mlp_detection_params* params, int max_k, float base_size,
+                     const float* const* fmaps_dev, const int32_t* fh, const int32_t* fw, int channels,
+                     int crop_h, int crop_w, float* det_dev, int32_t* keep_dev, int32_t* counts_dev,
+                     int32_t* m_dev, float* dist_dev, int32_t* level_counts_dev, int32_t* level_m_dev,
+                     float* const* crops_dev, float* roi_boxes_dev, mlp_stream_t stream);
+int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const float* roi_masks_dev, int batch,
+                   int r_rows, const int32_t* r_dev, int mask_h, int mask_w, int num_classes,
+                   float ratio_h, float ratio_w, int k_rows, int frame_h, int frame_w, int out_mode,
+                   int32_t* det_i32_dev, int32_t* counts_dev, int32_t* m_dev, void* out_dev,
+                   mlp_stream_t stream);
+
 /* ---- a8: MoldBatch.call (engine/layers/misc.py:231-286) as a standalone operator ----
  * x_dev [K,row_elems] of 4-byte elements, batch_idx_dev i32 [K] (image id of each row).
  * Plan: counts_dev i32 [B], m_dev i32 [1] = max(1, max_b count).  Run: out_dev

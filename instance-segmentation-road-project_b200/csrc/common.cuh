@@ -188,3 +188,25 @@ __device__ __forceinline__ float4 restore_box(const float4 loc, const int4 pr) {
     o.w = __fmul_rn(exp_cr(loc.w), ph);
     return o;
 }
+
+// MaskDistribute (engine/layers/instance.py:53-62):
+// k = clip(floor(log((sqrt(w*h)+eps)/(base+eps)) / log(2)), 0, max_k); -1 where cx == -1.
+__device__ __forceinline__ float level_of(float cx, float w, float h, float base_eps, float max_k) {
+    float size = __fsqrt_rn(__fmul_rn(w, h));
+    float ratio = __fdiv_rn(__fadd_rn(size, 1e-7f), base_eps);
+    float dk = __fdiv_rn(log_cr(ratio), log_cr(2.0f));
+    float k = floorf(dk);
+    k = fminf(fmaxf(k, 0.0f), max_k);
+    return (cx == -1.0f) ? cx : k;
+}
+
+// UpSampleOutput box arithmetic (engine/layers/misc.py:179-186): cx,w scale with ratio[0]=PH/hs and
+// cy,h with ratio[1]=PW/ws (sic), tf.cast truncates toward zero.
+__device__ __forceinline__ void upsample_row(const float* r, float rh, float rw, int32_t* o) {
+    o[0] = __float2int_rz(__fmul_rn(r[0], rh));
+    o[1] = __float2int_rz(__fmul_rn(r[1], rw));
+    o[2] = __float2int_rz(__fmul_rn(r[2], rh));
+    o[3] = __float2int_rz(__fmul_rn(r[3], rw));
+    o[4] = __float2int_rz(r[4]);
+    o[5] = __float2int_rz(__fmul_rn(r[5], 100.0f));
+}

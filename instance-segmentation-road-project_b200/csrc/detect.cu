@@ -57,6 +57,19 @@ __device__ __forceinline__ float key_score(uint64_t key) {
     return float_from_ordered(~(uint32_t)(key >> 32));
 }
 
+// Optional fusion of MaskDistribute (a9) and the PyramidRoiAlign plan (a10) into the epilogue of
+// the cross-class NMS kernel: the kept rows of an image are still on chip there.
+struct FusedPlan {
+    int enabled;
+    int L;                  // pyramid levels (max_k + 1)
+    float base_eps;         // base_size + K.epsilon()
+    float max_k;
+    float* dist;            // [B,K,7]
+    int32_t* roi_src;       // [L,B,K] slot -> row
+    int32_t* level_counts;  // [L,B]
+    int32_t* level_m;       // [L+1]
+};
+
 // ------------------------------------------------------------------ K1 -------
 // cand_keys [G][cap] (G = B*C), cand_count [G].  Every CTA streams one contiguous slice of
 // cls_pred with 4 independent 128-bit loads in flight per thread.  Hits (0.2-2 % of the
@@ -80,10 +93,12 @@ __device__ __forceinline__ void k1_append(uint32_t e, float s, int N, int C, uin
 __global__ void __launch_bounds__(kK1Threads)
 threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, int C, float thr,
                          uint64_t* __restrict__ cand_keys, int32_t* __restrict__ cand_count,
-                         int64_t cap, int32_t* __restrict__ m_dev) {
+                         int64_t cap, int32_t* __restrict__ m_dev, int32_t* __restrict__ zero_ptr,
+                         int zero_n) {
     __shared__ uint2 s_q[kK1Queue];
     __shared__ int s_qn;
     if (blockIdx.x == 0 && threadIdx.x == 0 && m_dev) *m_dev = 1;
+    if (blockIdx.x == 0 && (int)threadIdx.x < zero_n) zero_ptr[threadIdx.x] = 0;   // level_m for the fused plan
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
     auto hit = [&](uint32_t e, float s) {
@@ -466,10 +481,10 @@ struct FetchCat {
     __device__ float4 operator()(uint32_t p) const { return box[p]; }
 };
 
-__global__ void __launch_bounds__(kCrossThreads)
+__global__ void __launch_bounds__(kCrossThreads, 1)
 nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D,
                        float* __restrict__ det, int32_t* __restrict__ keep,
-                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev) {
+                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
     __shared__ int s_order[256];
@@ -547,6 +562,44 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         counts[b] = kept;
         if (m_dev) atomicMax(m_dev, kept > 1 ? kept : 1);
     }
+    if (!F.enabled) return;
+    // ---- fused MaskDistribute + RoIAlign plan for this image
+    __shared__ int s_lvl[MLP_MAX_KEEP];
+    __syncthreads();                               // det_b rows written by other threads
+    const int B = gridDim.x;
+    for (int r = tid; r < max_out; r += blockDim.x) {
+        float* drow = F.dist + ((int64_t)b * max_out + r) * 7;
+        int lv = -1;
+        if (r < kept) {
+            const float* o = det_b + r * 6;
+            const float k = level_of(o[0], o[2], o[3], F.base_eps, F.max_k);
+            drow[0] = k;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) drow[q + 1] = o[q];
+            lv = (int)k;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) drow[q] = -1.0f;
+        }
+        s_lvl[r] = lv;
+    }
+    __syncthreads();
+    const int f = tid >> 5, lane = tid & 31;
+    if (f < F.L) {
+        int32_t* src = F.roi_src + ((int64_t)f * B + b) * max_out;
+        int base = 0;
+        for (int r0 = 0; r0 < kept; r0 += 32) {
+            const int r = r0 + lane;
+            const bool hit = (r < kept) && (s_lvl[r] == f);
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (hit) src[base + __popc(mask & ((1u << lane) - 1u))] = r;
+            base += __popc(mask);
+        }
+        if (lane == 0) {
+            F.level_counts[f * B + b] = base;
+            atomicMax(F.level_m + f, base > 1 ? base : 1);
+        }
+    }
 }
 
 // ------------------------------------------------------------ host side ------
@@ -598,7 +651,8 @@ int pick_sort_cap(int want_items, int max_out, size_t smem_limit) {
 int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int width,
                    const float* cls_dev, const float* boxes_or_loc_dev, int B, int64_t N, int C,
                    const mlp_detection_params* p, float* det_dev, int32_t* keep_dev,
-                   int32_t* counts_dev, int32_t* m_dev, cudaStream_t stream, const char* who) {
+                   int32_t* counts_dev, int32_t* m_dev, cudaStream_t stream, const char* who,
+                   const FusedPlan& fp) {
     MLP_CHECK_ARG(ctx && cls_dev && boxes_or_loc_dev && p && det_dev && counts_dev,
                   "%s: NULL argument", who);
     MLP_CHECK_ARG(B >= 1 && N >= 1 && C >= 1, "%s: bad shape B=%d N=%lld C=%d", who, B, (long long)N, C);
@@ -642,7 +696,9 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
         int grid = (int)(tiles < capb ? (tiles < 1 ? 1 : tiles) : capb);
         threshold_compact_kernel<<<grid, kK1Threads, 0, stream>>>(cls_dev, (uint32_t)total, (int)N, C,
                                                           p->min_confidence, D.cand_keys,
-                                                          D.cand_count, D.cap, m_dev);
+                                                          D.cand_count, D.cap, m_dev,
+                                                          fp.enabled ? fp.level_m : nullptr,
+                                                          fp.enabled ? fp.L + 1 : 0);
         MLP_LAUNCH_CHECK(ctx);
     }
     // K2: per (image,class) NMS.  512-thread CTAs, <= 72 KB smem -> 3 CTAs per SM, so all
@@ -675,7 +731,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nms_cross_class_kernel<<<B, kCrossThreads, smem, stream>>>(C, p->post_iou_threshold, max_out,
                                                                 sort_cap, D, det_dev, keep_dev,
-                                                                counts_dev, m_dev);
+                                                                counts_dev, m_dev, fp);
         MLP_LAUNCH_CHECK(ctx);
     }
     return MLP_OK;
@@ -688,9 +744,11 @@ extern "C" int mlp_detection_proposal(mlp_ctx* ctx, const float* cls_dev, const 
                                       const mlp_detection_params* params, float* det_dev,
                                       int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev,
                                       mlp_stream_t stream) {
+    FusedPlan none;
+    memset(&none, 0, sizeof(none));
     return detection_impl(ctx, nullptr, 0, 0, cls_dev, boxes_dev, batch, num_boxes, num_classes, params,
                           det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream,
-                          "mlp_detection_proposal");
+                          "mlp_detection_proposal", none);
 }
 
 extern "C" int mlp_detect_from_heads(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
@@ -704,7 +762,52 @@ extern "C" int mlp_detect_from_heads(mlp_ctx* ctx, const mlp_prior_config* prior
     }
     int64_t N = mlp_prior_count(prior, height, width);
     if (N < 0) return (int)N;
+    FusedPlan none;
+    memset(&none, 0, sizeof(none));
     return detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,
                           det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream,
-                          "mlp_detect_from_heads");
+                          "mlp_detect_from_heads", none);
+}
+
+// Fused first half of the path (a2-a10): detection with MaskDistribute and the RoIAlign plan folded
+// into the cross-class NMS epilogue, then the RoIAlign run: 4 kernels for the whole half.
+extern "C" int mlp_detect_align(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                                const float* cls_dev, int batch, int height, int width, int num_classes,
+                                const mlp_detection_params* params, int max_k, float base_size,
+                                const float* const* fmaps_dev, const int32_t* fh, const int32_t* fw,
+                                int channels, int crop_h, int crop_w, float* det_dev, int32_t* keep_dev,
+                                int32_t* counts_dev, int32_t* m_dev, float* dist_dev,
+                                int32_t* level_counts_dev, int32_t* level_m_dev,
+                                float* const* crops_dev, float* roi_boxes_dev, mlp_stream_t stream) {
+    if (!ctx || !prior || !params || !dist_dev || !level_counts_dev || !level_m_dev) {
+        mlp_set_error("mlp_detect_align: NULL argument");
+        return MLP_EINVAL;
+    }
+    MLP_CHECK_ARG(max_k >= 0 && max_k + 1 <= MLP_MAX_LEVELS, "mlp_detect_align: max_k=%d out of range", max_k);
+    MLP_CHECK_ARG(params->nms_max_output_size >= 1 && params->nms_max_output_size <= MLP_MAX_KEEP,
+                  "mlp_detect_align: nms_max_output_size out of range");
+    int64_t N = mlp_prior_count(prior, height, width);
+    if (N < 0) return (int)N;
+    const int L = max_k + 1, K = params->nms_max_output_size;
+    {
+        DeviceGuard g(ctx->device);
+        int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)L * batch * K * 4);
+        if (rc) return rc;
+    }
+    FusedPlan fp;
+    fp.enabled = 1;
+    fp.L = L;
+    fp.base_eps = (float)((double)base_size + 1e-7);
+    fp.max_k = (float)max_k;
+    fp.dist = dist_dev;
+    fp.roi_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_ROI]);
+    fp.level_counts = level_counts_dev;
+    fp.level_m = level_m_dev;
+    int rc = detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,
+                            det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream, "mlp_detect_align",
+                            fp);
+    if (rc) return rc;
+    return mlp_roi_align_run(ctx, fmaps_dev, fh, fw, L, channels, dist_dev, batch, K, K, m_dev,
+                             (float)height, (float)width, crop_h, crop_w, level_counts_dev, level_m_dev,
+                             crops_dev, roi_boxes_dev, stream);
 }

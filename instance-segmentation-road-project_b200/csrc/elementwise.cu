@@ -90,16 +90,6 @@ normalize_boxes_kernel(const float* __restrict__ boxes, int64_t rows, int row_st
 }
 
 // ---- a9 ----------------------------------------------------------------------
-// k = clip(floor(log((sqrt(w*h)+eps)/(base+eps)) / log(2)), 0, max_k); -1 where cx == -1.
-__device__ __forceinline__ float level_of(float cx, float w, float h, float base_eps, float max_k) {
-    float size = __fsqrt_rn(__fmul_rn(w, h));
-    float ratio = __fdiv_rn(__fadd_rn(size, 1e-7f), base_eps);
-    float dk = __fdiv_rn(log_cr(ratio), log_cr(2.0f));
-    float k = floorf(dk);
-    k = fminf(fmaxf(k, 0.0f), max_k);
-    return (cx == -1.0f) ? cx : k;
-}
-
 __global__ void __launch_bounds__(kThreads)
 mask_distribute_kernel(const float* __restrict__ det, int64_t rows, float base_eps, float max_k,
                        float* __restrict__ out) {
@@ -122,14 +112,7 @@ upsample_boxes_kernel(const float* __restrict__ det, int64_t rows, float rh, flo
                       int32_t* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < rows;
          i += (int64_t)gridDim.x * kThreads) {
-        const float* r = det + i * 6;
-        int32_t* o = out + i * 6;
-        o[0] = __float2int_rz(__fmul_rn(r[0], rh));     // cx * ratio[0]   (misc.py:180)
-        o[1] = __float2int_rz(__fmul_rn(r[1], rw));     // cy * ratio[1]
-        o[2] = __float2int_rz(__fmul_rn(r[2], rh));     // w  * ratio[0]
-        o[3] = __float2int_rz(__fmul_rn(r[3], rw));     // h  * ratio[1]
-        o[4] = __float2int_rz(r[4]);
-        o[5] = __float2int_rz(__fmul_rn(r[5], 100.0f));
+        upsample_row(det + i * 6, rh, rw, out + i * 6);
     }
 }
 

@@ -1,14 +1,16 @@
-// paste.cu — CropAndPadMask (a13) with the consumers' > 0.5 threshold (a14) fused in.
+// paste.cu — CropAndPadMask (a13) with the consumers' > 0.5 threshold (a14) fused in, and the
+// fused tail of the path (TrimInstances a11 + UpSampleOutput a12 + CropAndPadMask a13/a14).
 //
 // Reference: /root/reference/engine/layers/misc.py:358-401 (paste), :457 and :611-615
-// (binary mask = pasted > 0.5).  For every instance the reference resizes its 28x28
-// int mask to the clipped box with tf.image.resize(align_corners=True) (legacy bilinear,
-// restated in oracle/tf_ops.py) and zero-pads to the frame.  Output [B,M,PH,PW] is the
-// largest tensor of the whole path (16.8 GB as uint8 at B=32, M=1000, 512x1024), so this
-// kernel is a pure streaming-store kernel: every thread owns 16 output bytes (one 128-bit
-// st.global per 16 uint8 pixels / 4 float pixels), only pixels inside the clipped box
-// evaluate the two-stage lerp from the mask tile held in shared memory, everything else
-// is written as zero without touching memory for reads.
+// (binary mask = pasted > 0.5), :169-188 (UpSampleOutput), engine/layers/instance.py:258-277
+// (TrimInstances).  For every instance the reference resizes its 28x28 int mask to the clipped
+// box with tf.image.resize(align_corners=True) (legacy bilinear, restated in oracle/tf_ops.py)
+// and zero-pads to the frame.  Output [B,M,PH,PW] is the largest tensor of the whole path
+// (16.8 GB as uint8 at B=32, M=1000, 512x1024), so the paste kernel is a pure streaming-store
+// kernel: every thread-store is 128 bits (16 uint8 / 4 float pixels), only pixels inside the
+// clipped box evaluate the two-stage lerp from the mask tile held in shared memory, everything
+// else is written as zero without reading memory.
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -17,6 +19,7 @@ namespace {
 
 constexpr int kPasteThreads = 256;
 constexpr int kMaxTile = 64 * 64;         // mask_h * mask_w <= 4096
+constexpr int kTileRegs = 4;              // tile elements prefetched per thread (covers 32x32)
 
 // threshold = 50 if max(conf) > 50 else -100  (misc.py:366-369); conf = column 5.
 __global__ void __launch_bounds__(1024)
@@ -26,9 +29,9 @@ paste_threshold_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m
     int M = m_dev ? *m_dev : m_rows;
     if (M > m_rows) M = m_rows;
     if (m_stride == 0) m_stride = M;            // compact [B,M,..] layout, M known on device only
-    if (threadIdx.x == 0) s_max = INT32_MIN;
+    if (threadIdx.x == 0) s_max = INT_MIN;
     __syncthreads();
-    int mx = INT32_MIN;
+    int mx = INT_MIN;
     const int total = B * M;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int b = i / M, j = i - b * M;
@@ -44,6 +47,27 @@ paste_threshold_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m
     if (threadIdx.x == 0) *thr_out = (s_max > 50) ? 50 : -100;
 }
 
+// Where the per-instance mask tile and the batch-wide scalars come from.
+//   standalone layer : int32 masks [B,stride,mh*mw]; M from m_dev/m_rows; threshold from thr_dev
+//   fused tail       : the class channel of the mask head output roi_masks [B,R,mh*mw,C] picked
+//                      through the slot->row table of tail_prep_kernel and thresholded at 0.5 on
+//                      the fly (TrimInstances + UpSampleOutput never materialise); M and the
+//                      confidence threshold are reduced from the per-image counts / conf maxima.
+struct PasteSrc {
+    const int32_t* masks_i32;
+    const int32_t* m_dev;
+    const int32_t* thr_dev;
+    int fused;
+    const float* roi_masks;
+    const int32_t* tail_src;      // [B, m_stride] row of roi_masks, -1 = MoldBatch padding
+    const int32_t* r_dev;
+    int r_rows;
+    int C;
+    const int32_t* counts;        // [B] valid instances per image
+    const int32_t* confmax;       // [B] max int confidence of the valid rows (INT_MIN if none)
+    int32_t* m_out;               // [1] M written back for the host
+};
+
 struct PasteGeom {
     int xmin, xmax, ymin, ymax;
     float sy, sx;          // resize scales (in-1)/(out-1) or in/out
@@ -51,8 +75,8 @@ struct PasteGeom {
 };
 
 // misc.py:373-386: box = max(box,1) -> float; ceil(c -/+ s/2) -> int -> clip.
-__device__ __forceinline__ PasteGeom paste_geometry(const int32_t* row, int thr, int mh,
-                                                    int mw, int PH, int PW) {
+__device__ __forceinline__ PasteGeom paste_geometry(const int32_t* row, int thr, int mh, int mw, int PH,
+                                                    int PW) {
     PasteGeom g;
     const int conf = row[5];
     const float cx = (float)max(row[0], 1), cy = (float)max(row[1], 1);
@@ -84,38 +108,86 @@ __device__ __forceinline__ float paste_value(const float* __restrict__ tile, int
     return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
 }
 
-// One work item = (image b, slot j, band of `band_rows` frame rows).  Every thread-store is
-// 128 bits: 16 uint8 pixels (kU8) or 4 float pixels.  PW must be a multiple of that vector
-// width (host checks; the scalar kernel below handles everything else).  The band is written
-// in three phases so that no warp mixes cheap and expensive lanes:
-//   A  rows of the band above/below the clipped box: one contiguous byte range, flat
-//      unrolled zero stores, no index arithmetic;
+// M and the row-filter threshold for this launch (block-uniform, every warp computes it).
+__device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_rows, int& M, int& thr) {
+    if (!S.fused) {
+        M = S.m_dev ? *S.m_dev : m_rows;
+        if (M > m_rows) M = m_rows;
+        thr = *S.thr_dev;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    int mx = 0, mn = INT_MAX, cm = INT_MIN;
+    for (int i = lane; i < B; i += 32) {
+        const int c = S.counts[i];
+        mx = max(mx, c); mn = min(mn, c); cm = max(cm, S.confmax[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    }
+    M = max(mx, 1);
+    if (M > m_rows) M = m_rows;
+    if (mn < M) cm = max(cm, -100);        // MoldBatch padding rows carry conf = int(-1*100)
+    thr = (cm > 50) ? 50 : -100;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+}
+
+// Tile element i of instance (b, j) as the int the reference's mask tensor would hold.
+struct TileRef {
+    const int32_t* mi;     // standalone
+    const float* mf;       // fused (already offset to the class channel), stride C
+    int C;
+    bool valid;
+    __device__ __forceinline__ int at(int i) const {
+        if (mi) return __ldg(mi + i);
+        return valid ? (int)(__ldg(mf + (int64_t)i * C) > 0.5f) : 0;
+    }
+};
+
+__device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int m_stride, int px, int cls) {
+    TileRef t;
+    t.mi = nullptr; t.mf = nullptr; t.C = S.C; t.valid = false;
+    if (!S.fused) {
+        t.mi = S.masks_i32 + ((int64_t)b * m_stride + j) * px;
+        return t;
+    }
+    const int R = S.r_dev ? *S.r_dev : S.r_rows;
+    const int jsrc = S.tail_src[(int64_t)b * m_stride + j];
+    t.valid = jsrc >= 0 && cls >= 0 && cls < S.C;
+    t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * px * S.C + cls) : 0);
+    return t;
+}
+
+// One CTA per (instance, band) item, NOT a persistent grid: on B200 a write-only stream of many
+// short-lived CTAs, each owning one contiguous 64 KB band, reaches ~7.4 TB/s while persistent
+// CTAs top out near 6.3 TB/s (tools/write_bw.cu, profiles/write_bw_r01.txt).  The grid is sized
+// for the capacity m_rows; CTAs past the device-side M exit at once.  kU8: 16 pixels per
+// thread-store, else 4 float pixels; PW must be a multiple of that (host checks; the scalar
+// kernel handles the rest).  Three phases so that no warp mixes cheap and expensive lanes:
+//   A  rows of the band above/below the clipped box: contiguous, flat unrolled zero stores;
 //   B1 rows crossing the box: the 16-byte segments left and right of it (zeros);
-//   B2 the segments that intersect the box, flattened over ALL threads of the CTA: each
-//      evaluates the reference's two-stage lerp per pixel from the mask tile in smem.
+//   B2 the segments intersecting the box, flattened over ALL threads of the CTA: each evaluates
+//      the reference's two-stage lerp per pixel from the mask tile in shared memory.
 template <bool kU8>
 __global__ void __launch_bounds__(kPasteThreads)
-paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks, int B, int m_rows,
-             int m_stride, const int32_t* __restrict__ m_dev, const int32_t* __restrict__ thr_dev,
-             int mh, int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
+paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
+             int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
     constexpr int kVec = kU8 ? 16 : 4;
     constexpr int kPx = kU8 ? 1 : 4;               // bytes per pixel
     __shared__ float s_tile[kMaxTile];
-    int M = m_dev ? *m_dev : m_rows;
-    if (M > m_rows) M = m_rows;
-    if (m_stride == 0) m_stride = M;
-    const int thr = *thr_dev;
+    int M, thr;
+    paste_scalars(S, B, m_rows, M, thr);
+    if (m_stride == 0) m_stride = M;               // compact [B,M,..] input layout
     const int bands = (PH + band_rows - 1) / band_rows;
     const int64_t items = (int64_t)B * M * bands;
     const int spr = PW / kVec;                     // 16-byte segments per frame row
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const int px = mh * mw;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    // One CTA per (instance, band) item, NOT a persistent grid: on B200 a write-only stream
-    // of many short-lived CTAs, each owning one contiguous 32 KB band, reaches ~7.4 TB/s while
-    // persistent CTAs top out near 6.3 TB/s (tools/write_bw.cu, profiles/write_bw_r01.txt).
-    // The grid is sized for the capacity m_rows; CTAs past the device-side M exit at once.
-    constexpr int kTileRegs = 4;                   // covers tiles up to 32x32; larger ones load late
+
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int inst = (int)(item / bands);
         const int band = (int)(item - (int64_t)inst * bands);
@@ -133,15 +205,17 @@ paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks,
         int ya = y1, yb = y1;
         if (g.active) { ya = min(max(g.ymin, y0), y1); yb = min(max(g.ymax, ya), y1); }
         const bool touches = yb > ya;              // block-uniform
-        // the mask tile is only needed by phase B2: issue its loads now, park them in
-        // shared memory after the zero rows have been streamed out
+        // the mask tile is only needed by phase B2: issue its loads now, park them in shared
+        // memory after the zero rows have been streamed out
         int tile_regs[kTileRegs];
+        TileRef tref;
+        tref.mi = nullptr; tref.mf = nullptr; tref.C = 1; tref.valid = false;
         if (touches) {
-            const int32_t* m = masks + ((int64_t)b * m_stride + j) * mh * mw;
+            tref = tile_ref(S, b, j, m_stride, px, row[4]);
 #pragma unroll
             for (int q = 0; q < kTileRegs; ++q) {
                 const int i = tid + q * kPasteThreads;
-                tile_regs[q] = (i < mh * mw) ? __ldg(m + i) : 0;
+                tile_regs[q] = (i < px) ? tref.at(i) : 0;
             }
         }
         uint4* band_base = reinterpret_cast<uint4*>(static_cast<unsigned char*>(out) +
@@ -173,13 +247,10 @@ paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks,
 #pragma unroll
         for (int q = 0; q < kTileRegs; ++q) {
             const int i = tid + q * kPasteThreads;
-            if (i < mh * mw) s_tile[i] = (float)tile_regs[q];
+            if (i < px) s_tile[i] = (float)tile_regs[q];
         }
-        if (mh * mw > kTileRegs * kPasteThreads) {
-            const int32_t* m = masks + ((int64_t)b * m_stride + j) * mh * mw;
-            for (int i = tid + kTileRegs * kPasteThreads; i < mh * mw; i += kPasteThreads)
-                s_tile[i] = (float)__ldg(m + i);
-        }
+        for (int i = tid + kTileRegs * kPasteThreads; i < px; i += kPasteThreads)
+            s_tile[i] = (float)tref.at(i);
         const int sL = g.xmin / kVec;                       // first segment touching the box
         const int sR = (g.xmax + kVec - 1) / kVec;          // one past the last
         const int bw = sR - sL;
@@ -236,15 +307,13 @@ paste_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks,
 // Generic fall-back for frame widths that are not a multiple of the vector width.
 template <bool kU8>
 __global__ void __launch_bounds__(kPasteThreads)
-paste_scalar_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__ masks, int B,
-                    int m_rows, int m_stride, const int32_t* __restrict__ m_dev,
-                    const int32_t* __restrict__ thr_dev, int mh, int mw, int PH, int PW,
-                    void* __restrict__ out) {
+paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride,
+                    int mh, int mw, int PH, int PW, void* __restrict__ out) {
     __shared__ float s_tile[kMaxTile];
-    int M = m_dev ? *m_dev : m_rows;
-    if (M > m_rows) M = m_rows;
+    int M, thr;
+    paste_scalars(S, B, m_rows, M, thr);
     if (m_stride == 0) m_stride = M;
-    const int thr = *thr_dev;
+    const int px = mh * mw;
     const int64_t items = (int64_t)B * M;
     for (int64_t inst = blockIdx.x; inst < items; inst += gridDim.x) {
         const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
@@ -252,8 +321,8 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         __syncthreads();
         if (g.active) {
-            const int32_t* m = masks + ((int64_t)b * m_stride + j) * mh * mw;
-            for (int i = threadIdx.x; i < mh * mw; i += kPasteThreads) s_tile[i] = (float)m[i];
+            const TileRef tref = tile_ref(S, b, j, m_stride, px, row[4]);
+            for (int i = threadIdx.x; i < px; i += kPasteThreads) s_tile[i] = (float)tref.at(i);
         }
         __syncthreads();
         const int64_t npx = (int64_t)PH * PW;
@@ -273,6 +342,139 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const int32_t* __restrict__
     }
 }
 
+// ---- fused tail, step 1 -------------------------------------------------------------------
+// One CTA per image: ranks the rows of roi_boxes [B,R,6] whose class != -1 in order j
+// (TrimInstances), converts them to the int32 rows of UpSampleOutput, and records slot -> row so
+// that the paste kernel can pick every instance's own class channel straight from the mask head
+// output.  Capacity layout (K rows per image), so nothing here depends on M.
+constexpr int kPrepThreads = 256;
+
+__global__ void __launch_bounds__(kPrepThreads)
+tail_prep_kernel(const float* __restrict__ roi_boxes, int r_rows, const int32_t* __restrict__ r_dev, int K,
+                 float rh, float rw, int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
+                 int32_t* __restrict__ counts, int32_t* __restrict__ confmax) {
+    constexpr int kWarps = kPrepThreads / 32;
+    __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int R = r_dev ? *r_dev : r_rows;
+    if (R > r_rows) R = r_rows;
+    const float* rows = roi_boxes + (int64_t)b * R * 6;
+    const int seg = (R + kWarps - 1) / kWarps;
+    const int j0 = min(warp * seg, R), j1 = min(j0 + seg, R);
+    int cnt = 0;
+    for (int jb = j0; jb < j1; jb += 32) {
+        const int j = jb + lane;
+        const bool hit = (j < j1) && (rows[(int64_t)j * 6 + 4] != -1.0f);
+        cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int w = 0; w < kWarps; ++w) { s_base[w] = acc; acc += s_cnt[w]; }
+        s_base[kWarps] = acc;
+    }
+    __syncthreads();
+    const int total = min(s_base[kWarps], K);
+    int base = s_base[warp];
+    int cm = INT_MIN;
+    int32_t* drows = det_i32 + (int64_t)b * K * 6;
+    int32_t* src = tail_src + (int64_t)b * K;
+    for (int jb = j0; jb < j1; jb += 32) {
+        const int j = jb + lane;
+        const bool hit = (j < j1) && (rows[(int64_t)j * 6 + 4] != -1.0f);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            if (slot < K) {
+                float r[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) r[q] = rows[(int64_t)j * 6 + q];
+                int32_t o[6];
+                upsample_row(r, rh, rw, o);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) drows[slot * 6 + q] = o[q];
+                src[slot] = j;
+                cm = max(cm, o[5]);
+            }
+        }
+        base += __popc(mask);
+    }
+    for (int o = 16; o > 0; o >>= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if (lane == 0) s_cm[warp] = cm;
+    // MoldBatch padding rows (-1) after UpSampleOutput
+    {
+        const float m1[6] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
+        int32_t o[6];
+        upsample_row(m1, rh, rw, o);
+        for (int s = total + threadIdx.x; s < K; s += kPrepThreads) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) drows[s * 6 + q] = o[q];
+            src[s] = -1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int m = INT_MIN;
+        for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
+        counts[b] = total;
+        confmax[b] = m;
+    }
+}
+
+int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, int batch, int m_rows,
+                 int m_stride, int mask_h, int mask_w, int frame_h, int frame_w, int out_mode,
+                 void* out_dev, cudaStream_t st) {
+    ProfScope prof(ctx, MLP_ST_PASTE, st);
+    const bool u8 = out_mode == MLP_PASTE_U8;
+    const int vec = u8 ? 16 : 4;
+    int band_kb = 64;                                  // tuning knobs (tools/bench_paste.py)
+    int ctas_per_sm = 0;                               // 0: one CTA per item (default)
+    if (const char* e = getenv("MLP_PASTE_CTAS_PER_SM")) ctas_per_sm = atoi(e);
+    if (const char* e = getenv("MLP_PASTE_BAND_KB")) band_kb = atoi(e) > 0 ? atoi(e) : 64;
+    if (frame_w % vec == 0) {
+        int band_rows = (band_kb * 1024) / (frame_w * (u8 ? 1 : 4));
+        if (band_rows < 1) band_rows = 1;
+        if (band_rows > frame_h) band_rows = frame_h;
+        const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
+        int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
+        if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
+        if (u8)
+            paste_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
+                                                              mask_h, mask_w, frame_h, frame_w,
+                                                              band_rows, out_dev);
+        else
+            paste_kernel<false><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
+                                                               mask_h, mask_w, frame_h, frame_w,
+                                                               band_rows, out_dev);
+    } else {
+        const int64_t items = (int64_t)batch * m_rows;
+        const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
+        if (u8)
+            paste_scalar_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows,
+                                                                     m_stride, mask_h, mask_w, frame_h,
+                                                                     frame_w, out_dev);
+        else
+            paste_scalar_kernel<false><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows,
+                                                                      m_stride, mask_h, mask_w, frame_h,
+                                                                      frame_w, out_dev);
+    }
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
+
+int check_paste_args(const char* who, int batch, int mask_h, int mask_w, int frame_h, int frame_w,
+                     int out_mode, const void* out_dev) {
+    MLP_CHECK_ARG(batch >= 1, "%s: batch=%d", who, batch);
+    MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_h * mask_w <= kMaxTile,
+                  "%s: mask tile %dx%d too large (max %d elements)", who, mask_h, mask_w, kMaxTile);
+    MLP_CHECK_ARG(frame_h >= 1 && frame_w >= 1, "%s: frame %dx%d", who, frame_h, frame_w);
+    MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8, "%s: unknown out_mode %d", who,
+                  out_mode);
+    MLP_CHECK_ARG(mlp_aligned16(out_dev), "%s: out_dev must be 16-byte aligned", who);
+    return MLP_OK;
+}
+
 }  // namespace
 
 extern "C" int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev,
@@ -280,15 +482,11 @@ extern "C" int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev,
                                      const int32_t* m_dev, int mask_h, int mask_w, int frame_h,
                                      int frame_w, int out_mode, void* out_dev, mlp_stream_t stream) {
     MLP_CHECK_ARG(ctx && det_i32_dev && masks_i32_dev && out_dev, "mlp_crop_and_pad_mask: NULL argument");
-    MLP_CHECK_ARG(batch >= 1 && m_rows >= 1 && (m_stride >= m_rows || (m_stride == 0 && m_dev)),
-                  "mlp_crop_and_pad_mask: bad shape B=%d M=%d stride=%d", batch, m_rows, m_stride);
-    MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_h * mask_w <= kMaxTile,
-                  "mlp_crop_and_pad_mask: mask tile %dx%d too large (max %d elements)", mask_h, mask_w,
-                  kMaxTile);
-    MLP_CHECK_ARG(frame_h >= 1 && frame_w >= 1, "mlp_crop_and_pad_mask: frame %dx%d", frame_h, frame_w);
-    MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8,
-                  "mlp_crop_and_pad_mask: unknown out_mode %d", out_mode);
-    MLP_CHECK_ARG(mlp_aligned16(out_dev), "mlp_crop_and_pad_mask: out_dev must be 16-byte aligned");
+    MLP_CHECK_ARG(m_rows >= 1 && (m_stride >= m_rows || (m_stride == 0 && m_dev)),
+                  "mlp_crop_and_pad_mask: bad shape M=%d stride=%d", m_rows, m_stride);
+    int rc = check_paste_args("mlp_crop_and_pad_mask", batch, mask_h, mask_w, frame_h, frame_w, out_mode,
+                              out_dev);
+    if (rc) return rc;
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* thr_dev = ctx->ctr;        // ctr[0]: paste row-filter threshold
@@ -297,46 +495,52 @@ extern "C" int mlp_crop_and_pad_mask(mlp_ctx* ctx, const int32_t* det_i32_dev,
         paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
         MLP_LAUNCH_CHECK(ctx);
     }
-    ProfScope prof(ctx, MLP_ST_PASTE, st);
-    const bool u8 = out_mode == MLP_PASTE_U8;
-    const int vec = u8 ? 16 : 4;
-    // persistent grid: exactly the resident CTA count, each CTA streams one contiguous slab
-    int occ = 0;
-    if (u8) MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_kernel<true>, kPasteThreads, 0));
-    else MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, paste_kernel<false>, kPasteThreads, 0));
-    if (occ < 1) occ = 1;
-    int ctas_per_sm = 0;                          // 0: one CTA per item (default)
-    int band_kb = 64;
-    if (const char* e = getenv("MLP_PASTE_CTAS_PER_SM")) ctas_per_sm = atoi(e);     // tuning knobs
-    if (const char* e = getenv("MLP_PASTE_BAND_KB")) band_kb = atoi(e) > 0 ? atoi(e) : 64;
-    int grid = ctx->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : occ);
-    if (frame_w % vec == 0) {
-        // bands of ~64 KB of output keep >> grid items in flight even for one small batch
-        int band_rows = (band_kb * 1024) / (frame_w * (u8 ? 1 : 4));
-        if (band_rows < 1) band_rows = 1;
-        if (band_rows > frame_h) band_rows = frame_h;
-        if (ctas_per_sm <= 0) {
-            const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
-            grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-        }
-        if (u8)
-            paste_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, masks_i32_dev, batch, m_rows,
-                                                              m_stride, m_dev, thr_dev, mask_h, mask_w,
-                                                              frame_h, frame_w, band_rows, out_dev);
-        else
-            paste_kernel<false><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, masks_i32_dev, batch, m_rows,
-                                                               m_stride, m_dev, thr_dev, mask_h, mask_w,
-                                                               frame_h, frame_w, band_rows, out_dev);
-    } else {
-        if (u8)
-            paste_scalar_kernel<true><<<grid, kPasteThreads, 0, st>>>(
-                det_i32_dev, masks_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev, mask_h, mask_w,
-                frame_h, frame_w, out_dev);
-        else
-            paste_scalar_kernel<false><<<grid, kPasteThreads, 0, st>>>(
-                det_i32_dev, masks_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev, mask_h, mask_w,
-                frame_h, frame_w, out_dev);
+    PasteSrc S;
+    memset(&S, 0, sizeof(S));
+    S.masks_i32 = masks_i32_dev;
+    S.m_dev = m_dev;
+    S.thr_dev = thr_dev;
+    return paste_launch(ctx, det_i32_dev, S, batch, m_rows, m_stride, mask_h, mask_w, frame_h, frame_w,
+                        out_mode, out_dev, st);
+}
+
+// Fused second half of the path (a11-a14): two kernels.
+extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const float* roi_masks_dev,
+                              int batch, int r_rows, const int32_t* r_dev, int mask_h, int mask_w,
+                              int num_classes, float ratio_h, float ratio_w, int k_rows, int frame_h,
+                              int frame_w, int out_mode, int32_t* det_i32_dev, int32_t* counts_dev,
+                              int32_t* m_dev, void* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && roi_boxes_dev && roi_masks_dev && det_i32_dev && counts_dev && m_dev && out_dev,
+                  "mlp_trim_paste: NULL argument");
+    MLP_CHECK_ARG(r_rows >= 1 && k_rows >= 1 && num_classes >= 1, "mlp_trim_paste: bad shape R=%d K=%d C=%d",
+                  r_rows, k_rows, num_classes);
+    int rc = check_paste_args("mlp_trim_paste", batch, mask_h, mask_w, frame_h, frame_w, out_mode, out_dev);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // arena: tail_src [B,K] + confmax [B]
+    rc = mlp_ensure_scratch(ctx, MLP_ARENA_FUSED, ((int64_t)batch * k_rows + batch) * 4);
+    if (rc) return rc;
+    int32_t* tail_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_FUSED]);
+    int32_t* confmax = tail_src + (int64_t)batch * k_rows;
+    {
+        ProfScope prof(ctx, MLP_ST_TAIL_FUSED, st);
+        tail_prep_kernel<<<batch, kPrepThreads, 0, st>>>(roi_boxes_dev, r_rows, r_dev, k_rows, ratio_h,
+                                                        ratio_w, det_i32_dev, tail_src, counts_dev,
+                                                        confmax);
+        MLP_LAUNCH_CHECK(ctx);
     }
-    MLP_LAUNCH_CHECK(ctx);
-    return MLP_OK;
+    PasteSrc S;
+    memset(&S, 0, sizeof(S));
+    S.fused = 1;
+    S.roi_masks = roi_masks_dev;
+    S.tail_src = tail_src;
+    S.r_dev = r_dev;
+    S.r_rows = r_rows;
+    S.C = num_classes;
+    S.counts = counts_dev;
+    S.confmax = confmax;
+    S.m_out = m_dev;
+    return paste_launch(ctx, det_i32_dev, S, batch, k_rows, k_rows, mask_h, mask_w, frame_h, frame_w,
+                        out_mode, out_dev, st);
 }

@@ -33,6 +33,7 @@ class DetectionConfig:
     padding: str = "same"
     strict_batch: bool = True
     paste_output: str = "uint8"          # 'uint8' (binary, > 0.5 fused) or 'float32' (drop-in)
+    fused: bool = True                   # fused halves (6 kernels) vs the chain of stage kernels (13)
 
 
 @dataclass
@@ -133,6 +134,18 @@ class PostProcessPipeline:
             if tuple(f.shape) != (B, h, w, self.Cf):
                 raise rt.InvalidArgumentError(
                     rt.MLP_EINVAL, f"FPN map {tuple(f.shape)} != {(B, h, w, self.Cf)}")
+        if self.cfg.fused:
+            fmap_ptrs = (ctypes.c_void_p * L)(*[c.view(f, torch.float32).value for f in fmaps[:L]])
+            ch, cw = self.cfg.crop_size
+            rt.check(lib.mlp_detect_align(
+                c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
+                c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
+                ctypes.byref(self.params), int(self.cfg.max_k), float(self.cfg.base_size), fmap_ptrs,
+                self._fh, self._fw, self.Cf, int(ch), int(cw), c.view(self.det), c.view(self.keep),
+                c.view(self.counts), c.view(self.m_dev), c.view(self.dist), c.view(self.level_counts),
+                c.view(self.level_m), self._crop_ptrs, c.view(self.roi_boxes), st))
+            return AlignedRois(self.det, self.keep, self.counts, self.m_dev, self.dist,
+                               self.level_counts, self.level_m, self.crops, self.roi_boxes)
         rt.check(lib.mlp_detect_from_heads(
             c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
             c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
@@ -165,24 +178,34 @@ class PostProcessPipeline:
     def trim_and_paste(self, rois, roi_masks):
         """roi_masks: mask-head output, f32, dense [B,R,mh,mw,C] (R = rois.level_m[-1]; a flat
         buffer whose prefix has that layout is fine).  Enqueues a11-a14.  Returns
-        (det_i32 flat, pasted flat, m_dev): valid prefixes [B,M,6] and [B,M,PH,PW]."""
+        (det_i32 flat, pasted flat, m_dev): pasted has the valid prefix [B,M,PH,PW]; det_i32 is
+        [B,K,6] (capacity rows, fused path) or has the valid prefix [B,M,6] (stage path) - use
+        result_views() for reference-shaped tensors."""
         c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
         st = c.stream()
         mh, mw = self.cfg.mask_size
         r_cap = L * K
         r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
         masks_ptr = c.view(roi_masks, torch.float32)
+        ratio = (torch.tensor([float(self.frame_hw[0]), float(self.frame_hw[1])], dtype=torch.float32)
+                 / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
+        mode = rt.MLP_PASTE_U8 if self.cfg.paste_output == "uint8" else rt.MLP_PASTE_F32
+        self._compact_det = not self.cfg.fused
+        if self.cfg.fused:
+            rt.check(lib.mlp_trim_paste(
+                c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
+                float(ratio[0]), float(ratio[1]), K, self.frame_hw[0], self.frame_hw[1], mode,
+                c.view(self.det_i32), c.view(self.trim_counts), c.view(self.trim_m), c.view(self.pasted),
+                st))
+            return self.det_i32, self.pasted, self.trim_m
         rt.check(lib.mlp_trim_plan(c.handle, c.view(rois.roi_boxes), B, r_cap, r_dev,
                                    c.view(self.trim_counts), c.view(self.trim_m), st))
         rt.check(lib.mlp_trim_run(c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw,
                                   self.C, c.view(self.trim_m), c.view(self.trim_boxes),
                                   c.view(self.trim_masks), st))
-        ratio = (torch.tensor([float(self.frame_hw[0]), float(self.frame_hw[1])], dtype=torch.float32)
-                 / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
         rt.check(lib.mlp_upsample_output(
             c.handle, c.view(self.trim_boxes), B * K, float(ratio[0]), float(ratio[1]),
             c.view(self.det_i32), c.view(self.trim_masks), B * K * mh * mw, c.view(self.masks_i32), st))
-        mode = rt.MLP_PASTE_U8 if self.cfg.paste_output == "uint8" else rt.MLP_PASTE_F32
         rt.check(lib.mlp_crop_and_pad_mask(
             c.handle, c.view(self.det_i32), c.view(self.masks_i32), B, K, 0, c.view(self.trim_m), mh, mw,
             self.frame_hw[0], self.frame_hw[1], mode, c.view(self.pasted), st))
@@ -192,6 +215,9 @@ class PostProcessPipeline:
         """Reference-shaped views of the last trim_and_paste (one D2H of M)."""
         M = int(self.trim_m.item())
         PH, PW = self.frame_hw
-        det = self.det_i32[:self.B * M * 6].view(self.B, M, 6)
+        if getattr(self, "_compact_det", True):
+            det = self.det_i32[:self.B * M * 6].view(self.B, M, 6)
+        else:
+            det = self.det_i32.view(self.B, self.K, 6)[:, :M]
         masks = self.pasted[:self.B * M * PH * PW].view(self.B, M, PH, PW)
         return det, masks

@@ -87,6 +87,11 @@ SIGNATURES = {
     "mlp_trim_run": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "mlp_upsample_output": (_I, [_P, _P, _L, _F, _F, _P, _P, _L, _P, _P]),
     "mlp_crop_and_pad_mask": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "mlp_detect_align": (_I, [_P, ctypes.POINTER(PriorConfigC), _P, _P, _I, _I, _I, _I,
+                              ctypes.POINTER(DetectionParamsC), _I, _F, ctypes.POINTER(_P),
+                              ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _I, _I, _I,
+                              _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P]),
+    "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mlp_mold_batch_plan": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "mlp_mold_batch_run": (_I, [_P, _P, _P, _L, _L, _I, _I, _P, _P, _P]),
 }

@@ -343,8 +343,9 @@ def test_mold_batch(ml):
 
 
 # --------------------------------------------------------------- whole path ---
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("paste", ["uint8", "float32"])
-def test_pipeline_matches_oracle(ml, paste):
+def test_pipeline_matches_oracle(ml, paste, fused):
     B, H, W, C, Cf = 3, 128, 256, 4, 16
     PH, PW = 256, 512
     cfgp = synth.prior_config()
@@ -361,7 +362,7 @@ def test_pipeline_matches_oracle(ml, paste):
         return probs["m"]
 
     want = mo.full_path(loc, cls, fmaps, mask_head, cfgp, (H, W), (PH, PW), **kw)
-    cfg = ml.DetectionConfig(paste_output=paste, **kw)
+    cfg = ml.DetectionConfig(paste_output=paste, fused=fused, **kw)
     pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, Cf, B, cfg)
     rois = pipe.detect_and_align(dev(loc), dev(cls), [dev(f) for f in fmaps])
     crops, roi_boxes = pipe.roi_views(rois)
@@ -377,3 +378,38 @@ def test_pipeline_matches_oracle(ml, paste):
         assert np.array_equal(host(pasted), want["binary"])
     else:
         assert np.array_equal(host(pasted), want["pasted"])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_pipeline_no_detections_and_high_confidence(ml, fused):
+    """Both confidence-threshold branches of the paste through the pipeline: (a) nothing detected
+    anywhere (one all -1 slot per image), (b) confident detections (max conf > 50)."""
+    B, H, W, C, Cf = 2, 96, 160, 3, 8
+    cfgp = synth.prior_config()
+    N = synth.num_anchors(cfgp, H, W)
+    fmaps = synth.fpn_maps(B, H, W, Cf, seed=92)
+    kw = dict(min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+              nms_max_output_size=20, max_k=2, base_size=36)
+    for case in ("none", "confident"):
+        loc, cls = synth.head_tensors(B, N, C, mu=-5.0, seed=91)
+        if case == "none":
+            cls[:] = 0
+        else:
+            cls[:, ::97, :] = np.float32(0.93)
+        probs = {}
+
+        def mask_head(roi_fmaps, roi_boxes):
+            probs["m"] = synth.mask_probs(B, roi_boxes.shape[1], C, seed=93)
+            return probs["m"]
+
+        want = mo.full_path(loc, cls, fmaps, mask_head, cfgp, (H, W), (H, W), **kw)
+        pipe = ml.PostProcessPipeline(cfgp, (H, W), (H, W), C, Cf, B, ml.DetectionConfig(fused=fused, **kw))
+        rois = pipe.detect_and_align(dev(loc), dev(cls), [dev(f) for f in fmaps])
+        crops, roi_boxes = pipe.roi_views(rois)
+        assert np.array_equal(host(roi_boxes), want["roi_boxes"])
+        pipe.trim_and_paste(rois, dev(probs["m"]))
+        det_i, pasted = pipe.result_views()
+        assert np.array_equal(host(det_i), want["det_i"])
+        assert np.array_equal(host(pasted), want["binary"])
+        if case == "confident":
+            assert want["det_i"][..., 5].max() > 50 and want["binary"].sum() > 0
