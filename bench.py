@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=2,
+                    help="independent pipelines/streams per GPU; consecutive batches alternate between them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
@@ -231,6 +233,12 @@ def run_ours(args, wl):
     pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local)
     ctx = pipe.ctx
     K = pipe.K
+    # independent per-GPU streams (north star): batch i runs on pipeline/stream i % S, so the
+    # latency-bound NMS kernels of one batch overlap the bandwidth-bound RoIAlign/paste of another
+    S = max(1, args.streams)
+    pipes = [pipe] + [ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local,
+                                             private_context=True) for _ in range(S - 1)]
+    streams = [torch.cuda.Stream() for _ in range(S)]
 
     # host (pinned) copies for the end-to-end leg, device copies for the kernel-only leg
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -248,9 +256,22 @@ def run_ours(args, wl):
     counts = rois.counts.cpu().numpy()
     torch.cuda.synchronize()
 
+    state = {"i": 0}
+
     def step():
-        r = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
-        pipe.trim_and_paste(r, d_masks)
+        k = state["i"] % S
+        state["i"] += 1
+        with torch.cuda.stream(streams[k]):
+            r = pipes[k].detect_and_align(d_loc, d_cls, d_fmaps)
+            pipes[k].trim_and_paste(r, d_masks)
+
+    def join_streams():
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
+
+    def fork_streams():
+        for s_ in streams:
+            s_.wait_stream(torch.cuda.current_stream())
 
     gathered = None
     if world > 1:
@@ -262,26 +283,35 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    fork_streams()
+    for _ in range(max(args.warmup, 3) * S):
         step()
+    join_streams()
     barrier()
-    launches0 = ctx.launch_count()
-    ctx.profile(True)
+    launches0 = sum(p.ctx.launch_count() for p in pipes)
+    for p in pipes:
+        p.ctx.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         ev0.record()
+        fork_streams()
         for _ in range(args.steps):
             step()
+        join_streams()
         if world > 1:           # the one collective of the path: gather detections at the end
             dist.all_gather(gathered, pipe.det)
             dist.all_gather(gathered_counts, pipe.counts)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
-    stages = ctx.profile_read()
-    ctx.profile(False)
+    launches = sum(p.ctx.launch_count() for p in pipes) - launches0
+    stages = {}
+    for p in pipes:
+        for k_, (t_, n_) in p.ctx.profile_read().items():
+            a_, b_ = stages.get(k_, (0.0, 0))
+            stages[k_] = (a_ + t_, b_ + n_)
+        p.ctx.profile(False)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,7 +339,10 @@ def run_ours(args, wl):
                 "whole_step": {"algorithmic_bytes": step_bytes,
                                "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()}}
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+                "note": ("stage times are CUDA-event brackets on each stream; with streams_per_gpu > 1 "
+                         "kernels of different batches overlap, so brackets include time shared with "
+                         "the other stream" if S > 1 else "single stream")}
 
     # ---- end to end through the public API with host buffers
     e2e = None

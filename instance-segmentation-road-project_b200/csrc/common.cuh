@@ -128,6 +128,34 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
                  : "memory");
 }
 
+// Packed f32x2 arithmetic (Blackwell FADD2): two IEEE-rounded float adds per instruction.  Only
+// add/sub are used packed - ptxas contracts a packed multiply feeding a packed add into FFMA2
+// even with .rn and -fmad=false, which would change the rounding, so multiplies stay scalar.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2_rn(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a + (b - a) * l on two lanes, every operation rounded separately (TF / NumPy order)
+__device__ __forceinline__ uint64_t lerp2_rn(uint64_t a, uint64_t b, float l) {
+    float d0, d1;
+    unpack2(sub2_rn(b, a), d0, d1);
+    return add2_rn(a, pack2(__fmul_rn(d0, l), __fmul_rn(d1, l)));
+}
+
 // Correctly rounded float32 exp / log (evaluate in fp64, round once).  The oracle
 // does the same (oracle/masklab_oracle.py exp_f32/log_f32), which makes the
 // decoded boxes and FPN levels agree bit for bit between CPU and GPU.

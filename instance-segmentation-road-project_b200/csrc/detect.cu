@@ -12,6 +12,8 @@
 // Reference: /root/reference/engine/layers/detection.py:482-567; TF NonMaxSuppressionV3
 // semantics restated in oracle/tf_ops.py.  Compiled with -fmad=false: IoU and decode
 // round every multiply/add separately so kept indices match the CPU oracle bit for bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -693,6 +695,10 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
         int occ = 0;
         MLP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, threshold_compact_kernel, kK1Threads, 0));
         int64_t capb = (int64_t)ctx->sm_count * (occ < 1 ? 1 : occ);      // one resident wave
+        if (const char* e = getenv("MLP_K1_TILES_PER_CTA")) {             // tuning knob
+            const int t = atoi(e);
+            if (t > 0) capb = (tiles + t - 1) / t;
+        }
         int grid = (int)(tiles < capb ? (tiles < 1 ? 1 : tiles) : capb);
         threshold_compact_kernel<<<grid, kK1Threads, 0, stream>>>(cls_dev, (uint32_t)total, (int)N, C,
                                                           p->min_confidence, D.cand_keys,

@@ -184,15 +184,16 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                     for (int u = 0; u < kPixUnroll; ++u) {
                         const float lx = w[u].x, ly = w[u].y;
                         const bool inside = lx >= 0.0f;               // else extrapolation_value = 0
+                        // bilinear: top/bottom lerp in x, then lerp in y (crop_and_resize order),
+                        // adds packed two channels per instruction
+                        const uint64_t t0 = lerp2_rn(pack2(tl[u].x, tl[u].y), pack2(tr[u].x, tr[u].y), lx);
+                        const uint64_t t1 = lerp2_rn(pack2(tl[u].z, tl[u].w), pack2(tr[u].z, tr[u].w), lx);
+                        const uint64_t b0 = lerp2_rn(pack2(bl[u].x, bl[u].y), pack2(br[u].x, br[u].y), lx);
+                        const uint64_t b1 = lerp2_rn(pack2(bl[u].z, bl[u].w), pack2(br[u].z, br[u].w), lx);
                         float4 r;
-#define MLP_LERP2(F)                                                                          \
-    {                                                                                         \
-        const float t_ = __fadd_rn(tl[u].F, __fmul_rn(__fsub_rn(tr[u].F, tl[u].F), lx));      \
-        const float b_ = __fadd_rn(bl[u].F, __fmul_rn(__fsub_rn(br[u].F, bl[u].F), lx));      \
-        r.F = inside ? __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), ly)) : 0.0f;                \
-    }
-                        MLP_LERP2(x) MLP_LERP2(y) MLP_LERP2(z) MLP_LERP2(w)
-#undef MLP_LERP2
+                        unpack2(lerp2_rn(t0, b0, ly), r.x, r.y);
+                        unpack2(lerp2_rn(t1, b1, ly), r.z, r.w);
+                        if (!inside) r = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p0 + u < npix) stg_stream_f4(obase + (size_t)u * C4, r);
                     }
                 }

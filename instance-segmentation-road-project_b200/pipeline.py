@@ -57,7 +57,7 @@ class AlignedRois:
 
 class PostProcessPipeline:
     def __init__(self, prior, image_hw, frame_hw, num_classes, fpn_channels, batch,
-                 config=None, device=None):
+                 config=None, device=None, private_context=False):
         self.cfg = config or DetectionConfig()
         self.prior = prior if isinstance(prior, PriorBoxes) else PriorBoxes(**prior)
         self.image_hw = (int(image_hw[0]), int(image_hw[1]))
@@ -65,7 +65,13 @@ class PostProcessPipeline:
         self.C = int(num_classes)
         self.Cf = int(fpn_channels)
         self.B = int(batch)
-        self.ctx = rt.Context.get(device)
+        # a context owns scratch and must not be shared between streams: pipelines that run
+        # concurrently on different streams each take a private one
+        if private_context:
+            dev = rt.Context.get(device).device
+            self.ctx = rt.Context(dev)
+        else:
+            self.ctx = rt.Context.get(device)
         self.lib = self.ctx.lib
         self.L = int(self.cfg.max_k) + 1
         self.K = int(self.cfg.nms_max_output_size)
