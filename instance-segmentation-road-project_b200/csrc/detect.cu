@@ -80,6 +80,7 @@ struct FusedPlan {
 // no 64-bit divisions and almost no divergence.
 constexpr int kK1Threads = 256;
 constexpr int kK1Queue = 2048;
+constexpr int kK1Groups = 512;           // (image,class) groups a CTA slice may touch on the fast flush path
 
 __device__ __forceinline__ void k1_append(uint32_t e, float s, int N, int C, uint64_t* cand_keys,
                                           int32_t* cand_count, int64_t cap) {
@@ -98,15 +99,56 @@ threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, i
                          int64_t cap, int32_t* __restrict__ m_dev, int32_t* __restrict__ zero_ptr,
                          int zero_n) {
     __shared__ uint2 s_q[kK1Queue];
+    __shared__ int s_hist[kK1Groups], s_cursor[kK1Groups], s_gbase[kK1Groups];
     __shared__ int s_qn;
     if (blockIdx.x == 0 && threadIdx.x == 0 && m_dev) *m_dev = 1;
     if (blockIdx.x == 0 && (int)threadIdx.x < zero_n) zero_ptr[threadIdx.x] = 0;   // level_m for the fused plan
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
-    auto hit = [&](uint32_t e, float s) {
+    const int lane = threadIdx.x & 31;
+    // Warp-aggregated append of one tile's hits: every lane holds the 16-bit mask of its 16
+    // scores; one shuffle scan + ONE shared atomic per warp reserves queue slots for all of them.
+    auto flush_tile = [&](const float4 (&v)[4], uint32_t base) {
+        uint32_t mask = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            mask |= (uint32_t)(v[u].x >= thr) << (4 * u);
+            mask |= (uint32_t)(v[u].y >= thr) << (4 * u + 1);
+            mask |= (uint32_t)(v[u].z >= thr) << (4 * u + 2);
+            mask |= (uint32_t)(v[u].w >= thr) << (4 * u + 3);
+        }
+        if (__ballot_sync(0xffffffffu, mask != 0) == 0) return;        // common: no hit in 512 scores
+        const int n = __popc(mask);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int qbase = 0;
+        if (lane == 31) qbase = atomicAdd(&s_qn, total);
+        qbase = __shfl_sync(0xffffffffu, qbase, 31);
+        int pos = qbase + incl - n;
+        if (mask == 0) return;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float comp[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((mask >> (4 * u + c)) & 1u) {
+                    const uint32_t e = ((base + u * kK1Threads + threadIdx.x) << 2) + c;
+                    if (pos < kK1Queue) s_q[pos] = make_uint2(e, __float_as_uint(comp[c]));
+                    else k1_append(e, comp[c], N, C, cand_keys, cand_count, cap);   // queue full
+                    ++pos;
+                }
+            }
+        }
+    };
+    auto hit = [&](uint32_t e, float sc) {                             // scalar tail only
         const int pos = atomicAdd(&s_qn, 1);
-        if (pos < kK1Queue) s_q[pos] = make_uint2(e, __float_as_uint(s));
-        else k1_append(e, s, N, C, cand_keys, cand_count, cap);      // queue full: slow path
+        if (pos < kK1Queue) s_q[pos] = make_uint2(e, __float_as_uint(sc));
+        else k1_append(e, sc, N, C, cand_keys, cand_count, cap);
     };
     const uint32_t total4 = total >> 2;
     const float4* cls4 = reinterpret_cast<const float4*>(cls);
@@ -118,6 +160,7 @@ threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, i
     uint32_t v0 = blockIdx.x * tiles_per_cta * tile;
     uint32_t v1 = v0 + tiles_per_cta * tile;
     if (v1 > total4) v1 = total4;
+    if (v0 > v1) v0 = v1;
     // software pipeline: the next tile's four 128-bit loads are in flight while the current
     // tile is compared against the threshold
     float4 cur[4], nxt[4];
@@ -131,14 +174,7 @@ threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, i
     if (v0 < v1) load_tile(cur, v0);
     for (uint32_t base = v0; base < v1; base += tile) {
         if (base + tile < v1) load_tile(nxt, base + tile);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t e = (base + u * kK1Threads + threadIdx.x) << 2;
-            if (cur[u].x >= thr) hit(e, cur[u].x);
-            if (cur[u].y >= thr) hit(e + 1, cur[u].y);
-            if (cur[u].z >= thr) hit(e + 2, cur[u].z);
-            if (cur[u].w >= thr) hit(e + 3, cur[u].w);
-        }
+        flush_tile(cur, base);
 #pragma unroll
         for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
     }
@@ -150,8 +186,45 @@ threshold_compact_kernel(const float* __restrict__ cls, uint32_t total, int N, i
     }
     __syncthreads();
     const int qn = s_qn < kK1Queue ? s_qn : kK1Queue;
-    for (int i = threadIdx.x; i < qn; i += kK1Threads)
-        k1_append(s_q[i].x, __uint_as_float(s_q[i].y), N, C, cand_keys, cand_count, cap);
+    // Flush: a CTA's slice covers at most a couple of images, i.e. a handful of (image,class)
+    // groups.  Hits are counted per group in shared memory first so that each CTA issues ONE
+    // global atomicAdd per group instead of one per hit: 626 k same-address atomics on 192
+    // counters (stress config) serialise in L2 and used to cost more than the streaming pass.
+    const uint32_t NC = (uint32_t)N * (uint32_t)C;
+    const uint32_t e_first = v0 << 2;
+    const uint32_t e_last = (blockIdx.x == gridDim.x - 1) ? total - 1 : (v1 > v0 ? (v1 << 2) - 1 : e_first);
+    const uint32_t b_first = e_first / NC;
+    const uint32_t nb = e_last / NC - b_first + 1;
+    if (qn > 0 && nb * (uint32_t)C <= (uint32_t)kK1Groups) {
+        const int ng = (int)nb * C;
+        for (int i = threadIdx.x; i < ng; i += kK1Threads) { s_hist[i] = 0; s_cursor[i] = 0; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < qn; i += kK1Threads) {
+            const uint32_t e = s_q[i].x;
+            const uint32_t bn = e / (uint32_t)C;
+            const int c = (int)(e - bn * (uint32_t)C);
+            const int gl = (int)(bn / (uint32_t)N - b_first) * C + c;
+            atomicAdd(&s_hist[gl], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < ng; i += kK1Threads)
+            if (s_hist[i] > 0) s_gbase[i] = atomicAdd(cand_count + (int)b_first * C + i, s_hist[i]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < qn; i += kK1Threads) {
+            const uint32_t e = s_q[i].x;
+            const uint32_t bn = e / (uint32_t)C;
+            const int c = (int)(e - bn * (uint32_t)C);
+            const uint32_t b = bn / (uint32_t)N;
+            const uint32_t n = bn - b * (uint32_t)N;
+            const int gl = (int)(b - b_first) * C + c;
+            const int pos = s_gbase[gl] + atomicAdd(&s_cursor[gl], 1);
+            if (pos < cap)
+                cand_keys[(int64_t)((int)b * C + c) * cap + pos] = make_key(__uint_as_float(s_q[i].y), n);
+        }
+    } else {
+        for (int i = threadIdx.x; i < qn; i += kK1Threads)
+            k1_append(s_q[i].x, __uint_as_float(s_q[i].y), N, C, cand_keys, cand_count, cap);
+    }
 }
 
 // --------------------------------------------------------- sort helpers ------
