@@ -348,9 +348,16 @@ def run_ours(args, wl):
     paste_bytes = B * M * PH * PW
     achieved = (paste_bytes / (paste_ms / paste_n * 1e-3) / 1e9) if paste_n else None
     step_bytes = algorithmic_bytes(wl, N, M)
+    traffic = None                                   # dram read+write of the paste kernel from the committed
+    try:                                             # ncu --set full capture (cfg2 only), per launch
+        if args.workload == "cfg2":
+            with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"].get("paste_kernel<1>")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "paste_kernel<uint8> (CropAndPadMask + >0.5)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_kind": peak_kind, "bytes_per_launch": paste_bytes,
                 "avg_launch_ms": (paste_ms / paste_n) if paste_n else None,
                 "whole_step": {"algorithmic_bytes": step_bytes,
