@@ -60,6 +60,7 @@ struct PasteSrc {
     int fused;
     const float* roi_masks;
     const int32_t* tail_src;      // [B, m_stride] row of roi_masks, -1 = MoldBatch padding
+    const uint32_t* tail_bits;    // [B, m_stride, mh] bit rows of the thresholded class channel (mw <= 32), or NULL
     const int32_t* r_dev;
     int r_rows;
     int C;
@@ -138,17 +139,23 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
 struct TileRef {
     const int32_t* mi;     // standalone
     const float* mf;       // fused (already offset to the class channel), stride C
-    int C;
+    const uint32_t* bits;  // fused, pre-thresholded bit rows
+    int C, mw;
     bool valid;
     __device__ __forceinline__ int at(int i) const {
         if (mi) return __ldg(mi + i);
+        if (bits) {
+            const int y = i / mw;
+            return valid ? (int)((__ldg(bits + y) >> (i - y * mw)) & 1u) : 0;
+        }
         return valid ? (int)(__ldg(mf + (int64_t)i * C) > 0.5f) : 0;
     }
 };
 
-__device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int m_stride, int px, int cls) {
+__device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int m_stride, int px, int cls,
+                                            int mh, int mw) {
     TileRef t;
-    t.mi = nullptr; t.mf = nullptr; t.C = S.C; t.valid = false;
+    t.mi = nullptr; t.mf = nullptr; t.bits = nullptr; t.C = S.C; t.mw = mw; t.valid = false;
     if (!S.fused) {
         t.mi = S.masks_i32 + ((int64_t)b * m_stride + j) * px;
         return t;
@@ -156,6 +163,7 @@ __device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int
     const int R = S.r_dev ? *S.r_dev : S.r_rows;
     const int jsrc = S.tail_src[(int64_t)b * m_stride + j];
     t.valid = jsrc >= 0 && cls >= 0 && cls < S.C;
+    if (S.tail_bits) t.bits = S.tail_bits + ((int64_t)b * m_stride + j) * mh;
     t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * px * S.C + cls) : 0);
     return t;
 }
@@ -209,9 +217,9 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         // memory after the zero rows have been streamed out
         int tile_regs[kTileRegs];
         TileRef tref;
-        tref.mi = nullptr; tref.mf = nullptr; tref.C = 1; tref.valid = false;
+        tref.mi = nullptr; tref.mf = nullptr; tref.bits = nullptr; tref.C = 1; tref.mw = mw; tref.valid = false;
         if (touches) {
-            tref = tile_ref(S, b, j, m_stride, px, row[4]);
+            tref = tile_ref(S, b, j, m_stride, px, row[4], mh, mw);
 #pragma unroll
             for (int q = 0; q < kTileRegs; ++q) {
                 const int i = tid + q * kPasteThreads;
@@ -321,7 +329,7 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         __syncthreads();
         if (g.active) {
-            const TileRef tref = tile_ref(S, b, j, m_stride, px, row[4]);
+            const TileRef tref = tile_ref(S, b, j, m_stride, px, row[4], mh, mw);
             for (int i = threadIdx.x; i < px; i += kPasteThreads) s_tile[i] = (float)tref.at(i);
         }
         __syncthreads();
@@ -348,14 +356,18 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
 // that the paste kernel can pick every instance's own class channel straight from the mask head
 // output.  Capacity layout (K rows per image), so nothing here depends on M.
 constexpr int kPrepThreads = 256;
+constexpr int kPrepParts = 8;             // CTAs per image (each repeats the cheap scan, owns 1/8 of the slots)
 
 __global__ void __launch_bounds__(kPrepThreads)
-tail_prep_kernel(const float* __restrict__ roi_boxes, int r_rows, const int32_t* __restrict__ r_dev, int K,
-                 float rh, float rw, int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
-                 int32_t* __restrict__ counts, int32_t* __restrict__ confmax) {
+tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ roi_masks, int r_rows,
+                 const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, float rh, float rw,
+                 int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
+                 uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
+                 int32_t* __restrict__ confmax) {
     constexpr int kWarps = kPrepThreads / 32;
     __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int R = r_dev ? *r_dev : r_rows;
     if (R > r_rows) R = r_rows;
     const float* rows = roi_boxes + (int64_t)b * R * 6;
@@ -392,10 +404,12 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, int r_rows, const int32_t*
                 for (int q = 0; q < 6; ++q) r[q] = rows[(int64_t)j * 6 + q];
                 int32_t o[6];
                 upsample_row(r, rh, rw, o);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) drows[slot * 6 + q] = o[q];
-                src[slot] = j;
                 cm = max(cm, o[5]);
+                if (slot % parts == part) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) drows[slot * 6 + q] = o[q];
+                    src[slot] = j;
+                }
             }
         }
         base += __popc(mask);
@@ -407,18 +421,42 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, int r_rows, const int32_t*
         const float m1[6] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
         int32_t o[6];
         upsample_row(m1, rh, rw, o);
-        for (int s = total + threadIdx.x; s < K; s += kPrepThreads) {
+        for (int s = total + part + parts * (int)threadIdx.x; s < K; s += parts * kPrepThreads) {
 #pragma unroll
             for (int q = 0; q < 6; ++q) drows[s * 6 + q] = o[q];
             src[s] = -1;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncthreads();                      // src[] / drows[] of this CTA's slots are written
+    if (threadIdx.x == 0 && part == 0) {
         int m = INT_MIN;
         for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
         counts[b] = total;
         confmax[b] = m;
+    }
+    // bit tiles of this CTA's slots: one warp per slot, lane = mask column, ballot per mask row
+    if (tail_bits == nullptr) return;
+    const int px = mh * mw;
+    for (int s = part + parts * warp; s < total; s += parts * kWarps) {
+        const int j = src[s];
+        const int cls = drows[s * 6 + 4];
+        uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
+        const bool ok = cls >= 0 && cls < C;
+        const float* m = roi_masks + (((int64_t)b * R + j) * px) * C + (ok ? cls : 0);
+        // all mask rows of the slot in flight at once (one DRAM round trip per 32 rows)
+        for (int y0 = 0; y0 < mh; y0 += 32) {
+            float v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const int y = y0 + u;
+                v[u] = (ok && y < mh && lane < mw) ? __ldg(m + (int64_t)(y * mw + lane) * C) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const unsigned w = __ballot_sync(0xffffffffu, v[u] > 0.5f);
+                if (lane == 0 && y0 + u < mh) out[y0 + u] = w;
+            }
+        }
     }
 }
 
@@ -518,16 +556,19 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     if (rc) return rc;
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // arena: tail_src [B,K] + confmax [B]
-    rc = mlp_ensure_scratch(ctx, MLP_ARENA_FUSED, ((int64_t)batch * k_rows + batch) * 4);
+    // arena: tail_src [B,K] + confmax [B] + bit tiles [B,K,mh] (mask rows of <= 32 columns)
+    const bool use_bits = mask_w <= 32;
+    rc = mlp_ensure_scratch(ctx, MLP_ARENA_FUSED,
+                            ((int64_t)batch * k_rows + batch + (use_bits ? (int64_t)batch * k_rows * mask_h : 0)) * 4);
     if (rc) return rc;
     int32_t* tail_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_FUSED]);
     int32_t* confmax = tail_src + (int64_t)batch * k_rows;
+    uint32_t* tail_bits = use_bits ? reinterpret_cast<uint32_t*>(confmax + batch) : nullptr;
     {
         ProfScope prof(ctx, MLP_ST_TAIL_FUSED, st);
-        tail_prep_kernel<<<batch, kPrepThreads, 0, st>>>(roi_boxes_dev, r_rows, r_dev, k_rows, ratio_h,
-                                                        ratio_w, det_i32_dev, tail_src, counts_dev,
-                                                        confmax);
+        tail_prep_kernel<<<dim3(batch, kPrepParts), kPrepThreads, 0, st>>>(
+            roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, ratio_h,
+            ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax);
         MLP_LAUNCH_CHECK(ctx);
     }
     PasteSrc S;
@@ -535,6 +576,7 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     S.fused = 1;
     S.roi_masks = roi_masks_dev;
     S.tail_src = tail_src;
+    S.tail_bits = tail_bits;
     S.r_dev = r_dev;
     S.r_rows = r_rows;
     S.C = num_classes;

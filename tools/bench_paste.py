@@ -11,6 +11,10 @@ B, M, PH, PW = int(os.environ.get("B", 32)), int(os.environ.get("M", 100)), 512,
 det = synth.detections(B, M, 5, PH, PW, seed=1)
 masks = synth.mask_probs(B, M, 1, seed=2)[..., 0]
 det_i, mask_i = mo.upsample_output(det, masks, (PH, PW), (PH, PW))
+if os.environ.get("ZERO"):
+    det_i[..., 0] = PW + 1000      # every box off-frame: the kernel degenerates to a pure zero fill
+if os.environ.get("SMALL"):
+    det_i[..., 2:4] = np.minimum(det_i[..., 2:4], int(os.environ["SMALL"]))
 d, m = torch.from_numpy(det_i).cuda(), torch.from_numpy(mask_i).cuda()
 layer = ml.CropAndPadMask(output=os.environ.get("OUT", "uint8"))
 ctx = ml.Context.get(0)
