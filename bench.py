@@ -140,10 +140,10 @@ class CpuSample:
     (oracle/c/masklab_oracle.c: "port" - restated CPU path, TensorFlow is not installable here).
     Threads parallelise over frames; ctypes releases the GIL during the C calls."""
 
-    def __init__(self, wl, frames):
+    def __init__(self, wl, frames, bits=False):
         import synth
         from oracle import c_oracle as co
-        self.wl, self.co = wl, co
+        self.wl, self.co, self.bits = wl, co, bits
         co.lib()
         self.inputs = [make_inputs(wl, 1, 7000 + i) for i in range(frames)]
         rcap = (wl["max_k"] + 1) * wl["nms_max_output_size"]
@@ -153,8 +153,9 @@ class CpuSample:
         wl = self.wl
         cfgp, N, loc, cls, fmaps = self.inputs[i]
         out = self.co.full_path(loc, cls, fmaps, lambda f, b: self.mask_pool[:, :b.shape[1]], cfgp,
-                                (wl["H"], wl["W"]), (wl["PH"], wl["PW"]), binary=True, **kwargs_of(wl))
-        return int(out["binary"].shape[1])
+                                (wl["H"], wl["W"]), (wl["PH"], wl["PW"]), binary=True, bits=self.bits,
+                                **kwargs_of(wl))
+        return int(out["bits" if self.bits else "binary"].shape[1])
 
     def run(self, threads, repeat=1):
         n = len(self.inputs)
@@ -191,6 +192,11 @@ def run_reference(args, wl):
         sample.run(threads)
     wall = time.perf_counter() - t0
     fps = steps * frames_per_step / wall
+    fps_bits = None
+    if wl["PW"] % 8 == 0:
+        sample_b = CpuSample(wl, frames_per_step, bits=True)
+        sample_b.run(threads)
+        fps_bits = sample_b.run(threads, repeat=steps)[0]
     desc = (f"{steps} step(s) x {frames_per_step} frames of workload {args.workload} through "
             f"oracle/c (uint8 paste), {threads} threads")
     line = {
@@ -201,6 +207,7 @@ def run_reference(args, wl):
         "config": workload_config(args, wl),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_bitpacked": {"value": fps_bits, "unit": "frames/s", "note": "same arm writing 1 bit per pixel"},
         "note": "C restatement of the reference path (TF kernels restated); TensorFlow 1.x is absent",
     }
     print(json.dumps(line), flush=True)
@@ -374,9 +381,16 @@ def run_ours(args, wl):
                          "the other stream" if S > 1 else "single stream")}
 
     # ---- end to end through the public API with host buffers
-    e2e = None
+    e2e = e2e_bits = None
     if not args.no_e2e:
         e2e = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier)
+        if PW % 8 == 0:
+            # same path, masks delivered 1 bit per pixel (lossless, 8x fewer bytes over PCIe)
+            del pipes[1:]
+            cfg_b = ml.DetectionConfig(paste_output="bits", **kwargs_of(wl))
+            pipe_b = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg_b, device=local,
+                                            private_context=True)
+            e2e_bits = run_e2e(args, wl, pipe_b, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=True)
 
     if rank == 0:
         cpu = None
@@ -395,7 +409,7 @@ def run_ours(args, wl):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_bitpacked": e2e_bits, "gpu_launches": int(launches), "clocks": clocks.summary(),
             "detections": {"M": M, "R": R, "Mf": mf, "kept_per_image_mean": float(counts.mean())},
             "device_bytes": pipe.device_bytes(),
         }
@@ -416,7 +430,7 @@ def algorithmic_bytes(wl, N, M):
     return decode + det + fm + crops + trim + paste
 
 
-def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier):
+def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
     host memory.  Three streams (copy-in, compute, copy-out) so that the input copy of step i+1
@@ -429,7 +443,7 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier):
     d_fmaps = [torch.empty_like(f, device="cuda") for f in h_fmaps]
     d_masks = torch.empty_like(h_masks, device="cuda")
     out_det = torch.empty((B * M * 6,), dtype=torch.int32).pin_memory()
-    out_masks = torch.empty((B * M * PH * PW,), dtype=torch.uint8).pin_memory()
+    out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps)
     d2h = out_det.numel() * 4 + out_masks.numel()
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -480,7 +494,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier):
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
             "ms_per_step": ms / args.e2e_steps,
             "api": "PostProcessPipeline.detect_and_align + trim_and_paste; pinned host inputs in, "
-                   "int32 detections + uint8 masks out to pinned host memory every step"}
+                   "int32 detections + " + ("bit-packed (1 bit/pixel)" if bits else "uint8") +
+                   " masks out to pinned host memory every step"}
 
 
 def main():

@@ -220,6 +220,8 @@ int mlp_upsample_output(mlp_ctx* ctx, const float* det_dev, int64_t rows, float 
 /* ---- a13/a14: CropAndPadMask.call (engine/layers/misc.py:358-401) ------------ */
 #define MLP_PASTE_F32 0   /* drop-in: f32 bilinear values, [B,M,PH,PW]                  */
 #define MLP_PASTE_U8  1   /* canonical binary mask (value > 0.5, misc.py:457,:611-615) */
+#define MLP_PASTE_BITS 2  /* the same binary mask, 1 bit per pixel: [B,M,PH,PW/8] uint8, bit k of byte i
+                             = pixel 8*i+k (numpy packbits bitorder='little'); PW % 8 == 0       */
 /* det_i32_dev [B,M,6], masks_i32_dev i32 [B,M,mh,mw] -> out_dev [B,M,PH,PW].
  * M is read from m_dev (i32 [1]) when not NULL, else m_rows; m_stride is the row
  * stride of det/masks per image.  A box clipped to zero area gives an all-zero mask

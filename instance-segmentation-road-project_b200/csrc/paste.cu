@@ -178,12 +178,12 @@ __device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int
 //   B1 rows crossing the box: the 16-byte segments left and right of it (zeros);
 //   B2 the segments intersecting the box, flattened over ALL threads of the CTA: each evaluates
 //      the reference's two-stage lerp per pixel from the mask tile in shared memory.
-template <bool kU8>
+template <int kMode>       // MLP_PASTE_F32 / MLP_PASTE_U8 / MLP_PASTE_BITS
 __global__ void __launch_bounds__(kPasteThreads)
 paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
              int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
-    constexpr int kVec = kU8 ? 16 : 4;
-    constexpr int kPx = kU8 ? 1 : 4;               // bytes per pixel
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);   // pixels per 16-byte store
+    constexpr bool kU8 = kMode == MLP_PASTE_U8;
     __shared__ float s_tile[kMaxTile];
     int M, thr;
     paste_scalars(S, B, m_rows, M, thr);
@@ -226,8 +226,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
                 tile_regs[q] = (i < px) ? tref.at(i) : 0;
             }
         }
-        uint4* band_base = reinterpret_cast<uint4*>(static_cast<unsigned char*>(out) +
-                                                    ((int64_t)inst * PH + y0) * PW * kPx);
+        uint4* band_base = reinterpret_cast<uint4*>(out) + ((int64_t)inst * PH + y0) * spr;
         // ---- phase A: zero rows [y0,ya) and [yb,y1)
         {
             const int n_top = (ya - y0) * spr;
@@ -296,6 +295,15 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
                     }
                 }
                 v = make_uint4(w[0], w[1], w[2], w[3]);
+            } else if (kMode == MLP_PASTE_BITS) {
+                // bit k of byte i = pixel 8*i + k  (numpy packbits, bitorder='little')
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                const int q0 = max(g.xmin - x0, 0), q1 = min(g.xmax - x0, 128);
+                for (int q = q0; q < q1; ++q) {
+                    const float val = paste_value(s_tile, mh, mw, ylo, yhi, ly, x0 + q - g.xmin, g.sx);
+                    if (val > 0.5f) w[q >> 5] |= 1u << (q & 31);
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
                 float f[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -313,7 +321,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
 }
 
 // Generic fall-back for frame widths that are not a multiple of the vector width.
-template <bool kU8>
+template <int kMode>
 __global__ void __launch_bounds__(kPasteThreads)
 paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride,
                     int mh, int mw, int PH, int PW, void* __restrict__ out) {
@@ -334,18 +342,31 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
         }
         __syncthreads();
         const int64_t npx = (int64_t)PH * PW;
-        for (int64_t i = threadIdx.x; i < npx; i += kPasteThreads) {
-            const int oy = (int)(i / PW), ox = (int)(i - (int64_t)oy * PW);
-            float val = 0.0f;
-            if (g.active && oy >= g.ymin && oy < g.ymax && ox >= g.xmin && ox < g.xmax) {
-                const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
-                const float fl = floorf(p);
-                const int ylo = max((int)fl, 0);
-                const int yhi = min((int)ceilf(p), mh - 1);
-                val = paste_value(s_tile, mh, mw, ylo, yhi, __fsub_rn(p, fl), ox - g.xmin, g.sx);
+        auto value_at = [&](int oy, int ox) -> float {
+            if (!(g.active && oy >= g.ymin && oy < g.ymax && ox >= g.xmin && ox < g.xmax)) return 0.0f;
+            const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
+            const float fl = floorf(p);
+            const int ylo = max((int)fl, 0);
+            const int yhi = min((int)ceilf(p), mh - 1);
+            return paste_value(s_tile, mh, mw, ylo, yhi, __fsub_rn(p, fl), ox - g.xmin, g.sx);
+        };
+        if (kMode == MLP_PASTE_BITS) {                       // PW % 8 == 0 (host checks)
+            const int bpr = PW >> 3;
+            const int64_t nbytes = (int64_t)PH * bpr;
+            for (int64_t i = threadIdx.x; i < nbytes; i += kPasteThreads) {
+                const int oy = (int)(i / bpr), bx = (int)(i - (int64_t)oy * bpr);
+                unsigned byte = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) byte |= (unsigned)(value_at(oy, bx * 8 + k) > 0.5f) << k;
+                static_cast<unsigned char*>(out)[inst * nbytes + i] = (unsigned char)byte;
             }
-            if (kU8) static_cast<unsigned char*>(out)[inst * npx + i] = val > 0.5f;
-            else static_cast<float*>(out)[inst * npx + i] = val;
+        } else {
+            for (int64_t i = threadIdx.x; i < npx; i += kPasteThreads) {
+                const int oy = (int)(i / PW), ox = (int)(i - (int64_t)oy * PW);
+                const float val = value_at(oy, ox);
+                if (kMode == MLP_PASTE_U8) static_cast<unsigned char*>(out)[inst * npx + i] = val > 0.5f;
+                else static_cast<float*>(out)[inst * npx + i] = val;
+            }
         }
     }
 }
@@ -464,38 +485,36 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
                  int m_stride, int mask_h, int mask_w, int frame_h, int frame_w, int out_mode,
                  void* out_dev, cudaStream_t st) {
     ProfScope prof(ctx, MLP_ST_PASTE, st);
-    const bool u8 = out_mode == MLP_PASTE_U8;
-    const int vec = u8 ? 16 : 4;
+    const int vec = out_mode == MLP_PASTE_F32 ? 4 : (out_mode == MLP_PASTE_U8 ? 16 : 128);
     int band_kb = 64;                                  // tuning knobs (tools/bench_paste.py)
     int ctas_per_sm = 0;                               // 0: one CTA per item (default)
     if (const char* e = getenv("MLP_PASTE_CTAS_PER_SM")) ctas_per_sm = atoi(e);
     if (const char* e = getenv("MLP_PASTE_BAND_KB")) band_kb = atoi(e) > 0 ? atoi(e) : 64;
     if (frame_w % vec == 0) {
-        int band_rows = (band_kb * 1024) / (frame_w * (u8 ? 1 : 4));
+        const int row_bytes = frame_w / vec * 16;
+        int band_rows = (band_kb * 1024) / row_bytes;
         if (band_rows < 1) band_rows = 1;
         if (band_rows > frame_h) band_rows = frame_h;
         const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
         int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
         if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
-        if (u8)
-            paste_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
-                                                              mask_h, mask_w, frame_h, frame_w,
-                                                              band_rows, out_dev);
-        else
-            paste_kernel<false><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
-                                                               mask_h, mask_w, frame_h, frame_w,
-                                                               band_rows, out_dev);
+#define MLP_PASTE_LAUNCH(MODE)                                                                         \
+    paste_kernel<MODE><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
+                                                      mask_w, frame_h, frame_w, band_rows, out_dev)
+        if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
+        else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
+        else MLP_PASTE_LAUNCH(MLP_PASTE_F32);
+#undef MLP_PASTE_LAUNCH
     } else {
         const int64_t items = (int64_t)batch * m_rows;
         const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-        if (u8)
-            paste_scalar_kernel<true><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows,
-                                                                     m_stride, mask_h, mask_w, frame_h,
-                                                                     frame_w, out_dev);
-        else
-            paste_scalar_kernel<false><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows,
-                                                                      m_stride, mask_h, mask_w, frame_h,
-                                                                      frame_w, out_dev);
+#define MLP_PASTE_LAUNCH(MODE)                                                                       \
+    paste_scalar_kernel<MODE><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride, \
+                                                             mask_h, mask_w, frame_h, frame_w, out_dev)
+        if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
+        else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
+        else MLP_PASTE_LAUNCH(MLP_PASTE_F32);
+#undef MLP_PASTE_LAUNCH
     }
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
@@ -507,8 +526,10 @@ int check_paste_args(const char* who, int batch, int mask_h, int mask_w, int fra
     MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_h * mask_w <= kMaxTile,
                   "%s: mask tile %dx%d too large (max %d elements)", who, mask_h, mask_w, kMaxTile);
     MLP_CHECK_ARG(frame_h >= 1 && frame_w >= 1, "%s: frame %dx%d", who, frame_h, frame_w);
-    MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8, "%s: unknown out_mode %d", who,
-                  out_mode);
+    MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8 || out_mode == MLP_PASTE_BITS,
+                  "%s: unknown out_mode %d", who, out_mode);
+    MLP_CHECK_ARG(out_mode != MLP_PASTE_BITS || frame_w % 8 == 0,
+                  "%s: bit-packed output needs a frame width that is a multiple of 8 (got %d)", who, frame_w);
     MLP_CHECK_ARG(mlp_aligned16(out_dev), "%s: out_dev must be 16-byte aligned", who);
     return MLP_OK;
 }

@@ -89,11 +89,13 @@ class CropAndPadMask(Layer):
 
     output='float32' (default) is the reference's tensor: bilinear values of the resized
     mask inside the clipped box, 0 elsewhere.  output='uint8' fuses the consumers'
-    `> 0.5` (misc.py:457, :611-615) and writes the binary mask, a quarter of the bytes."""
+    `> 0.5` (misc.py:457, :611-615) and writes the binary mask, a quarter of the bytes;
+    output='bits' packs that binary mask 8 pixels per byte ([B,M,PH,PW/8], numpy packbits
+    bitorder='little')."""
 
     def __init__(self, output="float32", **kwargs):
-        if output not in ("float32", "uint8"):
-            raise ValueError("output must be 'float32' or 'uint8'")
+        if output not in ("float32", "uint8", "bits"):
+            raise ValueError("output must be 'float32', 'uint8' or 'bits'")
         self.output = output
         super().__init__(**kwargs)
 
@@ -105,11 +107,17 @@ class CropAndPadMask(Layer):
         ins = ins_outs.to(torch.int32).contiguous()
         B, M = int(det.shape[0]), int(det.shape[1])
         mh, mw = int(ins.shape[2]), int(ins.shape[3])
-        u8 = self.output == "uint8"
-        out = ctx.empty((B, M, int(frame_h), int(frame_w)), torch.uint8 if u8 else torch.float32)
+        mode = {"float32": rt.MLP_PASTE_F32, "uint8": rt.MLP_PASTE_U8, "bits": rt.MLP_PASTE_BITS}[self.output]
+        if mode == rt.MLP_PASTE_BITS:
+            if int(frame_w) % 8:
+                raise rt.InvalidArgumentError(rt.MLP_EINVAL, "bit-packed output needs frame width % 8 == 0")
+            out = ctx.empty((B, M, int(frame_h), int(frame_w) // 8), torch.uint8)
+        else:
+            out = ctx.empty((B, M, int(frame_h), int(frame_w)),
+                            torch.uint8 if mode == rt.MLP_PASTE_U8 else torch.float32)
         rt.check(ctx.lib.mlp_crop_and_pad_mask(
             ctx.handle, ctx.view(det), ctx.view(ins), B, M, M, null(), mh, mw, int(frame_h),
-            int(frame_w), rt.MLP_PASTE_U8 if u8 else rt.MLP_PASTE_F32, ctx.view(out), ctx.stream()))
+            int(frame_w), mode, ctx.view(out), ctx.stream()))
         return out
 
     def get_config(self):

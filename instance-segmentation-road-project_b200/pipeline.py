@@ -32,7 +32,7 @@ class DetectionConfig:
     mask_size: tuple = (28, 28)
     padding: str = "same"
     strict_batch: bool = True
-    paste_output: str = "uint8"          # 'uint8' (binary, > 0.5 fused) or 'float32' (drop-in)
+    paste_output: str = "uint8"          # 'uint8' (binary, > 0.5 fused), 'bits' (8 px/byte) or 'float32' (drop-in)
     fused: bool = True                   # fused halves (6 kernels) vs the chain of stage kernels (13)
 
 
@@ -113,8 +113,14 @@ class PostProcessPipeline:
         self.det_i32 = c.empty((B * K * 6,), i32)
         self.masks_i32 = c.empty((B * K * mh * mw,), i32)
         PH, PW = self.frame_hw
-        u8 = self.cfg.paste_output == "uint8"
-        self.pasted = c.empty((B * K * PH * PW,), torch.uint8 if u8 else f32)
+        mode = self.cfg.paste_output
+        if mode not in ("uint8", "float32", "bits"):
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"unknown paste_output {mode!r}")
+        if mode == "bits" and PW % 8:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "bit-packed output needs frame width % 8 == 0")
+        self.paste_mode = {"float32": rt.MLP_PASTE_F32, "uint8": rt.MLP_PASTE_U8, "bits": rt.MLP_PASTE_BITS}[mode]
+        self.paste_row = PW // 8 if mode == "bits" else PW          # elements per frame row of `pasted`
+        self.pasted = c.empty((B * K * PH * self.paste_row,), f32 if mode == "float32" else torch.uint8)
         self._crop_ptrs = (ctypes.c_void_p * L)(*[c.view(t).value for t in self.crops])
         self._fh = (ctypes.c_int32 * L)(*[h for h, _ in self.fmap_hw])
         self._fw = (ctypes.c_int32 * L)(*[w for _, w in self.fmap_hw])
@@ -195,7 +201,7 @@ class PostProcessPipeline:
         masks_ptr = c.view(roi_masks, torch.float32)
         ratio = (torch.tensor([float(self.frame_hw[0]), float(self.frame_hw[1])], dtype=torch.float32)
                  / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
-        mode = rt.MLP_PASTE_U8 if self.cfg.paste_output == "uint8" else rt.MLP_PASTE_F32
+        mode = self.paste_mode
         self._compact_det = not self.cfg.fused
         if self.cfg.fused:
             rt.check(lib.mlp_trim_paste(
@@ -225,5 +231,5 @@ class PostProcessPipeline:
             det = self.det_i32[:self.B * M * 6].view(self.B, M, 6)
         else:
             det = self.det_i32.view(self.B, self.K, 6)[:, :M]
-        masks = self.pasted[:self.B * M * PH * PW].view(self.B, M, PH, PW)
+        masks = self.pasted[:self.B * M * PH * self.paste_row].view(self.B, M, PH, self.paste_row)
         return det, masks

@@ -334,7 +334,7 @@ void mlo_upsample(const float* det, int64_t rows, float ratio_h, float ratio_w, 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 void mlo_paste(const int32_t* det, const int32_t* masks, int B, int M, int mh, int mw, int PH, int PW,
-               float* out_f32, uint8_t* out_u8) {
+               float* out_f32, uint8_t* out_u8, uint8_t* out_bits /* [B,M,PH,PW/8], bit k of byte i = pixel 8i+k */) {
     int mx = INT32_MIN;
     for (int64_t i = 0; i < (int64_t)B * M; ++i) if (det[i * 6 + 5] > mx) mx = det[i * 6 + 5];
     int thr = (mx > 50) ? 50 : -100;
@@ -343,6 +343,7 @@ void mlo_paste(const int32_t* det, const int32_t* masks, int B, int M, int mh, i
         const int32_t* r = det + inst * 6;
         if (out_f32) memset(out_f32 + inst * frame, 0, (size_t)frame * sizeof(float));
         if (out_u8) memset(out_u8 + inst * frame, 0, (size_t)frame);
+        if (out_bits) memset(out_bits + inst * (frame / 8), 0, (size_t)(frame / 8));
         if (r[5] < thr) continue;
         float cx = (float)(r[0] > 1 ? r[0] : 1), cy = (float)(r[1] > 1 ? r[1] : 1);
         float w = (float)(r[2] > 1 ? r[2] : 1), h = (float)(r[3] > 1 ? r[3] : 1);
@@ -368,6 +369,7 @@ void mlo_paste(const int32_t* det, const int32_t* masks, int B, int M, int mh, i
                 int64_t o = inst * frame + (int64_t)(ymin + y) * PW + (xmin + x);
                 if (out_f32) out_f32[o] = v;
                 if (out_u8) out_u8[o] = v > 0.5f;
+                if (out_bits && v > 0.5f) out_bits[o >> 3] |= (uint8_t)(1u << (o & 7));
             }
         }
     }

@@ -49,7 +49,7 @@ def lib():
         L.mlo_trim_plan.argtypes = [_P, _I, _I, _P]
         L.mlo_trim_run.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]
         L.mlo_upsample.argtypes = [_P, _L, _F, _F, _P, _P, _L, _P]
-        L.mlo_paste.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]
+        L.mlo_paste.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]
         _lib = L
     return _lib
 
@@ -162,24 +162,28 @@ def upsample_output(det, masks, src_hw, dst_hw):
     return di, mi
 
 
-def crop_and_pad_mask(frame_hw, det_i, mask_i, binary=False):
+def crop_and_pad_mask(frame_hw, det_i, mask_i, binary=False, bits=False):
     det_i = np.ascontiguousarray(det_i, I32)
     mask_i = np.ascontiguousarray(mask_i, I32)
     B, M, _ = det_i.shape
     mh, mw = mask_i.shape[2:]
     PH, PW = int(frame_hw[0]), int(frame_hw[1])
-    if binary:
+    if bits:
+        assert PW % 8 == 0
+        out = np.empty((B, M, PH, PW // 8), np.uint8)
+        lib().mlo_paste(_ptr(det_i), _ptr(mask_i), B, M, mh, mw, PH, PW, None, None, _ptr(out))
+    elif binary:
         out = np.empty((B, M, PH, PW), np.uint8)
-        lib().mlo_paste(_ptr(det_i), _ptr(mask_i), B, M, mh, mw, PH, PW, None, _ptr(out))
+        lib().mlo_paste(_ptr(det_i), _ptr(mask_i), B, M, mh, mw, PH, PW, None, _ptr(out), None)
     else:
         out = np.empty((B, M, PH, PW), F32)
-        lib().mlo_paste(_ptr(det_i), _ptr(mask_i), B, M, mh, mw, PH, PW, _ptr(out), None)
+        lib().mlo_paste(_ptr(det_i), _ptr(mask_i), B, M, mh, mw, PH, PW, _ptr(out), None, None)
     return out
 
 
 def full_path(loc_pred, cls_pred, fmaps, mask_head, prior_cfg, image_hw, frame_hw, min_confidence=0.05,
               nms_iou_threshold=0.4, post_iou_threshold=0.65, nms_max_output_size=1000, max_k=2,
-              base_size=64, crop_size=(14, 14), padding="same", binary=True):
+              base_size=64, crop_size=(14, 14), padding="same", binary=True, bits=False):
     """Same chain as masklab_oracle.full_path, every stage in C."""
     B = cls_pred.shape[0]
     H, W = image_hw
@@ -192,7 +196,7 @@ def full_path(loc_pred, cls_pred, fmaps, mask_head, prior_cfg, image_hw, frame_h
     roi_masks = mask_head(roi_fmaps, roi_boxes)
     det, ins = trim_instances(roi_boxes, roi_masks)
     det_i, ins_i = upsample_output(det, ins, image_hw, frame_hw)
-    pasted = crop_and_pad_mask(frame_hw, det_i, ins_i, binary=binary)
+    pasted = crop_and_pad_mask(frame_hw, det_i, ins_i, binary=binary, bits=bits)
     return dict(priors=pr, restored=restored, proposed=proposed, dist=dist, roi_fmaps=roi_fmaps,
                 roi_boxes=roi_boxes, det=det, ins=ins, det_i=det_i, ins_i=ins_i,
-                **({"binary": pasted} if binary else {"pasted": pasted}))
+                **({"bits": pasted} if bits else ({"binary": pasted} if binary else {"pasted": pasted})))

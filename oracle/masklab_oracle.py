@@ -305,6 +305,11 @@ def binary_masks(pasted):
     return (np.asarray(pasted, dtype=F32) > F32(0.5)).astype(np.uint8)
 
 
+def packed_masks(pasted):
+    """Binary masks packed 8 pixels per byte, bit k of byte i = pixel 8*i+k."""
+    return np.packbits(binary_masks(pasted), axis=-1, bitorder="little")
+
+
 # ------------------------------------------------------- whole path -------
 def synth_mask_head(roi_boxes, num_classes, mask_hw=(28, 28), seed=0):
     """Stand-in for MaskSubNet (not on the path): U(0,1) probs."""

@@ -28,6 +28,8 @@ def test_full_path_c_equals_numpy(mu, max_out, C):
         assert np.array_equal(x, y)
     c = co.full_path(loc, cls, fmaps, head, cfgp, (H, W), (192, 320), binary=True, **kw)
     assert np.array_equal(c["binary"], a["binary"])
+    d = co.full_path(loc, cls, fmaps, head, cfgp, (H, W), (192, 320), bits=True, **kw)
+    assert np.array_equal(d["bits"], mo.packed_masks(a["pasted"]))
 
 
 def test_detection_ties_and_keep_indices():

@@ -297,7 +297,7 @@ def _paste_case(B, M, PH, PW, seed, pad_tail=2):
     return det_i, mask_i
 
 
-@pytest.mark.parametrize("PH,PW", [(128, 256), (135, 240), (64, 100), (50, 37)])
+@pytest.mark.parametrize("PH,PW", [(128, 256), (135, 240), (64, 100), (50, 37), (96, 1024), (40, 1920)])
 def test_crop_and_pad_mask_exact(ml, PH, PW):
     B, M = 2, 24
     det_i, mask_i = _paste_case(B, M, PH, PW, seed=61)
@@ -313,6 +313,12 @@ def test_crop_and_pad_mask_exact(ml, PH, PW):
     assert got.dtype == np.float32 and np.array_equal(got, want)
     got8 = host(ml.CropAndPadMask(output="uint8")([images, dev(det_i), dev(mask_i)]))
     assert got8.dtype == np.uint8 and np.array_equal(got8, mo.binary_masks(want))
+    if PW % 8 == 0:
+        bits = host(ml.CropAndPadMask(output="bits")([images, dev(det_i), dev(mask_i)]))
+        assert bits.shape == (B, M, PH, PW // 8) and np.array_equal(bits, mo.packed_masks(want))
+    else:
+        with pytest.raises(ValueError):
+            ml.CropAndPadMask(output="bits")([images, dev(det_i), dev(mask_i)])
     assert want[1, 1].sum() == 0 and want[0, 0].sum() == 0
 
 
@@ -344,7 +350,7 @@ def test_mold_batch(ml):
 
 # --------------------------------------------------------------- whole path ---
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("paste", ["uint8", "float32"])
+@pytest.mark.parametrize("paste", ["uint8", "float32", "bits"])
 def test_pipeline_matches_oracle(ml, paste, fused):
     B, H, W, C, Cf = 3, 128, 256, 4, 16
     PH, PW = 256, 512
@@ -376,6 +382,8 @@ def test_pipeline_matches_oracle(ml, paste, fused):
     assert np.array_equal(host(det_i), want["det_i"])
     if paste == "uint8":
         assert np.array_equal(host(pasted), want["binary"])
+    elif paste == "bits":
+        assert np.array_equal(host(pasted), mo.packed_masks(want["pasted"]))
     else:
         assert np.array_equal(host(pasted), want["pasted"])
 
