@@ -11,6 +11,8 @@ collective is one NCCL all_gather of the fixed-capacity detection records at the
 timed region.  Rank 0 prints ONE JSON line.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import sys
@@ -501,10 +503,30 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        run_reference(args, wl)
-    else:
-        run_ours(args, wl)
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner on
+    # stdout at communicator creation) must not interleave with it: route fd 1 to stderr while
+    # the benchmark runs and hand the real stdout back only for the final line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            if args.impl == "reference":
+                run_reference(args, wl)
+            else:
+                run_ours(args, wl)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [l for l in out.getvalue().splitlines() if l.strip()]
+    json_lines = [l for l in lines if l.lstrip().startswith("{")]
+    for l in lines:
+        if l not in json_lines:
+            print(l, file=sys.stderr)
+    for l in json_lines[-1:]:
+        print(l, flush=True)
 
 
 if __name__ == "__main__":
