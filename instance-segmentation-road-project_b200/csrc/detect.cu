@@ -283,8 +283,8 @@ __device__ uint64_t radix_select_pivot(const uint64_t* gkeys, int cnt, bool have
 // ------------------------------------------------------------ NMS core -------
 struct NmsSmem {
     uint64_t* skeys;        // [sort_cap]
-    float* k_ymin; float* k_xmin; float* k_ymax; float* k_xmax; float* k_area;   // [max_out]
-    float* c_ymin; float* c_xmin; float* c_ymax; float* c_xmax; float* c_area;   // [kChunk]
+    float4* k_crn; float* k_area;   // [max_out] kept boxes (ymin,xmin,ymax,xmax) + area: one LDS.128 + one LDS.32 per test
+    float4* c_crn; float* c_area;   // [kChunk]  candidates of the current chunk
     float4* c_box;          // [kChunk] cx,cy,w,h of the chunk's candidates
     uint32_t* c_mask;       // [kChunk][kMaskWords]
     int* c_supp;            // [kChunk]
@@ -315,15 +315,9 @@ __device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_
     S.skeys = reinterpret_cast<uint64_t*>(p); p += (size_t)sort_cap * 8;
     S.c_box = reinterpret_cast<float4*>(p);   p += (size_t)kChunk * 16;
     S.bcast = reinterpret_cast<unsigned long long*>(p); p += 16;
-    S.k_ymin = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
-    S.k_xmin = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
-    S.k_ymax = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
-    S.k_xmax = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
+    S.k_crn = reinterpret_cast<float4*>(p); p += (size_t)max_out * 16;     // 16-byte aligned (after c_box/bcast)
+    S.c_crn = reinterpret_cast<float4*>(p); p += (size_t)kChunk * 16;
     S.k_area = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
-    S.c_ymin = reinterpret_cast<float*>(p); p += kChunk * 4;
-    S.c_xmin = reinterpret_cast<float*>(p); p += kChunk * 4;
-    S.c_ymax = reinterpret_cast<float*>(p); p += kChunk * 4;
-    S.c_xmax = reinterpret_cast<float*>(p); p += kChunk * 4;
     S.c_area = reinterpret_cast<float*>(p); p += kChunk * 4;
     S.c_mask = reinterpret_cast<uint32_t*>(p); p += (size_t)kChunk * kMaskWords * 4;
     S.c_supp = reinterpret_cast<int*>(p); p += kChunk * 4;
@@ -384,8 +378,8 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                     float4 bx = fetch((uint32_t)key);
                     BoxC c = corners_of(bx);
                     S.c_box[tid] = bx;
-                    S.c_ymin[tid] = c.ymin; S.c_xmin[tid] = c.xmin;
-                    S.c_ymax[tid] = c.ymax; S.c_xmax[tid] = c.xmax; S.c_area[tid] = c.area;
+                    S.c_crn[tid] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+                    S.c_area[tid] = c.area;
                     S.c_supp[tid] = 0;
                 } else {
                     S.c_supp[tid] = 1;
@@ -395,13 +389,14 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
             }
             __syncthreads();
             const int t = tid % kChunk, r = tid / kChunk;
-            const float tymin = S.c_ymin[t], txmin = S.c_xmin[t], tymax = S.c_ymax[t],
-                        txmax = S.c_xmax[t], tarea = S.c_area[t];
+            const float4 tc = S.c_crn[t];
+            const float tymin = tc.x, txmin = tc.y, tymax = tc.z, txmax = tc.w, tarea = S.c_area[t];
             // (b) against the kept list, split over kLanesPerCand threads per candidate
             if (t < m) {
                 for (int j = r; j < kept; j += kLanesPerCand) {
-                    if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.k_ymin[j], S.k_xmin[j],
-                                    S.k_ymax[j], S.k_xmax[j], S.k_area[j], thr)) {
+                    const float4 kc = S.k_crn[j];
+                    if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, kc.x, kc.y, kc.z, kc.w, S.k_area[j],
+                                    thr)) {
                         S.c_supp[t] = 1;
                         break;
                     }
@@ -415,9 +410,10 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 const int u1 = (u0 + kSlice < t) ? (u0 + kSlice) : t;
                 uint32_t lo = 0, hi = 0;
                 for (int u = u0; u < u1; ++u) {
+                    const float4 uc = S.c_crn[u];
                     if (S.c_supp[u] == 0 &&
-                        iou_exceeds(tymin, txmin, tymax, txmax, tarea, S.c_ymin[u], S.c_xmin[u],
-                                    S.c_ymax[u], S.c_xmax[u], S.c_area[u], thr)) {
+                        iou_exceeds(tymin, txmin, tymax, txmax, tarea, uc.x, uc.y, uc.z, uc.w, S.c_area[u],
+                                    thr)) {
                         if (u < 32) lo |= 1u << u; else hi |= 1u << (u - 32);
                     }
                 }
@@ -460,8 +456,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 if ((wv >> (tid & 31)) & 1u) {
                     int rank = kept + ((tid < 32) ? 0 : __popc(w0));
                     rank += __popc(wv & ((1u << (tid & 31)) - 1u));
-                    S.k_ymin[rank] = S.c_ymin[tid]; S.k_xmin[rank] = S.c_xmin[tid];
-                    S.k_ymax[rank] = S.c_ymax[tid]; S.k_xmax[rank] = S.c_xmax[tid];
+                    S.k_crn[rank] = S.c_crn[tid];
                     S.k_area[rank] = S.c_area[tid];
                     emit(rank, S.skeys[base + tid], S.c_box[tid]);
                 }

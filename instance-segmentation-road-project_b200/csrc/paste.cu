@@ -377,7 +377,7 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
 // that the paste kernel can pick every instance's own class channel straight from the mask head
 // output.  Capacity layout (K rows per image), so nothing here depends on M.
 constexpr int kPrepThreads = 256;
-constexpr int kPrepParts = 8;             // CTAs per image (each repeats the cheap scan, owns 1/8 of the slots)
+constexpr int kPrepParts = 8;             // minimum CTAs per image (each repeats the cheap scan, owns 1/parts of the slots)
 
 __global__ void __launch_bounds__(kPrepThreads)
 tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ roi_masks, int r_rows,
@@ -578,7 +578,10 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     // arena: tail_src [B,K] + confmax [B] + bit tiles [B,K,mh] (mask rows of <= 32 columns)
-    const bool use_bits = mask_w <= 32;
+    // Bit tiles pay off when few instances are pasted (the strided class-channel gather would
+    // otherwise be repeated by every band CTA that touches the box); with many instances the
+    // gather is better left inside the paste kernel, where its reads overlap the write stream.
+    const bool use_bits = mask_w <= 32 && k_rows <= 256;
     rc = mlp_ensure_scratch(ctx, MLP_ARENA_FUSED,
                             ((int64_t)batch * k_rows + batch + (use_bits ? (int64_t)batch * k_rows * mask_h : 0)) * 4);
     if (rc) return rc;
@@ -587,7 +590,10 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     uint32_t* tail_bits = use_bits ? reinterpret_cast<uint32_t*>(confmax + batch) : nullptr;
     {
         ProfScope prof(ctx, MLP_ST_TAIL_FUSED, st);
-        tail_prep_kernel<<<dim3(batch, kPrepParts), kPrepThreads, 0, st>>>(
+        // CTAs per image grow with the capacity so that each warp gathers at most ~2 tiles
+        int parts = k_rows / 16;
+        parts = parts < kPrepParts ? kPrepParts : (parts > 64 ? 64 : parts);
+        tail_prep_kernel<<<dim3(batch, parts), kPrepThreads, 0, st>>>(
             roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, ratio_h,
             ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax);
         MLP_LAUNCH_CHECK(ctx);
