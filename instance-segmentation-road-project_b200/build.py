@@ -46,11 +46,13 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force=False, verbose=False):
-    """Compile every CUDA source into one shared library.  Returns the path."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, extra=()):
+    """Compile every CUDA source into one shared library.  Returns the path.  `out`/`extra`
+    build a tuning variant (other -D flags) next to the in-tree library."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + sources()
+    out = out or LIB_PATH
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-I", INCLUDE, "-I", CSRC, "-o", out] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -60,7 +62,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -128,6 +128,34 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
                  : "memory");
 }
 
+// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Waits for the given phase; traps instead of hanging the GPU if the copy never lands.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+    if (!ok) __trap();
+}
+
 // Packed f32x2 arithmetic (Blackwell FADD2): two IEEE-rounded float adds per instruction.  Only
 // add/sub are used packed - ptxas contracts a packed multiply feeding a packed add into FFMA2
 // even with .rn and -fmad=false, which would change the rounding, so multiplies stay scalar.

@@ -6,17 +6,24 @@
 // regroups crops per level as [B,Mf,ch,cw,Cf] padded with -1.  Here:
 //   plan : one CTA per image ranks its boxes per level (ballot prefix scan, order j)
 //          -> slot -> source-row table, per-level counts and Mf = max(1, max_b count).
-//   run  : persistent CTAs, one RoI (level, image, slot) at a time; each warp owns one
-//          output pixel, each lane a float4 of channels: the 4 bilinear corners are four
-//          fully coalesced 16*32-byte NHWC reads (L1-allocating: neighbouring output
-//          pixels of an up-sampled RoI share corners) and the result one streaming
-//          128-bit store per lane.  Padded slots are filled with -1 the same way.
+//   run  : one short-lived CTA per RoI (level, image, slot).  Warp 0 builds the RoI's tables
+//          (source coordinates, column table, row schedule) and TMA-copies the RoI's source
+//          window into shared memory (cp.async.bulk per window row, mbarrier completion);
+//          then every warp walks one output column top to bottom with the separable
+//          form of the bilinear lerp (see below), lanes own a float4 of channels, results leave
+//          as streaming 128-bit stores.  Padded slots are filled with -1 the same way.
 // The stage is write-dominated (B*M*196*Cf*4 bytes out vs <= the FPN maps in).
+#include <limits.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kRoiThreads = 256;
+#ifndef MLP_ROI_MAXNREG
+#define MLP_ROI_MAXNREG 56               // 5 CTAs x 7 warps per SM
+#endif
+constexpr int kRoiThreads = 224;         // upper bound (7 warps x 72 registers x 4 CTAs fill an SM); the launch uses 3..7 warps
 constexpr int kMaxCrop = 64;          // crop_h, crop_w <= 64
 
 struct RoiLevels {
@@ -54,169 +61,291 @@ roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
 }
 
 // ---- run ----------------------------------------------------------------------
-constexpr int kPixUnroll = 4;         // output pixels in flight per warp (16 corner loads)
-constexpr int kMaxPix = 1024;         // crop_h * crop_w <= 1024 (per-RoI pixel table in smem)
+// crop_and_resize is separable: out(y,x) = T + (Bo - T) * ly with T = H(top_y, x), Bo = H(bot_y, x)
+// and H(r, x) = img[r][left_x] + (img[r][right_x] - img[r][left_x]) * lx - a value that does not
+// depend on y.  Up-sampled RoIs (the common case: 14 samples over fewer source rows) reuse every
+// H(r, x) for several output rows, so each warp walks ONE output column top to bottom, keeps the
+// last two horizontal lerps in registers (hp, hc) and loads every source row once; bit-identical
+// to evaluating four corners per pixel because every H(r, x) is the same three rounded operations.
+// Per RoI warp 0 builds the schedule once: the list of source rows to load, and after each row
+// the outputs (row offset, ly) that become computable as lerp(hp, hc, ly).
+constexpr int kMaxRows = 2 * kMaxCrop;       // worst case two new source rows per output row
+constexpr int kRoiWindowBytes = 48 * 1024;   // FPN window staged in shared memory per RoI
 
-__global__ void __launch_bounds__(kRoiThreads)
+struct RoiOut { uint32_t yoff; float ly; };  // byte offset of the output row inside the crop, y weight
+struct RoiSched {                            // per-RoI tables, built once per CTA by warp 0
+    float iny[kMaxCrop], inx[kMaxCrop];          // crop_and_resize source coordinates
+    uint32_t xl[kMaxCrop], xr[kMaxCrop];         // byte offsets of the left/right source pixel in a row
+    float lx[kMaxCrop];                          // x lerp weight; < 0: column outside -> 0
+    uint32_t rowoff[kMaxRows];                   // byte offsets of the source rows, in load order
+    unsigned short obeg[kMaxRows + 1];           // outputs [obeg[k], obeg[k+1]) follow the load of row k
+    RoiOut out[kMaxCrop];
+    uint32_t zoff[kMaxCrop];                     // output rows outside the map -> 0
+    int nrows, nzero, staged;
+};
+
+__device__ __forceinline__ float4 lerp_v(const float4& a, const float4& b, float l) {
+    float4 r;
+    unpack2(lerp2_rn(pack2(a.x, a.y), pack2(b.x, b.y), l), r.x, r.y);
+    unpack2(lerp2_rn(pack2(a.z, a.w), pack2(b.z, b.w), l), r.z, r.w);
+    return r;
+}
+__device__ __forceinline__ float lerp_v(float a, float b, float l) {
+    return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), l));
+}
+__device__ __forceinline__ void zero_v(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void zero_v(float& v) { v = 0.f; }
+__device__ __forceinline__ void store_v(unsigned char* p, const float4& v) { stg_stream_f4(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void store_v(unsigned char* p, float v) { *reinterpret_cast<float*>(p) = v; }
+template <bool kStaged> __device__ __forceinline__ void load_v(const unsigned char* p, float4& v) {
+    if (kStaged) v = *reinterpret_cast<const float4*>(p);
+    else v = __ldg(reinterpret_cast<const float4*>(p));
+}
+template <bool kStaged> __device__ __forceinline__ void load_v(const unsigned char* p, float& v) {
+    if (kStaged) v = *reinterpret_cast<const float*>(p);
+    else v = __ldg(reinterpret_cast<const float*>(p));
+}
+
+// One source row (its left and right pixel) in registers.
+template <typename Vec> struct RowRegs { Vec l, r; };
+
+template <typename Vec, bool kStaged>
+__device__ __forceinline__ void row_load(RowRegs<Vec>& q, const RoiSched& S, const unsigned char* pl,
+                                         const unsigned char* pr, int k, int K) {
+    if (k < K) {
+        const uint32_t ro = S.rowoff[k];
+        load_v<kStaged>(pl + ro, q.l);
+        load_v<kStaged>(pr + ro, q.r);
+    }
+}
+template <typename Vec>
+__device__ __forceinline__ void row_consume(const RowRegs<Vec>& q, const RoiSched& S, unsigned char* o,
+                                            float lx, int k, int K, Vec& hp, Vec& hc) {
+    if (k < K) {
+        hp = hc;
+        hc = lerp_v(q.l, q.r, lx);
+        const int j1 = S.obeg[k + 1];
+#pragma unroll 1
+        for (int j = S.obeg[k]; j < j1; ++j) {
+            const RoiOut e = S.out[j];
+            store_v(o + e.yoff, lerp_v(hp, hc, e.ly));
+        }
+    }
+}
+
+// One RoI: warp-task = (output column x, group of 32 channel vectors); Vec = float4 (Cf % 4 == 0)
+// or float.  kStaged: source rows come from the TMA-staged window in shared memory.  The row loads
+// are double-buffered: the loads of row k+1 are in flight while row k is used.
+template <typename Vec, bool kStaged>
+__device__ __forceinline__ void roi_columns(const unsigned char* __restrict__ src, const RoiSched& S,
+                                            float* __restrict__ out, int ch, int cw, int Cf, int warp,
+                                            int lane, int nwarps) {
+    constexpr int V = sizeof(Vec) / 4;
+    const int CV = Cf / V;                                 // channel vectors per pixel
+    const int groups = (CV + 31) >> 5;
+    const int K = S.nrows, nz = S.nzero;
+    const uint32_t ystride = (uint32_t)(cw * Cf) * 4u;
+#pragma unroll 1
+    for (int task = warp; task < cw * groups; task += nwarps) {
+        const int g = task / cw, x = task - g * cw;
+        const int c = (g << 5) + lane;
+        if (c >= CV) continue;
+        unsigned char* o = reinterpret_cast<unsigned char*>(out + (size_t)x * Cf + (size_t)c * V);
+        const float lx = S.lx[x];
+        Vec z;
+        zero_v(z);
+        if (!(lx >= 0.0f)) {                                // column outside: extrapolation_value = 0
+            for (int y = 0; y < ch; ++y) store_v(o + y * ystride, z);
+            continue;
+        }
+        for (int i = 0; i < nz; ++i) store_v(o + S.zoff[i], z);
+        const unsigned char* pl = src + S.xl[x] + c * (V * 4);
+        const unsigned char* pr = src + S.xr[x] + c * (V * 4);
+        Vec hp = z, hc = z;                                 // H of the previous / the current source row
+        RowRegs<Vec> qa, qb;
+        row_load<Vec, kStaged>(qa, S, pl, pr, 0, K);
+#pragma unroll 1
+        for (int k0 = 0; k0 < K; k0 += 2) {
+            row_load<Vec, kStaged>(qb, S, pl, pr, k0 + 1, K);
+            row_consume<Vec>(qa, S, o, lx, k0, K, hp, hc);
+            row_load<Vec, kStaged>(qa, S, pl, pr, k0 + 2, K);
+            row_consume<Vec>(qb, S, o, lx, k0 + 1, K, hp, hc);
+        }
+    }
+}
+
+__global__ void __maxnreg__(MLP_ROI_MAXNREG)
 roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ dist, int B,
                  int m_rows, int m_stride, float image_h, float image_w, int ch, int cw,
                  const int32_t* __restrict__ roi_src, const int32_t* __restrict__ counts,
-                 int32_t* __restrict__ level_m, float* __restrict__ roi_boxes) {
-    // per-RoI tables, built once per RoI by ch+cw (coordinates) and ch*cw (pixels) threads so
-    // that the streaming loop below carries no divisions and no 64-bit address arithmetic
-    __shared__ float s_iny[kMaxCrop], s_inx[kMaxCrop];
-    __shared__ uint4 s_poff[kMaxPix];         // BYTE offsets of TL,TR,BL,BR inside this image's map
-    __shared__ float2 s_pw[kMaxPix];          // (lx, ly); lx < 0 marks "outside -> 0"
-    __shared__ int s_mf[MLP_MAX_LEVELS], s_off[MLP_MAX_LEVELS + 1];
-    if (threadIdx.x == 0) {
-        int off = 0;
-        for (int f = 0; f < L; ++f) {
-            const int m = level_m[f];
-            s_mf[f] = m; s_off[f] = off;
-            off += m;
-        }
-        s_off[L] = off;
-        if (blockIdx.x == 0) level_m[L] = off;               // R = sum of Mf, for TrimInstances
-    }
-    __syncthreads();
-    const int R = s_off[L];
+                 int32_t* __restrict__ level_m, float* __restrict__ roi_boxes, int window_cap) {
+    extern __shared__ __align__(128) unsigned char s_window[];   // TMA-staged FPN window of this RoI
+    __shared__ RoiSched S;
+    __shared__ __align__(8) uint64_t s_bar;   // mbarrier the TMA row copies complete on
+    const int nthreads = blockDim.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = kRoiThreads / 32;
+    const int nwarps = nthreads >> 5;
+    // every thread reads the device-side level sizes itself (one round trip, no barrier): CTAs
+    // beyond the B * R real items exit at once
+    int R = 0;
+#pragma unroll
+    for (int f = 0; f < MLP_MAX_LEVELS; ++f) R += (f < L ? level_m[f] : 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) level_m[L] = R;   // R = sum of Mf, for TrimInstances
+    const unsigned items = (unsigned)B * (unsigned)R;          // <= L * B * m_rows < 2^31 (host check)
+    if (blockIdx.x >= items) return;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     const int npix = ch * cw;
-    const int C4 = Cf >> 2;
     const bool vec = (Cf & 3) == 0;
-    // One CTA per (level, image, slot) over the CAPACITY m_rows (not a persistent grid: the
-    // stage is write-dominated and short-lived CTAs stream best, see paste.cu); slots past the
-    // device-side Mf exit at once.
-    const int64_t items = (int64_t)L * B * m_rows;
+    uint32_t phase = 0;                        // parity of the next mbarrier phase to wait for
 
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int slot = (int)(item % m_rows);
-        const int fb = (int)(item / m_rows);
-        const int f = fb / B, b = fb - f * B;
-        const int mf = s_mf[f];
-        if (slot >= mf) continue;
+    // item = (image b, row r of roi_boxes) -> (level f, slot): the output order of the reference
+    for (unsigned item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = (int)(item / (unsigned)R), r = (int)(item - (unsigned)b * (unsigned)R);
+        int f = 0, foff = 0, mf = 0;
+        {
+            int o = 0;
+#pragma unroll
+            for (int q = 0; q < MLP_MAX_LEVELS; ++q) {
+                const int m = q < L ? level_m[q] : 0;        // L1/L2 hits after the first read
+                if (q < L && r >= o) { f = q; foff = o; mf = m; }
+                o += m;
+            }
+        }
+        const int slot = r - foff;
         const int cnt = counts[f * B + b];
         float* out = lv.crops[f] + ((int64_t)b * mf + slot) * npix * Cf;
-        float* rb = roi_boxes + ((int64_t)b * R + s_off[f] + slot) * 6;
+        float* rb = roi_boxes + (int64_t)item * 6;
 
         if (slot >= cnt) {                                   // MoldBatch padding
             if (threadIdx.x < 6) rb[threadIdx.x] = -1.0f;
-            const int64_t n = (int64_t)npix * Cf;
+            const int n = npix * Cf;
             if (vec) {
                 float4* o4 = reinterpret_cast<float4*>(out);
                 const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
-                for (int64_t i = threadIdx.x; i < (n >> 2); i += kRoiThreads) stg_stream_f4(o4 + i, m1);
+                for (int i = threadIdx.x; i < (n >> 2); i += nthreads) stg_stream_f4(o4 + i, m1);
             } else {
-                for (int64_t i = threadIdx.x; i < n; i += kRoiThreads) out[i] = -1.0f;
+                for (int i = threadIdx.x; i < n; i += nthreads) out[i] = -1.0f;
             }
             continue;
         }
-        const int j = roi_src[((int64_t)f * B + b) * m_rows + slot];
-        const float* row = dist + ((int64_t)b * m_stride + j) * 7;
         const int Hf = lv.fh[f], Wf = lv.fw[f];
-        __syncthreads();                                     // previous RoI done with the tables
-        if (threadIdx.x < 6) rb[threadIdx.x] = row[1 + threadIdx.x];
-        if (threadIdx.x < ch + cw) {
-            // NormalizeBoxes(shape=image) then crop_and_resize source coordinates
-            const bool is_y = threadIdx.x < ch;
-            const int idx = is_y ? threadIdx.x : threadIdx.x - ch;
-            const float c = is_y ? row[2] : row[1];          // cy : cx
-            const float s = is_y ? row[4] : row[3];          // h  : w
-            const float dim = is_y ? image_h : image_w;
-            const float half = __fdiv_rn(s, 2.0f);
-            const float lo = __fdiv_rn(__fsub_rn(c, half), dim);      // y1 : x1
-            const float hi = __fdiv_rn(__fadd_rn(c, half), dim);      // y2 : x2
-            const int nout = is_y ? ch : cw;
-            const float fm1 = (float)((is_y ? Hf : Wf) - 1);
-            float in;
-            if (nout > 1) {
-                const float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), fm1), (float)(nout - 1));
-                in = __fadd_rn(__fmul_rn(lo, fm1), __fmul_rn((float)idx, scale));
-            } else {
-                in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo, hi)), fm1);
-            }
-            if (is_y) s_iny[idx] = in; else s_inx[idx] = in;
-        }
-        __syncthreads();
-        {
-            const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
-            for (int p = threadIdx.x; p < npix; p += kRoiThreads) {
-                const int y = p / cw, x = p - y * cw;
-                const float in_y = s_iny[y], in_x = s_inx[x];
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                float2 w = make_float2(-1.0f, 0.0f);
-                // TF: in < 0 || in > size-1 -> extrapolation value; NaN counts as outside
-                if (in_y >= 0.0f && in_y <= hm1 && in_x >= 0.0f && in_x <= wm1) {
-                    const float fy = floorf(in_y), fx = floorf(in_x);
-                    const int top = (int)fy, bot = (int)ceilf(in_y);
-                    const int left = (int)fx, right = (int)ceilf(in_x);
-                    w = make_float2(__fsub_rn(in_x, fx), __fsub_rn(in_y, fy));
-                    o = make_uint4((unsigned)((top * Wf + left) * Cf) * 4u, (unsigned)((top * Wf + right) * Cf) * 4u,
-                                   (unsigned)((bot * Wf + left) * Cf) * 4u, (unsigned)((bot * Wf + right) * Cf) * 4u);
-                }
-                s_poff[p] = o;
-                s_pw[p] = w;
-            }
-        }
-        __syncthreads();
         const float* img = lv.fmap[f] + (int64_t)b * Hf * Wf * Cf;
-        // each warp owns kPixUnroll consecutive output pixels per iteration
-        for (int p0 = warp * kPixUnroll; p0 < npix; p0 += nwarps * kPixUnroll) {
-            if (vec) {
-                for (int c4 = lane; c4 < C4; c4 += 32) {
-                    float4 tl[kPixUnroll], tr[kPixUnroll], bl[kPixUnroll], br[kPixUnroll];
-                    float2 w[kPixUnroll];
-                    // 64-bit lane base + 32-bit unsigned byte offsets: two adds per address
-                    const char* base = reinterpret_cast<const char*>(img) + c4 * 16;
-#pragma unroll
-                    for (int u = 0; u < kPixUnroll; ++u) {            // 16 loads in flight
-                        const int p = min(p0 + u, npix - 1);
-                        const uint4 o = s_poff[p];
-                        w[u] = s_pw[p];
-                        tl[u] = __ldg(reinterpret_cast<const float4*>(base + o.x));
-                        tr[u] = __ldg(reinterpret_cast<const float4*>(base + o.y));
-                        bl[u] = __ldg(reinterpret_cast<const float4*>(base + o.z));
-                        br[u] = __ldg(reinterpret_cast<const float4*>(base + o.w));
-                    }
-                    float4* obase = reinterpret_cast<float4*>(out + (int64_t)p0 * Cf) + c4;
-#pragma unroll
-                    for (int u = 0; u < kPixUnroll; ++u) {
-                        const float lx = w[u].x, ly = w[u].y;
-                        const bool inside = lx >= 0.0f;               // else extrapolation_value = 0
-                        // bilinear: top/bottom lerp in x, then lerp in y (crop_and_resize order),
-                        // adds packed two channels per instruction
-                        const uint64_t t0 = lerp2_rn(pack2(tl[u].x, tl[u].y), pack2(tr[u].x, tr[u].y), lx);
-                        const uint64_t t1 = lerp2_rn(pack2(tl[u].z, tl[u].w), pack2(tr[u].z, tr[u].w), lx);
-                        const uint64_t b0 = lerp2_rn(pack2(bl[u].x, bl[u].y), pack2(br[u].x, br[u].y), lx);
-                        const uint64_t b1 = lerp2_rn(pack2(bl[u].z, bl[u].w), pack2(br[u].z, br[u].w), lx);
-                        float4 r;
-                        unpack2(lerp2_rn(t0, b0, ly), r.x, r.y);
-                        unpack2(lerp2_rn(t1, b1, ly), r.z, r.w);
-                        if (!inside) r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p0 + u < npix) stg_stream_f4(obase + (size_t)u * C4, r);
-                    }
+        __syncthreads();                                     // previous RoI done with tables + window
+        if (warp == 0) {
+            // ---- the whole per-RoI setup in one warp, one barrier for everybody else
+            const int j = roi_src[((int64_t)f * B + b) * m_rows + slot];
+            const float* row = dist + ((int64_t)b * m_stride + j) * 7;
+            const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
+            if (lane < 6) rb[lane] = row[1 + lane];
+            int ylo = INT_MAX, yhi = -1, xlo = INT_MAX, xhi = -1;
+            for (int i = lane; i < ch + cw; i += 32) {
+                // NormalizeBoxes(shape=image) then crop_and_resize source coordinates
+                const bool is_y = i < ch;
+                const int idx = is_y ? i : i - ch;
+                const float c = is_y ? row[2] : row[1];          // cy : cx
+                const float s = is_y ? row[4] : row[3];          // h  : w
+                const float dim = is_y ? image_h : image_w;
+                const float half = __fdiv_rn(s, 2.0f);
+                const float lo = __fdiv_rn(__fsub_rn(c, half), dim);      // y1 : x1
+                const float hi = __fdiv_rn(__fadd_rn(c, half), dim);      // y2 : x2
+                const int nout = is_y ? ch : cw;
+                const float fm1 = is_y ? hm1 : wm1;
+                float in;
+                if (nout > 1) {
+                    const float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), fm1), (float)(nout - 1));
+                    in = __fadd_rn(__fmul_rn(lo, fm1), __fmul_rn((float)idx, scale));
+                } else {
+                    in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo, hi)), fm1);
                 }
-            } else {
-#pragma unroll
-                for (int u = 0; u < kPixUnroll; ++u) {
-                    const int p = p0 + u;
-                    if (p >= npix) continue;
-                    const uint4 o = s_poff[p];
-                    const float2 w = s_pw[p];
-                    float* op = out + p * Cf;
-                    for (int c = lane; c < Cf; c += 32) {
-                        float r = 0.0f;
-                        if (w.x >= 0.0f) {
-                            const float tl = img[(o.x >> 2) + c], tr = img[(o.y >> 2) + c], bl = img[(o.z >> 2) + c], br = img[(o.w >> 2) + c];
-                            const float t_ = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), w.x));
-                            const float b_ = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), w.x));
-                            r = __fadd_rn(t_, __fmul_rn(__fsub_rn(b_, t_), w.y));
-                        }
-                        op[c] = r;
-                    }
+                // TF: in < 0 || in > size-1 -> extrapolation value; NaN counts as outside
+                const bool ok = in >= 0.0f && in <= fm1;
+                if (is_y) {
+                    S.iny[idx] = in;
+                    if (ok) { ylo = min(ylo, (int)floorf(in)); yhi = max(yhi, (int)ceilf(in)); }
+                } else {
+                    S.inx[idx] = in;
+                    if (ok) { xlo = min(xlo, (int)floorf(in)); xhi = max(xhi, (int)ceilf(in)); }
                 }
             }
+            for (int o = 16; o > 0; o >>= 1) {
+                ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+                yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+                xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+                xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+            }
+            // source window of the valid samples; if it fits, TMA it into shared memory (one
+            // cp.async.bulk per window row - rows are contiguous in NHWC), else rows come from global
+            const bool any = yhi >= 0 && xhi >= 0;
+            const int rows = any ? yhi - ylo + 1 : 0, cols = any ? xhi - xlo + 1 : 0;
+            const int64_t row_bytes = (int64_t)cols * Cf * 4;
+            const bool staged = any && vec && row_bytes * rows <= window_cap;
+            if (staged) {
+                if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(row_bytes * rows));
+                __syncwarp();
+                // generic-proxy reads of the previous RoI's window (ordered by the barrier above)
+                // before the async proxy overwrites it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int q = lane; q < rows; q += 32)
+                    tma_load_1d(s_window + (size_t)q * row_bytes,
+                                img + ((int64_t)(ylo + q) * Wf + xlo) * Cf, (uint32_t)row_bytes, &s_bar);
+            }
+            const int top0 = staged ? ylo : 0, left0 = staged ? xlo : 0, pitch = staged ? cols : Wf;
+            __syncwarp();
+            for (int i = lane; i < cw; i += 32) {            // column table
+                const float in_x = S.inx[i];
+                uint32_t xl = 0, xr = 0;
+                float lx = -1.0f;
+                if (in_x >= 0.0f && in_x <= wm1) {
+                    const float fx = floorf(in_x);
+                    lx = __fsub_rn(in_x, fx);
+                    xl = (uint32_t)(((int)fx - left0) * Cf) * 4u;
+                    xr = (uint32_t)(((int)ceilf(in_x) - left0) * Cf) * 4u;
+                }
+                S.xl[i] = xl; S.xr[i] = xr; S.lx[i] = lx;
+            }
+            if (lane == 0) {                                 // row schedule (serial, ch steps)
+                const uint32_t pitch_bytes = (uint32_t)(pitch * Cf) * 4u;
+                const uint32_t ystride = (uint32_t)(cw * Cf) * 4u;
+                int K = 0, no = 0, nz = 0;
+                int prev = INT_MIN, cur = INT_MIN;           // source rows held in hp / hc
+                for (int y = 0; y < ch; ++y) {
+                    const float v = S.iny[y];
+                    if (!(v >= 0.0f && v <= hm1)) { S.zoff[nz++] = (uint32_t)y * ystride; continue; }
+                    const float fy = floorf(v);
+                    const int t = (int)fy, bo = (int)ceilf(v);
+                    // make hp = H(t), hc = H(bo) with as few new rows as possible
+                    int npush = 0, first = bo;
+                    if (prev == t && cur == bo) npush = 0;
+                    else if (cur == t) npush = 1;
+                    else { npush = 2; first = t; }
+                    if (npush == 2) {
+                        S.obeg[K] = (unsigned short)no;
+                        S.rowoff[K++] = (uint32_t)(first - top0) * pitch_bytes;
+                    }
+                    if (npush >= 1) {
+                        S.obeg[K] = (unsigned short)no;
+                        S.rowoff[K++] = (uint32_t)(bo - top0) * pitch_bytes;
+                    }
+                    prev = t; cur = bo;
+                    S.out[no].yoff = (uint32_t)y * ystride;
+                    S.out[no].ly = __fsub_rn(v, fy);
+                    ++no;
+                }
+                S.obeg[K] = (unsigned short)no;
+                S.nrows = K; S.nzero = nz; S.staged = staged;
+            }
+        }
+        __syncthreads();
+        if (S.staged) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            roi_columns<float4, true>(s_window, S, out, ch, cw, Cf, warp, lane, nwarps);
+        } else if (vec) {
+            roi_columns<float4, false>(reinterpret_cast<const unsigned char*>(img), S, out, ch, cw, Cf, warp, lane,
+                                       nwarps);
+        } else {
+            roi_columns<float, false>(reinterpret_cast<const unsigned char*>(img), S, out, ch, cw, Cf, warp, lane,
+                                      nwarps);
         }
     }
 }
@@ -340,7 +469,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     MLP_CHECK_ARG(channels >= 1 && batch >= 1 && m_rows >= 1 && m_stride >= m_rows,
                   "mlp_roi_align_run: bad shape");
     MLP_CHECK_ARG(crop_h >= 1 && crop_w >= 1 && crop_h <= kMaxCrop && crop_w <= kMaxCrop &&
-                      crop_h + crop_w <= kRoiThreads && crop_h * crop_w <= kMaxPix,
+                      crop_h + crop_w <= 2 * kMaxCrop,
                   "mlp_roi_align_run: crop size %dx%d out of range [1,%d]", crop_h, crop_w, kMaxCrop);
     MLP_CHECK_ARG(ctx->arena[MLP_ARENA_ROI] &&
                       ctx->arena_bytes[MLP_ARENA_ROI] >= (int64_t)num_levels * batch * m_rows * 4,
@@ -364,10 +493,30 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     ProfScope prof(ctx, MLP_ST_ROI_ALIGN, (cudaStream_t)stream);
     const int64_t items = (int64_t)num_levels * batch * m_rows;
     const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-    roi_align_kernel<<<grid, kRoiThreads, 0, (cudaStream_t)stream>>>(
+    int window_cap = kRoiWindowBytes;
+    if (const char* e = getenv("MLP_ROI_WINDOW_KB")) window_cap = atoi(e) * 1024;    // tuning knob; 0 = never stage
+    if (window_cap < 0) window_cap = 0;
+    if (window_cap > 160 * 1024) window_cap = 160 * 1024;
+    // warp-tasks per RoI = crop_w columns x groups of 32 channel vectors; pick the warp count
+    // (<= 8) that leaves no idle warp in the last round
+    const int cv = (channels & 3) ? channels : channels / 4;
+    const int tasks = crop_w * ((cv + 31) / 32);
+    int nwarps = 7;
+    double best = 2.0;
+    for (int w = 7; w >= 4; --w) {
+        const int rounds = (tasks + w - 1) / w;
+        const double idle = 1.0 - (double)tasks / (rounds * w);
+        if (idle < best - 1e-9) { best = idle; nwarps = w; }
+    }
+    if (const char* e = getenv("MLP_ROI_WARPS")) nwarps = atoi(e);
+    if (nwarps < 1) nwarps = 1;
+    if (nwarps > kRoiThreads / 32) nwarps = kRoiThreads / 32;
+    const size_t smem = (size_t)window_cap;
+    MLP_CUDA(cudaFuncSetAttribute(roi_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_kernel<<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
         lv, num_levels, channels, dist_dev, batch, m_rows, m_stride, image_h, image_w, crop_h, crop_w,
         static_cast<const int32_t*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev,
-        level_m_dev, roi_boxes_dev);
+        level_m_dev, roi_boxes_dev, window_cap);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }

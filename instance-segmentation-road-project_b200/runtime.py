@@ -101,7 +101,8 @@ _lib_lock = threading.Lock()
 
 
 def library_path():
-    return _build.LIB_PATH
+    """The in-tree library; MASKLAB_B200_LIB points at another BUILD of the same sources (A/B tuning)."""
+    return os.environ.get("MASKLAB_B200_LIB") or _build.LIB_PATH
 
 
 def load_library():
