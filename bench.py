@@ -440,43 +440,48 @@ def algorithmic_bytes(wl, N, M):
 def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
-    host memory.  Three streams (copy-in, compute, copy-out) so that the input copy of step i+1
-    overlaps the output copy of step i (PCIe is full duplex); one set of device buffers."""
+    host memory.  Three streams (copy-in, compute, copy-out) and two sets of device input buffers,
+    so that the input copy of step i+1 overlaps the compute and the output copy of step i (PCIe
+    is full duplex); every byte of every step still crosses PCIe inside the timed region."""
     import torch
     import torch.distributed as dist
     B, PH, PW = wl["B"], wl["PH"], wl["PW"]
-    d_loc = torch.empty_like(h_loc, device="cuda")
-    d_cls = torch.empty_like(h_cls, device="cuda")
-    d_fmaps = [torch.empty_like(f, device="cuda") for f in h_fmaps]
-    d_masks = torch.empty_like(h_masks, device="cuda")
+    # two sets of device input buffers: the copy-in of step i+1 runs while step i computes
+    NB = 2
+    d_in = [dict(loc=torch.empty_like(h_loc, device="cuda"), cls=torch.empty_like(h_cls, device="cuda"),
+                 fmaps=[torch.empty_like(f, device="cuda") for f in h_fmaps],
+                 masks=torch.empty_like(h_masks, device="cuda"), free=None) for _ in range(NB)]
     out_det = torch.empty((B * M * 6,), dtype=torch.int32).pin_memory()
     out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps)
     d2h = out_det.numel() * 4 + out_masks.numel()
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    state = {"cmp_done": None, "out_done": None}
+    state = {"i": 0, "out_done": None}
 
     def step():
+        buf = d_in[state["i"] % NB]
+        state["i"] += 1
         with torch.cuda.stream(s_in):
-            if state["cmp_done"] is not None:
-                s_in.wait_event(state["cmp_done"])          # device inputs free again
-            d_loc.copy_(h_loc, non_blocking=True)
-            d_cls.copy_(h_cls, non_blocking=True)
-            for d, h in zip(d_fmaps, h_fmaps):
+            if buf["free"] is not None:
+                s_in.wait_event(buf["free"])                # the step that used this set has computed
+            buf["loc"].copy_(h_loc, non_blocking=True)
+            buf["cls"].copy_(h_cls, non_blocking=True)
+            for d, h in zip(buf["fmaps"], h_fmaps):
                 d.copy_(h, non_blocking=True)
-            d_masks.copy_(h_masks, non_blocking=True)
+            buf["masks"].copy_(h_masks, non_blocking=True)
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in)
             if state["out_done"] is not None:
                 s_cmp.wait_event(state["out_done"])         # previous results copied out
-            r = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
-            det_i32, pasted, _ = pipe.trim_and_paste(r, d_masks)
-            state["cmp_done"] = torch.cuda.Event()
-            state["cmp_done"].record(s_cmp)
+            r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"])
+            det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
+            cmp_done = torch.cuda.Event()
+            cmp_done.record(s_cmp)
+            buf["free"] = cmp_done
         with torch.cuda.stream(s_out):
-            s_out.wait_event(state["cmp_done"])
+            s_out.wait_event(cmp_done)
             out_det.copy_(det_i32[:out_det.numel()], non_blocking=True)
             out_masks.copy_(pasted[:out_masks.numel()], non_blocking=True)
             state["out_done"] = torch.cuda.Event()

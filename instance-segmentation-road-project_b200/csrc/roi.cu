@@ -70,7 +70,7 @@ roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
 // Per RoI warp 0 builds the schedule once: the list of source rows to load, and after each row
 // the outputs (row offset, ly) that become computable as lerp(hp, hc, ly).
 constexpr int kMaxRows = 2 * kMaxCrop;       // worst case two new source rows per output row
-constexpr int kRoiWindowBytes = 48 * 1024;   // FPN window staged in shared memory per RoI
+constexpr int kRoiWindowBytes = 40 * 1024;   // FPN window staged in shared memory per RoI (5 CTAs per SM)
 
 struct RoiOut { uint32_t yoff; float ly; };  // byte offset of the output row inside the crop, y weight
 struct RoiSched {                            // per-RoI tables, built once per CTA by warp 0

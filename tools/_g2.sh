@@ -1,4 +1,4 @@
-for kb in 0 48; do
-MLP_ROI_WINDOW_KB=$kb timeout 600 ncu --set full --clock-control none --import-source on -k regex:roi_align --launch-skip 3 -c 1 -f -o gpurun_out/roi_col_kb$kb python bench.py --steps 3 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_roi_kb$kb.log 2>&1
-tail -3 gpurun_out/ncu_roi_kb$kb.log
-done
+timeout 600 python bench.py --steps 2 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/plain_r01b.log 2>&1 || exit 1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01b.csv python bench.py --steps 2 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_r01b.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --launch-skip 24 -c 6 -f -o gpurun_out/prof_r01b_full python bench.py --steps 2 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_r01b.log 2>&1
+tail -2 gpurun_out/ncu_full_r01b.log
