@@ -3,3 +3,4 @@ from .base import Layer, get_custom_objects                                    #
 from .detection import PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal   # noqa: F401
 from .instance import MaskDistribute, PyramidRoiAlign, TrimInstances          # noqa: F401
 from .misc import MoldBatch, UpSampleOutput, CropAndPadMask                   # noqa: F401
+from .summary import CrackToInstance, SummaryOutput, IncludeMyRoad, CalculateInstanceSize   # noqa: F401

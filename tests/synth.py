@@ -71,3 +71,52 @@ def detections(B, M, C, H, W, seed=3, lo=16.0, hi=400.0, pad_tail=0):
     if pad_tail:
         det[:, M - pad_tail:] = -1
     return det
+
+
+def semantic_map(B, PH, PW, S=3, seed=4, crack=True, road=True):
+    """Stand-in for UpSampleOutput's thresholded semantic map, int32 {0,1} [B,PH,PW,S]:
+    channel 1 (my_road) is a noisy trapezoid widening towards the bottom of the frame with a few
+    gaps (rows without road, single-pixel rows), channel 2 (crack) a few thin random strokes,
+    channel 0 background."""
+    rng = np.random.default_rng(seed)
+    seg = np.zeros((B, PH, PW, S), dtype=np.int32)
+    ys = np.arange(PH)
+    for b in range(B):
+        if road:
+            top = int(PH * rng.uniform(0.25, 0.45))
+            cx = PW * rng.uniform(0.4, 0.6)
+            half_top, half_bot = PW * rng.uniform(0.02, 0.06), PW * rng.uniform(0.25, 0.45)
+            t = np.clip((ys - top) / max(PH - 1 - top, 1), 0, 1)
+            left = np.round(cx - (half_top + (half_bot - half_top) * t) + rng.normal(0, 1.5, PH)).astype(int)
+            right = np.round(cx + (half_top + (half_bot - half_top) * t) + rng.normal(0, 1.5, PH)).astype(int)
+            for y in range(top, PH):
+                if rng.random() < 0.03:
+                    continue                                   # a row without road pixels
+                lo, hi = max(left[y], 0), min(right[y], PW - 1)
+                if rng.random() < 0.02:
+                    hi = lo                                    # single-pixel row (x_min == x_max)
+                if hi >= lo:
+                    seg[b, y, lo:hi + 1, 1] = 1
+                    holes = rng.random(hi + 1 - lo) < 0.01     # interior holes do not move the borders
+                    holes[[0, -1]] = False
+                    seg[b, y, lo:hi + 1, 1][holes] = 0
+        if crack and S > 2:
+            for _ in range(int(rng.integers(0, 3))):
+                y0, x0 = int(rng.integers(PH // 2, PH)), int(rng.integers(0, PW))
+                for k in range(int(rng.integers(5, 40))):
+                    y, x = y0 + k // 2, x0 + k + int(rng.integers(-1, 2))
+                    if 0 <= y < PH and 0 <= x < PW:
+                        seg[b, y, x, 2] = 1
+        seg[b, :, :, 0] = 1 - np.clip(seg[b, :, :, 1:].sum(-1), 0, 1)
+    return seg
+
+
+def int_detections(B, M, C, PH, PW, seed=5, pad_tail=0):
+    """det_outs as UpSampleOutput returns them: int32 [B,M,6] (cx,cy,w,h,class,conf*100)."""
+    rng = np.random.default_rng(seed)
+    det = np.stack([rng.integers(0, PW, (B, M)), rng.integers(0, PH, (B, M)),
+                    rng.integers(2, max(3, PW // 3), (B, M)), rng.integers(2, max(3, PH // 3), (B, M)),
+                    rng.integers(0, C, (B, M)), rng.integers(51, 100, (B, M))], axis=-1).astype(np.int32)
+    if pad_tail:
+        det[:, M - pad_tail:] = np.array([-1, -1, -1, -1, -1, -100], dtype=np.int32)
+    return det

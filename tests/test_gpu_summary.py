@@ -1,0 +1,112 @@
+"""GPU parity of the SummaryOutput family against oracle/summary_oracle.py,
+through the C ABI (mlp_road_scan, mlp_summary_output) and the drop-in layers.
+
+Integer-valued columns, the metres-per-pixel table and include_my_road are bit-exact; the four
+float reductions are float64 sums rounded to float32 on both sides - equal up to the summation
+order of the float64 accumulation, compared with rtol 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import masklab_oracle as mo
+from oracle import summary_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def pasted(B, M, C, PH, PW, seed, pad_tail=1):
+    det = synth.int_detections(B, M, C, PH, PW, seed=seed, pad_tail=pad_tail)
+    rng = np.random.default_rng(seed + 1)
+    ins = (rng.random((B, M, 28, 28)) > 0.45).astype(np.int32)
+    return det, mo.crop_and_pad_mask((PH, PW), det, ins)
+
+
+def check_summary(got, want):
+    assert got.shape == want.shape
+    assert np.array_equal(got[..., :6], want[..., :6])
+    assert np.array_equal(got[..., 10], want[..., 10])
+    np.testing.assert_allclose(got[..., 6:10], want[..., 6:10], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("PH,PW", [(48, 80), (64, 1100), (37, 53)])
+def test_unit_lengths_bitexact(PH, PW):
+    import masklab_b200 as ml
+    from masklab_b200.layers import summary as ls
+    B = 3
+    seg = synth.semantic_map(B, PH, PW, seed=PH)
+    seg[2, :, :, 1] = 0                                         # an image without road
+    ctx = ml.Context.get()
+    unit, bits, box = ls.road_scan(ctx, dev(seg), 3.25, True)
+    want = np.stack([so.road_unit_lengths(seg[b, :, :, 1]) for b in range(B)])
+    assert np.array_equal(unit.cpu().numpy(), want)
+    packed = np.packbits(seg[..., 1].astype(np.uint8), axis=-1, bitorder="little")
+    gotbits = bits.cpu().numpy().view(np.uint8)[..., :packed.shape[-1]]
+    assert np.array_equal(gotbits, packed)
+    idx = np.argwhere(seg[..., 2] != 0)
+    if idx.size:
+        assert box.tolist() == [idx[:, 1].min(), idx[:, 2].min(), idx[:, 1].max(), idx[:, 2].max()]
+
+
+@pytest.mark.parametrize("PH,PW,M,dtype", [(48, 80, 5, "f32"), (64, 1100, 3, "f32"), (37, 53, 4, "f32"),
+                                           (48, 80, 5, "u8"), (40, 1030, 2, "u8")])
+def test_summary_output_matches_oracle(PH, PW, M, dtype):
+    import masklab_b200 as ml
+    B, C = 2, 4
+    seg = synth.semantic_map(B, PH, PW, seed=7 + PW)
+    seg[0, PH // 2:PH // 2 + 4, 3:PW // 2, 2] = 1                # make sure there is a crack region
+    det, masks = pasted(B, M, C, PH, PW, seed=PW)
+    if dtype == "u8":
+        masks = (masks > 0.5).astype(np.uint8)
+    want = so.summary_output(det, seg, masks.astype(np.float32))
+    got = ml.SummaryOutput(default_road_size=3.25)([dev(det), dev(seg), dev(masks)])
+    assert want.shape[1] == M + 1
+    check_summary(got.cpu().numpy(), want)
+
+
+def test_summary_without_crack_and_without_road():
+    import masklab_b200 as ml
+    B, M, C, PH, PW = 2, 3, 4, 40, 64
+    seg = synth.semantic_map(B, PH, PW, seed=3, crack=False, road=False)
+    det, masks = pasted(B, M, C, PH, PW, seed=9)
+    want = so.summary_output(det, seg, masks)
+    got = ml.SummaryOutput()([dev(det), dev(seg), dev(masks)]).cpu().numpy()
+    assert want.shape == (B, M, 11)
+    check_summary(got, want)
+    # zero-area crack region (one row): conf = 0 -> not appended
+    seg[1, 5, 3:20, 2] = 1
+    want = so.summary_output(det, seg, masks)
+    got = ml.SummaryOutput()([dev(det), dev(seg), dev(masks)]).cpu().numpy()
+    assert want.shape == (B, M, 11)
+    check_summary(got, want)
+
+
+def test_member_layers():
+    import masklab_b200 as ml
+    B, M, C, PH, PW = 2, 4, 4, 56, 96
+    seg = synth.semantic_map(B, PH, PW, seed=21)
+    det, masks = pasted(B, M, C, PH, PW, seed=22)
+    inc = ml.IncludeMyRoad(threshold=0.1)([dev(seg), dev(masks)]).cpu().numpy()
+    assert np.array_equal(inc, so.include_my_road(seg, masks, 0.1))
+    inc5 = ml.IncludeMyRoad(threshold=0.5)([dev(seg), dev(masks)]).cpu().numpy()
+    assert np.array_equal(inc5, so.include_my_road(seg, masks, 0.5))
+    size = ml.CalculateInstanceSize(default_road_size=2.5)([dev(seg), dev(masks)]).cpu().numpy()
+    np.testing.assert_allclose(size, so.calculate_instance_size(seg, masks, 2.5), rtol=1e-6)
+    cdet, cseg = ml.CrackToInstance()(dev(seg[..., 2]))
+    wdet, wseg = so.crack_to_instance(seg[..., 2])
+    assert np.array_equal(cdet.cpu().numpy(), wdet) and np.array_equal(cseg.cpu().numpy(), wseg)
+    e_det, _ = ml.CrackToInstance()(dev(np.zeros((2, 8, 8), dtype=np.int32)))
+    assert np.array_equal(e_det.cpu().numpy(), so.crack_to_instance(np.zeros((2, 8, 8), np.int32))[0])
+    cfg = ml.SummaryOutput(default_road_size=3.0).get_config()
+    assert cfg["default_road_size"] == 3.0 and "SummaryOutput" in ml.get_custom_objects()
+
+
+def test_summary_rejects_cpu_tensors():
+    import masklab_b200 as ml
+    det = torch.zeros((1, 1, 6), dtype=torch.int32)
+    with pytest.raises(ml.InvalidArgumentError):
+        ml.SummaryOutput()([det, torch.zeros((1, 8, 8, 3), dtype=torch.int32), torch.zeros((1, 1, 8, 8))])
