@@ -222,6 +222,8 @@ int mlp_upsample_output(mlp_ctx* ctx, const float* det_dev, int64_t rows, float 
 #define MLP_PASTE_U8  1   /* canonical binary mask (value > 0.5, misc.py:457,:611-615) */
 #define MLP_PASTE_BITS 2  /* the same binary mask, 1 bit per pixel: [B,M,PH,PW/8] uint8, bit k of byte i
                              = pixel 8*i+k (numpy packbits bitorder='little'); PW % 8 == 0       */
+#define MLP_PASTE_NONE 3  /* mlp_trim_paste only: prepare the tail (int boxes, tile table), write no masks;
+                           * out_dev may be NULL and M is left to mlp_tile_summary                    */
 /* det_i32_dev [B,M,6], masks_i32_dev i32 [B,M,mh,mw] -> out_dev [B,M,PH,PW].
  * M is read from m_dev (i32 [1]) when not NULL, else m_rows; m_stride is the row
  * stride of det/masks per image.  A box clipped to zero area gives an all-zero mask
@@ -296,6 +298,23 @@ int mlp_mold_batch_run(mlp_ctx* ctx, const void* x_dev, const int32_t* counts_de
  *   M from m_dev (i32 [1]) when not NULL, else m_rows; m_stride 0 = compact.  With crack_box_dev
  *   not NULL the crack pseudo-instance (mask = seg channel crack_channel) is appended when its box
  *   has positive area: M' = M + 1, written to m_out_dev; out_dev needs B*(m_rows+1)*11 floats.   */
+/* mlp_tile_summary: the same [B,M',11] summary WITHOUT the [B,M,PH,PW] tensor - every instance's
+ *   float32 paste values are evaluated inside its clipped box straight from its 28x28 tile (exactly
+ *   the values mlp_crop_and_pad_mask(MLP_PASTE_F32) would write) and reduced on the fly, so the
+ *   largest tensor of the path is neither written nor re-read.  Two sources:
+ *   masks_i32_dev != NULL : int32 tiles [B,m_stride,mh,mw] + det_i32_dev [B,m_stride,6], M from
+ *                           m_dev / m_rows (the standalone CropAndPadMask inputs);
+ *   masks_i32_dev == NULL : the fused tail - call mlp_trim_paste (any out_mode, MLP_PASTE_NONE to skip
+ *                           the masks altogether) with the same ctx, shapes and stream first; tiles come
+ *                           from roi_masks_dev [B,R,mh,mw,C] through the tail's slot table, m_rows =
+ *                           m_stride = k_rows, counts_dev from that call; M is written to m_dev_out.  */
+int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* masks_i32_dev,
+                     const float* roi_masks_dev, int r_rows, const int32_t* r_dev, int num_classes,
+                     const int32_t* counts_dev, int batch, int m_rows, int m_stride, const int32_t* m_dev,
+                     int mask_h, int mask_w, const int32_t* seg_dev, const float* unit_dev,
+                     const uint32_t* road_bits_dev, const int32_t* crack_box_dev, int frame_h, int frame_w,
+                     int channels, int crack_channel, float include_threshold, float* out_dev,
+                     int32_t* m_out_dev, int32_t* m_dev_out, mlp_stream_t stream);
 int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, int frame_h, int frame_w,
                   int channels, int road_channel, int crack_channel, float default_road_size,
                   float* unit_dev, uint32_t* road_bits_dev, int32_t* crack_box_dev, mlp_stream_t stream);

@@ -41,7 +41,8 @@ def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "masklab_b200.h"),
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "paste_common.cuh"),
+                        os.path.join(INCLUDE, "masklab_b200.h"),
                         os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 

@@ -1,0 +1,183 @@
+// paste_common.cuh — pieces of CropAndPadMask shared by the paste kernels (paste.cu) and the
+// per-instance reductions evaluated straight from the mask tiles (summary.cu): where an instance's
+// 28x28 tile comes from, the clipped box geometry and the two-stage lerp of
+// /root/reference/engine/layers/misc.py:373-391 (tf.image.resize, align_corners=True).
+#pragma once
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxTile = 64 * 64;         // mask_h * mask_w <= 4096
+
+// Where the per-instance mask tile and the batch-wide scalars come from.
+//   standalone layer : int32 masks [B,stride,mh*mw]; M from m_dev/m_rows; threshold from thr_dev
+//   fused tail       : the class channel of the mask head output roi_masks [B,R,mh*mw,C] picked
+//                      through the slot->row table of tail_prep_kernel and thresholded at 0.5 on
+//                      the fly (TrimInstances + UpSampleOutput never materialise); M and the
+//                      confidence threshold are reduced from the per-image counts / conf maxima.
+struct PasteSrc {
+    const int32_t* masks_i32;
+    const int32_t* m_dev;
+    const int32_t* thr_dev;
+    int fused;
+    const float* roi_masks;
+    const int32_t* tail_src;      // [B, m_stride] row of roi_masks, -1 = MoldBatch padding
+    const uint32_t* tail_bits;    // [B, m_stride, mh] bit rows of the thresholded class channel (mw <= 32), or NULL
+    const int32_t* r_dev;
+    int r_rows;
+    int C;
+    const int32_t* counts;        // [B] valid instances per image
+    const int32_t* confmax;       // [B] max int confidence of the valid rows (INT_MIN if none)
+    int32_t* m_out;               // [1] M written back for the host
+};
+
+struct PasteGeom {
+    int xmin, xmax, ymin, ymax;
+    float sy, sx;          // resize scales (in-1)/(out-1) or in/out
+    bool active;
+};
+
+// misc.py:373-386: box = max(box,1) -> float; ceil(c -/+ s/2) -> int -> clip.
+__device__ __forceinline__ PasteGeom paste_geometry(const int32_t* row, int thr, int mh, int mw, int PH,
+                                                    int PW) {
+    PasteGeom g;
+    const int conf = row[5];
+    const float cx = (float)max(row[0], 1), cy = (float)max(row[1], 1);
+    const float w = (float)max(row[2], 1), h = (float)max(row[3], 1);
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    g.xmin = min(max(__float2int_rz(ceilf(__fsub_rn(cx, hw))), 0), PW);
+    g.xmax = min(max(__float2int_rz(ceilf(__fadd_rn(cx, hw))), 0), PW);
+    g.ymin = min(max(__float2int_rz(ceilf(__fsub_rn(cy, hh))), 0), PH);
+    g.ymax = min(max(__float2int_rz(ceilf(__fadd_rn(cy, hh))), 0), PH);
+    const int oh = g.ymax - g.ymin, ow = g.xmax - g.xmin;
+    g.active = (conf >= thr) && oh > 0 && ow > 0;
+    // CalculateResizeScale(in, out, align_corners=true)
+    g.sy = (oh > 1) ? __fdiv_rn((float)(mh - 1), (float)(oh - 1)) : __fdiv_rn((float)mh, (float)max(oh, 1));
+    g.sx = (ow > 1) ? __fdiv_rn((float)(mw - 1), (float)(ow - 1)) : __fdiv_rn((float)mw, (float)max(ow, 1));
+    return g;
+}
+
+__device__ __forceinline__ float paste_value(const float* __restrict__ tile, int mh, int mw, int ylo,
+                                             int yhi, float ly, int ox_local, float sx) {
+    const float p = __fmul_rn((float)ox_local, sx);
+    const float fl = floorf(p);
+    const int xlo = max((int)fl, 0);
+    const int xhi = min((int)ceilf(p), mw - 1);
+    const float lx = __fsub_rn(p, fl);
+    const float tl = tile[ylo * mw + xlo], tr = tile[ylo * mw + xhi];
+    const float bl = tile[yhi * mw + xlo], br = tile[yhi * mw + xhi];
+    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+    const float b = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+    return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
+}
+
+// M and the row-filter threshold for this launch (block-uniform, every warp computes it).
+__device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_rows, int& M, int& thr) {
+    if (!S.fused) {
+        M = S.m_dev ? *S.m_dev : m_rows;
+        if (M > m_rows) M = m_rows;
+        thr = *S.thr_dev;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    int mx = 0, mn = INT_MAX, cm = INT_MIN;
+    for (int i = lane; i < B; i += 32) {
+        const int c = S.counts[i];
+        mx = max(mx, c); mn = min(mn, c); cm = max(cm, S.confmax[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    }
+    M = max(mx, 1);
+    if (M > m_rows) M = m_rows;
+    if (mn < M) cm = max(cm, -100);        // MoldBatch padding rows carry conf = int(-1*100)
+    thr = (cm > 50) ? 50 : -100;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+}
+
+// Tile element i of instance (b, j) as the int the reference's mask tensor would hold.
+struct TileRef {
+    const int32_t* mi;     // standalone
+    const float* mf;       // fused (already offset to the class channel), stride C
+    const uint32_t* bits;  // fused, pre-thresholded bit rows
+    int C, mw;
+    bool valid;
+    __device__ __forceinline__ int at(int i) const {
+        if (mi) return __ldg(mi + i);
+        if (bits) {
+            const int y = i / mw;
+            return valid ? (int)((__ldg(bits + y) >> (i - y * mw)) & 1u) : 0;
+        }
+        return valid ? (int)(__ldg(mf + (int64_t)i * C) > 0.5f) : 0;
+    }
+};
+
+__device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int m_stride, int px, int cls,
+                                            int mh, int mw) {
+    TileRef t;
+    t.mi = nullptr; t.mf = nullptr; t.bits = nullptr; t.C = S.C; t.mw = mw; t.valid = false;
+    if (!S.fused) {
+        t.mi = S.masks_i32 + ((int64_t)b * m_stride + j) * px;
+        return t;
+    }
+    const int R = S.r_dev ? *S.r_dev : S.r_rows;
+    const int jsrc = S.tail_src[(int64_t)b * m_stride + j];
+    t.valid = jsrc >= 0 && cls >= 0 && cls < S.C;
+    if (S.tail_bits) t.bits = S.tail_bits + ((int64_t)b * m_stride + j) * mh;
+    t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * px * S.C + cls) : 0);
+    return t;
+}
+
+
+// threshold = 50 if max(conf) > 50 else -100  (misc.py:366-369); conf = column 5.
+__global__ void __launch_bounds__(1024)
+paste_threshold_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stride,
+                       const int32_t* __restrict__ m_dev, int32_t* __restrict__ thr_out) {
+    __shared__ int s_max;
+    int M = m_dev ? *m_dev : m_rows;
+    if (M > m_rows) M = m_rows;
+    if (m_stride == 0) m_stride = M;            // compact [B,M,..] layout, M known on device only
+    if (threadIdx.x == 0) s_max = INT_MIN;
+    __syncthreads();
+    int mx = INT_MIN;
+    const int total = B * M;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int b = i / M, j = i - b * M;
+        const int v = det[((int64_t)b * m_stride + j) * 6 + 5];
+        mx = v > mx ? v : mx;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int v = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = v > mx ? v : mx;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) *thr_out = (s_max > 50) ? 50 : -100;
+}
+
+// Layout of the fused tail's scratch (MLP_ARENA_FUSED), written by tail_prep_kernel in
+// mlp_trim_paste: tail_src [B,K] + confmax [B] + bit tiles [B,K,mh] (mask rows of <= 32 columns).
+struct FusedTail {
+    int32_t* tail_src;
+    int32_t* confmax;
+    uint32_t* tail_bits;      // NULL when bit tiles are not used
+    int64_t bytes;
+};
+inline FusedTail fused_tail_layout(void* base, int batch, int k_rows, int mask_h, int mask_w) {
+    // Bit tiles pay off when few instances are pasted (the strided class-channel gather would
+    // otherwise be repeated by every band CTA that touches the box); with many instances the
+    // gather is better left inside the paste kernel, where its reads overlap the write stream.
+    const bool use_bits = mask_w <= 32 && k_rows <= 256;
+    FusedTail t;
+    t.bytes = ((int64_t)batch * k_rows + batch + (use_bits ? (int64_t)batch * k_rows * mask_h : 0)) * 4;
+    t.tail_src = static_cast<int32_t*>(base);
+    t.confmax = t.tail_src + (int64_t)batch * k_rows;
+    t.tail_bits = use_bits ? reinterpret_cast<uint32_t*>(t.confmax + batch) : nullptr;
+    return t;
+}
+
+}  // namespace

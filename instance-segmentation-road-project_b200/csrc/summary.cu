@@ -19,7 +19,7 @@
 //                         size, my_road overlap - and writes the 11-column summary row.
 #include <limits.h>
 
-#include "common.cuh"
+#include "paste_common.cuh"
 
 namespace {
 
@@ -188,6 +188,41 @@ __device__ __forceinline__ void load4<uint8_t>(const uint8_t* __restrict__ rowp,
     }
 }
 
+// Block-wide reduction of the per-thread partial results and the 11-column summary row
+// (SummaryOutput.call, misc.py:569-583); called by every thread of the CTA.
+__device__ __forceinline__ void finish_row(double pix, double size, double vert, double colmax, int cnt,
+                                           int inter, double (*s_d)[4], int (*s_i)[2], const int32_t* row,
+                                           float threshold, float* __restrict__ o) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int k = 16; k > 0; k >>= 1) {
+        pix = __dadd_rn(pix, shfl_xor_d(pix, k));
+        size = __dadd_rn(size, shfl_xor_d(size, k));
+        vert = __dadd_rn(vert, shfl_xor_d(vert, k));
+        colmax = fmax(colmax, shfl_xor_d(colmax, k));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, k);
+        inter += __shfl_xor_sync(0xffffffffu, inter, k);
+    }
+    __syncthreads();                                       // s_d / s_i free (previous item)
+    if (lane == 0) {
+        s_d[warp][0] = pix; s_d[warp][1] = size; s_d[warp][2] = vert; s_d[warp][3] = colmax;
+        s_i[warp][0] = cnt; s_i[warp][1] = inter;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kReduceThreads / 32; ++w) {
+            pix = __dadd_rn(pix, s_d[w][0]); size = __dadd_rn(size, s_d[w][1]);
+            vert = __dadd_rn(vert, s_d[w][2]); colmax = fmax(colmax, s_d[w][3]);
+            cnt += s_i[w][0]; inter += s_i[w][1];
+        }
+        // (class, cx, cy, w, h, conf, pixel_counts, instance, horizontal, vertical, include_my_road)
+        o[0] = (float)row[4]; o[1] = (float)row[0]; o[2] = (float)row[1]; o[3] = (float)row[2];
+        o[4] = (float)row[3]; o[5] = (float)row[5];
+        o[6] = (float)pix; o[7] = (float)size; o[8] = (float)colmax; o[9] = (float)vert;
+        const float ioi = __fdiv_rn((float)inter, __fadd_rn((float)cnt, 1e-5f));      // misc.py:616
+        o[10] = ioi > threshold ? 1.0f : 0.0f;
+    }
+}
+
 struct SummaryArgs {
     const int32_t* det;        // [B, m_stride, 6] int32
     const void* masks;         // [B, M, PH, PW] MaskT (dense over the device-side M)
@@ -200,6 +235,7 @@ struct SummaryArgs {
     float threshold;           // IncludeMyRoad threshold
     float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
+    int only_crack;            // 1: only the crack pseudo-rows (the others come from tile_summary_kernel)
 };
 
 template <typename MaskT>
@@ -209,7 +245,7 @@ instance_reduce_kernel(const SummaryArgs A) {
     __shared__ unsigned s_rowany[kMaxFrameRows / 32];
     __shared__ double s_d[kReduceThreads / 32][4];
     __shared__ int s_i[kReduceThreads / 32][2];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     int M = A.m_dev ? *A.m_dev : A.m_rows;
     if (M > A.m_rows) M = A.m_rows;
     const int m_stride = A.m_stride ? A.m_stride : M;
@@ -220,9 +256,10 @@ instance_reduce_kernel(const SummaryArgs A) {
     const int PH = A.PH, PW = A.PW;
     const int words = (PW + 31) >> 5;
     const bool aligned = (PW & 3) == 0;
-    const int64_t items = (int64_t)A.B * Mo;
+    const int64_t items = A.only_crack ? (has_crack ? A.B : 0) : (int64_t)A.B * Mo;
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int b = (int)(item / Mo), j = (int)(item - (int64_t)b * Mo);
+        const int b = A.only_crack ? (int)item : (int)(item / Mo);
+        const int j = A.only_crack ? M : (int)(item - (int64_t)b * Mo);
         const bool crack = j >= M;
         __syncthreads();                                   // previous item done with shared memory
         for (int y = tid; y < PH; y += kReduceThreads) s_unit[y] = A.unit[(int64_t)b * PH + y];
@@ -277,41 +314,109 @@ instance_reduce_kernel(const SummaryArgs A) {
         double vert = 0.0;
         for (int y = tid; y < PH; y += kReduceThreads)
             if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)s_unit[y]);
-        for (int o = 16; o > 0; o >>= 1) {
-            pix = __dadd_rn(pix, shfl_xor_d(pix, o));
-            size = __dadd_rn(size, shfl_xor_d(size, o));
-            vert = __dadd_rn(vert, shfl_xor_d(vert, o));
-            colmax = fmax(colmax, shfl_xor_d(colmax, o));
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            inter += __shfl_xor_sync(0xffffffffu, inter, o);
-        }
-        if (lane == 0) {
-            s_d[warp][0] = pix; s_d[warp][1] = size; s_d[warp][2] = vert; s_d[warp][3] = colmax;
-            s_i[warp][0] = cnt; s_i[warp][1] = inter;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kReduceThreads / 32; ++w) {
-                pix = __dadd_rn(pix, s_d[w][0]); size = __dadd_rn(size, s_d[w][1]);
-                vert = __dadd_rn(vert, s_d[w][2]); colmax = fmax(colmax, s_d[w][3]);
-                cnt += s_i[w][0]; inter += s_i[w][1];
+        finish_row(pix, size, vert, colmax, cnt, inter, s_d, s_i,
+                   crack ? crow : A.det + ((int64_t)b * m_stride + j) * 6, A.threshold,
+                   A.out + ((int64_t)b * Mo + j) * 11);
+    }
+}
+
+// ---- the same reductions straight from the mask tiles -------------------------------------
+// One CTA per instance: the float32 paste values exist only inside the clipped box, so only the box
+// is evaluated (two-stage lerp from the tile in shared memory, the values CropAndPadMask would
+// write); a thread owns a box column, walks it top to bottom and carries the column sum, warps
+// vote the per-row "any pixel > 0.5" flags.  Nothing of size [PH,PW] is read or written.
+struct TileSummaryArgs {
+    const int32_t* det;        // [B, m_stride, 6] int32 (UpSampleOutput rows)
+    PasteSrc src;              // tile source (standalone int32 tiles or the fused tail)
+    const float* unit;         // [B, PH]
+    const uint32_t* road_bits; // [B, PH, words]
+    const int32_t* crack_box;  // [4] or NULL
+    int B, m_rows, m_stride, mh, mw, PH, PW;
+    float threshold;
+    float* out;                // [B, M', 11], rows j < M
+    int32_t* m_out;            // [1] M'
+};
+
+__global__ void __launch_bounds__(kReduceThreads)
+tile_summary_kernel(const TileSummaryArgs A) {
+    __shared__ float s_tile[kMaxTile];
+    __shared__ float s_unit[kMaxFrameRows];
+    __shared__ unsigned s_rowany[kMaxFrameRows / 32];
+    __shared__ double s_d[kReduceThreads / 32][4];
+    __shared__ int s_i[kReduceThreads / 32][2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    int M, thr;
+    paste_scalars(A.src, A.B, A.m_rows, M, thr);
+    const int m_stride = A.m_stride ? A.m_stride : M;
+    int32_t crow[6];
+    const bool has_crack = A.crack_box && crack_row(A.crack_box, crow);
+    const int Mo = M + (has_crack ? 1 : 0);
+    if (blockIdx.x == 0 && tid == 0 && A.m_out) *A.m_out = Mo;
+    const int PH = A.PH, PW = A.PW, mh = A.mh, mw = A.mw;
+    const int words = (PW + 31) >> 5;
+    const int px = mh * mw;
+    const int64_t items = (int64_t)A.B * M;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = (int)(item / M), j = (int)(item - (int64_t)b * M);
+        const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
+        const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
+        double pix = 0.0, size = 0.0, colmax = 0.0, vert = 0.0;
+        int cnt = 0, inter = 0;
+        __syncthreads();                                   // previous item done with shared memory
+        if (g.active) {
+            const TileRef tref = tile_ref(A.src, b, j, m_stride, px, row[4], mh, mw);
+            for (int i = tid; i < px; i += kReduceThreads) s_tile[i] = (float)tref.at(i);
+            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) s_unit[y] = A.unit[(int64_t)b * PH + y];
+            for (int i = tid; i < (PH + 31) / 32; i += kReduceThreads) s_rowany[i] = 0u;
+            __syncthreads();
+            const uint32_t* rbits = A.road_bits + (int64_t)b * PH * words;
+            const int bw = g.xmax - g.xmin;
+            for (int c0 = 0; c0 < bw; c0 += kReduceThreads) {             // 256 box columns per pass
+                const int oxl = c0 + tid;                                 // column inside the box
+                const bool live = oxl < bw;
+                const int ox = g.xmin + oxl;
+                // x terms of the lerp are per column (paste_value, paste_common.cuh)
+                const float p = __fmul_rn((float)oxl, g.sx);
+                const float fl = floorf(p);
+                const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
+                const float lx = __fsub_rn(p, fl);
+                double col = 0.0;
+                for (int oy = g.ymin; oy < g.ymax; ++oy) {
+                    bool on = false;
+                    if (live) {
+                        const float py = __fmul_rn((float)(oy - g.ymin), g.sy);
+                        const float fy = floorf(py);
+                        const int ylo = max((int)fy, 0), yhi = min((int)ceilf(py), mh - 1);
+                        const float ly = __fsub_rn(py, fy);
+                        const float tl = s_tile[ylo * mw + xlo], tr = s_tile[ylo * mw + xhi];
+                        const float bl = s_tile[yhi * mw + xlo], br = s_tile[yhi * mw + xhi];
+                        const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+                        const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+                        const float v = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
+                        if (v != 0.0f) {
+                            const float u = s_unit[oy];
+                            const double dv = (double)v;
+                            pix = __dadd_rn(pix, dv);
+                            size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), dv));
+                            col = __dadd_rn(col, __dmul_rn((double)u, dv));
+                            on = v > 0.5f;
+                            if (on) {
+                                ++cnt;
+                                inter += (__ldg(rbits + (int64_t)oy * words + (ox >> 5)) >> (ox & 31)) & 1u;
+                            }
+                        }
+                    }
+                    const unsigned anyw = __ballot_sync(0xffffffffu, on);
+                    if (lane == 0 && anyw) atomicOr(&s_rowany[oy >> 5], 1u << (oy & 31));
+                }
+                colmax = fmax(colmax, col);
             }
-            int32_t row[6];
-            if (crack) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) row[q] = crow[q];
-            } else {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) row[q] = A.det[((int64_t)b * m_stride + j) * 6 + q];
-            }
-            float* o = A.out + item * 11;
-            // (class, cx, cy, w, h, conf, pixel_counts, instance, horizontal, vertical, include_my_road)
-            o[0] = (float)row[4]; o[1] = (float)row[0]; o[2] = (float)row[1]; o[3] = (float)row[2];
-            o[4] = (float)row[3]; o[5] = (float)row[5];
-            o[6] = (float)pix; o[7] = (float)size; o[8] = (float)colmax; o[9] = (float)vert;
-            const float ioi = __fdiv_rn((float)inter, __fadd_rn((float)cnt, 1e-5f));      // misc.py:616
-            o[10] = ioi > A.threshold ? 1.0f : 0.0f;
+            __syncthreads();                               // row flags complete
+            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
+                if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)s_unit[y]);
         }
+        finish_row(pix, size, vert, colmax, cnt, inter, s_d, s_i, row, A.threshold,
+                   A.out + ((int64_t)b * Mo + j) * 11);
     }
 }
 
@@ -366,11 +471,81 @@ extern "C" int mlp_summary_output(mlp_ctx* ctx, const int32_t* det_i32_dev, cons
     A.road_bits = road_bits_dev; A.crack_box = crack_box_dev; A.m_dev = m_dev;
     A.B = batch; A.m_rows = m_rows; A.m_stride = m_stride; A.PH = frame_h; A.PW = frame_w;
     A.S = channels > 0 ? channels : 1; A.crack_ch = crack_channel >= 0 ? crack_channel : 0;
-    A.threshold = include_threshold; A.out = out_dev; A.m_out = m_out_dev;
+    A.threshold = include_threshold; A.out = out_dev; A.m_out = m_out_dev; A.only_crack = 0;
     const int64_t items = (int64_t)batch * (m_rows + 1);
     const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
     if (mask_dtype == MLP_F32) instance_reduce_kernel<float><<<grid, kReduceThreads, 0, st>>>(A);
     else instance_reduce_kernel<uint8_t><<<grid, kReduceThreads, 0, st>>>(A);
     MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
+
+extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* masks_i32_dev,
+                                const float* roi_masks_dev, int r_rows, const int32_t* r_dev,
+                                int num_classes, const int32_t* counts_dev, int batch, int m_rows,
+                                int m_stride, const int32_t* m_dev, int mask_h, int mask_w,
+                                const int32_t* seg_dev, const float* unit_dev, const uint32_t* road_bits_dev,
+                                const int32_t* crack_box_dev, int frame_h, int frame_w, int channels,
+                                int crack_channel, float include_threshold, float* out_dev,
+                                int32_t* m_out_dev, int32_t* m_dev_out, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && det_i32_dev && unit_dev && road_bits_dev && out_dev, "mlp_tile_summary: NULL argument");
+    MLP_CHECK_ARG(masks_i32_dev || (roi_masks_dev && counts_dev && m_dev_out && num_classes >= 1 && r_rows >= 1),
+                  "mlp_tile_summary: neither int32 tiles nor a prepared fused tail");
+    MLP_CHECK_ARG(batch >= 1 && m_rows >= 1 && frame_h >= 1 && frame_w >= 1 &&
+                      (m_stride >= m_rows || (m_stride == 0 && m_dev)),
+                  "mlp_tile_summary: bad shape");
+    MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_h * mask_w <= kMaxTile, "mlp_tile_summary: mask tile %dx%d",
+                  mask_h, mask_w);
+    MLP_CHECK_ARG(frame_h <= kMaxFrameRows, "mlp_tile_summary: frame height %d > %d", frame_h, kMaxFrameRows);
+    MLP_CHECK_ARG(!crack_box_dev || (seg_dev && crack_channel >= 0 && crack_channel < channels),
+                  "mlp_tile_summary: the crack instance needs the semantic map and its channel");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_SUMMARY, st);
+    TileSummaryArgs T;
+    memset(&T, 0, sizeof(T));
+    const int32_t* m_for_crack = m_dev;
+    if (masks_i32_dev) {
+        int32_t* thr_dev = ctx->ctr;        // ctr[0]: paste row-filter threshold
+        paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
+        MLP_LAUNCH_CHECK(ctx);
+        T.src.masks_i32 = masks_i32_dev;
+        T.src.m_dev = m_dev;
+        T.src.thr_dev = thr_dev;
+    } else {
+        MLP_CHECK_ARG(m_stride == m_rows, "mlp_tile_summary: the fused tail uses capacity rows (m_stride == m_rows)");
+        const FusedTail need = fused_tail_layout(nullptr, batch, m_rows, mask_h, mask_w);
+        MLP_CHECK_ARG(ctx->arena[MLP_ARENA_FUSED] && ctx->arena_bytes[MLP_ARENA_FUSED] >= need.bytes,
+                      "mlp_tile_summary: call mlp_trim_paste with the same shapes first");
+        const FusedTail ft = fused_tail_layout(ctx->arena[MLP_ARENA_FUSED], batch, m_rows, mask_h, mask_w);
+        T.src.fused = 1;
+        T.src.roi_masks = roi_masks_dev;
+        T.src.tail_src = ft.tail_src;
+        T.src.tail_bits = ft.tail_bits;
+        T.src.r_dev = r_dev;
+        T.src.r_rows = r_rows;
+        T.src.C = num_classes;
+        T.src.counts = counts_dev;
+        T.src.confmax = ft.confmax;
+        T.src.m_out = m_dev_out;
+        m_for_crack = m_dev_out;
+    }
+    T.det = det_i32_dev; T.unit = unit_dev; T.road_bits = road_bits_dev; T.crack_box = crack_box_dev;
+    T.B = batch; T.m_rows = m_rows; T.m_stride = m_stride; T.mh = mask_h; T.mw = mask_w;
+    T.PH = frame_h; T.PW = frame_w; T.threshold = include_threshold; T.out = out_dev; T.m_out = m_out_dev;
+    const int64_t items = (int64_t)batch * m_rows;
+    const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
+    tile_summary_kernel<<<grid, kReduceThreads, 0, st>>>(T);
+    MLP_LAUNCH_CHECK(ctx);
+    if (crack_box_dev) {
+        SummaryArgs A;
+        A.det = det_i32_dev; A.masks = det_i32_dev; A.seg = seg_dev; A.unit = unit_dev;
+        A.road_bits = road_bits_dev; A.crack_box = crack_box_dev; A.m_dev = m_for_crack;
+        A.B = batch; A.m_rows = m_rows; A.m_stride = m_stride; A.PH = frame_h; A.PW = frame_w;
+        A.S = channels; A.crack_ch = crack_channel; A.threshold = include_threshold; A.out = out_dev;
+        A.m_out = nullptr; A.only_crack = 1;
+        instance_reduce_kernel<float><<<batch, kReduceThreads, 0, st>>>(A);
+        MLP_LAUNCH_CHECK(ctx);
+    }
     return MLP_OK;
 }

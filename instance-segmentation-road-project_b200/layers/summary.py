@@ -67,6 +67,28 @@ def summarize(ctx, det, masks, seg, default_road_size=3.25, threshold=0.1, with_
     return out[:B * Mo * 11].view(B, Mo, 11)
 
 
+def summarize_from_tiles(ctx, det, ins, seg, default_road_size=3.25, threshold=0.1, with_crack=True):
+    """The same [B,M',11] summary without the pasted tensor: det int32 [B,M,6] and the int32
+    {0,1} tiles ins [B,M,mh,mw] (UpSampleOutput's outputs, i.e. CropAndPadMask's inputs); every
+    instance's float32 paste values are evaluated inside its box and reduced on the fly."""
+    B, M = int(det.shape[0]), int(det.shape[1])
+    mh, mw = int(ins.shape[2]), int(ins.shape[3])
+    PH, PW, S = int(seg.shape[1]), int(seg.shape[2]), int(seg.shape[3])
+    if int(seg.shape[0]) != B or tuple(ins.shape[:2]) != (B, M):
+        raise rt.InvalidArgumentError(
+            rt.MLP_EINVAL, f"shape mismatch: det {tuple(det.shape)}, ins {tuple(ins.shape)}, seg {tuple(seg.shape)}")
+    unit, bits, box = road_scan(ctx, seg, default_road_size, with_crack)
+    out = ctx.empty((B * (M + 1) * 11,), torch.float32)
+    m_out = i32_scalar(ctx, 1)
+    rt.check(ctx.lib.mlp_tile_summary(
+        ctx.handle, ctx.view(det), ctx.view(ins), null(), 0, null(), 0, null(), B, M, M, null(), mh, mw,
+        ctx.view(seg), ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(), PH, PW, S,
+        CRACK_CHANNEL if with_crack else -1, float(threshold), ctx.view(out), ctx.view(m_out), null(),
+        ctx.stream()))
+    Mo = int(m_out.item()) if with_crack else M
+    return out[:B * Mo * 11].view(B, Mo, 11)
+
+
 @register
 class CrackToInstance(Layer):
     """crack int [B,PH,PW] -> (crack_det_outs int32 [B,1,6], crack_seg_outs f32 [B,1,PH,PW]): the
@@ -119,6 +141,15 @@ class SummaryOutput(Layer):
         det = det_outs.to(torch.int32).contiguous()
         return summarize(ctx, det, _masks(ctx, crop_ins_outs, "SummaryOutput"),
                          _seg_i32(ctx, seg_outs, "SummaryOutput"), self.default_road_size)
+
+    def from_tiles(self, inputs):
+        """[det_outs int32 [B,M,6], seg_outs, ins_outs int32 [B,M,mh,mw]] -> the same summary, computed
+        from CropAndPadMask's INPUTS: the [B,M,PH,PW] tensor is never materialised."""
+        det_outs, seg_outs, ins_outs = inputs[0], inputs[1], inputs[2]
+        ctx = ctx_of(det_outs)
+        return summarize_from_tiles(ctx, det_outs.to(torch.int32).contiguous(),
+                                    ins_outs.to(torch.int32).contiguous(),
+                                    _seg_i32(ctx, seg_outs, "SummaryOutput"), self.default_road_size)
 
     def get_config(self):
         config = super().get_config()

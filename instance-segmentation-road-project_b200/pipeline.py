@@ -223,6 +223,58 @@ class PostProcessPipeline:
             self.frame_hw[0], self.frame_hw[1], mode, c.view(self.pasted), st))
         return self.det_i32, self.pasted, self.trim_m
 
+    def trim_and_summarize(self, rois, roi_masks, seg_outs, default_road_size=3.25, threshold=0.1,
+                           paste=False):
+        """SURVEY 8(f) rank 1 fused behind the tail: TrimInstances + UpSampleOutput, then
+        SummaryOutput (road_project/setup/serving.py:45-48) evaluated straight from the mask tiles.
+        With paste=False the [B,M,PH,PW] masks are never written (the serving graph only reduces
+        them); paste=True also writes them in the configured output mode.  seg_outs: int32
+        [B,PH,PW,S] (UpSampleOutput's thresholded semantic map).  Returns (det_i32 [B,K,6],
+        summary flat with the valid prefix [B,M',11], m_out [1] = M' on the device)."""
+        from .layers import summary as ls
+        c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
+        if not self.cfg.fused:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "trim_and_summarize needs the fused tail (fused=True)")
+        st = c.stream()
+        mh, mw = self.cfg.mask_size
+        PH, PW = self.frame_hw
+        if tuple(seg_outs.shape[:3]) != (B, PH, PW) or seg_outs.dtype != torch.int32:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"seg_outs must be int32 [{B},{PH},{PW},S]")
+        S = int(seg_outs.shape[3])
+        r_cap = L * K
+        r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
+        masks_ptr = c.view(roi_masks, torch.float32)
+        ratio = (torch.tensor([float(PH), float(PW)], dtype=torch.float32)
+                 / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
+        if not hasattr(self, "summary"):
+            self.summary = c.empty((B * (K + 1) * 11,), torch.float32)
+            self.summary_m = c.empty((1,), torch.int32)
+            self.road_unit = c.empty((B, PH), torch.float32)
+            self.road_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
+            self.crack_box = c.empty((4,), torch.int32)
+        rt.check(lib.mlp_trim_paste(
+            c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
+            float(ratio[0]), float(ratio[1]), K, PH, PW, self.paste_mode if paste else rt.MLP_PASTE_NONE,
+            c.view(self.det_i32), c.view(self.trim_counts), c.view(self.trim_m),
+            c.view(self.pasted) if paste else ctypes.c_void_p(None), st))
+        rt.check(lib.mlp_road_scan(
+            c.handle, c.view(seg_outs), B, PH, PW, S, ls.ROAD_CHANNEL, ls.CRACK_CHANNEL,
+            float(default_road_size), c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box),
+            st))
+        rt.check(lib.mlp_tile_summary(
+            c.handle, c.view(self.det_i32), ctypes.c_void_p(None), masks_ptr, r_cap, r_dev, self.C,
+            c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw, c.view(seg_outs),
+            c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box), PH, PW, S,
+            ls.CRACK_CHANNEL, float(threshold), c.view(self.summary), c.view(self.summary_m),
+            c.view(self.trim_m), st))
+        self._compact_det = False
+        return self.det_i32, self.summary, self.summary_m
+
+    def summary_view(self):
+        """Reference-shaped [B,M',11] view of the last trim_and_summarize (one D2H of M')."""
+        Mo = int(self.summary_m.item())
+        return self.summary[:self.B * Mo * 11].view(self.B, Mo, 11)
+
     def result_views(self):
         """Reference-shaped views of the last trim_and_paste (one D2H of M)."""
         M = int(self.trim_m.item())

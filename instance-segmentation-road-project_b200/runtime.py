@@ -17,7 +17,7 @@ from . import build as _build
 MLP_OK, MLP_EINVAL, MLP_ECUDA, MLP_ENOMEM, MLP_EDLPACK, MLP_EBATCH = 0, -1, -2, -3, -4, -5
 MLP_F32, MLP_I32, MLP_U8, MLP_I64 = 0, 1, 2, 3
 MLP_MAX_LEVELS, MLP_MAX_ANCHORS, MLP_MAX_BATCH, MLP_MAX_KEEP = 8, 32, 32, 2048
-MLP_PASTE_F32, MLP_PASTE_U8, MLP_PASTE_BITS = 0, 1, 2
+MLP_PASTE_F32, MLP_PASTE_U8, MLP_PASTE_BITS, MLP_PASTE_NONE = 0, 1, 2, 3
 
 _ERRNAMES = {MLP_EINVAL: "MLP_EINVAL", MLP_ECUDA: "MLP_ECUDA", MLP_ENOMEM: "MLP_ENOMEM",
              MLP_EDLPACK: "MLP_EDLPACK", MLP_EBATCH: "MLP_EBATCH"}
@@ -92,6 +92,8 @@ SIGNATURES = {
                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _I, _I, _I,
                               _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P]),
     "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I, _I,
+                              _I, _F, _P, _P, _P, _P]),
     "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "mlp_mold_batch_plan": (_I, [_P, _P, _L, _I, _P, _P, _P]),

@@ -110,3 +110,57 @@ def test_summary_rejects_cpu_tensors():
     det = torch.zeros((1, 1, 6), dtype=torch.int32)
     with pytest.raises(ml.InvalidArgumentError):
         ml.SummaryOutput()([det, torch.zeros((1, 8, 8, 3), dtype=torch.int32), torch.zeros((1, 1, 8, 8))])
+
+
+@pytest.mark.parametrize("PH,PW,M", [(48, 80, 5), (64, 1100, 3), (37, 53, 4), (300, 420, 6)])
+def test_summary_from_tiles_equals_summary_of_pasted_masks(PH, PW, M):
+    """The tile path never materialises [B,M,PH,PW]; it must agree with the oracle's summary of the
+    pasted float32 masks (and hence with the drop-in layer fed CropAndPadMask's output)."""
+    import masklab_b200 as ml
+    B, C = 2, 4
+    seg = synth.semantic_map(B, PH, PW, seed=31 + PW)
+    seg[1, PH // 2:PH // 2 + 3, 2:PW // 3, 2] = 1
+    det = synth.int_detections(B, M, C, PH, PW, seed=PW + 1, pad_tail=1)
+    det[0, 0] = [PW // 2, PH // 2, 2 * PW, 2 * PH, 1, 99]        # a box clipped by the whole frame
+    det[0, 1, 5] = 40                                             # below the batch confidence threshold
+    rng = np.random.default_rng(PW)
+    ins = (rng.random((B, M, 28, 28)) > 0.45).astype(np.int32)
+    masks = mo.crop_and_pad_mask((PH, PW), det, ins)
+    want = so.summary_output(det, seg, masks)
+    layer = ml.SummaryOutput()
+    got = layer.from_tiles([dev(det), dev(seg), dev(ins)]).cpu().numpy()
+    check_summary(got, want)
+    got2 = layer([dev(det), dev(seg), ml.CropAndPadMask()([(PH, PW), dev(det), dev(ins)])]).cpu().numpy()
+    check_summary(got2, want)
+
+
+def test_pipeline_trim_and_summarize():
+    import masklab_b200 as ml
+    B, H, W, C, Cf = 2, 128, 256, 3, 16
+    PH, PW = 256, 512
+    cfgp = synth.prior_config()
+    N = synth.num_anchors(cfgp, H, W)
+    loc, cls = synth.head_tensors(B, N, C, mu=-5.0, seed=41)
+    fmaps = synth.fpn_maps(B, H, W, Cf, seed=42)
+    kw = dict(min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+              nms_max_output_size=30, max_k=2, base_size=36)
+    probs = {}
+
+    def mask_head(roi_fmaps, roi_boxes):
+        probs["m"] = synth.mask_probs(B, roi_boxes.shape[1], C, seed=43)
+        return probs["m"]
+
+    want = mo.full_path(loc, cls, fmaps, mask_head, cfgp, (H, W), (PH, PW), **kw)
+    seg = synth.semantic_map(B, PH, PW, seed=44)
+    seg[0, 100:104, 20:200, 2] = 1
+    want_sum = so.summary_output(want["det_i"], seg, want["pasted"])
+    for paste in (False, True):
+        pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, Cf, B, ml.DetectionConfig(**kw))
+        rois = pipe.detect_and_align(dev(loc), dev(cls), [dev(f) for f in fmaps])
+        pipe.trim_and_summarize(rois, dev(probs["m"]), dev(seg), paste=paste)
+        got = pipe.summary_view().cpu().numpy()
+        check_summary(got, want_sum)
+        if paste:
+            det_i, pasted = pipe.result_views()
+            assert np.array_equal(pasted.cpu().numpy(), want["binary"])
+            assert np.array_equal(det_i.cpu().numpy(), want["det_i"])
