@@ -58,6 +58,8 @@ def parse_args():
                     help="independent pipelines/streams per GPU; consecutive batches alternate between them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-summary", action="store_true",
+                    help="skip the SummaryOutput legs (SURVEY 8(f) rank 1: the consumer of the masks)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -399,6 +401,38 @@ def run_ours(args, wl):
                                             private_context=True)
             e2e_bits = run_e2e(args, wl, pipe_b, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=True)
 
+    # ---- the consumer of the masks (SummaryOutput) fused behind the tail
+    summary_leg = None
+    if not args.no_summary:
+        h_seg = pin(synth.semantic_map(B, PH, PW, seed=500 + rank))
+        d_seg = h_seg.cuda()
+        pipe.ctx.profile(False)
+        r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+        pipe.trim_and_summarize(r_, d_masks, d_seg)
+        Mo = int(pipe.summary_m.item())
+        torch.cuda.synchronize()
+        pipe.ctx.profile(True)
+        n_ = max(10, min(50, args.steps))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_):
+            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+            pipe.trim_and_summarize(r_, d_masks, d_seg)
+        e1.record()
+        torch.cuda.synchronize()
+        st_ = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
+        pipe.ctx.profile(False)
+        ms_s = e0.elapsed_time(e1) / n_
+        summary_leg = {
+            "what": "decode+NMS+RoIAlign, then SummaryOutput straight from the mask tiles "
+                    "(trim_and_summarize, no [B,M,PH,PW] tensor); single stream, inputs resident in HBM",
+            "value": world * B / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
+            "rows_per_image": Mo, "stage_ms": st_,
+            "seg_bytes": int(h_seg.numel() * 4)}
+        if not args.no_e2e:
+            summary_leg["e2e"] = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier,
+                                         h_seg=h_seg, summary_rows=Mo)
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -416,7 +450,7 @@ def run_ours(args, wl):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "e2e_bitpacked": e2e_bits, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_bitpacked": e2e_bits, "summary_path": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
             "detections": {"M": M, "R": R, "Mf": mf, "kept_per_image_mean": float(counts.mean())},
             "device_bytes": pipe.device_bytes(),
         }
@@ -437,7 +471,8 @@ def algorithmic_bytes(wl, N, M):
     return decode + det + fm + crops + trim + paste
 
 
-def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False):
+def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False, h_seg=None,
+            summary_rows=0):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
     host memory.  Three streams (copy-in, compute, copy-out) and two sets of device input buffers,
@@ -450,11 +485,17 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
     NB = 2
     d_in = [dict(loc=torch.empty_like(h_loc, device="cuda"), cls=torch.empty_like(h_cls, device="cuda"),
                  fmaps=[torch.empty_like(f, device="cuda") for f in h_fmaps],
-                 masks=torch.empty_like(h_masks, device="cuda"), free=None) for _ in range(NB)]
-    out_det = torch.empty((B * M * 6,), dtype=torch.int32).pin_memory()
-    out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps)
-    d2h = out_det.numel() * 4 + out_masks.numel()
+                 masks=torch.empty_like(h_masks, device="cuda"),
+                 seg=(torch.empty_like(h_seg, device="cuda") if h_seg is not None else None),
+                 free=None) for _ in range(NB)]
+    summary = h_seg is not None
+    out_det = torch.empty((B * (pipe.K if summary else M) * 6,), dtype=torch.int32).pin_memory()
+    if summary:
+        out_masks = torch.empty((B * summary_rows * 11,), dtype=torch.float32).pin_memory()
+    else:
+        out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps + ([h_seg] if summary else []))
+    d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size()
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     state = {"i": 0, "out_done": None}
 
@@ -469,6 +510,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             for d, h in zip(buf["fmaps"], h_fmaps):
                 d.copy_(h, non_blocking=True)
             buf["masks"].copy_(h_masks, non_blocking=True)
+            if summary:
+                buf["seg"].copy_(h_seg, non_blocking=True)
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
         with torch.cuda.stream(s_cmp):
@@ -476,7 +519,10 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             if state["out_done"] is not None:
                 s_cmp.wait_event(state["out_done"])         # previous results copied out
             r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"])
-            det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
+            if summary:
+                det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])
+            else:
+                det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
             cmp_done = torch.cuda.Event()
             cmp_done.record(s_cmp)
             buf["free"] = cmp_done
@@ -505,9 +551,12 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
     return {"value": world * B * args.e2e_steps / (ms * 1e-3), "unit": "frames/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
             "ms_per_step": ms / args.e2e_steps,
-            "api": "PostProcessPipeline.detect_and_align + trim_and_paste; pinned host inputs in, "
-                   "int32 detections + " + ("bit-packed (1 bit/pixel)" if bits else "uint8") +
-                   " masks out to pinned host memory every step"}
+            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize; pinned host inputs (heads, FPN "
+                    "maps, mask-head output, semantic map) in, int32 detections + [B,M',11] summary out "
+                    "every step; the [B,M,PH,PW] masks are never written" if summary else
+                    "PostProcessPipeline.detect_and_align + trim_and_paste; pinned host inputs in, "
+                    "int32 detections + " + ("bit-packed (1 bit/pixel)" if bits else "uint8") +
+                    " masks out to pinned host memory every step")}
 
 
 def main():

@@ -283,22 +283,27 @@ int mlp_mold_batch_run(mlp_ctx* ctx, const void* x_dev, const int32_t* counts_de
  * CalculateInstanceSize (:633-724) and IncludeMyRoad (:603-617); wiring
  * road_project/setup/serving.py:45-48.  Floating-point contract (oracle/summary_oracle.py): sums
  * are accumulated in float64 and rounded to float32 once; the road-border fit is the closed-form
- * least squares in float64.
+ * least squares in float64.  The semantic map is UpSampleOutput's {0,1} int32 tensor.
  *
- * mlp_road_scan: one pass over seg_dev i32 [B,PH,PW,S] (UpSampleOutput's thresholded semantic map):
+ * mlp_road_scan: one pass over seg_dev i32 [B,PH,PW,S]:
  *   unit_dev f32 [B,PH] = metres per pixel on each frame row
  *   (CalculateInstanceSize._calculate_road_size_by_vertical_per_batch, misc.py:660-678),
  *   road_bits_dev u32 [B,PH,ceil(PW/32)] = my_road bitmap (bit i of word k = pixel 32k+i), and, when
- *   crack_channel >= 0, crack_box_dev i32 [4] = (ymin,xmin,ymax,xmax) of the non-zero crack pixels
- *   of the whole batch ((INT_MAX,INT_MAX,-1,-1) if none) for CrackToInstance.
+ *   crack_channel >= 0, crack_bits_dev (same layout) and crack_box_dev i32 [4 + 8*B] (16-byte
+ *   aligned): words 0-3 = (ymin,xmin,ymax,xmax) of the non-zero crack pixels of the whole batch
+ *   ((INT_MAX,INT_MAX,-1,-1) if none) for CrackToInstance, then 8 words per image with the
+ *   reductions of its crack pseudo-instance (opaque; consumed by the two functions below).
+ *   2 kernel launches, 3 with a crack channel.
  *
  * mlp_summary_output: det_i32_dev [B,m_stride,6] + masks_dev [B,M,PH,PW] (MLP_F32 as CropAndPadMask
  *   returns them, or MLP_U8 binary) -> out_dev f32 [B,M',11] =
  *   (class,cx,cy,w,h,conf,pixel_counts,instance_size,horizontal_size,vertical_size,include_my_road).
  *   M from m_dev (i32 [1]) when not NULL, else m_rows; m_stride 0 = compact.  With crack_box_dev
- *   not NULL the crack pseudo-instance (mask = seg channel crack_channel) is appended when its box
- *   has positive area: M' = M + 1, written to m_out_dev; out_dev needs B*(m_rows+1)*11 floats.   */
-/* mlp_tile_summary: the same [B,M',11] summary WITHOUT the [B,M,PH,PW] tensor - every instance's
+ *   (as filled by mlp_road_scan) not NULL the crack pseudo-instance (mask = the crack bitmap) is
+ *   appended when its box has positive area: M' = M + 1, written to m_out_dev; out_dev needs
+ *   B*(m_rows+1)*11 floats.
+ *
+ * mlp_tile_summary: the same [B,M',11] summary WITHOUT the [B,M,PH,PW] tensor - every instance's
  *   float32 paste values are evaluated inside its clipped box straight from its 28x28 tile (exactly
  *   the values mlp_crop_and_pad_mask(MLP_PASTE_F32) would write) and reduced on the fly, so the
  *   largest tensor of the path is neither written nor re-read.  Two sources:
@@ -308,21 +313,22 @@ int mlp_mold_batch_run(mlp_ctx* ctx, const void* x_dev, const int32_t* counts_de
  *                           the masks altogether) with the same ctx, shapes and stream first; tiles come
  *                           from roi_masks_dev [B,R,mh,mw,C] through the tail's slot table, m_rows =
  *                           m_stride = k_rows, counts_dev from that call; M is written to m_dev_out.  */
+int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, int frame_h, int frame_w,
+                  int channels, int road_channel, int crack_channel, float default_road_size,
+                  float* unit_dev, uint32_t* road_bits_dev, uint32_t* crack_bits_dev,
+                  int32_t* crack_box_dev, mlp_stream_t stream);
+int mlp_summary_output(mlp_ctx* ctx, const int32_t* det_i32_dev, const void* masks_dev, int mask_dtype,
+                       const float* unit_dev, const uint32_t* road_bits_dev,
+                       const int32_t* crack_box_dev, int batch, int m_rows, int m_stride,
+                       const int32_t* m_dev, int frame_h, int frame_w, float include_threshold,
+                       float* out_dev, int32_t* m_out_dev, mlp_stream_t stream);
 int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* masks_i32_dev,
                      const float* roi_masks_dev, int r_rows, const int32_t* r_dev, int num_classes,
                      const int32_t* counts_dev, int batch, int m_rows, int m_stride, const int32_t* m_dev,
-                     int mask_h, int mask_w, const int32_t* seg_dev, const float* unit_dev,
-                     const uint32_t* road_bits_dev, const int32_t* crack_box_dev, int frame_h, int frame_w,
-                     int channels, int crack_channel, float include_threshold, float* out_dev,
-                     int32_t* m_out_dev, int32_t* m_dev_out, mlp_stream_t stream);
-int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, int frame_h, int frame_w,
-                  int channels, int road_channel, int crack_channel, float default_road_size,
-                  float* unit_dev, uint32_t* road_bits_dev, int32_t* crack_box_dev, mlp_stream_t stream);
-int mlp_summary_output(mlp_ctx* ctx, const int32_t* det_i32_dev, const void* masks_dev, int mask_dtype,
-                       const int32_t* seg_dev, const float* unit_dev, const uint32_t* road_bits_dev,
-                       const int32_t* crack_box_dev, int batch, int m_rows, int m_stride,
-                       const int32_t* m_dev, int frame_h, int frame_w, int channels, int crack_channel,
-                       float include_threshold, float* out_dev, int32_t* m_out_dev, mlp_stream_t stream);
+                     int mask_h, int mask_w, const float* unit_dev, const uint32_t* road_bits_dev,
+                     const int32_t* crack_box_dev, int frame_h, int frame_w,
+                     float include_threshold, float* out_dev, int32_t* m_out_dev, int32_t* m_dev_out,
+                     mlp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@
 #endif
 
 // ---------------------------------------------------------------- context ----
-#define MLP_NUM_ARENAS 6
+#define MLP_NUM_ARENAS 8
 struct mlp_ctx {
     int device;
     int sm_count;
@@ -60,6 +60,8 @@ struct ProfScope {
 #define MLP_ARENA_PASTE  3
 #define MLP_ARENA_MOLD   4
 #define MLP_ARENA_FUSED  5
+#define MLP_ARENA_SUMMARY 6
+#define MLP_ARENA_BOXACC 7
 
 void mlp_set_error(const char* fmt, ...);
 int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes);

@@ -32,6 +32,15 @@ __device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
 }
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 
+// Reductions of the crack pseudo-instance of one image (bitmap mask), produced by mlp_road_scan and
+// stored behind the crack box: crack_box_dev i32 [4 + 8 * B] = box, then one CrackPart per image.
+struct CrackPart {
+    double size, vert;                   // sum_y unit^2[y] * count[y],  sum_y unit[y] * [count[y] > 0]
+    unsigned long long colmax_bits;      // bit pattern of max_x sum_y unit[y] * bit[y,x]  (>= 0)
+    int pix, inter;                      // crack pixels, crack pixels on my_road
+};
+static_assert(sizeof(CrackPart) == 32, "CrackPart is 8 int32 words");
+
 // theta of x = theta0 * y + theta1 through the selected rows (misc.py:706-718); zeros when
 // det(X^T X) <= 0.  Moments are exact integers (< 2^53).
 __device__ __forceinline__ void fit_line(long long n, long long sy, long long syy, long long sx,
@@ -45,10 +54,69 @@ __device__ __forceinline__ void fit_line(long long n, long long sy, long long sy
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-road_scan_kernel(const int32_t* __restrict__ seg, int PH, int PW, int S, int road_ch, int crack_ch,
-                 float road_size, float* __restrict__ unit, uint32_t* __restrict__ road_bits,
+// Pass 1 over the semantic map, one warp per frame row: road extent of the row (tf.segment_min /
+// segment_max: 0 for empty rows), the my_road and crack bitmaps, the batch-wide crack box.
+constexpr int kRowsThreads = 256;
+constexpr int kRowsUnroll = 4;            // 32-pixel groups in flight per warp
+
+__global__ void __launch_bounds__(kRowsThreads)
+road_rows_kernel(const int32_t* __restrict__ seg, int PH, int PW, int S, int road_ch, int crack_ch,
+                 int2* __restrict__ row_ext, uint32_t* __restrict__ road_bits,
+                 uint32_t* __restrict__ crack_bits, int2* __restrict__ crack_rows,
                  int32_t* __restrict__ crack_box) {
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int nwarps = kRowsThreads / 32;
+    const int y = blockIdx.x * nwarps + warp;
+    if (y >= PH) return;
+    const int words = (PW + 31) >> 5;
+    const int32_t* rowp = seg + ((int64_t)b * PH + y) * PW * S;
+    uint32_t* rb = road_bits + ((int64_t)b * PH + y) * words;
+    uint32_t* cb = crack_bits ? crack_bits + ((int64_t)b * PH + y) * words : nullptr;
+    int xmin = INT_MAX, xmax = -1, cx0 = INT_MAX, cx1 = -1;
+    int cpix = 0, cinter = 0;                               // crack pixels of the row, and those on my_road
+    for (int w0 = 0; w0 < words; w0 += kRowsUnroll) {
+        int road[kRowsUnroll], cr[kRowsUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowsUnroll; ++u) {
+            const int x = (w0 + u) * 32 + lane;
+            const bool in = x < PW;
+            road[u] = in ? __ldg(rowp + (int64_t)x * S + road_ch) : 0;
+            cr[u] = (in && cb) ? __ldg(rowp + (int64_t)x * S + crack_ch) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowsUnroll; ++u) {
+            const int x0 = (w0 + u) * 32;
+            const unsigned m = __ballot_sync(0xffffffffu, road[u] > 0);     // tf.where(image > 0), misc.py:661
+            const unsigned c = __ballot_sync(0xffffffffu, cr[u] != 0);      // tf.where(inputs), misc.py:516
+            if (w0 + u < words) {
+                if (lane == 0) {
+                    rb[w0 + u] = m;
+                    if (cb) cb[w0 + u] = c;
+                }
+                if (m) { xmin = min(xmin, x0 + __ffs(m) - 1); xmax = max(xmax, x0 + 31 - __clz(m)); }
+                if (c) {
+                    cx0 = min(cx0, x0 + __ffs(c) - 1); cx1 = max(cx1, x0 + 31 - __clz(c));
+                    cpix += __popc(c); cinter += __popc(c & m);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        row_ext[(int64_t)b * PH + y] = xmax >= 0 ? make_int2(xmin, xmax) : make_int2(0, 0);
+        if (crack_rows) crack_rows[(int64_t)b * PH + y] = make_int2(cpix, cinter);
+        if (cx1 >= 0) {
+            atomicMin(crack_box + 0, y); atomicMin(crack_box + 1, cx0);
+            atomicMax(crack_box + 2, y); atomicMax(crack_box + 3, cx1);
+        }
+    }
+}
+
+// Pass 2, one CTA per image: the 15 % trimmed least-squares fit of both road borders over the rows
+// with x_min != x_max, then metres per pixel on every frame row.
+__global__ void __launch_bounds__(kScanThreads)
+road_fit_kernel(const int2* __restrict__ row_ext, int PH, float road_size, float* __restrict__ unit,
+                const int2* __restrict__ crack_rows, CrackPart* __restrict__ crack_part) {
     __shared__ int s_xmin[kMaxFrameRows], s_xmax[kMaxFrameRows];
     __shared__ int s_scan[kScanThreads / 32];
     __shared__ long long s_red[kScanThreads / 32][7];
@@ -56,42 +124,9 @@ road_scan_kernel(const int32_t* __restrict__ seg, int PH, int PW, int S, int roa
     const int b = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int nwarps = kScanThreads / 32;
-    const int words = (PW + 31) >> 5;
-    const int32_t* img = seg + (int64_t)b * PH * PW * S;
-    int cy0 = INT_MAX, cy1 = -1, cx0 = INT_MAX, cx1 = -1;            // crack box of this warp's rows
-    for (int y = warp; y < PH; y += nwarps) {
-        const int32_t* rowp = img + (int64_t)y * PW * S;
-        int xmin = INT_MAX, xmax = -1;
-        for (int x0 = 0; x0 < PW; x0 += 32) {
-            const int x = x0 + lane;
-            const bool in = x < PW;
-            const int road = in ? __ldg(rowp + (int64_t)x * S + road_ch) : 0;
-            const bool on = road > 0;                                 // tf.where(image > 0), misc.py:661
-            const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) road_bits[((int64_t)b * PH + y) * words + (x0 >> 5)] = m;
-            if (m) {
-                xmin = min(xmin, x0 + __ffs(m) - 1);
-                xmax = max(xmax, x0 + 31 - __clz(m));
-            }
-            if (crack_ch >= 0) {
-                const int cr = in ? __ldg(rowp + (int64_t)x * S + crack_ch) : 0;
-                const unsigned c = __ballot_sync(0xffffffffu, cr != 0);   // tf.where(inputs), misc.py:516
-                if (c) {
-                    cx0 = min(cx0, x0 + __ffs(c) - 1);
-                    cx1 = max(cx1, x0 + 31 - __clz(c));
-                    cy0 = min(cy0, y);
-                    cy1 = max(cy1, y);
-                }
-            }
-        }
-        if (lane == 0) {                                              // tf.segment_min/max: 0 for empty rows
-            s_xmin[y] = xmax >= 0 ? xmin : 0;
-            s_xmax[y] = xmax >= 0 ? xmax : 0;
-        }
-    }
-    if (crack_ch >= 0 && lane == 0 && cy1 >= 0) {
-        atomicMin(crack_box + 0, cy0); atomicMin(crack_box + 1, cx0);
-        atomicMax(crack_box + 2, cy1); atomicMax(crack_box + 3, cx1);
+    for (int y = tid; y < PH; y += kScanThreads) {
+        const int2 e = row_ext[(int64_t)b * PH + y];
+        s_xmin[y] = e.x; s_xmax[y] = e.y;
     }
     __syncthreads();
     // rank the rows with x_min != x_max (misc.py:689-694): contiguous chunk per thread + block scan
@@ -142,13 +177,79 @@ road_scan_kernel(const int32_t* __restrict__ seg, int PH, int PW, int S, int roa
     __syncthreads();
     // metres per pixel on every frame row (misc.py:669-678)
     const float l0 = s_theta[0], l1 = s_theta[1], r0 = s_theta[2], r1 = s_theta[3];
+    // the crack pseudo-instance is a bitmap: everything but its horizontal size follows from the
+    // per-row pixel counts of pass 1 (pixel count, instance size, vertical size, my_road overlap)
+    double size = 0.0, vert = 0.0;
+    long long pix = 0, inter = 0;
     for (int y = tid; y < PH; y += kScanThreads) {
         const float fy = (float)y;
         const float pl = __fadd_rn(__fmul_rn(fy, l0), l1);
         const float pr = __fadd_rn(__fmul_rn(fy, r0), r1);
         const float width = fmaxf(__fsub_rn(pr, pl), 1.0f);           // clip_by_value(.., 1, inf)
-        unit[(int64_t)b * PH + y] = __fdiv_rn(road_size, width);
+        const float u = __fdiv_rn(road_size, width);
+        unit[(int64_t)b * PH + y] = u;
+        if (crack_rows) {
+            const int2 c = crack_rows[(int64_t)b * PH + y];
+            if (c.x > 0) {
+                pix += c.x; inter += c.y;
+                size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), (double)c.x));
+                vert = __dadd_rn(vert, (double)u);
+            }
+        }
     }
+    if (crack_rows == nullptr) return;
+    __syncthreads();                                        // s_red free
+    for (int o = 16; o > 0; o >>= 1) {
+        size = __dadd_rn(size, shfl_xor_d(size, o));
+        vert = __dadd_rn(vert, shfl_xor_d(vert, o));
+        pix += shfl_xor_ll(pix, o);
+        inter += shfl_xor_ll(inter, o);
+    }
+    if (lane == 0) {
+        s_red[warp][0] = __double_as_longlong(size); s_red[warp][1] = __double_as_longlong(vert);
+        s_red[warp][2] = pix; s_red[warp][3] = inter;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) {
+            size = __dadd_rn(size, __longlong_as_double(s_red[w][0]));
+            vert = __dadd_rn(vert, __longlong_as_double(s_red[w][1]));
+            pix += s_red[w][2]; inter += s_red[w][3];
+        }
+        CrackPart& P = crack_part[b];
+        P.size = size; P.vert = vert; P.colmax_bits = 0ull; P.pix = (int)pix; P.inter = (int)inter;
+    }
+}
+
+// Pass 3 (crack only): horizontal size of the crack pseudo-instance = max over columns of
+// sum_y unit[y] * bit[y,x].  One warp per 32-column word of the batch-wide crack box walks the box
+// rows (8 word loads in flight, zero words skipped), lane = column; the warp maximum goes to the
+// image's CrackPart with an atomicMax on the bit pattern (sums are >= 0, so the order is preserved).
+constexpr int kColsThreads = 128;
+
+__global__ void __launch_bounds__(kColsThreads)
+crack_cols_kernel(const uint32_t* __restrict__ crack_bits, const float* __restrict__ unit,
+                  const int32_t* __restrict__ crack_box, int PH, int words, CrackPart* __restrict__ crack_part) {
+    const int y0 = crack_box[0], x0 = crack_box[1], y1 = crack_box[2], x1 = crack_box[3];
+    if (y1 < 0) return;                                     // no crack pixel in the batch
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = (x0 >> 5) + blockIdx.x * (kColsThreads / 32) + warp;
+    if (wi > (x1 >> 5)) return;
+    const uint32_t* cb = crack_bits + (int64_t)b * PH * words + wi;
+    const float* un = unit + (int64_t)b * PH;
+    double col = 0.0;
+    for (int oy = y0; oy <= y1; oy += 8) {
+        uint32_t cw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cw[u] = (oy + u <= y1) ? __ldg(cb + (int64_t)(oy + u) * words) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if ((cw[u] >> lane) & 1u) col = __dadd_rn(col, (double)__ldg(un + oy + u));
+    }
+    for (int o = 16; o > 0; o >>= 1) col = fmax(col, shfl_xor_d(col, o));
+    if (lane == 0 && col > 0.0)
+        atomicMax(&crack_part[b].colmax_bits, (unsigned long long)__double_as_longlong(col));
 }
 
 // CrackToInstance row (misc.py:521-533) from the batch-wide box; false when the region is empty
@@ -188,11 +289,10 @@ __device__ __forceinline__ void load4<uint8_t>(const uint8_t* __restrict__ rowp,
     }
 }
 
-// Block-wide reduction of the per-thread partial results and the 11-column summary row
-// (SummaryOutput.call, misc.py:569-583); called by every thread of the CTA.
-__device__ __forceinline__ void finish_row(double pix, double size, double vert, double colmax, int cnt,
-                                           int inter, double (*s_d)[4], int (*s_i)[2], const int32_t* row,
-                                           float threshold, float* __restrict__ o) {
+// Block-wide reduction of the per-thread partial results; thread 0 returns with the totals.
+// Called by every thread of the CTA.
+__device__ __forceinline__ void block_totals(double& pix, double& size, double& vert, double& colmax, int& cnt,
+                                             int& inter, double (*s_d)[4], int (*s_i)[2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = 16; k > 0; k >>= 1) {
         pix = __dadd_rn(pix, shfl_xor_d(pix, k));
@@ -202,7 +302,7 @@ __device__ __forceinline__ void finish_row(double pix, double size, double vert,
         cnt += __shfl_xor_sync(0xffffffffu, cnt, k);
         inter += __shfl_xor_sync(0xffffffffu, inter, k);
     }
-    __syncthreads();                                       // s_d / s_i free (previous item)
+    __syncthreads();                                       // s_d / s_i free (previous use)
     if (lane == 0) {
         s_d[warp][0] = pix; s_d[warp][1] = size; s_d[warp][2] = vert; s_d[warp][3] = colmax;
         s_i[warp][0] = cnt; s_i[warp][1] = inter;
@@ -214,28 +314,38 @@ __device__ __forceinline__ void finish_row(double pix, double size, double vert,
             vert = __dadd_rn(vert, s_d[w][2]); colmax = fmax(colmax, s_d[w][3]);
             cnt += s_i[w][0]; inter += s_i[w][1];
         }
-        // (class, cx, cy, w, h, conf, pixel_counts, instance, horizontal, vertical, include_my_road)
-        o[0] = (float)row[4]; o[1] = (float)row[0]; o[2] = (float)row[1]; o[3] = (float)row[2];
-        o[4] = (float)row[3]; o[5] = (float)row[5];
-        o[6] = (float)pix; o[7] = (float)size; o[8] = (float)colmax; o[9] = (float)vert;
-        const float ioi = __fdiv_rn((float)inter, __fadd_rn((float)cnt, 1e-5f));      // misc.py:616
-        o[10] = ioi > threshold ? 1.0f : 0.0f;
     }
+}
+
+// The 11-column summary row (SummaryOutput.call, misc.py:569-583):
+// (class, cx, cy, w, h, conf, pixel_counts, instance, horizontal, vertical, include_my_road)
+__device__ __forceinline__ void write_row(double pix, double size, double vert, double colmax, int cnt, int inter,
+                                          const int32_t* row, float threshold, float* __restrict__ o) {
+    o[0] = (float)row[4]; o[1] = (float)row[0]; o[2] = (float)row[1]; o[3] = (float)row[2];
+    o[4] = (float)row[3]; o[5] = (float)row[5];
+    o[6] = (float)pix; o[7] = (float)size; o[8] = (float)colmax; o[9] = (float)vert;
+    const float ioi = __fdiv_rn((float)inter, __fadd_rn((float)cnt, 1e-5f));      // misc.py:616
+    o[10] = ioi > threshold ? 1.0f : 0.0f;
+}
+
+__device__ __forceinline__ void finish_row(double pix, double size, double vert, double colmax, int cnt,
+                                           int inter, double (*s_d)[4], int (*s_i)[2], const int32_t* row,
+                                           float threshold, float* __restrict__ o) {
+    block_totals(pix, size, vert, colmax, cnt, inter, s_d, s_i);
+    if (threadIdx.x == 0) write_row(pix, size, vert, colmax, cnt, inter, row, threshold, o);
 }
 
 struct SummaryArgs {
     const int32_t* det;        // [B, m_stride, 6] int32
     const void* masks;         // [B, M, PH, PW] MaskT (dense over the device-side M)
-    const int32_t* seg;        // [B, PH, PW, S] int32 (crack pseudo-instance, may be NULL)
     const float* unit;         // [B, PH]
     const uint32_t* road_bits; // [B, PH, words]
     const int32_t* crack_box;  // [4] or NULL: no crack instance is appended
     const int32_t* m_dev;      // [1] or NULL
-    int B, m_rows, m_stride, PH, PW, S, crack_ch;
+    int B, m_rows, m_stride, PH, PW;
     float threshold;           // IncludeMyRoad threshold
     float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
-    int only_crack;            // 1: only the crack pseudo-rows (the others come from tile_summary_kernel)
 };
 
 template <typename MaskT>
@@ -256,17 +366,14 @@ instance_reduce_kernel(const SummaryArgs A) {
     const int PH = A.PH, PW = A.PW;
     const int words = (PW + 31) >> 5;
     const bool aligned = (PW & 3) == 0;
-    const int64_t items = A.only_crack ? (has_crack ? A.B : 0) : (int64_t)A.B * Mo;
+    const int64_t items = (int64_t)A.B * M;                 // the crack rows come from box_summary_kernel
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int b = A.only_crack ? (int)item : (int)(item / Mo);
-        const int j = A.only_crack ? M : (int)(item - (int64_t)b * Mo);
-        const bool crack = j >= M;
+        const int b = (int)(item / M), j = (int)(item - (int64_t)b * M);
         __syncthreads();                                   // previous item done with shared memory
         for (int y = tid; y < PH; y += kReduceThreads) s_unit[y] = A.unit[(int64_t)b * PH + y];
         for (int i = tid; i < (PH + 31) / 32; i += kReduceThreads) s_rowany[i] = 0u;
         __syncthreads();
-        const MaskT* mask = static_cast<const MaskT*>(A.masks) + ((int64_t)b * M + (crack ? 0 : j)) * PH * PW;
-        const int32_t* cseg = A.seg + (int64_t)b * PH * PW * A.S + A.crack_ch;
+        const MaskT* mask = static_cast<const MaskT*>(A.masks) + ((int64_t)b * M + j) * PH * PW;
         const uint32_t* rbits = A.road_bits + (int64_t)b * PH * words;
         double pix = 0.0, size = 0.0, colmax = 0.0;
         int cnt = 0, inter = 0;
@@ -277,15 +384,7 @@ instance_reduce_kernel(const SummaryArgs A) {
 #pragma unroll 4
             for (int y = 0; y < PH; ++y) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (live) {
-                    if (crack) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            v[q] = (x + q < PW) ? (float)__ldg(cseg + ((int64_t)y * PW + x + q) * A.S) : 0.0f;
-                    } else {
-                        load4<MaskT>(mask + (int64_t)y * PW, x, PW, aligned, v);
-                    }
-                }
+                if (live) load4<MaskT>(mask + (int64_t)y * PW, x, PW, aligned, v);
                 unsigned on = 0u;
                 if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) {   // frames are mostly zeros
                     const float u = s_unit[y];
@@ -315,108 +414,221 @@ instance_reduce_kernel(const SummaryArgs A) {
         for (int y = tid; y < PH; y += kReduceThreads)
             if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)s_unit[y]);
         finish_row(pix, size, vert, colmax, cnt, inter, s_d, s_i,
-                   crack ? crow : A.det + ((int64_t)b * m_stride + j) * 6, A.threshold,
-                   A.out + ((int64_t)b * Mo + j) * 11);
+                   A.det + ((int64_t)b * m_stride + j) * 6, A.threshold, A.out + ((int64_t)b * Mo + j) * 11);
     }
 }
 
-// ---- the same reductions straight from the mask tiles -------------------------------------
-// One CTA per instance: the float32 paste values exist only inside the clipped box, so only the box
-// is evaluated (two-stage lerp from the tile in shared memory, the values CropAndPadMask would
-// write); a thread owns a box column, walks it top to bottom and carries the column sum, warps
-// vote the per-row "any pixel > 0.5" flags.  Nothing of size [PH,PW] is read or written.
-struct TileSummaryArgs {
+// ---- the same reductions inside a box, without any [PH,PW] tensor ---------------------------
+// One CTA per (instance, 128-column chunk of its clipped box).  An instance's float32 paste values
+// exist only inside the box and are evaluated there from its tile (two-stage lerp, the values
+// CropAndPadMask would write).  The 8 warps take the box rows round-robin, lanes take 4 columns of
+// the chunk each (interleaved so that narrow boxes still fill the warp) and carry their column
+// sums; the warps' column sums meet in shared memory for the horizontal maximum.  Rows vote their
+// "any pixel > 0.5" flag.  Boxes wider than one chunk are split over several CTAs whose partial
+// results meet in a per-instance accumulator; the last CTA to arrive writes the row.  The crack
+// pseudo-instance of every image was reduced by mlp_road_scan and is only copied here.
+constexpr int kBoxWarps = kReduceThreads / 32;
+constexpr int kBoxCols = 128;             // columns per chunk = 32 lanes x 4
+
+struct BoxAcc {                           // per-instance accumulator of a box split over several CTAs
+    double pix, size;
+    unsigned long long colmax_bits;
+    int cnt, inter, done, pad;
+};
+static_assert(sizeof(BoxAcc) == 40, "BoxAcc layout");
+
+struct BoxSummaryArgs {
     const int32_t* det;        // [B, m_stride, 6] int32 (UpSampleOutput rows)
     PasteSrc src;              // tile source (standalone int32 tiles or the fused tail)
+    int has_tiles;             // 0: only the crack pseudo-instances (rows j < M come from elsewhere)
     const float* unit;         // [B, PH]
     const uint32_t* road_bits; // [B, PH, words]
-    const int32_t* crack_box;  // [4] or NULL
-    int B, m_rows, m_stride, mh, mw, PH, PW;
+    const int32_t* crack_box;  // [4 + 8 * B] box + CrackPart per image (mlp_road_scan), or NULL
+    const int32_t* m_dev;      // M when there are no tiles
+    BoxAcc* acc;               // [B * m_rows], zeroed before the launch
+    uint32_t* acc_rowany;      // [B * m_rows, ceil(PH / 32)], zeroed before the launch
+    int B, m_rows, m_stride, mh, mw, PH, PW, chunks;      // chunks = ceil(PW / kBoxCols)
     float threshold;
-    float* out;                // [B, M', 11], rows j < M
+    float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
 };
 
-__global__ void __launch_bounds__(kReduceThreads)
-tile_summary_kernel(const TileSummaryArgs A) {
-    __shared__ float s_tile[kMaxTile];
-    __shared__ float s_unit[kMaxFrameRows];
-    __shared__ unsigned s_rowany[kMaxFrameRows / 32];
-    __shared__ double s_d[kReduceThreads / 32][4];
-    __shared__ int s_i[kReduceThreads / 32][2];
-    const int tid = threadIdx.x, lane = tid & 31;
-    int M, thr;
-    paste_scalars(A.src, A.B, A.m_rows, M, thr);
+struct BoxSmem {
+    float tile[kMaxTile];
+    float unit[kMaxFrameRows];
+    unsigned rowany[kMaxFrameRows / 32];
+    double col[kBoxWarps][kBoxCols];
+    double d[kBoxWarps][4];
+    int i[kBoxWarps][2];
+    int last;
+};
+
+// One chunk (columns [c0, c0+128) of the box); every thread of the CTA calls it.
+__device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c0, int mh, int mw,
+                                           const uint32_t* __restrict__ rbits, int words, double& pix,
+                                           double& size, double& colmax, int& cnt, int& inter) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bw = g.xmax - g.xmin;
+    // this lane's 4 columns of the chunk and their x lerp terms (paste_value, paste_common.cuh)
+    int xlo[4], xhi[4];
+    float lx[4];
+    bool live[4];
+    double col[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int oxl = c0 + lane + 32 * q;
+        live[q] = oxl < bw;
+        const float p = __fmul_rn((float)oxl, g.sx);
+        const float fl = floorf(p);
+        xlo[q] = max((int)fl, 0);
+        xhi[q] = min((int)ceilf(p), mw - 1);
+        lx[q] = __fsub_rn(p, fl);
+    }
+    const int xw0 = g.xmin + c0 + lane;                      // frame column of q = 0; q adds 32 = one word
+    for (int oy = g.ymin + warp; oy < g.ymax; oy += kBoxWarps) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            const float py = __fmul_rn((float)(oy - g.ymin), g.sy);
+            const float fy = floorf(py);
+            const float* r0 = S.tile + max((int)fy, 0) * mw;
+            const float* r1 = S.tile + min((int)ceilf(py), mh - 1) * mw;
+            const float ly = __fsub_rn(py, fy);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (live[q]) {
+                    const float tl = r0[xlo[q]], tr = r0[xhi[q]], bl = r1[xlo[q]], br = r1[xhi[q]];
+                    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx[q]));
+                    const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx[q]));
+                    v[q] = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
+                }
+            }
+        }
+        unsigned on = 0u;
+        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) {
+            const float u = S.unit[oy];
+            const double du = (double)u;
+            const double d0 = (double)v[0], d1 = (double)v[1], d2 = (double)v[2], d3 = (double)v[3];
+            col[0] = __dadd_rn(col[0], __dmul_rn(du, d0));
+            col[1] = __dadd_rn(col[1], __dmul_rn(du, d1));
+            col[2] = __dadd_rn(col[2], __dmul_rn(du, d2));
+            col[3] = __dadd_rn(col[3], __dmul_rn(du, d3));
+            const double rs = __dadd_rn(__dadd_rn(d0, d1), __dadd_rn(d2, d3));
+            pix = __dadd_rn(pix, rs);
+            size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), rs));          // unit ** 2 in float32
+#pragma unroll
+            for (int q = 0; q < 4; ++q) on |= (v[q] > 0.5f ? 1u : 0u) << q;
+        }
+        if (__any_sync(0xffffffffu, on != 0u)) {             // warp-uniform: the row has a pixel > 0.5
+            if (lane == 0) atomicOr(&S.rowany[oy >> 5], 1u << (oy & 31));
+            cnt += __popc(on);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((on >> q) & 1u)
+                    inter += (__ldg(rbits + (int64_t)oy * words + ((xw0 + 32 * q) >> 5)) >> ((xw0 + 32 * q) & 31)) & 1u;
+        }
+    }
+    // horizontal size: column sums of the 8 warps meet in shared memory
+#pragma unroll
+    for (int q = 0; q < 4; ++q) S.col[warp][lane + 32 * q] = col[q];
+    __syncthreads();
+    if (tid < kBoxCols) {
+        double c = S.col[0][tid];
+#pragma unroll
+        for (int w = 1; w < kBoxWarps; ++w) c = __dadd_rn(c, S.col[w][tid]);
+        colmax = fmax(colmax, c);
+    }
+}
+
+__global__ void __launch_bounds__(kReduceThreads, 4)
+box_summary_kernel(const BoxSummaryArgs A) {
+    __shared__ BoxSmem S;
+    const int tid = threadIdx.x;
+    int M, thr = 0;
+    if (A.has_tiles) {
+        paste_scalars(A.src, A.B, A.m_rows, M, thr);
+    } else {
+        M = A.m_dev ? *A.m_dev : A.m_rows;
+        if (M > A.m_rows) M = A.m_rows;
+    }
     const int m_stride = A.m_stride ? A.m_stride : M;
     int32_t crow[6];
     const bool has_crack = A.crack_box && crack_row(A.crack_box, crow);
     const int Mo = M + (has_crack ? 1 : 0);
     if (blockIdx.x == 0 && tid == 0 && A.m_out) *A.m_out = Mo;
     const int PH = A.PH, PW = A.PW, mh = A.mh, mw = A.mw;
-    const int words = (PW + 31) >> 5;
-    const int px = mh * mw;
-    const int64_t items = (int64_t)A.B * M;
+    const int words = (PW + 31) >> 5, ywords = (PH + 31) >> 5;
+    const int n_crack = has_crack ? A.B : 0;
+    const int64_t items = n_crack + (A.has_tiles ? (int64_t)A.B * M * A.chunks : 0);
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int b = (int)(item / M), j = (int)(item - (int64_t)b * M);
+        if (item < n_crack) {                               // reduced by mlp_road_scan already
+            if (tid == 0) {
+                const int b = (int)item;
+                const CrackPart P = reinterpret_cast<const CrackPart*>(A.crack_box + 4)[b];
+                write_row((double)P.pix, P.size, P.vert, __longlong_as_double((long long)P.colmax_bits), P.pix,
+                          P.inter, crow, A.threshold, A.out + ((int64_t)b * Mo + M) * 11);
+            }
+            continue;
+        }
+        const int64_t t = item - n_crack;
+        const int chunk = (int)(t % A.chunks);
+        const int64_t inst = t / A.chunks;
+        const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
+        const int nchunks = g.active ? (g.xmax - g.xmin + kBoxCols - 1) / kBoxCols : 1;
+        if (chunk >= nchunks) continue;                     // CTA-uniform
+        float* o = A.out + ((int64_t)b * Mo + j) * 11;
         double pix = 0.0, size = 0.0, colmax = 0.0, vert = 0.0;
         int cnt = 0, inter = 0;
-        __syncthreads();                                   // previous item done with shared memory
-        if (g.active) {
-            const TileRef tref = tile_ref(A.src, b, j, m_stride, px, row[4], mh, mw);
-            for (int i = tid; i < px; i += kReduceThreads) s_tile[i] = (float)tref.at(i);
-            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) s_unit[y] = A.unit[(int64_t)b * PH + y];
-            for (int i = tid; i < (PH + 31) / 32; i += kReduceThreads) s_rowany[i] = 0u;
-            __syncthreads();
-            const uint32_t* rbits = A.road_bits + (int64_t)b * PH * words;
-            const int bw = g.xmax - g.xmin;
-            for (int c0 = 0; c0 < bw; c0 += kReduceThreads) {             // 256 box columns per pass
-                const int oxl = c0 + tid;                                 // column inside the box
-                const bool live = oxl < bw;
-                const int ox = g.xmin + oxl;
-                // x terms of the lerp are per column (paste_value, paste_common.cuh)
-                const float p = __fmul_rn((float)oxl, g.sx);
-                const float fl = floorf(p);
-                const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
-                const float lx = __fsub_rn(p, fl);
-                double col = 0.0;
-                for (int oy = g.ymin; oy < g.ymax; ++oy) {
-                    bool on = false;
-                    if (live) {
-                        const float py = __fmul_rn((float)(oy - g.ymin), g.sy);
-                        const float fy = floorf(py);
-                        const int ylo = max((int)fy, 0), yhi = min((int)ceilf(py), mh - 1);
-                        const float ly = __fsub_rn(py, fy);
-                        const float tl = s_tile[ylo * mw + xlo], tr = s_tile[ylo * mw + xhi];
-                        const float bl = s_tile[yhi * mw + xlo], br = s_tile[yhi * mw + xhi];
-                        const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-                        const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-                        const float v = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
-                        if (v != 0.0f) {
-                            const float u = s_unit[oy];
-                            const double dv = (double)v;
-                            pix = __dadd_rn(pix, dv);
-                            size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), dv));
-                            col = __dadd_rn(col, __dmul_rn((double)u, dv));
-                            on = v > 0.5f;
-                            if (on) {
-                                ++cnt;
-                                inter += (__ldg(rbits + (int64_t)oy * words + (ox >> 5)) >> (ox & 31)) & 1u;
-                            }
-                        }
-                    }
-                    const unsigned anyw = __ballot_sync(0xffffffffu, on);
-                    if (lane == 0 && anyw) atomicOr(&s_rowany[oy >> 5], 1u << (oy & 31));
-                }
-                colmax = fmax(colmax, col);
-            }
-            __syncthreads();                               // row flags complete
-            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
-                if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)s_unit[y]);
+        if (!g.active) {                                    // all-zero mask
+            if (tid == 0) write_row(pix, size, vert, colmax, cnt, inter, row, A.threshold, o);
+            continue;
         }
-        finish_row(pix, size, vert, colmax, cnt, inter, s_d, s_i, row, A.threshold,
-                   A.out + ((int64_t)b * Mo + j) * 11);
+        __syncthreads();                                   // previous item done with shared memory
+        const TileRef tref = tile_ref(A.src, b, j, m_stride, mh * mw, row[4], mh, mw);
+        for (int i = tid; i < mh * mw; i += kReduceThreads) S.tile[i] = (float)tref.at(i);
+        for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) S.unit[y] = A.unit[(int64_t)b * PH + y];
+        for (int i = (g.ymin >> 5) + tid; i <= ((g.ymax - 1) >> 5); i += kReduceThreads) S.rowany[i] = 0u;
+        __syncthreads();
+        box_reduce(S, g, chunk * kBoxCols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size, colmax,
+                   cnt, inter);
+        __syncthreads();                                   // row flags complete
+        if (nchunks == 1) {                                 // the whole box: finish here
+            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
+                if ((S.rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)S.unit[y]);
+            finish_row(pix, size, vert, colmax, cnt, inter, S.d, S.i, row, A.threshold, o);
+            continue;
+        }
+        // partial results of this chunk meet the other chunks' in the instance's accumulator
+        BoxAcc* acc = A.acc + ((int64_t)b * A.m_rows + j);
+        uint32_t* grow = A.acc_rowany + ((int64_t)b * A.m_rows + j) * ywords;
+        for (int i = (g.ymin >> 5) + tid; i <= ((g.ymax - 1) >> 5); i += kReduceThreads)
+            if (S.rowany[i]) atomicOr(grow + i, S.rowany[i]);
+        block_totals(pix, size, vert, colmax, cnt, inter, S.d, S.i);
+        if (tid == 0) {
+            atomicAdd(&acc->pix, pix);
+            atomicAdd(&acc->size, size);
+            atomicMax(&acc->colmax_bits, (unsigned long long)__double_as_longlong(colmax));
+            atomicAdd(&acc->cnt, cnt);
+            atomicAdd(&acc->inter, inter);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) S.last = (atomicAdd(&acc->done, 1) == nchunks - 1);
+        __syncthreads();
+        if (S.last) {                                       // every chunk has arrived
+            __threadfence();
+            vert = 0.0;
+            for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
+                if ((__ldcg(grow + (y >> 5)) >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)S.unit[y]);
+            double z0 = 0.0, z1 = 0.0, z3 = 0.0;
+            int i0 = 0, i1 = 0;
+            block_totals(z0, z1, vert, z3, i0, i1, S.d, S.i);
+            if (tid == 0)
+                write_row(__ldcg(&acc->pix), __ldcg(&acc->size), vert,
+                          __longlong_as_double((long long)__ldcg(&acc->colmax_bits)), __ldcg(&acc->cnt),
+                          __ldcg(&acc->inter), row, A.threshold, o);
+        }
     }
 }
 
@@ -425,58 +637,82 @@ tile_summary_kernel(const TileSummaryArgs A) {
 // ================================================================ host side ===
 extern "C" int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, int frame_h, int frame_w,
                              int channels, int road_channel, int crack_channel, float default_road_size,
-                             float* unit_dev, uint32_t* road_bits_dev, int32_t* crack_box_dev,
-                             mlp_stream_t stream) {
+                             float* unit_dev, uint32_t* road_bits_dev, uint32_t* crack_bits_dev,
+                             int32_t* crack_box_dev, mlp_stream_t stream) {
     MLP_CHECK_ARG(ctx && seg_dev && unit_dev && road_bits_dev, "mlp_road_scan: NULL argument");
     MLP_CHECK_ARG(batch >= 1 && frame_h >= 1 && frame_w >= 1 && channels >= 1, "mlp_road_scan: bad shape");
     MLP_CHECK_ARG(frame_h <= kMaxFrameRows, "mlp_road_scan: frame height %d > %d", frame_h, kMaxFrameRows);
     MLP_CHECK_ARG(road_channel >= 0 && road_channel < channels, "mlp_road_scan: road channel %d out of range",
                   road_channel);
-    MLP_CHECK_ARG(crack_channel < channels && (crack_channel < 0 || crack_box_dev),
-                  "mlp_road_scan: crack channel %d needs a crack box / is out of range", crack_channel);
+    MLP_CHECK_ARG(crack_channel < 0 || mlp_aligned16(crack_box_dev), "mlp_road_scan: crack_box_dev must be 16-byte aligned");
+    MLP_CHECK_ARG(crack_channel < channels && (crack_channel < 0 || (crack_box_dev && crack_bits_dev)),
+                  "mlp_road_scan: crack channel %d needs crack_bits_dev and crack_box_dev / is out of range",
+                  crack_channel);
     MLP_CHECK_ARG((int64_t)frame_h * frame_w * channels < (1ll << 31), "mlp_road_scan: frame too large");
     DeviceGuard g(ctx->device);
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_SUMMARY, (int64_t)batch * frame_h * 16);
+    if (rc) return rc;
+    int2* row_ext = static_cast<int2*>(ctx->arena[MLP_ARENA_SUMMARY]);
+    int2* crack_rows = crack_channel >= 0 ? row_ext + (int64_t)batch * frame_h : nullptr;
+    CrackPart* crack_part = crack_channel >= 0 ? reinterpret_cast<CrackPart*>(crack_box_dev + 4) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_ROAD_SCAN, st);
     if (crack_channel >= 0) {
-        const int32_t init[4] = {INT_MAX, INT_MAX, -1, -1};
+        static const int32_t init[4] = {INT_MAX, INT_MAX, -1, -1};
         MLP_CUDA(cudaMemcpyAsync(crack_box_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    road_scan_kernel<<<batch, kScanThreads, 0, st>>>(seg_dev, frame_h, frame_w, channels, road_channel,
-                                                   crack_channel, default_road_size, unit_dev,
-                                                   road_bits_dev, crack_box_dev);
+    const int rows_per_cta = kRowsThreads / 32;
+    road_rows_kernel<<<dim3((frame_h + rows_per_cta - 1) / rows_per_cta, batch), kRowsThreads, 0, st>>>(
+        seg_dev, frame_h, frame_w, channels, road_channel, crack_channel >= 0 ? crack_channel : 0, row_ext,
+        road_bits_dev, crack_channel >= 0 ? crack_bits_dev : nullptr, crack_rows, crack_box_dev);
     MLP_LAUNCH_CHECK(ctx);
+    road_fit_kernel<<<batch, kScanThreads, 0, st>>>(row_ext, frame_h, default_road_size, unit_dev, crack_rows,
+                                                  crack_part);
+    MLP_LAUNCH_CHECK(ctx);
+    if (crack_channel >= 0) {
+        const int words = (frame_w + 31) / 32, wpc = kColsThreads / 32;
+        crack_cols_kernel<<<dim3((words + wpc - 1) / wpc, batch), kColsThreads, 0, st>>>(
+            crack_bits_dev, unit_dev, crack_box_dev, frame_h, words, crack_part);
+        MLP_LAUNCH_CHECK(ctx);
+    }
     return MLP_OK;
 }
 
 extern "C" int mlp_summary_output(mlp_ctx* ctx, const int32_t* det_i32_dev, const void* masks_dev,
-                                  int mask_dtype, const int32_t* seg_dev, const float* unit_dev,
-                                  const uint32_t* road_bits_dev, const int32_t* crack_box_dev, int batch,
+                                  int mask_dtype, const float* unit_dev, const uint32_t* road_bits_dev,
+                                  const int32_t* crack_box_dev, int batch,
                                   int m_rows, int m_stride, const int32_t* m_dev, int frame_h, int frame_w,
-                                  int channels, int crack_channel, float include_threshold,
-                                  float* out_dev, int32_t* m_out_dev, mlp_stream_t stream) {
+                                  float include_threshold, float* out_dev, int32_t* m_out_dev,
+                                  mlp_stream_t stream) {
     MLP_CHECK_ARG(ctx && det_i32_dev && masks_dev && unit_dev && road_bits_dev && out_dev,
                   "mlp_summary_output: NULL argument");
     MLP_CHECK_ARG(batch >= 1 && m_rows >= 1 && frame_h >= 1 && frame_w >= 1, "mlp_summary_output: bad shape");
     MLP_CHECK_ARG(frame_h <= kMaxFrameRows, "mlp_summary_output: frame height %d > %d", frame_h, kMaxFrameRows);
     MLP_CHECK_ARG(mask_dtype == MLP_F32 || mask_dtype == MLP_U8, "mlp_summary_output: masks must be f32 or u8");
-    MLP_CHECK_ARG(!crack_box_dev || (seg_dev && crack_channel >= 0 && crack_channel < channels),
-                  "mlp_summary_output: the crack instance needs the semantic map and its channel");
     MLP_CHECK_ARG(mlp_aligned16(masks_dev), "mlp_summary_output: masks must be 16-byte aligned");
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_SUMMARY, st);
     SummaryArgs A;
-    A.det = det_i32_dev; A.masks = masks_dev; A.seg = seg_dev ? seg_dev : det_i32_dev; A.unit = unit_dev;
-    A.road_bits = road_bits_dev; A.crack_box = crack_box_dev; A.m_dev = m_dev;
+    A.det = det_i32_dev; A.masks = masks_dev; A.unit = unit_dev; A.road_bits = road_bits_dev;
+    A.crack_box = crack_box_dev; A.m_dev = m_dev;
     A.B = batch; A.m_rows = m_rows; A.m_stride = m_stride; A.PH = frame_h; A.PW = frame_w;
-    A.S = channels > 0 ? channels : 1; A.crack_ch = crack_channel >= 0 ? crack_channel : 0;
-    A.threshold = include_threshold; A.out = out_dev; A.m_out = m_out_dev; A.only_crack = 0;
-    const int64_t items = (int64_t)batch * (m_rows + 1);
+    A.threshold = include_threshold; A.out = out_dev; A.m_out = m_out_dev;
+    const int64_t items = (int64_t)batch * m_rows;
     const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
     if (mask_dtype == MLP_F32) instance_reduce_kernel<float><<<grid, kReduceThreads, 0, st>>>(A);
     else instance_reduce_kernel<uint8_t><<<grid, kReduceThreads, 0, st>>>(A);
     MLP_LAUNCH_CHECK(ctx);
+    if (crack_box_dev) {                    // the crack pseudo-instance of every image, over the bitmaps
+        BoxSummaryArgs X;
+        memset(&X, 0, sizeof(X));
+        X.det = det_i32_dev; X.unit = unit_dev; X.road_bits = road_bits_dev;
+        X.crack_box = crack_box_dev; X.m_dev = m_dev; X.B = batch; X.m_rows = m_rows; X.m_stride = m_stride;
+        X.mh = 1; X.mw = 1; X.PH = frame_h; X.PW = frame_w; X.chunks = 1; X.threshold = include_threshold;
+        X.out = out_dev;
+        box_summary_kernel<<<batch, kReduceThreads, 0, st>>>(X);
+        MLP_LAUNCH_CHECK(ctx);
+    }
     return MLP_OK;
 }
 
@@ -484,10 +720,10 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
                                 const float* roi_masks_dev, int r_rows, const int32_t* r_dev,
                                 int num_classes, const int32_t* counts_dev, int batch, int m_rows,
                                 int m_stride, const int32_t* m_dev, int mask_h, int mask_w,
-                                const int32_t* seg_dev, const float* unit_dev, const uint32_t* road_bits_dev,
-                                const int32_t* crack_box_dev, int frame_h, int frame_w, int channels,
-                                int crack_channel, float include_threshold, float* out_dev,
-                                int32_t* m_out_dev, int32_t* m_dev_out, mlp_stream_t stream) {
+                                const float* unit_dev, const uint32_t* road_bits_dev,
+                                const int32_t* crack_box_dev, int frame_h,
+                                int frame_w, float include_threshold, float* out_dev, int32_t* m_out_dev,
+                                int32_t* m_dev_out, mlp_stream_t stream) {
     MLP_CHECK_ARG(ctx && det_i32_dev && unit_dev && road_bits_dev && out_dev, "mlp_tile_summary: NULL argument");
     MLP_CHECK_ARG(masks_i32_dev || (roi_masks_dev && counts_dev && m_dev_out && num_classes >= 1 && r_rows >= 1),
                   "mlp_tile_summary: neither int32 tiles nor a prepared fused tail");
@@ -497,14 +733,12 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
     MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_h * mask_w <= kMaxTile, "mlp_tile_summary: mask tile %dx%d",
                   mask_h, mask_w);
     MLP_CHECK_ARG(frame_h <= kMaxFrameRows, "mlp_tile_summary: frame height %d > %d", frame_h, kMaxFrameRows);
-    MLP_CHECK_ARG(!crack_box_dev || (seg_dev && crack_channel >= 0 && crack_channel < channels),
-                  "mlp_tile_summary: the crack instance needs the semantic map and its channel");
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_SUMMARY, st);
-    TileSummaryArgs T;
+    BoxSummaryArgs T;
     memset(&T, 0, sizeof(T));
-    const int32_t* m_for_crack = m_dev;
+    T.has_tiles = 1;
     if (masks_i32_dev) {
         int32_t* thr_dev = ctx->ctr;        // ctr[0]: paste row-filter threshold
         paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
@@ -528,24 +762,24 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
         T.src.counts = counts_dev;
         T.src.confmax = ft.confmax;
         T.src.m_out = m_dev_out;
-        m_for_crack = m_dev_out;
     }
-    T.det = det_i32_dev; T.unit = unit_dev; T.road_bits = road_bits_dev; T.crack_box = crack_box_dev;
+    T.det = det_i32_dev; T.unit = unit_dev; T.road_bits = road_bits_dev;
+    T.crack_box = crack_box_dev; T.m_dev = m_dev;
     T.B = batch; T.m_rows = m_rows; T.m_stride = m_stride; T.mh = mask_h; T.mw = mask_w;
     T.PH = frame_h; T.PW = frame_w; T.threshold = include_threshold; T.out = out_dev; T.m_out = m_out_dev;
-    const int64_t items = (int64_t)batch * m_rows;
-    const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-    tile_summary_kernel<<<grid, kReduceThreads, 0, st>>>(T);
+    // per-instance accumulators for boxes split over several CTAs (zeroed every call)
+    const int ywords = (frame_h + 31) / 32;
+    const int64_t acc_bytes = (int64_t)batch * m_rows * (sizeof(BoxAcc) + (int64_t)ywords * 4);
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_BOXACC, acc_bytes);
+    if (rc) return rc;
+    MLP_CUDA(cudaMemsetAsync(ctx->arena[MLP_ARENA_BOXACC], 0, (size_t)acc_bytes, st));
+    T.acc = static_cast<BoxAcc*>(ctx->arena[MLP_ARENA_BOXACC]);
+    T.acc_rowany = reinterpret_cast<uint32_t*>(T.acc + (int64_t)batch * m_rows);
+    T.chunks = (frame_w + kBoxCols - 1) / kBoxCols;
+    const int64_t items = (int64_t)batch * m_rows * T.chunks + batch;
+    const int64_t cap = (int64_t)ctx->sm_count * 64;       // idle (instance, chunk) items are skipped in a loop
+    const int grid = (int)(items < cap ? items : cap);
+    box_summary_kernel<<<grid, kReduceThreads, 0, st>>>(T);
     MLP_LAUNCH_CHECK(ctx);
-    if (crack_box_dev) {
-        SummaryArgs A;
-        A.det = det_i32_dev; A.masks = det_i32_dev; A.seg = seg_dev; A.unit = unit_dev;
-        A.road_bits = road_bits_dev; A.crack_box = crack_box_dev; A.m_dev = m_for_crack;
-        A.B = batch; A.m_rows = m_rows; A.m_stride = m_stride; A.PH = frame_h; A.PW = frame_w;
-        A.S = channels; A.crack_ch = crack_channel; A.threshold = include_threshold; A.out = out_dev;
-        A.m_out = nullptr; A.only_crack = 1;
-        instance_reduce_kernel<float><<<batch, kReduceThreads, 0, st>>>(A);
-        MLP_LAUNCH_CHECK(ctx);
-    }
     return MLP_OK;
 }

@@ -34,18 +34,20 @@ def _masks(ctx, masks, what):
 
 
 def road_scan(ctx, seg, default_road_size, with_crack):
-    """seg int32 [B,PH,PW,S] -> (unit [B,PH] f32, road_bits [B,PH,ceil(PW/32)] i32, crack_box [4] i32|None)."""
+    """seg int32 [B,PH,PW,S] -> (unit [B,PH] f32, road_bits [B,PH,ceil(PW/32)] i32,
+    crack_bits (same layout)|None, crack_box [4] i32|None)."""
     B, PH, PW, S = (int(d) for d in seg.shape)
     if S <= ROAD_CHANNEL or (with_crack and S <= CRACK_CHANNEL):
         raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"seg_outs has {S} channels; my_road is 1, crack is 2")
     unit = ctx.empty((B, PH), torch.float32)
     bits = ctx.empty((B, PH, (PW + 31) // 32), torch.int32)
-    box = i32_scalar(ctx, 4) if with_crack else None
+    box = i32_scalar(ctx, 4 + 8 * B) if with_crack else None      # box + per-image crack reductions
+    cbits = ctx.empty((B, PH, (PW + 31) // 32), torch.int32) if with_crack else None
     rt.check(ctx.lib.mlp_road_scan(
         ctx.handle, ctx.view(seg), B, PH, PW, S, ROAD_CHANNEL, CRACK_CHANNEL if with_crack else -1,
-        float(default_road_size), ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(),
-        ctx.stream()))
-    return unit, bits, box
+        float(default_road_size), ctx.view(unit), ctx.view(bits), ctx.view(cbits) if with_crack else null(),
+        ctx.view(box) if with_crack else null(), ctx.stream()))
+    return unit, bits, cbits, box
 
 
 def summarize(ctx, det, masks, seg, default_road_size=3.25, threshold=0.1, with_crack=True):
@@ -55,14 +57,13 @@ def summarize(ctx, det, masks, seg, default_road_size=3.25, threshold=0.1, with_
     if tuple(seg.shape[:3]) != (B, PH, PW) or tuple(masks.shape[:2]) != (B, M):
         raise rt.InvalidArgumentError(
             rt.MLP_EINVAL, f"shape mismatch: det {tuple(det.shape)}, masks {tuple(masks.shape)}, seg {tuple(seg.shape)}")
-    unit, bits, box = road_scan(ctx, seg, default_road_size, with_crack)
+    unit, bits, cbits, box = road_scan(ctx, seg, default_road_size, with_crack)
     out = ctx.empty((B * (M + 1) * 11,), torch.float32)
     m_out = i32_scalar(ctx, 1)
     rt.check(ctx.lib.mlp_summary_output(
         ctx.handle, ctx.view(det), ctx.view(masks), rt.MLP_F32 if masks.dtype == torch.float32 else rt.MLP_U8,
-        ctx.view(seg), ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(), B, M, M,
-        null(), PH, PW, int(seg.shape[3]), CRACK_CHANNEL if with_crack else -1, float(threshold),
-        ctx.view(out), ctx.view(m_out), ctx.stream()))
+        ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(), B, M, M, null(), PH, PW,
+        float(threshold), ctx.view(out), ctx.view(m_out), ctx.stream()))
     Mo = int(m_out.item()) if with_crack else M              # one 4-byte D2H: the dynamic shape
     return out[:B * Mo * 11].view(B, Mo, 11)
 
@@ -77,14 +78,13 @@ def summarize_from_tiles(ctx, det, ins, seg, default_road_size=3.25, threshold=0
     if int(seg.shape[0]) != B or tuple(ins.shape[:2]) != (B, M):
         raise rt.InvalidArgumentError(
             rt.MLP_EINVAL, f"shape mismatch: det {tuple(det.shape)}, ins {tuple(ins.shape)}, seg {tuple(seg.shape)}")
-    unit, bits, box = road_scan(ctx, seg, default_road_size, with_crack)
+    unit, bits, cbits, box = road_scan(ctx, seg, default_road_size, with_crack)
     out = ctx.empty((B * (M + 1) * 11,), torch.float32)
     m_out = i32_scalar(ctx, 1)
     rt.check(ctx.lib.mlp_tile_summary(
         ctx.handle, ctx.view(det), ctx.view(ins), null(), 0, null(), 0, null(), B, M, M, null(), mh, mw,
-        ctx.view(seg), ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(), PH, PW, S,
-        CRACK_CHANNEL if with_crack else -1, float(threshold), ctx.view(out), ctx.view(m_out), null(),
-        ctx.stream()))
+        ctx.view(unit), ctx.view(bits), ctx.view(box) if with_crack else null(), PH, PW, float(threshold),
+        ctx.view(out), ctx.view(m_out), null(), ctx.stream()))
     Mo = int(m_out.item()) if with_crack else M
     return out[:B * Mo * 11].view(B, Mo, 11)
 
@@ -106,10 +106,11 @@ class CrackToInstance(Layer):
         # the scan reads a [B,PH,PW,S] map: view the crack plane as S = 1 with both channels = 0
         unit = ctx.empty((B, PH), torch.float32)
         bits = ctx.empty((B, PH, (PW + 31) // 32), torch.int32)
-        box = i32_scalar(ctx, 4)
-        rt.check(ctx.lib.mlp_road_scan(ctx.handle, ctx.view(crack), B, PH, PW, 1, 0, 0, 3.25,
-                                       ctx.view(unit), ctx.view(bits), ctx.view(box), ctx.stream()))
-        y0, x0, y1, x1 = box.tolist()
+        cbits = torch.empty_like(bits)
+        box = i32_scalar(ctx, 4 + 8 * B)
+        rt.check(ctx.lib.mlp_road_scan(ctx.handle, ctx.view(crack), B, PH, PW, 1, 0, 0, 3.25, ctx.view(unit),
+                                       ctx.view(bits), ctx.view(cbits), ctx.view(box), ctx.stream()))
+        y0, x0, y1, x1 = box[:4].tolist()
         if y1 < 0:
             y0 = x0 = y1 = x1 = 0
         h, w = y1 - y0, x1 - x0

@@ -251,7 +251,8 @@ class PostProcessPipeline:
             self.summary_m = c.empty((1,), torch.int32)
             self.road_unit = c.empty((B, PH), torch.float32)
             self.road_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
-            self.crack_box = c.empty((4,), torch.int32)
+            self.crack_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
+            self.crack_box = c.empty((4 + 8 * B,), torch.int32)
         rt.check(lib.mlp_trim_paste(
             c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
             float(ratio[0]), float(ratio[1]), K, PH, PW, self.paste_mode if paste else rt.MLP_PASTE_NONE,
@@ -259,14 +260,13 @@ class PostProcessPipeline:
             c.view(self.pasted) if paste else ctypes.c_void_p(None), st))
         rt.check(lib.mlp_road_scan(
             c.handle, c.view(seg_outs), B, PH, PW, S, ls.ROAD_CHANNEL, ls.CRACK_CHANNEL,
-            float(default_road_size), c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box),
-            st))
+            float(default_road_size), c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_bits),
+            c.view(self.crack_box), st))
         rt.check(lib.mlp_tile_summary(
             c.handle, c.view(self.det_i32), ctypes.c_void_p(None), masks_ptr, r_cap, r_dev, self.C,
-            c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw, c.view(seg_outs),
-            c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box), PH, PW, S,
-            ls.CRACK_CHANNEL, float(threshold), c.view(self.summary), c.view(self.summary_m),
-            c.view(self.trim_m), st))
+            c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw,
+            c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box),
+            PH, PW, float(threshold), c.view(self.summary), c.view(self.summary_m), c.view(self.trim_m), st))
         self._compact_det = False
         return self.det_i32, self.summary, self.summary_m
 

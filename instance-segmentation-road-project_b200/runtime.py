@@ -92,10 +92,10 @@ SIGNATURES = {
                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _I, _I, _I,
                               _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P]),
     "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I, _I,
-                              _I, _F, _P, _P, _P, _P]),
-    "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
-    "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
+    "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
+                              _F, _P, _P, _P, _P]),
     "mlp_mold_batch_plan": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "mlp_mold_batch_run": (_I, [_P, _P, _P, _L, _L, _I, _I, _P, _P, _P]),
 }

@@ -41,15 +41,17 @@ def test_unit_lengths_bitexact(PH, PW):
     seg = synth.semantic_map(B, PH, PW, seed=PH)
     seg[2, :, :, 1] = 0                                         # an image without road
     ctx = ml.Context.get()
-    unit, bits, box = ls.road_scan(ctx, dev(seg), 3.25, True)
+    unit, bits, cbits, box = ls.road_scan(ctx, dev(seg), 3.25, True)
     want = np.stack([so.road_unit_lengths(seg[b, :, :, 1]) for b in range(B)])
     assert np.array_equal(unit.cpu().numpy(), want)
     packed = np.packbits(seg[..., 1].astype(np.uint8), axis=-1, bitorder="little")
     gotbits = bits.cpu().numpy().view(np.uint8)[..., :packed.shape[-1]]
     assert np.array_equal(gotbits, packed)
+    cpacked = np.packbits((seg[..., 2] != 0).astype(np.uint8), axis=-1, bitorder="little")
+    assert np.array_equal(cbits.cpu().numpy().view(np.uint8)[..., :cpacked.shape[-1]], cpacked)
     idx = np.argwhere(seg[..., 2] != 0)
     if idx.size:
-        assert box.tolist() == [idx[:, 1].min(), idx[:, 2].min(), idx[:, 1].max(), idx[:, 2].max()]
+        assert box[:4].tolist() == [idx[:, 1].min(), idx[:, 2].min(), idx[:, 1].max(), idx[:, 2].max()]
 
 
 @pytest.mark.parametrize("PH,PW,M,dtype", [(48, 80, 5, "f32"), (64, 1100, 3, "f32"), (37, 53, 4, "f32"),
