@@ -419,7 +419,7 @@ instance_reduce_kernel(const SummaryArgs A) {
 }
 
 // ---- the same reductions inside a box, without any [PH,PW] tensor ---------------------------
-// One CTA per (instance, 128-column chunk of its clipped box).  An instance's float32 paste values
+// One CTA per (instance, column chunk of its clipped box: 128 columns, 32 for large boxes).  An instance's float32 paste values
 // exist only inside the box and are evaluated there from its tile (two-stage lerp, the values
 // CropAndPadMask would write).  The 8 warps take the box rows round-robin, lanes take 4 columns of
 // the chunk each (interleaved so that narrow boxes still fill the warp) and carry their column
@@ -447,7 +447,7 @@ struct BoxSummaryArgs {
     const int32_t* m_dev;      // M when there are no tiles
     BoxAcc* acc;               // [B * m_rows], zeroed before the launch
     uint32_t* acc_rowany;      // [B * m_rows, ceil(PH / 32)], zeroed before the launch
-    int B, m_rows, m_stride, mh, mw, PH, PW, chunks;      // chunks = ceil(PW / kBoxCols)
+    int B, m_rows, m_stride, mh, mw, PH, PW, chunks;      // chunks = ceil(PW / 32): most per instance
     float threshold;
     float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
@@ -463,19 +463,21 @@ struct BoxSmem {
     int last;
 };
 
-// One chunk (columns [c0, c0+128) of the box); every thread of the CTA calls it.
+// One chunk (columns [c0, c0 + 32*Q) of the box); every thread of the CTA calls it.  Q = 4 columns
+// per lane for small boxes (one CTA does the whole box), Q = 1 for large ones (more, shorter CTAs).
+template <int Q>
 __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c0, int mh, int mw,
                                            const uint32_t* __restrict__ rbits, int words, double& pix,
                                            double& size, double& colmax, int& cnt, int& inter) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bw = g.xmax - g.xmin;
-    // this lane's 4 columns of the chunk and their x lerp terms (paste_value, paste_common.cuh)
-    int xlo[4], xhi[4];
-    float lx[4];
-    bool live[4];
-    double col[4] = {0.0, 0.0, 0.0, 0.0};
+    // this lane's Q columns of the chunk and their x lerp terms (paste_value, paste_common.cuh)
+    int xlo[Q], xhi[Q];
+    float lx[Q];
+    bool live[Q];
+    double col[Q];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
         const int oxl = c0 + lane + 32 * q;
         live[q] = oxl < bw;
         const float p = __fmul_rn((float)oxl, g.sx);
@@ -483,10 +485,12 @@ __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c
         xlo[q] = max((int)fl, 0);
         xhi[q] = min((int)ceilf(p), mw - 1);
         lx[q] = __fsub_rn(p, fl);
+        col[q] = 0.0;
     }
     const int xw0 = g.xmin + c0 + lane;                      // frame column of q = 0; q adds 32 = one word
     for (int oy = g.ymin + warp; oy < g.ymax; oy += kBoxWarps) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float v[Q];
+        bool nz = false;
         {
             const float py = __fmul_rn((float)(oy - g.ymin), g.sy);
             const float fy = floorf(py);
@@ -494,49 +498,62 @@ __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c
             const float* r1 = S.tile + min((int)ceilf(py), mh - 1) * mw;
             const float ly = __fsub_rn(py, fy);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < Q; ++q) {
+                v[q] = 0.0f;
                 if (live[q]) {
                     const float tl = r0[xlo[q]], tr = r0[xhi[q]], bl = r1[xlo[q]], br = r1[xhi[q]];
                     const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx[q]));
                     const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx[q]));
                     v[q] = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
                 }
+                nz |= v[q] != 0.0f;
             }
         }
         unsigned on = 0u;
-        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) {
+        if (nz) {
             const float u = S.unit[oy];
             const double du = (double)u;
-            const double d0 = (double)v[0], d1 = (double)v[1], d2 = (double)v[2], d3 = (double)v[3];
-            col[0] = __dadd_rn(col[0], __dmul_rn(du, d0));
-            col[1] = __dadd_rn(col[1], __dmul_rn(du, d1));
-            col[2] = __dadd_rn(col[2], __dmul_rn(du, d2));
-            col[3] = __dadd_rn(col[3], __dmul_rn(du, d3));
-            const double rs = __dadd_rn(__dadd_rn(d0, d1), __dadd_rn(d2, d3));
+            double d[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                d[q] = (double)v[q];
+                col[q] = __dadd_rn(col[q], __dmul_rn(du, d[q]));
+                on |= (v[q] > 0.5f ? 1u : 0u) << q;
+            }
+            const double rs = Q == 4 ? __dadd_rn(__dadd_rn(d[0], d[1]), __dadd_rn(d[Q / 2], d[Q - 1])) : d[0];
             pix = __dadd_rn(pix, rs);
             size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), rs));          // unit ** 2 in float32
-#pragma unroll
-            for (int q = 0; q < 4; ++q) on |= (v[q] > 0.5f ? 1u : 0u) << q;
         }
         if (__any_sync(0xffffffffu, on != 0u)) {             // warp-uniform: the row has a pixel > 0.5
             if (lane == 0) atomicOr(&S.rowany[oy >> 5], 1u << (oy & 31));
             cnt += __popc(on);
+            // my_road bits of the lane's columns: all loads in flight before the first use
+            unsigned rw[Q];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if ((on >> q) & 1u)
-                    inter += (__ldg(rbits + (int64_t)oy * words + ((xw0 + 32 * q) >> 5)) >> ((xw0 + 32 * q) & 31)) & 1u;
+            for (int q = 0; q < Q; ++q) rw[q] = __ldg(rbits + (int64_t)oy * words + min((xw0 + 32 * q) >> 5, words - 1));
+#pragma unroll
+            for (int q = 0; q < Q; ++q) inter += ((on >> q) & 1u) & (rw[q] >> ((xw0 + 32 * q) & 31));
         }
     }
     // horizontal size: column sums of the 8 warps meet in shared memory
 #pragma unroll
-    for (int q = 0; q < 4; ++q) S.col[warp][lane + 32 * q] = col[q];
+    for (int q = 0; q < Q; ++q) S.col[warp][lane + 32 * q] = col[q];
     __syncthreads();
-    if (tid < kBoxCols) {
+    if (tid < 32 * Q) {
         double c = S.col[0][tid];
 #pragma unroll
         for (int w = 1; w < kBoxWarps; ++w) c = __dadd_rn(c, S.col[w][tid]);
         colmax = fmax(colmax, c);
     }
+}
+
+// Columns per lane for a box: 4 (one CTA per 128 columns) up to kBoxSmallArea pixels, else 1.
+// Measured on B200 (cfg-2 / stress): 32-column chunks for boxes > 16 K pixels made the kernel 1.8x /
+// 4x SLOWER (more CTAs, each paying the tile staging and the accumulator atomics), so the narrow
+// variant is disabled; the knob stays for frames much taller than 1080 rows.
+constexpr int kBoxSmallArea = INT_MAX;
+__device__ __forceinline__ int box_q(const PasteGeom& g) {
+    return (int64_t)(g.xmax - g.xmin) * (g.ymax - g.ymin) <= kBoxSmallArea ? 4 : 1;
 }
 
 __global__ void __launch_bounds__(kReduceThreads, 4)
@@ -575,7 +592,8 @@ box_summary_kernel(const BoxSummaryArgs A) {
         const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
-        const int nchunks = g.active ? (g.xmax - g.xmin + kBoxCols - 1) / kBoxCols : 1;
+        const int cols = 32 * box_q(g);                     // columns per chunk of this box
+        const int nchunks = g.active ? (g.xmax - g.xmin + cols - 1) / cols : 1;
         if (chunk >= nchunks) continue;                     // CTA-uniform
         float* o = A.out + ((int64_t)b * Mo + j) * 11;
         double pix = 0.0, size = 0.0, colmax = 0.0, vert = 0.0;
@@ -590,8 +608,12 @@ box_summary_kernel(const BoxSummaryArgs A) {
         for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) S.unit[y] = A.unit[(int64_t)b * PH + y];
         for (int i = (g.ymin >> 5) + tid; i <= ((g.ymax - 1) >> 5); i += kReduceThreads) S.rowany[i] = 0u;
         __syncthreads();
-        box_reduce(S, g, chunk * kBoxCols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size, colmax,
-                   cnt, inter);
+        if (cols == 32)
+            box_reduce<1>(S, g, chunk * cols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size,
+                          colmax, cnt, inter);
+        else
+            box_reduce<4>(S, g, chunk * cols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size,
+                          colmax, cnt, inter);
         __syncthreads();                                   // row flags complete
         if (nchunks == 1) {                                 // the whole box: finish here
             for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
@@ -775,7 +797,7 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
     MLP_CUDA(cudaMemsetAsync(ctx->arena[MLP_ARENA_BOXACC], 0, (size_t)acc_bytes, st));
     T.acc = static_cast<BoxAcc*>(ctx->arena[MLP_ARENA_BOXACC]);
     T.acc_rowany = reinterpret_cast<uint32_t*>(T.acc + (int64_t)batch * m_rows);
-    T.chunks = (frame_w + kBoxCols - 1) / kBoxCols;
+    T.chunks = kBoxSmallArea == INT_MAX ? (frame_w + kBoxCols - 1) / kBoxCols : (frame_w + 31) / 32;
     const int64_t items = (int64_t)batch * m_rows * T.chunks + batch;
     const int64_t cap = (int64_t)ctx->sm_count * 64;       // idle (instance, chunk) items are skipped in a loop
     const int grid = (int)(items < cap ? items : cap);
