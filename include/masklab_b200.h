@@ -330,6 +330,40 @@ int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* ma
                      float include_threshold, float* out_dev, int32_t* m_out_dev, int32_t* m_dev_out,
                      mlp_stream_t stream);
 
+/* ---- the overlay layers of the serving graph ------------------------------
+ * DrawSegmentation.call (engine/layers/misc.py:412-421) and DrawInstance.call (:440-463), wired in
+ * road_project/setup/serving.py:34-40.  images_dev [B,PH,PW,3] (MLP_U8 or MLP_F32), out_dev uint8
+ * [B,PH,PW,3] = cast(clip(images + (sum_c colors[c] * seg[..., c]) * alpha, 0, 255)).
+ *
+ * mlp_draw_segmentation: seg_dev [B,PH,PW,C] (MLP_I32 or MLP_F32), C = colors->num_classes.
+ * mlp_draw_instance: seg[..., c] = (sum of masks_dev[b, j] over the instances with det class == c)
+ *   > 0.5, masks_dev [B,M,PH,PW] (MLP_F32 as CropAndPadMask returns them, or MLP_U8 binary), summed
+ *   in instance order; M from m_dev / m_rows, m_stride 0 = compact.
+ * mlp_draw_tiles: the same image WITHOUT the [B,M,PH,PW] tensor: every instance's float32 paste
+ *   values are evaluated from its tile only where a pixel block touches its clipped box.  Tile
+ *   sources as for mlp_tile_summary (int32 tiles, or the fused tail after mlp_trim_paste); mask rows
+ *   of at most 32 columns.  With seg_dev / sem_colors not NULL, DrawSegmentation over the result
+ *   (serving.py:38-40) is applied in the same pass.                                             */
+#define MLP_MAX_DRAW_CLASSES 16
+typedef struct {
+    int32_t num_classes;
+    float   alpha;
+    float   rgb[MLP_MAX_DRAW_CLASSES][3];
+} mlp_draw_colors;
+int mlp_draw_segmentation(mlp_ctx* ctx, const void* images_dev, int image_dtype, const void* seg_dev,
+                          int seg_dtype, int batch, int frame_h, int frame_w, const mlp_draw_colors* colors,
+                          uint8_t* out_dev, mlp_stream_t stream);
+int mlp_draw_instance(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                      const void* masks_dev, int mask_dtype, int batch, int m_rows, int m_stride,
+                      const int32_t* m_dev, int frame_h, int frame_w, const mlp_draw_colors* colors,
+                      uint8_t* out_dev, mlp_stream_t stream);
+int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                   const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows, const int32_t* r_dev,
+                   int num_classes, const int32_t* counts_dev, int batch, int m_rows, int m_stride,
+                   const int32_t* m_dev, int mask_h, int mask_w, int frame_h, int frame_w,
+                   const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
+                   const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

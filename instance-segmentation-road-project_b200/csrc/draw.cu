@@ -1,0 +1,432 @@
+// draw.cu — the overlay layers of the serving graph: DrawSegmentation and
+// DrawInstance.
+//
+// Reference: /root/reference/engine/layers/misc.py:404-429 (DrawSegmentation: clip(images +
+// (sum_c colors[c] * seg[..., c]) * alpha, 0, 255) -> uint8), :432-475 (DrawInstance: per image and
+// class, (sum of the pasted masks of that class) > 0.5, then DrawSegmentation), wired in
+// /root/reference/road_project/setup/serving.py:34-40.  Restated in oracle/draw_oracle.py.
+//
+//   draw_segmentation_kernel  element-wise, one thread per pixel.
+//   draw_instance_kernel      drop-in: reads the [B,M,PH,PW] masks once (float32 or uint8), four
+//                             pixels per thread, instances grouped per class in shared memory so
+//                             that the per-class sums live in registers (HBM read-bound).
+//   pack_tiles_kernel +       fused: every instance's 28x28 tile as 28 bit rows plus its clipped-box
+//   draw_tiles_kernel         geometry; then one CTA per 16x64 pixel block finds the instances whose
+//                             box touches the block and evaluates their float32 paste values from
+//                             the bit rows (the values CropAndPadMask would write) only there.  The
+//                             [B,M,PH,PW] tensor is never written or read; the semantic overlay of
+//                             serving.py:38-40 can ride along in the same pass.
+#include "paste_common.cuh"
+
+namespace {
+
+constexpr int kDrawThreads = 256;
+constexpr int kMaxDrawInst = 2048;        // instances per image the class lists hold (MLP_MAX_KEEP)
+
+__device__ __forceinline__ float blend(float img, float csum, float alpha) {
+    // clip_by_value(images + color * alpha, 0, 255); the uint8 cast truncates
+    return fminf(fmaxf(__fadd_rn(img, __fmul_rn(csum, alpha)), 0.0f), 255.0f);
+}
+__device__ __forceinline__ float px_f32(const uint8_t* p) { return (float)__ldg(p); }
+__device__ __forceinline__ float px_f32(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float px_f32(const int32_t* p) { return (float)__ldg(p); }
+
+// ---- DrawSegmentation -----------------------------------------------------------------------
+template <typename ImgT, typename SegT>
+__global__ void __launch_bounds__(kDrawThreads)
+draw_segmentation_kernel(const ImgT* __restrict__ images, const SegT* __restrict__ seg, int64_t npix,
+                         const mlp_draw_colors col, uint8_t* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * kDrawThreads + threadIdx.x;
+    if (p >= npix) return;
+    const int C = col.num_classes;
+    float cs[3] = {0.f, 0.f, 0.f};
+    const SegT* s = seg + p * C;
+    for (int c = 0; c < C; ++c) {                          // reduce_sum(colors * seg[..., None], axis=-2)
+        const float v = px_f32(s + c);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cs[k] = __fadd_rn(cs[k], __fmul_rn(col.rgb[c][k], v));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        out[p * 3 + k] = (uint8_t)__float2uint_rz(blend(px_f32(images + p * 3 + k), cs[k], col.alpha));
+}
+
+// ---- DrawInstance over the materialised masks -----------------------------------------------
+template <typename T> __device__ __forceinline__ void mask4(const T* p, bool vec, int n, float* v);
+template <> __device__ __forceinline__ void mask4<float>(const float* p, bool vec, int n, float* v) {
+    if (vec) {
+        const float4 f = ldg_stream_f4(reinterpret_cast<const float4*>(p));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = q < n ? __ldg(p + q) : 0.0f;
+    }
+}
+template <> __device__ __forceinline__ void mask4<uint8_t>(const uint8_t* p, bool vec, int n, float* v) {
+    if (vec) {
+        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+        v[0] = (float)u.x; v[1] = (float)u.y; v[2] = (float)u.z; v[3] = (float)u.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = q < n ? (float)__ldg(p + q) : 0.0f;
+    }
+}
+
+template <typename ImgT, typename MaskT>
+__global__ void __launch_bounds__(kDrawThreads)
+draw_instance_kernel(const ImgT* __restrict__ images, const int32_t* __restrict__ det, const MaskT* __restrict__ masks,
+                     int m_rows, int m_stride, const int32_t* __restrict__ m_dev, int npx,
+                     const mlp_draw_colors col, uint8_t* __restrict__ out) {
+    __shared__ unsigned short s_list[kMaxDrawInst];        // instances grouped by class, order j inside
+    __shared__ int s_beg[MLP_MAX_DRAW_CLASSES + 1];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int M = m_dev ? *m_dev : m_rows;
+    if (M > m_rows) M = m_rows;
+    if (m_stride == 0) m_stride = M;
+    const int C = col.num_classes;
+    if (tid < 32) {                                        // tf.where(det[..., -2] == class_id) per class
+        int n = 0;
+        for (int c = 0; c < C; ++c) {
+            if (lane == 0) s_beg[c] = n;
+            for (int j0 = 0; j0 < M; j0 += 32) {
+                const int j = j0 + lane;
+                const bool hit = j < M && det[((int64_t)b * m_stride + j) * 6 + 4] == c;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) s_list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+                n += __popc(m);
+            }
+        }
+        if (lane == 0) s_beg[C] = n;
+    }
+    __syncthreads();
+    const int p = (blockIdx.x * kDrawThreads + tid) * 4;   // four consecutive pixels of the frame
+    if (p >= npx) return;
+    const int n = min(4, npx - p);
+    const bool vec = n == 4 && (npx & 3) == 0;
+    const MaskT* mb = masks + (int64_t)b * M * npx + p;
+    float cs[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};               // reduce_sum of the class's masks, order j
+        const int i1 = s_beg[c + 1];
+        int i = s_beg[c];
+        for (; i + 4 <= i1; i += 4) {                      // four mask loads in flight
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mask4<MaskT>(mb + (int64_t)s_list[i + u] * npx, vec, n, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = __fadd_rn(acc[q], v[u][q]);
+        }
+        for (; i < i1; ++i) {
+            float v[4];
+            mask4<MaskT>(mb + (int64_t)s_list[i] * npx, vec, n, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = __fadd_rn(acc[q], v[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (acc[q] > 0.5f)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], col.rgb[c][k]);
+    }
+    const int64_t o = ((int64_t)b * npx + p) * 3;
+    for (int q = 0; q < n; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            out[o + q * 3 + k] = (uint8_t)__float2uint_rz(blend(px_f32(images + o + q * 3 + k), cs[q][k], col.alpha));
+}
+
+// ---- DrawInstance straight from the mask tiles ----------------------------------------------
+struct DrawGeom {                         // clipped box of an instance in the frame, 32 bytes
+    int xmin, xmax, ymin, ymax;
+    float sx, sy;
+    int cls;                              // -1: inactive (filtered, empty box) or class outside the colour table
+    int pad;
+};
+
+// One warp per instance: bit rows of its {0,1} tile (mask_w <= 32) and its geometry.
+__global__ void __launch_bounds__(kDrawThreads)
+pack_tiles_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh, int mw,
+                  int PH, int PW, int num_colors, DrawGeom* __restrict__ geom, uint32_t* __restrict__ bits,
+                  int32_t* __restrict__ m_used) {
+    int M, thr;
+    paste_scalars(S, B, m_rows, M, thr);
+    if (m_stride == 0) m_stride = M;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *m_used = M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t inst = (int64_t)blockIdx.x * (kDrawThreads / 32) + warp;
+    if (inst >= (int64_t)B * M) return;
+    const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
+    const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
+    const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
+    const int cls = row[4];
+    const bool draw = g.active && cls >= 0 && cls < num_colors;
+    const int64_t slot = (int64_t)b * m_rows + j;
+    if (lane == 0) {
+        DrawGeom d;
+        d.xmin = g.xmin; d.xmax = g.xmax; d.ymin = g.ymin; d.ymax = g.ymax; d.sx = g.sx; d.sy = g.sy;
+        d.cls = draw ? cls : -1; d.pad = 0;
+        geom[slot] = d;
+    }
+    if (!draw) return;
+    const TileRef tref = tile_ref(S, b, j, m_stride, mh * mw, cls, mh, mw);
+    for (int y = 0; y < mh; ++y) {
+        const int v = lane < mw ? tref.at(y * mw + lane) : 0;
+        const unsigned w = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) bits[slot * mh + y] = w;
+    }
+}
+
+constexpr int kBlkH = 16, kBlkW = 64;     // pixel block of a CTA: 16 rows x 16 threads x 4 pixels
+constexpr int kMaxCand = 1024;            // instances touching one block kept in shared memory
+
+struct DrawTilesArgs {
+    const void* images;
+    int image_is_f32;
+    const DrawGeom* geom;      // [B, m_rows]
+    const uint32_t* bits;      // [B, m_rows, mh]
+    const int32_t* m_used;     // [1]
+    const void* seg;           // [B, PH, PW, Cs] or NULL
+    int seg_is_f32;
+    int B, m_rows, mh, mw, PH, PW;
+    mlp_draw_colors inst, sem;
+    uint8_t* out;
+};
+
+__global__ void __launch_bounds__(kDrawThreads)
+draw_tiles_kernel(const DrawTilesArgs A) {
+    __shared__ unsigned short s_cand[kMaxCand];
+    __shared__ int s_n;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int M = min(*A.m_used, A.m_rows);
+    const int by0 = blockIdx.y * kBlkH, bx0 = blockIdx.x * kBlkW;
+    const DrawGeom* G = A.geom + (int64_t)b * A.m_rows;
+    // instances whose clipped box touches this block, in instance order (one warp, ballot compaction)
+    if (tid < 32) {
+        int n = 0;
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            if (j < M) {
+                const DrawGeom d = G[j];
+                hit = d.cls >= 0 && d.ymin < by0 + kBlkH && d.ymax > by0 && d.xmin < bx0 + kBlkW && d.xmax > bx0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int k = n + __popc(m & ((1u << lane) - 1u));
+            if (hit && k < kMaxCand) s_cand[k] = (unsigned short)j;
+            n += __popc(m);
+        }
+        if (lane == 0) s_n = n;
+    }
+    __syncthreads();
+    const int ncand = s_n;
+    const int oy = by0 + (tid >> 4), ox = bx0 + (tid & 15) * 4;
+    if (oy >= A.PH || ox >= A.PW) return;
+    const int mh = A.mh, mw = A.mw;
+    const int C = A.inst.num_classes;
+    float cs[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};               // reduce_sum of the class's masks, order j
+        // more candidates than the list holds: walk all instances instead (same order, same result)
+        const int nwalk = ncand <= kMaxCand ? ncand : M;
+        for (int i = 0; i < nwalk; ++i) {
+            const int j = ncand <= kMaxCand ? (int)s_cand[i] : i;
+            const DrawGeom d = G[j];
+            if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
+            // the float32 value CropAndPadMask writes at (oy, ox+q): two-stage lerp of the {0,1} tile
+            const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
+            const float fy = floorf(py);
+            const float ly = __fsub_rn(py, fy);
+            const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + j) * mh;
+            const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = ox + q;
+                if (x < d.xmin || x >= d.xmax) continue;
+                const float p = __fmul_rn((float)(x - d.xmin), d.sx);
+                const float fl = floorf(p);
+                const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
+                const float lx = __fsub_rn(p, fl);
+                const float tl = (float)((w0 >> xlo) & 1u), tr = (float)((w0 >> xhi) & 1u);
+                const float bl = (float)((w1 >> xlo) & 1u), br = (float)((w1 >> xhi) & 1u);
+                const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+                const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+                acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (acc[q] > 0.5f)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], A.inst.rgb[c][k]);
+    }
+    const int64_t pix0 = ((int64_t)b * A.PH + oy) * A.PW + ox;
+    const int n = min(4, A.PW - ox);
+    for (int q = 0; q < n; ++q) {
+        const int64_t p = pix0 + q;
+        float sc[3] = {0.f, 0.f, 0.f};
+        if (A.seg) {                                       // DrawSegmentation over the result (serving.py:38-40)
+            for (int c = 0; c < A.sem.num_classes; ++c) {
+                const float v = A.seg_is_f32 ? px_f32(static_cast<const float*>(A.seg) + p * A.sem.num_classes + c)
+                                             : px_f32(static_cast<const int32_t*>(A.seg) + p * A.sem.num_classes + c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[k] = __fadd_rn(sc[k], __fmul_rn(A.sem.rgb[c][k], v));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float img = A.image_is_f32 ? px_f32(static_cast<const float*>(A.images) + p * 3 + k)
+                                             : px_f32(static_cast<const uint8_t*>(A.images) + p * 3 + k);
+            float v = (float)__float2uint_rz(blend(img, cs[q][k], A.inst.alpha));      // uint8 of DrawInstance
+            if (A.seg) v = (float)__float2uint_rz(blend(v, sc[k], A.sem.alpha));
+            A.out[p * 3 + k] = (uint8_t)v;
+        }
+    }
+}
+
+int check_colors(const char* who, const mlp_draw_colors* c) {
+    MLP_CHECK_ARG(c && c->num_classes >= 1 && c->num_classes <= MLP_MAX_DRAW_CLASSES,
+                  "%s: colour table needs 1..%d classes", who, MLP_MAX_DRAW_CLASSES);
+    return MLP_OK;
+}
+
+}  // namespace
+
+// ================================================================ host side ===
+extern "C" int mlp_draw_segmentation(mlp_ctx* ctx, const void* images_dev, int image_dtype, const void* seg_dev,
+                                     int seg_dtype, int batch, int frame_h, int frame_w,
+                                     const mlp_draw_colors* colors, uint8_t* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && images_dev && seg_dev && out_dev, "mlp_draw_segmentation: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && frame_h >= 1 && frame_w >= 1, "mlp_draw_segmentation: bad shape");
+    MLP_CHECK_ARG(image_dtype == MLP_U8 || image_dtype == MLP_F32, "mlp_draw_segmentation: images must be u8 or f32");
+    MLP_CHECK_ARG(seg_dtype == MLP_I32 || seg_dtype == MLP_F32, "mlp_draw_segmentation: seg must be i32 or f32");
+    int rc = check_colors("mlp_draw_segmentation", colors);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_DRAW, st);
+    const int64_t npix = (int64_t)batch * frame_h * frame_w;
+    const int grid = (int)((npix + kDrawThreads - 1) / kDrawThreads);
+#define MLP_DRAW_SEG(IT, ST)                                                                             \
+    draw_segmentation_kernel<IT, ST><<<grid, kDrawThreads, 0, st>>>(static_cast<const IT*>(images_dev), \
+                                                                    static_cast<const ST*>(seg_dev), npix, *colors, out_dev)
+    if (image_dtype == MLP_U8 && seg_dtype == MLP_I32) MLP_DRAW_SEG(uint8_t, int32_t);
+    else if (image_dtype == MLP_U8) MLP_DRAW_SEG(uint8_t, float);
+    else if (seg_dtype == MLP_I32) MLP_DRAW_SEG(float, int32_t);
+    else MLP_DRAW_SEG(float, float);
+#undef MLP_DRAW_SEG
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
+
+extern "C" int mlp_draw_instance(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                                 const void* masks_dev, int mask_dtype, int batch, int m_rows, int m_stride,
+                                 const int32_t* m_dev, int frame_h, int frame_w, const mlp_draw_colors* colors,
+                                 uint8_t* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && images_dev && det_i32_dev && masks_dev && out_dev, "mlp_draw_instance: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && batch <= 65535 && frame_h >= 1 && frame_w >= 1 && m_rows >= 1 &&
+                      m_rows <= kMaxDrawInst && (m_stride >= m_rows || (m_stride == 0 && m_dev)),
+                  "mlp_draw_instance: bad shape");
+    MLP_CHECK_ARG((int64_t)frame_h * frame_w < (1ll << 30), "mlp_draw_instance: frame too large");
+    MLP_CHECK_ARG(image_dtype == MLP_U8 || image_dtype == MLP_F32, "mlp_draw_instance: images must be u8 or f32");
+    MLP_CHECK_ARG(mask_dtype == MLP_U8 || mask_dtype == MLP_F32, "mlp_draw_instance: masks must be u8 or f32");
+    MLP_CHECK_ARG(mlp_aligned16(masks_dev), "mlp_draw_instance: masks must be 16-byte aligned");
+    int rc = check_colors("mlp_draw_instance", colors);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_DRAW, st);
+    const int npx = frame_h * frame_w;
+    const dim3 grid((npx + kDrawThreads * 4 - 1) / (kDrawThreads * 4), batch);
+#define MLP_DRAW_INST(IT, MT)                                                                               \
+    draw_instance_kernel<IT, MT><<<grid, kDrawThreads, 0, st>>>(static_cast<const IT*>(images_dev), det_i32_dev, \
+                                                                static_cast<const MT*>(masks_dev), m_rows,   \
+                                                                m_stride, m_dev, npx, *colors, out_dev)
+    if (image_dtype == MLP_U8 && mask_dtype == MLP_U8) MLP_DRAW_INST(uint8_t, uint8_t);
+    else if (image_dtype == MLP_U8) MLP_DRAW_INST(uint8_t, float);
+    else if (mask_dtype == MLP_U8) MLP_DRAW_INST(float, uint8_t);
+    else MLP_DRAW_INST(float, float);
+#undef MLP_DRAW_INST
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
+
+extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                              const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows,
+                              const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch,
+                              int m_rows, int m_stride, const int32_t* m_dev, int mask_h, int mask_w, int frame_h,
+                              int frame_w, const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
+                              const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && images_dev && det_i32_dev && out_dev, "mlp_draw_tiles: NULL argument");
+    MLP_CHECK_ARG(masks_i32_dev || (roi_masks_dev && counts_dev && num_classes >= 1 && r_rows >= 1),
+                  "mlp_draw_tiles: neither int32 tiles nor a prepared fused tail");
+    MLP_CHECK_ARG(batch >= 1 && batch <= 65535 && m_rows >= 1 && m_rows <= 65535 && frame_h >= 1 && frame_w >= 1 &&
+                      (m_stride >= m_rows || (m_stride == 0 && m_dev)),
+                  "mlp_draw_tiles: bad shape");
+    MLP_CHECK_ARG(mask_h >= 1 && mask_w >= 1 && mask_w <= 32 && mask_h * mask_w <= kMaxTile,
+                  "mlp_draw_tiles: mask tile %dx%d (rows of at most 32 columns)", mask_h, mask_w);
+    MLP_CHECK_ARG(image_dtype == MLP_U8 || image_dtype == MLP_F32, "mlp_draw_tiles: images must be u8 or f32");
+    MLP_CHECK_ARG((seg_dev != nullptr) == (sem_colors != nullptr), "mlp_draw_tiles: seg_dev and sem_colors go together");
+    MLP_CHECK_ARG(!seg_dev || seg_dtype == MLP_I32 || seg_dtype == MLP_F32, "mlp_draw_tiles: seg must be i32 or f32");
+    int rc = check_colors("mlp_draw_tiles", inst_colors);
+    if (rc) return rc;
+    if (sem_colors && (rc = check_colors("mlp_draw_tiles", sem_colors))) return rc;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_DRAW, st);
+    PasteSrc S;
+    memset(&S, 0, sizeof(S));
+    if (masks_i32_dev) {
+        int32_t* thr_dev = ctx->ctr;        // ctr[0]: paste row-filter threshold
+        paste_threshold_kernel<<<1, 1024, 0, st>>>(det_i32_dev, batch, m_rows, m_stride, m_dev, thr_dev);
+        MLP_LAUNCH_CHECK(ctx);
+        S.masks_i32 = masks_i32_dev;
+        S.m_dev = m_dev;
+        S.thr_dev = thr_dev;
+    } else {
+        MLP_CHECK_ARG(m_stride == m_rows, "mlp_draw_tiles: the fused tail uses capacity rows (m_stride == m_rows)");
+        const FusedTail need = fused_tail_layout(nullptr, batch, m_rows, mask_h, mask_w);
+        MLP_CHECK_ARG(ctx->arena[MLP_ARENA_FUSED] && ctx->arena_bytes[MLP_ARENA_FUSED] >= need.bytes,
+                      "mlp_draw_tiles: call mlp_trim_paste with the same shapes first");
+        const FusedTail ft = fused_tail_layout(ctx->arena[MLP_ARENA_FUSED], batch, m_rows, mask_h, mask_w);
+        S.fused = 1;
+        S.roi_masks = roi_masks_dev;
+        S.tail_src = ft.tail_src;
+        S.tail_bits = ft.tail_bits;
+        S.r_dev = r_dev;
+        S.r_rows = r_rows;
+        S.C = num_classes;
+        S.counts = counts_dev;
+        S.confmax = ft.confmax;
+    }
+    // scratch: geometry [B,m_rows] + bit rows [B,m_rows,mh] + M
+    const int64_t n_inst = (int64_t)batch * m_rows;
+    const int64_t bytes = n_inst * (int64_t)sizeof(DrawGeom) + n_inst * mask_h * 4 + 16;
+    rc = mlp_ensure_scratch(ctx, MLP_ARENA_DRAW, bytes);
+    if (rc) return rc;
+    DrawGeom* geom = static_cast<DrawGeom*>(ctx->arena[MLP_ARENA_DRAW]);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(geom + n_inst);
+    int32_t* m_used = reinterpret_cast<int32_t*>(bits + n_inst * mask_h);
+    const int wpc = kDrawThreads / 32;
+    pack_tiles_kernel<<<(int)((n_inst + wpc - 1) / wpc), kDrawThreads, 0, st>>>(
+        det_i32_dev, S, batch, m_rows, m_stride, mask_h, mask_w, frame_h, frame_w, inst_colors->num_classes, geom,
+        bits, m_used);
+    MLP_LAUNCH_CHECK(ctx);
+    DrawTilesArgs A;
+    memset(&A, 0, sizeof(A));
+    A.images = images_dev; A.image_is_f32 = image_dtype == MLP_F32; A.geom = geom; A.bits = bits; A.m_used = m_used;
+    A.seg = seg_dev; A.seg_is_f32 = seg_dtype == MLP_F32; A.B = batch; A.m_rows = m_rows; A.mh = mask_h;
+    A.mw = mask_w; A.PH = frame_h; A.PW = frame_w; A.inst = *inst_colors;
+    if (sem_colors) A.sem = *sem_colors;
+    A.out = out_dev;
+    draw_tiles_kernel<<<dim3((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch), kDrawThreads, 0, st>>>(A);
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}

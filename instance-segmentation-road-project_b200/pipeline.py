@@ -270,6 +270,37 @@ class PostProcessPipeline:
         self._compact_det = False
         return self.det_i32, self.summary, self.summary_m
 
+    def draw(self, rois, roi_masks, images, instance_colors, instance_alpha=.3, seg_outs=None,
+             semantic_colors=None, semantic_alpha=.3):
+        """SURVEY 8(f) rank 2 behind the tail: DrawInstance (+ DrawSegmentation when seg_outs is given)
+        of road_project/setup/serving.py:34-40 drawn straight from the mask tiles.  Needs the tail
+        prepared by trim_and_paste / trim_and_summarize of the same batch.  images: uint8 or float32
+        [B,PH,PW,3].  Returns uint8 [B,PH,PW,3]."""
+        c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
+        if not self.cfg.fused:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "draw needs the fused tail (fused=True)")
+        mh, mw = self.cfg.mask_size
+        PH, PW = self.frame_hw
+        if tuple(images.shape) != (B, PH, PW, 3) or images.dtype not in (torch.uint8, torch.float32):
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"images must be uint8/float32 [{B},{PH},{PW},3]")
+        col = rt.DrawColorsC.make(instance_colors, instance_alpha)
+        sem, seg_ptr, seg_t = None, ctypes.c_void_p(None), rt.MLP_I32
+        if seg_outs is not None:
+            sem = rt.DrawColorsC.make(semantic_colors, semantic_alpha)
+            if tuple(seg_outs.shape) != (B, PH, PW, sem.num_classes) or seg_outs.dtype not in (torch.int32, torch.float32):
+                raise rt.InvalidArgumentError(rt.MLP_EINVAL, "seg_outs must be int32/float32 [B,PH,PW,len(semantic_colors)]")
+            seg_ptr = c.view(seg_outs)
+            seg_t = rt.MLP_I32 if seg_outs.dtype == torch.int32 else rt.MLP_F32
+        if not hasattr(self, "vis"):
+            self.vis = c.empty((B, PH, PW, 3), torch.uint8)
+        r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
+        rt.check(lib.mlp_draw_tiles(
+            c.handle, c.view(images), rt.MLP_U8 if images.dtype == torch.uint8 else rt.MLP_F32,
+            c.view(self.det_i32), ctypes.c_void_p(None), c.view(roi_masks, torch.float32), L * K, r_dev, self.C,
+            c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw, PH, PW, ctypes.byref(col),
+            seg_ptr, seg_t, ctypes.byref(sem) if sem is not None else None, c.view(self.vis), c.stream()))
+        return self.vis
+
     def summary_view(self):
         """Reference-shaped [B,M',11] view of the last trim_and_summarize (one D2H of M')."""
         Mo = int(self.summary_m.item())

@@ -47,6 +47,27 @@ class DetectionParamsC(ctypes.Structure):
                 ("strict_batch", ctypes.c_int32)]
 
 
+MLP_MAX_DRAW_CLASSES = 16
+
+
+class DrawColorsC(ctypes.Structure):
+    _fields_ = [("num_classes", ctypes.c_int32), ("alpha", ctypes.c_float),
+                ("rgb", (ctypes.c_float * 3) * MLP_MAX_DRAW_CLASSES)]
+
+    @classmethod
+    def make(cls, colors, alpha):
+        colors = [list(c) for c in colors]
+        if not 1 <= len(colors) <= MLP_MAX_DRAW_CLASSES or any(len(c) != 3 for c in colors):
+            raise InvalidArgumentError(MLP_EINVAL, f"colors must be 1..{MLP_MAX_DRAW_CLASSES} RGB triples")
+        out = cls()
+        out.num_classes = len(colors)
+        out.alpha = float(alpha)
+        for i, c in enumerate(colors):
+            for k in range(3):
+                out.rgb[i][k] = float(c[k])
+        return out
+
+
 class TensorViewC(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("device_id", ctypes.c_int32), ("ndim", ctypes.c_int32),
                 ("dtype_code", ctypes.c_int32), ("dtype_bits", ctypes.c_int32),
@@ -96,6 +117,10 @@ SIGNATURES = {
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
                               _F, _P, _P, _P, _P]),
+    "mlp_draw_segmentation": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
+    "mlp_draw_instance": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
+    "mlp_draw_tiles": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I,
+                            ctypes.POINTER(DrawColorsC), _P, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_mold_batch_plan": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "mlp_mold_batch_run": (_I, [_P, _P, _P, _L, _L, _I, _I, _P, _P, _P]),
 }

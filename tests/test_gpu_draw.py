@@ -1,0 +1,122 @@
+"""GPU parity of the overlay layers against oracle/draw_oracle.py through the
+C ABI (mlp_draw_segmentation, mlp_draw_instance, mlp_draw_tiles): uint8 images, bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import draw_oracle as do
+from oracle import masklab_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+INST_COLORS = [[192, 32, 128], [160, 96, 0], [96, 0, 128], [32, 96, 192], [96, 32, 128]]   # config.py:32-36
+SEM_COLORS = [[64, 0, 128], [128, 96, 0], [128, 192, 0]]                                    # config.py:39-41
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def frames(B, PH, PW, seed):
+    return np.random.default_rng(seed).integers(0, 256, (B, PH, PW, 3)).astype(np.uint8)
+
+
+def scene(B, M, PH, PW, seed, C=5):
+    det = synth.int_detections(B, M, C, PH, PW, seed=seed, pad_tail=1)
+    det[0, 0] = [PW // 2, PH // 2, 2 * PW, 2 * PH, 1, 99]        # frame-sized box
+    det[0, 1] = det[0, 2]                                         # two instances of one class on one box
+    det[0, 1, 5] = 95
+    if M > 4:
+        det[1, 3, 4] = 7                                          # class outside the colour table
+    rng = np.random.default_rng(seed + 1)
+    ins = (rng.random((B, M, 28, 28)) > 0.45).astype(np.int32)
+    return det, ins, mo.crop_and_pad_mask((PH, PW), det, ins)
+
+
+@pytest.mark.parametrize("PH,PW,img_dtype,seg_dtype", [(40, 64, "u8", "i32"), (33, 50, "f32", "i32"),
+                                                       (24, 130, "u8", "f32")])
+def test_draw_segmentation(PH, PW, img_dtype, seg_dtype):
+    import masklab_b200 as ml
+    B = 2
+    img = frames(B, PH, PW, 1)
+    seg = synth.semantic_map(B, PH, PW, seed=2)
+    if img_dtype == "f32":
+        img = img.astype(np.float32) + np.float32(0.25)
+    if seg_dtype == "f32":
+        seg = (seg * np.random.default_rng(3).random(seg.shape)).astype(np.float32)   # soft maps
+    want = do.draw_segmentation(img, seg, SEM_COLORS, 0.3)
+    got = ml.DrawSegmentation(SEM_COLORS, 0.3)([dev(img), dev(seg)])
+    assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("PH,PW,M,mask_dtype", [(48, 80, 5, "f32"), (37, 53, 4, "f32"), (48, 80, 5, "u8"),
+                                                (64, 300, 7, "f32")])
+def test_draw_instance_matches_oracle(PH, PW, M, mask_dtype):
+    import masklab_b200 as ml
+    B = 2
+    img = frames(B, PH, PW, 5)
+    det, ins, masks = scene(B, M, PH, PW, seed=PW)
+    if mask_dtype == "u8":
+        masks = (masks > 0.5).astype(np.uint8)
+    want = do.draw_instance(img, det, masks, INST_COLORS, 0.3)
+    got = ml.DrawInstance(INST_COLORS, 0.3)([dev(img), dev(det), dev(masks)]).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert (want != img).any()
+
+
+@pytest.mark.parametrize("PH,PW,M", [(48, 80, 5), (37, 53, 4), (64, 300, 7), (200, 333, 12)])
+def test_draw_from_tiles_equals_draw_of_pasted_masks(PH, PW, M):
+    import masklab_b200 as ml
+    B = 2
+    img = frames(B, PH, PW, 7)
+    det, ins, masks = scene(B, M, PH, PW, seed=PW + 3)
+    layer = ml.DrawInstance(INST_COLORS, 0.3)
+    want = do.draw_instance(img, det, masks, INST_COLORS, 0.3)
+    got = layer.from_tiles([dev(img), dev(det), dev(ins)]).cpu().numpy()
+    assert np.array_equal(got, want)
+    # with the semantic overlay of serving.py:38-40 in the same pass
+    seg = synth.semantic_map(B, PH, PW, seed=9)
+    want2 = do.draw_segmentation(want, seg, SEM_COLORS, 0.3)
+    got2 = layer.from_tiles([dev(img), dev(det), dev(ins)], seg_outs=dev(seg), semantic_colors=SEM_COLORS,
+                            semantic_alpha=0.3).cpu().numpy()
+    assert np.array_equal(got2, want2)
+
+
+def test_pipeline_draw():
+    import masklab_b200 as ml
+    B, H, W, C, Cf = 2, 128, 256, 3, 16
+    PH, PW = 256, 512
+    cfgp = synth.prior_config()
+    N = synth.num_anchors(cfgp, H, W)
+    loc, cls = synth.head_tensors(B, N, C, mu=-5.0, seed=51)
+    fmaps = synth.fpn_maps(B, H, W, Cf, seed=52)
+    kw = dict(min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+              nms_max_output_size=30, max_k=2, base_size=36)
+    probs = {}
+
+    def mask_head(roi_fmaps, roi_boxes):
+        probs["m"] = synth.mask_probs(B, roi_boxes.shape[1], C, seed=53)
+        return probs["m"]
+
+    want = mo.full_path(loc, cls, fmaps, mask_head, cfgp, (H, W), (PH, PW), **kw)
+    img = frames(B, PH, PW, 54)
+    seg = synth.semantic_map(B, PH, PW, seed=55)
+    vis_i = do.draw_instance(img, want["det_i"], want["pasted"], INST_COLORS[:C], 0.3)
+    vis = do.draw_segmentation(vis_i, seg, SEM_COLORS, 0.3)
+    pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, Cf, B, ml.DetectionConfig(**kw))
+    rois = pipe.detect_and_align(dev(loc), dev(cls), [dev(f) for f in fmaps])
+    pipe.trim_and_summarize(rois, dev(probs["m"]), dev(seg))
+    got_i = pipe.draw(rois, dev(probs["m"]), dev(img), INST_COLORS[:C], 0.3).cpu().numpy().copy()
+    assert np.array_equal(got_i, vis_i)
+    got = pipe.draw(rois, dev(probs["m"]), dev(img), INST_COLORS[:C], 0.3, seg_outs=dev(seg),
+                    semantic_colors=SEM_COLORS, semantic_alpha=0.3).cpu().numpy()
+    assert np.array_equal(got, vis)
+    assert ml.DrawInstance(INST_COLORS).get_config()["alpha"] == 0.3
+
+
+def test_draw_rejects_cpu_tensors():
+    import masklab_b200 as ml
+    with pytest.raises(ml.InvalidArgumentError):
+        ml.DrawSegmentation(SEM_COLORS)([torch.zeros((1, 4, 4, 3), dtype=torch.uint8),
+                                         torch.zeros((1, 4, 4, 3), dtype=torch.int32)])
