@@ -410,9 +410,17 @@ def run_ours(args, wl):
     if not args.no_summary:
         h_seg = pin(synth.semantic_map(B, PH, PW, seed=500 + rank))
         d_seg = h_seg.cuda()
+        h_img = pin(np.random.default_rng(600 + rank).integers(0, 256, (B, PH, PW, 3)).astype(np.uint8))
+        d_img = h_img.cuda()
+
+        def serve():
+            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+            pipe.trim_and_summarize(r_, d_masks, d_seg)
+            pipe.draw(r_, d_masks, d_img, INST_COLORS[:C], 0.3, seg_outs=d_seg, semantic_colors=SEM_COLORS,
+                      semantic_alpha=0.3)
+
         pipe.ctx.profile(False)
-        r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
-        pipe.trim_and_summarize(r_, d_masks, d_seg)
+        serve()
         Mo = int(pipe.summary_m.item())
         torch.cuda.synchronize()
         pipe.ctx.profile(True)
@@ -420,22 +428,22 @@ def run_ours(args, wl):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_):
-            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
-            pipe.trim_and_summarize(r_, d_masks, d_seg)
+            serve()
         e1.record()
         torch.cuda.synchronize()
         st_ = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
         pipe.ctx.profile(False)
         ms_s = e0.elapsed_time(e1) / n_
         summary_leg = {
-            "what": "decode+NMS+RoIAlign, then SummaryOutput straight from the mask tiles "
-                    "(trim_and_summarize, no [B,M,PH,PW] tensor); single stream, inputs resident in HBM",
+            "what": "decode+NMS+RoIAlign, then the two consumers of the masks in the serving graph - SummaryOutput "
+                    "and the DrawInstance+DrawSegmentation overlay - straight from the mask tiles "
+                    "(trim_and_summarize + draw, no [B,M,PH,PW] tensor); single stream, inputs resident in HBM",
             "value": world * B / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
             "rows_per_image": Mo, "stage_ms": st_,
-            "seg_bytes": int(h_seg.numel() * 4)}
+            "seg_bytes": int(h_seg.numel() * 4), "frame_bytes": int(h_img.numel())}
         if not args.no_e2e:
             summary_leg["e2e"] = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier,
-                                         h_seg=h_seg, summary_rows=Mo)
+                                         h_seg=h_seg, summary_rows=Mo, h_img=h_img)
 
     if rank == 0:
         cpu = None
@@ -454,7 +462,7 @@ def run_ours(args, wl):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "e2e_bitpacked": e2e_bits, "summary_path": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_bitpacked": e2e_bits, "serving_tail": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
             "detections": {"M": M, "R": R, "Mf": mf, "kept_per_image_mean": float(counts.mean())},
             "device_bytes": pipe.device_bytes(),
         }
@@ -475,8 +483,12 @@ def algorithmic_bytes(wl, N, M):
     return decode + det + fm + crops + trim + paste
 
 
+INST_COLORS = [[192, 32, 128], [160, 96, 0], [96, 0, 128], [32, 96, 192], [96, 32, 128], [64, 64, 64]]
+SEM_COLORS = [[64, 0, 128], [128, 96, 0], [128, 192, 0]]      # engine/config.py:32-42
+
+
 def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False, h_seg=None,
-            summary_rows=0):
+            summary_rows=0, h_img=None):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
     host memory.  Three streams (copy-in, compute, copy-out) and two sets of device input buffers,
@@ -491,6 +503,7 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
                  fmaps=[torch.empty_like(f, device="cuda") for f in h_fmaps],
                  masks=torch.empty_like(h_masks, device="cuda"),
                  seg=(torch.empty_like(h_seg, device="cuda") if h_seg is not None else None),
+                 img=(torch.empty_like(h_img, device="cuda") if h_img is not None else None),
                  free=None) for _ in range(NB)]
     summary = h_seg is not None
     out_det = torch.empty((B * (pipe.K if summary else M) * 6,), dtype=torch.int32).pin_memory()
@@ -498,8 +511,10 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
         out_masks = torch.empty((B * summary_rows * 11,), dtype=torch.float32).pin_memory()
     else:
         out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps + ([h_seg] if summary else []))
-    d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size()
+    out_vis = torch.empty_like(h_img).pin_memory() if h_img is not None else None
+    h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps + ([h_seg] if summary else [])
+              + ([h_img] if h_img is not None else []))
+    d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size() + (out_vis.numel() if h_img is not None else 0)
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     state = {"i": 0, "out_done": None}
 
@@ -516,6 +531,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             buf["masks"].copy_(h_masks, non_blocking=True)
             if summary:
                 buf["seg"].copy_(h_seg, non_blocking=True)
+            if h_img is not None:
+                buf["img"].copy_(h_img, non_blocking=True)
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
         with torch.cuda.stream(s_cmp):
@@ -523,8 +540,12 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             if state["out_done"] is not None:
                 s_cmp.wait_event(state["out_done"])         # previous results copied out
             r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"])
+            vis = None
             if summary:
                 det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])
+                if h_img is not None:
+                    vis = pipe.draw(r, buf["masks"], buf["img"], INST_COLORS[:wl["C"]], 0.3, seg_outs=buf["seg"],
+                                    semantic_colors=SEM_COLORS, semantic_alpha=0.3)
             else:
                 det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
             cmp_done = torch.cuda.Event()
@@ -534,6 +555,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             s_out.wait_event(cmp_done)
             out_det.copy_(det_i32[:out_det.numel()], non_blocking=True)
             out_masks.copy_(pasted[:out_masks.numel()], non_blocking=True)
+            if vis is not None:
+                out_vis.copy_(vis, non_blocking=True)
             state["out_done"] = torch.cuda.Event()
             state["out_done"].record(s_out)
 
@@ -555,9 +578,11 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
     return {"value": world * B * args.e2e_steps / (ms * 1e-3), "unit": "frames/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
             "ms_per_step": ms / args.e2e_steps,
-            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize; pinned host inputs (heads, FPN "
-                    "maps, mask-head output, semantic map) in, int32 detections + [B,M',11] summary out "
-                    "every step; the [B,M,PH,PW] masks are never written" if summary else
+            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw" if h_img is not None else "")
+                    + "; pinned host inputs (heads, FPN maps, mask-head output, semantic map"
+                    + (", frames" if h_img is not None else "") + ") in, int32 detections + [B,M',11] summary"
+                    + (" + uint8 overlay image" if h_img is not None else "") + " out every step; the [B,M,PH,PW] "
+                    "masks are never written" if summary else
                     "PostProcessPipeline.detect_and_align + trim_and_paste; pinned host inputs in, "
                     "int32 detections + " + ("bit-packed (1 bit/pixel)" if bits else "uint8") +
                     " masks out to pinned host memory every step")}

@@ -1,2 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_draw.py -x -q > gpurun_out/pytest_draw.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_draw.log
-tail -30 gpurun_out/pytest_draw.log
+timeout 900 python bench.py --no-cpu-baseline --steps 50 > gpurun_out/bench_serv.json 2> gpurun_out/bench_serv.err; echo "rc=$?"; tail -3 gpurun_out/bench_serv.err

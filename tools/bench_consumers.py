@@ -1,0 +1,57 @@
+"""Times the two consumers of the pasted masks on cfg-2 both ways: drop-in layers reading the
+materialised [B,M,PH,PW] masks (uint8 and float32) vs the tile path that never writes them."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import synth
+import bench
+import masklab_b200 as ml
+from masklab_b200.layers import summary as ls
+
+
+def timeit(fn, n=20):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+wl = bench.WORKLOADS["cfg2"]
+B, C, PH, PW = wl["B"], wl["C"], wl["PH"], wl["PW"]
+cfgp, N, loc, cls, fmaps = bench.make_inputs(wl, B, seed=100)
+d = lambda a: torch.from_numpy(a).cuda()
+d_loc, d_cls, d_fm = d(loc), d(cls), [d(f) for f in fmaps]
+seg = d(synth.semantic_map(B, PH, PW, seed=500))
+img = d(np.random.default_rng(600).integers(0, 256, (B, PH, PW, 3)).astype(np.uint8))
+out = {}
+for mode in ("uint8", "float32"):
+    cfg = ml.DetectionConfig(paste_output=mode, **bench.kwargs_of(wl))
+    pipe = ml.PostProcessPipeline(cfgp, (wl["H"], wl["W"]), (PH, PW), C, wl["Cf"], B, cfg)
+    r = pipe.detect_and_align(d_loc, d_cls, d_fm)
+    mf, R = r.shapes()
+    masks = d(synth.mask_probs(B, R, C, seed=300))
+    pipe.trim_and_paste(r, masks)
+    det_i, pasted = pipe.result_views()
+    det_i = det_i.contiguous()
+    out[f"paste_{mode}_ms"] = timeit(lambda: pipe.trim_and_paste(r, masks))
+    out[f"SummaryOutput_on_{mode}_masks_ms"] = timeit(lambda: ml.SummaryOutput()([det_i, seg, pasted]))
+    out[f"DrawInstance_on_{mode}_masks_ms"] = timeit(lambda: ml.DrawInstance(bench.INST_COLORS[:C])([img, det_i, pasted]))
+    if mode == "uint8":
+        out["tiles_trim_and_summarize_ms"] = timeit(lambda: pipe.trim_and_summarize(r, masks, seg))
+        out["tiles_draw_instance_and_semantic_ms"] = timeit(
+            lambda: pipe.draw(r, masks, img, bench.INST_COLORS[:C], 0.3, seg_outs=seg, semantic_colors=bench.SEM_COLORS))
+    del pipe, pasted
+    torch.cuda.empty_cache()
+out["DrawSegmentation_ms"] = timeit(lambda: ml.DrawSegmentation(bench.SEM_COLORS)([img, seg]))
+for k, v in out.items():
+    print(f"{k:48s} {v:8.3f}")
