@@ -16,9 +16,13 @@ Where, Unique, DynamicPartition) are restated from their published algorithms;
 the only reference code that executes here is engine/prior.py, whose outputs
 are committed as tests/golden/prior_tables.json (made by
 tests/golden/make_prior_golden.py).  Everything else is pinned by hand-derived
-known-answer tests and by cross-checks against independent implementations
-(torchvision.ops.nms, torch interpolate/grid_sample with align_corners=True)
-and by a second, independently written C restatement (oracle/c/).
+known-answer tests, by the known-answer vectors published with TensorFlow's
+own kernel unit tests (non_max_suppression_op_test, crop_and_resize_op_test,
+resize_bilinear_op_test; transcribed in tests/test_tf_published_vectors.py -
+the closest published fixtures of the third-party arithmetic), by cross-checks
+against independent implementations (torchvision.ops.nms, torch
+interpolate/grid_sample with align_corners=True) and by a second,
+independently written C restatement (oracle/c/).
 
 Two documented deviations from "whatever TF does", both fixed by
 BASELINE.json's north_star or forced by bit-reproducibility:

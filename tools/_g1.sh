@@ -1,1 +1,2 @@
-timeout 900 python bench.py --no-cpu-baseline --steps 50 > gpurun_out/bench_serv.json 2> gpurun_out/bench_serv.err; echo "rc=$?"; tail -3 gpurun_out/bench_serv.err
+timeout 900 python -m pytest tests/test_gpu_tf_published_vectors.py -x -q > gpurun_out/pytest_tfv.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_tfv.log
+tail -30 gpurun_out/pytest_tfv.log
