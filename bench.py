@@ -417,7 +417,7 @@ def run_ours(args, wl):
             r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
             pipe.trim_and_summarize(r_, d_masks, d_seg)
             pipe.draw(r_, d_masks, d_img, INST_COLORS[:C], 0.3, seg_outs=d_seg, semantic_colors=SEM_COLORS,
-                      semantic_alpha=0.3)
+                      semantic_alpha=0.3, boxes=True)
 
         pipe.ctx.profile(False)
         serve()
@@ -436,7 +436,7 @@ def run_ours(args, wl):
         ms_s = e0.elapsed_time(e1) / n_
         summary_leg = {
             "what": "decode+NMS+RoIAlign, then the two consumers of the masks in the serving graph - SummaryOutput "
-                    "and the DrawInstance+DrawSegmentation overlay - straight from the mask tiles "
+                    "and the DrawBoxes+DrawInstance+DrawSegmentation overlay - straight from the mask tiles "
                     "(trim_and_summarize + draw, no [B,M,PH,PW] tensor); single stream, inputs resident in HBM",
             "value": world * B / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
             "rows_per_image": Mo, "stage_ms": st_,
@@ -545,7 +545,7 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
                 det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])
                 if h_img is not None:
                     vis = pipe.draw(r, buf["masks"], buf["img"], INST_COLORS[:wl["C"]], 0.3, seg_outs=buf["seg"],
-                                    semantic_colors=SEM_COLORS, semantic_alpha=0.3)
+                                    semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
             else:
                 det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
             cmp_done = torch.cuda.Event()

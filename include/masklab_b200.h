@@ -344,6 +344,14 @@ int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* ma
  *   sources as for mlp_tile_summary (int32 tiles, or the fused tail after mlp_trim_paste); mask rows
  *   of at most 32 columns.  With seg_dev / sem_colors not NULL, DrawSegmentation over the result
  *   (serving.py:38-40) is applied in the same pass.                                             */
+/* mlp_draw_boxes: DrawBoxes.call (engine/layers/misc.py:481-503, serving.py:34): out_dev uint8
+ *   [B,PH,PW,3] = the frame (float32 frames clipped to [0,255] and truncated) with the one-pixel white
+ *   rectangle of tf.image.draw_bounding_boxes for every row of det_i32_dev [B,m_stride,6] (negative
+ *   coordinates clamped to 0 first, so padding rows mark the pixel at the origin like the reference).
+ *   images_dev == out_dev (uint8) draws in place.                                               */
+int mlp_draw_boxes(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev, int batch,
+                   int m_rows, int m_stride, const int32_t* m_dev, int frame_h, int frame_w, uint8_t* out_dev,
+                   mlp_stream_t stream);
 #define MLP_MAX_DRAW_CLASSES 16
 typedef struct {
     int32_t num_classes;

@@ -291,6 +291,50 @@ draw_tiles_kernel(const DrawTilesArgs A) {
     }
 }
 
+// ---- DrawBoxes --------------------------------------------------------------------------------
+// clip(float image, 0, 255) -> uint8 (the canvas before the rectangles; identity for uint8 frames)
+__global__ void __launch_bounds__(kDrawThreads)
+canvas_kernel(const float* __restrict__ images, int64_t n, uint8_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kDrawThreads + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)__float2uint_rz(fminf(fmaxf(__ldg(images + i), 0.0f), 255.0f));
+}
+
+// One warp per box: DrawBoxes.call (misc.py:486-497) corner arithmetic, then the four one-pixel
+// lines of tf.image.draw_bounding_boxes (draw_bounding_box_op.cc, restated in oracle/draw_oracle.py).
+__global__ void __launch_bounds__(kDrawThreads)
+draw_boxes_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stride, const int32_t* __restrict__ m_dev,
+                  int H, int W, uint8_t* __restrict__ out) {
+    int M = m_dev ? *m_dev : m_rows;
+    if (M > m_rows) M = m_rows;
+    if (m_stride == 0) m_stride = M;
+    const int lane = threadIdx.x & 31;
+    const int64_t box = (int64_t)blockIdx.x * (kDrawThreads / 32) + (threadIdx.x >> 5);
+    if (box >= (int64_t)B * M) return;
+    const int b = (int)(box / M), j = (int)(box - (int64_t)b * M);
+    const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
+    const float cx = (float)max(row[0], 0), cy = (float)max(row[1], 0);       // tf.maximum(det[..., :4], 0)
+    const float w = (float)max(row[2], 0), h = (float)max(row[3], 0);
+    const float fh = (float)H, fw = (float)W;
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    const float xmin = __fdiv_rn(__fsub_rn(cx, hw), fw), xmax = __fdiv_rn(__fadd_rn(cx, hw), fw);
+    const float ymin = __fdiv_rn(__fsub_rn(cy, hh), fh), ymax = __fdiv_rn(__fadd_rn(cy, hh), fh);
+    // box * (size - 1), converted to an integer by C++ truncation (toward zero)
+    const int y0 = __float2int_rz(__fmul_rn(ymin, (float)(H - 1))), y1 = __float2int_rz(__fmul_rn(ymax, (float)(H - 1)));
+    const int x0 = __float2int_rz(__fmul_rn(xmin, (float)(W - 1))), x1 = __float2int_rz(__fmul_rn(xmax, (float)(W - 1)));
+    if (y0 > y1 || x0 > x1) return;
+    if (y0 >= H || y1 < 0 || x0 >= W || x1 < 0) return;
+    const int y0c = max(y0, 0), y1c = min(y1, H - 1), x0c = max(x0, 0), x1c = min(x1, W - 1);
+    uint8_t* img = out + (int64_t)b * H * W * 3;
+    for (int x = x0c + lane; x <= x1c; x += 32) {
+        if (y0 >= 0) { uint8_t* p = img + ((int64_t)y0 * W + x) * 3; p[0] = p[1] = p[2] = 255; }
+        if (y1 < H) { uint8_t* p = img + ((int64_t)y1 * W + x) * 3; p[0] = p[1] = p[2] = 255; }
+    }
+    for (int y = y0c + lane; y <= y1c; y += 32) {
+        if (x0 >= 0) { uint8_t* p = img + ((int64_t)y * W + x0) * 3; p[0] = p[1] = p[2] = 255; }
+        if (x1 < W) { uint8_t* p = img + ((int64_t)y * W + x1) * 3; p[0] = p[1] = p[2] = 255; }
+    }
+}
+
 int check_colors(const char* who, const mlp_draw_colors* c) {
     MLP_CHECK_ARG(c && c->num_classes >= 1 && c->num_classes <= MLP_MAX_DRAW_CLASSES,
                   "%s: colour table needs 1..%d classes", who, MLP_MAX_DRAW_CLASSES);
@@ -427,6 +471,34 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
     if (sem_colors) A.sem = *sem_colors;
     A.out = out_dev;
     draw_tiles_kernel<<<dim3((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch), kDrawThreads, 0, st>>>(A);
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
+
+extern "C" int mlp_draw_boxes(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                              int batch, int m_rows, int m_stride, const int32_t* m_dev, int frame_h, int frame_w,
+                              uint8_t* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && images_dev && det_i32_dev && out_dev, "mlp_draw_boxes: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && m_rows >= 1 && frame_h >= 1 && frame_w >= 1 &&
+                      (m_stride >= m_rows || (m_stride == 0 && m_dev)),
+                  "mlp_draw_boxes: bad shape");
+    MLP_CHECK_ARG(image_dtype == MLP_U8 || image_dtype == MLP_F32, "mlp_draw_boxes: images must be u8 or f32");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_DRAW, st);
+    const int64_t n = (int64_t)batch * frame_h * frame_w * 3;
+    if (image_dtype == MLP_U8) {
+        if (images_dev != out_dev)
+            MLP_CUDA(cudaMemcpyAsync(out_dev, images_dev, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    } else {
+        canvas_kernel<<<(int)((n + kDrawThreads - 1) / kDrawThreads), kDrawThreads, 0, st>>>(
+            static_cast<const float*>(images_dev), n, out_dev);
+        MLP_LAUNCH_CHECK(ctx);
+    }
+    const int64_t boxes = (int64_t)batch * m_rows;
+    const int wpc = kDrawThreads / 32;
+    draw_boxes_kernel<<<(int)((boxes + wpc - 1) / wpc), kDrawThreads, 0, st>>>(det_i32_dev, batch, m_rows, m_stride,
+                                                                            m_dev, frame_h, frame_w, out_dev);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }

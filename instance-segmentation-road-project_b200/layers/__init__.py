@@ -4,4 +4,4 @@ from .detection import PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionPropos
 from .instance import MaskDistribute, PyramidRoiAlign, TrimInstances          # noqa: F401
 from .misc import MoldBatch, UpSampleOutput, CropAndPadMask                   # noqa: F401
 from .summary import CrackToInstance, SummaryOutput, IncludeMyRoad, CalculateInstanceSize   # noqa: F401
-from .draw import DrawSegmentation, DrawInstance                              # noqa: F401
+from .draw import DrawBoxes, DrawSegmentation, DrawInstance                              # noqa: F401

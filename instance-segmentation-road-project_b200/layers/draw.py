@@ -29,6 +29,22 @@ def _seg(seg_outs, what):
 
 
 @register
+class DrawBoxes(Layer):
+    """[images [B,PH,PW,3], det_outs int32 [B,M,6]] -> uint8 [B,PH,PW,3]: the one-pixel white rectangle
+    of tf.image.draw_bounding_boxes for every detection row (misc.py:481-503)."""
+
+    def call(self, inputs, **kwargs):
+        ctx = ctx_of(inputs[1])
+        img, it = _image(ctx, inputs[0], "DrawBoxes")
+        det = inputs[1].to(torch.int32).contiguous()
+        B, PH, PW = (int(d) for d in img.shape[:3])
+        out = ctx.empty((B, PH, PW, 3), torch.uint8)
+        rt.check(ctx.lib.mlp_draw_boxes(ctx.handle, ctx.view(img), it, ctx.view(det), B, int(det.shape[1]),
+                                        int(det.shape[1]), null(), PH, PW, ctx.view(out), ctx.stream()))
+        return out
+
+
+@register
 class DrawSegmentation(Layer):
     """[images [B,PH,PW,3], seg_outs [B,PH,PW,C]] -> uint8 [B,PH,PW,3]: every class colour times its
     mask, summed, scaled by alpha, added to the image, clipped to [0,255] and truncated."""

@@ -271,11 +271,12 @@ class PostProcessPipeline:
         return self.det_i32, self.summary, self.summary_m
 
     def draw(self, rois, roi_masks, images, instance_colors, instance_alpha=.3, seg_outs=None,
-             semantic_colors=None, semantic_alpha=.3):
-        """SURVEY 8(f) rank 2 behind the tail: DrawInstance (+ DrawSegmentation when seg_outs is given)
-        of road_project/setup/serving.py:34-40 drawn straight from the mask tiles.  Needs the tail
-        prepared by trim_and_paste / trim_and_summarize of the same batch.  images: uint8 or float32
-        [B,PH,PW,3].  Returns uint8 [B,PH,PW,3]."""
+             semantic_colors=None, semantic_alpha=.3, boxes=False):
+        """SURVEY 8(f) rank 2 behind the tail: the visualisation branch of
+        road_project/setup/serving.py:34-40 - DrawBoxes (boxes=True), DrawInstance and, when seg_outs is
+        given, DrawSegmentation - drawn straight from the mask tiles.  Needs the tail prepared by
+        trim_and_paste / trim_and_summarize of the same batch.  images: uint8 or float32 [B,PH,PW,3].
+        Returns uint8 [B,PH,PW,3]."""
         c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
         if not self.cfg.fused:
             raise rt.InvalidArgumentError(rt.MLP_EINVAL, "draw needs the fused tail (fused=True)")
@@ -294,6 +295,13 @@ class PostProcessPipeline:
         if not hasattr(self, "vis"):
             self.vis = c.empty((B, PH, PW, 3), torch.uint8)
         r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
+        if boxes:
+            if not hasattr(self, "vis_boxes"):
+                self.vis_boxes = c.empty((B, PH, PW, 3), torch.uint8)
+            rt.check(lib.mlp_draw_boxes(
+                c.handle, c.view(images), rt.MLP_U8 if images.dtype == torch.uint8 else rt.MLP_F32,
+                c.view(self.det_i32), B, K, K, c.view(self.trim_m), PH, PW, c.view(self.vis_boxes), c.stream()))
+            images = self.vis_boxes
         rt.check(lib.mlp_draw_tiles(
             c.handle, c.view(images), rt.MLP_U8 if images.dtype == torch.uint8 else rt.MLP_F32,
             c.view(self.det_i32), ctypes.c_void_p(None), c.view(roi_masks, torch.float32), L * K, r_dev, self.C,

@@ -117,6 +117,7 @@ SIGNATURES = {
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
                               _F, _P, _P, _P, _P]),
+    "mlp_draw_boxes": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "mlp_draw_segmentation": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_draw_instance": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_draw_tiles": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I,

@@ -46,3 +46,50 @@ def draw_instance(images, det_outs, masks, colors, alpha=0.3):
     """misc.py:440-463: DrawSegmentation over the per-class instance masks."""
     cm = class_masks(det_outs, masks, len(colors))
     return draw_segmentation(images, cm, colors, alpha)
+
+
+def draw_bounding_boxes(images, boxes, color=(255.0, 255.0, 255.0, 255.0)):
+    """tf.image.draw_bounding_boxes with one colour (TensorFlow core/kernels/draw_bounding_box_op.cc,
+    restated): images float [B,H,W,D], boxes [B,n,4] normalised (ymin,xmin,ymax,xmax).  Corner
+    coordinates are box * (size - 1) converted to integers by C++ truncation (toward zero); boxes
+    with min > max or entirely outside are skipped; each of the four one-pixel lines is drawn
+    only if its own coordinate lies inside the image."""
+    out = np.array(images, dtype=F32, copy=True)
+    B, H, W, D = out.shape
+    boxes = np.asarray(boxes, dtype=F32)
+    col = np.asarray(color, dtype=F32)[:D]
+    for b in range(B):
+        for bb in range(boxes.shape[1]):
+            y0 = int(np.trunc(boxes[b, bb, 0] * F32(H - 1)))
+            x0 = int(np.trunc(boxes[b, bb, 1] * F32(W - 1)))
+            y1 = int(np.trunc(boxes[b, bb, 2] * F32(H - 1)))
+            x1 = int(np.trunc(boxes[b, bb, 3] * F32(W - 1)))
+            y0c, y1c, x0c, x1c = max(y0, 0), min(y1, H - 1), max(x0, 0), min(x1, W - 1)
+            if y0 > y1 or x0 > x1:
+                continue
+            if y0 >= H or y1 < 0 or x0 >= W or x1 < 0:
+                continue
+            if y0 >= 0:
+                out[b, y0, x0c:x1c + 1] = col
+            if y1 < H:
+                out[b, y1, x0c:x1c + 1] = col
+            if x0 >= 0:
+                out[b, y0c:y1c + 1, x0] = col
+            if x1 < W:
+                out[b, y0c:y1c + 1, x1] = col
+    return out
+
+
+def draw_boxes(images, det_outs):
+    """DrawBoxes.call, misc.py:481-503: boxes = max(det[..., :4], 0) as (cx,cy,w,h) -> normalised
+    corners -> white one-pixel rectangles on the float image, clipped to [0,255], uint8."""
+    images = np.asarray(images)
+    B, H, W, _ = images.shape
+    d = np.maximum(np.asarray(det_outs)[..., :4], 0).astype(F32)
+    cx, cy, w, h = d[..., 0], d[..., 1], d[..., 2], d[..., 3]
+    fh, fw = F32(H), F32(W)
+    xmin, xmax = (cx - w / F32(2)) / fw, (cx + w / F32(2)) / fw
+    ymin, ymax = (cy - h / F32(2)) / fh, (cy + h / F32(2)) / fh
+    bboxes = np.stack([ymin, xmin, ymax, xmax], axis=-1).astype(F32)
+    vis = draw_bounding_boxes(images.astype(F32), bboxes)
+    return np.clip(vis, F32(0), F32(255)).astype(np.uint8)

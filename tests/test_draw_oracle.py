@@ -40,3 +40,34 @@ def test_class_masks_sum_then_threshold():
     assert out[0, 0, 0].tolist() == [int(F32(100) + F32(160) * F32(0.3)), int(F32(100) + F32(96) * F32(0.3)), 100]
     assert out[0, 0, 2].tolist() == [int(F32(100) + F32(192) * F32(0.3)), int(F32(100) + F32(32) * F32(0.3)),
                                      int(F32(100) + F32(128) * F32(0.3))]
+
+
+def test_draw_boxes_known_answer():
+    img = np.full((1, 10, 12, 3), 7, dtype=np.uint8)
+    # cx=6, cy=5, w=4, h=6 -> x in [4,8]/12, y in [2,8]/10 -> rows trunc(.2*9)=1 .. trunc(.8*9)=7,
+    # cols trunc(4/12*11)=3 .. trunc(8/12*11)=7
+    det = np.array([[[6, 5, 4, 6, 1, 90], [-1, -1, -1, -1, -1, -100]]], dtype=np.int32)
+    out = do.draw_boxes(img, det)
+    want = img.copy()
+    want[0, 1, 3:8] = 255
+    want[0, 7, 3:8] = 255
+    want[0, 1:8, 3] = 255
+    want[0, 1:8, 7] = 255
+    want[0, 0, 0] = 255            # the padding row: max(-1, 0) = 0 -> a one-pixel box at the origin
+    assert np.array_equal(out, want)
+    # a corner in (-1, 0) pixels: C++ truncation toward zero makes it 0, so the top/left lines ARE drawn
+    det2 = np.array([[[1, 1, 3, 3, 0, 90]]], dtype=np.int32)
+    out2 = do.draw_boxes(img, det2)
+    want2 = img.copy()
+    want2[0, 0, 0:3] = 255
+    want2[0, 2, 0:3] = 255
+    want2[0, 0:3, 0] = 255
+    want2[0, 0:3, 2] = 255
+    assert np.array_equal(out2, want2)
+    # a corner beyond -1 pixel stays negative: its line is outside and not drawn
+    det3 = np.array([[[1, 1, 6, 6, 0, 90]]], dtype=np.int32)
+    out3 = do.draw_boxes(img, det3)
+    want3 = img.copy()
+    want3[0, 3, 0:4] = 255
+    want3[0, 0:4, 3] = 255
+    assert np.array_equal(out3, want3)

@@ -112,6 +112,13 @@ def test_pipeline_draw():
     got = pipe.draw(rois, dev(probs["m"]), dev(img), INST_COLORS[:C], 0.3, seg_outs=dev(seg),
                     semantic_colors=SEM_COLORS, semantic_alpha=0.3).cpu().numpy()
     assert np.array_equal(got, vis)
+    # the whole visualisation branch of serving.py:34-40: boxes, instances, semantic
+    vis_b = do.draw_boxes(img, want["det_i"])
+    vis_all = do.draw_segmentation(do.draw_instance(vis_b, want["det_i"], want["pasted"], INST_COLORS[:C], 0.3),
+                                   seg, SEM_COLORS, 0.3)
+    got_all = pipe.draw(rois, dev(probs["m"]), dev(img), INST_COLORS[:C], 0.3, seg_outs=dev(seg),
+                        semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True).cpu().numpy()
+    assert np.array_equal(got_all, vis_all)
     assert ml.DrawInstance(INST_COLORS).get_config()["alpha"] == 0.3
 
 
@@ -120,3 +127,22 @@ def test_draw_rejects_cpu_tensors():
     with pytest.raises(ml.InvalidArgumentError):
         ml.DrawSegmentation(SEM_COLORS)([torch.zeros((1, 4, 4, 3), dtype=torch.uint8),
                                          torch.zeros((1, 4, 4, 3), dtype=torch.int32)])
+
+
+@pytest.mark.parametrize("PH,PW,img_dtype", [(48, 80, "u8"), (37, 53, "f32"), (200, 333, "u8")])
+def test_draw_boxes(PH, PW, img_dtype):
+    import masklab_b200 as ml
+    B, M = 2, 9
+    img = frames(B, PH, PW, 11)
+    if img_dtype == "f32":
+        img = img.astype(np.float32) * np.float32(1.1) - np.float32(10.0)       # needs the clip
+    det = synth.int_detections(B, M, 5, PH, PW, seed=PH, pad_tail=2)
+    det[0, 0] = [1, 1, 3, 3, 0, 90]                     # corner in (-1, 0) px: truncation draws the line
+    det[0, 1] = [1, 1, 6, 6, 0, 90]                     # corner beyond -1 px: line outside
+    det[0, 2] = [PW, PH, 40, 40, 0, 90]                 # sticks out bottom/right
+    det[1, 0] = [PW // 2, PH // 2, 0, 0, 0, 90]         # zero-size box: a single pixel
+    det[1, 1] = [5 * PW, 5 * PH, 4, 4, 0, 90]           # entirely outside
+    want = do.draw_boxes(img, det)
+    got = ml.DrawBoxes()([dev(img), dev(det)]).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert (want == 255).sum() > (np.clip(img, 0, 255).astype(np.uint8) == 255).sum()

@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_tf_published_vectors.py -x -q > gpurun_out/pytest_tfv.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_tfv.log
-tail -30 gpurun_out/pytest_tfv.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_all.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_all.log
+tail -4 gpurun_out/pytest_all.log
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_default.err
+timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
