@@ -182,112 +182,173 @@ pack_tiles_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int 
 }
 
 constexpr int kBlkH = 16, kBlkW = 64;     // pixel block of a CTA: 16 rows x 16 threads x 4 pixels
-constexpr int kMaxCand = 1024;            // instances touching one block kept in shared memory
+constexpr int kMaxCand = 1024;            // instances touching one block kept in shared memory (indices)
+constexpr int kGeomCache = 32;            // ... of which the first ones with their geometry
 
 struct DrawTilesArgs {
     const void* images;
-    int image_is_f32;
     const DrawGeom* geom;      // [B, m_rows]
     const uint32_t* bits;      // [B, m_rows, mh]
     const int32_t* m_used;     // [1]
     const void* seg;           // [B, PH, PW, Cs] or NULL
-    int seg_is_f32;
     int B, m_rows, mh, mw, PH, PW;
     mlp_draw_colors inst, sem;
     uint8_t* out;
 };
 
+// 4 consecutive channel-interleaved pixels (12 values) of a frame row as float
+__device__ __forceinline__ void load_px12(const uint8_t* p, bool vec, int n, float* v) {
+    if (vec) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t u = __ldg(w + k);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[k * 4 + i] = (float)((u >> (8 * i)) & 0xffu);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = i < 3 * n ? (float)__ldg(p + i) : 0.0f;
+    }
+}
+__device__ __forceinline__ void load_px12(const float* p, bool vec, int n, float* v) {
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p) + k);
+            v[k * 4] = f.x; v[k * 4 + 1] = f.y; v[k * 4 + 2] = f.z; v[k * 4 + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = i < 3 * n ? __ldg(p + i) : 0.0f;
+    }
+}
+__device__ __forceinline__ float seg_f32(const int32_t* p) { return (float)__ldg(p); }
+__device__ __forceinline__ float seg_f32(const float* p) { return __ldg(p); }
+
+template <typename ImgT, typename SegT>
 __global__ void __launch_bounds__(kDrawThreads)
 draw_tiles_kernel(const DrawTilesArgs A) {
-    __shared__ unsigned short s_cand[kMaxCand];
-    __shared__ int s_n;
+    __shared__ unsigned short s_cand[kMaxCand];            // instances touching the block, instance order
+    __shared__ signed char s_cls[kMaxCand];
+    __shared__ DrawGeom s_geom[kGeomCache];
+    __shared__ int s_wcnt[kDrawThreads / 32];
     const int b = blockIdx.z;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = min(*A.m_used, A.m_rows);
     const int by0 = blockIdx.y * kBlkH, bx0 = blockIdx.x * kBlkW;
     const DrawGeom* G = A.geom + (int64_t)b * A.m_rows;
-    // instances whose clipped box touches this block, in instance order (one warp, ballot compaction)
-    if (tid < 32) {
-        int n = 0;
-        for (int j0 = 0; j0 < M; j0 += 32) {
-            const int j = j0 + lane;
-            bool hit = false;
-            if (j < M) {
-                const DrawGeom d = G[j];
-                hit = d.cls >= 0 && d.ymin < by0 + kBlkH && d.ymax > by0 && d.xmin < bx0 + kBlkW && d.xmax > bx0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int k = n + __popc(m & ((1u << lane) - 1u));
-            if (hit && k < kMaxCand) s_cand[k] = (unsigned short)j;
-            n += __popc(m);
+    const int C = A.inst.num_classes;
+    // instances whose clipped box touches this block, in instance order: 256 instances per round,
+    // one per thread, ordered compaction with warp ballots + a prefix over the 8 warp counts
+    int ncand = 0;
+    for (int base = 0; base < M; base += kDrawThreads) {
+        const int j = base + tid;
+        bool hit = false;
+        DrawGeom d;
+        if (j < M) {
+            d = G[j];
+            hit = d.cls >= 0 && d.ymin < by0 + kBlkH && d.ymax > by0 && d.xmin < bx0 + kBlkW && d.xmax > bx0;
         }
-        if (lane == 0) s_n = n;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kDrawThreads / 32; ++w) {
+            const int v = s_wcnt[w];
+            if (w < warp) pre += v;
+            tot += v;
+        }
+        const int k = ncand + pre + __popc(m & ((1u << lane) - 1u));
+        if (hit && k < kMaxCand) {
+            s_cand[k] = (unsigned short)j;
+            s_cls[k] = (signed char)d.cls;
+            if (k < kGeomCache) s_geom[k] = d;
+        }
+        ncand += tot;
+        __syncthreads();
     }
-    __syncthreads();
-    const int ncand = s_n;
     const int oy = by0 + (tid >> 4), ox = bx0 + (tid & 15) * 4;
     if (oy >= A.PH || ox >= A.PW) return;
     const int mh = A.mh, mw = A.mw;
-    const int C = A.inst.num_classes;
     float cs[4][3];
 #pragma unroll
     for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
-    for (int c = 0; c < C; ++c) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};               // reduce_sum of the class's masks, order j
-        // more candidates than the list holds: walk all instances instead (same order, same result)
-        const int nwalk = ncand <= kMaxCand ? ncand : M;
-        for (int i = 0; i < nwalk; ++i) {
-            const int j = ncand <= kMaxCand ? (int)s_cand[i] : i;
-            const DrawGeom d = G[j];
-            if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
-            // the float32 value CropAndPadMask writes at (oy, ox+q): two-stage lerp of the {0,1} tile
-            const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
-            const float fy = floorf(py);
-            const float ly = __fsub_rn(py, fy);
-            const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + j) * mh;
-            const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
+    if (ncand > 0) {
+        for (int c = 0; c < C; ++c) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};           // reduce_sum of the class's masks, order j
+            // list overflow: walk all instances of the image instead (same order, same result)
+            const bool all = ncand > kMaxCand;
+            const int i1 = all ? M : ncand;
+            for (int i = 0; i < i1; ++i) {
+                if (!all && s_cls[i] != c) continue;
+                const int j = all ? i : (int)s_cand[i];
+                const DrawGeom d = (!all && i < kGeomCache) ? s_geom[i] : G[j];
+                if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
+                // the float32 value CropAndPadMask writes at (oy, ox+q): two-stage lerp of the {0,1} tile
+                const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
+                const float fy = floorf(py);
+                const float ly = __fsub_rn(py, fy);
+                const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + j) * mh;
+                const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int x = ox + q;
-                if (x < d.xmin || x >= d.xmax) continue;
-                const float p = __fmul_rn((float)(x - d.xmin), d.sx);
-                const float fl = floorf(p);
-                const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
-                const float lx = __fsub_rn(p, fl);
-                const float tl = (float)((w0 >> xlo) & 1u), tr = (float)((w0 >> xhi) & 1u);
-                const float bl = (float)((w1 >> xlo) & 1u), br = (float)((w1 >> xhi) & 1u);
-                const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-                const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-                acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+                for (int q = 0; q < 4; ++q) {
+                    const int x = ox + q;
+                    if (x < d.xmin || x >= d.xmax) continue;
+                    const float p = __fmul_rn((float)(x - d.xmin), d.sx);
+                    const float fl = floorf(p);
+                    const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
+                    const float lx = __fsub_rn(p, fl);
+                    const float tl = (float)((w0 >> xlo) & 1u), tr = (float)((w0 >> xhi) & 1u);
+                    const float bl = (float)((w1 >> xlo) & 1u), br = (float)((w1 >> xhi) & 1u);
+                    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+                    const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+                    acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+                }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (acc[q] > 0.5f)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], A.inst.rgb[c][k]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (acc[q] > 0.5f)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], A.inst.rgb[c][k]);
     }
+    // ---- blend: DrawInstance's uint8, then (optionally) DrawSegmentation over it (serving.py:38-40)
     const int64_t pix0 = ((int64_t)b * A.PH + oy) * A.PW + ox;
     const int n = min(4, A.PW - ox);
-    for (int q = 0; q < n; ++q) {
-        const int64_t p = pix0 + q;
-        float sc[3] = {0.f, 0.f, 0.f};
-        if (A.seg) {                                       // DrawSegmentation over the result (serving.py:38-40)
-            for (int c = 0; c < A.sem.num_classes; ++c) {
-                const float v = A.seg_is_f32 ? px_f32(static_cast<const float*>(A.seg) + p * A.sem.num_classes + c)
-                                             : px_f32(static_cast<const int32_t*>(A.seg) + p * A.sem.num_classes + c);
+    const bool vec = n == 4 && (A.PW & 3) == 0;            // 4-pixel groups are 12-byte / 48-byte aligned
+    float img[12];
+    load_px12(static_cast<const ImgT*>(A.images) + pix0 * 3, vec, n, img);
+    float sc[4][3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) sc[k] = __fadd_rn(sc[k], __fmul_rn(A.sem.rgb[c][k], v));
+    for (int q = 0; q < 4; ++q) sc[q][0] = sc[q][1] = sc[q][2] = 0.0f;
+    if (A.seg) {
+        const int Cs = A.sem.num_classes;
+        const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * Cs;
+        for (int q = 0; q < n; ++q)
+            for (int c = 0; c < Cs; ++c) {
+                const float v = seg_f32(sp + q * Cs + c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[q][k] = __fadd_rn(sc[q][k], __fmul_rn(A.sem.rgb[c][k], v));
             }
-        }
+    }
+    uint32_t word[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float img = A.image_is_f32 ? px_f32(static_cast<const float*>(A.images) + p * 3 + k)
-                                             : px_f32(static_cast<const uint8_t*>(A.images) + p * 3 + k);
-            float v = (float)__float2uint_rz(blend(img, cs[q][k], A.inst.alpha));      // uint8 of DrawInstance
-            if (A.seg) v = (float)__float2uint_rz(blend(v, sc[k], A.sem.alpha));
-            A.out[p * 3 + k] = (uint8_t)v;
+            float v = (float)__float2uint_rz(blend(img[q * 3 + k], cs[q][k], A.inst.alpha));
+            if (A.seg) v = (float)__float2uint_rz(blend(v, sc[q][k], A.sem.alpha));
+            const int i = q * 3 + k;
+            word[i >> 2] |= __float2uint_rz(v) << (8 * (i & 3));
         }
+    uint8_t* op = A.out + pix0 * 3;
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) reinterpret_cast<uint32_t*>(op)[k] = word[k];
+    } else {
+        for (int i = 0; i < 3 * n; ++i) op[i] = (uint8_t)(word[i >> 2] >> (8 * (i & 3)));
     }
 }
 
@@ -465,12 +526,16 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
     MLP_LAUNCH_CHECK(ctx);
     DrawTilesArgs A;
     memset(&A, 0, sizeof(A));
-    A.images = images_dev; A.image_is_f32 = image_dtype == MLP_F32; A.geom = geom; A.bits = bits; A.m_used = m_used;
-    A.seg = seg_dev; A.seg_is_f32 = seg_dtype == MLP_F32; A.B = batch; A.m_rows = m_rows; A.mh = mask_h;
-    A.mw = mask_w; A.PH = frame_h; A.PW = frame_w; A.inst = *inst_colors;
+    A.images = images_dev; A.geom = geom; A.bits = bits; A.m_used = m_used; A.seg = seg_dev; A.B = batch;
+    A.m_rows = m_rows; A.mh = mask_h; A.mw = mask_w; A.PH = frame_h; A.PW = frame_w; A.inst = *inst_colors;
     if (sem_colors) A.sem = *sem_colors;
     A.out = out_dev;
-    draw_tiles_kernel<<<dim3((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch), kDrawThreads, 0, st>>>(A);
+    const dim3 grid((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch);
+    const bool seg_f = seg_dev && seg_dtype == MLP_F32;
+    if (image_dtype == MLP_U8 && !seg_f) draw_tiles_kernel<uint8_t, int32_t><<<grid, kDrawThreads, 0, st>>>(A);
+    else if (image_dtype == MLP_U8) draw_tiles_kernel<uint8_t, float><<<grid, kDrawThreads, 0, st>>>(A);
+    else if (!seg_f) draw_tiles_kernel<float, int32_t><<<grid, kDrawThreads, 0, st>>>(A);
+    else draw_tiles_kernel<float, float><<<grid, kDrawThreads, 0, st>>>(A);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }

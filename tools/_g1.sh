@@ -1,4 +1,3 @@
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_all.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_all.log
-tail -4 gpurun_out/pytest_all.log
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_default.err
-timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
+timeout 900 python -m pytest tests/test_gpu_draw.py -x -q > gpurun_out/pytest_draw.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_draw.log
+tail -12 gpurun_out/pytest_draw.log
+timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 30 > gpurun_out/bench_sum.json 2> gpurun_out/bench_sum.err; echo "cfg2 rc=$?"; tail -3 gpurun_out/bench_sum.err
