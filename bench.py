@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--no-summary", action="store_true",
                     help="skip the SummaryOutput legs (SURVEY 8(f) rank 1: the consumer of the masks)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="streaming job (BASELINE configs[4]): process this many frames in total, sharded by image "
+                         "over the ranks in batches of B, detections gathered at the end; overrides --steps "
+                         "(strong scaling)")
     return ap.parse_args()
 
 
@@ -221,6 +225,7 @@ def workload_config(args, wl):
     return {"workload": f"{args.workload}: B={wl['B']}/GPU {wl['W']}x{wl['H']} frames, C={wl['C']}, "
                         f"Cf={wl['Cf']}, max_out={wl['nms_max_output_size']}, paste {wl['PW']}x{wl['PH']} uint8",
             "batch_per_gpu": wl["B"], "parallelism": f"image-sharded x{args.gpus}",
+            "stream_frames": (args.frames or None),
             "l2_policy": "inputs (>=365 MB) and outputs (>=1.6 GB) per step exceed the 126 MB L2",
             "score_mu": wl["mu"]}
 
@@ -240,6 +245,12 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, C = wl["B"], wl["C"]
     H, W, PH, PW = wl["H"], wl["W"], wl["PH"], wl["PW"]
+    if args.frames:
+        # a stream of `frames` frames sharded by image: every rank owns frames/world of them and runs
+        # them in batches of B (masklab_b200.dist.shard_frames / chunks); one gather at the end
+        from masklab_b200 import dist as mdist
+        shard = mdist.shard_frames(args.frames, world, rank)
+        args.steps = max(1, len(mdist.chunks(shard.padded, B)))
     cfgp, N, loc, cls, fmaps = make_inputs(wl, B, seed=100 + rank)
     cfg = ml.DetectionConfig(paste_output="uint8", **kwargs_of(wl))
     pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local)
@@ -269,13 +280,23 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
 
     state = {"i": 0}
+    # streaming job: the detection records of every batch of the shard are kept for the final gather
+    stream_det = stream_cnt = None
+    if args.frames:
+        stream_det = torch.empty((args.steps * B, K, 6), dtype=torch.float32, device="cuda")
+        stream_cnt = torch.empty((args.steps * B,), dtype=torch.int32, device="cuda")
 
     def step():
-        k = state["i"] % S
+        i = state["i"]
+        k = i % S
         state["i"] += 1
         with torch.cuda.stream(streams[k]):
             r = pipes[k].detect_and_align(d_loc, d_cls, d_fmaps)
             pipes[k].trim_and_paste(r, d_masks)
+            if stream_det is not None:
+                s0 = (i % args.steps) * B
+                stream_det[s0:s0 + B].copy_(pipes[k].det, non_blocking=True)
+                stream_cnt[s0:s0 + B].copy_(pipes[k].counts, non_blocking=True)
 
     def join_streams():
         for s_ in streams:
@@ -286,9 +307,10 @@ def run_ours(args, wl):
             s_.wait_stream(torch.cuda.current_stream())
 
     gathered = None
+    g_det, g_cnt = (stream_det, stream_cnt) if args.frames else (pipe.det, pipe.counts)
     if world > 1:
-        gathered = [torch.empty_like(pipe.det) for _ in range(world)]
-        gathered_counts = [torch.empty_like(pipe.counts) for _ in range(world)]
+        gathered = [torch.empty_like(g_det) for _ in range(world)]
+        gathered_counts = [torch.empty_like(g_cnt) for _ in range(world)]
 
     def barrier():
         if world > 1:
@@ -312,8 +334,8 @@ def run_ours(args, wl):
             step()
         join_streams()
         if world > 1:           # the one collective of the path: gather detections at the end
-            dist.all_gather(gathered, pipe.det)
-            dist.all_gather(gathered_counts, pipe.counts)
+            dist.all_gather(gathered, g_det)
+            dist.all_gather(gathered_counts, g_cnt)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -459,7 +481,8 @@ def run_ours(args, wl):
         line = {
             "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.frames else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "e2e_bitpacked": e2e_bits, "serving_tail": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
