@@ -5,7 +5,7 @@ layers (engine/layers/{detection,instance,misc}.py, engine/prior.py) and of the
 TensorFlow kernels they delegate to.  It exists to CHECK the CUDA path; it is
 never the thing shipped or measured.  Only `tests/`, `__graft_entry__.smoke()`
 and the `cpu_baseline` / `--impl reference` legs of `bench.py` may import it.
-The product package must never import from here (tests/test_layout.py greps
+The product package must never import from here (tests/test_abi.py::test_product_never_imports_oracle greps
 for that).
 
 PARITY UNPINNED.  The reference holds no tests, golden vectors or fixtures for
