@@ -67,7 +67,7 @@ int64_t     mlp_ctx_launch_count(const mlp_ctx* ctx);
  * When enabled, every stage function brackets its kernels with a pair of CUDA events on
  * the launching stream (no extra synchronisation).  mlp_ctx_profile_read [syncs] sums
  * the elapsed milliseconds and the number of bracketed calls per stage.               */
-#define MLP_NUM_STAGES 16
+#define MLP_NUM_STAGES 24
 const char* mlp_stage_name(int stage);
 int mlp_ctx_profile_enable(mlp_ctx* ctx, int enable);
 int mlp_ctx_profile_read(mlp_ctx* ctx, double* ms_out /*[MLP_NUM_STAGES]*/,
@@ -329,6 +329,14 @@ int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* ma
                      const int32_t* crack_box_dev, int frame_h, int frame_w,
                      float include_threshold, float* out_dev, int32_t* m_out_dev, int32_t* m_dev_out,
                      mlp_stream_t stream);
+
+/* ---- SURVEY 8(f) rank 3 (resize part): the bilinear resizes either side of the path -----------
+ * tf.compat.v1.image.resize_bilinear(align_corners=True) of DownSampleInput.call
+ * (engine/layers/misc.py:143-154) and of the semantic half of UpSampleOutput.call (:190-195).
+ * in_dev [B,in_h,in_w,S] (MLP_F32, MLP_U8 or MLP_I32, cast to float32) -> out_dev [B,out_h,out_w,S]:
+ * float32 values (threshold = 0) or int32 (value > 0.5) (threshold = 1, misc.py:194).            */
+int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
+                        int channels, int out_h, int out_w, int threshold, void* out_dev, mlp_stream_t stream);
 
 /* ---- the overlay layers of the serving graph ------------------------------
  * DrawSegmentation.call (engine/layers/misc.py:412-421) and DrawInstance.call (:440-463), wired in

@@ -4,7 +4,7 @@
 # Keras layer interface over the C ABI in include/masklab_b200.h.
 from .prior import PriorBoxes                                    # noqa: F401
 from .layers import (PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal,   # noqa: F401
-                     MoldBatch, MaskDistribute, PyramidRoiAlign, TrimInstances,
+                     DownSampleInput, MoldBatch, MaskDistribute, PyramidRoiAlign, TrimInstances,
                      UpSampleOutput, CropAndPadMask, CrackToInstance, SummaryOutput, IncludeMyRoad,
                      CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, get_custom_objects)
 from .pipeline import PostProcessPipeline, DetectionConfig      # noqa: F401

@@ -35,7 +35,7 @@ struct mlp_ctx {
 enum {
     MLP_ST_THRESHOLD = 0, MLP_ST_NMS_CLASS, MLP_ST_NMS_CROSS, MLP_ST_DISTRIBUTE, MLP_ST_ROI_PLAN,
     MLP_ST_ROI_ALIGN, MLP_ST_TRIM, MLP_ST_UPSAMPLE, MLP_ST_PASTE_THR, MLP_ST_PASTE, MLP_ST_ELEMENTWISE,
-    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW
+    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW, MLP_ST_RESIZE
 };
 
 // RAII: records a start event now and a stop event when it goes out of scope.

@@ -1,0 +1,157 @@
+// resize.cu — the bilinear resizes either side of the path (resize part):
+// DownSampleInput (/root/reference/engine/layers/misc.py:133-161) and the semantic half of
+// UpSampleOutput (:190-195: resize to the frame, > 0.5, int32).  Both are
+// tf.compat.v1.image.resize_bilinear(align_corners=True) - the legacy ResizeBilinear kernel
+// (resize_bilinear_op.cc + image_resizer_state.h, half_pixel_centers = false), restated in
+// oracle/tf_ops.py / oracle/semantic_oracle.py: scale = (in-1)/(out-1) (in/out when out == 1),
+// source coordinate = index * scale, lower = floor, upper = min(ceil, in-1), two-stage lerp
+// top/bottom in x then in y, every float32 operation rounded separately (-fmad=false).
+//
+// One thread per output pixel, all channels (NHWC: the channels of a pixel are contiguous, the four
+// source pixels are read as contiguous channel runs).  Up-sampling is write-bound (int32/f32 out),
+// down-sampling read-bound; there is no reuse worth staging - neighbouring threads hit the same
+// source lines in L1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kResizeThreads = 256;
+
+__device__ __forceinline__ float src_f32(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float src_f32(const uint8_t* p) { return (float)__ldg(p); }
+__device__ __forceinline__ float src_f32(const int32_t* p) { return (float)__ldg(p); }
+
+template <typename InT, bool kThreshold>
+__global__ void __launch_bounds__(kResizeThreads)
+resize_bilinear_kernel(const InT* __restrict__ in, int B, int ih, int iw, int S, int oh, int ow, float sy, float sx,
+                       void* __restrict__ out) {
+    const int64_t npix = (int64_t)B * oh * ow;
+    for (int64_t p = (int64_t)blockIdx.x * kResizeThreads + threadIdx.x; p < npix;
+         p += (int64_t)gridDim.x * kResizeThreads) {
+        const int x = (int)(p % ow);
+        const int64_t t = p / ow;
+        const int y = (int)(t % oh), b = (int)(t / oh);
+        const float py = __fmul_rn((float)y, sy), px = __fmul_rn((float)x, sx);
+        const float fy = floorf(py), fx = floorf(px);
+        const int ylo = max((int)fy, 0), yhi = min((int)ceilf(py), ih - 1);
+        const int xlo = max((int)fx, 0), xhi = min((int)ceilf(px), iw - 1);
+        const float ly = __fsub_rn(py, fy), lx = __fsub_rn(px, fx);
+        const InT* img = in + (int64_t)b * ih * iw * S;
+        const InT* tl = img + ((int64_t)ylo * iw + xlo) * S;
+        const InT* tr = img + ((int64_t)ylo * iw + xhi) * S;
+        const InT* bl = img + ((int64_t)yhi * iw + xlo) * S;
+        const InT* br = img + ((int64_t)yhi * iw + xhi) * S;
+        for (int c = 0; c < S; ++c) {
+            const float a = src_f32(tl + c), bq = src_f32(tr + c), cq = src_f32(bl + c), d = src_f32(br + c);
+            const float top = __fadd_rn(a, __fmul_rn(__fsub_rn(bq, a), lx));
+            const float bot = __fadd_rn(cq, __fmul_rn(__fsub_rn(d, cq), lx));
+            const float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+            if (kThreshold) static_cast<int32_t*>(out)[p * S + c] = v > 0.5f ? 1 : 0;
+            else static_cast<float*>(out)[p * S + c] = v;
+        }
+    }
+}
+
+// Four consecutive output pixels of a row per thread (out_w % 4 == 0, S <= 4): the y terms are
+// shared, the 4*S results leave as S 128-bit streaming stores.
+template <typename InT, bool kThreshold, int S>
+__global__ void __launch_bounds__(kResizeThreads)
+resize_bilinear4_kernel(const InT* __restrict__ in, int B, int ih, int iw, int oh, int ow, float sy, float sx,
+                        void* __restrict__ out) {
+    const int owq = ow >> 2;
+    const int64_t nq = (int64_t)B * oh * owq;
+    for (int64_t i = (int64_t)blockIdx.x * kResizeThreads + threadIdx.x; i < nq;
+         i += (int64_t)gridDim.x * kResizeThreads) {
+        const int xq = (int)(i % owq);
+        const int64_t t = i / owq;
+        const int y = (int)(t % oh), b = (int)(t / oh);
+        const float py = __fmul_rn((float)y, sy);
+        const float fy = floorf(py);
+        const int ylo = max((int)fy, 0), yhi = min((int)ceilf(py), ih - 1);
+        const float ly = __fsub_rn(py, fy);
+        const InT* r0 = in + ((int64_t)b * ih + ylo) * iw * S;
+        const InT* r1 = in + ((int64_t)b * ih + yhi) * iw * S;
+        float v[4 * S];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float px = __fmul_rn((float)(xq * 4 + q), sx);
+            const float fx = floorf(px);
+            const int xlo = max((int)fx, 0), xhi = min((int)ceilf(px), iw - 1);
+            const float lx = __fsub_rn(px, fx);
+#pragma unroll
+            for (int c = 0; c < S; ++c) {
+                const float a = src_f32(r0 + xlo * S + c), bq = src_f32(r0 + xhi * S + c);
+                const float cq = src_f32(r1 + xlo * S + c), d = src_f32(r1 + xhi * S + c);
+                const float top = __fadd_rn(a, __fmul_rn(__fsub_rn(bq, a), lx));
+                const float bot = __fadd_rn(cq, __fmul_rn(__fsub_rn(d, cq), lx));
+                v[q * S + c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+            }
+        }
+        uint4* o = reinterpret_cast<uint4*>(out) + i * S;       // 4*S values = S x 16 bytes
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                w[e] = kThreshold ? (v[k * 4 + e] > 0.5f ? 1u : 0u) : __float_as_uint(v[k * 4 + e]);
+            stg_stream_u4(o + k, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+    }
+}
+
+template <typename InT, bool kThreshold>
+void launch_resize4(int S, int grid, cudaStream_t st, const void* in, int B, int ih, int iw, int oh, int ow, float sy,
+                    float sx, void* out) {
+    const InT* p = static_cast<const InT*>(in);
+    if (S == 1) resize_bilinear4_kernel<InT, kThreshold, 1><<<grid, kResizeThreads, 0, st>>>(p, B, ih, iw, oh, ow, sy, sx, out);
+    else if (S == 2) resize_bilinear4_kernel<InT, kThreshold, 2><<<grid, kResizeThreads, 0, st>>>(p, B, ih, iw, oh, ow, sy, sx, out);
+    else if (S == 3) resize_bilinear4_kernel<InT, kThreshold, 3><<<grid, kResizeThreads, 0, st>>>(p, B, ih, iw, oh, ow, sy, sx, out);
+    else resize_bilinear4_kernel<InT, kThreshold, 4><<<grid, kResizeThreads, 0, st>>>(p, B, ih, iw, oh, ow, sy, sx, out);
+}
+
+}  // namespace
+
+extern "C" int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
+                                   int channels, int out_h, int out_w, int threshold, void* out_dev,
+                                   mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && in_dev && out_dev, "mlp_resize_bilinear: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && in_h >= 1 && in_w >= 1 && channels >= 1, "mlp_resize_bilinear: bad input shape");
+    MLP_CHECK_ARG(out_h >= 1 && out_w >= 1, "mlp_resize_bilinear: output dimensions must be positive (%dx%d)", out_h,
+                  out_w);
+    MLP_CHECK_ARG(in_dtype == MLP_F32 || in_dtype == MLP_U8 || in_dtype == MLP_I32,
+                  "mlp_resize_bilinear: input must be f32, u8 or i32");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_RESIZE, st);
+    // CalculateResizeScale(in, out, align_corners = true)
+    const float sy = out_h > 1 ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
+    const float sx = out_w > 1 ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
+    const int64_t npix = (int64_t)batch * out_h * out_w;
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (channels <= 4 && (out_w & 3) == 0 && mlp_aligned16(out_dev)) {
+        const int64_t blocks4 = (npix / 4 + kResizeThreads - 1) / kResizeThreads;
+        const int grid4 = (int)(blocks4 < cap ? (blocks4 < 1 ? 1 : blocks4) : cap);
+#define MLP_RESIZE4(T)                                                                                              \
+    do {                                                                                                            \
+        if (threshold) launch_resize4<T, true>(channels, grid4, st, in_dev, batch, in_h, in_w, out_h, out_w, sy, sx, out_dev); \
+        else launch_resize4<T, false>(channels, grid4, st, in_dev, batch, in_h, in_w, out_h, out_w, sy, sx, out_dev);          \
+    } while (0)
+        if (in_dtype == MLP_F32) MLP_RESIZE4(float);
+        else if (in_dtype == MLP_U8) MLP_RESIZE4(uint8_t);
+        else MLP_RESIZE4(int32_t);
+#undef MLP_RESIZE4
+        MLP_LAUNCH_CHECK(ctx);
+        return MLP_OK;
+    }
+    int64_t blocks = (npix + kResizeThreads - 1) / kResizeThreads;
+    const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+#define MLP_RESIZE(T, THR)                                                                                   \
+    resize_bilinear_kernel<T, THR><<<grid, kResizeThreads, 0, st>>>(static_cast<const T*>(in_dev), batch, in_h, \
+                                                                    in_w, channels, out_h, out_w, sy, sx, out_dev)
+    if (in_dtype == MLP_F32) { if (threshold) MLP_RESIZE(float, true); else MLP_RESIZE(float, false); }
+    else if (in_dtype == MLP_U8) { if (threshold) MLP_RESIZE(uint8_t, true); else MLP_RESIZE(uint8_t, false); }
+    else { if (threshold) MLP_RESIZE(int32_t, true); else MLP_RESIZE(int32_t, false); }
+#undef MLP_RESIZE
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}

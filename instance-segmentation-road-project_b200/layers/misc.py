@@ -1,5 +1,5 @@
 """Misc layers of the hot path — mirror of /root/reference/engine/layers/misc.py:
-MoldBatch (:213-293), UpSampleOutput (:164-196, instance part), CropAndPadMask (:354-401).
+DownSampleInput (:133-161), MoldBatch (:213-293), UpSampleOutput (:164-196), CropAndPadMask (:354-401).
 """
 import torch
 
@@ -53,15 +53,69 @@ class MoldBatch(Layer):
         return config
 
 
+def resize_bilinear(ctx, x, out_h, out_w, threshold=False):
+    """tf.compat.v1.image.resize_bilinear(x, (out_h, out_w), align_corners=True) on a CUDA NHWC tensor;
+    threshold=True returns int32 (value > 0.5)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise rt.InvalidArgumentError(rt.MLP_EDLPACK, "resize_bilinear: expected a CUDA tensor (no CPU path)")
+    if x.dim() != 4:
+        raise rt.InvalidArgumentError(rt.MLP_EINVAL, "resize_bilinear: expected [B,h,w,S]")
+    if x.dtype not in (torch.float32, torch.uint8, torch.int32):
+        x = x.to(torch.float32)
+    x = x.contiguous()
+    code = {torch.float32: rt.MLP_F32, torch.uint8: rt.MLP_U8, torch.int32: rt.MLP_I32}[x.dtype]
+    B, h, w, S = (int(d) for d in x.shape)
+    out = ctx.empty((B, int(out_h), int(out_w), S), torch.int32 if threshold else torch.float32)
+    rt.check(ctx.lib.mlp_resize_bilinear(ctx.handle, ctx.view(x), code, B, h, w, S, int(out_h), int(out_w),
+                                         1 if threshold else 0, ctx.view(out), ctx.stream()))
+    return out
+
+
+@register
+class DownSampleInput(Layer):
+    """frames [B,H,W,C] -> float32 [B,th,tw,C]: resized with the smaller of the two ratios to
+    target_size (aspect kept; the output size is truncated to int), bilinear, align_corners=True."""
+
+    def __init__(self, target_size=(540, 960), **kwargs):
+        self.target_size = target_size
+        super().__init__(**kwargs)
+
+    def call(self, inputs, **kwargs):
+        ctx = ctx_of(inputs)
+        ih, iw = int(inputs.shape[1]), int(inputs.shape[2])
+        f32 = torch.float32
+        ratio = torch.minimum(torch.tensor(float(self.target_size[0]), dtype=f32) / torch.tensor(float(ih), dtype=f32),
+                              torch.tensor(float(self.target_size[1]), dtype=f32) / torch.tensor(float(iw), dtype=f32))
+        th = int((ratio * torch.tensor(float(ih), dtype=f32)).to(torch.int32))      # tf.cast(.., tf.int32)
+        tw = int((ratio * torch.tensor(float(iw), dtype=f32)).to(torch.int32))
+        return resize_bilinear(ctx, inputs, th, tw)
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"target_size": self.target_size})
+        return config
+
+
 @register
 class UpSampleOutput(Layer):
     """[roi_box [B,M,6] f32, roi_mask [B,M,mh,mw] f32, semantic [B,hs,ws,S]], target=frames
-    -> (int32 boxes, int32 {0,1} masks, semantic).
+    -> (int32 boxes, int32 {0,1} masks, int32 {0,1} semantic [B,PH,PW,S]).
 
     Boxes are scaled to the target frame with the reference's (swapped) ratios
     (misc.py:180-183: cx,w by PH/hs and cy,h by PW/ws) and truncated to int32; masks are
-    thresholded at 0.5.  The semantic branch (resize + threshold, misc.py:190-195) is outside
-    this path: the semantic tensor is only read for its shape and returned unchanged."""
+    thresholded at 0.5; the semantic map is resized to the target frame (bilinear,
+    align_corners=True) and thresholded at 0.5 (misc.py:190-195).  `semantic` may also be a shape
+    tuple (hs, ws) when that branch is handled elsewhere - it is then returned unchanged, as it is
+    with semantic=False."""
+
+    def __init__(self, semantic=True, **kwargs):
+        self.semantic = semantic
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"semantic": self.semantic})
+        return config
 
     def call(self, inputs, **kwargs):
         target = kwargs.get("target")
@@ -79,6 +133,8 @@ class UpSampleOutput(Layer):
         rt.check(ctx.lib.mlp_upsample_output(
             ctx.handle, ctx.view(box), box.numel() // 6, float(ratio[0]), float(ratio[1]),
             ctx.view(box_i), ctx.view(mask), mask.numel(), ctx.view(mask_i), ctx.stream()))
+        if self.semantic and isinstance(semantic, torch.Tensor) and semantic.is_cuda:
+            semantic = resize_bilinear(ctx, semantic, int(dst_h), int(dst_w), threshold=True)
         return box_i, mask_i, semantic
 
 

@@ -48,6 +48,7 @@ class DetectionParamsC(ctypes.Structure):
 
 
 MLP_MAX_DRAW_CLASSES = 16
+MLP_NUM_STAGES = 24
 
 
 class DrawColorsC(ctypes.Structure):
@@ -117,6 +118,7 @@ SIGNATURES = {
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
                               _F, _P, _P, _P, _P]),
+    "mlp_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mlp_draw_boxes": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "mlp_draw_segmentation": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_draw_instance": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
@@ -231,11 +233,11 @@ class Context:
 
     def profile_read(self):
         """{stage name: (total ms, bracketed calls)} since profile(True); synchronises."""
-        ms = (ctypes.c_double * 16)()
-        cnt = (ctypes.c_int64 * 16)()
+        ms = (ctypes.c_double * MLP_NUM_STAGES)()
+        cnt = (ctypes.c_int64 * MLP_NUM_STAGES)()
         check(self.lib.mlp_ctx_profile_read(self.handle, ms, cnt))
         out = {}
-        for i in range(16):
+        for i in range(MLP_NUM_STAGES):
             name = self.lib.mlp_stage_name(i).decode()
             if name and cnt[i]:
                 out[name] = (float(ms[i]), int(cnt[i]))

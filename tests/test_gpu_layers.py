@@ -283,10 +283,37 @@ def test_upsample_output_exact(ml):
     for dst in ((1080, 1920), (540, 960), (720, 1000)):
         target = torch.zeros((2, dst[0], dst[1], 3), device="cuda")
         want_b, want_m = mo.upsample_output(det, masks, (540, 960), dst)
-        got_b, got_m, sem_out = ml.UpSampleOutput()([dev(det), dev(masks), sem], target=target)
+        got_b, got_m, sem_out = ml.UpSampleOutput(semantic=False)([dev(det), dev(masks), sem], target=target)
         assert got_b.dtype == torch.int32 and got_m.dtype == torch.int32
         assert np.array_equal(host(got_b), want_b) and np.array_equal(host(got_m), want_m)
         assert sem_out is sem
+
+
+@pytest.mark.parametrize("src,dst", [((27, 48), (54, 96)), ((30, 41), (77, 53)), ((20, 32), (20, 32)), ((9, 7), (1, 1))])
+def test_upsample_output_semantic_half(ml, src, dst):
+    """misc.py:190-195: resize_bilinear(align_corners=True) to the frame, > 0.5, int32."""
+    from oracle import semantic_oracle as so
+    rng = np.random.default_rng(src[0])
+    sem = rng.random((2, src[0], src[1], 3)).astype(F32)
+    det = synth.detections(2, 4, 5, src[0], src[1], seed=1)
+    masks = synth.mask_probs(2, 4, 1, seed=2)[..., 0]
+    target = torch.zeros((2, dst[0], dst[1], 3), device="cuda")
+    _, _, got = ml.UpSampleOutput()([dev(det), dev(masks), dev(sem)], target=target)
+    assert got.dtype == torch.int32 and np.array_equal(host(got), so.upsample_semantic(sem, dst))
+
+
+@pytest.mark.parametrize("hw,target", [((108, 192), (54, 96)), ((100, 100), (54, 96)), ((50, 333), (54, 96))])
+def test_downsample_input(ml, hw, target):
+    """misc.py:143-154: min ratio, truncated size, bilinear align_corners=True, float32 out."""
+    from oracle import semantic_oracle as so
+    frames = np.random.default_rng(hw[1]).integers(0, 256, (2, hw[0], hw[1], 3)).astype(np.uint8)
+    want = so.downsample_input(frames, target)
+    got = ml.DownSampleInput(target)(dev(frames))
+    assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
+    assert np.array_equal(host(got), want)
+    got_f = ml.DownSampleInput(target)(dev(frames.astype(F32)))
+    assert np.array_equal(host(got_f), want)
+    assert ml.DownSampleInput(target).get_config()["target_size"] == target
 
 
 # ---------------------------------------------------------------- a13/a14 -----

@@ -52,6 +52,11 @@ for mode in ("uint8", "float32"):
             lambda: pipe.draw(r, masks, img, bench.INST_COLORS[:C], 0.3, seg_outs=seg, semantic_colors=bench.SEM_COLORS))
     del pipe, pasted
     torch.cuda.empty_cache()
+sem_lo = torch.rand((B, 540, 960, 3), device="cuda")
+frames_hi = torch.randint(0, 256, (B, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+out["UpSampleOutput_semantic_540x960_to_1080x1920_ms"] = timeit(
+    lambda: ml.layers.misc.resize_bilinear(ml.Context.get(), sem_lo, 1080, 1920, threshold=True))
+out["DownSampleInput_1080x1920_to_540x960_ms"] = timeit(lambda: ml.DownSampleInput((540, 960))(frames_hi))
 out["DrawSegmentation_ms"] = timeit(lambda: ml.DrawSegmentation(bench.SEM_COLORS)([img, seg]))
 for k, v in out.items():
     print(f"{k:48s} {v:8.3f}")
