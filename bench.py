@@ -598,9 +598,13 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    step_ms = ms / args.e2e_steps
     return {"value": world * B * args.e2e_steps / (ms * 1e-3), "unit": "frames/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-            "ms_per_step": ms / args.e2e_steps,
+            "ms_per_step": step_ms,
+            # both directions run concurrently (PCIe is full duplex): the busier one bounds the step
+            "pcie_gbs_busier_direction": max(h2d, d2h) / (step_ms * 1e-3) / 1e9,
+            "bound": "PCIe (host<->device copies of every step), not the kernels",
             "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw" if h_img is not None else "")
                     + "; pinned host inputs (heads, FPN maps, mask-head output, semantic map"
                     + (", frames" if h_img is not None else "") + ") in, int32 detections + [B,M',11] summary"

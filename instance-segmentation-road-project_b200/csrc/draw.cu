@@ -52,31 +52,15 @@ draw_segmentation_kernel(const ImgT* __restrict__ images, const SegT* __restrict
 }
 
 // ---- DrawInstance over the materialised masks -----------------------------------------------
-template <typename T> __device__ __forceinline__ void mask4(const T* p, bool vec, int n, float* v);
-template <> __device__ __forceinline__ void mask4<float>(const float* p, bool vec, int n, float* v) {
-    if (vec) {
-        const float4 f = ldg_stream_f4(reinterpret_cast<const float4*>(p));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = q < n ? __ldg(p + q) : 0.0f;
-    }
-}
-template <> __device__ __forceinline__ void mask4<uint8_t>(const uint8_t* p, bool vec, int n, float* v) {
-    if (vec) {
-        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
-        v[0] = (float)u.x; v[1] = (float)u.y; v[2] = (float)u.z; v[3] = (float)u.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = q < n ? (float)__ldg(p + q) : 0.0f;
-    }
-}
-
+// One thread per 16 bytes of the frame (4 float32 / 16 uint8 mask pixels, MaskVec in
+// paste_common.cuh): every mask of the image is read once with 128-bit loads.
 template <typename ImgT, typename MaskT>
 __global__ void __launch_bounds__(kDrawThreads)
 draw_instance_kernel(const ImgT* __restrict__ images, const int32_t* __restrict__ det, const MaskT* __restrict__ masks,
                      int m_rows, int m_stride, const int32_t* __restrict__ m_dev, int npx,
                      const mlp_draw_colors col, uint8_t* __restrict__ out) {
+    using Vec = MaskVec<MaskT>;
+    constexpr int kPx = Vec::kPx;
     __shared__ unsigned short s_list[kMaxDrawInst];        // instances grouped by class, order j inside
     __shared__ int s_beg[MLP_MAX_DRAW_CLASSES + 1];
     const int b = blockIdx.y;
@@ -100,44 +84,45 @@ draw_instance_kernel(const ImgT* __restrict__ images, const int32_t* __restrict_
         if (lane == 0) s_beg[C] = n;
     }
     __syncthreads();
-    const int p = (blockIdx.x * kDrawThreads + tid) * 4;   // four consecutive pixels of the frame
+    const int p = (blockIdx.x * kDrawThreads + tid) * kPx; // kPx consecutive pixels of the frame
     if (p >= npx) return;
-    const int n = min(4, npx - p);
-    const bool vec = n == 4 && (npx & 3) == 0;
+    const int n = min(kPx, npx - p);
+    const bool vec = n == kPx && (npx % kPx) == 0;         // every mask plane starts 16-byte aligned
     const MaskT* mb = masks + (int64_t)b * M * npx + p;
-    float cs[4][3];
+    float cs[kPx][3];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
+    for (int q = 0; q < kPx; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
     for (int c = 0; c < C; ++c) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};               // reduce_sum of the class's masks, order j
-        const int i1 = s_beg[c + 1];
-        int i = s_beg[c];
-        for (; i + 4 <= i1; i += 4) {                      // four mask loads in flight
-            float v[4][4];
+        float acc[kPx];                                    // reduce_sum of the class's masks, order j
 #pragma unroll
-            for (int u = 0; u < 4; ++u) mask4<MaskT>(mb + (int64_t)s_list[i + u] * npx, vec, n, v[u]);
+        for (int q = 0; q < kPx; ++q) acc[q] = 0.0f;
+        const int i1 = s_beg[c + 1];
+        for (int i = s_beg[c]; i < i1; i += 4) {           // four mask loads in flight
+            Vec v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const MaskT* src = mb + (int64_t)s_list[min(i + u, i1 - 1)] * npx;
+                if (vec) v[u].load(src); else v[u].load_tail(src, n);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
+                if (i + u < i1 && v[u].any())              // adding zeros is exact: skip them
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[q] = __fadd_rn(acc[q], v[u][q]);
-        }
-        for (; i < i1; ++i) {
-            float v[4];
-            mask4<MaskT>(mb + (int64_t)s_list[i] * npx, vec, n, v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = __fadd_rn(acc[q], v[q]);
+                    for (int q = 0; q < kPx; ++q) acc[q] = __fadd_rn(acc[q], v[u].at(q));
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < kPx; ++q)
             if (acc[q] > 0.5f)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], col.rgb[c][k]);
     }
     const int64_t o = ((int64_t)b * npx + p) * 3;
-    for (int q = 0; q < n; ++q)
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            out[o + q * 3 + k] = (uint8_t)__float2uint_rz(blend(px_f32(images + o + q * 3 + k), cs[q][k], col.alpha));
+    for (int q = 0; q < kPx; ++q)
+        if (q < n)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                out[o + q * 3 + k] = (uint8_t)__float2uint_rz(blend(px_f32(images + o + q * 3 + k), cs[q][k], col.alpha));
 }
 
 // ---- DrawInstance straight from the mask tiles ----------------------------------------------
@@ -449,7 +434,8 @@ extern "C" int mlp_draw_instance(mlp_ctx* ctx, const void* images_dev, int image
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_DRAW, st);
     const int npx = frame_h * frame_w;
-    const dim3 grid((npx + kDrawThreads * 4 - 1) / (kDrawThreads * 4), batch);
+    const int ppt = mask_dtype == MLP_U8 ? 16 : 4;          // pixels per thread: 16 bytes of mask
+    const dim3 grid((npx + kDrawThreads * ppt - 1) / (kDrawThreads * ppt), batch);
 #define MLP_DRAW_INST(IT, MT)                                                                               \
     draw_instance_kernel<IT, MT><<<grid, kDrawThreads, 0, st>>>(static_cast<const IT*>(images_dev), det_i32_dev, \
                                                                 static_cast<const MT*>(masks_dev), m_rows,   \

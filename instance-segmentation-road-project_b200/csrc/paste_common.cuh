@@ -159,6 +159,38 @@ paste_threshold_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m
     if (threadIdx.x == 0) *thr_out = (s_max > 50) ? 50 : -100;
 }
 
+// 16 bytes of one mask row (4 float32 / 16 uint8 pixels) as floats
+template <typename T> struct MaskVec;
+template <> struct MaskVec<float> {
+    static constexpr int kPx = 4;
+    uint4 raw;
+    __device__ __forceinline__ void load(const float* p) { raw = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void load_tail(const float* p, int n) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int q = 0; q < n; ++q) w[q] = __float_as_uint(__ldg(p + q));
+        raw = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ bool any() const { return ((raw.x | raw.y | raw.z | raw.w) & 0x7fffffffu) != 0u; }
+    __device__ __forceinline__ float at(int q) const {
+        return __uint_as_float(q == 0 ? raw.x : (q == 1 ? raw.y : (q == 2 ? raw.z : raw.w)));
+    }
+};
+template <> struct MaskVec<uint8_t> {
+    static constexpr int kPx = 16;
+    uint4 raw;
+    __device__ __forceinline__ void load(const uint8_t* p) { raw = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void load_tail(const uint8_t* p, int n) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int q = 0; q < n; ++q) w[q >> 2] |= (uint32_t)__ldg(p + q) << (8 * (q & 3));
+        raw = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ bool any() const { return (raw.x | raw.y | raw.z | raw.w) != 0u; }
+    __device__ __forceinline__ float at(int q) const {
+        const uint32_t w = (q >> 2) == 0 ? raw.x : ((q >> 2) == 1 ? raw.y : ((q >> 2) == 2 ? raw.z : raw.w));
+        return (float)((w >> (8 * (q & 3))) & 0xffu);
+    }
+};
+
 // Layout of the fused tail's scratch (MLP_ARENA_FUSED), written by tail_prep_kernel in
 // mlp_trim_paste: tail_src [B,K] + confmax [B] + bit tiles [B,K,mh] (mask rows of <= 32 columns).
 struct FusedTail {

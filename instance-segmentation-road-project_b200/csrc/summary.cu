@@ -264,31 +264,6 @@ __device__ __forceinline__ bool crack_row(const int32_t* crack_box, int32_t* row
     return row[5] > 0;
 }
 
-// four adjacent mask pixels x..x+3 of one frame row as float (vector load when the row is aligned)
-template <typename T>
-__device__ __forceinline__ void load4(const T* __restrict__ rowp, int x, int PW, bool aligned, float* v);
-template <>
-__device__ __forceinline__ void load4<float>(const float* __restrict__ rowp, int x, int PW, bool aligned, float* v) {
-    if (aligned && x + 3 < PW) {
-        const float4 f = ldg_stream_f4(reinterpret_cast<const float4*>(rowp + x));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (x + q < PW) ? __ldg(rowp + x + q) : 0.0f;
-    }
-}
-template <>
-__device__ __forceinline__ void load4<uint8_t>(const uint8_t* __restrict__ rowp, int x, int PW, bool aligned,
-                                               float* v) {
-    if (aligned && x + 3 < PW) {
-        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(rowp + x));
-        v[0] = (float)u.x; v[1] = (float)u.y; v[2] = (float)u.z; v[3] = (float)u.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (x + q < PW) ? (float)__ldg(rowp + x + q) : 0.0f;
-    }
-}
-
 // Block-wide reduction of the per-thread partial results; thread 0 returns with the totals.
 // Called by every thread of the CTA.
 __device__ __forceinline__ void block_totals(double& pix, double& size, double& vert, double& colmax, int& cnt,
@@ -309,7 +284,7 @@ __device__ __forceinline__ void block_totals(double& pix, double& size, double& 
     }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < kReduceThreads / 32; ++w) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
             pix = __dadd_rn(pix, s_d[w][0]); size = __dadd_rn(size, s_d[w][1]);
             vert = __dadd_rn(vert, s_d[w][2]); colmax = fmax(colmax, s_d[w][3]);
             cnt += s_i[w][0]; inter += s_i[w][1];
@@ -348,14 +323,20 @@ struct SummaryArgs {
     int32_t* m_out;            // [1] M'
 };
 
+constexpr int kRowsInFlight = 8;          // 16-byte row loads in flight per thread
+
+// One CTA per instance, one thread per 16-byte column group (4 float32 / 16 uint8 pixels), walking
+// all frame rows with kRowsInFlight independent loads in flight: a pure streaming read whose
+// arithmetic only runs on the (few) non-zero groups.  blockDim = min(256, groups per row).
 template <typename MaskT>
 __global__ void __launch_bounds__(kReduceThreads)
 instance_reduce_kernel(const SummaryArgs A) {
-    __shared__ float s_unit[kMaxFrameRows];
+    using Vec = MaskVec<MaskT>;
+    constexpr int kPx = Vec::kPx;
     __shared__ unsigned s_rowany[kMaxFrameRows / 32];
     __shared__ double s_d[kReduceThreads / 32][4];
     __shared__ int s_i[kReduceThreads / 32][2];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
     int M = A.m_dev ? *A.m_dev : A.m_rows;
     if (M > A.m_rows) M = A.m_rows;
     const int m_stride = A.m_stride ? A.m_stride : M;
@@ -365,54 +346,69 @@ instance_reduce_kernel(const SummaryArgs A) {
     if (blockIdx.x == 0 && tid == 0 && A.m_out) *A.m_out = Mo;
     const int PH = A.PH, PW = A.PW;
     const int words = (PW + 31) >> 5;
-    const bool aligned = (PW & 3) == 0;
+    const bool aligned = (PW % kPx) == 0;                   // every row starts 16-byte aligned
+    const int groups = (PW + kPx - 1) / kPx;
     const int64_t items = (int64_t)A.B * M;                 // the crack rows come from box_summary_kernel
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = (int)(item / M), j = (int)(item - (int64_t)b * M);
         __syncthreads();                                   // previous item done with shared memory
-        for (int y = tid; y < PH; y += kReduceThreads) s_unit[y] = A.unit[(int64_t)b * PH + y];
-        for (int i = tid; i < (PH + 31) / 32; i += kReduceThreads) s_rowany[i] = 0u;
+        for (int i = tid; i < (PH + 31) / 32; i += nthreads) s_rowany[i] = 0u;
         __syncthreads();
         const MaskT* mask = static_cast<const MaskT*>(A.masks) + ((int64_t)b * M + j) * PH * PW;
         const uint32_t* rbits = A.road_bits + (int64_t)b * PH * words;
+        const float* unit = A.unit + (int64_t)b * PH;
         double pix = 0.0, size = 0.0, colmax = 0.0;
         int cnt = 0, inter = 0;
-        for (int x0 = 0; x0 < PW; x0 += kReduceThreads * 4) {             // 1024-column tiles
-            const int x = x0 + tid * 4;                                   // this thread's 4 columns
-            const bool live = x < PW;
-            double col[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-            for (int y = 0; y < PH; ++y) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (live) load4<MaskT>(mask + (int64_t)y * PW, x, PW, aligned, v);
-                unsigned on = 0u;
-                if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) {   // frames are mostly zeros
-                    const float u = s_unit[y];
-                    const double du = (double)u, du2 = (double)__fmul_rn(u, u);      // unit ** 2 in float32
-                    const unsigned road = (__ldg(rbits + (int64_t)y * words + (x >> 5)) >> (x & 31)) & 0xFu;
-                    double rs = 0.0;
+        for (int g = tid; g < groups; g += nthreads) {
+            const int x = g * kPx;
+            const int n = min(kPx, PW - x);
+            const bool vec = aligned && n == kPx;
+            double col[kPx];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double dv = (double)v[q];
+            for (int q = 0; q < kPx; ++q) col[q] = 0.0;
+            for (int y0 = 0; y0 < PH; y0 += kRowsInFlight) {
+                Vec v[kRowsInFlight];
+#pragma unroll
+                for (int u = 0; u < kRowsInFlight; ++u) {
+                    const int y = min(y0 + u, PH - 1);
+                    if (vec) v[u].load(mask + (int64_t)y * PW + x);
+                    else v[u].load_tail(mask + (int64_t)y * PW + x, n);
+                }
+#pragma unroll
+                for (int u = 0; u < kRowsInFlight; ++u) {
+                    const int y = y0 + u;
+                    if (y >= PH || !v[u].any()) continue;                 // frames are mostly zeros
+                    const float un = __ldg(unit + y);
+                    const double du = (double)un;
+                    double rs = 0.0;
+                    unsigned on = 0u;
+#pragma unroll
+                    for (int q = 0; q < kPx; ++q) {
+                        const float f = v[u].at(q);
+                        const double dv = (double)f;
                         rs = __dadd_rn(rs, dv);
                         col[q] = __dadd_rn(col[q], __dmul_rn(du, dv));
-                        on |= (v[q] > 0.5f ? 1u : 0u) << q;
+                        on |= (f > 0.5f ? 1u : 0u) << q;
                     }
                     pix = __dadd_rn(pix, rs);
-                    size = __dadd_rn(size, __dmul_rn(du2, rs));
-                    cnt += __popc(on);
-                    inter += __popc(on & road);
+                    size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(un, un), rs));   // unit ** 2 in float32
+                    if (on) {
+                        atomicOr(&s_rowany[y >> 5], 1u << (y & 31));
+                        cnt += __popc(on);
+                        // my_road bits of pixels x .. x+kPx-1 (kPx divides 32: inside one word)
+                        const unsigned road = (__ldg(rbits + (int64_t)y * words + (x >> 5)) >> (x & 31)) &
+                                              (kPx == 16 ? 0xffffu : 0xfu);
+                        inter += __popc(on & road);
+                    }
                 }
-                const unsigned anyw = __ballot_sync(0xffffffffu, on != 0u);
-                if (lane == 0 && anyw) atomicOr(&s_rowany[y >> 5], 1u << (y & 31));
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) colmax = fmax(colmax, col[q]);
+            for (int q = 0; q < kPx; ++q) colmax = fmax(colmax, col[q]);
         }
         __syncthreads();                                   // row flags complete
         double vert = 0.0;
-        for (int y = tid; y < PH; y += kReduceThreads)
-            if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)s_unit[y]);
+        for (int y = tid; y < PH; y += nthreads)
+            if ((s_rowany[y >> 5] >> (y & 31)) & 1u) vert = __dadd_rn(vert, (double)__ldg(unit + y));
         finish_row(pix, size, vert, colmax, cnt, inter, s_d, s_i,
                    A.det + ((int64_t)b * m_stride + j) * 6, A.threshold, A.out + ((int64_t)b * Mo + j) * 11);
     }
@@ -722,8 +718,12 @@ extern "C" int mlp_summary_output(mlp_ctx* ctx, const int32_t* det_i32_dev, cons
     A.threshold = include_threshold; A.out = out_dev; A.m_out = m_out_dev;
     const int64_t items = (int64_t)batch * m_rows;
     const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-    if (mask_dtype == MLP_F32) instance_reduce_kernel<float><<<grid, kReduceThreads, 0, st>>>(A);
-    else instance_reduce_kernel<uint8_t><<<grid, kReduceThreads, 0, st>>>(A);
+    // one thread per 16-byte column group of a frame row
+    const int groups = mask_dtype == MLP_F32 ? (frame_w + 3) / 4 : (frame_w + 15) / 16;
+    int threads = ((groups + 31) / 32) * 32;
+    threads = threads < 32 ? 32 : (threads > kReduceThreads ? kReduceThreads : threads);
+    if (mask_dtype == MLP_F32) instance_reduce_kernel<float><<<grid, threads, 0, st>>>(A);
+    else instance_reduce_kernel<uint8_t><<<grid, threads, 0, st>>>(A);
     MLP_LAUNCH_CHECK(ctx);
     if (crack_box_dev) {                    // the crack pseudo-instance of every image, over the bitmaps
         BoxSummaryArgs X;
