@@ -110,7 +110,45 @@ def test_layer_configs_roundtrip_without_gpu():
               ml.MaskDistribute(3, 40), ml.PyramidRoiAlign((7, 7), 16), ml.TrimInstances(False, 4),
               ml.MoldBatch(12), ml.RestoreBoxes(), ml.NormalizeBoxes(), ml.UpSampleOutput(),
               ml.CropAndPadMask(output="uint8")]
+    # the consumers and the steps either side of the path
+    for name in ("DownSampleInput", "CrackToInstance", "SummaryOutput", "IncludeMyRoad", "CalculateInstanceSize",
+                 "DrawBoxes", "DrawSegmentation", "DrawInstance"):
+        assert name in objs
+    colors = [[192, 32, 128], [160, 96, 0]]
+    layers += [ml.DownSampleInput((270, 480)), ml.CrackToInstance(4), ml.SummaryOutput(2.5), ml.IncludeMyRoad(0.2),
+               ml.CalculateInstanceSize(3.0), ml.DrawBoxes(), ml.DrawSegmentation(colors, 0.4),
+               ml.DrawInstance(colors, 0.5), ml.UpSampleOutput(semantic=False)]
     for layer in layers:
         clone = type(layer).from_config(layer.get_config())
         assert clone.get_config() == layer.get_config()
     assert layers[0].get_config()["trainable"] is False        # detection.py:264-266
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_gpu(lib):
+    """Argument validation happens on the host: NULL pointers and bad shapes come back as MLP_EINVAL
+    with a message, with or without a CUDA device."""
+    from masklab_b200 import runtime as rt
+    null = ctypes.c_void_p(None)
+    cases = [
+        lib.mlp_road_scan(null, null, 1, 8, 8, 3, 1, 2, 3.25, null, null, null, null, null),
+        lib.mlp_summary_output(null, null, null, rt.MLP_F32, null, null, null, 1, 1, 1, null, 8, 8, 0.1, null, null, null),
+        lib.mlp_tile_summary(null, null, null, null, 0, null, 0, null, 1, 1, 1, null, 28, 28, null, null, null, 8, 8,
+                             0.1, null, null, null, null),
+        lib.mlp_draw_boxes(null, null, rt.MLP_U8, null, 1, 1, 1, null, 8, 8, null, null),
+        lib.mlp_draw_segmentation(null, null, rt.MLP_U8, null, rt.MLP_I32, 1, 8, 8, None, null, null),
+        lib.mlp_draw_instance(null, null, rt.MLP_U8, null, null, rt.MLP_U8, 1, 1, 1, null, 8, 8, None, null, null),
+        lib.mlp_draw_tiles(null, null, rt.MLP_U8, null, null, null, 0, null, 0, null, 1, 1, 1, null, 28, 28, 8, 8,
+                           None, null, rt.MLP_I32, None, null, null),
+        lib.mlp_resize_bilinear(null, null, rt.MLP_F32, 1, 4, 4, 3, 8, 8, 0, null, null),
+        lib.mlp_trim_paste(null, null, null, 1, 1, null, 28, 28, 1, 1.0, 1.0, 1, 8, 8, rt.MLP_PASTE_U8, null, null,
+                           null, null, null),
+    ]
+    assert all(rc == rt.MLP_EINVAL for rc in cases), cases
+    assert b"NULL" in lib.mlp_last_error()
+    with pytest.raises(rt.InvalidArgumentError):
+        rt.DrawColorsC.make([[1, 2]], 0.3)                      # not an RGB triple
+    with pytest.raises(rt.InvalidArgumentError):
+        rt.DrawColorsC.make([[0, 0, 0]] * 17, 0.3)              # more than MLP_MAX_DRAW_CLASSES
+    c = rt.DrawColorsC.make([[1, 2, 3], [4, 5, 6]], 0.25)
+    assert c.num_classes == 2 and c.alpha == 0.25 and list(c.rgb[1]) == [4.0, 5.0, 6.0]
+    assert ctypes.sizeof(rt.DrawColorsC) == 8 + 16 * 3 * 4
