@@ -337,6 +337,11 @@ int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* ma
  * float32 values (threshold = 0) or int32 (value > 0.5) (threshold = 1, misc.py:194).            */
 int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
                         int channels, int out_h, int out_w, int threshold, void* out_dev, mlp_stream_t stream);
+/* SemanticSmoothing.call (engine/layers/semantic.py:270-284): tf.nn.erosion2d then tf.nn.dilation2d
+ * with a flat kernel_size x kernel_size kernel, strides/rates 1, padding SAME, times weight;
+ * kernel_size <= 0: only the weight.  in_dev/out_dev f32 [B,h,w,S]; in_dev != out_dev.          */
+int mlp_semantic_smoothing(mlp_ctx* ctx, const float* in_dev, int batch, int height, int width, int channels,
+                           int kernel_size, float weight, float* out_dev, mlp_stream_t stream);
 
 /* ---- the overlay layers of the serving graph ------------------------------
  * DrawSegmentation.call (engine/layers/misc.py:412-421) and DrawInstance.call (:440-463), wired in

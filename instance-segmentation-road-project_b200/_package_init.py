@@ -6,7 +6,8 @@ from .prior import PriorBoxes                                    # noqa: F401
 from .layers import (PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal,   # noqa: F401
                      DownSampleInput, MoldBatch, MaskDistribute, PyramidRoiAlign, TrimInstances,
                      UpSampleOutput, CropAndPadMask, CrackToInstance, SummaryOutput, IncludeMyRoad,
-                     CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, get_custom_objects)
+                     CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, SemanticSmoothing,
+                     get_custom_objects)
 from .pipeline import PostProcessPipeline, DetectionConfig      # noqa: F401
 from .runtime import Context, MaskLabError, InvalidArgumentError, load_library   # noqa: F401
 

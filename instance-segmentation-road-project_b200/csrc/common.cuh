@@ -12,7 +12,7 @@
 #endif
 
 // ---------------------------------------------------------------- context ----
-#define MLP_NUM_ARENAS 9
+#define MLP_NUM_ARENAS 10
 struct mlp_ctx {
     int device;
     int sm_count;
@@ -63,6 +63,7 @@ struct ProfScope {
 #define MLP_ARENA_SUMMARY 6
 #define MLP_ARENA_BOXACC 7
 #define MLP_ARENA_DRAW 8
+#define MLP_ARENA_SMOOTH 9
 
 void mlp_set_error(const char* fmt, ...);
 int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes);

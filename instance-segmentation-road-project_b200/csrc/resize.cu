@@ -11,6 +11,8 @@
 // source pixels are read as contiguous channel runs).  Up-sampling is write-bound (int32/f32 out),
 // down-sampling read-bound; there is no reuse worth staging - neighbouring threads hit the same
 // source lines in L1.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
@@ -109,7 +111,94 @@ void launch_resize4(int S, int grid, cudaStream_t st, const void* in, int B, int
     else resize_bilinear4_kernel<InT, kThreshold, 4><<<grid, kResizeThreads, 0, st>>>(p, B, ih, iw, oh, ow, sy, sx, out);
 }
 
+// ---- SemanticSmoothing ----------------------------------------------------------------------
+// Grey erosion then dilation with a flat k x k structuring element, padding SAME
+// (/root/reference/engine/layers/semantic.py:270-284; tf.nn.erosion2d is -dilation2d(-v, reverse(k)),
+// so with the all-zero kernel both read the window p-(k-1)/2 .. p-(k-1)/2+k-1 and skip positions
+// outside the map; restated in oracle/semantic_oracle.py).  min/max are exact, so each 2-D window
+// is evaluated separably: four streaming passes (min along x, min along y, max along x, max along y),
+// one thread per element, k L1-served taps each; the last pass applies the weight.
+// Element i = (outer * len + p) * step + inner; a thread owns FOUR consecutive positions p of one
+// (outer, inner) line, so neighbouring outputs share their taps (k + 3 loads instead of 4 k).
+template <bool kMax>
+__global__ void __launch_bounds__(kResizeThreads)
+window_pass_kernel(const float* __restrict__ in, int64_t lines_outer, int len, int64_t step, int k, int pt,
+                   float weight, float* __restrict__ out) {
+    const int groups = (len + 3) >> 2;
+    const int64_t total = lines_outer * groups * step;
+    const float neutral = kMax ? -INFINITY : INFINITY;
+    for (int64_t t = (int64_t)blockIdx.x * kResizeThreads + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * kResizeThreads) {
+        const int64_t inner = t % step;
+        const int64_t og = t / step;
+        const int p0 = (int)(og % groups) * 4;
+        const int64_t outer = og / groups;
+        const float* line = in + outer * len * step + inner;
+        float acc[4] = {neutral, neutral, neutral, neutral};
+        const int lo = max(p0 - pt, 0), hi = min(p0 + 3 + (k - 1 - pt), len - 1);
+        for (int s = lo; s <= hi; ++s) {                    // source position; feeds outputs s-(k-1-pt) .. s+pt
+            const float v = __ldg(line + (int64_t)s * step);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int d = s - (p0 + q);
+                if (d >= -pt && d <= k - 1 - pt) acc[q] = kMax ? fmaxf(acc[q], v) : fminf(acc[q], v);
+            }
+        }
+        float* o = out + outer * len * step + inner;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (p0 + q < len) o[(int64_t)(p0 + q) * step] = __fmul_rn(acc[q], weight);
+    }
+}
+
+__global__ void __launch_bounds__(kResizeThreads)
+scale_kernel(const float* __restrict__ in, int64_t n, float weight, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * kResizeThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kResizeThreads)
+        out[i] = __fmul_rn(__ldg(in + i), weight);
+}
+
 }  // namespace
+
+extern "C" int mlp_semantic_smoothing(mlp_ctx* ctx, const float* in_dev, int batch, int height, int width,
+                                      int channels, int kernel_size, float weight, float* out_dev,
+                                      mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && in_dev && out_dev, "mlp_semantic_smoothing: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && height >= 1 && width >= 1 && channels >= 1, "mlp_semantic_smoothing: bad shape");
+    MLP_CHECK_ARG(kernel_size <= 1024, "mlp_semantic_smoothing: kernel_size %d too large", kernel_size);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_RESIZE, st);
+    const int64_t n = (int64_t)batch * height * width * channels;
+    int64_t blocks = (n + kResizeThreads - 1) / kResizeThreads;
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    if (kernel_size <= 0) {                                  // semantic.py:283-284
+        scale_kernel<<<grid, kResizeThreads, 0, st>>>(in_dev, n, weight, out_dev);
+        MLP_LAUNCH_CHECK(ctx);
+        return MLP_OK;
+    }
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_SMOOTH, n * 4);
+    if (rc) return rc;
+    float* tmp = static_cast<float*>(ctx->arena[MLP_ARENA_SMOOTH]);
+    const int k = kernel_size, pt = (kernel_size - 1) / 2;
+    const int64_t sx = channels, sy = (int64_t)width * channels;
+    const int64_t outer_x = (int64_t)batch * height, outer_y = batch;      // lines along x / along y
+    auto grid_for = [&](int64_t outer, int len, int64_t step) {
+        const int64_t work = outer * ((len + 3) / 4) * step;
+        const int64_t bl = (work + kResizeThreads - 1) / kResizeThreads;
+        return (int)(bl < cap ? (bl < 1 ? 1 : bl) : cap);
+    };
+    window_pass_kernel<false><<<grid_for(outer_x, width, sx), kResizeThreads, 0, st>>>(in_dev, outer_x, width, sx, k, pt, 1.0f, tmp);
+    MLP_LAUNCH_CHECK(ctx);
+    window_pass_kernel<false><<<grid_for(outer_y, height, sy), kResizeThreads, 0, st>>>(tmp, outer_y, height, sy, k, pt, 1.0f, out_dev);
+    MLP_LAUNCH_CHECK(ctx);
+    window_pass_kernel<true><<<grid_for(outer_x, width, sx), kResizeThreads, 0, st>>>(out_dev, outer_x, width, sx, k, pt, 1.0f, tmp);
+    MLP_LAUNCH_CHECK(ctx);
+    window_pass_kernel<true><<<grid_for(outer_y, height, sy), kResizeThreads, 0, st>>>(tmp, outer_y, height, sy, k, pt, weight, out_dev);
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
+}
 
 extern "C" int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
                                    int channels, int out_h, int out_w, int threshold, void* out_dev,

@@ -5,3 +5,4 @@ from .instance import MaskDistribute, PyramidRoiAlign, TrimInstances          # 
 from .misc import DownSampleInput, MoldBatch, UpSampleOutput, CropAndPadMask                   # noqa: F401
 from .summary import CrackToInstance, SummaryOutput, IncludeMyRoad, CalculateInstanceSize   # noqa: F401
 from .draw import DrawBoxes, DrawSegmentation, DrawInstance                              # noqa: F401
+from .semantic import SemanticSmoothing                                       # noqa: F401

@@ -119,6 +119,7 @@ SIGNATURES = {
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
                               _F, _P, _P, _P, _P]),
     "mlp_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mlp_semantic_smoothing": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "mlp_draw_boxes": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "mlp_draw_segmentation": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_draw_instance": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),

@@ -448,3 +448,16 @@ def test_pipeline_no_detections_and_high_confidence(ml, fused):
         assert np.array_equal(host(pasted), want["binary"])
         if case == "confident":
             assert want["det_i"][..., 5].max() > 50 and want["binary"].sum() > 0
+
+
+@pytest.mark.parametrize("shape,k,weight", [((2, 40, 56, 3), 10, 1.0), ((1, 33, 29, 2), 4, 2.0), ((2, 9, 11, 3), 1, 0.5),
+                                            ((1, 6, 7, 1), 10, 1.0), ((2, 12, 12, 3), 0, 0.25), ((1, 50, 70, 4), 7, 1.5)])
+def test_semantic_smoothing(ml, shape, k, weight):
+    """semantic.py:270-284: erosion2d then dilation2d with a flat k x k kernel, SAME, times weight."""
+    from oracle import semantic_oracle as so
+    rng = np.random.default_rng(shape[1] + k)
+    x = rng.random(shape).astype(F32)
+    x[x < 0.3] = 0.0                                                 # plateaus and specks
+    want = so.semantic_smoothing(x, k, weight)
+    got = ml.SemanticSmoothing(kernel_size=k, weight=weight)(dev(x))
+    assert got.dtype == torch.float32 and np.array_equal(host(got), want)

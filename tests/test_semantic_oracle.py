@@ -40,3 +40,40 @@ def test_upsample_semantic_thresholds_after_the_resize():
     assert up[0, :, :, 0].tolist() == [[1, 0, 0], [0, 0, 0], [0, 0, 0]]        # 0.5 is not > 0.5
     sem[0, 0, 1, 0] = 0.2
     assert so.upsample_semantic(sem, (3, 3))[0, 0, :, 0].tolist() == [1, 1, 0]  # (1 + 0.2) / 2 = 0.6
+
+
+def test_semantic_smoothing_known_answers():
+    # an isolated speck is erased by the erosion; a block at least k wide survives the opening.
+    # Erosion and dilation read the SAME even-sized window p-4 .. p+5 (the duality only reverses the
+    # kernel values, all zero here), so the surviving block comes back shifted by one pixel up/left.
+    x = np.zeros((1, 30, 30, 1), F32)
+    x[0, 5, 5, 0] = 1.0                     # noise
+    x[0, 10:22, 8:20, 0] = 0.8              # 12 x 12 block
+    out = so.semantic_smoothing(x, 10, 1.0)
+    assert out[0, 5, 5, 0] == 0 and out[0, :9].sum() == 0
+    assert np.array_equal(out[0, 9:21, 7:19, 0], np.full((12, 12), F32(0.8)))
+    assert np.isclose(out.sum(), 0.8 * 144)  # same size, nothing else
+    # window alignment of the even-sized SAME kernel: rows p-4 .. p+5.  Erosion of a step edge
+    # (ones from row 10 on) keeps ones where the whole window is inside the ones: p-4 >= 10.
+    step = np.zeros((1, 30, 3, 1), F32)
+    step[0, 10:, :, 0] = 1.0
+    e = so._window_reduce(step, 10, 1, np.minimum, F32(np.inf))
+    assert e[0, :, 0, 0].tolist() == [0.0] * 14 + [1.0] * 16
+    d = so._window_reduce(e, 10, 1, np.maximum, F32(-np.inf))
+    assert d[0, :, 0, 0].tolist() == [0.0] * 9 + [1.0] * 21    # dilation reaches back to p+5 >= 14 -> p >= 9
+    # kernel_size 0: only the weight (semantic.py:283-284)
+    y = np.random.default_rng(0).random((1, 4, 5, 2)).astype(F32)
+    assert np.array_equal(so.semantic_smoothing(y, 0, 0.5), y * F32(0.5))
+    # brute force on a small random map
+    z = np.random.default_rng(1).random((2, 9, 11, 3)).astype(F32)
+    got = so.semantic_smoothing(z, 4, 2.0)
+    pt = 1
+    er = np.empty_like(z)
+    for yy in range(9):
+        for xx in range(11):
+            er[:, yy, xx] = z[:, max(0, yy - pt):yy - pt + 4, max(0, xx - pt):xx - pt + 4].min(axis=(1, 2))
+    di = np.empty_like(z)
+    for yy in range(9):
+        for xx in range(11):
+            di[:, yy, xx] = er[:, max(0, yy - pt):yy - pt + 4, max(0, xx - pt):xx - pt + 4].max(axis=(1, 2))
+    assert np.array_equal(got, di * F32(2.0))
