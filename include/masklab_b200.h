@@ -385,6 +385,30 @@ int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const 
                    const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
                    const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream);
 
+/* ---- training-side target assignment -------------------------------------
+ * CalculateIOU.call (engine/layers/detection.py:391-422): aa_dev [Na, aa_stride >= 4], bb_dev
+ *   [Nb, bb_stride >= 4] (cx,cy,w,h) -> out_dev f32 [Na,Nb] = inter / (union + 1e-5).
+ * AssignBoxes.call (detection.py:619-690): gt_boxes_dev f32 [B,G,6] (-1 padded), pr_boxes_dev
+ *   [B,N,4] (MLP_F32 or MLP_I32 as PriorLayer returns them) -> cls_true_dev [B,N,C] one-hot,
+ *   loc_true_dev [B,N,4], assign_mask_dev [B,N,1] (1 background, 0 assigned, -1 ignore band
+ *   0.4 <= IoU < 0.5).  Repeated scatter indices behave like TensorFlow's CPU kernels: the last class
+ *   update wins, regression targets of repeated matches add up.
+ * AssignMasks.call (engine/layers/instance.py:330-380): roi_boxes_dev [B,R,6], gt_boxes_dev [B,G,6],
+ *   gt_masks_dev f32 [B,G,H,W] -> out_dev i32 [B,R,mh,mw]: class id where the best ground truth's mask
+ *   cropped to the RoI is > 0.5, num_classes elsewhere.
+ * DetectionIOUMetric.call (engine/metrics.py:117-160): pred_boxes_dev [B,P,6], gt_boxes_dev [B,G,6]
+ *   -> out_dev f32 [B,3] = (precision, recall, fmeasure) at IoU > 0.5.                          */
+int mlp_calculate_iou(mlp_ctx* ctx, const float* aa_dev, int num_aa, int aa_stride, const float* bb_dev, int num_bb,
+                      int bb_stride, float* out_dev, mlp_stream_t stream);
+int mlp_assign_boxes(mlp_ctx* ctx, const float* gt_boxes_dev, const void* pr_boxes_dev, int pr_dtype, int batch,
+                     int num_gt, int num_priors, int num_classes, float* cls_true_dev, float* loc_true_dev,
+                     float* assign_mask_dev, mlp_stream_t stream);
+int mlp_assign_masks(mlp_ctx* ctx, const float* roi_boxes_dev, int num_rois, const float* gt_boxes_dev, int num_gt,
+                     const float* gt_masks_dev, int batch, int height, int width, int mask_h, int mask_w,
+                     int num_classes, float match_iou_threshold, int32_t* out_dev, mlp_stream_t stream);
+int mlp_detection_iou_metric(mlp_ctx* ctx, const float* pred_boxes_dev, int num_pred, const float* gt_boxes_dev,
+                             int num_gt, int batch, float* out_dev, mlp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ from .layers import (PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal
                      DownSampleInput, MoldBatch, MaskDistribute, PyramidRoiAlign, TrimInstances,
                      UpSampleOutput, CropAndPadMask, CrackToInstance, SummaryOutput, IncludeMyRoad,
                      CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, SemanticSmoothing,
-                     get_custom_objects)
+                     CalculateIOU, AssignBoxes, AssignMasks, DetectionIOUMetric, get_custom_objects)
 from .pipeline import PostProcessPipeline, DetectionConfig      # noqa: F401
 from .runtime import Context, MaskLabError, InvalidArgumentError, load_library   # noqa: F401
 

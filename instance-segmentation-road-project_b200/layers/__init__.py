@@ -6,3 +6,4 @@ from .misc import DownSampleInput, MoldBatch, UpSampleOutput, CropAndPadMask    
 from .summary import CrackToInstance, SummaryOutput, IncludeMyRoad, CalculateInstanceSize   # noqa: F401
 from .draw import DrawBoxes, DrawSegmentation, DrawInstance                              # noqa: F401
 from .semantic import SemanticSmoothing                                       # noqa: F401
+from .training import CalculateIOU, AssignBoxes, AssignMasks, DetectionIOUMetric  # noqa: F401

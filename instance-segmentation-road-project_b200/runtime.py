@@ -119,6 +119,10 @@ SIGNATURES = {
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
                               _F, _P, _P, _P, _P]),
     "mlp_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mlp_calculate_iou": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
+    "mlp_assign_boxes": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "mlp_assign_masks": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "mlp_detection_iou_metric": (_I, [_P, _P, _I, _P, _I, _I, _P, _P]),
     "mlp_semantic_smoothing": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "mlp_draw_boxes": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "mlp_draw_segmentation": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
