@@ -54,10 +54,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=6,
                     help="independent pipelines/streams per GPU; consecutive batches alternate between them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
+    ap.add_argument("--no-graph-main", dest="graph_main", action="store_false",
+                    help="eager launches in the timed region instead of one captured CUDA graph per stream")
     ap.add_argument("--no-summary", action="store_true",
                     help="skip the SummaryOutput legs (SURVEY 8(f) rank 1: the consumer of the masks)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
@@ -225,7 +228,7 @@ def workload_config(args, wl):
     return {"workload": f"{args.workload}: B={wl['B']}/GPU {wl['W']}x{wl['H']} frames, C={wl['C']}, "
                         f"Cf={wl['Cf']}, max_out={wl['nms_max_output_size']}, paste {wl['PW']}x{wl['PH']} uint8",
             "batch_per_gpu": wl["B"], "parallelism": f"image-sharded x{args.gpus}",
-            "stream_frames": (args.frames or None),
+            "stream_frames": (args.frames or None), "cuda_graphs": bool(getattr(args, "graph_main", False)) and not args.frames,
             "l2_policy": "inputs (>=365 MB) and outputs (>=1.6 GB) per step exceed the 126 MB L2",
             "score_mu": wl["mu"]}
 
@@ -286,11 +289,26 @@ def run_ours(args, wl):
         stream_det = torch.empty((args.steps * B, K, 6), dtype=torch.float32, device="cuda")
         stream_cnt = torch.empty((args.steps * B,), dtype=torch.int32, device="cuda")
 
+    graphs = None
+    launches_per_step = None
+    if args.graph_main and not args.frames:
+        # the path is sync-free, so a whole batch replays as ONE graph launch per stream
+        try:
+            l0 = sum(p.ctx.launch_count() for p in pipes)
+            graphs = [p.capture(d_loc, d_cls, d_fmaps, d_masks)[0] for p in pipes]
+            launches_per_step = (sum(p.ctx.launch_count() for p in pipes) - l0) // (3 * S)    # 2 warm-ups + capture
+        except Exception as exc:                     # pragma: no cover - fall back to eager launches
+            print(f"CUDA graph capture failed, eager launches instead: {exc!r}", file=sys.stderr)
+            graphs = None
+
     def step():
         i = state["i"]
         k = i % S
         state["i"] += 1
         with torch.cuda.stream(streams[k]):
+            if graphs is not None:
+                graphs[k].replay()
+                return
             r = pipes[k].detect_and_align(d_loc, d_cls, d_fmaps)
             pipes[k].trim_and_paste(r, d_masks)
             if stream_det is not None:
@@ -340,6 +358,8 @@ def run_ours(args, wl):
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = sum(p.ctx.launch_count() for p in pipes) - launches0
+    if graphs is not None:
+        launches = launches_per_step * args.steps           # kernels inside the replayed graphs
     stages = {}
     for p in pipes:
         for k_, (t_, n_) in p.ctx.profile_read().items():
@@ -367,6 +387,26 @@ def run_ours(args, wl):
         iso = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
         iso["_step_ms"] = e0.elapsed_time(e1) / iso_steps
         pipe.ctx.profile(False)
+
+    # ---- the same step as ONE CUDA graph launch (single stream): what the launch gaps cost
+    graph_ms = None
+    if not args.no_graph:
+        try:
+            g_, _ = pipe.capture(d_loc, d_cls, d_fmaps, d_masks)
+            for _ in range(3):
+                g_.replay()
+            torch.cuda.synchronize()
+            n_ = max(10, min(100, args.steps))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_):
+                g_.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            graph_ms = e0.elapsed_time(e1) / n_
+            del g_
+        except Exception as exc:                     # pragma: no cover
+            graph_ms = f"capture failed: {exc!r}"
 
     # ---- roofline of the dominant kernel (mask paste): algorithmic bytes = B*M*PH*PW uint8
     peaks = {}
@@ -411,6 +451,7 @@ def run_ours(args, wl):
                 "whole_step": {"algorithmic_bytes": step_bytes,
                                "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                "cuda_graph_single_stream_ms_per_step": graph_ms,
                 "single_stream": ({"ms_per_step": iso.get("_step_ms"),
                                    "stage_ms": {k_: v_ for k_, v_ in iso.items() if not k_.startswith("_")}}
                                   if iso else None)}

@@ -314,6 +314,29 @@ class PostProcessPipeline:
         Mo = int(self.summary_m.item())
         return self.summary[:self.B * Mo * 11].view(self.B, Mo, 11)
 
+    # ---------------------------------------------------------------- CUDA graph
+    def capture(self, loc_pred, cls_pred, fmaps, roi_masks):
+        """Capture one whole batch (detect_and_align + trim_and_paste over THESE buffers) into a CUDA
+        graph: the path is sync-free - every data-dependent size stays on the device - so the six
+        kernels and their memsets replay as one launch.  Refill the same input tensors and call
+        `.replay()` on the returned graph; results land in the pipeline's buffers as usual.  The
+        mask head is not part of the graph: roi_masks must already hold its output for the RoIs of
+        this batch when the graph is replayed (for a real model capture the two halves separately)."""
+        torch.cuda.synchronize(self.ctx.device)
+        side = torch.cuda.Stream(device=self.ctx.device)
+        side.wait_stream(torch.cuda.current_stream(self.ctx.device))
+        with torch.cuda.stream(side):                       # warm-up: scratch growth, function attributes
+            for _ in range(2):
+                rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+                self.trim_and_paste(rois, roi_masks)
+        torch.cuda.current_stream(self.ctx.device).wait_stream(side)
+        torch.cuda.synchronize(self.ctx.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+            self.trim_and_paste(rois, roi_masks)
+        return graph, rois
+
     def result_views(self):
         """Reference-shaped views of the last trim_and_paste (one D2H of M)."""
         M = int(self.trim_m.item())

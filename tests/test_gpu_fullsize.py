@@ -124,3 +124,22 @@ def test_idempotent_and_deterministic_at_full_size(run):
                                                        "post_iou_threshold", "nms_max_output_size")})(
         [torch.from_numpy(cls2).cuda(), boxes, None]).cpu().numpy()
     assert again.shape[1] == n and np.array_equal(again[0], det[b, :n])
+
+
+def test_cuda_graph_replay_reproduces_the_batch(run):
+    """The whole batch captured as one CUDA graph (no host round trip inside the path) gives the same
+    bytes, also after the inputs are refilled with another batch and back."""
+    pipe = run["pipe"]
+    d_loc, d_cls, d_fm = run["inputs"]
+    ref_det = pipe.det.clone()
+    ref_pasted = pipe.pasted.clone()
+    graph, rois = pipe.capture(d_loc, d_cls, d_fm, run["probs"])
+    keep_cls = d_cls.clone()
+    d_cls.copy_(torch.roll(keep_cls, 1, dims=0))             # another batch through the same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(pipe.det, ref_det)
+    d_cls.copy_(keep_cls)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.det, ref_det) and torch.equal(pipe.pasted, ref_pasted)
