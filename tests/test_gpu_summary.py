@@ -166,3 +166,34 @@ def test_pipeline_trim_and_summarize():
             det_i, pasted = pipe.result_views()
             assert np.array_equal(pasted.cpu().numpy(), want["binary"])
             assert np.array_equal(det_i.cpu().numpy(), want["det_i"])
+
+
+def test_serving_consumers_at_1080p():
+    """Frame-resolution check of both consumers (1080 x 1920, the streaming configuration): summary from
+    tiles and from materialised masks, overlays from tiles, against the oracles."""
+    import masklab_b200 as ml
+    from oracle import draw_oracle as do
+    B, M, C, PH, PW = 1, 7, 5, 1080, 1920
+    seg = synth.semantic_map(B, PH, PW, seed=77)
+    seg[0, 600:640, 100:1500, 2] = 1
+    det = synth.int_detections(B, M, C, PH, PW, seed=78, pad_tail=1)
+    det[0, 0] = [PW // 2, PH // 2, PW + 100, PH + 100, 1, 99]     # frame-sized box: 15 column chunks
+    det[0, 1] = [1500, 900, 700, 300, 2, 88]
+    rng = np.random.default_rng(79)
+    ins = (rng.random((B, M, 28, 28)) > 0.4).astype(np.int32)
+    masks = mo.crop_and_pad_mask((PH, PW), det, ins)
+    want = so.summary_output(det, seg, masks)
+    layer = ml.SummaryOutput()
+    check_summary(layer.from_tiles([dev(det), dev(seg), dev(ins)]).cpu().numpy(), want)
+    check_summary(layer([dev(det), dev(seg), dev(masks)]).cpu().numpy(), want)
+    check_summary(layer([dev(det), dev(seg), dev((masks > 0.5).astype(np.uint8))]).cpu().numpy(),
+                  so.summary_output(det, seg, (masks > 0.5).astype(np.float32)))
+    img = np.random.default_rng(80).integers(0, 256, (B, PH, PW, 3)).astype(np.uint8)
+    colors = [[192, 32, 128], [160, 96, 0], [96, 0, 128], [32, 96, 192], [96, 32, 128]]
+    sem_colors = [[64, 0, 128], [128, 96, 0], [128, 192, 0]]
+    want_vis = do.draw_segmentation(do.draw_instance(do.draw_boxes(img, det), det, masks, colors, 0.3), seg,
+                                    sem_colors, 0.3)
+    boxed = ml.DrawBoxes()([dev(img), dev(det)])
+    got_vis = ml.DrawInstance(colors, 0.3).from_tiles([boxed, dev(det), dev(ins)], seg_outs=dev(seg),
+                                                      semantic_colors=sem_colors, semantic_alpha=0.3)
+    assert np.array_equal(got_vis.cpu().numpy(), want_vis)
