@@ -58,9 +58,7 @@ out["UpSampleOutput_semantic_540x960_to_1080x1920_ms"] = timeit(
     lambda: ml.layers.misc.resize_bilinear(ml.Context.get(), sem_lo, 1080, 1920, threshold=True))
 out["DownSampleInput_1080x1920_to_540x960_ms"] = timeit(lambda: ml.DownSampleInput((540, 960))(frames_hi))
 # training-side target assignment at cfg-2 scale: 32 images, 163,680 priors, 50 ground truths each
-from oracle import masklab_oracle as _mo                     # (tool only: builds the prior table on the host)
-pr = torch.from_numpy(_mo.prior_layer(_mo.prior_table(**cfgp), wl["H"], wl["W"])).cuda()
-prb = pr[None].expand(B, -1, -1).contiguous()
+prb = ml.PriorLayer(cfgp)(torch.zeros((B, wl["H"], wl["W"], 3), dtype=torch.uint8, device="cuda"))   # [B,N,4] int32
 gt = torch.from_numpy(synth.detections(B, 50, C, wl["H"], wl["W"], seed=9, lo=12.0, hi=300.0, pad_tail=5)).cuda()
 gt[..., 5] = torch.where(gt[..., 0] == -1, -1.0, 1.0)
 out["AssignBoxes_B32_N163680_G50_ms"] = timeit(lambda: ml.AssignBoxes(C)([gt, prb]))
