@@ -4,13 +4,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import synth
-from oracle import masklab_oracle as mo
 import masklab_b200 as ml
 
 B, M, PH, PW = int(os.environ.get("B", 32)), int(os.environ.get("M", 100)), 512, 1024
 det = synth.detections(B, M, 5, PH, PW, seed=1)
 masks = synth.mask_probs(B, M, 1, seed=2)[..., 0]
-det_i, mask_i = mo.upsample_output(det, masks, (PH, PW), (PH, PW))
+det_i, mask_i, _ = ml.UpSampleOutput(semantic=False)([torch.from_numpy(det).cuda(), torch.from_numpy(masks).cuda(),
+                                                      (PH, PW)], target=(PH, PW))
+det_i, mask_i = det_i.cpu().numpy(), mask_i.cpu().numpy()
 if os.environ.get("ZERO"):
     det_i[..., 0] = PW + 1000      # every box off-frame: the kernel degenerates to a pure zero fill
 if os.environ.get("SMALL"):
