@@ -519,6 +519,8 @@ def run_ours(args, wl):
             cpu = {"value": v, "unit": "frames/s", "cores": 1, "kind": "port",
                    "sample": f"{frames * rep} frames ({frames} distinct) of workload {args.workload} "
                              f"through oracle/c (single thread, uint8 paste), {wall:.1f} s wall"}
+        if summary_leg is not None and not args.no_cpu_baseline and world == 1:
+            summary_leg["cpu_port"] = cpu_serving_tail(wl, frames=2)
         line = {
             "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -533,6 +535,35 @@ def run_ours(args, wl):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_serving_tail(wl, frames=2):
+    """CPU restatement of the serving tail on a bounded sample: the C restatement of the path up to the
+    pasted float32 masks, then the NumPy restatements of SummaryOutput and of the three overlay layers
+    (oracle/summary_oracle.py, oracle/draw_oracle.py), one frame at a time on one thread."""
+    import synth
+    from oracle import c_oracle as co, summary_oracle as so, draw_oracle as do
+    t_path = t_cons = 0.0
+    for i in range(frames):
+        cfgp, N, loc, cls, fmaps = make_inputs(wl, 1, 9000 + i)
+        pool = synth.mask_probs(1, (wl["max_k"] + 1) * wl["nms_max_output_size"], wl["C"], seed=98)
+        seg = synth.semantic_map(1, wl["PH"], wl["PW"], seed=9100 + i)
+        img = np.random.default_rng(9200 + i).integers(0, 256, (1, wl["PH"], wl["PW"], 3)).astype(np.uint8)
+        t0 = time.perf_counter()
+        out = co.full_path(loc, cls, fmaps, lambda f, b: pool[:, :b.shape[1]], cfgp, (wl["H"], wl["W"]),
+                           (wl["PH"], wl["PW"]), binary=False, **kwargs_of(wl))
+        t1 = time.perf_counter()
+        so.summary_output(out["det_i"], seg, out["pasted"])
+        vis = do.draw_boxes(img, out["det_i"])
+        vis = do.draw_instance(vis, out["det_i"], out["pasted"], INST_COLORS[:wl["C"]], 0.3)
+        do.draw_segmentation(vis, seg, SEM_COLORS, 0.3)
+        t2 = time.perf_counter()
+        t_path += t1 - t0
+        t_cons += t2 - t1
+    return {"value": frames / (t_path + t_cons), "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{frames} frames of workload through oracle/c (path, float32 paste) + NumPy restatements "
+                      f"of SummaryOutput / DrawBoxes / DrawInstance / DrawSegmentation",
+            "consumers_ms_per_frame": 1e3 * t_cons / frames, "path_ms_per_frame": 1e3 * t_path / frames}
 
 
 def algorithmic_bytes(wl, N, M):
