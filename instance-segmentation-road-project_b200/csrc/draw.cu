@@ -210,8 +210,13 @@ __device__ __forceinline__ void load_px12(const float* p, bool vec, int n, float
 }
 __device__ __forceinline__ float seg_f32(const int32_t* p) { return (float)__ldg(p); }
 __device__ __forceinline__ float seg_f32(const float* p) { return __ldg(p); }
+template <typename T> __device__ __forceinline__ float seg_word(uint32_t w);          // one element of a 128-bit load
+template <> __device__ __forceinline__ float seg_word<float>(uint32_t w) { return __uint_as_float(w); }
+template <> __device__ __forceinline__ float seg_word<int32_t>(uint32_t w) { return (float)(int32_t)w; }
 
-template <typename ImgT, typename SegT>
+// kCs: semantic classes known at compile time (0 = no semantic overlay, 3 = the serving graph's three
+// classes with their colours in registers and 128-bit map loads, -1 = any number, generic loop).
+template <typename ImgT, typename SegT, int kCs>
 __global__ void __launch_bounds__(kDrawThreads)
 draw_tiles_kernel(const DrawTilesArgs A) {
     __shared__ unsigned short s_cand[kMaxCand];            // instances touching the block, instance order
@@ -308,7 +313,34 @@ draw_tiles_kernel(const DrawTilesArgs A) {
     float sc[4][3];
 #pragma unroll
     for (int q = 0; q < 4; ++q) sc[q][0] = sc[q][1] = sc[q][2] = 0.0f;
-    if (A.seg) {
+    if (kCs == 3) {
+        float rgb[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rgb[c][k] = A.sem.rgb[c][k];
+        const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * 3;
+        float sv[12];
+        if (vec) {                                         // 4 pixels x 3 classes = three 128-bit loads
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(sp) + k);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    sv[k * 4 + e] = seg_word<SegT>(w[e]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) sv[i] = i < 3 * n ? seg_f32(sp + i) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[q][k] = __fadd_rn(sc[q][k], __fmul_rn(rgb[c][k], sv[q * 3 + c]));
+    } else if (kCs != 0) {
         const int Cs = A.sem.num_classes;
         const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * Cs;
         for (int q = 0; q < n; ++q)
@@ -324,7 +356,7 @@ draw_tiles_kernel(const DrawTilesArgs A) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float v = (float)__float2uint_rz(blend(img[q * 3 + k], cs[q][k], A.inst.alpha));
-            if (A.seg) v = (float)__float2uint_rz(blend(v, sc[q][k], A.sem.alpha));
+            if (kCs != 0) v = (float)__float2uint_rz(blend(v, sc[q][k], A.sem.alpha));
             const int i = q * 3 + k;
             word[i >> 2] |= __float2uint_rz(v) << (8 * (i & 3));
         }
@@ -518,10 +550,18 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
     A.out = out_dev;
     const dim3 grid((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch);
     const bool seg_f = seg_dev && seg_dtype == MLP_F32;
-    if (image_dtype == MLP_U8 && !seg_f) draw_tiles_kernel<uint8_t, int32_t><<<grid, kDrawThreads, 0, st>>>(A);
-    else if (image_dtype == MLP_U8) draw_tiles_kernel<uint8_t, float><<<grid, kDrawThreads, 0, st>>>(A);
-    else if (!seg_f) draw_tiles_kernel<float, int32_t><<<grid, kDrawThreads, 0, st>>>(A);
-    else draw_tiles_kernel<float, float><<<grid, kDrawThreads, 0, st>>>(A);
+    const int cs = !seg_dev ? 0 : (sem_colors->num_classes == 3 ? 3 : -1);
+#define MLP_DRAW_TILES(IT, ST)                                                                  \
+    do {                                                                                        \
+        if (cs == 0) draw_tiles_kernel<IT, ST, 0><<<grid, kDrawThreads, 0, st>>>(A);            \
+        else if (cs == 3) draw_tiles_kernel<IT, ST, 3><<<grid, kDrawThreads, 0, st>>>(A);       \
+        else draw_tiles_kernel<IT, ST, -1><<<grid, kDrawThreads, 0, st>>>(A);                   \
+    } while (0)
+    if (image_dtype == MLP_U8 && !seg_f) MLP_DRAW_TILES(uint8_t, int32_t);
+    else if (image_dtype == MLP_U8) MLP_DRAW_TILES(uint8_t, float);
+    else if (!seg_f) MLP_DRAW_TILES(float, int32_t);
+    else MLP_DRAW_TILES(float, float);
+#undef MLP_DRAW_TILES
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }
