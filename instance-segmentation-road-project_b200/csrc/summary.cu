@@ -582,11 +582,21 @@ box_summary_kernel(const BoxSummaryArgs A) {
             }
             continue;
         }
+        // chunk-major, highest chunk first: the extra chunks of wide (= large) boxes start before the
+        // bulk of small boxes, so the longest CTAs are not the last ones
         const int64_t t = item - n_crack;
-        const int chunk = (int)(t % A.chunks);
-        const int64_t inst = t / A.chunks;
+        const int64_t n_inst = (int64_t)A.B * M;
+        const int chunk = A.chunks - 1 - (int)(t / n_inst);
+        const int64_t inst = t % n_inst;
         const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
+        if (chunk > 0) {                                    // most (instance, chunk) items do not exist: decide that
+            const float cx = (float)max(row[0], 1);         // from the box width alone (x part of paste_geometry)
+            const float hw = __fdiv_rn((float)max(row[2], 1), 2.0f);
+            const int x0 = min(max(__float2int_rz(ceilf(__fsub_rn(cx, hw))), 0), PW);
+            const int x1 = min(max(__float2int_rz(ceilf(__fadd_rn(cx, hw))), 0), PW);
+            if (chunk * 32 >= x1 - x0) continue;            // 32 = the narrowest chunk; CTA-uniform
+        }
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         const int cols = 32 * box_q(g);                     // columns per chunk of this box
         const int nchunks = g.active ? (g.xmax - g.xmin + cols - 1) / cols : 1;
