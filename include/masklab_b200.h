@@ -333,10 +333,14 @@ int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const int32_t* ma
 /* ---- SURVEY 8(f) rank 3 (resize part): the bilinear resizes either side of the path -----------
  * tf.compat.v1.image.resize_bilinear(align_corners=True) of DownSampleInput.call
  * (engine/layers/misc.py:143-154) and of the semantic half of UpSampleOutput.call (:190-195).
- * in_dev [B,in_h,in_w,S] (MLP_F32, MLP_U8 or MLP_I32, cast to float32) -> out_dev [B,out_h,out_w,S]:
- * float32 values (threshold = 0) or int32 (value > 0.5) (threshold = 1, misc.py:194).            */
+ * Also ResizeLike.call (misc.py:302-307).  in_dev [B,in_h,in_w,S] (MLP_F32, MLP_U8 or MLP_I32, cast to
+ * float32) -> out_dev [B,out_h,out_w,S]: float32 values, or with MLP_RESIZE_THRESHOLD int32
+ * (value > 0.5) (misc.py:194).  MLP_RESIZE_NO_ALIGN_CORNERS selects the legacy align_corners=False
+ * scale in/out (ResizeLike(align_corners=False)).                                               */
+#define MLP_RESIZE_THRESHOLD        1
+#define MLP_RESIZE_NO_ALIGN_CORNERS 2
 int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
-                        int channels, int out_h, int out_w, int threshold, void* out_dev, mlp_stream_t stream);
+                        int channels, int out_h, int out_w, int flags, void* out_dev, mlp_stream_t stream);
 /* SemanticSmoothing.call (engine/layers/semantic.py:270-284): tf.nn.erosion2d then tf.nn.dilation2d
  * with a flat kernel_size x kernel_size kernel, strides/rates 1, padding SAME, times weight;
  * kernel_size <= 0: only the weight.  in_dev/out_dev f32 [B,h,w,S]; in_dev != out_dev.          */

@@ -4,11 +4,12 @@
 # Keras layer interface over the C ABI in include/masklab_b200.h.
 from .prior import PriorBoxes                                    # noqa: F401
 from .layers import (PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal,   # noqa: F401
-                     DownSampleInput, MoldBatch, MaskDistribute, PyramidRoiAlign, TrimInstances,
+                     DownSampleInput, MoldBatch, ResizeLike, MaskDistribute, PyramidRoiAlign, TrimInstances,
                      UpSampleOutput, CropAndPadMask, CrackToInstance, SummaryOutput, IncludeMyRoad,
                      CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, SemanticSmoothing,
                      CalculateIOU, AssignBoxes, AssignMasks, DetectionIOUMetric, get_custom_objects)
 from .pipeline import PostProcessPipeline, DetectionConfig      # noqa: F401
+from .serving import PostProcessConfig, serving_outputs        # noqa: F401
 from .runtime import Context, MaskLabError, InvalidArgumentError, load_library   # noqa: F401
 
 __version__ = "0.1.0"

@@ -201,8 +201,10 @@ extern "C" int mlp_semantic_smoothing(mlp_ctx* ctx, const float* in_dev, int bat
 }
 
 extern "C" int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtype, int batch, int in_h, int in_w,
-                                   int channels, int out_h, int out_w, int threshold, void* out_dev,
+                                   int channels, int out_h, int out_w, int flags, void* out_dev,
                                    mlp_stream_t stream) {
+    const int threshold = flags & MLP_RESIZE_THRESHOLD;
+    const bool align = !(flags & MLP_RESIZE_NO_ALIGN_CORNERS);
     MLP_CHECK_ARG(ctx && in_dev && out_dev, "mlp_resize_bilinear: NULL argument");
     MLP_CHECK_ARG(batch >= 1 && in_h >= 1 && in_w >= 1 && channels >= 1, "mlp_resize_bilinear: bad input shape");
     MLP_CHECK_ARG(out_h >= 1 && out_w >= 1, "mlp_resize_bilinear: output dimensions must be positive (%dx%d)", out_h,
@@ -212,9 +214,9 @@ extern "C" int mlp_resize_bilinear(mlp_ctx* ctx, const void* in_dev, int in_dtyp
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_RESIZE, st);
-    // CalculateResizeScale(in, out, align_corners = true)
-    const float sy = out_h > 1 ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
-    const float sx = out_w > 1 ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
+    // CalculateResizeScale(in, out, align_corners)
+    const float sy = (align && out_h > 1) ? (float)(in_h - 1) / (float)(out_h - 1) : (float)in_h / (float)out_h;
+    const float sx = (align && out_w > 1) ? (float)(in_w - 1) / (float)(out_w - 1) : (float)in_w / (float)out_w;
     const int64_t npix = (int64_t)batch * out_h * out_w;
     const int64_t cap = (int64_t)ctx->sm_count * 32;
     if (channels <= 4 && (out_w & 3) == 0 && mlp_aligned16(out_dev)) {

@@ -53,8 +53,8 @@ class MoldBatch(Layer):
         return config
 
 
-def resize_bilinear(ctx, x, out_h, out_w, threshold=False):
-    """tf.compat.v1.image.resize_bilinear(x, (out_h, out_w), align_corners=True) on a CUDA NHWC tensor;
+def resize_bilinear(ctx, x, out_h, out_w, threshold=False, align_corners=True):
+    """tf.compat.v1.image.resize_bilinear(x, (out_h, out_w), align_corners) on a CUDA NHWC tensor;
     threshold=True returns int32 (value > 0.5)."""
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise rt.InvalidArgumentError(rt.MLP_EDLPACK, "resize_bilinear: expected a CUDA tensor (no CPU path)")
@@ -67,8 +67,28 @@ def resize_bilinear(ctx, x, out_h, out_w, threshold=False):
     B, h, w, S = (int(d) for d in x.shape)
     out = ctx.empty((B, int(out_h), int(out_w), S), torch.int32 if threshold else torch.float32)
     rt.check(ctx.lib.mlp_resize_bilinear(ctx.handle, ctx.view(x), code, B, h, w, S, int(out_h), int(out_w),
-                                         1 if threshold else 0, ctx.view(out), ctx.stream()))
+                                         (1 if threshold else 0) | (0 if align_corners else 2), ctx.view(out),
+                                         ctx.stream()))
     return out
+
+
+@register
+class ResizeLike(Layer):
+    """x [B,h,w,S], target=<tensor [B,H,W,..] or (H, W)> -> float32 [B,H,W,S] (bilinear)."""
+
+    def __init__(self, align_corners=True, **kwargs):
+        self.align_corners = align_corners
+        super().__init__(**kwargs)
+
+    def call(self, inputs, **kwargs):
+        target = kwargs.get("target")
+        th, tw = (target.shape[1], target.shape[2]) if hasattr(target, "shape") else target
+        return resize_bilinear(ctx_of(inputs), inputs, int(th), int(tw), align_corners=bool(self.align_corners))
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"align_corners": self.align_corners})
+        return config
 
 
 @register

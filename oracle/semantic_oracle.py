@@ -14,12 +14,13 @@ from . import tf_ops
 F32 = np.float32
 
 
-def resize_bilinear_nhwc(x, out_h, out_w):
-    """x [B,h,w,S] (any numeric, cast to f32) -> [B,out_h,out_w,S] f32, align_corners=True."""
+def resize_bilinear_nhwc(x, out_h, out_w, align_corners=True):
+    """x [B,h,w,S] (any numeric, cast to f32) -> [B,out_h,out_w,S] f32 (ResizeLike.call, misc.py:302-307,
+    with the layer's align_corners; True everywhere else on the path)."""
     x = np.asarray(x).astype(F32)
     B, h, w, S = x.shape
-    ylo, yhi, yl = tf_ops.resize_interp_weights(out_h, h)
-    xlo, xhi, xl = tf_ops.resize_interp_weights(out_w, w)
+    ylo, yhi, yl = tf_ops.resize_interp_weights(out_h, h, align_corners)
+    xlo, xhi, xl = tf_ops.resize_interp_weights(out_w, w, align_corners)
     tl = x[:, ylo][:, :, xlo]
     tr = x[:, ylo][:, :, xhi]
     bl = x[:, yhi][:, :, xlo]

@@ -111,7 +111,7 @@ def test_layer_configs_roundtrip_without_gpu():
               ml.MoldBatch(12), ml.RestoreBoxes(), ml.NormalizeBoxes(), ml.UpSampleOutput(),
               ml.CropAndPadMask(output="uint8")]
     # the consumers and the steps either side of the path
-    for name in ("DownSampleInput", "CrackToInstance", "SummaryOutput", "IncludeMyRoad", "CalculateInstanceSize",
+    for name in ("DownSampleInput", "ResizeLike", "CrackToInstance", "SummaryOutput", "IncludeMyRoad", "CalculateInstanceSize",
                  "DrawBoxes", "DrawSegmentation", "DrawInstance", "SemanticSmoothing", "CalculateIOU", "AssignBoxes",
                  "AssignMasks", "DetectionIOUMetric"):
         assert name in objs
@@ -119,7 +119,7 @@ def test_layer_configs_roundtrip_without_gpu():
     layers += [ml.DownSampleInput((270, 480)), ml.CrackToInstance(4), ml.SummaryOutput(2.5), ml.IncludeMyRoad(0.2),
                ml.CalculateInstanceSize(3.0), ml.DrawBoxes(), ml.DrawSegmentation(colors, 0.4),
                ml.DrawInstance(colors, 0.5), ml.UpSampleOutput(semantic=False), ml.SemanticSmoothing(6, 0.5),
-               ml.CalculateIOU(), ml.AssignBoxes(7), ml.AssignMasks(0.6), ml.DetectionIOUMetric()]
+               ml.CalculateIOU(), ml.AssignBoxes(7), ml.AssignMasks(0.6), ml.DetectionIOUMetric(), ml.ResizeLike(False)]
     for layer in layers:
         clone = type(layer).from_config(layer.get_config())
         assert clone.get_config() == layer.get_config()
