@@ -413,6 +413,21 @@ int mlp_assign_masks(mlp_ctx* ctx, const float* roi_boxes_dev, int num_rois, con
 int mlp_detection_iou_metric(mlp_ctx* ctx, const float* pred_boxes_dev, int num_pred, const float* gt_boxes_dev,
                              int num_gt, int batch, float* out_dev, mlp_stream_t stream);
 
+/* ---- SURVEY 8(f) rank 2, last step of the serving graph: the JPEG encode -----------------------
+ * EncodeImageContent.call (engine/layers/misc.py:343-351, road_project/setup/serving.py:41) =
+ * tf.io.encode_jpeg(image) with default attributes: libjpeg baseline, quality 95, YCbCr 4:2:0,
+ * JDCT_ISLOW, Annex K Huffman tables, JFIF 300x300 dpi.  images_dev uint8 [B,H,W,3] ->
+ * out_dev[b * out_stride ...] = the complete JPEG file of frame b, len_dev[b] = its size in bytes.
+ * The bytes equal libjpeg(-turbo)'s for the same parameters.  A frame whose file would exceed
+ * out_stride writes nothing and reports -(bytes needed); mlp_jpeg_max_bytes is the bound that can
+ * never be exceeded (about 10 bytes per pixel; typical files take 0.3-1).  The reference encodes
+ * frame 0 only; batch > 1 encodes every frame.
+ * mlp_jpeg_header: the 623 header bytes (SOI .. SOS) for a frame size, into host memory.        */
+int64_t mlp_jpeg_max_bytes(int frame_h, int frame_w);
+int mlp_jpeg_header(int frame_h, int frame_w, int quality, uint8_t* out_host, int capacity);
+int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batch, int frame_h, int frame_w, int quality,
+                    uint8_t* out_dev, int64_t out_stride, int32_t* len_dev, mlp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@
 #endif
 
 // ---------------------------------------------------------------- context ----
-#define MLP_NUM_ARENAS 11
+#define MLP_NUM_ARENAS 12
 struct mlp_ctx {
     int device;
     int sm_count;
@@ -35,7 +35,7 @@ struct mlp_ctx {
 enum {
     MLP_ST_THRESHOLD = 0, MLP_ST_NMS_CLASS, MLP_ST_NMS_CROSS, MLP_ST_DISTRIBUTE, MLP_ST_ROI_PLAN,
     MLP_ST_ROI_ALIGN, MLP_ST_TRIM, MLP_ST_UPSAMPLE, MLP_ST_PASTE_THR, MLP_ST_PASTE, MLP_ST_ELEMENTWISE,
-    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW, MLP_ST_RESIZE, MLP_ST_ASSIGN
+    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW, MLP_ST_RESIZE, MLP_ST_ASSIGN, MLP_ST_JPEG
 };
 
 // RAII: records a start event now and a stop event when it goes out of scope.
@@ -65,6 +65,7 @@ struct ProfScope {
 #define MLP_ARENA_DRAW 8
 #define MLP_ARENA_SMOOTH 9
 #define MLP_ARENA_ASSIGN 10
+#define MLP_ARENA_JPEG 11
 
 void mlp_set_error(const char* fmt, ...);
 int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes);

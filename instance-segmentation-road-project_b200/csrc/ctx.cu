@@ -78,7 +78,7 @@ extern "C" int64_t mlp_ctx_launch_count(const mlp_ctx* ctx) { return ctx ? ctx->
 static const char* kStageNames[MLP_NUM_STAGES] = {
     "threshold_compact", "nms_per_class", "nms_cross_class", "mask_distribute", "roi_plan",
     "roi_align", "trim", "upsample", "paste_threshold", "paste", "elementwise", "mold_batch",
-    "tail_fused", "road_scan", "summary", "draw", "resize", "assign", "", "", "", "", "", ""};
+    "tail_fused", "road_scan", "summary", "draw", "resize", "assign", "jpeg", "", "", "", "", ""};
 
 extern "C" const char* mlp_stage_name(int stage) {
     return (stage >= 0 && stage < MLP_NUM_STAGES) ? kStageNames[stage] : "";

@@ -200,3 +200,60 @@ class CropAndPadMask(Layer):
         config = super().get_config()
         config.update({"output": self.output})
         return config
+
+
+@register
+class EncodeImageContent(Layer):
+    """[images uint8 [B,H,W,3]] -> the JPEG file of images[0] as a one-element list of `bytes` (the
+    reference returns a string tensor of shape [1]): misc.py:343-351 = tf.io.encode_jpeg(inputs[0]) with
+    default attributes (quality 95, 4:2:0, baseline, standard Huffman tables, JFIF 300 dpi), wired in
+    road_project/setup/serving.py:41.  The bytes equal libjpeg(-turbo)'s.  `quality` is tf.io.encode_jpeg's
+    attribute of that name.  `encode_batch` compresses every frame of the batch in the same five launches and
+    leaves the files on the device."""
+
+    def __init__(self, quality=95, **kwargs):
+        self.quality = int(quality)
+        super().__init__(**kwargs)
+
+    def encode_batch(self, images, out=None, lengths=None):
+        """images uint8 [B,H,W,3] (CUDA) -> (files uint8 [B,stride], lengths int32 [B]) on the device; file b is
+        files[b, :lengths[b]].  A negative length means the file did not fit `out`'s stride (-bytes needed)."""
+        if not isinstance(images, torch.Tensor) or not images.is_cuda:
+            raise rt.InvalidArgumentError(rt.MLP_EDLPACK, "EncodeImageContent: images must be a CUDA tensor (no CPU path)")
+        if images.dim() != 4 or int(images.shape[3]) != 3:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "EncodeImageContent: images must be [B,H,W,3]")
+        if images.dtype != torch.uint8:
+            raise rt.InvalidArgumentError(rt.MLP_EDLPACK, "EncodeImageContent: images must be uint8 (tf.io.encode_jpeg)")
+        ctx = ctx_of(images)
+        images = images.contiguous()
+        B, H, W = (int(d) for d in images.shape[:3])
+        if out is None:
+            # room for the largest possible file when that is small, else 3 bytes per pixel (a quality-95 file of
+            # pure noise takes about 1.3); a frame that would not fit reports a negative length
+            worst = int(ctx.lib.mlp_jpeg_max_bytes(H, W))
+            stride = worst if B * worst <= (64 << 20) else min(worst, 1024 + 3 * H * W)
+            out = ctx.empty((B, (stride + 15) // 16 * 16), torch.uint8)
+        if lengths is None:
+            lengths = ctx.empty((B,), torch.int32)
+        rt.check(ctx.lib.mlp_jpeg_encode(ctx.handle, ctx.view(images), B, H, W, self.quality, ctx.view(out),
+                                         int(out.shape[1]), ctx.view(lengths), ctx.stream()))
+        return out, lengths
+
+    def call(self, inputs, **kwargs):
+        images = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+        if isinstance(images, torch.Tensor) and images.dim() == 3:
+            images = images[None]
+        first = images[:1]
+        files, lengths = self.encode_batch(first)
+        n = int(lengths[0])
+        if n < 0:                                           # pathological frame: retry with the hard bound
+            ctx = ctx_of(first)
+            worst = int(ctx.lib.mlp_jpeg_max_bytes(int(first.shape[1]), int(first.shape[2])))
+            files, lengths = self.encode_batch(first, out=ctx.empty((1, (worst + 15) // 16 * 16), torch.uint8))
+            n = int(lengths[0])
+        return [files[0, :n].cpu().numpy().tobytes()]
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"quality": self.quality})
+        return config

@@ -113,13 +113,14 @@ def test_layer_configs_roundtrip_without_gpu():
     # the consumers and the steps either side of the path
     for name in ("DownSampleInput", "ResizeLike", "CrackToInstance", "SummaryOutput", "IncludeMyRoad", "CalculateInstanceSize",
                  "DrawBoxes", "DrawSegmentation", "DrawInstance", "SemanticSmoothing", "CalculateIOU", "AssignBoxes",
-                 "AssignMasks", "DetectionIOUMetric"):
+                 "AssignMasks", "DetectionIOUMetric", "EncodeImageContent"):
         assert name in objs
     colors = [[192, 32, 128], [160, 96, 0]]
     layers += [ml.DownSampleInput((270, 480)), ml.CrackToInstance(4), ml.SummaryOutput(2.5), ml.IncludeMyRoad(0.2),
                ml.CalculateInstanceSize(3.0), ml.DrawBoxes(), ml.DrawSegmentation(colors, 0.4),
                ml.DrawInstance(colors, 0.5), ml.UpSampleOutput(semantic=False), ml.SemanticSmoothing(6, 0.5),
-               ml.CalculateIOU(), ml.AssignBoxes(7), ml.AssignMasks(0.6), ml.DetectionIOUMetric(), ml.ResizeLike(False)]
+               ml.CalculateIOU(), ml.AssignBoxes(7), ml.AssignMasks(0.6), ml.DetectionIOUMetric(), ml.ResizeLike(False),
+               ml.EncodeImageContent(), ml.EncodeImageContent(quality=80)]
     for layer in layers:
         clone = type(layer).from_config(layer.get_config())
         assert clone.get_config() == layer.get_config()
@@ -154,3 +155,19 @@ def test_entry_points_reject_bad_arguments_before_touching_the_gpu(lib):
     c = rt.DrawColorsC.make([[1, 2, 3], [4, 5, 6]], 0.25)
     assert c.num_classes == 2 and c.alpha == 0.25 and list(c.rgb[1]) == [4.0, 5.0, 6.0]
     assert ctypes.sizeof(rt.DrawColorsC) == 8 + 16 * 3 * 4
+
+
+def test_jpeg_header_and_bounds_are_host_side(lib):
+    """mlp_jpeg_header / mlp_jpeg_max_bytes run on the host: the 623 header bytes (SOI, JFIF 300 dpi, DQT at the
+    requested quality, SOF0 4:2:0, the four Annex K DHT segments, SOS) equal the oracle's, which equals libjpeg's."""
+    import ctypes
+    from oracle import jpeg_oracle as jo
+    buf = (ctypes.c_uint8 * 640)()
+    for H, W, q in ((1080, 1920, 95), (512, 1024, 95), (37, 29, 30), (1, 1, 100), (65535, 65535, 1)):
+        n = lib.mlp_jpeg_header(H, W, q, buf, 640)
+        assert n == 623 and bytes(buf[:n]) == jo.headers(H, W, q).tobytes()
+    assert lib.mlp_jpeg_header(0, 10, 95, buf, 640) < 0 and lib.mlp_jpeg_header(10, 70000, 95, buf, 640) < 0
+    assert lib.mlp_jpeg_header(16, 16, 95, buf, 100) < 0
+    assert lib.mlp_jpeg_max_bytes(16, 16) == 623 + 2 * 6 * 208 + 2 and lib.mlp_jpeg_max_bytes(0, 5) == 0
+    # argument validation of the encoder happens before any CUDA call
+    assert lib.mlp_jpeg_encode(None, None, 1, 16, 16, 95, None, 4096, None, None) < 0

@@ -1,0 +1,147 @@
+"""GPU parity of the JPEG encode that ends the serving graph (EncodeImageContent = tf.io.encode_jpeg defaults,
+/root/reference/engine/layers/misc.py:343-351) through the C ABI (mlp_jpeg_encode): the files are compared BYTE FOR
+BYTE with libjpeg-turbo's own output (tests/golden/jpeg_golden.npz) and with oracle/jpeg_oracle.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jpeg_oracle as jo
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_golden.npz")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def golden_cases():
+    z = np.load(GOLDEN)
+    names = sorted({k.split("/")[0] for k in z.files})
+    return [(n, z[n + "/rgb"], z[n + "/jpeg"].tobytes()) for n in names]
+
+
+def road_like(B, H, W, seed):
+    """Smooth frames with flat overlay regions, white one-pixel rectangles and sensor noise."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.zeros((B, H, W, 3), dtype=np.uint8)
+    for b in range(B):
+        img = np.stack([120 + 90 * np.sin(xx / (23.0 + b) + yy / 31.0), 110 + 80 * np.cos(xx / 57.0 - yy / (19.0 + b)),
+                        90 + yy * (120.0 / H) + 30 * np.sin(xx / 7.0)], -1)
+        img += rng.normal(0, 5 + 2 * (b % 3), img.shape)
+        img = np.clip(img, 0, 255)
+        y0, x0 = H // 5, W // 6
+        img[y0:y0 + H // 3, x0:x0 + W // 3] = img[y0:y0 + H // 3, x0:x0 + W // 3] * 0.7 + np.array([57.6, 9.6, 38.4])
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        img[y0, x0:x0 + W // 3] = 255
+        img[y0:y0 + H // 3, x0] = 255
+        out[b] = img
+    return out
+
+
+def files_of(out, lengths):
+    out, lengths = out.cpu().numpy(), lengths.cpu().numpy()
+    assert (lengths > 0).all()
+    return [out[b, :lengths[b]].tobytes() for b in range(out.shape[0])]
+
+
+@pytest.mark.parametrize("name,rgb,want", golden_cases(), ids=[c[0] for c in golden_cases()])
+def test_layer_reproduces_libjpeg_bytes(name, rgb, want):
+    import masklab_b200 as ml
+    got = ml.EncodeImageContent()([dev(rgb[None])])
+    assert isinstance(got, list) and len(got) == 1
+    assert got[0] == want
+
+
+def test_only_the_first_frame_is_encoded_by_call():
+    import masklab_b200 as ml
+    fr = road_like(3, 40, 56, 1)
+    got = ml.EncodeImageContent()([dev(fr)])
+    assert got == [jo.encode_jpeg(fr[0])]
+
+
+@pytest.mark.parametrize("B,H,W", [(5, 48, 80), (3, 37, 61), (2, 130, 18), (4, 16, 16), (2, 72, 64), (1, 8, 1000)])
+def test_batch_against_oracle(B, H, W):
+    import masklab_b200 as ml
+    fr = road_like(B, H, W, 10 + H)
+    fr[-1] = np.random.default_rng(H).integers(0, 256, (H, W, 3), dtype=np.uint8)    # one frame of pure noise
+    out, lengths = ml.EncodeImageContent().encode_batch(dev(fr))
+    for b, f in enumerate(files_of(out, lengths)):
+        assert f == jo.encode_jpeg(fr[b]), f"frame {b}"
+
+
+@pytest.mark.parametrize("quality", [1, 25, 50, 75, 100])
+def test_quality_attribute(quality):
+    import masklab_b200 as ml
+    fr = road_like(2, 45, 70, quality)
+    out, lengths = ml.EncodeImageContent(quality=quality).encode_batch(dev(fr))
+    for b, f in enumerate(files_of(out, lengths)):
+        assert f == jo.encode_jpeg(fr[b], quality)
+
+
+def test_byte_stuffing_and_long_codes():
+    """Saturated one-pixel checkerboards and full-range noise: 16-bit codes, ZRL runs, many 0xFF bytes in the scan."""
+    import masklab_b200 as ml
+    rng = np.random.default_rng(5)
+    H, W = 64, 96
+    fr = np.zeros((4, H, W, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    c = (((yy + xx) % 2) * 255).astype(np.uint8)
+    fr[0] = np.stack([c, 255 - c, c], -1)
+    fr[1] = rng.integers(0, 2, (H, W, 3)).astype(np.uint8) * 255
+    fr[2] = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    fr[3, ::8, ::8] = 255                                               # sparse impulses: long zero runs
+    out, lengths = ml.EncodeImageContent(quality=100).encode_batch(dev(fr))
+    files = files_of(out, lengths)
+    for b, f in enumerate(files):
+        assert f == jo.encode_jpeg(fr[b], 100), f"frame {b}"
+    assert sum(f[623:].count(b"\xff\x00") for f in files) > 50
+
+
+def test_too_small_output_reports_the_size_needed():
+    import masklab_b200 as ml
+    fr = np.random.default_rng(6).integers(0, 256, (2, 64, 64, 3), dtype=np.uint8)
+    fr[1] = 0
+    want = [len(jo.encode_jpeg(fr[b])) for b in range(2)]
+    out = torch.full((2, 1024), 7, dtype=torch.uint8, device="cuda")
+    _, lengths = ml.EncodeImageContent().encode_batch(dev(fr), out=out)
+    lengths = lengths.cpu().numpy()
+    assert lengths[0] == -want[0] and lengths[1] == want[1] and want[1] <= 1024
+    assert (out[0].cpu().numpy() == 7).all()                            # nothing written for the frame that did not fit
+    assert out[1, :want[1]].cpu().numpy().tobytes() == jo.encode_jpeg(fr[1])
+
+
+def test_rejects_what_tf_rejects():
+    import masklab_b200 as ml
+    with pytest.raises(ml.InvalidArgumentError):
+        ml.EncodeImageContent().encode_batch(torch.zeros((1, 8, 8, 3), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ml.InvalidArgumentError):
+        ml.EncodeImageContent().encode_batch(torch.zeros((1, 8, 8, 4), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ml.InvalidArgumentError):
+        ml.EncodeImageContent().encode_batch(torch.zeros((1, 8, 8, 3), dtype=torch.uint8))
+
+
+@pytest.mark.parametrize("H,W", [(512, 1024), (1080, 1920)])
+def test_full_frames(H, W):
+    """cfg-2 and cfg-5 frame sizes (1080 = 67.5 MCU rows: a row of dummy luma blocks): byte-identical files, and the
+    decoded file is the frame again (when a JPEG decoder is importable where the tests run)."""
+    import masklab_b200 as ml
+    fr = road_like(2, H, W, 7)
+    out, lengths = ml.EncodeImageContent().encode_batch(dev(fr))
+    files = files_of(out, lengths)
+    for b in range(2):
+        assert files[b] == jo.encode_jpeg(fr[b]), f"frame {b}"
+    try:
+        import io
+        from PIL import Image
+    except ImportError:
+        return
+    back = np.asarray(Image.open(io.BytesIO(files[0])).convert("RGB")).astype(int)
+    assert back.shape == (H, W, 3) and np.abs(back - fr[0]).mean() < 6
+    buf = io.BytesIO()
+    Image.fromarray(fr[1]).save(buf, format="JPEG", quality=95, dpi=(300, 300))
+    assert buf.getvalue() == files[1]                                   # a live libjpeg-turbo agrees as well
