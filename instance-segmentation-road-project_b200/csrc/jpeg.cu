@@ -5,20 +5,22 @@
 // baseline sequential, JFIF 300x300 dpi.  All of it is integer work, so the byte stream is reproduced EXACTLY
 // (oracle/jpeg_oracle.py restates it and is pinned byte for byte against libjpeg-turbo's own output).
 //
-// Five launches per batch of frames, everything stays on the device:
+// Six launches per batch of frames, everything stays on the device:
 //   jpeg_dct_kernel     one CTA per four MCUs of a row: colour conversion (jccolor.c fixed point), h2v2 chroma
 //                       down-sampling with the alternating 1,2 bias (jcsample.c), edge replication and dummy blocks
 //                       (jcprepct.c / jccoefct.c), jpeg_fdct_islow in registers with conflict-free shared-memory
-//                       transposes (jfdctint.c), quantisation (jcdctmgr.c); writes zigzag int16 coefficients and per
-//                       block (AC bit length, DC)                       HBM: 3 B/px in, 3 B/px out
-//   jpeg_scan_kernel    one CTA per frame: DC differences -> bit length of every block -> exclusive scan (bit offset
-//                       of every block in the frame's scan), zero-fills exactly the words the scan will occupy
-//   jpeg_huff_kernel    one warp per 8x8 block: every lane composes the bit field of two coefficients (ZRL run, run/size
-//                       code, value bits; jchuff.c encode_one_block), a warp scan places them, the block is assembled
-//                       in shared memory and stored at its bit offset (only the two boundary words are atomics)
-//   jpeg_ffscan_kernel  one CTA per frame: 0xFF bytes per 4 KB chunk of the scan + exclusive scan (byte stuffing moves
-//                       every later byte) and the final length
-//   jpeg_stuff_kernel   header (jcmarker.c), scan bytes with a 0x00 after every 0xFF, EOI
+//                       transposes (jfdctint.c), quantisation by exact reciprocal multiplication (jcdctmgr.c); writes
+//                       zigzag int16 coefficients, the 64-bit non-zero mask and the DC of every block
+//   jpeg_len_kernel     one THREAD per 8x8 block walks the set bits of its mask (jchuff.c encode_one_block without
+//                       output): bit length of the block, exclusive scan inside the CTA, one total per CTA
+//   jpeg_offsets_kernel per frame: scan of the CTA totals -> bit offset of every CTA, and zero-fill of exactly the
+//                       words the scan will occupy (spread over 16 CTAs per frame), 1-padding of the last byte
+//   jpeg_huff_kernel    one thread per block again: DC difference, ZRL / run-size codes and value bits shifted into
+//                       a 64-bit accumulator, whole words stored at the block's bit offset (only the first and last
+//                       word of a block are atomics - neighbours share them)
+//   jpeg_ffcount_kernel 0xFF bytes per 4 KB chunk of the scan (byte stuffing moves every later byte)
+//   jpeg_stuff_kernel   header (jcmarker.c), scan bytes with a 0x00 after every 0xFF, EOI, length
+// The coefficient passes are integer-issue bound, not HBM bound (3 B/px in, 3 B/px of coefficients out and back).
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -62,10 +64,12 @@ const uint8_t kAcChromaVals[162] = {
 constexpr int kHeaderBytes = 623;
 constexpr int kMaxBlockWords = 52;            // 20 (DC) + 63 * 26 (AC) = 1658 bits
 constexpr int kChunkBytes = 4096;             // byte-stuffing chunk of the scan
+constexpr int kPartBlocks = 256;              // blocks per CTA of the length / Huffman passes
 
 // Everything a launch needs that depends only on (H, W, quality): passed by value (kernel parameter space).
 struct JpegTables {
     uint16_t div[2][64];       // natural order, q << 3 (jcdctmgr.c start_pass_fdctmgr)
+    uint32_t rcp[2][64];       // ceil(2^32 / div): n / div == umulhi(n, rcp) for every n < 2^16
     uint8_t izz[64];           // natural index -> zigzag position
     uint32_t ac[2][256];       // symbol -> length << 16 | code (jchuff.c jpeg_make_c_derived_tbl)
     uint32_t dc[2][12];
@@ -81,6 +85,7 @@ struct JpegGeom {
     int c_real_rows;                // chroma rows that come from real pixel rows: ceil(H / 2)
     int64_t words_cap;              // 32-bit words reserved for one frame's unstuffed scan
     int chunks_cap;                 // 4 KB chunks of that reservation
+    int parts;                      // groups of kPartBlocks blocks per frame (two-level scan of the bit lengths)
 };
 
 void zigzag_natural(uint8_t* nat_of_zz) {     // jutils.c jpeg_natural_order
@@ -123,7 +128,10 @@ void build_tables(int H, int W, int quality, JpegTables* T, JpegHeader* hdr) {
     memset(T, 0, sizeof(*T));
     for (int z = 0; z < 64; ++z) T->izz[nat[z]] = (uint8_t)z;
     for (int t = 0; t < 2; ++t)
-        for (int i = 0; i < 64; ++i) T->div[t][i] = (uint16_t)(q[t][i] << 3);
+        for (int i = 0; i < 64; ++i) {
+            T->div[t][i] = (uint16_t)(q[t][i] << 3);
+            T->rcp[t][i] = (uint32_t)((((uint64_t)1 << 32) + T->div[t][i] - 1) / T->div[t][i]);
+        }
     derive_huff(kDcLumaBits, kDcVals, T->dc[0]);
     derive_huff(kDcChromaBits, kDcVals, T->dc[1]);
     derive_huff(kAcLumaBits, kAcLumaVals, T->ac[0]);
@@ -165,6 +173,7 @@ JpegGeom make_geom(int H, int W) {
     g.words_cap = (int64_t)g.n_blk * kMaxBlockWords + 4;
     g.words_cap = (g.words_cap + 3) & ~(int64_t)3;
     g.chunks_cap = (int)((g.words_cap * 4 + kChunkBytes - 1) / kChunkBytes);
+    g.parts = (g.n_blk + kPartBlocks - 1) / kPartBlocks;
     return g;
 }
 
@@ -211,112 +220,106 @@ __device__ __forceinline__ void fdct8(int (&d)[8]) {
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(abs(v)); }
 
-// Bit length of the AC part of one block held as (position lane, position lane + 32) per lane.
-// ac_len: smem table of code lengths for this block's component.
-__device__ __forceinline__ int ac_bit_length(int c0, int c1, int lane, const uint8_t* ac_len) {
-    const uint32_t lo = __ballot_sync(0xffffffffu, c0 != 0) & ~1u;          // position 0 is the DC slot
-    const uint32_t hi = __ballot_sync(0xffffffffu, c1 != 0);
-    const uint64_t nz = ((uint64_t)hi << 32) | lo;
-    const int zrl = ac_len[0xF0];
-    int bits = 0;
-    if (lane > 0 && c0 != 0) {
-        const uint32_t below = lo & ((1u << lane) - 1u);
-        const int prev = below ? 31 - __clz(below) : 0;
-        const int run = lane - prev - 1, nb = nbits_of(c0);
-        bits += (run >> 4) * zrl + ac_len[((run & 15) << 4) | nb] + nb;
-    }
-    if (c1 != 0) {
-        const uint64_t below = nz & ((1ull << (lane + 32)) - 1ull);
-        const int prev = below ? 63 - __clzll(below) : 0;
-        const int run = lane + 32 - prev - 1, nb = nbits_of(c1);
-        bits += (run >> 4) * zrl + ac_len[((run & 15) << 4) | nb] + nb;
-    } else if (lane == 31) {
-        bits += ac_len[0x00];                                               // EOB
-    }
-    return __reduce_add_sync(0xffffffffu, bits);
-}
-
-constexpr int kDctThreads = 256;
+constexpr int kDctThreads = 192;
 constexpr int kMcuPerCta = 4;
+
+__device__ __forceinline__ void store_luma(int (*ws)[72], int m, int yy, int xx, int y) {
+    ws[m * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 9 + (xx & 7)] = y - 128;
+}
 
 __global__ void __launch_bounds__(kDctThreads)
 jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_constant__ JpegTables T,
-                int16_t* __restrict__ coefs, uint32_t* __restrict__ meta) {
+                int16_t* __restrict__ coefs, uint64_t* __restrict__ nzmask, int16_t* __restrict__ dcs) {
     __shared__ __align__(16) uint8_t raw[16][kMcuPerCta * 48];
     __shared__ int ws[kMcuPerCta * 6][72];                 // 8 rows of 9: both passes are bank-conflict free
     __shared__ __align__(16) int16_t outc[kMcuPerCta * 6][64];
-    __shared__ uint8_t s_aclen[2][256];
     __shared__ uint8_t s_izz[64];
-    __shared__ uint16_t s_div[2][64];
+    __shared__ uint16_t s_half[2][64];
+    __shared__ uint32_t s_rcp[2][64];
 
     const int t = threadIdx.x;
     const int b = blockIdx.z, my = blockIdx.y, mx0 = blockIdx.x * kMcuPerCta;
     const int n_here = min(kMcuPerCta, G.mcu_cols - mx0);
     const uint8_t* img = frames + (int64_t)b * G.H * G.W * 3;
 
-    for (int i = t; i < 512; i += kDctThreads) s_aclen[i >> 8][i & 255] = (uint8_t)(T.ac[i >> 8][i & 255] >> 16);
     if (t < 64) s_izz[t] = T.izz[t];
-    if (t < 128) s_div[t >> 6][t & 63] = T.div[t >> 6][t & 63];
+    if (t < 128) {
+        s_half[t >> 6][t & 63] = T.div[t >> 6][t & 63] >> 1;
+        s_rcp[t >> 6][t & 63] = T.rcp[t >> 6][t & 63];
+    }
 
     // ---- phase 0: the 16 x 64 pixel strip of this CTA, 16-byte loads when rows are aligned and inside the frame
     const bool fast = (G.W % 16 == 0) && (my * 16 + 16 <= G.H) && (n_here == kMcuPerCta) &&
                       ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
     if (fast) {
-        if (t < 16 * 12) {
-            const int row = t / 12, seg = t - row * 12;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((int64_t)(my * 16 + row) * G.W + mx0 * 16) * 3) + seg);
-            *reinterpret_cast<uint4*>(&raw[row][seg * 16]) = v;
-        }
+        const int row = t / 12, seg = t - row * 12;          // 16 rows x 12 vectors = 192 threads
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((int64_t)(my * 16 + row) * G.W + mx0 * 16) * 3) + seg);
+        *reinterpret_cast<uint4*>(&raw[row][seg * 16]) = v;
     }
     __syncthreads();
 
-    // ---- phase 1: one 2x2 quad per thread: four luma samples, one Cb and one Cr sample
-    const int m = t >> 6, q = t & 63, qy = q >> 3, qx = q & 7;
-    if (m < n_here) {
-        int cbs = 0, crs = 0;
-        const int gy = my * 16 + 2 * qy, gx = (mx0 + m) * 16 + 2 * qx;
+    // ---- phase 1: one warp per MCU, a 4 x 2 pixel patch per lane: eight luma samples, two Cb and two Cr samples
+    if (t < 128 && (t >> 5) < n_here) {
+        const int m = t >> 5, l = t & 31, qy = l >> 2, qp = l & 3;
+        const int gy = my * 16 + 2 * qy, gx = (mx0 + m) * 16 + 4 * qp;
+        int cbs[2] = {0, 0}, crs[2] = {0, 0};
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
+            uint32_t w[3];
+            if (fast) {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(&raw[2 * qy + dy][m * 48 + qp * 12]);
+                w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
+            } else {
+                const int yy = min(gy + dy, G.H - 1);
+                uint8_t px[12];
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                int r, g, bl;
-                if (fast) {
-                    const uint8_t* p = &raw[2 * qy + dy][m * 48 + (2 * qx + dx) * 3];
-                    r = p[0]; g = p[1]; bl = p[2];
-                } else {
-                    const int yy = min(gy + dy, G.H - 1), xx = min(gx + dx, G.W - 1);
-                    const uint8_t* p = img + ((int64_t)yy * G.W + xx) * 3;
-                    r = __ldg(p); g = __ldg(p + 1); bl = __ldg(p + 2);
+                for (int dx = 0; dx < 4; ++dx) {
+                    const uint8_t* p = img + ((int64_t)yy * G.W + min(gx + dx, G.W - 1)) * 3;
+                    px[dx * 3] = __ldg(p); px[dx * 3 + 1] = __ldg(p + 1); px[dx * 3 + 2] = __ldg(p + 2);
                 }
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    w[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
+            }
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx) {
+                const int o = dx * 3;
+                const int r = (w[o >> 2] >> (8 * (o & 3))) & 255;
+                const int g = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 255;
+                const int bl = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 255;
                 int y, cb, cr;
                 rgb_to_ycc(r, g, bl, y, cb, cr);
-                const int yy = 2 * qy + dy, xx = 2 * qx + dx;
-                ws[m * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 9 + (xx & 7)] = y - 128;
-                cbs += cb; crs += cr;
+                store_luma(ws, m, 2 * qy + dy, 4 * qp + dx, y);
+                cbs[dx >> 1] += cb; crs[dx >> 1] += cr;
             }
         }
         if (gy >= G.H) {
             // chroma rows below the last real row group replicate the last DOWN-SAMPLED row (jcprepct.c pads the
             // down-sampler's output), which is not what the clamped luma rows give when H is even
             const int r0 = 2 * (G.c_real_rows - 1), r1 = min(r0 + 1, G.H - 1);
-            cbs = 0; crs = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int yy = (k >> 1) ? r1 : r0, xx = min(gx + (k & 1), G.W - 1);
-                const uint8_t* p = img + ((int64_t)yy * G.W + xx) * 3;
-                int y, cb, cr;
-                rgb_to_ycc(__ldg(p), __ldg(p + 1), __ldg(p + 2), y, cb, cr);
-                cbs += cb; crs += cr;
+            for (int h = 0; h < 2; ++h) {
+                cbs[h] = 0; crs[h] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = (k >> 1) ? r1 : r0, xx = min(gx + 2 * h + (k & 1), G.W - 1);
+                    const uint8_t* p = img + ((int64_t)yy * G.W + xx) * 3;
+                    int y, cb, cr;
+                    rgb_to_ycc(__ldg(p), __ldg(p + 1), __ldg(p + 2), y, cb, cr);
+                    cbs[h] += cb; crs[h] += cr;
+                }
             }
         }
-        const int bias = 1 + (qx & 1);                       // h2v2_downsample: 1, 2, 1, 2, ...
-        ws[m * 6 + 4][qy * 9 + qx] = ((cbs + bias) >> 2) - 128;
-        ws[m * 6 + 5][qy * 9 + qx] = ((crs + bias) >> 2) - 128;
+        // h2v2_downsample: bias 1, 2, 1, 2, ... along the row; this lane owns an even and an odd column
+        ws[m * 6 + 4][qy * 9 + 2 * qp] = ((cbs[0] + 1) >> 2) - 128;
+        ws[m * 6 + 4][qy * 9 + 2 * qp + 1] = ((cbs[1] + 2) >> 2) - 128;
+        ws[m * 6 + 5][qy * 9 + 2 * qp] = ((crs[0] + 1) >> 2) - 128;
+        ws[m * 6 + 5][qy * 9 + 2 * qp + 1] = ((crs[1] + 2) >> 2) - 128;
     }
     __syncthreads();
 
     // ---- phase 2: row pass (thread = block * 8 + row; address 9 * t + j: no bank conflicts)
-    if (t < kMcuPerCta * 48) {
+    {
         int d[8];
         int* row = &ws[t >> 3][(t & 7) * 9];
 #pragma unroll
@@ -328,7 +331,7 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
     __syncthreads();
 
     // ---- phase 3: column pass + quantisation, zigzag order
-    if (t < kMcuPerCta * 48) {
+    {
         const int blk = t >> 3, c = t & 7, k = blk % 6, mm = blk / 6;
         bool dummy = false;
         if (k < 4) {
@@ -339,12 +342,12 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
 #pragma unroll
         for (int r = 0; r < 8; ++r) d[r] = ws[blk][r * 9 + c];
         fdct8<false>(d);
-        const uint16_t* dv = s_div[k >= 4];
+        const int tb = k >= 4;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int n = r * 8 + c;
-            const int qv = dv[n];
-            const int mag = (int)((unsigned)(abs(d[r]) + (qv >> 1)) / (unsigned)qv);
+            // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16, so the reciprocal is exact
+            const int mag = (int)__umulhi((uint32_t)(abs(d[r]) + s_half[tb][n]), s_rcp[tb][n]);
             outc[blk][s_izz[n]] = dummy ? (int16_t)0 : (int16_t)(d[r] < 0 ? -mag : mag);
         }
     }
@@ -360,28 +363,29 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
     }
     __syncthreads();
 
-    // ---- phase 4: coefficients out (contiguous: the MCUs of a CTA are neighbours in scan order), AC bit lengths
+    // ---- phase 4: coefficients out (contiguous: the MCUs of a CTA are neighbours in scan order), masks, DCs
     const int64_t mcu0 = (int64_t)b * G.n_mcu + (int64_t)my * G.mcu_cols + mx0;
     if (t < n_here * 48)
         reinterpret_cast<uint4*>(coefs + mcu0 * 384)[t] = reinterpret_cast<const uint4*>(&outc[0][0])[t];
     const int warp = t >> 5, lane = t & 31;
     for (int blk = warp; blk < n_here * 6; blk += kDctThreads / 32) {
         const int c0 = outc[blk][lane], c1 = outc[blk][lane + 32];
-        const int bits = ac_bit_length(c0, c1, lane, s_aclen[(blk % 6) >= 4]);
-        if (lane == 0) meta[mcu0 * 6 + blk] = ((uint32_t)bits << 16) | (uint32_t)(uint16_t)(int16_t)c0;
+        const uint32_t lo = __ballot_sync(0xffffffffu, c0 != 0) & ~1u;      // position 0 is the DC slot
+        const uint32_t hi = __ballot_sync(0xffffffffu, c1 != 0);
+        if (lane == 0) {
+            nzmask[mcu0 * 6 + blk] = ((uint64_t)hi << 32) | lo;
+            dcs[mcu0 * 6 + blk] = (int16_t)c0;
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------------- scan
+// --------------------------------------------------------------------------------------- lengths and offsets
 __device__ __forceinline__ int pred_block(int i) {          // previous block of the same component, -1: none
     const int k = i % 6;
     if (k >= 1 && k <= 3) return i - 1;
     if (i < 6) return -1;
     return k == 0 ? i - 3 : i - 6;
 }
-__device__ __forceinline__ int dc_of(uint32_t m) { return (int)(int16_t)(m & 0xffffu); }
-
-constexpr int kScanThreads = 1024;
 
 // block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = the sum
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
@@ -410,214 +414,211 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return s_warp[warp] + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-jpeg_scan_kernel(const uint32_t* __restrict__ meta, JpegGeom G, const __grid_constant__ JpegTables T,
-                 uint32_t* __restrict__ blk_off, uint32_t* __restrict__ frame_bits, uint32_t* __restrict__ stream) {
-    __shared__ uint32_t s_warp[33];
+__global__ void __launch_bounds__(kPartBlocks)
+jpeg_len_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
+                JpegGeom G, const __grid_constant__ JpegTables T, uint32_t* __restrict__ loc_off,
+                uint32_t* __restrict__ part_bits) {
+    __shared__ uint8_t s_aclen[2][256];
     __shared__ uint8_t s_dclen[2][12];
-    const int b = blockIdx.x, t = threadIdx.x;
+    __shared__ uint32_t s_warp[33];
+    const int t = threadIdx.x, b = blockIdx.y;
+    for (int i = t; i < 512; i += kPartBlocks) s_aclen[i >> 8][i & 255] = (uint8_t)(T.ac[i >> 8][i & 255] >> 16);
     if (t < 24) s_dclen[t / 12][t % 12] = (uint8_t)(T.dc[t / 12][t % 12] >> 16);
     __syncthreads();
-    const uint32_t* mt = meta + (int64_t)b * G.n_blk;
-    uint32_t* off = blk_off + (int64_t)b * G.n_blk;
-    const int per = (G.n_blk + kScanThreads - 1) / kScanThreads;
-    const int i0 = min(t * per, G.n_blk), i1 = min(i0 + per, G.n_blk);
-    auto length_of = [&](int i) -> uint32_t {
-        const uint32_t mi = __ldg(mt + i);
+    const int i = blockIdx.x * kPartBlocks + t;             // block index inside the frame
+    uint32_t bits = 0;
+    if (i < G.n_blk) {
+        const int64_t gb = (int64_t)b * G.n_blk + i;
+        const int chroma = (i % 6) >= 4;
         const int p = pred_block(i);
-        const int diff = dc_of(mi) - (p >= 0 ? dc_of(__ldg(mt + p)) : 0);
-        const int nb = nbits_of(diff);
-        return (mi >> 16) + s_dclen[(i % 6) >= 4][nb] + nb;
-    };
+        const int diff = (int)__ldg(dcs + gb) - (p >= 0 ? (int)__ldg(dcs + gb - i + p) : 0);
+        int nb = nbits_of(diff);
+        bits = s_dclen[chroma][nb] + nb;
+        const uint8_t* al = s_aclen[chroma];
+        const int16_t* cf = coefs + gb * 64;
+        uint64_t mask = __ldg(nzmask + gb);
+        int prev = 0;
+        while (mask) {
+            const int k = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            nb = nbits_of((int)__ldg(cf + k));
+            const int run = k - prev - 1;
+            bits += (run >> 4) * al[0xF0] + al[((run & 15) << 4) | nb] + nb;
+            prev = k;
+        }
+        if (prev != 63) bits += al[0x00];                   // EOB
+    }
+    uint32_t total;
+    const uint32_t exc = block_exclusive_scan(bits, s_warp, &total);
+    if (i < G.n_blk) loc_off[(int64_t)b * G.n_blk + i] = exc;
+    if (t == 0) part_bits[(int64_t)b * G.parts + blockIdx.x] = total;
+}
+
+constexpr int kZeroCtas = 16;
+constexpr int kOffThreads = 256;
+
+__global__ void __launch_bounds__(kOffThreads)
+jpeg_offsets_kernel(const uint32_t* __restrict__ part_bits, JpegGeom G, uint32_t* __restrict__ part_off,
+                    uint32_t* __restrict__ frame_bits, uint32_t* __restrict__ stream) {
+    __shared__ uint32_t s_warp[33];
+    const int t = threadIdx.x, z = blockIdx.x, b = blockIdx.y;
+    const uint32_t* pb = part_bits + (int64_t)b * G.parts;
+    const int per = (G.parts + kOffThreads - 1) / kOffThreads;
+    const int i0 = min(t * per, G.parts), i1 = min(i0 + per, G.parts);
     uint32_t sum = 0;
-    for (int i = i0; i < i1; ++i) sum += length_of(i);
+    for (int i = i0; i < i1; ++i) sum += __ldg(pb + i);
     uint32_t total;
     uint32_t run = block_exclusive_scan(sum, s_warp, &total);
-    for (int i = i0; i < i1; ++i) {
-        off[i] = run;
-        run += length_of(i);
+    if (z == 0) {
+        for (int i = i0; i < i1; ++i) {
+            part_off[(int64_t)b * G.parts + i] = run;
+            run += __ldg(pb + i);
+        }
+        if (t == 0) frame_bits[b] = total;
     }
-    // the scan of this frame occupies `total` bits: clear exactly those words (the Huffman pass ORs into them) and
-    // pad the last byte with 1-bits (jchuff.c flush_bits)
+    // the scan of this frame occupies `total` bits: clear exactly those words (the Huffman pass ORs into its
+    // boundary words) and pad the last byte with 1-bits (jchuff.c flush_bits); kZeroCtas CTAs share the frame
     uint32_t* st = stream + (int64_t)b * G.words_cap;
-    const uint32_t nwords = (total + 31) / 32 + 1;
+    const uint32_t nvec = ((total + 31) / 32 + 1 + 3) / 4;
+    const uint32_t slice = (nvec + kZeroCtas - 1) / kZeroCtas;
+    const uint32_t v0 = z * slice, v1 = min(v0 + slice, nvec);
     uint4* st4 = reinterpret_cast<uint4*>(st);
-    for (uint32_t i = t; i < (nwords + 3) / 4; i += kScanThreads) st4[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    if (t == 0) {
-        frame_bits[b] = total;
-        const uint32_t pad = (8 - (total & 7)) & 7;
-        if (pad) st[total >> 5] = ((1u << pad) - 1u) << (32 - (total & 31) - pad);
+    for (uint32_t i = v0 + t; i < v1; i += kOffThreads) st4[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t pad_word = total >> 5, pad = (8 - (total & 7)) & 7;
+    if (pad && (pad_word >> 2) >= v0 && (pad_word >> 2) < v1) {
+        __syncthreads();
+        if (t == 0) st[pad_word] = ((1u << pad) - 1u) << (32 - (total & 31) - pad);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- Huffman
-constexpr int kHuffWarps = 8;
-constexpr int kStageWords = 56;
-
-__device__ __forceinline__ void field_append(uint64_t& f, int& n, uint32_t code_len) {
-    const int len = (int)(code_len >> 16);
-    f = (f << len) | (code_len & 0xffffu);
-    n += len;
-}
-
-// ORs the `n` low bits of `f` (MSB first) into the word array at bit position q
-__device__ __forceinline__ void stage_put(uint32_t* words, uint32_t q, uint64_t f, int n) {
-    if (n == 0) return;
-    const uint64_t F = f << (64 - n);
-    const uint32_t hi = (uint32_t)(F >> 32), lo = (uint32_t)F;
-    const uint32_t sh = q & 31, w = q >> 5;
-    atomicOr(&words[w], hi >> sh);
-    if (sh + n > 32) atomicOr(&words[w + 1], __funnelshift_r(lo, hi, sh));
-    if (sh + n > 64) atomicOr(&words[w + 2], __funnelshift_r(0u, lo, sh));
-}
-
-__global__ void __launch_bounds__(kHuffWarps * 32)
-jpeg_huff_kernel(const int16_t* __restrict__ coefs, const uint32_t* __restrict__ meta,
-                 const uint32_t* __restrict__ blk_off, JpegGeom G, const __grid_constant__ JpegTables T, int batch,
-                 uint32_t* __restrict__ stream) {
+__global__ void __launch_bounds__(kPartBlocks)
+jpeg_huff_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
+                 const uint32_t* __restrict__ loc_off, const uint32_t* __restrict__ part_off, JpegGeom G,
+                 const __grid_constant__ JpegTables T, uint32_t* __restrict__ stream) {
     __shared__ uint32_t s_ac[2][256];
     __shared__ uint32_t s_dc[2][12];
-    __shared__ uint32_t s_stage[kHuffWarps][kStageWords];
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    for (int i = t; i < 512; i += kHuffWarps * 32) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
+    const int t = threadIdx.x, b = blockIdx.y;
+    for (int i = t; i < 512; i += kPartBlocks) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
     if (t < 24) s_dc[t / 12][t % 12] = T.dc[t / 12][t % 12];
     __syncthreads();
-
-    const int64_t total_blk = (int64_t)batch * G.n_blk;
-    uint32_t* stage = s_stage[warp];
-    for (int64_t gb = (int64_t)blockIdx.x * kHuffWarps + warp; gb < total_blk; gb += (int64_t)gridDim.x * kHuffWarps) {
-        const int b = (int)(gb / G.n_blk), i = (int)(gb - (int64_t)b * G.n_blk);
-        const int chroma = (i % 6) >= 4;
-        const int16_t* cf = coefs + gb * 64;
-        int c0 = cf[lane];
-        const int c1 = cf[lane + 32];
-        const uint32_t* ac = s_ac[chroma];
-        stage[lane] = 0;
-        if (lane < kStageWords - 32) stage[lane + 32] = 0;
-
-        const uint32_t lo = __ballot_sync(0xffffffffu, c0 != 0) & ~1u;
-        const uint32_t hi = __ballot_sync(0xffffffffu, c1 != 0);
-        const uint64_t nz = ((uint64_t)hi << 32) | lo;
-
-        uint64_t f0 = 0, f1 = 0;
-        int n0 = 0, n1 = 0;
-        if (lane == 0) {                                      // DC difference (jchuff.c encode_one_block)
-            const int p = pred_block(i);
-            const int diff = c0 - (p >= 0 ? dc_of(__ldg(meta + (int64_t)b * G.n_blk + p)) : 0);
-            const int nb = nbits_of(diff);
-            field_append(f0, n0, s_dc[chroma][nb]);
-            f0 = (f0 << nb) | (uint32_t)((diff < 0 ? diff - 1 : diff) & ((1 << nb) - 1));
-            n0 += nb;
-        } else if (c0 != 0) {
-            const uint32_t below = lo & ((1u << lane) - 1u);
-            const int prev = below ? 31 - __clz(below) : 0;
-            const int run = lane - prev - 1, nb = nbits_of(c0);
-            for (int z = 0; z < (run >> 4); ++z) field_append(f0, n0, ac[0xF0]);
-            field_append(f0, n0, ac[((run & 15) << 4) | nb]);
-            f0 = (f0 << nb) | (uint32_t)((c0 < 0 ? c0 - 1 : c0) & ((1 << nb) - 1));
-            n0 += nb;
+    const int i = blockIdx.x * kPartBlocks + t;
+    if (i >= G.n_blk) return;
+    const int64_t gb = (int64_t)b * G.n_blk + i;
+    const int chroma = (i % 6) >= 4;
+    const uint32_t start = __ldg(part_off + (int64_t)b * G.parts + blockIdx.x) + __ldg(loc_off + gb);
+    uint32_t* dst = stream + (int64_t)b * G.words_cap + (start >> 5);
+    // bits enter at the low end of `acc`; `nacc` counts them including the phantom bits of the first word that
+    // belong to the previous block.  A full word leaves as soon as 32 bits are there.
+    uint64_t acc = 0;
+    int nacc = (int)(start & 31);
+    bool first = true;
+    auto emit = [&](uint32_t bits, int len) {
+        acc = (acc << len) | bits;
+        nacc += len;
+        if (nacc >= 32) {
+            nacc -= 32;
+            const uint32_t w = (uint32_t)(acc >> nacc);
+            if (first) { atomicOr(dst, w); first = false; }
+            else *dst = w;
+            ++dst;
+            acc &= (1ull << nacc) - 1ull;
         }
-        if (c1 != 0) {
-            const uint64_t below = nz & ((1ull << (lane + 32)) - 1ull);
-            const int prev = below ? 63 - __clzll(below) : 0;
-            const int run = lane + 32 - prev - 1, nb = nbits_of(c1);
-            for (int z = 0; z < (run >> 4); ++z) field_append(f1, n1, ac[0xF0]);
-            field_append(f1, n1, ac[((run & 15) << 4) | nb]);
-            f1 = (f1 << nb) | (uint32_t)((c1 < 0 ? c1 - 1 : c1) & ((1 << nb) - 1));
-            n1 += nb;
-        } else if (lane == 31) {
-            field_append(f1, n1, ac[0x00]);                   // EOB
-        }
-        // positions 0..31 come before 32..63: one warp scan over the packed pair of lengths
-        uint32_t inc = (uint32_t)n0 | ((uint32_t)n1 << 16);
-        const uint32_t own = inc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t exc = inc - own;
-        const uint32_t len0 = tot & 0xffffu, blk_len = len0 + (tot >> 16);
-        const uint32_t start = __ldg(blk_off + gb);
-        const uint32_t sh0 = start & 31;
-        __syncwarp();
-        stage_put(stage, sh0 + (exc & 0xffffu), f0, n0);
-        stage_put(stage, sh0 + len0 + (exc >> 16), f1, n1);
-        __syncwarp();
-        uint32_t* dst = stream + (int64_t)b * G.words_cap + (start >> 5);
-        const int nwords = (int)((sh0 + blk_len + 31) >> 5);
-        for (int j = lane; j < nwords; j += 32) {
-            const uint32_t v = stage[j];
-            if (j == 0 || j == nwords - 1) atomicOr(dst + j, v);
-            else dst[j] = v;
-        }
-        __syncwarp();
+    };
+    {   // DC difference (jchuff.c encode_one_block)
+        const int p = pred_block(i);
+        const int diff = (int)__ldg(dcs + gb) - (p >= 0 ? (int)__ldg(dcs + gb - i + p) : 0);
+        const int nb = nbits_of(diff);
+        const uint32_t cl = s_dc[chroma][nb];
+        emit(((cl & 0xffffu) << nb) | (uint32_t)((diff < 0 ? diff - 1 : diff) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
     }
+    const uint32_t* ac = s_ac[chroma];
+    const int16_t* cf = coefs + gb * 64;
+    uint64_t mask = __ldg(nzmask + gb);
+    int prev = 0;
+    while (mask) {
+        const int k = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const int v = (int)__ldg(cf + k);
+        const int nb = nbits_of(v);
+        const int run = k - prev - 1;
+        for (int zr = run >> 4; zr > 0; --zr) emit(ac[0xF0] & 0xffffu, (int)(ac[0xF0] >> 16));
+        const uint32_t cl = ac[((run & 15) << 4) | nb];
+        emit(((cl & 0xffffu) << nb) | (uint32_t)((v < 0 ? v - 1 : v) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
+        prev = k;
+    }
+    if (prev != 63) emit(ac[0x00] & 0xffffu, (int)(ac[0x00] >> 16));     // EOB
+    if (nacc > 0) atomicOr(dst, (uint32_t)(acc << (32 - nacc)));
 }
 
 // ------------------------------------------------------------------------------------------ byte stuffing
 __device__ __forceinline__ int count_ff(uint32_t w) { return __popc(__vcmpeq4(w, 0xffffffffu)) >> 3; }
 
-__global__ void __launch_bounds__(kScanThreads)
-jpeg_ffscan_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ frame_bits, JpegGeom G,
-                   uint32_t* __restrict__ chunk_ff, int64_t out_stride, int32_t* __restrict__ len_out) {
-    __shared__ uint32_t s_warp[33];
-    const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+constexpr int kStuffThreads = 256;
+
+__global__ void __launch_bounds__(kStuffThreads)
+jpeg_ffcount_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ frame_bits, JpegGeom G,
+                    uint32_t* __restrict__ chunk_ff) {
+    __shared__ uint32_t s_n;
+    const int b = blockIdx.y, t = threadIdx.x;
     const uint32_t nbytes = (frame_bits[b] + 7) >> 3;
     const int n_chunks = (int)((nbytes + kChunkBytes - 1) / kChunkBytes);
     const uint4* st = reinterpret_cast<const uint4*>(stream + (int64_t)b * G.words_cap);
-    uint32_t* cff = chunk_ff + (int64_t)b * G.chunks_cap;
-    // bytes past nbytes inside the last word are zero (cleared by the scan kernel), never 0xFF
-    for (int c = warp; c < n_chunks; c += kScanThreads / 32) {
-        const uint32_t vecs = min((uint32_t)(kChunkBytes / 16), (nbytes - (uint32_t)c * kChunkBytes + 15) / 16);
+    // bytes past nbytes inside the last vector are zero (cleared by the offsets kernel), never 0xFF
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        if (t == 0) s_n = 0;
+        __syncthreads();
         int n = 0;
-        for (uint32_t v = lane; v < vecs; v += 32) {
-            const uint4 x = st[(int64_t)c * (kChunkBytes / 16) + v];
-            n += count_ff(x.x) + count_ff(x.y) + count_ff(x.z) + count_ff(x.w);
+        if ((uint32_t)c * kChunkBytes + 16u * t < nbytes) {
+            const uint4 x = st[(int64_t)c * (kChunkBytes / 16) + t];
+            n = count_ff(x.x) + count_ff(x.y) + count_ff(x.z) + count_ff(x.w);
         }
         n = __reduce_add_sync(0xffffffffu, n);
-        if (lane == 0) cff[c] = (uint32_t)n;
-    }
-    __syncthreads();
-    const int per = (n_chunks + kScanThreads - 1) / kScanThreads;
-    const int i0 = min(t * per, n_chunks), i1 = min(i0 + per, n_chunks);
-    uint32_t sum = 0;
-    for (int i = i0; i < i1; ++i) sum += cff[i];
-    uint32_t total;
-    uint32_t run = block_exclusive_scan(sum, s_warp, &total);
-    for (int i = i0; i < i1; ++i) {
-        const uint32_t n = cff[i];
-        cff[i] = run;
-        run += n;
-    }
-    if (t == 0) {
-        const int64_t need = (int64_t)kHeaderBytes + nbytes + total + 2;
-        len_out[b] = need <= out_stride ? (int32_t)need : (int32_t)-need;
+        if ((t & 31) == 0 && n) atomicAdd(&s_n, (uint32_t)n);
+        __syncthreads();
+        if (t == 0) chunk_ff[(int64_t)b * G.chunks_cap + c] = s_n;
+        __syncthreads();
     }
 }
-
-constexpr int kStuffThreads = 256;
 
 __global__ void __launch_bounds__(kStuffThreads)
 jpeg_stuff_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ frame_bits,
                   const uint32_t* __restrict__ chunk_ff, JpegGeom G, const __grid_constant__ JpegHeader hdr,
-                  const int32_t* __restrict__ len_out, uint8_t* __restrict__ out, int64_t out_stride) {
+                  uint8_t* __restrict__ out, int64_t out_stride, int32_t* __restrict__ len_out) {
     __shared__ uint8_t s_out[2 * kChunkBytes];
     __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_sum[2];
     const int b = blockIdx.y, t = threadIdx.x;
-    const int32_t len = len_out[b];
-    if (len < 0) return;                                        // does not fit out_stride: nothing is written
     const uint32_t nbytes = (frame_bits[b] + 7) >> 3;
     const int n_chunks = (int)((nbytes + kChunkBytes - 1) / kChunkBytes);
+    const uint32_t* cff = chunk_ff + (int64_t)b * G.chunks_cap;
     uint8_t* dst = out + (int64_t)b * out_stride;
-    if (blockIdx.x == 0) {
-        for (int i = t; i < kHeaderBytes; i += kStuffThreads) dst[i] = hdr.bytes[i];
-        if (t == 0) { dst[len - 2] = 0xFF; dst[len - 1] = 0xD9; }
-    }
     const uint4* st = reinterpret_cast<const uint4*>(stream + (int64_t)b * G.words_cap);
-    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    for (int c = blockIdx.x; c < n_chunks || c == 0; c += gridDim.x) {
+        // 0xFF bytes in the chunks before this one, and in the whole scan (decides whether the file fits)
+        if (t < 2) s_sum[t] = 0;
+        __syncthreads();
+        uint32_t pre = 0, all = 0;
+        for (int i = t; i < n_chunks; i += kStuffThreads) {
+            const uint32_t v = __ldg(cff + i);
+            all += v;
+            if (i < c) pre += v;
+        }
+        pre = __reduce_add_sync(0xffffffffu, pre);
+        all = __reduce_add_sync(0xffffffffu, all);
+        if ((t & 31) == 0) { atomicAdd(&s_sum[0], pre); atomicAdd(&s_sum[1], all); }
+        __syncthreads();
+        pre = s_sum[0]; all = s_sum[1];
+        const int64_t need = (int64_t)kHeaderBytes + nbytes + all + 2;
+        if (need > out_stride) {                               // does not fit: nothing is written but the size needed
+            if (c == 0 && t == 0) len_out[b] = (int32_t)-need;
+            return;
+        }
+        if (c == 0) {
+            for (int i = t; i < kHeaderBytes; i += kStuffThreads) dst[i] = hdr.bytes[i];
+            if (t == 0) { dst[need - 2] = 0xFF; dst[need - 1] = 0xD9; len_out[b] = (int32_t)need; }
+        }
+        if (c >= n_chunks) break;
         const uint32_t base = (uint32_t)c * kChunkBytes;
         const uint32_t mine = base + 16u * t;                   // first byte of this thread
         uint4 x = make_uint4(0, 0, 0, 0);
@@ -641,7 +642,7 @@ jpeg_stuff_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restric
         }
         __syncthreads();
         const uint32_t n_out = min((uint32_t)kChunkBytes, nbytes - base) + total;
-        uint8_t* d = dst + kHeaderBytes + base + chunk_ff[(int64_t)b * G.chunks_cap + c];
+        uint8_t* d = dst + kHeaderBytes + base + pre;
         for (uint32_t i = t; i < n_out; i += kStuffThreads) d[i] = s_out[i];
         __syncthreads();
     }
@@ -680,16 +681,18 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     MLP_CHECK_ARG((int64_t)G.n_blk * 1664 < ((int64_t)1 << 32), "mlp_jpeg_encode: frame %dx%d too large (bit offsets are 32-bit)",
                   frame_h, frame_w);
     MLP_CHECK_ARG(batch <= 65535, "mlp_jpeg_encode: batch %d > 65535", batch);
-    MLP_CHECK_ARG(G.mcu_rows <= 65535, "mlp_jpeg_encode: frame too tall");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DeviceGuard guard(ctx->device);
 
     const int64_t nb = (int64_t)batch * G.n_blk;
     auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
     const int64_t o_coef = 0;
-    const int64_t o_meta = o_coef + up(nb * 64 * 2);
-    const int64_t o_off = o_meta + up(nb * 4);
-    const int64_t o_bits = o_off + up(nb * 4);
+    const int64_t o_mask = o_coef + up(nb * 64 * 2);
+    const int64_t o_dc = o_mask + up(nb * 8);
+    const int64_t o_loc = o_dc + up(nb * 2);
+    const int64_t o_pbits = o_loc + up(nb * 4);
+    const int64_t o_poff = o_pbits + up((int64_t)batch * G.parts * 4);
+    const int64_t o_bits = o_poff + up((int64_t)batch * G.parts * 4);
     const int64_t o_cff = o_bits + up((int64_t)batch * 4);
     const int64_t o_stream = o_cff + up((int64_t)batch * G.chunks_cap * 4);
     const int64_t bytes = o_stream + up((int64_t)batch * G.words_cap * 4);
@@ -697,8 +700,11 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     if (rc != MLP_OK) return rc;
     char* base = static_cast<char*>(ctx->arena[MLP_ARENA_JPEG]);
     int16_t* coefs = reinterpret_cast<int16_t*>(base + o_coef);
-    uint32_t* meta = reinterpret_cast<uint32_t*>(base + o_meta);
-    uint32_t* blk_off = reinterpret_cast<uint32_t*>(base + o_off);
+    uint64_t* nzmask = reinterpret_cast<uint64_t*>(base + o_mask);
+    int16_t* dcs = reinterpret_cast<int16_t*>(base + o_dc);
+    uint32_t* loc_off = reinterpret_cast<uint32_t*>(base + o_loc);
+    uint32_t* part_bits = reinterpret_cast<uint32_t*>(base + o_pbits);
+    uint32_t* part_off = reinterpret_cast<uint32_t*>(base + o_poff);
     uint32_t* frame_bits = reinterpret_cast<uint32_t*>(base + o_bits);
     uint32_t* chunk_ff = reinterpret_cast<uint32_t*>(base + o_cff);
     uint32_t* scan = reinterpret_cast<uint32_t*>(base + o_stream);
@@ -708,22 +714,24 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     build_tables(frame_h, frame_w, quality, &T, &H);
 
     ProfScope prof(ctx, MLP_ST_JPEG, stream);
+    // frames taller than 65535 MCU rows cannot exist (H <= 65535), so the grid's y extent is safe
     dim3 dgrid((G.mcu_cols + kMcuPerCta - 1) / kMcuPerCta, G.mcu_rows, batch);
-    jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, meta);
+    jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, nzmask, dcs);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_scan_kernel<<<batch, kScanThreads, 0, stream>>>(meta, G, T, blk_off, frame_bits, scan);
+    jpeg_len_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, G, T, loc_off, part_bits);
     MLP_LAUNCH_CHECK(ctx);
-    const int64_t hgrid = (nb + kHuffWarps - 1) / kHuffWarps;
-    jpeg_huff_kernel<<<(unsigned)(hgrid < (1 << 30) ? hgrid : (1 << 30)), kHuffWarps * 32, 0, stream>>>(
-        coefs, meta, blk_off, G, T, batch, scan);
+    jpeg_offsets_kernel<<<dim3(kZeroCtas, batch), kOffThreads, 0, stream>>>(part_bits, G, part_off, frame_bits, scan);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_ffscan_kernel<<<batch, kScanThreads, 0, stream>>>(scan, frame_bits, G, chunk_ff, out_stride, len_dev);
+    jpeg_huff_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, loc_off, part_off, G, T, scan);
     MLP_LAUNCH_CHECK(ctx);
-    // typical scans take 0.3-1 byte per pixel; the chunk loop covers the rest
+    // typical scans take 0.3-1 byte per pixel; the chunk loops cover the rest
     int sgrid = (int)(((int64_t)frame_h * frame_w + kChunkBytes - 1) / kChunkBytes);
     sgrid = sgrid < 1 ? 1 : (sgrid > G.chunks_cap ? G.chunks_cap : sgrid);
-    jpeg_stuff_kernel<<<dim3(sgrid, batch), kStuffThreads, 0, stream>>>(scan, frame_bits, chunk_ff, G, H, len_dev, out_dev,
-                                                                        out_stride);
+    sgrid = sgrid > 65535 ? 65535 : sgrid;
+    jpeg_ffcount_kernel<<<dim3(sgrid, batch), kStuffThreads, 0, stream>>>(scan, frame_bits, G, chunk_ff);
+    MLP_LAUNCH_CHECK(ctx);
+    jpeg_stuff_kernel<<<dim3(sgrid, batch), kStuffThreads, 0, stream>>>(scan, frame_bits, chunk_ff, G, H, out_dev, out_stride,
+                                                                        len_dev);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }
