@@ -473,7 +473,7 @@ def run_ours(args, wl):
     if not args.no_summary:
         h_seg = pin(synth.semantic_map(B, PH, PW, seed=500 + rank))
         d_seg = h_seg.cuda()
-        h_img = pin(np.random.default_rng(600 + rank).integers(0, 256, (B, PH, PW, 3)).astype(np.uint8))
+        h_img = pin(synth.road_frames(B, PH, PW, seed=600 + rank))
         d_img = h_img.cuda()
 
         def serve():
@@ -481,10 +481,12 @@ def run_ours(args, wl):
             pipe.trim_and_summarize(r_, d_masks, d_seg)
             pipe.draw(r_, d_masks, d_img, INST_COLORS[:C], 0.3, seg_outs=d_seg, semantic_colors=SEM_COLORS,
                       semantic_alpha=0.3, boxes=True)
+            pipe.encode()
 
         pipe.ctx.profile(False)
         serve()
         Mo = int(pipe.summary_m.item())
+        jpeg_len = pipe.jpeg_len.cpu().numpy()
         torch.cuda.synchronize()
         pipe.ctx.profile(True)
         n_ = max(10, min(50, args.steps))
@@ -500,13 +502,15 @@ def run_ours(args, wl):
         summary_leg = {
             "what": "decode+NMS+RoIAlign, then the two consumers of the masks in the serving graph - SummaryOutput "
                     "and the DrawBoxes+DrawInstance+DrawSegmentation overlay - straight from the mask tiles "
-                    "(trim_and_summarize + draw, no [B,M,PH,PW] tensor); single stream, inputs resident in HBM",
+                    "(trim_and_summarize + draw, no [B,M,PH,PW] tensor), then the JPEG encode of every overlay frame "
+                    "(EncodeImageContent, bytes identical to libjpeg); single stream, inputs resident in HBM",
             "value": world * B / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
             "rows_per_image": Mo, "stage_ms": st_,
-            "seg_bytes": int(h_seg.numel() * 4), "frame_bytes": int(h_img.numel())}
+            "seg_bytes": int(h_seg.numel() * 4), "frame_bytes": int(h_img.numel()),
+            "jpeg_bytes_per_frame_mean": float(jpeg_len.mean()), "jpeg_bytes_per_frame_max": int(jpeg_len.max())}
         if not args.no_e2e:
             summary_leg["e2e"] = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier,
-                                         h_seg=h_seg, summary_rows=Mo, h_img=h_img)
+                                         h_seg=h_seg, summary_rows=Mo, h_img=h_img, jpeg_cap=int(jpeg_len.max()))
 
     if rank == 0:
         cpu = None
@@ -543,12 +547,13 @@ def cpu_serving_tail(wl, frames=2):
     (oracle/summary_oracle.py, oracle/draw_oracle.py), one frame at a time on one thread."""
     import synth
     from oracle import c_oracle as co, summary_oracle as so, draw_oracle as do
-    t_path = t_cons = 0.0
+    t_path = t_cons = t_jpeg = 0.0
+    cpu_jpeg(np.zeros((16, 16, 3), dtype=np.uint8))                  # library import outside the timed part
     for i in range(frames):
         cfgp, N, loc, cls, fmaps = make_inputs(wl, 1, 9000 + i)
         pool = synth.mask_probs(1, (wl["max_k"] + 1) * wl["nms_max_output_size"], wl["C"], seed=98)
         seg = synth.semantic_map(1, wl["PH"], wl["PW"], seed=9100 + i)
-        img = np.random.default_rng(9200 + i).integers(0, 256, (1, wl["PH"], wl["PW"], 3)).astype(np.uint8)
+        img = synth.road_frames(1, wl["PH"], wl["PW"], seed=9200 + i)
         t0 = time.perf_counter()
         out = co.full_path(loc, cls, fmaps, lambda f, b: pool[:, :b.shape[1]], cfgp, (wl["H"], wl["W"]),
                            (wl["PH"], wl["PW"]), binary=False, **kwargs_of(wl))
@@ -556,14 +561,33 @@ def cpu_serving_tail(wl, frames=2):
         so.summary_output(out["det_i"], seg, out["pasted"])
         vis = do.draw_boxes(img, out["det_i"])
         vis = do.draw_instance(vis, out["det_i"], out["pasted"], INST_COLORS[:wl["C"]], 0.3)
-        do.draw_segmentation(vis, seg, SEM_COLORS, 0.3)
+        vis = do.draw_segmentation(vis, seg, SEM_COLORS, 0.3)
         t2 = time.perf_counter()
+        jpeg_kind = cpu_jpeg(vis[0])
+        t3 = time.perf_counter()
         t_path += t1 - t0
         t_cons += t2 - t1
-    return {"value": frames / (t_path + t_cons), "unit": "frames/s", "cores": 1, "kind": "port",
+        t_jpeg += t3 - t2
+    return {"value": frames / (t_path + t_cons + t_jpeg), "unit": "frames/s", "cores": 1, "kind": "port",
             "sample": f"{frames} frames of workload through oracle/c (path, float32 paste) + NumPy restatements "
-                      f"of SummaryOutput / DrawBoxes / DrawInstance / DrawSegmentation",
-            "consumers_ms_per_frame": 1e3 * t_cons / frames, "path_ms_per_frame": 1e3 * t_path / frames}
+                      f"of SummaryOutput / DrawBoxes / DrawInstance / DrawSegmentation + JPEG encode ({jpeg_kind})",
+            "consumers_ms_per_frame": 1e3 * t_cons / frames, "path_ms_per_frame": 1e3 * t_path / frames,
+            "jpeg_ms_per_frame": 1e3 * t_jpeg / frames, "jpeg_kind": jpeg_kind}
+
+
+def cpu_jpeg(frame):
+    """JPEG encode of one frame on the CPU: libjpeg-turbo itself through Pillow when it is importable (the library
+    tf.io.encode_jpeg links, same parameters), else the NumPy restatement."""
+    try:
+        import io
+        from PIL import Image
+        buf = io.BytesIO()
+        Image.fromarray(frame).save(buf, format="JPEG", quality=95, dpi=(300, 300))
+        return "libjpeg-turbo via Pillow (the reference's library)"
+    except ImportError:
+        from oracle import jpeg_oracle as jo
+        jo.encode_jpeg(frame)
+        return "oracle/jpeg_oracle.py (NumPy restatement)"
 
 
 def algorithmic_bytes(wl, N, M):
@@ -583,7 +607,7 @@ SEM_COLORS = [[64, 0, 128], [128, 96, 0], [128, 192, 0]]      # engine/config.py
 
 
 def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False, h_seg=None,
-            summary_rows=0, h_img=None):
+            summary_rows=0, h_img=None, jpeg_cap=0):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
     host memory.  Three streams (copy-in, compute, copy-out) and two sets of device input buffers,
@@ -606,10 +630,14 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
         out_masks = torch.empty((B * summary_rows * 11,), dtype=torch.float32).pin_memory()
     else:
         out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
-    out_vis = torch.empty_like(h_img).pin_memory() if h_img is not None else None
+    # the overlay leaves as JPEG files: a fixed per-frame bound (1.25 x the largest file of the warm-up step, 64 KB
+    # granules) is copied without asking the device for the lengths first; the lengths travel with it
+    jpeg_cap = (int(jpeg_cap * 1.25) + 65535) // 65536 * 65536 if h_img is not None else 0
+    out_vis = torch.empty((B, jpeg_cap), dtype=torch.uint8).pin_memory() if h_img is not None else None
+    out_len = torch.empty((B,), dtype=torch.int32).pin_memory() if h_img is not None else None
     h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps + ([h_seg] if summary else [])
               + ([h_img] if h_img is not None else []))
-    d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size() + (out_vis.numel() if h_img is not None else 0)
+    d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size() + (out_vis.numel() + 4 * B if h_img is not None else 0)
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     state = {"i": 0, "out_done": None}
 
@@ -639,8 +667,9 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             if summary:
                 det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])
                 if h_img is not None:
-                    vis = pipe.draw(r, buf["masks"], buf["img"], INST_COLORS[:wl["C"]], 0.3, seg_outs=buf["seg"],
-                                    semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
+                    pipe.draw(r, buf["masks"], buf["img"], INST_COLORS[:wl["C"]], 0.3, seg_outs=buf["seg"],
+                              semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
+                    vis, vis_len = pipe.encode()
             else:
                 det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
             cmp_done = torch.cuda.Event()
@@ -651,7 +680,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             out_det.copy_(det_i32[:out_det.numel()], non_blocking=True)
             out_masks.copy_(pasted[:out_masks.numel()], non_blocking=True)
             if vis is not None:
-                out_vis.copy_(vis, non_blocking=True)
+                out_vis.copy_(vis[:, :jpeg_cap], non_blocking=True)
+                out_len.copy_(vis_len, non_blocking=True)
             state["out_done"] = torch.cuda.Event()
             state["out_done"].record(s_out)
 
@@ -677,10 +707,11 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             # both directions run concurrently (PCIe is full duplex): the busier one bounds the step
             "pcie_gbs_busier_direction": max(h2d, d2h) / (step_ms * 1e-3) / 1e9,
             "bound": "PCIe (host<->device copies of every step), not the kernels",
-            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw" if h_img is not None else "")
+            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw + encode" if h_img is not None else "")
                     + "; pinned host inputs (heads, FPN maps, mask-head output, semantic map"
                     + (", frames" if h_img is not None else "") + ") in, int32 detections + [B,M',11] summary"
-                    + (" + uint8 overlay image" if h_img is not None else "") + " out every step; the [B,M,PH,PW] "
+                    + (" + the JPEG files of the overlay (fixed per-frame bound)" if h_img is not None else "")
+                    + " out every step; the [B,M,PH,PW] "
                     "masks are never written" if summary else
                     "PostProcessPipeline.detect_and_align + trim_and_paste; pinned host inputs in, "
                     "int32 detections + " + ("bit-packed (1 bit/pixel)" if bits else "uint8") +

@@ -309,6 +309,25 @@ class PostProcessPipeline:
             seg_ptr, seg_t, ctypes.byref(sem) if sem is not None else None, c.view(self.vis), c.stream()))
         return self.vis
 
+    def encode(self, images=None, quality=95):
+        """Last step of the serving graph (road_project/setup/serving.py:41, EncodeImageContent): the JPEG files
+        of `images` (default: the overlay of the last draw) as (files uint8 [B,stride], lengths int32 [B]) on
+        the device - every frame of the batch, bytes identical to tf.io.encode_jpeg / libjpeg.  A negative
+        length reports a file that did not fit the stride (3 bytes per pixel)."""
+        c, B = self.ctx, self.B
+        images = self.vis if images is None else images
+        PH, PW = int(images.shape[1]), int(images.shape[2])
+        if tuple(images.shape) != (B, PH, PW, 3) or images.dtype != torch.uint8:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"images must be uint8 [{B},H,W,3]")
+        if getattr(self, "jpeg_hw", None) != (PH, PW):
+            stride = min(int(self.lib.mlp_jpeg_max_bytes(PH, PW)), 1024 + 3 * PH * PW)
+            self.jpeg_files = c.empty((B, (stride + 15) // 16 * 16), torch.uint8)
+            self.jpeg_len = c.empty((B,), torch.int32)
+            self.jpeg_hw = (PH, PW)
+        rt.check(self.lib.mlp_jpeg_encode(c.handle, c.view(images), B, PH, PW, int(quality), c.view(self.jpeg_files),
+                                          int(self.jpeg_files.shape[1]), c.view(self.jpeg_len), c.stream()))
+        return self.jpeg_files, self.jpeg_len
+
     def summary_view(self):
         """Reference-shaped [B,M',11] view of the last trim_and_summarize (one D2H of M')."""
         Mo = int(self.summary_m.item())

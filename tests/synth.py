@@ -120,3 +120,18 @@ def int_detections(B, M, C, PH, PW, seed=5, pad_tail=0):
     if pad_tail:
         det[:, M - pad_tail:] = np.array([-1, -1, -1, -1, -1, -100], dtype=np.int32)
     return det
+
+
+def road_frames(B, PH, PW, seed=0):
+    """uint8 [B,PH,PW,3] camera-like frames: smooth shading, a textured band and mild sensor noise (uniform noise
+    would be meaningless input for the JPEG encode at the end of the serving graph)."""
+    rng = np.random.default_rng(seed)
+    yy = np.arange(PH, dtype=np.float32)[:, None]
+    xx = np.arange(PW, dtype=np.float32)[None, :]
+    out = np.empty((B, PH, PW, 3), dtype=np.uint8)
+    for b in range(B):
+        base = np.stack([120 + 70 * np.sin(xx / (41.0 + b) + yy / 67.0), 115 + 60 * np.cos(xx / 93.0 - yy / (29.0 + b)),
+                         95 + yy * (110.0 / PH) + 20 * np.sin(xx / 11.0)], -1)
+        base += rng.normal(0, 3.0, base.shape).astype(np.float32)
+        out[b] = np.clip(base, 0, 255).astype(np.uint8)
+    return out

@@ -119,6 +119,12 @@ def test_pipeline_draw():
     got_all = pipe.draw(rois, dev(probs["m"]), dev(img), INST_COLORS[:C], 0.3, seg_outs=dev(seg),
                         semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True).cpu().numpy()
     assert np.array_equal(got_all, vis_all)
+    # ... and its JPEG encode (serving.py:41), every frame of the batch
+    from oracle import jpeg_oracle as jo
+    files, lengths = pipe.encode()
+    files, lengths = files.cpu().numpy(), lengths.cpu().numpy()
+    for b in range(B):
+        assert files[b, :lengths[b]].tobytes() == jo.encode_jpeg(vis_all[b])
     assert ml.DrawInstance(INST_COLORS).get_config()["alpha"] == 0.3
 
 

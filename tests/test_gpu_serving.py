@@ -6,6 +6,7 @@ import torch
 
 import synth
 from oracle import draw_oracle as do
+from oracle import jpeg_oracle as jo
 from oracle import masklab_oracle as mo
 from oracle import semantic_oracle as seo
 from oracle import summary_oracle as so
@@ -49,8 +50,9 @@ def test_serving_outputs_match_the_oracle_composition(kernels, mask_output):
     sum_o = so.summary_output(det_i, seg_i, masks_o, cfg.default_road_size)
 
     # --- the drop-in layers
-    vis, summary, det_outs, ins_outs, seg_outs = ml.serving_outputs(
-        dev(frames), (h, w), dev(roi_boxes), dev(roi_masks), dev(seg_pred), cfg, mask_output=mask_output)
+    vis, summary, det_outs, ins_outs, seg_outs, contents = ml.serving_outputs(
+        dev(frames), (h, w), dev(roi_boxes), dev(roi_masks), dev(seg_pred), cfg, mask_output=mask_output, encode=True)
+    assert contents == jo.encode_image_content(vis_o)                  # serving.py:41: the JPEG of frame 0
     assert np.array_equal(det_outs.cpu().numpy(), det_i) and np.array_equal(ins_outs.cpu().numpy(), ins_i)
     assert np.array_equal(seg_outs.cpu().numpy(), seg_i)
     assert np.array_equal(vis.cpu().numpy(), vis_o)
