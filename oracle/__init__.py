@@ -24,6 +24,11 @@ against independent implementations (torchvision.ops.nms, torch
 interpolate/grid_sample with align_corners=True) and by a second,
 independently written C restatement (oracle/c/).
 
+One row IS pinned: oracle/jpeg_oracle.py (EncodeImageContent = tf.io.encode_jpeg
+defaults, i.e. libjpeg baseline) reproduces byte for byte the files libjpeg-turbo
+itself wrote for tests/golden/jpeg_golden.npz (made with Pillow by
+tests/golden/make_jpeg_golden.py).
+
 Two documented deviations from "whatever TF does", both fixed by
 BASELINE.json's north_star or forced by bit-reproducibility:
   * NMS score ties pop the lower candidate index first (TF>=2.2 comparator;
