@@ -6,18 +6,19 @@
 // (oracle/jpeg_oracle.py restates it and is pinned byte for byte against libjpeg-turbo's own output).
 //
 // Six launches per batch of frames, everything stays on the device:
-//   jpeg_dct_kernel     one CTA per four MCUs of a row: colour conversion (jccolor.c fixed point), h2v2 chroma
+//   jpeg_dct_kernel     one CTA per four strips of four MCUs of a row (the next strip is in flight while this one is
+//                       transformed; per-thread quantisation constants stay in registers): colour conversion (jccolor.c fixed point), h2v2 chroma
 //                       down-sampling with the alternating 1,2 bias (jcsample.c), edge replication and dummy blocks
 //                       (jcprepct.c / jccoefct.c), jpeg_fdct_islow in registers with conflict-free shared-memory
 //                       transposes (jfdctint.c), quantisation by exact reciprocal multiplication (jcdctmgr.c); writes
 //                       zigzag int16 coefficients, the 64-bit non-zero mask and the DC of every block
-//   jpeg_len_kernel     one THREAD per 8x8 block walks the set bits of its mask (jchuff.c encode_one_block without
-//                       output): bit length of the block, exclusive scan inside the CTA, one total per CTA
+//   jpeg_enc_kernel     one THREAD per 8x8 block walks the set bits of its mask (jchuff.c encode_one_block): DC
+//                       difference, ZRL / run-size codes and value bits go, left-aligned, into the block's private
+//                       slot; the bit lengths are scanned inside the CTA (32 MCUs), one total per CTA
 //   jpeg_offsets_kernel per frame: scan of the CTA totals -> bit offset of every CTA, and zero-fill of exactly the
 //                       words the scan will occupy (spread over 16 CTAs per frame), 1-padding of the last byte
-//   jpeg_huff_kernel    one thread per block again: DC difference, ZRL / run-size codes and value bits shifted into
-//                       a 64-bit accumulator, whole words stored at the block's bit offset (only the first and last
-//                       word of a block are atomics - neighbours share them)
+//   jpeg_place_kernel   one thread per block funnel-shifts its slot to the block's bit offset in the scan (only the
+//                       first and last word of a block are atomics - neighbours share them)
 //   jpeg_ffcount_kernel 0xFF bytes per 4 KB chunk of the scan (byte stuffing moves every later byte)
 //   jpeg_stuff_kernel   header (jcmarker.c), scan bytes with a 0x00 after every 0xFF, EOI, length
 // The coefficient passes are integer-issue bound, not HBM bound (3 B/px in, 3 B/px of coefficients out and back).
@@ -64,7 +65,7 @@ const uint8_t kAcChromaVals[162] = {
 constexpr int kHeaderBytes = 623;
 constexpr int kMaxBlockWords = 52;            // 20 (DC) + 63 * 26 (AC) = 1658 bits
 constexpr int kChunkBytes = 4096;             // byte-stuffing chunk of the scan
-constexpr int kPartBlocks = 256;              // blocks per CTA of the length / Huffman passes
+constexpr int kPartBlocks = 192;              // blocks per CTA of the entropy pass: 32 whole MCUs
 
 // Everything a launch needs that depends only on (H, W, quality): passed by value (kernel parameter space).
 struct JpegTables {
@@ -220,162 +221,184 @@ __device__ __forceinline__ void fdct8(int (&d)[8]) {
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(abs(v)); }
 
+#ifndef JPEG_DCT_MINB
+#define JPEG_DCT_MINB 5            // resident CTAs per SM the register allocation aims at (56 registers)
+#endif
 constexpr int kDctThreads = 192;
-constexpr int kMcuPerCta = 4;
+constexpr int kMcuPerGroup = 4;               // one pass of the CTA: a 16 x 64 pixel strip = 24 blocks = 192 (block, row) pairs
+constexpr int kGroupsPerCta = 4;              // strips per CTA along the MCU row (tables and indices set up once)
 
 __device__ __forceinline__ void store_luma(int (*ws)[72], int m, int yy, int xx, int y) {
     ws[m * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 9 + (xx & 7)] = y - 128;
 }
 
-__global__ void __launch_bounds__(kDctThreads)
+__global__ void __launch_bounds__(kDctThreads, JPEG_DCT_MINB)
 jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_constant__ JpegTables T,
                 int16_t* __restrict__ coefs, uint64_t* __restrict__ nzmask, int16_t* __restrict__ dcs) {
-    __shared__ __align__(16) uint8_t raw[16][kMcuPerCta * 48];
-    __shared__ int ws[kMcuPerCta * 6][72];                 // 8 rows of 9: both passes are bank-conflict free
-    __shared__ __align__(16) int16_t outc[kMcuPerCta * 6][64];
-    __shared__ uint8_t s_izz[64];
-    __shared__ uint16_t s_half[2][64];
-    __shared__ uint32_t s_rcp[2][64];
+    __shared__ __align__(16) uint8_t raw[16][kMcuPerGroup * 48];
+    __shared__ int ws[kMcuPerGroup * 6][72];               // 8 rows of 9: both passes are bank-conflict free
+    __shared__ __align__(16) int16_t outc[kMcuPerGroup * 6][64];
+    __shared__ uint32_t s_mlo[kMcuPerGroup * 6], s_mhi[kMcuPerGroup * 6];
+    __shared__ uint32_t s_rcp[2][64], s_hz[2][64];
 
     const int t = threadIdx.x;
-    const int b = blockIdx.z, my = blockIdx.y, mx0 = blockIdx.x * kMcuPerCta;
-    const int n_here = min(kMcuPerCta, G.mcu_cols - mx0);
-    const uint8_t* img = frames + (int64_t)b * G.H * G.W * 3;
+    const int b = blockIdx.z, my = blockIdx.y;
+    const uint8_t* img = frames + (size_t)b * G.H * G.W * 3;
+    const int groups = (G.mcu_cols + kMcuPerGroup - 1) / kMcuPerGroup;
+    const int g0 = blockIdx.x * kGroupsPerCta, g1 = min(g0 + kGroupsPerCta, groups);
 
-    if (t < 64) s_izz[t] = T.izz[t];
+    // quantisation tables of the column pass, staged once per CTA: exact reciprocal, and div / 2 | zigzag position << 16
+    // (the lanes of a warp that share a column read the same word: broadcasts, no bank conflicts)
     if (t < 128) {
-        s_half[t >> 6][t & 63] = T.div[t >> 6][t & 63] >> 1;
-        s_rcp[t >> 6][t & 63] = T.rcp[t >> 6][t & 63];
+        const int tb = t >> 6, n = t & 63;
+        s_rcp[tb][n] = T.rcp[tb][n];
+        s_hz[tb][n] = (uint32_t)(T.div[tb][n] >> 1) | ((uint32_t)T.izz[n] << 16);
     }
+    const int blk = t >> 3, col = t & 7, kk = blk % 6, mm = blk / 6;
+    const uint32_t* rcp = &s_rcp[kk >= 4][col];
+    const uint32_t* hz = &s_hz[kk >= 4][col];
 
-    // ---- phase 0: the 16 x 64 pixel strip of this CTA, 16-byte loads when rows are aligned and inside the frame
-    const bool fast = (G.W % 16 == 0) && (my * 16 + 16 <= G.H) && (n_here == kMcuPerCta) &&
-                      ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
-    if (fast) {
-        const int row = t / 12, seg = t - row * 12;          // 16 rows x 12 vectors = 192 threads
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((int64_t)(my * 16 + row) * G.W + mx0 * 16) * 3) + seg);
-        *reinterpret_cast<uint4*>(&raw[row][seg * 16]) = v;
-    }
-    __syncthreads();
+    // the strip loader: 16 rows x 12 vectors of 16 bytes = 192 threads; only when rows are aligned and inside the frame
+    const bool can_fast = (G.W % 16 == 0) && (my * 16 + 16 <= G.H) && ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
+    const int lrow = t / 12, lseg = t - lrow * 12;
+    const uint8_t* lptr = img + (size_t)(my * 16 + lrow) * G.W * 3 + lseg * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    bool fast = can_fast && (G.mcu_cols - g0 * kMcuPerGroup >= kMcuPerGroup);
+    if (fast) v = __ldg(reinterpret_cast<const uint4*>(lptr + (size_t)g0 * kMcuPerGroup * 48));
 
-    // ---- phase 1: one warp per MCU, a 4 x 2 pixel patch per lane: eight luma samples, two Cb and two Cr samples
-    if (t < 128 && (t >> 5) < n_here) {
-        const int m = t >> 5, l = t & 31, qy = l >> 2, qp = l & 3;
-        const int gy = my * 16 + 2 * qy, gx = (mx0 + m) * 16 + 4 * qp;
-        int cbs[2] = {0, 0}, crs[2] = {0, 0};
+    for (int g = g0; g < g1; ++g) {
+        const int mx0 = g * kMcuPerGroup;
+        const int n_here = min(kMcuPerGroup, G.mcu_cols - mx0);
+        if (fast) *reinterpret_cast<uint4*>(&raw[lrow][lseg * 16]) = v;
+        if (t < kMcuPerGroup * 6) { s_mlo[t] = 0; s_mhi[t] = 0; }
+        __syncthreads();
+        // the next strip travels while this one is transformed
+        const bool fast_next = can_fast && (g + 1 < g1) && (G.mcu_cols - (mx0 + kMcuPerGroup) >= kMcuPerGroup);
+        if (fast_next) v = __ldg(reinterpret_cast<const uint4*>(lptr + (size_t)(g + 1) * kMcuPerGroup * 48));
+
+        // ---- phase 1: one warp per MCU, a 4 x 2 pixel patch per lane: eight luma samples, two Cb and two Cr samples
+        if (t < 128 && (t >> 5) < n_here) {
+            const int m = t >> 5, l = t & 31, qy = l >> 2, qp = l & 3;
+            const int gy = my * 16 + 2 * qy, gx = (mx0 + m) * 16 + 4 * qp;
+            int cbs[2] = {0, 0}, crs[2] = {0, 0};
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            uint32_t w[3];
-            if (fast) {
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(&raw[2 * qy + dy][m * 48 + qp * 12]);
-                w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
-            } else {
-                const int yy = min(gy + dy, G.H - 1);
-                uint8_t px[12];
+            for (int dy = 0; dy < 2; ++dy) {
+                uint32_t w[3];
+                if (fast) {
+                    const uint32_t* p = reinterpret_cast<const uint32_t*>(&raw[2 * qy + dy][m * 48 + qp * 12]);
+                    w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
+                } else {
+                    const int yy = min(gy + dy, G.H - 1);
+                    uint8_t px[12];
+#pragma unroll
+                    for (int dx = 0; dx < 4; ++dx) {
+                        const uint8_t* p = img + ((size_t)yy * G.W + min(gx + dx, G.W - 1)) * 3;
+                        px[dx * 3] = __ldg(p); px[dx * 3 + 1] = __ldg(p + 1); px[dx * 3 + 2] = __ldg(p + 2);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        w[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
+                }
 #pragma unroll
                 for (int dx = 0; dx < 4; ++dx) {
-                    const uint8_t* p = img + ((int64_t)yy * G.W + min(gx + dx, G.W - 1)) * 3;
-                    px[dx * 3] = __ldg(p); px[dx * 3 + 1] = __ldg(p + 1); px[dx * 3 + 2] = __ldg(p + 2);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    w[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
-            }
-#pragma unroll
-            for (int dx = 0; dx < 4; ++dx) {
-                const int o = dx * 3;
-                const int r = (w[o >> 2] >> (8 * (o & 3))) & 255;
-                const int g = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 255;
-                const int bl = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 255;
-                int y, cb, cr;
-                rgb_to_ycc(r, g, bl, y, cb, cr);
-                store_luma(ws, m, 2 * qy + dy, 4 * qp + dx, y);
-                cbs[dx >> 1] += cb; crs[dx >> 1] += cr;
-            }
-        }
-        if (gy >= G.H) {
-            // chroma rows below the last real row group replicate the last DOWN-SAMPLED row (jcprepct.c pads the
-            // down-sampler's output), which is not what the clamped luma rows give when H is even
-            const int r0 = 2 * (G.c_real_rows - 1), r1 = min(r0 + 1, G.H - 1);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                cbs[h] = 0; crs[h] = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int yy = (k >> 1) ? r1 : r0, xx = min(gx + 2 * h + (k & 1), G.W - 1);
-                    const uint8_t* p = img + ((int64_t)yy * G.W + xx) * 3;
+                    const int o = dx * 3;
+                    const int r = (w[o >> 2] >> (8 * (o & 3))) & 255;
+                    const int gch = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 255;
+                    const int bl = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 255;
                     int y, cb, cr;
-                    rgb_to_ycc(__ldg(p), __ldg(p + 1), __ldg(p + 2), y, cb, cr);
-                    cbs[h] += cb; crs[h] += cr;
+                    rgb_to_ycc(r, gch, bl, y, cb, cr);
+                    store_luma(ws, m, 2 * qy + dy, 4 * qp + dx, y);
+                    cbs[dx >> 1] += cb; crs[dx >> 1] += cr;
                 }
             }
+            if (gy >= G.H) {
+                // chroma rows below the last real row group replicate the last DOWN-SAMPLED row (jcprepct.c pads the
+                // down-sampler's output), which is not what the clamped luma rows give when H is even
+                const int r0 = 2 * (G.c_real_rows - 1), r1 = min(r0 + 1, G.H - 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cbs[h] = 0; crs[h] = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int yy = (k >> 1) ? r1 : r0, xx = min(gx + 2 * h + (k & 1), G.W - 1);
+                        const uint8_t* p = img + ((size_t)yy * G.W + xx) * 3;
+                        int y, cb, cr;
+                        rgb_to_ycc(__ldg(p), __ldg(p + 1), __ldg(p + 2), y, cb, cr);
+                        cbs[h] += cb; crs[h] += cr;
+                    }
+                }
+            }
+            // h2v2_downsample: bias 1, 2, 1, 2, ... along the row; this lane owns an even and an odd column
+            ws[m * 6 + 4][qy * 9 + 2 * qp] = ((cbs[0] + 1) >> 2) - 128;
+            ws[m * 6 + 4][qy * 9 + 2 * qp + 1] = ((cbs[1] + 2) >> 2) - 128;
+            ws[m * 6 + 5][qy * 9 + 2 * qp] = ((crs[0] + 1) >> 2) - 128;
+            ws[m * 6 + 5][qy * 9 + 2 * qp + 1] = ((crs[1] + 2) >> 2) - 128;
         }
-        // h2v2_downsample: bias 1, 2, 1, 2, ... along the row; this lane owns an even and an odd column
-        ws[m * 6 + 4][qy * 9 + 2 * qp] = ((cbs[0] + 1) >> 2) - 128;
-        ws[m * 6 + 4][qy * 9 + 2 * qp + 1] = ((cbs[1] + 2) >> 2) - 128;
-        ws[m * 6 + 5][qy * 9 + 2 * qp] = ((crs[0] + 1) >> 2) - 128;
-        ws[m * 6 + 5][qy * 9 + 2 * qp + 1] = ((crs[1] + 2) >> 2) - 128;
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- phase 2: row pass (thread = block * 8 + row; address 9 * t + j: no bank conflicts)
-    {
-        int d[8];
-        int* row = &ws[t >> 3][(t & 7) * 9];
+        // ---- phase 2: row pass (thread = block * 8 + row; address 9 * t + j: no bank conflicts)
+        {
+            int d[8];
+            int* row = &ws[t >> 3][(t & 7) * 9];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = row[j];
-        fdct8<true>(d);
+            for (int j = 0; j < 8; ++j) d[j] = row[j];
+            fdct8<true>(d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) row[j] = d[j];
-    }
-    __syncthreads();
+            for (int j = 0; j < 8; ++j) row[j] = d[j];
+        }
+        __syncthreads();
 
-    // ---- phase 3: column pass + quantisation, zigzag order
-    {
-        const int blk = t >> 3, c = t & 7, k = blk % 6, mm = blk / 6;
-        bool dummy = false;
-        if (k < 4) {
-            const int by = my * 2 + (k >> 1), bx = (mx0 + mm) * 2 + (k & 1);
-            dummy = by >= G.y_blk_rows || bx >= G.y_blk_cols;
-        }
-        int d[8];
+        // ---- phase 3: column pass + quantisation, zigzag order, non-zero mask
+        const bool right_edge = (mx0 + n_here) * 2 > G.y_blk_cols, bottom_edge = my * 2 + 2 > G.y_blk_rows;
+        {
+            bool dummy = false;
+            if (kk < 4 && (right_edge || bottom_edge)) {
+                const int by = my * 2 + (kk >> 1), bx = (mx0 + mm) * 2 + (kk & 1);
+                dummy = by >= G.y_blk_rows || bx >= G.y_blk_cols;
+            }
+            int d[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) d[r] = ws[blk][r * 9 + c];
-        fdct8<false>(d);
-        const int tb = k >= 4;
+            for (int r = 0; r < 8; ++r) d[r] = ws[blk][r * 9 + col];
+            fdct8<false>(d);
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int n = r * 8 + c;
-            // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16, so the reciprocal is exact
-            const int mag = (int)__umulhi((uint32_t)(abs(d[r]) + s_half[tb][n]), s_rcp[tb][n]);
-            outc[blk][s_izz[n]] = dummy ? (int16_t)0 : (int16_t)(d[r] < 0 ? -mag : mag);
+            for (int r = 0; r < 8; ++r) {
+                // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16, so the reciprocal is exact
+                const uint32_t hzr = hz[r * 8];
+                const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r * 8]);
+                const int q = dummy ? 0 : (d[r] < 0 ? -mag : mag);
+                const uint32_t z = hzr >> 16;
+                outc[blk][z] = (int16_t)q;
+                const uint32_t bit = (uint32_t)(q != 0) << (z & 31u);
+                if (z < 32u) lo |= bit; else hi |= bit;
+            }
+            if (lo) atomicOr(&s_mlo[blk], lo);
+            if (hi) atomicOr(&s_mhi[blk], hi);
         }
-    }
-    __syncthreads();
-    // dummy blocks right of / below the frame carry the DC of the previous block of the MCU (jccoefct.c)
-    if (t < n_here) {
-        int prev = 0;
-        for (int k = 0; k < 4; ++k) {
-            const int by = my * 2 + (k >> 1), bx = (mx0 + t) * 2 + (k & 1);
-            if (by >= G.y_blk_rows || bx >= G.y_blk_cols) outc[t * 6 + k][0] = (int16_t)prev;
-            prev = outc[t * 6 + k][0];
+        __syncthreads();
+        // dummy blocks right of / below the frame carry the DC of the previous block of the MCU (jccoefct.c)
+        if (right_edge || bottom_edge) {
+            if (t < n_here) {
+                int prev = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int by = my * 2 + (k >> 1), bx = (mx0 + t) * 2 + (k & 1);
+                    if (by >= G.y_blk_rows || bx >= G.y_blk_cols) outc[t * 6 + k][0] = (int16_t)prev;
+                    prev = outc[t * 6 + k][0];
+                }
+            }
+            __syncthreads();
         }
-    }
-    __syncthreads();
 
-    // ---- phase 4: coefficients out (contiguous: the MCUs of a CTA are neighbours in scan order), masks, DCs
-    const int64_t mcu0 = (int64_t)b * G.n_mcu + (int64_t)my * G.mcu_cols + mx0;
-    if (t < n_here * 48)
-        reinterpret_cast<uint4*>(coefs + mcu0 * 384)[t] = reinterpret_cast<const uint4*>(&outc[0][0])[t];
-    const int warp = t >> 5, lane = t & 31;
-    for (int blk = warp; blk < n_here * 6; blk += kDctThreads / 32) {
-        const int c0 = outc[blk][lane], c1 = outc[blk][lane + 32];
-        const uint32_t lo = __ballot_sync(0xffffffffu, c0 != 0) & ~1u;      // position 0 is the DC slot
-        const uint32_t hi = __ballot_sync(0xffffffffu, c1 != 0);
-        if (lane == 0) {
-            nzmask[mcu0 * 6 + blk] = ((uint64_t)hi << 32) | lo;
-            dcs[mcu0 * 6 + blk] = (int16_t)c0;
+        // ---- phase 4: coefficients out (contiguous: the MCUs of a strip are neighbours in scan order), masks, DCs
+        const size_t mcu0 = (size_t)b * G.n_mcu + (size_t)my * G.mcu_cols + mx0;
+        if (t < n_here * 48)
+            reinterpret_cast<uint4*>(coefs + mcu0 * 384)[t] = reinterpret_cast<const uint4*>(&outc[0][0])[t];
+        if (t < n_here * 6) {
+            nzmask[mcu0 * 6 + t] = (((uint64_t)s_mhi[t] << 32) | s_mlo[t]) & ~1ull;     // position 0 is the DC slot
+            dcs[mcu0 * 6 + t] = outc[t][0];
         }
+        __syncthreads();
+        fast = fast_next;
     }
 }
 
@@ -414,43 +437,82 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return s_warp[warp] + inc - v;
 }
 
+// One THREAD per 8x8 block encodes it (jchuff.c encode_one_block) into a private slot of kMaxBlockWords words,
+// left-aligned from bit 0.  Warps 0-3 of a CTA take the 128 luma blocks of 32 MCUs, warps 4-5 their 64 chroma blocks:
+// a warp then walks blocks of one kind (similar numbers of coefficients, one Huffman table).  The bit lengths are
+// scanned in scan order inside the CTA; blk_meta = exclusive offset << 11 | length.
 __global__ void __launch_bounds__(kPartBlocks)
-jpeg_len_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
-                JpegGeom G, const __grid_constant__ JpegTables T, uint32_t* __restrict__ loc_off,
-                uint32_t* __restrict__ part_bits) {
-    __shared__ uint8_t s_aclen[2][256];
-    __shared__ uint8_t s_dclen[2][12];
+jpeg_enc_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
+                JpegGeom G, const __grid_constant__ JpegTables T, uint32_t* __restrict__ slots,
+                uint32_t* __restrict__ blk_meta, uint32_t* __restrict__ part_bits) {
+    __shared__ uint32_t s_ac[2][256];
+    __shared__ uint32_t s_dc[2][12];
+    __shared__ uint32_t s_len[kPartBlocks];
     __shared__ uint32_t s_warp[33];
     const int t = threadIdx.x, b = blockIdx.y;
-    for (int i = t; i < 512; i += kPartBlocks) s_aclen[i >> 8][i & 255] = (uint8_t)(T.ac[i >> 8][i & 255] >> 16);
-    if (t < 24) s_dclen[t / 12][t % 12] = (uint8_t)(T.dc[t / 12][t % 12] >> 16);
+    for (int i = t; i < 512; i += kPartBlocks) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
+    if (t < 24) s_dc[t / 12][t % 12] = T.dc[t / 12][t % 12];
     __syncthreads();
-    const int i = blockIdx.x * kPartBlocks + t;             // block index inside the frame
-    uint32_t bits = 0;
+    const int chroma = t >= 128;
+    const int li = chroma ? ((t - 128) >> 1) * 6 + 4 + (t & 1) : (t >> 2) * 6 + (t & 3);
+    const int i = blockIdx.x * kPartBlocks + li;            // block index inside the frame, scan order
+    uint32_t nbits = 0;
     if (i < G.n_blk) {
         const int64_t gb = (int64_t)b * G.n_blk + i;
-        const int chroma = (i % 6) >= 4;
-        const int p = pred_block(i);
-        const int diff = (int)__ldg(dcs + gb) - (p >= 0 ? (int)__ldg(dcs + gb - i + p) : 0);
-        int nb = nbits_of(diff);
-        bits = s_dclen[chroma][nb] + nb;
-        const uint8_t* al = s_aclen[chroma];
+        uint32_t* w = slots + gb * kMaxBlockWords;
+        uint32_t cur = 0;
+        int fill = 0;
+        auto emit = [&](uint32_t bits, int len) {           // len <= 27
+            nbits += len;
+            const int room = 32 - fill;
+            if (len < room) {
+                cur |= bits << (room - len);
+                fill += len;
+            } else {
+                *w++ = cur | (bits >> (len - room));
+                fill = len - room;
+                cur = __funnelshift_lc(0u, bits, 32 - fill);    // bits << (32 - fill), 0 when fill == 0
+            }
+        };
+        {   // DC difference
+            const int p = pred_block(i);
+            const int diff = (int)__ldg(dcs + gb) - (p >= 0 ? (int)__ldg(dcs + gb - i + p) : 0);
+            const int nb = nbits_of(diff);
+            const uint32_t cl = s_dc[chroma][nb];
+            emit(((cl & 0xffffu) << nb) | (uint32_t)((diff < 0 ? diff - 1 : diff) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
+        }
+        const uint32_t* ac = s_ac[chroma];
         const int16_t* cf = coefs + gb * 64;
         uint64_t mask = __ldg(nzmask + gb);
-        int prev = 0;
-        while (mask) {
-            const int k = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            nb = nbits_of((int)__ldg(cf + k));
-            const int run = k - prev - 1;
-            bits += (run >> 4) * al[0xF0] + al[((run & 15) << 4) | nb] + nb;
-            prev = k;
+        int prev = 0, k = 0, v = 0;
+        if (mask) {
+            k = __ffsll((long long)mask) - 1;
+            v = (int)__ldg(cf + k);
         }
-        if (prev != 63) bits += al[0x00];                   // EOB
+        while (mask) {
+            mask &= mask - 1;
+            int kn = 0, vn = 0;
+            if (mask) {                                      // the next coefficient is in flight while this one is coded
+                kn = __ffsll((long long)mask) - 1;
+                vn = (int)__ldg(cf + kn);
+            }
+            const int nb = nbits_of(v);
+            const int run = k - prev - 1;
+            for (int zr = run >> 4; zr > 0; --zr) emit(ac[0xF0] & 0xffffu, (int)(ac[0xF0] >> 16));
+            const uint32_t cl = ac[((run & 15) << 4) | nb];
+            emit(((cl & 0xffffu) << nb) | (uint32_t)((v < 0 ? v - 1 : v) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
+            prev = k; k = kn; v = vn;
+        }
+        if (prev != 63) emit(ac[0x00] & 0xffffu, (int)(ac[0x00] >> 16));     // EOB
+        if (fill) *w = cur;
     }
+    s_len[li] = nbits;
+    __syncthreads();
+    const uint32_t mine = s_len[t];
     uint32_t total;
-    const uint32_t exc = block_exclusive_scan(bits, s_warp, &total);
-    if (i < G.n_blk) loc_off[(int64_t)b * G.n_blk + i] = exc;
+    const uint32_t exc = block_exclusive_scan(mine, s_warp, &total);
+    const int i2 = blockIdx.x * kPartBlocks + t;
+    if (i2 < G.n_blk) blk_meta[(int64_t)b * G.n_blk + i2] = (exc << 11) | mine;
     if (t == 0) part_bits[(int64_t)b * G.parts + blockIdx.x] = total;
 }
 
@@ -491,64 +553,33 @@ jpeg_offsets_kernel(const uint32_t* __restrict__ part_bits, JpegGeom G, uint32_t
     }
 }
 
-// ---------------------------------------------------------------------------------------------- Huffman
-__global__ void __launch_bounds__(kPartBlocks)
-jpeg_huff_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
-                 const uint32_t* __restrict__ loc_off, const uint32_t* __restrict__ part_off, JpegGeom G,
-                 const __grid_constant__ JpegTables T, uint32_t* __restrict__ stream) {
-    __shared__ uint32_t s_ac[2][256];
-    __shared__ uint32_t s_dc[2][12];
-    const int t = threadIdx.x, b = blockIdx.y;
-    for (int i = t; i < 512; i += kPartBlocks) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
-    if (t < 24) s_dc[t / 12][t % 12] = T.dc[t / 12][t % 12];
-    __syncthreads();
-    const int i = blockIdx.x * kPartBlocks + t;
+// ------------------------------------------------------------------------------------------------ placement
+// Moves every block's bits from its slot to its bit offset in the frame's scan: a funnel shift per word; the first
+// and the last word of a block are shared with its neighbours (atomic OR into the zero-filled scan), the others
+// are plain stores.
+constexpr int kPlaceThreads = 256;
+
+__global__ void __launch_bounds__(kPlaceThreads)
+jpeg_place_kernel(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ blk_meta,
+                  const uint32_t* __restrict__ part_off, JpegGeom G, uint32_t* __restrict__ stream) {
+    const int i = blockIdx.x * kPlaceThreads + threadIdx.x, b = blockIdx.y;
     if (i >= G.n_blk) return;
     const int64_t gb = (int64_t)b * G.n_blk + i;
-    const int chroma = (i % 6) >= 4;
-    const uint32_t start = __ldg(part_off + (int64_t)b * G.parts + blockIdx.x) + __ldg(loc_off + gb);
+    const uint32_t m = __ldg(blk_meta + gb);
+    const uint32_t len = m & 2047u;
+    const uint32_t start = __ldg(part_off + (int64_t)b * G.parts + i / kPartBlocks) + (m >> 11);
+    const uint32_t* src = slots + gb * kMaxBlockWords;
     uint32_t* dst = stream + (int64_t)b * G.words_cap + (start >> 5);
-    // bits enter at the low end of `acc`; `nacc` counts them including the phantom bits of the first word that
-    // belong to the previous block.  A full word leaves as soon as 32 bits are there.
-    uint64_t acc = 0;
-    int nacc = (int)(start & 31);
-    bool first = true;
-    auto emit = [&](uint32_t bits, int len) {
-        acc = (acc << len) | bits;
-        nacc += len;
-        if (nacc >= 32) {
-            nacc -= 32;
-            const uint32_t w = (uint32_t)(acc >> nacc);
-            if (first) { atomicOr(dst, w); first = false; }
-            else *dst = w;
-            ++dst;
-            acc &= (1ull << nacc) - 1ull;
-        }
-    };
-    {   // DC difference (jchuff.c encode_one_block)
-        const int p = pred_block(i);
-        const int diff = (int)__ldg(dcs + gb) - (p >= 0 ? (int)__ldg(dcs + gb - i + p) : 0);
-        const int nb = nbits_of(diff);
-        const uint32_t cl = s_dc[chroma][nb];
-        emit(((cl & 0xffffu) << nb) | (uint32_t)((diff < 0 ? diff - 1 : diff) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
+    const uint32_t sh = start & 31u;
+    const int nsrc = (int)((len + 31) >> 5), nd = (int)((sh + len + 31) >> 5);
+    uint32_t prev = 0;
+    for (int j = 0; j < nd; ++j) {
+        const uint32_t cur = j < nsrc ? __ldg(src + j) : 0u;
+        const uint32_t w = __funnelshift_r(cur, prev, sh);  // (prev : cur) >> sh
+        if (j == 0 || j == nd - 1) atomicOr(dst + j, w);
+        else dst[j] = w;
+        prev = cur;
     }
-    const uint32_t* ac = s_ac[chroma];
-    const int16_t* cf = coefs + gb * 64;
-    uint64_t mask = __ldg(nzmask + gb);
-    int prev = 0;
-    while (mask) {
-        const int k = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        const int v = (int)__ldg(cf + k);
-        const int nb = nbits_of(v);
-        const int run = k - prev - 1;
-        for (int zr = run >> 4; zr > 0; --zr) emit(ac[0xF0] & 0xffffu, (int)(ac[0xF0] >> 16));
-        const uint32_t cl = ac[((run & 15) << 4) | nb];
-        emit(((cl & 0xffffu) << nb) | (uint32_t)((v < 0 ? v - 1 : v) & ((1 << nb) - 1)), (int)(cl >> 16) + nb);
-        prev = k;
-    }
-    if (prev != 63) emit(ac[0x00] & 0xffffu, (int)(ac[0x00] >> 16));     // EOB
-    if (nacc > 0) atomicOr(dst, (uint32_t)(acc << (32 - nacc)));
 }
 
 // ------------------------------------------------------------------------------------------ byte stuffing
@@ -690,7 +721,8 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     const int64_t o_mask = o_coef + up(nb * 64 * 2);
     const int64_t o_dc = o_mask + up(nb * 8);
     const int64_t o_loc = o_dc + up(nb * 2);
-    const int64_t o_pbits = o_loc + up(nb * 4);
+    const int64_t o_slots = o_loc + up(nb * 4);
+    const int64_t o_pbits = o_slots + up(nb * kMaxBlockWords * 4);
     const int64_t o_poff = o_pbits + up((int64_t)batch * G.parts * 4);
     const int64_t o_bits = o_poff + up((int64_t)batch * G.parts * 4);
     const int64_t o_cff = o_bits + up((int64_t)batch * 4);
@@ -702,7 +734,8 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     int16_t* coefs = reinterpret_cast<int16_t*>(base + o_coef);
     uint64_t* nzmask = reinterpret_cast<uint64_t*>(base + o_mask);
     int16_t* dcs = reinterpret_cast<int16_t*>(base + o_dc);
-    uint32_t* loc_off = reinterpret_cast<uint32_t*>(base + o_loc);
+    uint32_t* blk_meta = reinterpret_cast<uint32_t*>(base + o_loc);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(base + o_slots);
     uint32_t* part_bits = reinterpret_cast<uint32_t*>(base + o_pbits);
     uint32_t* part_off = reinterpret_cast<uint32_t*>(base + o_poff);
     uint32_t* frame_bits = reinterpret_cast<uint32_t*>(base + o_bits);
@@ -715,14 +748,16 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
 
     ProfScope prof(ctx, MLP_ST_JPEG, stream);
     // frames taller than 65535 MCU rows cannot exist (H <= 65535), so the grid's y extent is safe
-    dim3 dgrid((G.mcu_cols + kMcuPerCta - 1) / kMcuPerCta, G.mcu_rows, batch);
+    const int dgroups = (G.mcu_cols + kMcuPerGroup - 1) / kMcuPerGroup;
+    dim3 dgrid((dgroups + kGroupsPerCta - 1) / kGroupsPerCta, G.mcu_rows, batch);
     jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, nzmask, dcs);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_len_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, G, T, loc_off, part_bits);
+    jpeg_enc_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, G, T, slots, blk_meta, part_bits);
     MLP_LAUNCH_CHECK(ctx);
     jpeg_offsets_kernel<<<dim3(kZeroCtas, batch), kOffThreads, 0, stream>>>(part_bits, G, part_off, frame_bits, scan);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_huff_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, loc_off, part_off, G, T, scan);
+    jpeg_place_kernel<<<dim3((G.n_blk + kPlaceThreads - 1) / kPlaceThreads, batch), kPlaceThreads, 0, stream>>>(
+        slots, blk_meta, part_off, G, scan);
     MLP_LAUNCH_CHECK(ctx);
     // typical scans take 0.3-1 byte per pixel; the chunk loops cover the rest
     int sgrid = (int)(((int64_t)frame_h * frame_w + kChunkBytes - 1) / kChunkBytes);
