@@ -11,8 +11,9 @@
 //                       down-sampling with the alternating 1,2 bias (jcsample.c), edge replication and dummy blocks
 //                       (jcprepct.c / jccoefct.c), jpeg_fdct_islow in registers with conflict-free shared-memory
 //                       transposes (jfdctint.c), quantisation by exact reciprocal multiplication (jcdctmgr.c); writes
-//                       zigzag int16 coefficients, the 64-bit non-zero mask and the DC of every block
-//   jpeg_enc_kernel     one THREAD per 8x8 block walks the set bits of its mask (jchuff.c encode_one_block): DC
+//                       zigzag int16 coefficients and the DC of every block
+//   jpeg_enc_kernel     one THREAD per 8x8 block builds the 64-bit non-zero mask of its coefficients (two per
+//                       comparison) and walks its set bits (jchuff.c encode_one_block): DC
 //                       difference, ZRL / run-size codes and value bits go, left-aligned, into the block's private
 //                       slot; the bit lengths are scanned inside the CTA (32 MCUs), one total per CTA
 //   jpeg_offsets_kernel per frame: scan of the CTA totals -> bit offset of every CTA, and zero-fill of exactly the
@@ -234,11 +235,10 @@ __device__ __forceinline__ void store_luma(int (*ws)[72], int m, int yy, int xx,
 
 __global__ void __launch_bounds__(kDctThreads, JPEG_DCT_MINB)
 jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_constant__ JpegTables T,
-                int16_t* __restrict__ coefs, uint64_t* __restrict__ nzmask, int16_t* __restrict__ dcs) {
+                int16_t* __restrict__ coefs, int16_t* __restrict__ dcs) {
     __shared__ __align__(16) uint8_t raw[16][kMcuPerGroup * 48];
     __shared__ int ws[kMcuPerGroup * 6][72];               // 8 rows of 9: both passes are bank-conflict free
     __shared__ __align__(16) int16_t outc[kMcuPerGroup * 6][64];
-    __shared__ uint32_t s_mlo[kMcuPerGroup * 6], s_mhi[kMcuPerGroup * 6];
     __shared__ uint32_t s_rcp[2][64], s_hz[2][64];
 
     const int t = threadIdx.x;
@@ -254,7 +254,7 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
         s_rcp[tb][n] = T.rcp[tb][n];
         s_hz[tb][n] = (uint32_t)(T.div[tb][n] >> 1) | ((uint32_t)T.izz[n] << 16);
     }
-    const int blk = t >> 3, col = t & 7, kk = blk % 6, mm = blk / 6;
+    const int blk = t >> 3, col = t & 7, kk = blk % 6;
     const uint32_t* rcp = &s_rcp[kk >= 4][col];
     const uint32_t* hz = &s_hz[kk >= 4][col];
 
@@ -270,7 +270,6 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
         const int mx0 = g * kMcuPerGroup;
         const int n_here = min(kMcuPerGroup, G.mcu_cols - mx0);
         if (fast) *reinterpret_cast<uint4*>(&raw[lrow][lseg * 16]) = v;
-        if (t < kMcuPerGroup * 6) { s_mlo[t] = 0; s_mhi[t] = 0; }
         __syncthreads();
         // the next strip travels while this one is transformed
         const bool fast_next = can_fast && (g + 1 < g1) && (G.mcu_cols - (mx0 + kMcuPerGroup) >= kMcuPerGroup);
@@ -348,55 +347,42 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
         }
         __syncthreads();
 
-        // ---- phase 3: column pass + quantisation, zigzag order, non-zero mask
-        const bool right_edge = (mx0 + n_here) * 2 > G.y_blk_cols, bottom_edge = my * 2 + 2 > G.y_blk_rows;
+        // ---- phase 3: column pass + quantisation, zigzag order
         {
-            bool dummy = false;
-            if (kk < 4 && (right_edge || bottom_edge)) {
-                const int by = my * 2 + (kk >> 1), bx = (mx0 + mm) * 2 + (kk & 1);
-                dummy = by >= G.y_blk_rows || bx >= G.y_blk_cols;
-            }
             int d[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) d[r] = ws[blk][r * 9 + col];
             fdct8<false>(d);
-            uint32_t lo = 0, hi = 0;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16, so the reciprocal is exact
                 const uint32_t hzr = hz[r * 8];
                 const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r * 8]);
-                const int q = dummy ? 0 : (d[r] < 0 ? -mag : mag);
-                const uint32_t z = hzr >> 16;
-                outc[blk][z] = (int16_t)q;
-                const uint32_t bit = (uint32_t)(q != 0) << (z & 31u);
-                if (z < 32u) lo |= bit; else hi |= bit;
+                outc[blk][hzr >> 16] = (int16_t)(d[r] < 0 ? -mag : mag);
             }
-            if (lo) atomicOr(&s_mlo[blk], lo);
-            if (hi) atomicOr(&s_mhi[blk], hi);
         }
         __syncthreads();
-        // dummy blocks right of / below the frame carry the DC of the previous block of the MCU (jccoefct.c)
-        if (right_edge || bottom_edge) {
+        // dummy blocks right of / below the frame: zero AC, the DC of the previous block of the MCU (jccoefct.c)
+        if ((mx0 + n_here) * 2 > G.y_blk_cols || my * 2 + 2 > G.y_blk_rows) {
             if (t < n_here) {
                 int prev = 0;
                 for (int k = 0; k < 4; ++k) {
                     const int by = my * 2 + (k >> 1), bx = (mx0 + t) * 2 + (k & 1);
-                    if (by >= G.y_blk_rows || bx >= G.y_blk_cols) outc[t * 6 + k][0] = (int16_t)prev;
+                    if (by >= G.y_blk_rows || bx >= G.y_blk_cols) {
+                        for (int z = 1; z < 64; ++z) outc[t * 6 + k][z] = 0;
+                        outc[t * 6 + k][0] = (int16_t)prev;
+                    }
                     prev = outc[t * 6 + k][0];
                 }
             }
             __syncthreads();
         }
 
-        // ---- phase 4: coefficients out (contiguous: the MCUs of a strip are neighbours in scan order), masks, DCs
+        // ---- phase 4: coefficients out (contiguous: the MCUs of a strip are neighbours in scan order) and DCs
         const size_t mcu0 = (size_t)b * G.n_mcu + (size_t)my * G.mcu_cols + mx0;
         if (t < n_here * 48)
             reinterpret_cast<uint4*>(coefs + mcu0 * 384)[t] = reinterpret_cast<const uint4*>(&outc[0][0])[t];
-        if (t < n_here * 6) {
-            nzmask[mcu0 * 6 + t] = (((uint64_t)s_mhi[t] << 32) | s_mlo[t]) & ~1ull;     // position 0 is the DC slot
-            dcs[mcu0 * 6 + t] = outc[t][0];
-        }
+        if (t < n_here * 6) dcs[mcu0 * 6 + t] = outc[t][0];
         __syncthreads();
         fast = fast_next;
     }
@@ -442,7 +428,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 // a warp then walks blocks of one kind (similar numbers of coefficients, one Huffman table).  The bit lengths are
 // scanned in scan order inside the CTA; blk_meta = exclusive offset << 11 | length.
 __global__ void __launch_bounds__(kPartBlocks)
-jpeg_enc_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ nzmask, const int16_t* __restrict__ dcs,
+jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ dcs,
                 JpegGeom G, const __grid_constant__ JpegTables T, uint32_t* __restrict__ slots,
                 uint32_t* __restrict__ blk_meta, uint32_t* __restrict__ part_bits) {
     __shared__ uint32_t s_ac[2][256];
@@ -483,7 +469,22 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const uint64_t* __restrict__ 
         }
         const uint32_t* ac = s_ac[chroma];
         const int16_t* cf = coefs + gb * 64;
-        uint64_t mask = __ldg(nzmask + gb);
+        // non-zero mask of the 63 AC positions: the block's 128 bytes pass through registers once (and stay in L1 for
+        // the walk below); two coefficients per comparison
+        uint64_t mask = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(cf) + q);
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            uint32_t byte = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ne = __vsetne2(xs[j], 0u) & 0x00010001u;       // bit 0 / bit 16: halfword != 0
+                byte |= ((ne | (ne >> 15)) & 3u) << (2 * j);
+            }
+            mask |= (uint64_t)byte << (8 * q);
+        }
+        mask &= ~1ull;                                        // position 0 is the DC slot
         int prev = 0, k = 0, v = 0;
         if (mask) {
             k = __ffsll((long long)mask) - 1;
@@ -718,8 +719,7 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     const int64_t nb = (int64_t)batch * G.n_blk;
     auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
     const int64_t o_coef = 0;
-    const int64_t o_mask = o_coef + up(nb * 64 * 2);
-    const int64_t o_dc = o_mask + up(nb * 8);
+    const int64_t o_dc = o_coef + up(nb * 64 * 2);
     const int64_t o_loc = o_dc + up(nb * 2);
     const int64_t o_slots = o_loc + up(nb * 4);
     const int64_t o_pbits = o_slots + up(nb * kMaxBlockWords * 4);
@@ -732,7 +732,6 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     if (rc != MLP_OK) return rc;
     char* base = static_cast<char*>(ctx->arena[MLP_ARENA_JPEG]);
     int16_t* coefs = reinterpret_cast<int16_t*>(base + o_coef);
-    uint64_t* nzmask = reinterpret_cast<uint64_t*>(base + o_mask);
     int16_t* dcs = reinterpret_cast<int16_t*>(base + o_dc);
     uint32_t* blk_meta = reinterpret_cast<uint32_t*>(base + o_loc);
     uint32_t* slots = reinterpret_cast<uint32_t*>(base + o_slots);
@@ -750,9 +749,9 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     // frames taller than 65535 MCU rows cannot exist (H <= 65535), so the grid's y extent is safe
     const int dgroups = (G.mcu_cols + kMcuPerGroup - 1) / kMcuPerGroup;
     dim3 dgrid((dgroups + kGroupsPerCta - 1) / kGroupsPerCta, G.mcu_rows, batch);
-    jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, nzmask, dcs);
+    jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, dcs);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_enc_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, nzmask, dcs, G, T, slots, blk_meta, part_bits);
+    jpeg_enc_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, dcs, G, T, slots, blk_meta, part_bits);
     MLP_LAUNCH_CHECK(ctx);
     jpeg_offsets_kernel<<<dim3(kZeroCtas, batch), kOffThreads, 0, stream>>>(part_bits, G, part_off, frame_bits, scan);
     MLP_LAUNCH_CHECK(ctx);
