@@ -445,7 +445,9 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
     uint32_t nbits = 0;
     if (i < G.n_blk) {
         const int64_t gb = (int64_t)b * G.n_blk + i;
-        uint32_t* w = slots + gb * kMaxBlockWords;
+        // slot words of the 32 blocks of a warp are interleaved (word j of lane l at (warp * 52 + j) * 32 + l):
+        // lanes that are equally far along share a 128-byte line, here and in the placement pass
+        uint32_t* w = slots + (((int64_t)b * G.parts + blockIdx.x) * (kPartBlocks / 32) + (t >> 5)) * (kMaxBlockWords * 32) + (t & 31);
         uint32_t cur = 0;
         int fill = 0;
         auto emit = [&](uint32_t bits, int len) {           // len <= 27
@@ -455,7 +457,8 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
                 cur |= bits << (room - len);
                 fill += len;
             } else {
-                *w++ = cur | (bits >> (len - room));
+                *w = cur | (bits >> (len - room));
+                w += 32;
                 fill = len - room;
                 cur = __funnelshift_lc(0u, bits, 32 - fill);    // bits << (32 - fill), 0 when fill == 0
             }
@@ -558,24 +561,24 @@ jpeg_offsets_kernel(const uint32_t* __restrict__ part_bits, JpegGeom G, uint32_t
 // Moves every block's bits from its slot to its bit offset in the frame's scan: a funnel shift per word; the first
 // and the last word of a block are shared with its neighbours (atomic OR into the zero-filled scan), the others
 // are plain stores.
-constexpr int kPlaceThreads = 256;
-
-__global__ void __launch_bounds__(kPlaceThreads)
+__global__ void __launch_bounds__(kPartBlocks)
 jpeg_place_kernel(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ blk_meta,
                   const uint32_t* __restrict__ part_off, JpegGeom G, uint32_t* __restrict__ stream) {
-    const int i = blockIdx.x * kPlaceThreads + threadIdx.x, b = blockIdx.y;
+    const int t = threadIdx.x, b = blockIdx.y;
+    // same thread <-> block mapping as the entropy pass, so that a warp reads its interleaved slots line by line
+    const int li = t >= 128 ? ((t - 128) >> 1) * 6 + 4 + (t & 1) : (t >> 2) * 6 + (t & 3);
+    const int i = blockIdx.x * kPartBlocks + li;
     if (i >= G.n_blk) return;
-    const int64_t gb = (int64_t)b * G.n_blk + i;
-    const uint32_t m = __ldg(blk_meta + gb);
+    const uint32_t m = __ldg(blk_meta + (int64_t)b * G.n_blk + i);
     const uint32_t len = m & 2047u;
-    const uint32_t start = __ldg(part_off + (int64_t)b * G.parts + i / kPartBlocks) + (m >> 11);
-    const uint32_t* src = slots + gb * kMaxBlockWords;
+    const uint32_t start = __ldg(part_off + (int64_t)b * G.parts + blockIdx.x) + (m >> 11);
+    const uint32_t* src = slots + (((int64_t)b * G.parts + blockIdx.x) * (kPartBlocks / 32) + (t >> 5)) * (kMaxBlockWords * 32) + (t & 31);
     uint32_t* dst = stream + (int64_t)b * G.words_cap + (start >> 5);
     const uint32_t sh = start & 31u;
     const int nsrc = (int)((len + 31) >> 5), nd = (int)((sh + len + 31) >> 5);
     uint32_t prev = 0;
     for (int j = 0; j < nd; ++j) {
-        const uint32_t cur = j < nsrc ? __ldg(src + j) : 0u;
+        const uint32_t cur = j < nsrc ? __ldg(src + j * 32) : 0u;
         const uint32_t w = __funnelshift_r(cur, prev, sh);  // (prev : cur) >> sh
         if (j == 0 || j == nd - 1) atomicOr(dst + j, w);
         else dst[j] = w;
@@ -722,7 +725,7 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     const int64_t o_dc = o_coef + up(nb * 64 * 2);
     const int64_t o_loc = o_dc + up(nb * 2);
     const int64_t o_slots = o_loc + up(nb * 4);
-    const int64_t o_pbits = o_slots + up(nb * kMaxBlockWords * 4);
+    const int64_t o_pbits = o_slots + up((int64_t)batch * G.parts * kPartBlocks * kMaxBlockWords * 4);
     const int64_t o_poff = o_pbits + up((int64_t)batch * G.parts * 4);
     const int64_t o_bits = o_poff + up((int64_t)batch * G.parts * 4);
     const int64_t o_cff = o_bits + up((int64_t)batch * 4);
@@ -755,8 +758,7 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
     MLP_LAUNCH_CHECK(ctx);
     jpeg_offsets_kernel<<<dim3(kZeroCtas, batch), kOffThreads, 0, stream>>>(part_bits, G, part_off, frame_bits, scan);
     MLP_LAUNCH_CHECK(ctx);
-    jpeg_place_kernel<<<dim3((G.n_blk + kPlaceThreads - 1) / kPlaceThreads, batch), kPlaceThreads, 0, stream>>>(
-        slots, blk_meta, part_off, G, scan);
+    jpeg_place_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(slots, blk_meta, part_off, G, scan);
     MLP_LAUNCH_CHECK(ctx);
     // typical scans take 0.3-1 byte per pixel; the chunk loops cover the rest
     int sgrid = (int)(((int64_t)frame_h * frame_w + kChunkBytes - 1) / kChunkBytes);
