@@ -145,3 +145,35 @@ def test_full_frames(H, W):
     buf = io.BytesIO()
     Image.fromarray(fr[1]).save(buf, format="JPEG", quality=95, dpi=(300, 300))
     assert buf.getvalue() == files[1]                                   # a live libjpeg-turbo agrees as well
+
+
+def test_whole_cfg2_batch_against_a_live_libjpeg():
+    """All 32 frames of a cfg-2 batch (1024x512) in one call, each compared with libjpeg-turbo on the host."""
+    import io
+    Image = pytest.importorskip("PIL.Image")
+    import masklab_b200 as ml
+    fr = road_like(32, 512, 1024, 11)
+    out, lengths = ml.EncodeImageContent().encode_batch(dev(fr))
+    for b, f in enumerate(files_of(out, lengths)):
+        buf = io.BytesIO()
+        Image.fromarray(fr[b]).save(buf, format="JPEG", quality=95, dpi=(300, 300))
+        assert f == buf.getvalue(), f"frame {b}"
+
+
+def test_deterministic_on_another_stream():
+    """The scan is assembled with atomics into zero-filled words: repeated encodes of the same batch, enqueued back
+    to back on a side stream (one context serves one stream at a time), give the same bytes every time."""
+    import masklab_b200 as ml
+    fr = dev(road_like(4, 120, 200, 12))
+    enc = ml.EncodeImageContent()
+    out0, len0 = enc.encode_batch(fr)
+    ref = files_of(out0, len0)
+    torch.cuda.synchronize()
+    s1 = torch.cuda.Stream()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            outs.append(enc.encode_batch(fr))
+    torch.cuda.synchronize()
+    for o, l in outs:
+        assert files_of(o, l) == ref
