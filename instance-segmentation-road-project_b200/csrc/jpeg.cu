@@ -6,8 +6,8 @@
 // (oracle/jpeg_oracle.py restates it and is pinned byte for byte against libjpeg-turbo's own output).
 //
 // Six launches per batch of frames, everything stays on the device:
-//   jpeg_dct_kernel     one CTA per four strips of four MCUs of a row (the next strip is in flight while this one is
-//                       transformed; per-thread quantisation constants stay in registers): colour conversion (jccolor.c fixed point), h2v2 chroma
+//   jpeg_dct_kernel     one WARP per pair of MCUs, four pairs in a row per warp (the next strip is in flight while this
+//                       one is transformed; no CTA barrier inside the loop): colour conversion (jccolor.c fixed point), h2v2 chroma
 //                       down-sampling with the alternating 1,2 bias (jcsample.c), edge replication and dummy blocks
 //                       (jcprepct.c / jccoefct.c), jpeg_fdct_islow in registers with conflict-free shared-memory
 //                       transposes (jfdctint.c), quantisation by exact reciprocal multiplication (jcdctmgr.c); writes
@@ -222,77 +222,91 @@ __device__ __forceinline__ void fdct8(int (&d)[8]) {
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(abs(v)); }
 
+// One WARP owns two neighbouring MCUs (a 16 x 32 pixel strip = 12 blocks = 96 (block, row) pairs = three full rounds
+// of the warp) from the pixel loads to the coefficient stores, so the passes are separated by __syncwarp only and the
+// warps of an SM drift apart instead of meeting at CTA barriers.
 #ifndef JPEG_DCT_MINB
-#define JPEG_DCT_MINB 5            // resident CTAs per SM the register allocation aims at (56 registers)
+#define JPEG_DCT_MINB 6            // resident CTAs per SM the register allocation aims at
 #endif
-constexpr int kDctThreads = 192;
-constexpr int kMcuPerGroup = 4;               // one pass of the CTA: a 16 x 64 pixel strip = 24 blocks = 192 (block, row) pairs
-constexpr int kGroupsPerCta = 4;              // strips per CTA along the MCU row (tables and indices set up once)
+constexpr int kDctWarps = 4;
+constexpr int kDctThreads = kDctWarps * 32;
+constexpr int kPairsPerWarp = 4;              // MCU pairs a warp walks along the row (the next one is in flight)
 
-__device__ __forceinline__ void store_luma(int (*ws)[72], int m, int yy, int xx, int y) {
-    ws[m * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 9 + (xx & 7)] = y - 128;
-}
+struct __align__(16) DctWarpSmem {
+    uint8_t raw[16][96];                       // 16 rows x 32 pixels x RGB
+    int ws[12][72];                            // 8 rows of 9 words: both passes are bank-conflict free
+    int16_t outc[12][64];
+};
 
 __global__ void __launch_bounds__(kDctThreads, JPEG_DCT_MINB)
 jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_constant__ JpegTables T,
                 int16_t* __restrict__ coefs, int16_t* __restrict__ dcs) {
-    __shared__ __align__(16) uint8_t raw[16][kMcuPerGroup * 48];
-    __shared__ int ws[kMcuPerGroup * 6][72];               // 8 rows of 9: both passes are bank-conflict free
-    __shared__ __align__(16) int16_t outc[kMcuPerGroup * 6][64];
+    __shared__ DctWarpSmem s_warp[kDctWarps];
     __shared__ uint32_t s_rcp[2][64], s_hz[2][64];
 
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int b = blockIdx.z, my = blockIdx.y;
     const uint8_t* img = frames + (size_t)b * G.H * G.W * 3;
-    const int groups = (G.mcu_cols + kMcuPerGroup - 1) / kMcuPerGroup;
-    const int g0 = blockIdx.x * kGroupsPerCta, g1 = min(g0 + kGroupsPerCta, groups);
-
-    // quantisation tables of the column pass, staged once per CTA: exact reciprocal, and div / 2 | zigzag position << 16
-    // (the lanes of a warp that share a column read the same word: broadcasts, no bank conflicts)
-    if (t < 128) {
+    // quantisation tables, staged once per CTA: exact reciprocal, and div / 2 | zigzag position << 16
+    {
         const int tb = t >> 6, n = t & 63;
         s_rcp[tb][n] = T.rcp[tb][n];
         s_hz[tb][n] = (uint32_t)(T.div[tb][n] >> 1) | ((uint32_t)T.izz[n] << 16);
     }
-    const int blk = t >> 3, col = t & 7, kk = blk % 6;
-    const uint32_t* rcp = &s_rcp[kk >= 4][col];
-    const uint32_t* hz = &s_hz[kk >= 4][col];
+    __syncthreads();
+    DctWarpSmem& S = s_warp[warp];
 
-    // the strip loader: 16 rows x 12 vectors of 16 bytes = 192 threads; only when rows are aligned and inside the frame
+    const int pairs = (G.mcu_cols + 1) / 2;
+    const int p0 = (blockIdx.x * kDctWarps + warp) * kPairsPerWarp, p1 = min(p0 + kPairsPerWarp, pairs);
+    if (p0 >= pairs) return;
+
+    // the strip loader: 16 rows x 6 vectors of 16 bytes, three per lane; only when rows are aligned and inside the frame
     const bool can_fast = (G.W % 16 == 0) && (my * 16 + 16 <= G.H) && ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
-    const int lrow = t / 12, lseg = t - lrow * 12;
-    const uint8_t* lptr = img + (size_t)(my * 16 + lrow) * G.W * 3 + lseg * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    bool fast = can_fast && (G.mcu_cols - g0 * kMcuPerGroup >= kMcuPerGroup);
-    if (fast) v = __ldg(reinterpret_cast<const uint4*>(lptr + (size_t)g0 * kMcuPerGroup * 48));
+    const uint8_t* rowbase = img + (size_t)(my * 16) * G.W * 3;
+    uint4 v[3];
+    auto fetch = [&](int p) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = lane + 32 * k, row = idx / 6, seg = idx - row * 6;
+            v[k] = __ldg(reinterpret_cast<const uint4*>(rowbase + (size_t)row * G.W * 3 + (size_t)p * 96) + seg);
+        }
+    };
+    bool fast = can_fast && (G.mcu_cols - p0 * 2 >= 2);
+    if (fast) fetch(p0);
 
-    for (int g = g0; g < g1; ++g) {
-        const int mx0 = g * kMcuPerGroup;
-        const int n_here = min(kMcuPerGroup, G.mcu_cols - mx0);
-        if (fast) *reinterpret_cast<uint4*>(&raw[lrow][lseg * 16]) = v;
-        __syncthreads();
+    for (int p = p0; p < p1; ++p) {
+        const int mx0 = p * 2;
+        const int n_here = min(2, G.mcu_cols - mx0);
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx = lane + 32 * k, row = idx / 6, seg = idx - row * 6;
+                *reinterpret_cast<uint4*>(&S.raw[row][seg * 16]) = v[k];
+            }
+        }
+        __syncwarp();
         // the next strip travels while this one is transformed
-        const bool fast_next = can_fast && (g + 1 < g1) && (G.mcu_cols - (mx0 + kMcuPerGroup) >= kMcuPerGroup);
-        if (fast_next) v = __ldg(reinterpret_cast<const uint4*>(lptr + (size_t)(g + 1) * kMcuPerGroup * 48));
+        const bool fast_next = can_fast && (p + 1 < p1) && (G.mcu_cols - (mx0 + 2) >= 2);
+        if (fast_next) fetch(p + 1);
 
-        // ---- phase 1: one warp per MCU, a 4 x 2 pixel patch per lane: eight luma samples, two Cb and two Cr samples
-        if (t < 128 && (t >> 5) < n_here) {
-            const int m = t >> 5, l = t & 31, qy = l >> 2, qp = l & 3;
+        // ---- phase 1: a 4 x 2 pixel patch per lane and MCU: eight luma samples, two Cb and two Cr samples
+        const int qy = lane >> 2, qp = lane & 3;
+        for (int m = 0; m < n_here; ++m) {
             const int gy = my * 16 + 2 * qy, gx = (mx0 + m) * 16 + 4 * qp;
             int cbs[2] = {0, 0}, crs[2] = {0, 0};
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
                 uint32_t w[3];
                 if (fast) {
-                    const uint32_t* p = reinterpret_cast<const uint32_t*>(&raw[2 * qy + dy][m * 48 + qp * 12]);
-                    w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(&S.raw[2 * qy + dy][m * 48 + qp * 12]);
+                    w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
                 } else {
                     const int yy = min(gy + dy, G.H - 1);
                     uint8_t px[12];
 #pragma unroll
                     for (int dx = 0; dx < 4; ++dx) {
-                        const uint8_t* p = img + ((size_t)yy * G.W + min(gx + dx, G.W - 1)) * 3;
-                        px[dx * 3] = __ldg(p); px[dx * 3 + 1] = __ldg(p + 1); px[dx * 3 + 2] = __ldg(p + 2);
+                        const uint8_t* q = img + ((size_t)yy * G.W + min(gx + dx, G.W - 1)) * 3;
+                        px[dx * 3] = __ldg(q); px[dx * 3 + 1] = __ldg(q + 1); px[dx * 3 + 2] = __ldg(q + 2);
                     }
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
@@ -306,7 +320,8 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
                     const int bl = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 255;
                     int y, cb, cr;
                     rgb_to_ycc(r, gch, bl, y, cb, cr);
-                    store_luma(ws, m, 2 * qy + dy, 4 * qp + dx, y);
+                    const int yy = 2 * qy + dy, xx = 4 * qp + dx;
+                    S.ws[m * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 9 + (xx & 7)] = y - 128;
                     cbs[dx >> 1] += cb; crs[dx >> 1] += cr;
                 }
             }
@@ -320,70 +335,87 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int yy = (k >> 1) ? r1 : r0, xx = min(gx + 2 * h + (k & 1), G.W - 1);
-                        const uint8_t* p = img + ((size_t)yy * G.W + xx) * 3;
+                        const uint8_t* q = img + ((size_t)yy * G.W + xx) * 3;
                         int y, cb, cr;
-                        rgb_to_ycc(__ldg(p), __ldg(p + 1), __ldg(p + 2), y, cb, cr);
+                        rgb_to_ycc(__ldg(q), __ldg(q + 1), __ldg(q + 2), y, cb, cr);
                         cbs[h] += cb; crs[h] += cr;
                     }
                 }
             }
             // h2v2_downsample: bias 1, 2, 1, 2, ... along the row; this lane owns an even and an odd column
-            ws[m * 6 + 4][qy * 9 + 2 * qp] = ((cbs[0] + 1) >> 2) - 128;
-            ws[m * 6 + 4][qy * 9 + 2 * qp + 1] = ((cbs[1] + 2) >> 2) - 128;
-            ws[m * 6 + 5][qy * 9 + 2 * qp] = ((crs[0] + 1) >> 2) - 128;
-            ws[m * 6 + 5][qy * 9 + 2 * qp + 1] = ((crs[1] + 2) >> 2) - 128;
+            S.ws[m * 6 + 4][qy * 9 + 2 * qp] = ((cbs[0] + 1) >> 2) - 128;
+            S.ws[m * 6 + 4][qy * 9 + 2 * qp + 1] = ((cbs[1] + 2) >> 2) - 128;
+            S.ws[m * 6 + 5][qy * 9 + 2 * qp] = ((crs[0] + 1) >> 2) - 128;
+            S.ws[m * 6 + 5][qy * 9 + 2 * qp + 1] = ((crs[1] + 2) >> 2) - 128;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- phase 2: row pass (thread = block * 8 + row; address 9 * t + j: no bank conflicts)
-        {
-            int d[8];
-            int* row = &ws[t >> 3][(t & 7) * 9];
+        // ---- phase 2: row pass, item = block * 8 + row (address 9 * item + j: no bank conflicts)
+        const int rounds = n_here == 2 ? 3 : 2;              // one MCU: 48 items, the second round half empty
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = row[j];
-            fdct8<true>(d);
+        for (int rd = 0; rd < 3; ++rd) {
+            const int item = rd * 32 + lane;
+            if (rd < rounds && item < n_here * 48) {
+                int d[8];
+                int* row = &S.ws[0][0] + item * 9;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) row[j] = d[j];
+                for (int j = 0; j < 8; ++j) d[j] = row[j];
+                fdct8<true>(d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) row[j] = d[j];
+            }
         }
-        __syncthreads();
+        __syncwarp();
 
         // ---- phase 3: column pass + quantisation, zigzag order
-        {
-            int d[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) d[r] = ws[blk][r * 9 + col];
-            fdct8<false>(d);
+        for (int rd = 0; rd < 3; ++rd) {
+            const int item = rd * 32 + lane;
+            if (rd < rounds && item < n_here * 48) {
+                const int blk = item >> 3, col = item & 7;
+                const int tb = (blk == 4) | (blk == 5) | (blk >= 10);
+                const uint32_t* rcp = &s_rcp[tb][col];
+                const uint32_t* hz = &s_hz[tb][col];
+                int d[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16, so the reciprocal is exact
-                const uint32_t hzr = hz[r * 8];
-                const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r * 8]);
-                outc[blk][hzr >> 16] = (int16_t)(d[r] < 0 ? -mag : mag);
-            }
-        }
-        __syncthreads();
-        // dummy blocks right of / below the frame: zero AC, the DC of the previous block of the MCU (jccoefct.c)
-        if ((mx0 + n_here) * 2 > G.y_blk_cols || my * 2 + 2 > G.y_blk_rows) {
-            if (t < n_here) {
-                int prev = 0;
-                for (int k = 0; k < 4; ++k) {
-                    const int by = my * 2 + (k >> 1), bx = (mx0 + t) * 2 + (k & 1);
-                    if (by >= G.y_blk_rows || bx >= G.y_blk_cols) {
-                        for (int z = 1; z < 64; ++z) outc[t * 6 + k][z] = 0;
-                        outc[t * 6 + k][0] = (int16_t)prev;
-                    }
-                    prev = outc[t * 6 + k][0];
+                for (int r = 0; r < 8; ++r) d[r] = S.ws[blk][r * 9 + col];
+                fdct8<false>(d);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16: the reciprocal is exact
+                    const uint32_t hzr = hz[r * 8];
+                    const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r * 8]);
+                    S.outc[blk][hzr >> 16] = (int16_t)(d[r] < 0 ? -mag : mag);
                 }
             }
-            __syncthreads();
+        }
+        __syncwarp();
+        // dummy blocks right of / below the frame: zero AC, the DC of the previous block of the MCU (jccoefct.c)
+        if ((mx0 + n_here) * 2 > G.y_blk_cols || my * 2 + 2 > G.y_blk_rows) {
+            if (lane < n_here) {
+                int prev = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int by = my * 2 + (k >> 1), bx = (mx0 + lane) * 2 + (k & 1);
+                    if (by >= G.y_blk_rows || bx >= G.y_blk_cols) {
+                        for (int z = 1; z < 64; ++z) S.outc[lane * 6 + k][z] = 0;
+                        S.outc[lane * 6 + k][0] = (int16_t)prev;
+                    }
+                    prev = S.outc[lane * 6 + k][0];
+                }
+            }
+            __syncwarp();
         }
 
-        // ---- phase 4: coefficients out (contiguous: the MCUs of a strip are neighbours in scan order) and DCs
+        // ---- phase 4: coefficients out (contiguous: the MCUs of a pair are neighbours in scan order) and DCs
         const size_t mcu0 = (size_t)b * G.n_mcu + (size_t)my * G.mcu_cols + mx0;
-        if (t < n_here * 48)
-            reinterpret_cast<uint4*>(coefs + mcu0 * 384)[t] = reinterpret_cast<const uint4*>(&outc[0][0])[t];
-        if (t < n_here * 6) dcs[mcu0 * 6 + t] = outc[t][0];
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < n_here * 48)
+                reinterpret_cast<uint4*>(coefs + mcu0 * 384)[idx] = reinterpret_cast<const uint4*>(&S.outc[0][0])[idx];
+        }
+        if (lane < n_here * 6) dcs[mcu0 * 6 + lane] = S.outc[lane][0];
+        __syncwarp();
         fast = fast_next;
     }
 }
@@ -756,8 +788,8 @@ extern "C" int mlp_jpeg_encode(mlp_ctx* ctx, const uint8_t* images_dev, int batc
 
     ProfScope prof(ctx, MLP_ST_JPEG, stream);
     // frames taller than 65535 MCU rows cannot exist (H <= 65535), so the grid's y extent is safe
-    const int dgroups = (G.mcu_cols + kMcuPerGroup - 1) / kMcuPerGroup;
-    dim3 dgrid((dgroups + kGroupsPerCta - 1) / kGroupsPerCta, G.mcu_rows, batch);
+    const int dpairs = (G.mcu_cols + 1) / 2;
+    dim3 dgrid((dpairs + kDctWarps * kPairsPerWarp - 1) / (kDctWarps * kPairsPerWarp), G.mcu_rows, batch);
     jpeg_dct_kernel<<<dgrid, kDctThreads, 0, stream>>>(images_dev, G, T, coefs, dcs);
     MLP_LAUNCH_CHECK(ctx);
     jpeg_enc_kernel<<<dim3(G.parts, batch), kPartBlocks, 0, stream>>>(coefs, dcs, G, T, slots, blk_meta, part_bits);
