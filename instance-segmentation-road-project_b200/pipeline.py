@@ -356,6 +356,33 @@ class PostProcessPipeline:
             self.trim_and_paste(rois, roi_masks)
         return graph, rois
 
+    def capture_serving(self, loc_pred, cls_pred, fmaps, roi_masks, seg_outs, images, instance_colors,
+                        instance_alpha=.3, semantic_colors=None, semantic_alpha=.3, boxes=True, quality=95):
+        """The serving tail of one batch as ONE CUDA graph: detect_and_align -> trim_and_summarize -> draw ->
+        encode (SummaryOutput, the three overlays and the JPEG files; road_project/setup/serving.py:29-48).  All of
+        it is sync-free, so the ~25 kernels replay as one launch.  Refill the same input tensors and call
+        `.replay()`; summary, overlay and files land in the pipeline's buffers (summary_view(), vis, jpeg_files,
+        jpeg_len).  As with capture(), the mask head is not part of the graph."""
+        def run():
+            rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+            self.trim_and_summarize(rois, roi_masks, seg_outs)
+            self.draw(rois, roi_masks, images, instance_colors, instance_alpha, seg_outs=seg_outs,
+                      semantic_colors=semantic_colors, semantic_alpha=semantic_alpha, boxes=boxes)
+            self.encode(quality=quality)
+            return rois
+        torch.cuda.synchronize(self.ctx.device)
+        side = torch.cuda.Stream(device=self.ctx.device)
+        side.wait_stream(torch.cuda.current_stream(self.ctx.device))
+        with torch.cuda.stream(side):                       # warm-up: buffers, scratch growth, function attributes
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream(self.ctx.device).wait_stream(side)
+        torch.cuda.synchronize(self.ctx.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            rois = run()
+        return graph, rois
+
     def result_views(self):
         """Reference-shaped views of the last trim_and_paste (one D2H of M)."""
         M = int(self.trim_m.item())

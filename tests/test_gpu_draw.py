@@ -125,6 +125,25 @@ def test_pipeline_draw():
     files, lengths = files.cpu().numpy(), lengths.cpu().numpy()
     for b in range(B):
         assert files[b, :lengths[b]].tobytes() == jo.encode_jpeg(vis_all[b])
+    # the whole serving tail as one CUDA graph: same summary, overlay and files, also after other inputs passed through
+    d_loc, d_cls, d_fm, d_m, d_seg, d_img = dev(loc), dev(cls), [dev(f) for f in fmaps], dev(probs["m"]), dev(seg), dev(img)
+    ref_summary = pipe.summary.clone()
+    graph, _ = pipe.capture_serving(d_loc, d_cls, d_fm, d_m, d_seg, d_img, INST_COLORS[:C], 0.3,
+                                    semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
+    keep = d_img.clone()
+    d_img.copy_(255 - keep)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert not np.array_equal(pipe.vis.cpu().numpy(), vis_all)
+    d_img.copy_(keep)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(pipe.vis.cpu().numpy(), vis_all)
+    f2, l2 = pipe.jpeg_files.cpu().numpy(), pipe.jpeg_len.cpu().numpy()
+    for b in range(B):
+        assert f2[b, :l2[b]].tobytes() == files[b, :lengths[b]].tobytes()
+    Mo = int(pipe.summary_m.item())
+    assert torch.equal(pipe.summary[:B * Mo * 11], ref_summary[:B * Mo * 11])
     assert ml.DrawInstance(INST_COLORS).get_config()["alpha"] == 0.3
 
 
