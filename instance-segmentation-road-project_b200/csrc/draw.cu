@@ -223,6 +223,8 @@ draw_tiles_kernel(const DrawTilesArgs A) {
     __shared__ signed char s_cls[kMaxCand];
     __shared__ DrawGeom s_geom[kGeomCache];
     __shared__ int s_wcnt[kDrawThreads / 32];
+    __shared__ unsigned char s_ord[kGeomCache];
+    __shared__ int s_start[MLP_MAX_DRAW_CLASSES + 1];
     const int b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = min(*A.m_used, A.m_rows);
@@ -259,6 +261,23 @@ draw_tiles_kernel(const DrawTilesArgs A) {
         ncand += tot;
         __syncthreads();
     }
+    // At most 32 candidates (= the geometry cache): warp 0 groups them by class with ballots, order kept, so that
+    // the per-class loops below touch only their own candidates instead of scanning the list once per class.
+    const bool grouped = ncand > 0 && ncand <= kGeomCache && C <= MLP_MAX_DRAW_CLASSES;
+    if (grouped) {
+        if (warp == 0) {
+            const int mine = lane < ncand ? (int)s_cls[lane] : -1;
+            int start = 0;
+            for (int c = 0; c < C; ++c) {
+                const unsigned m = __ballot_sync(0xffffffffu, mine == c);
+                if (mine == c) s_ord[start + __popc(m & ((1u << lane) - 1u))] = (unsigned char)lane;
+                if (lane == 0) s_start[c] = start;
+                start += __popc(m);
+            }
+            if (lane == 0) s_start[C] = start;
+        }
+        __syncthreads();
+    }
     const int oy = by0 + (tid >> 4), ox = bx0 + (tid & 15) * 4;
     if (oy >= A.PH || ox >= A.PW) return;
     const int mh = A.mh, mw = A.mw;
@@ -266,35 +285,48 @@ draw_tiles_kernel(const DrawTilesArgs A) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
     if (ncand > 0) {
+        // the float32 value CropAndPadMask writes at (oy, ox+q) for instance j: two-stage lerp of the {0,1} tile
+        auto eval = [&](int j, const DrawGeom& d, float (&acc)[4]) {
+            const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
+            const float fy = floorf(py);
+            const float ly = __fsub_rn(py, fy);
+            const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + j) * mh;
+            const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x = ox + q;
+                if (x < d.xmin || x >= d.xmax) continue;
+                const float p = __fmul_rn((float)(x - d.xmin), d.sx);
+                const float fl = floorf(p);
+                const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
+                const float lx = __fsub_rn(p, fl);
+                const float tl = (float)((w0 >> xlo) & 1u), tr = (float)((w0 >> xhi) & 1u);
+                const float bl = (float)((w1 >> xlo) & 1u), br = (float)((w1 >> xhi) & 1u);
+                const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+                const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+                acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+            }
+        };
         for (int c = 0; c < C; ++c) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};           // reduce_sum of the class's masks, order j
-            // list overflow: walk all instances of the image instead (same order, same result)
-            const bool all = ncand > kMaxCand;
-            const int i1 = all ? M : ncand;
-            for (int i = 0; i < i1; ++i) {
-                if (!all && s_cls[i] != c) continue;
-                const int j = all ? i : (int)s_cand[i];
-                const DrawGeom d = (!all && i < kGeomCache) ? s_geom[i] : G[j];
-                if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
-                // the float32 value CropAndPadMask writes at (oy, ox+q): two-stage lerp of the {0,1} tile
-                const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
-                const float fy = floorf(py);
-                const float ly = __fsub_rn(py, fy);
-                const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + j) * mh;
-                const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int x = ox + q;
-                    if (x < d.xmin || x >= d.xmax) continue;
-                    const float p = __fmul_rn((float)(x - d.xmin), d.sx);
-                    const float fl = floorf(p);
-                    const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
-                    const float lx = __fsub_rn(p, fl);
-                    const float tl = (float)((w0 >> xlo) & 1u), tr = (float)((w0 >> xhi) & 1u);
-                    const float bl = (float)((w1 >> xlo) & 1u), br = (float)((w1 >> xhi) & 1u);
-                    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-                    const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-                    acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+            if (grouped) {
+                // the usual case (at most 32 candidates): only this class's candidates, still in instance order
+                for (int k = s_start[c]; k < s_start[c + 1]; ++k) {
+                    const int i = s_ord[k];
+                    const DrawGeom d = s_geom[i];
+                    if (oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
+                    eval((int)s_cand[i], d, acc);
+                }
+            } else {
+                // list overflow: walk all instances of the image instead (same order, same result)
+                const bool all = ncand > kMaxCand;
+                const int i1 = all ? M : ncand;
+                for (int i = 0; i < i1; ++i) {
+                    if (!all && s_cls[i] != c) continue;
+                    const int j = all ? i : (int)s_cand[i];
+                    const DrawGeom d = (!all && i < kGeomCache) ? s_geom[i] : G[j];
+                    if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
+                    eval(j, d, acc);
                 }
             }
 #pragma unroll

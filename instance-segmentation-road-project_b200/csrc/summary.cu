@@ -112,6 +112,89 @@ road_rows_kernel(const int32_t* __restrict__ seg, int PH, int PW, int S, int roa
     }
 }
 
+// The same pass for the serving graph's three-channel map (channels == 3, frame width a multiple of 4, 16-byte aligned
+// rows): every lane takes four pixels = three 128-bit loads, a warp 128 pixels = 1.5 KB of contiguous row per step, two
+// steps in flight - every byte of the map crosses once, in full 128-byte lines.  The four bits of a lane meet the
+// other seven lanes of its 32-pixel word through three xor-shuffles.
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned or_over_8(unsigned v) {
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+template <int kRoad, int kCrack>
+__global__ void __launch_bounds__(kRowsThreads)
+road_rows3_kernel(const int32_t* __restrict__ seg, int PH, int PW, int2* __restrict__ row_ext,
+                  uint32_t* __restrict__ road_bits, uint32_t* __restrict__ crack_bits, int2* __restrict__ crack_rows,
+                  int32_t* __restrict__ crack_box) {
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int nwarps = kRowsThreads / 32;
+    const int y = blockIdx.x * nwarps + warp;
+    if (y >= PH) return;
+    const int words = (PW + 31) >> 5;
+    const uint4* rowv = reinterpret_cast<const uint4*>(seg + ((int64_t)b * PH + y) * PW * 3);
+    uint32_t* rb = road_bits + ((int64_t)b * PH + y) * words;
+    uint32_t* cb = crack_bits ? crack_bits + ((int64_t)b * PH + y) * words : nullptr;
+    const int grp = lane >> 3, sub = lane & 7;
+    int xmin = INT_MAX, xmax = -1, cx0 = INT_MAX, cx1 = -1;
+    int cpix = 0, cinter = 0;                               // crack pixels of the row, and those on my_road
+    constexpr int kSteps = 2;
+    for (int base = 0; base < PW; base += 128 * kSteps) {
+        uint4 v[kSteps][3];
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+            const int x = base + u * 128 + 4 * lane;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                v[u][k] = x < PW ? ldg_stream_u4(rowv + (x >> 2) * 3 + k) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+            const int32_t e[12] = {(int32_t)v[u][0].x, (int32_t)v[u][0].y, (int32_t)v[u][0].z, (int32_t)v[u][0].w,
+                                   (int32_t)v[u][1].x, (int32_t)v[u][1].y, (int32_t)v[u][1].z, (int32_t)v[u][1].w,
+                                   (int32_t)v[u][2].x, (int32_t)v[u][2].y, (int32_t)v[u][2].z, (int32_t)v[u][2].w};
+            unsigned mn = 0, cn = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mn |= (e[3 * q + kRoad] > 0 ? 1u : 0u) << q;             // tf.where(image > 0), misc.py:661
+                cn |= (e[3 * q + kCrack] != 0 ? 1u : 0u) << q;           // tf.where(inputs), misc.py:516
+            }
+            const unsigned m = or_over_8(mn << (4 * sub));
+            const unsigned c = cb ? or_over_8(cn << (4 * sub)) : 0u;
+            const int wi = ((base + u * 128) >> 5) + grp, x0 = wi * 32;
+            if (sub == 0 && x0 < PW) {
+                rb[wi] = m;
+                if (cb) cb[wi] = c;
+                if (m) { xmin = min(xmin, x0 + __ffs(m) - 1); xmax = max(xmax, x0 + 31 - __clz(m)); }
+                if (c) {
+                    cx0 = min(cx0, x0 + __ffs(c) - 1); cx1 = max(cx1, x0 + 31 - __clz(c));
+                    cpix += __popc(c); cinter += __popc(c & m);
+                }
+            }
+        }
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    cx0 = __reduce_min_sync(0xffffffffu, cx0); cx1 = __reduce_max_sync(0xffffffffu, cx1);
+    cpix = __reduce_add_sync(0xffffffffu, cpix); cinter = __reduce_add_sync(0xffffffffu, cinter);
+    if (lane == 0) {
+        row_ext[(int64_t)b * PH + y] = xmax >= 0 ? make_int2(xmin, xmax) : make_int2(0, 0);
+        if (crack_rows) crack_rows[(int64_t)b * PH + y] = make_int2(cpix, cinter);
+        if (cx1 >= 0) {
+            atomicMin(crack_box + 0, y); atomicMin(crack_box + 1, cx0);
+            atomicMax(crack_box + 2, y); atomicMax(crack_box + 3, cx1);
+        }
+    }
+}
+
 // Pass 2, one CTA per image: the 15 % trimmed least-squares fit of both road borders over the rows
 // with x_min != x_max, then metres per pixel on every frame row.
 __global__ void __launch_bounds__(kScanThreads)
@@ -584,11 +667,22 @@ box_summary_kernel(const BoxSummaryArgs A) {
         }
         // chunk-major, highest chunk first: the extra chunks of wide (= large) boxes start before the
         // bulk of small boxes, so the longest CTAs are not the last ones
-        const int64_t t = item - n_crack;
-        const int64_t n_inst = (int64_t)A.B * M;
-        const int chunk = A.chunks - 1 - (int)(t / n_inst);
-        const int64_t inst = t % n_inst;
-        const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
+        // (most items only get as far as the width test below, so the index arithmetic is kept 32-bit when it fits)
+        int chunk, b, j;
+        if (items <= 0x7fffffffLL) {
+            const uint32_t t = (uint32_t)(item - n_crack), n_inst = (uint32_t)A.B * (uint32_t)M;
+            const uint32_t cq = t / n_inst, inst = t - cq * n_inst;
+            chunk = A.chunks - 1 - (int)cq;
+            b = (int)(inst / (uint32_t)M);
+            j = (int)(inst - (uint32_t)b * (uint32_t)M);
+        } else {
+            const int64_t t = item - n_crack;
+            const int64_t n_inst = (int64_t)A.B * M;
+            chunk = A.chunks - 1 - (int)(t / n_inst);
+            const int64_t inst = t % n_inst;
+            b = (int)(inst / M);
+            j = (int)(inst - (int64_t)b * M);
+        }
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
         if (chunk > 0) {                                    // most (instance, chunk) items do not exist: decide that
             const float cx = (float)max(row[0], 1);         // from the box width alone (x part of paste_geometry)
@@ -690,9 +784,29 @@ extern "C" int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, in
         MLP_CUDA(cudaMemcpyAsync(crack_box_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     const int rows_per_cta = kRowsThreads / 32;
-    road_rows_kernel<<<dim3((frame_h + rows_per_cta - 1) / rows_per_cta, batch), kRowsThreads, 0, st>>>(
-        seg_dev, frame_h, frame_w, channels, road_channel, crack_channel >= 0 ? crack_channel : 0, row_ext,
-        road_bits_dev, crack_channel >= 0 ? crack_bits_dev : nullptr, crack_rows, crack_box_dev);
+    const dim3 rgrid((frame_h + rows_per_cta - 1) / rows_per_cta, batch);
+    const int crack_ch = crack_channel >= 0 ? crack_channel : 0;
+    uint32_t* cbits = crack_channel >= 0 ? crack_bits_dev : nullptr;
+    if (channels == 3 && frame_w % 4 == 0 && mlp_aligned16(seg_dev)) {
+#define MLP_ROAD3(R, C)                                                                                     \
+    road_rows3_kernel<R, C><<<rgrid, kRowsThreads, 0, st>>>(seg_dev, frame_h, frame_w, row_ext, road_bits_dev, \
+                                                            cbits, crack_rows, crack_box_dev)
+        switch (road_channel * 3 + crack_ch) {
+            case 0: MLP_ROAD3(0, 0); break;
+            case 1: MLP_ROAD3(0, 1); break;
+            case 2: MLP_ROAD3(0, 2); break;
+            case 3: MLP_ROAD3(1, 0); break;
+            case 4: MLP_ROAD3(1, 1); break;
+            case 5: MLP_ROAD3(1, 2); break;
+            case 6: MLP_ROAD3(2, 0); break;
+            case 7: MLP_ROAD3(2, 1); break;
+            default: MLP_ROAD3(2, 2); break;
+        }
+#undef MLP_ROAD3
+    } else {
+        road_rows_kernel<<<rgrid, kRowsThreads, 0, st>>>(seg_dev, frame_h, frame_w, channels, road_channel, crack_ch,
+                                                         row_ext, road_bits_dev, cbits, crack_rows, crack_box_dev);
+    }
     MLP_LAUNCH_CHECK(ctx);
     road_fit_kernel<<<batch, kScanThreads, 0, st>>>(row_ext, frame_h, default_road_size, unit_dev, crack_rows,
                                                   crack_part);

@@ -10,14 +10,19 @@ def main():
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", f"regex:{kern}"],
                          capture_output=True, text=True).stdout.splitlines()
-    rows, hdr, seen = [], None, False
+    rows, hdr, fname, files = [], None, "", set()
     for r in csv.reader(out):
+        if r and r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+            if fname in files:
+                break                                     # the same file again: the next launch
+            files.add(fname)
+            continue
         if r and r[0] == "Line No":
-            if seen:
-                break                                     # only the first launch
-            hdr, seen = r, True
+            hdr = r
             continue
         if hdr and len(r) == len(hdr) and r[0].strip().isdigit():
+            r[1] = fname + ": " + r[1].strip()
             rows.append(r)
     ie = hdr.index("Instructions Executed")
     sm = hdr.index("# Samples")
