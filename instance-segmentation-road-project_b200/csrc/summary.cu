@@ -305,24 +305,27 @@ road_fit_kernel(const int2* __restrict__ row_ext, int PH, float road_size, float
 }
 
 // Pass 3 (crack only): horizontal size of the crack pseudo-instance = max over columns of
-// sum_y unit[y] * bit[y,x].  One warp per 32-column word of the batch-wide crack box walks the box
-// rows (8 word loads in flight, zero words skipped), lane = column; the warp maximum goes to the
-// image's CrackPart with an atomicMax on the bit pattern (sums are >= 0, so the order is preserved).
-constexpr int kColsThreads = 128;
+// sum_y unit[y] * bit[y,x].  One CTA per 32-column word of the batch-wide crack box: its eight warps take the box
+// rows in interleaved runs of eight (eight word loads in flight, zero words skipped), lane = column; the warps'
+// column sums meet in shared memory, the maximum goes to the image's CrackPart with an atomicMax on the bit
+// pattern (sums are >= 0, so the order is preserved).
+constexpr int kColsThreads = 256;
 
 __global__ void __launch_bounds__(kColsThreads)
 crack_cols_kernel(const uint32_t* __restrict__ crack_bits, const float* __restrict__ unit,
                   const int32_t* __restrict__ crack_box, int PH, int words, CrackPart* __restrict__ crack_part) {
+    __shared__ double s_col[kColsThreads / 32][32];
     const int y0 = crack_box[0], x0 = crack_box[1], y1 = crack_box[2], x1 = crack_box[3];
     if (y1 < 0) return;                                     // no crack pixel in the batch
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wi = (x0 >> 5) + blockIdx.x * (kColsThreads / 32) + warp;
+    constexpr int nwarps = kColsThreads / 32;
+    const int wi = (x0 >> 5) + blockIdx.x;
     if (wi > (x1 >> 5)) return;
     const uint32_t* cb = crack_bits + (int64_t)b * PH * words + wi;
     const float* un = unit + (int64_t)b * PH;
     double col = 0.0;
-    for (int oy = y0; oy <= y1; oy += 8) {
+    for (int oy = y0 + 8 * warp; oy <= y1; oy += 8 * nwarps) {
         uint32_t cw[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) cw[u] = (oy + u <= y1) ? __ldg(cb + (int64_t)(oy + u) * words) : 0u;
@@ -330,9 +333,15 @@ crack_cols_kernel(const uint32_t* __restrict__ crack_bits, const float* __restri
         for (int u = 0; u < 8; ++u)
             if ((cw[u] >> lane) & 1u) col = __dadd_rn(col, (double)__ldg(un + oy + u));
     }
-    for (int o = 16; o > 0; o >>= 1) col = fmax(col, shfl_xor_d(col, o));
-    if (lane == 0 && col > 0.0)
-        atomicMax(&crack_part[b].colmax_bits, (unsigned long long)__double_as_longlong(col));
+    s_col[warp][lane] = col;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int w = 1; w < nwarps; ++w) col = __dadd_rn(col, s_col[w][lane]);
+        for (int o = 16; o > 0; o >>= 1) col = fmax(col, shfl_xor_d(col, o));
+        if (lane == 0 && col > 0.0)
+            atomicMax(&crack_part[b].colmax_bits, (unsigned long long)__double_as_longlong(col));
+    }
 }
 
 // CrackToInstance row (misc.py:521-533) from the batch-wide box; false when the region is empty
@@ -812,8 +821,8 @@ extern "C" int mlp_road_scan(mlp_ctx* ctx, const int32_t* seg_dev, int batch, in
                                                   crack_part);
     MLP_LAUNCH_CHECK(ctx);
     if (crack_channel >= 0) {
-        const int words = (frame_w + 31) / 32, wpc = kColsThreads / 32;
-        crack_cols_kernel<<<dim3((words + wpc - 1) / wpc, batch), kColsThreads, 0, st>>>(
+        const int words = (frame_w + 31) / 32;
+        crack_cols_kernel<<<dim3(words, batch), kColsThreads, 0, st>>>(
             crack_bits_dev, unit_dev, crack_box_dev, frame_h, words, crack_part);
         MLP_LAUNCH_CHECK(ctx);
     }
