@@ -177,3 +177,28 @@ def test_deterministic_on_another_stream():
     torch.cuda.synchronize()
     for o, l in outs:
         assert files_of(o, l) == ref
+
+
+def test_randomised_sizes_contents_and_qualities():
+    """24 random (height, width, batch, quality, content) draws, every file against the oracle byte for byte."""
+    import masklab_b200 as ml
+    rng = np.random.default_rng(2026)
+    for case in range(24):
+        H, W = int(rng.integers(1, 150)), int(rng.integers(1, 300))
+        if case % 6 == 0:
+            W = int(rng.integers(1, 12)) * 16                       # the aligned fast path of the pixel loads
+        B, quality = int(rng.integers(1, 4)), int(rng.integers(1, 101))
+        kind = case % 4
+        if kind == 0:
+            fr = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+        elif kind == 1:
+            fr = road_like(B, H, W, 100 + case)
+        elif kind == 2:
+            fr = np.full((B, H, W, 3), int(rng.integers(0, 256)), dtype=np.uint8)
+            fr[:, ::max(1, H // 3), :, :] = 255
+        else:
+            base = rng.integers(0, 256, (B, (H + 7) // 8, (W + 7) // 8, 3), dtype=np.uint8)
+            fr = np.repeat(np.repeat(base, 8, axis=1), 8, axis=2)[:, :H, :W].copy()   # flat 8x8 tiles: DC only
+        out, lengths = ml.EncodeImageContent(quality=quality).encode_batch(dev(fr))
+        for b, f in enumerate(files_of(out, lengths)):
+            assert f == jo.encode_jpeg(fr[b], quality), f"case {case} {H}x{W} q{quality} frame {b}"
