@@ -388,6 +388,16 @@ int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const 
                    const int32_t* m_dev, int mask_h, int mask_w, int frame_h, int frame_w,
                    const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
                    const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream);
+/* mlp_draw_tiles_boxes: mlp_draw_boxes followed by mlp_draw_tiles in one pass over the frame (the whole
+ *   visualisation branch of serving.py:34-40): the rectangles go into a one-bit-per-pixel map first, so the
+ *   frame is neither copied nor written before the overlay pass.  Same arguments and result as drawing the
+ *   boxes into a copy of the frame and handing that to mlp_draw_tiles.                           */
+int mlp_draw_tiles_boxes(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                   const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows, const int32_t* r_dev,
+                   int num_classes, const int32_t* counts_dev, int batch, int m_rows, int m_stride,
+                   const int32_t* m_dev, int mask_h, int mask_w, int frame_h, int frame_w,
+                   const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
+                   const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream);
 
 /* ---- training-side target assignment -------------------------------------
  * CalculateIOU.call (engine/layers/detection.py:391-422): aa_dev [Na, aa_stride >= 4], bb_dev

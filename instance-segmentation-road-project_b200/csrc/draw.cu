@@ -179,6 +179,8 @@ struct DrawTilesArgs {
     int B, m_rows, mh, mw, PH, PW;
     mlp_draw_colors inst, sem;
     uint8_t* out;
+    const uint32_t* line_bits; // [B, PH, line_words] pixels on DrawBoxes' rectangles (1 bit each), or NULL
+    int line_words;
 };
 
 // 4 consecutive channel-interleaved pixels (12 values) of a frame row as float
@@ -308,6 +310,7 @@ draw_tiles_kernel(const DrawTilesArgs A) {
             }
         };
         for (int c = 0; c < C; ++c) {
+            if (grouped && s_start[c] == s_start[c + 1]) continue;      // no instance of this class near the block
             float acc[4] = {0.f, 0.f, 0.f, 0.f};           // reduce_sum of the class's masks, order j
             if (grouped) {
                 // the usual case (at most 32 candidates): only this class's candidates, still in instance order
@@ -342,6 +345,16 @@ draw_tiles_kernel(const DrawTilesArgs A) {
     const bool vec = n == 4 && (A.PW & 3) == 0;            // 4-pixel groups are 12-byte / 48-byte aligned
     float img[12];
     load_px12(static_cast<const ImgT*>(A.images) + pix0 * 3, vec, n, img);
+    if (A.line_bits) {
+        // DrawBoxes in front of the overlays (serving.py:34): its uint8 canvas (clip + truncation for float frames)
+        // with the rectangles' pixels at 255; ox is a multiple of 4, so the four pixels share one word of the bitmap
+#pragma unroll
+        for (int i = 0; i < 12; ++i) img[i] = (float)__float2uint_rz(fminf(fmaxf(img[i], 0.0f), 255.0f));
+        const uint32_t lw = __ldg(A.line_bits + ((int64_t)b * A.PH + oy) * A.line_words + (ox >> 5)) >> (ox & 31);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((lw >> q) & 1u) img[q * 3] = img[q * 3 + 1] = img[q * 3 + 2] = 255.0f;
+    }
     float sc[4][3];
 #pragma unroll
     for (int q = 0; q < 4; ++q) sc[q][0] = sc[q][1] = sc[q][2] = 0.0f;
@@ -409,8 +422,25 @@ canvas_kernel(const float* __restrict__ images, int64_t n, uint8_t* __restrict__
     if (i < n) out[i] = (uint8_t)__float2uint_rz(fminf(fmaxf(__ldg(images + i), 0.0f), 255.0f));
 }
 
-// One warp per box: DrawBoxes.call (misc.py:486-497) corner arithmetic, then the four one-pixel
-// lines of tf.image.draw_bounding_boxes (draw_bounding_box_op.cc, restated in oracle/draw_oracle.py).
+// DrawBoxes.call (misc.py:486-497) corner arithmetic and the rectangle tf.image.draw_bounding_boxes draws for it
+// (draw_bounding_box_op.cc, restated in oracle/draw_oracle.py); false: nothing to draw.
+struct BoxRect { int y0, y1, x0, x1; };
+__device__ __forceinline__ bool box_rect(const int32_t* row, int H, int W, BoxRect& r) {
+    const float cx = (float)max(row[0], 0), cy = (float)max(row[1], 0);       // tf.maximum(det[..., :4], 0)
+    const float w = (float)max(row[2], 0), h = (float)max(row[3], 0);
+    const float fh = (float)H, fw = (float)W;
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    const float xmin = __fdiv_rn(__fsub_rn(cx, hw), fw), xmax = __fdiv_rn(__fadd_rn(cx, hw), fw);
+    const float ymin = __fdiv_rn(__fsub_rn(cy, hh), fh), ymax = __fdiv_rn(__fadd_rn(cy, hh), fh);
+    // box * (size - 1), converted to an integer by C++ truncation (toward zero)
+    r.y0 = __float2int_rz(__fmul_rn(ymin, (float)(H - 1))); r.y1 = __float2int_rz(__fmul_rn(ymax, (float)(H - 1)));
+    r.x0 = __float2int_rz(__fmul_rn(xmin, (float)(W - 1))); r.x1 = __float2int_rz(__fmul_rn(xmax, (float)(W - 1)));
+    if (r.y0 > r.y1 || r.x0 > r.x1) return false;
+    if (r.y0 >= H || r.y1 < 0 || r.x0 >= W || r.x1 < 0) return false;
+    return true;
+}
+
+// One warp per box: the four one-pixel lines, written into the frame.
 __global__ void __launch_bounds__(kDrawThreads)
 draw_boxes_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stride, const int32_t* __restrict__ m_dev,
                   int H, int W, uint8_t* __restrict__ out) {
@@ -421,18 +451,9 @@ draw_boxes_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stri
     const int64_t box = (int64_t)blockIdx.x * (kDrawThreads / 32) + (threadIdx.x >> 5);
     if (box >= (int64_t)B * M) return;
     const int b = (int)(box / M), j = (int)(box - (int64_t)b * M);
-    const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
-    const float cx = (float)max(row[0], 0), cy = (float)max(row[1], 0);       // tf.maximum(det[..., :4], 0)
-    const float w = (float)max(row[2], 0), h = (float)max(row[3], 0);
-    const float fh = (float)H, fw = (float)W;
-    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-    const float xmin = __fdiv_rn(__fsub_rn(cx, hw), fw), xmax = __fdiv_rn(__fadd_rn(cx, hw), fw);
-    const float ymin = __fdiv_rn(__fsub_rn(cy, hh), fh), ymax = __fdiv_rn(__fadd_rn(cy, hh), fh);
-    // box * (size - 1), converted to an integer by C++ truncation (toward zero)
-    const int y0 = __float2int_rz(__fmul_rn(ymin, (float)(H - 1))), y1 = __float2int_rz(__fmul_rn(ymax, (float)(H - 1)));
-    const int x0 = __float2int_rz(__fmul_rn(xmin, (float)(W - 1))), x1 = __float2int_rz(__fmul_rn(xmax, (float)(W - 1)));
-    if (y0 > y1 || x0 > x1) return;
-    if (y0 >= H || y1 < 0 || x0 >= W || x1 < 0) return;
+    BoxRect r;
+    if (!box_rect(det + ((int64_t)b * m_stride + j) * 6, H, W, r)) return;
+    const int y0 = r.y0, y1 = r.y1, x0 = r.x0, x1 = r.x1;
     const int y0c = max(y0, 0), y1c = min(y1, H - 1), x0c = max(x0, 0), x1c = min(x1, W - 1);
     uint8_t* img = out + (int64_t)b * H * W * 3;
     for (int x = x0c + lane; x <= x1c; x += 32) {
@@ -442,6 +463,34 @@ draw_boxes_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stri
     for (int y = y0c + lane; y <= y1c; y += 32) {
         if (x0 >= 0) { uint8_t* p = img + ((int64_t)y * W + x0) * 3; p[0] = p[1] = p[2] = 255; }
         if (x1 < W) { uint8_t* p = img + ((int64_t)y * W + x1) * 3; p[0] = p[1] = p[2] = 255; }
+    }
+}
+
+// The same lines as one bit per pixel ([B, H, words], zeroed before the launch) for draw_tiles_kernel: the frame is
+// then neither copied nor written before the overlay pass.  Horizontal lines are word-wide ORs.
+__global__ void __launch_bounds__(kDrawThreads)
+box_lines_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int H, int W,
+                 int words, uint32_t* __restrict__ bits) {
+    int M, thr;
+    paste_scalars(S, B, m_rows, M, thr);                  // the rows the tail kept (M on the device)
+    if (m_stride == 0) m_stride = M;
+    const int lane = threadIdx.x & 31;
+    const int64_t box = (int64_t)blockIdx.x * (kDrawThreads / 32) + (threadIdx.x >> 5);
+    if (box >= (int64_t)B * M) return;
+    const int b = (int)(box / M), j = (int)(box - (int64_t)b * M);
+    BoxRect r;
+    if (!box_rect(det + ((int64_t)b * m_stride + j) * 6, H, W, r)) return;
+    const int y0c = max(r.y0, 0), y1c = min(r.y1, H - 1), x0c = max(r.x0, 0), x1c = min(r.x1, W - 1);
+    uint32_t* img = bits + (int64_t)b * H * words;
+    for (int wi = (x0c >> 5) + lane; wi <= (x1c >> 5); wi += 32) {
+        const int lo = max(x0c - wi * 32, 0), hi = min(x1c - wi * 32, 31);
+        const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+        if (r.y0 >= 0) atomicOr(img + (int64_t)r.y0 * words + wi, m);
+        if (r.y1 < H) atomicOr(img + (int64_t)r.y1 * words + wi, m);
+    }
+    for (int y = y0c + lane; y <= y1c; y += 32) {
+        if (r.x0 >= 0) atomicOr(img + (int64_t)y * words + (r.x0 >> 5), 1u << (r.x0 & 31));
+        if (r.x1 < W) atomicOr(img + (int64_t)y * words + (r.x1 >> 5), 1u << (r.x1 & 31));
     }
 }
 
@@ -513,12 +562,12 @@ extern "C" int mlp_draw_instance(mlp_ctx* ctx, const void* images_dev, int image
     return MLP_OK;
 }
 
-extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
-                              const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows,
-                              const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch,
-                              int m_rows, int m_stride, const int32_t* m_dev, int mask_h, int mask_w, int frame_h,
-                              int frame_w, const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
-                              const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream) {
+static int draw_tiles_impl(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                           const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows,
+                           const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch,
+                           int m_rows, int m_stride, const int32_t* m_dev, int mask_h, int mask_w, int frame_h,
+                           int frame_w, const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
+                           const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream, bool boxes) {
     MLP_CHECK_ARG(ctx && images_dev && det_i32_dev && out_dev, "mlp_draw_tiles: NULL argument");
     MLP_CHECK_ARG(masks_i32_dev || (roi_masks_dev && counts_dev && num_classes >= 1 && r_rows >= 1),
                   "mlp_draw_tiles: neither int32 tiles nor a prepared fused tail");
@@ -563,13 +612,23 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
     }
     // scratch: geometry [B,m_rows] + bit rows [B,m_rows,mh] + M
     const int64_t n_inst = (int64_t)batch * m_rows;
-    const int64_t bytes = n_inst * (int64_t)sizeof(DrawGeom) + n_inst * mask_h * 4 + 16;
+    // (+ with boxes: one bit per frame pixel for DrawBoxes' rectangles)
+    const int line_words = (frame_w + 31) / 32;
+    const int64_t line_bytes = boxes ? (int64_t)batch * frame_h * line_words * 4 : 0;
+    const int64_t bytes = n_inst * (int64_t)sizeof(DrawGeom) + n_inst * mask_h * 4 + 16 + line_bytes;
     rc = mlp_ensure_scratch(ctx, MLP_ARENA_DRAW, bytes);
     if (rc) return rc;
     DrawGeom* geom = static_cast<DrawGeom*>(ctx->arena[MLP_ARENA_DRAW]);
     uint32_t* bits = reinterpret_cast<uint32_t*>(geom + n_inst);
     int32_t* m_used = reinterpret_cast<int32_t*>(bits + n_inst * mask_h);
+    uint32_t* line_bits = boxes ? reinterpret_cast<uint32_t*>(m_used + 4) : nullptr;
     const int wpc = kDrawThreads / 32;
+    if (boxes) {
+        MLP_CUDA(cudaMemsetAsync(line_bits, 0, (size_t)line_bytes, st));
+        box_lines_kernel<<<(int)((n_inst + wpc - 1) / wpc), kDrawThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
+                                                                                  frame_h, frame_w, line_words, line_bits);
+        MLP_LAUNCH_CHECK(ctx);
+    }
     pack_tiles_kernel<<<(int)((n_inst + wpc - 1) / wpc), kDrawThreads, 0, st>>>(
         det_i32_dev, S, batch, m_rows, m_stride, mask_h, mask_w, frame_h, frame_w, inst_colors->num_classes, geom,
         bits, m_used);
@@ -580,6 +639,7 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
     A.m_rows = m_rows; A.mh = mask_h; A.mw = mask_w; A.PH = frame_h; A.PW = frame_w; A.inst = *inst_colors;
     if (sem_colors) A.sem = *sem_colors;
     A.out = out_dev;
+    A.line_bits = line_bits; A.line_words = line_words;
     const dim3 grid((frame_w + kBlkW - 1) / kBlkW, (frame_h + kBlkH - 1) / kBlkH, batch);
     const bool seg_f = seg_dev && seg_dtype == MLP_F32;
     const int cs = !seg_dev ? 0 : (sem_colors->num_classes == 3 ? 3 : -1);
@@ -596,6 +656,29 @@ extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dt
 #undef MLP_DRAW_TILES
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
+}
+
+extern "C" int mlp_draw_tiles(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                              const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows,
+                              const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch,
+                              int m_rows, int m_stride, const int32_t* m_dev, int mask_h, int mask_w, int frame_h,
+                              int frame_w, const mlp_draw_colors* inst_colors, const void* seg_dev, int seg_dtype,
+                              const mlp_draw_colors* sem_colors, uint8_t* out_dev, mlp_stream_t stream) {
+    return draw_tiles_impl(ctx, images_dev, image_dtype, det_i32_dev, masks_i32_dev, roi_masks_dev, r_rows, r_dev,
+                           num_classes, counts_dev, batch, m_rows, m_stride, m_dev, mask_h, mask_w, frame_h, frame_w,
+                           inst_colors, seg_dev, seg_dtype, sem_colors, out_dev, stream, false);
+}
+
+extern "C" int mlp_draw_tiles_boxes(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,
+                                    const int32_t* masks_i32_dev, const float* roi_masks_dev, int r_rows,
+                                    const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch,
+                                    int m_rows, int m_stride, const int32_t* m_dev, int mask_h, int mask_w,
+                                    int frame_h, int frame_w, const mlp_draw_colors* inst_colors, const void* seg_dev,
+                                    int seg_dtype, const mlp_draw_colors* sem_colors, uint8_t* out_dev,
+                                    mlp_stream_t stream) {
+    return draw_tiles_impl(ctx, images_dev, image_dtype, det_i32_dev, masks_i32_dev, roi_masks_dev, r_rows, r_dev,
+                           num_classes, counts_dev, batch, m_rows, m_stride, m_dev, mask_h, mask_w, frame_h, frame_w,
+                           inst_colors, seg_dev, seg_dtype, sem_colors, out_dev, stream, true);
 }
 
 extern "C" int mlp_draw_boxes(mlp_ctx* ctx, const void* images_dev, int image_dtype, const int32_t* det_i32_dev,

@@ -108,10 +108,11 @@ class DrawInstance(Layer):
             ctypes.byref(col), ctx.view(out), ctx.stream()))
         return out
 
-    def from_tiles(self, inputs, seg_outs=None, semantic_colors=None, semantic_alpha=.3):
+    def from_tiles(self, inputs, seg_outs=None, semantic_colors=None, semantic_alpha=.3, boxes=False):
         """[images, det_outs int32 [B,M,6], ins_outs int32 [B,M,mh,mw]] -> the same image without the
         [B,M,PH,PW] tensor.  With seg_outs and semantic_colors, DrawSegmentation(semantic_colors,
-        semantic_alpha) over the result (serving.py:38-40) is applied in the same pass."""
+        semantic_alpha) over the result (serving.py:38-40) is applied in the same pass; with boxes=True
+        DrawBoxes()([images, det_outs]) (serving.py:34) goes in front of it, also in the same pass."""
         ctx = ctx_of(inputs[1])
         img, it = _image(ctx, inputs[0], "DrawInstance")
         det = inputs[1].to(torch.int32).contiguous()
@@ -127,7 +128,8 @@ class DrawInstance(Layer):
                 raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"DrawInstance: seg_outs {tuple(seg.shape)}")
             seg_ptr = ctx.view(seg)
         out = ctx.empty((B, PH, PW, 3), torch.uint8)
-        rt.check(ctx.lib.mlp_draw_tiles(
+        fn = ctx.lib.mlp_draw_tiles_boxes if boxes else ctx.lib.mlp_draw_tiles
+        rt.check(fn(
             ctx.handle, ctx.view(img), it, ctx.view(det), ctx.view(ins), null(), 0, null(), 0, null(), B, M, M,
             null(), mh, mw, PH, PW, ctypes.byref(col), seg_ptr, st,
             ctypes.byref(sem) if sem is not None else None, ctx.view(out), ctx.stream()))

@@ -295,14 +295,9 @@ class PostProcessPipeline:
         if not hasattr(self, "vis"):
             self.vis = c.empty((B, PH, PW, 3), torch.uint8)
         r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
-        if boxes:
-            if not hasattr(self, "vis_boxes"):
-                self.vis_boxes = c.empty((B, PH, PW, 3), torch.uint8)
-            rt.check(lib.mlp_draw_boxes(
-                c.handle, c.view(images), rt.MLP_U8 if images.dtype == torch.uint8 else rt.MLP_F32,
-                c.view(self.det_i32), B, K, K, c.view(self.trim_m), PH, PW, c.view(self.vis_boxes), c.stream()))
-            images = self.vis_boxes
-        rt.check(lib.mlp_draw_tiles(
+        # boxes=True: DrawBoxes' rectangles ride along as a one-bit-per-pixel map (no copy of the frame)
+        fn = lib.mlp_draw_tiles_boxes if boxes else lib.mlp_draw_tiles
+        rt.check(fn(
             c.handle, c.view(images), rt.MLP_U8 if images.dtype == torch.uint8 else rt.MLP_F32,
             c.view(self.det_i32), ctypes.c_void_p(None), c.view(roi_masks, torch.float32), L * K, r_dev, self.C,
             c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw, PH, PW, ctypes.byref(col),

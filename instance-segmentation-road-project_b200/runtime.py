@@ -129,6 +129,8 @@ SIGNATURES = {
     "mlp_draw_instance": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_draw_tiles": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I,
                             ctypes.POINTER(DrawColorsC), _P, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
+    "mlp_draw_tiles_boxes": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I,
+                                  ctypes.POINTER(DrawColorsC), _P, _I, ctypes.POINTER(DrawColorsC), _P, _P]),
     "mlp_jpeg_max_bytes": (_L, [_I, _I]),
     "mlp_jpeg_header": (_I, [_I, _I, _I, _P, _I]),
     "mlp_jpeg_encode": (_I, [_P, _P, _I, _I, _I, _I, _P, _L, _P, _P]),

@@ -81,6 +81,15 @@ def test_draw_from_tiles_equals_draw_of_pasted_masks(PH, PW, M):
     got2 = layer.from_tiles([dev(img), dev(det), dev(ins)], seg_outs=dev(seg), semantic_colors=SEM_COLORS,
                             semantic_alpha=0.3).cpu().numpy()
     assert np.array_equal(got2, want2)
+    # ... and with DrawBoxes in front (serving.py:34), uint8 and float32 frames
+    want3 = do.draw_segmentation(do.draw_instance(do.draw_boxes(img, det), det, masks, INST_COLORS, 0.3), seg, SEM_COLORS, 0.3)
+    got3 = layer.from_tiles([dev(img), dev(det), dev(ins)], seg_outs=dev(seg), semantic_colors=SEM_COLORS,
+                            semantic_alpha=0.3, boxes=True).cpu().numpy()
+    assert np.array_equal(got3, want3)
+    imgf = (img.astype(np.float32) * 1.1 - 9.5)                        # outside [0, 255] in places, fractional
+    want4 = do.draw_instance(do.draw_boxes(imgf, det), det, masks, INST_COLORS, 0.3)
+    got4 = layer.from_tiles([dev(imgf), dev(det), dev(ins)], boxes=True).cpu().numpy()
+    assert np.array_equal(got4, want4)
 
 
 def test_pipeline_draw():
