@@ -499,7 +499,7 @@ def run_ours(args, wl):
         st_ = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
         pipe.ctx.profile(False)
         ms_s = e0.elapsed_time(e1) / n_
-        graph_s_ms = None
+        graph_s_ms = graph_seq_ms = None
         if not args.no_graph:
             g_, _ = pipe.capture_serving(d_loc, d_cls, d_fmaps, d_masks, d_seg, d_img, INST_COLORS[:C], 0.3,
                                          semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
@@ -513,13 +513,26 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             graph_s_ms = e0.elapsed_time(e1) / n_
             del g_
+            g_, _ = pipe.capture_serving(d_loc, d_cls, d_fmaps, d_masks, d_seg, d_img, INST_COLORS[:C], 0.3,
+                                         semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True,
+                                         parallel_branches=False)
+            for _ in range(3):
+                g_.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_):
+                g_.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            graph_seq_ms = e0.elapsed_time(e1) / n_
+            del g_
         summary_leg = {
             "what": "decode+NMS+RoIAlign, then the two consumers of the masks in the serving graph - SummaryOutput "
                     "and the DrawBoxes+DrawInstance+DrawSegmentation overlay - straight from the mask tiles "
                     "(trim_and_summarize + draw, no [B,M,PH,PW] tensor), then the JPEG encode of every overlay frame "
                     "(EncodeImageContent, bytes identical to libjpeg); single stream, inputs resident in HBM",
             "value": world * B / (ms_s * 1e-3), "unit": "frames/s", "ms_per_step": ms_s,
-            "cuda_graph_ms_per_step": graph_s_ms,
+            "cuda_graph_ms_per_step": graph_s_ms, "cuda_graph_single_branch_ms_per_step": graph_seq_ms,
             "cuda_graph_value": (world * B / (graph_s_ms * 1e-3)) if graph_s_ms else None,
             "rows_per_image": Mo, "stage_ms": st_,
             "seg_bytes": int(h_seg.numel() * 4), "frame_bytes": int(h_img.numel()),

@@ -348,8 +348,10 @@ draw_tiles_kernel(const DrawTilesArgs A) {
     if (A.line_bits) {
         // DrawBoxes in front of the overlays (serving.py:34): its uint8 canvas (clip + truncation for float frames)
         // with the rectangles' pixels at 255; ox is a multiple of 4, so the four pixels share one word of the bitmap
+        if (sizeof(ImgT) != 1) {                           // uint8 frames are their own canvas
 #pragma unroll
-        for (int i = 0; i < 12; ++i) img[i] = (float)__float2uint_rz(fminf(fmaxf(img[i], 0.0f), 255.0f));
+            for (int i = 0; i < 12; ++i) img[i] = (float)__float2uint_rz(fminf(fmaxf(img[i], 0.0f), 255.0f));
+        }
         const uint32_t lw = __ldg(A.line_bits + ((int64_t)b * A.PH + oy) * A.line_words + (ox >> 5)) >> (ox & 31);
 #pragma unroll
         for (int q = 0; q < 4; ++q)

@@ -224,7 +224,7 @@ class PostProcessPipeline:
         return self.det_i32, self.pasted, self.trim_m
 
     def trim_and_summarize(self, rois, roi_masks, seg_outs, default_road_size=3.25, threshold=0.1,
-                           paste=False):
+                           paste=False, split=False):
         """SURVEY 8(f) rank 1 fused behind the tail: TrimInstances + UpSampleOutput, then
         SummaryOutput (road_project/setup/serving.py:45-48) evaluated straight from the mask tiles.
         With paste=False the [B,M,PH,PW] masks are never written (the serving graph only reduces
@@ -253,20 +253,32 @@ class PostProcessPipeline:
             self.road_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
             self.crack_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
             self.crack_box = c.empty((4 + 8 * B,), torch.int32)
-        rt.check(lib.mlp_trim_paste(
-            c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
-            float(ratio[0]), float(ratio[1]), K, PH, PW, self.paste_mode if paste else rt.MLP_PASTE_NONE,
-            c.view(self.det_i32), c.view(self.trim_counts), c.view(self.trim_m),
-            c.view(self.pasted) if paste else ctypes.c_void_p(None), st))
-        rt.check(lib.mlp_road_scan(
-            c.handle, c.view(seg_outs), B, PH, PW, S, ls.ROAD_CHANNEL, ls.CRACK_CHANNEL,
-            float(default_road_size), c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_bits),
-            c.view(self.crack_box), st))
-        rt.check(lib.mlp_tile_summary(
-            c.handle, c.view(self.det_i32), ctypes.c_void_p(None), masks_ptr, r_cap, r_dev, self.C,
-            c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw,
-            c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box),
-            PH, PW, float(threshold), c.view(self.summary), c.view(self.summary_m), c.view(self.trim_m), st))
+        def tail():
+            rt.check(lib.mlp_trim_paste(
+                c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
+                float(ratio[0]), float(ratio[1]), K, PH, PW, self.paste_mode if paste else rt.MLP_PASTE_NONE,
+                c.view(self.det_i32), c.view(self.trim_counts), c.view(self.trim_m),
+                c.view(self.pasted) if paste else ctypes.c_void_p(None), c.stream()))
+
+        def road():                    # needs only the semantic map
+            rt.check(lib.mlp_road_scan(
+                c.handle, c.view(seg_outs), B, PH, PW, S, ls.ROAD_CHANNEL, ls.CRACK_CHANNEL,
+                float(default_road_size), c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_bits),
+                c.view(self.crack_box), c.stream()))
+
+        def summarize():               # needs the tail and the road scan
+            rt.check(lib.mlp_tile_summary(
+                c.handle, c.view(self.det_i32), ctypes.c_void_p(None), masks_ptr, r_cap, r_dev, self.C,
+                c.view(self.trim_counts), B, K, K, ctypes.c_void_p(None), mh, mw,
+                c.view(self.road_unit), c.view(self.road_bits), c.view(self.crack_box),
+                PH, PW, float(threshold), c.view(self.summary), c.view(self.summary_m), c.view(self.trim_m), c.stream()))
+
+        self._compact_det = False
+        if split:                      # the caller enqueues the parts itself (capture_serving: on two streams)
+            return tail, road, summarize
+        tail()
+        road()
+        summarize()
         self._compact_det = False
         return self.det_i32, self.summary, self.summary_m
 
@@ -352,18 +364,44 @@ class PostProcessPipeline:
         return graph, rois
 
     def capture_serving(self, loc_pred, cls_pred, fmaps, roi_masks, seg_outs, images, instance_colors,
-                        instance_alpha=.3, semantic_colors=None, semantic_alpha=.3, boxes=True, quality=95):
+                        instance_alpha=.3, semantic_colors=None, semantic_alpha=.3, boxes=True, quality=95,
+                        parallel_branches=True):
         """The serving tail of one batch as ONE CUDA graph: detect_and_align -> trim_and_summarize -> draw ->
         encode (SummaryOutput, the three overlays and the JPEG files; road_project/setup/serving.py:29-48).  All of
-        it is sync-free, so the ~25 kernels replay as one launch.  Refill the same input tensors and call
+        it is sync-free, so the ~25 kernels replay as one launch; with parallel_branches the graph forks after the
+        tail (road scan + summary beside overlays + JPEG).  Refill the same input tensors and call
         `.replay()`; summary, overlay and files land in the pipeline's buffers (summary_view(), vis, jpeg_files,
         jpeg_len).  As with capture(), the mask head is not part of the graph."""
+        branch = torch.cuda.Stream(device=self.ctx.device)
+
         def run():
+            # two branches (different scratch arenas, no shared state), joined at the end: road scan from the start and
+            # the summary after the tail on one, detection, tail, overlays and JPEG on the other
+            cur = torch.cuda.current_stream(self.ctx.device)
+            if parallel_branches:
+                start = torch.cuda.Event()
+                start.record(cur)
             rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
-            self.trim_and_summarize(rois, roi_masks, seg_outs)
+            tail, road, summarize = self.trim_and_summarize(rois, roi_masks, seg_outs, split=True)
+            if parallel_branches:
+                with torch.cuda.stream(branch):             # the road scan only reads the semantic map: it runs beside
+                    branch.wait_event(start)                # the latency-bound NMS kernels
+                    road()
+            tail()
+            if parallel_branches:
+                fork = torch.cuda.Event()
+                fork.record(cur)
+                with torch.cuda.stream(branch):
+                    branch.wait_event(fork)
+                    summarize()
+            else:
+                road()
+                summarize()
             self.draw(rois, roi_masks, images, instance_colors, instance_alpha, seg_outs=seg_outs,
                       semantic_colors=semantic_colors, semantic_alpha=semantic_alpha, boxes=boxes)
             self.encode(quality=quality)
+            if parallel_branches:
+                cur.wait_stream(branch)
             return rois
         torch.cuda.synchronize(self.ctx.device)
         side = torch.cuda.Stream(device=self.ctx.device)
