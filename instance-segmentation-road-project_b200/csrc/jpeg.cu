@@ -467,6 +467,7 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
     __shared__ uint32_t s_dc[2][12];
     __shared__ uint32_t s_len[kPartBlocks];
     __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_cf[32][kPartBlocks];             // the thread's block, transposed: column t, never a bank conflict
     const int t = threadIdx.x, b = blockIdx.y;
     for (int i = t; i < 512; i += kPartBlocks) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
     if (t < 24) s_dc[t / 12][t % 12] = T.dc[t / 12][t % 12];
@@ -504,13 +505,15 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
         }
         const uint32_t* ac = s_ac[chroma];
         const int16_t* cf = coefs + gb * 64;
-        // non-zero mask of the 63 AC positions: the block's 128 bytes pass through registers once (and stay in L1 for
-        // the walk below); two coefficients per comparison
+        // non-zero mask of the 63 AC positions: the block's 128 bytes pass through registers once, on their way into this
+        // thread's column of shared memory (the walk below picks single coefficients from there); two per comparison
         uint64_t mask = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint4 x = __ldg(reinterpret_cast<const uint4*>(cf) + q);
             const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_cf[4 * q + j][t] = xs[j];
             uint32_t byte = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -524,14 +527,15 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
         // the set bits of one 32-bit half (32-bit ffs / clear-lowest are a quarter of the 64-bit instruction count)
         auto walk = [&](uint32_t m32, int base) {
             if (!m32) return;
+            auto coef = [&](int kk) { return (int)(int16_t)(s_cf[kk >> 1][t] >> (16 * (kk & 1))); };
             int k = base + __ffs((int)m32) - 1;
-            int v = (int)__ldg(cf + k);
+            int v = coef(k);
             for (;;) {
                 m32 &= m32 - 1;
                 int kn = 0, vn = 0;
                 if (m32) {                                   // the next coefficient is in flight while this one is coded
                     kn = base + __ffs((int)m32) - 1;
-                    vn = (int)__ldg(cf + kn);
+                    vn = coef(kn);
                 }
                 const int nb = nbits_of(v);
                 const int run = k - prev - 1;
