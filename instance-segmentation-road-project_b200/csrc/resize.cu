@@ -12,6 +12,7 @@
 // down-sampling read-bound; there is no reuse worth staging - neighbouring threads hit the same
 // source lines in L1.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -151,6 +152,133 @@ window_pass_kernel(const float* __restrict__ in, int64_t lines_outer, int len, i
     }
 }
 
+// The same opening in ONE pass over the map for window sizes up to kFusedMaxK: a CTA owns a 32 x 64 tile of one
+// channel, stages it with a halo of two windows (2 pt before, 2 pb after) in shared memory and runs the four separable
+// passes there - every element is read from and written to HBM once (the halo comes out of L2) instead of four times.
+// Positions outside the map are +inf for the erosion and -inf for the dilation (the reference skips them).  Every
+// pass gives a thread four consecutive outputs of a line (k + 3 taps for 4 outputs); tasks are numbered so that the
+// lanes of a warp sit on neighbouring lines (row pitch odd): no bank conflicts in either direction.
+constexpr int kFusedMaxK = 16;
+constexpr int kFusedTh = 32, kFusedTw = 64;
+constexpr int kFusedRh = kFusedTh + 2 * (kFusedMaxK - 1), kFusedRw = kFusedTw + 2 * (kFusedMaxK - 1);
+constexpr int kFusedPitch = kFusedRw | 1;
+
+// Four consecutive outputs p0 .. p0+3 of a line from the k + 3 taps src[base + j * step], j = 0 .. k+2 (output q
+// covers taps q .. q+k-1).  The taps all four share (3 .. k-1) are reduced once: k + 6 min/max for four outputs.
+// Tap indices are clamped to jmax (only the last three can pass it, and only for outputs nobody stores).
+template <bool kMax>
+__device__ __forceinline__ void window4(const float* __restrict__ src, int base, int step, int k, int jmax, float (&o)[4]) {
+    auto op = [](float a, float b) { return kMax ? fmaxf(a, b) : fminf(a, b); };
+    auto tap = [&](int j) { return src[base + min(j, jmax) * step]; };
+    if (k >= 4) {
+        float c = src[base + 3 * step];
+        for (int j = 4; j < k; ++j) c = op(c, src[base + j * step]);
+        const float t0 = src[base], t1 = src[base + step], t2 = src[base + 2 * step];
+        const float u0 = tap(k), u1 = tap(k + 1), u2 = tap(k + 2);
+        const float a = op(t1, t2), b = op(u0, u1);
+        o[0] = op(c, op(t0, a));
+        o[1] = op(c, op(a, u0));
+        o[2] = op(c, op(t2, b));
+        o[3] = op(c, op(b, u2));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = tap(q);
+            for (int j = 1; j < k; ++j) v = op(v, tap(q + j));
+            o[q] = v;
+        }
+    }
+}
+
+// dst[r][c] = min / max of src over the window [p - pt, p + pb] along x (kAlongX) or y, for r in [r0, r1), c in [c0, c1);
+// lim: valid extent of src along the window direction
+template <bool kMax, bool kAlongX>
+__device__ __forceinline__ void fused_window_pass(const float* __restrict__ src, float* __restrict__ dst, int r0, int r1,
+                                                  int c0, int c1, int pt, int k, int lim) {
+    const int nr = r1 - r0, nc = c1 - c0;
+    const int lines = kAlongX ? nr : nc, len = kAlongX ? nc : nr;
+    const int groups = (len + 3) >> 2;
+    for (int t = threadIdx.x; t < lines * groups; t += kResizeThreads) {
+        const int line = t % lines, p0 = (kAlongX ? c0 : r0) + (t / lines) * 4;
+        const int fixed = (kAlongX ? r0 : c0) + line;
+        const int first = p0 - pt;                                             // tap 0
+        float acc[4];
+        window4<kMax>(src, kAlongX ? fixed * kFusedPitch + first : first * kFusedPitch + fixed,
+                      kAlongX ? 1 : kFusedPitch, k, lim - 1 - first, acc);
+        const int pend = kAlongX ? c1 : r1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (p0 + q < pend) {
+                if (kAlongX) dst[fixed * kFusedPitch + p0 + q] = acc[q];
+                else dst[(p0 + q) * kFusedPitch + fixed] = acc[q];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(kResizeThreads)
+smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k, float weight, float* __restrict__ out) {
+    __shared__ float sa[kFusedRh * kFusedPitch];
+    __shared__ float sb[kFusedRh * kFusedPitch];
+    const int pt = (k - 1) / 2, pb = k - 1 - pt;
+    const int rh = kFusedTh + 2 * (k - 1), rw = kFusedTw + 2 * (k - 1);       // region actually used
+    const int b = blockIdx.z / S, c = blockIdx.z - b * S;
+    const int ty0 = blockIdx.y * kFusedTh, tx0 = blockIdx.x * kFusedTw;
+    const int oy = ty0 - 2 * pt, ox = tx0 - 2 * pt;                            // map coordinates of region (0, 0)
+    const float* img = in + (int64_t)b * H * W * S + c;
+    // stage the region (a warp per row, lanes along x); outside the map: +inf (skipped by the erosion)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool inside = oy >= 0 && oy + rh <= H && ox >= 0 && ox + rw <= W;    // CTA-uniform: no position to skip
+    for (int ry = warp; ry < rh; ry += kResizeThreads / 32) {
+        const int y = oy + ry;
+        const bool yin = y >= 0 && y < H;
+        const float* rowp = img + ((int64_t)y * W + ox) * S;
+        for (int rx = lane; rx < rw; rx += 32) {
+            const int x = ox + rx;
+            sa[ry * kFusedPitch + rx] = (inside || (yin && x >= 0 && x < W)) ? __ldg(rowp + (int64_t)rx * S) : INFINITY;
+        }
+    }
+    __syncthreads();
+    // erosion along x: every region row, columns [pt, rw - pb)
+    fused_window_pass<false, true>(sa, sb, 0, rh, pt, rw - pb, pt, k, rw);
+    __syncthreads();
+    // erosion along y: rows [pt, rh - pb)
+    fused_window_pass<false, false>(sb, sa, pt, rh - pb, pt, rw - pb, pt, k, rh);
+    __syncthreads();
+    // eroded values outside the map do not exist: -inf (skipped by the dilation); interior tiles have none
+    if (!inside) {
+        for (int ry = pt + warp; ry < rh - pb; ry += kResizeThreads / 32) {
+            const int y = oy + ry;
+            for (int rx = pt + lane; rx < rw - pb; rx += 32) {
+                const int x = ox + rx;
+                if (y < 0 || y >= H || x < 0 || x >= W) sa[ry * kFusedPitch + rx] = -INFINITY;
+            }
+        }
+        __syncthreads();
+    }
+    // dilation along x: rows [pt, rh - pb), columns of the tile [2 pt, 2 pt + Tw)
+    fused_window_pass<true, true>(sa, sb, pt, rh - pb, 2 * pt, 2 * pt + kFusedTw, pt, k, rw);
+    __syncthreads();
+    // dilation along y straight to the map, times the weight
+    {
+        const int groups = kFusedTh / 4;
+        float* o = out + (int64_t)b * H * W * S + c;
+        for (int t = threadIdx.x; t < kFusedTw * groups; t += kResizeThreads) {
+            const int col = t % kFusedTw, g = t / kFusedTw;
+            const int x = tx0 + col;
+            const int r0 = 2 * pt + g * 4;                                     // region row of the first output
+            float acc[4];
+            window4<true>(sb, (r0 - pt) * kFusedPitch + 2 * pt + col, kFusedPitch, k, rh - 1 - (r0 - pt), acc);
+            if (x < W) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int y = ty0 + g * 4 + q;
+                    if (y < H) o[((int64_t)y * W + x) * S] = __fmul_rn(acc[q], weight);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kResizeThreads)
 scale_kernel(const float* __restrict__ in, int64_t n, float weight, float* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * kResizeThreads + threadIdx.x; i < n;
@@ -175,6 +303,13 @@ extern "C" int mlp_semantic_smoothing(mlp_ctx* ctx, const float* in_dev, int bat
     const int grid = (int)(blocks < cap ? blocks : cap);
     if (kernel_size <= 0) {                                  // semantic.py:283-284
         scale_kernel<<<grid, kResizeThreads, 0, st>>>(in_dev, n, weight, out_dev);
+        MLP_LAUNCH_CHECK(ctx);
+        return MLP_OK;
+    }
+    if (kernel_size <= kFusedMaxK && (int64_t)batch * channels <= 65535 && !getenv("MLP_SMOOTH_PASSES")) {
+        const dim3 fgrid((width + kFusedTw - 1) / kFusedTw, (height + kFusedTh - 1) / kFusedTh, batch * channels);
+        smoothing_fused_kernel<<<fgrid, kResizeThreads, 0, st>>>(in_dev, height, width, channels, kernel_size, weight,
+                                                                 out_dev);
         MLP_LAUNCH_CHECK(ctx);
         return MLP_OK;
     }
