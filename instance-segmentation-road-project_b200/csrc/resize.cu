@@ -198,8 +198,12 @@ __device__ __forceinline__ void fused_window_pass(const float* __restrict__ src,
     const int nr = r1 - r0, nc = c1 - c0;
     const int lines = kAlongX ? nr : nc, len = kAlongX ? nc : nr;
     const int groups = (len + 3) >> 2;
-    for (int t = threadIdx.x; t < lines * groups; t += kResizeThreads) {
-        const int line = t % lines, p0 = (kAlongX ? c0 : r0) + (t / lines) * 4;
+    // task t = group * lines + line, walked with a stride of the CTA size: one division per pass, then additions
+    const int dl = kResizeThreads % lines, dg = kResizeThreads / lines;
+    int line = (int)threadIdx.x % lines, grp = (int)threadIdx.x / lines;
+    for (; grp < groups; line += dl, grp += dg) {
+        if (line >= lines) { line -= lines; ++grp; if (grp >= groups) break; }
+        const int p0 = (kAlongX ? c0 : r0) + grp * 4;
         const int fixed = (kAlongX ? r0 : c0) + line;
         const int first = p0 - pt;                                             // tap 0
         float acc[4];
@@ -230,11 +234,16 @@ smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k,
     const bool inside = oy >= 0 && oy + rh <= H && ox >= 0 && ox + rw <= W;    // CTA-uniform: no position to skip
     for (int ry = warp; ry < rh; ry += kResizeThreads / 32) {
         const int y = oy + ry;
-        const bool yin = y >= 0 && y < H;
-        const float* rowp = img + ((int64_t)y * W + ox) * S;
-        for (int rx = lane; rx < rw; rx += 32) {
-            const int x = ox + rx;
-            sa[ry * kFusedPitch + rx] = (inside || (yin && x >= 0 && x < W)) ? __ldg(rowp + (int64_t)rx * S) : INFINITY;
+        float* srow = sa + ry * kFusedPitch;
+        if (inside) {
+            const float* rowp = img + ((int64_t)y * W + ox) * S;
+            for (int rx = lane; rx < rw; rx += 32) srow[rx] = __ldg(rowp + rx * S);
+        } else {
+            const bool yin = y >= 0 && y < H;
+            for (int rx = lane; rx < rw; rx += 32) {
+                const int x = ox + rx;
+                srow[rx] = (yin && x >= 0 && x < W) ? __ldg(img + ((int64_t)y * W + x) * S) : INFINITY;
+            }
         }
     }
     __syncthreads();
