@@ -467,7 +467,7 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
     __shared__ uint32_t s_dc[2][12];
     __shared__ uint32_t s_len[kPartBlocks];
     __shared__ uint32_t s_warp[33];
-    __shared__ uint32_t s_cf[32][kPartBlocks];             // the thread's block, transposed: column t, never a bank conflict
+    __shared__ int16_t s_cf[64][kPartBlocks];              // the thread's block, transposed: column t
     const int t = threadIdx.x, b = blockIdx.y;
     for (int i = t; i < 512; i += kPartBlocks) s_ac[i >> 8][i & 255] = T.ac[i >> 8][i & 255];
     if (t < 24) s_dc[t / 12][t % 12] = T.dc[t / 12][t % 12];
@@ -513,7 +513,10 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
             const uint4 x = __ldg(reinterpret_cast<const uint4*>(cf) + q);
             const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s_cf[4 * q + j][t] = xs[j];
+            for (int j = 0; j < 4; ++j) {
+                s_cf[8 * q + 2 * j][t] = (int16_t)(xs[j] & 0xffffu);
+                s_cf[8 * q + 2 * j + 1][t] = (int16_t)(xs[j] >> 16);
+            }
             uint32_t byte = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -527,7 +530,7 @@ jpeg_enc_kernel(const int16_t* __restrict__ coefs, const int16_t* __restrict__ d
         // the set bits of one 32-bit half (32-bit ffs / clear-lowest are a quarter of the 64-bit instruction count)
         auto walk = [&](uint32_t m32, int base) {
             if (!m32) return;
-            auto coef = [&](int kk) { return (int)(int16_t)(s_cf[kk >> 1][t] >> (16 * (kk & 1))); };
+            auto coef = [&](int kk) { return (int)s_cf[kk][t]; };
             int k = base + __ffs((int)m32) - 1;
             int v = coef(k);
             for (;;) {
