@@ -461,3 +461,24 @@ def test_semantic_smoothing(ml, shape, k, weight):
     want = so.semantic_smoothing(x, k, weight)
     got = ml.SemanticSmoothing(kernel_size=k, weight=weight)(dev(x))
     assert got.dtype == torch.float32 and np.array_equal(host(got), want)
+
+
+@pytest.mark.parametrize("k", [2, 3, 9, 16, 17])
+def test_semantic_smoothing_tiles_and_window_sizes(ml, k):
+    """Several 32 x 64 tiles with partial ones at the right / bottom edge, window sizes either side of the fused
+    kernel's limit (16); the tile-fused opening, the four streaming passes and the oracle agree bit for bit."""
+    import os
+    from oracle import semantic_oracle as so
+    rng = np.random.default_rng(100 + k)
+    x = rng.random((2, 100, 203, 2)).astype(F32)
+    x[x < 0.35] = 0.0
+    want = so.semantic_smoothing(x, k, 1.25)
+    layer = ml.SemanticSmoothing(kernel_size=k, weight=1.25)
+    got = host(layer(dev(x)))
+    assert np.array_equal(got, want)
+    os.environ["MLP_SMOOTH_PASSES"] = "1"
+    try:
+        passes = host(layer(dev(x)))
+    finally:
+        del os.environ["MLP_SMOOTH_PASSES"]
+    assert np.array_equal(passes, want)
