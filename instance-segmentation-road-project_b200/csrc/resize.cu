@@ -163,18 +163,20 @@ constexpr int kFusedTh = 32, kFusedTw = 64;
 constexpr int kFusedRh = kFusedTh + 2 * (kFusedMaxK - 1), kFusedRw = kFusedTw + 2 * (kFusedMaxK - 1);
 constexpr int kFusedPitch = kFusedRw | 1;
 
-// Four consecutive outputs p0 .. p0+3 of a line from the k + 3 taps src[base + j * step], j = 0 .. k+2 (output q
-// covers taps q .. q+k-1).  The taps all four share (3 .. k-1) are reduced once: k + 6 min/max for four outputs.
-// Tap indices are clamped to jmax (only the last three can pass it, and only for outputs nobody stores).
-template <bool kMax>
-__device__ __forceinline__ void window4(const float* __restrict__ src, int base, int step, int k, int jmax, float (&o)[4]) {
+// Four consecutive outputs p0 .. p0+3 of a line from the K + 3 taps src[base + j * kStep], j = 0 .. K+2 (output q
+// covers taps q .. q+K-1).  The taps all four share (3 .. K-1) are reduced once: K + 6 min/max for four outputs.  K
+// and the step are compile-time: the taps are loads at immediate offsets, no loop.  Tap indices are clamped to jmax
+// (only the last three can pass it, and only for outputs nobody stores).
+template <bool kMax, int K, int kStep>
+__device__ __forceinline__ void window4(const float* __restrict__ src, int jmax, float (&o)[4]) {
     auto op = [](float a, float b) { return kMax ? fmaxf(a, b) : fminf(a, b); };
-    auto tap = [&](int j) { return src[base + min(j, jmax) * step]; };
-    if (k >= 4) {
-        float c = src[base + 3 * step];
-        for (int j = 4; j < k; ++j) c = op(c, src[base + j * step]);
-        const float t0 = src[base], t1 = src[base + step], t2 = src[base + 2 * step];
-        const float u0 = tap(k), u1 = tap(k + 1), u2 = tap(k + 2);
+    auto tap = [&](int j) { return src[min(j, jmax) * kStep]; };
+    if (K >= 4) {
+        float c = src[3 * kStep];
+#pragma unroll
+        for (int j = 4; j < K; ++j) c = op(c, src[j * kStep]);
+        const float t0 = src[0], t1 = src[kStep], t2 = src[2 * kStep];
+        const float u0 = tap(K), u1 = tap(K + 1), u2 = tap(K + 2);
         const float a = op(t1, t2), b = op(u0, u1);
         o[0] = op(c, op(t0, a));
         o[1] = op(c, op(a, u0));
@@ -184,17 +186,19 @@ __device__ __forceinline__ void window4(const float* __restrict__ src, int base,
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v = tap(q);
-            for (int j = 1; j < k; ++j) v = op(v, tap(q + j));
+#pragma unroll
+            for (int j = 1; j < K; ++j) v = op(v, tap(q + j));
             o[q] = v;
         }
     }
 }
 
-// dst[r][c] = min / max of src over the window [p - pt, p + pb] along x (kAlongX) or y, for r in [r0, r1), c in [c0, c1);
-// lim: valid extent of src along the window direction
-template <bool kMax, bool kAlongX>
+// dst[r][c] = min / max of src over the window [p - pt, p - pt + K - 1] along x (kAlongX) or y, for r in [r0, r1),
+// c in [c0, c1); lim: valid extent of src along the window direction
+template <bool kMax, bool kAlongX, int K>
 __device__ __forceinline__ void fused_window_pass(const float* __restrict__ src, float* __restrict__ dst, int r0, int r1,
-                                                  int c0, int c1, int pt, int k, int lim) {
+                                                  int c0, int c1, int lim) {
+    constexpr int pt = (K - 1) / 2;
     const int nr = r1 - r0, nc = c1 - c0;
     const int lines = kAlongX ? nr : nc, len = kAlongX ? nc : nr;
     const int groups = (len + 3) >> 2;
@@ -207,8 +211,8 @@ __device__ __forceinline__ void fused_window_pass(const float* __restrict__ src,
         const int fixed = (kAlongX ? r0 : c0) + line;
         const int first = p0 - pt;                                             // tap 0
         float acc[4];
-        window4<kMax>(src, kAlongX ? fixed * kFusedPitch + first : first * kFusedPitch + fixed,
-                      kAlongX ? 1 : kFusedPitch, k, lim - 1 - first, acc);
+        window4<kMax, K, kAlongX ? 1 : kFusedPitch>(
+            src + (kAlongX ? fixed * kFusedPitch + first : first * kFusedPitch + fixed), lim - 1 - first, acc);
         const int pend = kAlongX ? c1 : r1;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -219,12 +223,13 @@ __device__ __forceinline__ void fused_window_pass(const float* __restrict__ src,
     }
 }
 
+template <int K>
 __global__ void __launch_bounds__(kResizeThreads)
-smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k, float weight, float* __restrict__ out) {
+smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, float weight, float* __restrict__ out) {
     __shared__ float sa[kFusedRh * kFusedPitch];
     __shared__ float sb[kFusedRh * kFusedPitch];
-    const int pt = (k - 1) / 2, pb = k - 1 - pt;
-    const int rh = kFusedTh + 2 * (k - 1), rw = kFusedTw + 2 * (k - 1);       // region actually used
+    constexpr int pt = (K - 1) / 2, pb = K - 1 - pt;
+    constexpr int rh = kFusedTh + 2 * (K - 1), rw = kFusedTw + 2 * (K - 1);   // region actually used
     const int b = blockIdx.z / S, c = blockIdx.z - b * S;
     const int ty0 = blockIdx.y * kFusedTh, tx0 = blockIdx.x * kFusedTw;
     const int oy = ty0 - 2 * pt, ox = tx0 - 2 * pt;                            // map coordinates of region (0, 0)
@@ -248,10 +253,10 @@ smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k,
     }
     __syncthreads();
     // erosion along x: every region row, columns [pt, rw - pb)
-    fused_window_pass<false, true>(sa, sb, 0, rh, pt, rw - pb, pt, k, rw);
+    fused_window_pass<false, true, K>(sa, sb, 0, rh, pt, rw - pb, rw);
     __syncthreads();
     // erosion along y: rows [pt, rh - pb)
-    fused_window_pass<false, false>(sb, sa, pt, rh - pb, pt, rw - pb, pt, k, rh);
+    fused_window_pass<false, false, K>(sb, sa, pt, rh - pb, pt, rw - pb, rh);
     __syncthreads();
     // eroded values outside the map do not exist: -inf (skipped by the dilation); interior tiles have none
     if (!inside) {
@@ -265,18 +270,18 @@ smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k,
         __syncthreads();
     }
     // dilation along x: rows [pt, rh - pb), columns of the tile [2 pt, 2 pt + Tw)
-    fused_window_pass<true, true>(sa, sb, pt, rh - pb, 2 * pt, 2 * pt + kFusedTw, pt, k, rw);
+    fused_window_pass<true, true, K>(sa, sb, pt, rh - pb, 2 * pt, 2 * pt + kFusedTw, rw);
     __syncthreads();
     // dilation along y straight to the map, times the weight
     {
-        const int groups = kFusedTh / 4;
+        constexpr int groups = kFusedTh / 4;
         float* o = out + (int64_t)b * H * W * S + c;
         for (int t = threadIdx.x; t < kFusedTw * groups; t += kResizeThreads) {
             const int col = t % kFusedTw, g = t / kFusedTw;
             const int x = tx0 + col;
             const int r0 = 2 * pt + g * 4;                                     // region row of the first output
             float acc[4];
-            window4<true>(sb, (r0 - pt) * kFusedPitch + 2 * pt + col, kFusedPitch, k, rh - 1 - (r0 - pt), acc);
+            window4<true, K, kFusedPitch>(sb + (r0 - pt) * kFusedPitch + 2 * pt + col, rh - 1 - (r0 - pt), acc);
             if (x < W) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -286,6 +291,11 @@ smoothing_fused_kernel(const float* __restrict__ in, int H, int W, int S, int k,
             }
         }
     }
+}
+
+template <int K>
+void launch_smoothing_fused(dim3 grid, cudaStream_t st, const float* in, int H, int W, int S, float weight, float* out) {
+    smoothing_fused_kernel<K><<<grid, kResizeThreads, 0, st>>>(in, H, W, S, weight, out);
 }
 
 __global__ void __launch_bounds__(kResizeThreads)
@@ -317,8 +327,13 @@ extern "C" int mlp_semantic_smoothing(mlp_ctx* ctx, const float* in_dev, int bat
     }
     if (kernel_size <= kFusedMaxK && (int64_t)batch * channels <= 65535 && !getenv("MLP_SMOOTH_PASSES")) {
         const dim3 fgrid((width + kFusedTw - 1) / kFusedTw, (height + kFusedTh - 1) / kFusedTh, batch * channels);
-        smoothing_fused_kernel<<<fgrid, kResizeThreads, 0, st>>>(in_dev, height, width, channels, kernel_size, weight,
-                                                                 out_dev);
+#define MLP_SMOOTH_K(K) case K: launch_smoothing_fused<K>(fgrid, st, in_dev, height, width, channels, weight, out_dev); break;
+        switch (kernel_size) {
+            MLP_SMOOTH_K(1) MLP_SMOOTH_K(2) MLP_SMOOTH_K(3) MLP_SMOOTH_K(4) MLP_SMOOTH_K(5) MLP_SMOOTH_K(6)
+            MLP_SMOOTH_K(7) MLP_SMOOTH_K(8) MLP_SMOOTH_K(9) MLP_SMOOTH_K(10) MLP_SMOOTH_K(11) MLP_SMOOTH_K(12)
+            MLP_SMOOTH_K(13) MLP_SMOOTH_K(14) MLP_SMOOTH_K(15) MLP_SMOOTH_K(16)
+        }
+#undef MLP_SMOOTH_K
         MLP_LAUNCH_CHECK(ctx);
         return MLP_OK;
     }
