@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(kDctThreads, JPEG_DCT_MINB)
 jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_constant__ JpegTables T,
                 int16_t* __restrict__ coefs, int16_t* __restrict__ dcs) {
     __shared__ DctWarpSmem s_warp[kDctWarps];
-    __shared__ uint32_t s_rcp[2][64], s_hz[2][64];
+    // quantisation tables transposed per column of a block: the eight values a column-pass item needs are two 128-bit
+    // loads (rows of 12 words: the eight columns of a quarter-warp land in eight different bank groups)
+    __shared__ __align__(16) uint32_t s_rcp[2][8][12], s_hz[2][8][12];
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int b = blockIdx.z, my = blockIdx.y;
@@ -250,8 +252,8 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
     // quantisation tables, staged once per CTA: exact reciprocal, and div / 2 | zigzag position << 16
     {
         const int tb = t >> 6, n = t & 63;
-        s_rcp[tb][n] = T.rcp[tb][n];
-        s_hz[tb][n] = (uint32_t)(T.div[tb][n] >> 1) | ((uint32_t)T.izz[n] << 16);
+        s_rcp[tb][n & 7][n >> 3] = T.rcp[tb][n];
+        s_hz[tb][n & 7][n >> 3] = (uint32_t)(T.div[tb][n] >> 1) | ((uint32_t)T.izz[n] << 16);
     }
     __syncthreads();
     DctWarpSmem& S = s_warp[warp];
@@ -374,8 +376,12 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
             if (rd < rounds && item < n_here * 48) {
                 const int blk = item >> 3, col = item & 7;
                 const int tb = (blk == 4) | (blk == 5) | (blk >= 10);
-                const uint32_t* rcp = &s_rcp[tb][col];
-                const uint32_t* hz = &s_hz[tb][col];
+                const uint4 ra = *reinterpret_cast<const uint4*>(&s_rcp[tb][col][0]);
+                const uint4 rb = *reinterpret_cast<const uint4*>(&s_rcp[tb][col][4]);
+                const uint4 ha = *reinterpret_cast<const uint4*>(&s_hz[tb][col][0]);
+                const uint4 hb = *reinterpret_cast<const uint4*>(&s_hz[tb][col][4]);
+                const uint32_t rcp[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                const uint32_t hz[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
                 int d[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) d[r] = S.ws[blk][r * 9 + col];
@@ -383,8 +389,8 @@ jpeg_dct_kernel(const uint8_t* __restrict__ frames, JpegGeom G, const __grid_con
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     // (|d| + div / 2) / div, rounding half away from zero; the dividend is < 2^16: the reciprocal is exact
-                    const uint32_t hzr = hz[r * 8];
-                    const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r * 8]);
+                    const uint32_t hzr = hz[r];
+                    const int mag = (int)__umulhi((uint32_t)abs(d[r]) + (hzr & 0xffffu), rcp[r]);
                     S.outc[blk][hzr >> 16] = (int16_t)(d[r] < 0 ? -mag : mag);
                 }
             }
