@@ -70,3 +70,19 @@ def test_against_a_live_libjpeg_when_present():
         assert jo.encode_jpeg(img) == buf.getvalue()
         back = np.asarray(Image.open(io.BytesIO(jo.encode_jpeg(img))).convert("RGB")).astype(int)
         assert np.abs(back - img).mean() < 20                           # it decodes to the frame it came from
+
+
+def test_against_opencv_when_present():
+    """A second consumer of libjpeg-turbo (OpenCV's bundled build, BGR input): the same file except for the JFIF
+    density field (OpenCV writes unit 0, 1 x 1; tf.io.encode_jpeg writes unit 1 = inch, 300 x 300)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for H, W in ((48, 80), (35, 51)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        img = np.clip(np.stack([xx * 3 + yy, 255 - xx * 2, yy * 5], -1) + rng.normal(0, 10, (H, W, 3)), 0, 255).astype(np.uint8)
+        ok, buf = cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 95])
+        assert ok
+        theirs, mine = bytes(buf), jo.encode_jpeg(img)
+        assert len(theirs) == len(mine)
+        assert theirs[:13] == mine[:13] and theirs[18:] == mine[18:]          # all but density unit / X / Y
+        assert mine[13:18] == bytes([1, 0x01, 0x2C, 0x01, 0x2C]) and theirs[13:18] == bytes([0, 0, 1, 0, 1])
