@@ -26,6 +26,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
+    # BASELINE.json configs[0] / SURVEY §8 cfg-1: the serving graph's own shape - ONE 1920x1080 frame, the model at
+    # DownSampleInput resolution 540x960 (N=163,275), masks pasted at 1080x1920 (retinamasklab.py:601,
+    # road_project/setup/serving.py, engine/config.py:19); 5 instance classes (README: car/bump/manhole/steel/pothole)
+    "cfg1": dict(B=1, H=540, W=960, PH=1080, PW=1920, C=5, Cf=128, ratios="default", mu=-5.8,
+                 min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.6,
+                 nms_max_output_size=100, max_k=2, base_size=36),
     # BASELINE.json configs[1] / SURVEY §8 cfg-2: ResNeXt default ModelConfiguration shapes
     # (engine/config.py:53,60-64,83-86,150) with the north-star score threshold 0.05.
     "cfg2": dict(B=32, H=512, W=1024, PH=512, PW=1024, C=5, Cf=128, ratios="default", mu=-5.8,
@@ -56,6 +62,12 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--streams", type=int, default=6,
                     help="independent pipelines/streams per GPU; consecutive batches alternate between them")
+    ap.add_argument("--input-sets", type=int, default=3,
+                    help="distinct input sets per stream, rotated step by step: no tensor is read by two batches in "
+                         "flight and none is re-read before everything else has passed through L2")
+    ap.add_argument("--prefill", type=int, default=1,
+                    help="1: CropAndPadMask's zero background is streamed out on a second stream from the moment "
+                         "NMS has produced M (mlp_paste_prefill), the paste kernel writes the boxes only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
@@ -123,7 +135,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.0005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -186,7 +198,9 @@ class CpuSample:
 def run_reference(args, wl):
     """--impl reference: the reference's own implementation is Python over TensorFlow 1.x CPU
     kernels, which cannot be installed here; this arm times the C restatement of
-    that path on all host cores, on bounded samples of the same workload."""
+    that path on all host cores.  W warm-up steps, then exactly K timed steps; a step is a bounded
+    sample of the workload (one batch; fewer frames when K steps of a whole batch would not
+    end within a few minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -194,25 +208,29 @@ def run_reference(args, wl):
     threads = max(1, min(cores, 64))
     frames_per_step = max(threads, wl["B"])
     sample = CpuSample(wl, frames_per_step)
-    warm = max(0, min(args.warmup, 1))
-    for _ in range(warm):
+    _, w1 = sample.run(threads)                         # page faults, thread pool (untimed, before the W warm-ups)
+    budget_s = 150.0
+    if w1 * (args.steps + args.warmup) > budget_s:      # bound the whole run: fewer frames per step
+        frames_per_step = max(1, int(frames_per_step * budget_s / (w1 * (args.steps + args.warmup))))
+        sample.inputs = sample.inputs[:frames_per_step]
+    for _ in range(args.warmup):
         sample.run(threads)
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         sample.run(threads)
     wall = time.perf_counter() - t0
+    steps = args.steps
     fps = steps * frames_per_step / wall
     fps_bits = None
     if wl["PW"] % 8 == 0:
         sample_b = CpuSample(wl, frames_per_step, bits=True)
         sample_b.run(threads)
-        fps_bits = sample_b.run(threads, repeat=steps)[0]
+        fps_bits = sample_b.run(threads, repeat=max(1, min(steps, 5)))[0]
     desc = (f"{steps} step(s) x {frames_per_step} frames of workload {args.workload} through "
             f"oracle/c (uint8 paste), {threads} threads")
     line = {
         "impl": "reference", "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps,
-        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, wl),
@@ -229,8 +247,23 @@ def workload_config(args, wl):
                         f"Cf={wl['Cf']}, max_out={wl['nms_max_output_size']}, paste {wl['PW']}x{wl['PH']} uint8",
             "batch_per_gpu": wl["B"], "parallelism": f"image-sharded x{args.gpus}",
             "stream_frames": (args.frames or None), "cuda_graphs": bool(getattr(args, "graph_main", False)) and not args.frames,
-            "l2_policy": "inputs (>=365 MB) and outputs (>=1.6 GB) per step exceed the 126 MB L2",
+            "streams": args.streams, "input_sets_per_stream": args.input_sets, "prefill": bool(args.prefill),
+            "l2_policy": f"{args.input_sets} distinct input sets per stream rotated step by step (no tensor is read by "
+                         "two batches in flight); one set (>= 365 MB at cfg2) and one batch of outputs (>= 1.6 GB) each "
+                         "exceed the 126 MB L2",
             "score_mu": wl["mu"]}
+
+
+def source_hash():
+    """sha256 over the CUDA sources + the header: ties a committed ncu capture to the build that produced it."""
+    import hashlib
+    import masklab_b200.build as b
+    h = hashlib.sha256()
+    for f in sorted(b.sources() + [os.path.join(b.CSRC, "common.cuh"), os.path.join(b.CSRC, "paste_common.cuh"),
+                                   os.path.join(b.INCLUDE, "masklab_b200.h")]):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 # -------------------------------------------------------------------- ours -----
@@ -239,6 +272,7 @@ def run_ours(args, wl):
     import torch.distributed as dist
     import synth
     import masklab_b200 as ml
+    from masklab_b200 import dist as mdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,20 +285,12 @@ def run_ours(args, wl):
     if args.frames:
         # a stream of `frames` frames sharded by image: every rank owns frames/world of them and runs
         # them in batches of B (masklab_b200.dist.shard_frames / chunks); one gather at the end
-        from masklab_b200 import dist as mdist
         shard = mdist.shard_frames(args.frames, world, rank)
         args.steps = max(1, len(mdist.chunks(shard.padded, B)))
     cfgp, N, loc, cls, fmaps = make_inputs(wl, B, seed=100 + rank)
-    cfg = ml.DetectionConfig(paste_output="uint8", **kwargs_of(wl))
-    pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local)
-    ctx = pipe.ctx
+    cfg = ml.DetectionConfig(paste_output="uint8", prefill=bool(args.prefill), **kwargs_of(wl))
+    pipe = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local, private_context=True)
     K = pipe.K
-    # independent per-GPU streams (north star): batch i runs on pipeline/stream i % S, so the
-    # latency-bound NMS kernels of one batch overlap the bandwidth-bound RoIAlign/paste of another
-    S = max(1, args.streams)
-    pipes = [pipe] + [ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local,
-                                             private_context=True) for _ in range(S - 1)]
-    streams = [torch.cuda.Stream() for _ in range(S)]
 
     # host (pinned) copies for the end-to-end leg, device copies for the kernel-only leg
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -273,30 +299,53 @@ def run_ours(args, wl):
     d_fmaps = [f.cuda(non_blocking=True) for f in h_fmaps]
 
     # first pass: discover R (rows the mask head would produce) and make its synthetic output
+    l0 = pipe.ctx.launch_count()
     rois = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
     mf, R = rois.shapes()
     h_masks = pin(synth.mask_probs(B, R, C, seed=300 + rank))
     d_masks = h_masks.cuda()
     pipe.trim_and_paste(rois, d_masks)
+    launches_per_step = pipe.ctx.launch_count() - l0                 # this library's kernels in one pass of the path
     M = int(pipe.trim_m.item())
     counts = rois.counts.cpu().numpy()
     torch.cuda.synchronize()
 
+    # independent per-GPU streams (north star): batch i runs on pipeline/stream i % S, so the latency-bound NMS
+    # kernels of one batch overlap the bandwidth-bound RoIAlign/paste of another.  S pipelines and S*NSETS input
+    # sets must fit: both are trimmed to 80 % of the free memory (the stress workload holds 27 GB per pipeline).
+    S = max(1, args.streams)
+    NSETS = max(1, args.input_sets)
+    set_bytes = sum(t.numel() * t.element_size() for t in [d_loc, d_cls, d_masks] + d_fmaps)
+    free_b = torch.cuda.mem_get_info(local)[0]
+    pipe_bytes = pipe.device_bytes()
+    while S > 1 and (S - 1) * pipe_bytes + S * NSETS * set_bytes > 0.8 * free_b:
+        if NSETS > 2:
+            NSETS -= 1
+        else:
+            S -= 1
+    pipes = [pipe] + [ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg, device=local,
+                                             private_context=True) for _ in range(S - 1)]
+    streams = [torch.cuda.Stream(priority=-1) for _ in range(S)]     # above the pipelines' background-fill streams
+    # input set q = set 0 rolled by q frames along the batch axis: its own buffers (what L2 sees), the same
+    # statistics, detections that are the rolled detections of set 0 (same M, R)
+    def rolled(q):
+        if q == 0:
+            return dict(loc=d_loc, cls=d_cls, fmaps=d_fmaps, masks=d_masks)
+        r = lambda t: torch.roll(t, q % max(B, 1), dims=0) if B > 1 else t.clone()
+        return dict(loc=r(d_loc), cls=r(d_cls), fmaps=[r(f) for f in d_fmaps], masks=r(d_masks))
+    sets = [[rolled(k * NSETS + q) for q in range(NSETS)] for k in range(S)]
+
     state = {"i": 0}
     # streaming job: the detection records of every batch of the shard are kept for the final gather
-    stream_det = stream_cnt = None
-    if args.frames:
-        stream_det = torch.empty((args.steps * B, K, 6), dtype=torch.float32, device="cuda")
-        stream_cnt = torch.empty((args.steps * B,), dtype=torch.int32, device="cuda")
+    words = pipe.record.numel()
+    stream_rec = torch.empty((args.steps, words), dtype=torch.int32, device="cuda") if args.frames else None
 
     graphs = None
-    launches_per_step = None
     if args.graph_main and not args.frames:
-        # the path is sync-free, so a whole batch replays as ONE graph launch per stream
+        # the path is sync-free, so a whole batch replays as ONE graph launch per (stream, input set)
         try:
-            l0 = sum(p.ctx.launch_count() for p in pipes)
-            graphs = [p.capture(d_loc, d_cls, d_fmaps, d_masks)[0] for p in pipes]
-            launches_per_step = (sum(p.ctx.launch_count() for p in pipes) - l0) // (3 * S)    # 2 warm-ups + capture
+            graphs = [[pipes[k].capture(z["loc"], z["cls"], z["fmaps"], z["masks"])[0] for z in sets[k]]
+                      for k in range(S)]
         except Exception as exc:                     # pragma: no cover - fall back to eager launches
             print(f"CUDA graph capture failed, eager launches instead: {exc!r}", file=sys.stderr)
             graphs = None
@@ -304,17 +353,17 @@ def run_ours(args, wl):
     def step():
         i = state["i"]
         k = i % S
+        q = (i // S) % NSETS
         state["i"] += 1
         with torch.cuda.stream(streams[k]):
             if graphs is not None:
-                graphs[k].replay()
+                graphs[k][q].replay()
                 return
-            r = pipes[k].detect_and_align(d_loc, d_cls, d_fmaps)
-            pipes[k].trim_and_paste(r, d_masks)
-            if stream_det is not None:
-                s0 = (i % args.steps) * B
-                stream_det[s0:s0 + B].copy_(pipes[k].det, non_blocking=True)
-                stream_cnt[s0:s0 + B].copy_(pipes[k].counts, non_blocking=True)
+            z = sets[k][q]
+            r = pipes[k].detect_and_align(z["loc"], z["cls"], z["fmaps"])
+            pipes[k].trim_and_paste(r, z["masks"])
+            if stream_rec is not None:
+                stream_rec[i % args.steps].copy_(pipes[k].record, non_blocking=True)
 
     def join_streams():
         for s_ in streams:
@@ -324,91 +373,124 @@ def run_ours(args, wl):
         for s_ in streams:
             s_.wait_stream(torch.cuda.current_stream())
 
-    gathered = None
-    g_det, g_cnt = (stream_det, stream_cnt) if args.frames else (pipe.det, pipe.counts)
-    if world > 1:
-        gathered = [torch.empty_like(g_det) for _ in range(world)]
-        gathered_counts = [torch.empty_like(g_cnt) for _ in range(world)]
+    # the one collective of the path: ONE all_gather_into_tensor of the packed records (det + counts in one buffer
+    # that the cross-class NMS kernel wrote in place)
+    g_src = stream_rec.view(-1) if args.frames else pipe.record
+    gathered = torch.empty((world, g_src.numel()), dtype=torch.int32, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    fork_streams()
-    for _ in range(max(args.warmup, 3) * S):
-        step()
-    join_streams()
-    barrier()
-    launches0 = sum(p.ctx.launch_count() for p in pipes)
-    for p in pipes:
-        p.ctx.profile(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    warm = max(args.warmup, 3)
+    with ClockSampler(local) as clocks:                # clocks are sampled over warm-up + timed region
+        fork_streams()
+        for _ in range(warm * S):
+            step()
+        join_streams()
+        if world > 1:                                  # the collective is warmed like everything else
+            mdist.gather_records(g_src, out=gathered)
+        barrier()
+        state["i"] = 0
+        ev0, evg, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         barrier()
         ev0.record()
         fork_streams()
         for _ in range(args.steps):
             step()
         join_streams()
-        if world > 1:           # the one collective of the path: gather detections at the end
-            dist.all_gather(gathered, g_det)
-            dist.all_gather(gathered_counts, g_cnt)
+        evg.record()
+        if world > 1:
+            mdist.gather_records(g_src, out=gathered)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = sum(p.ctx.launch_count() for p in pipes) - launches0
-    if graphs is not None:
-        launches = launches_per_step * args.steps           # kernels inside the replayed graphs
-    stages = {}
-    for p in pipes:
-        for k_, (t_, n_) in p.ctx.profile_read().items():
-            a_, b_ = stages.get(k_, (0.0, 0))
-            stages[k_] = (a_ + t_, b_ + n_)
-        p.ctx.profile(False)
+    compute_ms, gather_ms = ev0.elapsed_time(evg), evg.elapsed_time(ev1)
+    launches = launches_per_step * args.steps           # counted on an eager pass; a graph replays the same kernels
+    per_rank = None
+    gather_verified = oracle_verified = None
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.tensor([ms, compute_ms, gather_ms], device="cuda")
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"total_ms": [float(x[0]) for x in allt], "compute_ms": [float(x[1]) for x in allt],
+                    "gather_ms": [float(x[2]) for x in allt]}
+        ms = max(per_rank["total_ms"])
+        # what NCCL delivered in the timed region is what the ranks sent (own slice bit-equal, 64-bit checksums
+        # of every slice exchanged); then a second, untimed gather of set 0's records, of which rank 0 checks
+        # frame 0 of EVERY rank against the C restatement of the reference path
+        gather_verified = mdist.verify_gather(gathered, g_src)
+        if not args.frames:
+            r0 = pipe.detect_and_align(d_loc, d_cls, d_fmaps, prefill=False)
+            torch.cuda.synchronize()
+            g2 = mdist.gather_records(pipe.record)
+            gather_verified = gather_verified and mdist.verify_gather(g2, pipe.record)
+            if rank == 0:
+                oracle_verified = verify_against_oracle(wl, g2.cpu(), B, K, world)
     fps = world * B * args.steps / (ms * 1e-3)
 
-    # ---- isolated pass: the same step on ONE stream, for per-kernel times free of overlap
-    iso = {}
-    if S > 1:
-        pipe.ctx.profile(True)
-        iso_steps = max(10, min(50, args.steps))
+    # ---- isolated pass: the same step on ONE stream with eager launches, for per-kernel times free of overlap
+    # (prefill off: every kernel of the path alone on the GPU, brackets = CUDA events on the launching stream)
+    def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
         e0.record()
-        for _ in range(iso_steps):
-            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
-            pipe.trim_and_paste(r_, d_masks)
+        for _ in range(n):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        iso = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
-        iso["_step_ms"] = e0.elapsed_time(e1) / iso_steps
-        pipe.ctx.profile(False)
+        return e0.elapsed_time(e1) / n
 
-    # ---- the same step as ONE CUDA graph launch (single stream): what the launch gaps cost
-    graph_ms = None
+    iso_steps = max(10, min(50, args.steps))
+    pipe.ctx.profile(True)
+
+    def eager_plain():
+        r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps, prefill=False)
+        pipe.trim_and_paste(r_, d_masks)
+    step_plain_ms = timed(eager_plain, iso_steps)
+    iso = {k_: v_[0] / v_[1] for k_, v_ in pipe.ctx.profile_read().items()}
+    iso["_step_ms"] = step_plain_ms
+    pipe.ctx.profile(False)
+    # the fill alone (one stream, nothing beside it) and the boxes-only paste behind a fill
+    fill_ms = box_ms = None
+    if pipe._can_prefill():
+        fill_ms = timed(pipe.prefill_background, iso_steps)
+        pipe.ctx.profile(True)
+
+        def eager_prefilled():
+            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps, prefill=True)
+            pipe.trim_and_paste(r_, d_masks)
+        iso["_step_prefill_ms"] = timed(eager_prefilled, iso_steps)
+        pf = pipe.ctx.profile_read()
+        pipe.ctx.profile(False)
+        box_ms = pf["paste"][0] / pf["paste"][1] if "paste" in pf else None
+
+    # ---- the same step as ONE CUDA graph launch (single stream): what the launch gaps cost, with the
+    # background fill forked inside the graph and without it
+    graph_ms = graph_plain_ms = None
     if not args.no_graph:
         try:
-            g_, _ = pipe.capture(d_loc, d_cls, d_fmaps, d_masks)
-            for _ in range(3):
-                g_.replay()
-            torch.cuda.synchronize()
-            n_ = max(10, min(100, args.steps))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(n_):
-                g_.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            graph_ms = e0.elapsed_time(e1) / n_
-            del g_
+            for pf_on in (True, False):
+                if pf_on and not pipe._can_prefill():
+                    continue
+                g_, _ = pipe.capture(d_loc, d_cls, d_fmaps, d_masks, prefill=pf_on)
+                v_ = timed(g_.replay, max(10, min(100, args.steps)))
+                if pf_on:
+                    graph_ms = v_
+                else:
+                    graph_plain_ms = v_
+                del g_
         except Exception as exc:                     # pragma: no cover
             graph_ms = f"capture failed: {exc!r}"
+    if graph_ms is None:
+        graph_ms = graph_plain_ms
 
-    # ---- roofline of the dominant kernel (mask paste): algorithmic bytes = B*M*PH*PW uint8
+    # ---- roofline of the dominant kernel: the one that writes the [B,M,PH,PW] uint8 masks.  With prefill that
+    # is paste_fill_kernel (the zero background: every byte of the output once), timed ALONE on one stream;
+    # without it paste_kernel<uint8> (background + boxes in one kernel), timed alone in the eager pass above.
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -417,44 +499,48 @@ def run_ours(args, wl):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    paste_ms, paste_n = stages.get("paste", (0.0, 0))
     paste_bytes = B * M * PH * PW
-    bracket_ms = (paste_ms / paste_n) if paste_n else None          # event bracket inside the timed region
-    # With S > 1 streams a bracket spans time the kernel shares with kernels of other batches, so
-    # the kernel's own duration is taken from the single-stream pass of the same process (below
-    # the timed region); with S == 1 the two coincide.
-    launch_ms = iso.get("paste") if iso else bracket_ms
+    use_fill = bool(args.prefill) and fill_ms is not None
+    launch_ms = fill_ms if use_fill else iso.get("paste")
+    kernel = ("paste_fill_kernel (CropAndPadMask's zero background, mlp_paste_prefill)" if use_fill
+              else "paste_kernel<uint8> (CropAndPadMask + >0.5)")
     achieved = (paste_bytes / (launch_ms * 1e-3) / 1e9) if launch_ms else None
     step_bytes = algorithmic_bytes(wl, N, M)
-    traffic = None                                   # dram read+write of the paste kernel from the committed
-    try:                                             # ncu --set full capture (cfg2 only), per launch
-        if args.workload == "cfg2":
-            with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"].get("paste_kernel<1>")
+    # DRAM bytes of that kernel from the committed ncu --set full capture - only when the capture was taken from
+    # THIS build (hash of the CUDA sources) and this workload; otherwise null
+    traffic = traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
+            tj = json.load(f)
+        if tj.get("source_hash") == source_hash() and tj.get("workload") == args.workload:
+            traffic = tj["dram_bytes_per_launch"].get("paste_fill_kernel" if use_fill else "paste_kernel<1, 0>")
+            traffic_src = tj.get("source")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "paste_kernel<uint8> (CropAndPadMask + >0.5)",
+    write_peak = 7232.0                               # cudaMemsetAsync on this pool (profiles/write_bw_r01.txt)
+    roofline = {"bound": "hbm", "kernel": kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                "source_hash": source_hash(),
                 "peak_kind": peak_kind, "bytes_per_launch": paste_bytes,
                 "peak_note": "the measured peak is a read+write COPY figure; a write-only stream (this kernel) "
                              "reaches 7232 GB/s with cudaMemsetAsync on the same pool (profiles/write_bw_r01.txt), "
-                             "so frac can exceed 1",
-                "frac_of_write_only_peak": (achieved / 7232.0) if achieved else None,
+                             "so frac can exceed 1; frac_of_write_only_peak is the stricter figure",
+                "frac_of_write_only_peak": (achieved / write_peak) if achieved else None,
                 "avg_launch_ms": launch_ms,
-                "how": ("CUDA events recorded by the library around the launch on its stream; "
-                        + ("single-stream pass of this process (kernel alone on the GPU)" if iso else
-                           "inside the timed region")),
-                "timed_region": {"streams": S, "paste_bracket_ms": bracket_ms,
-                                 "stage_bracket_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
-                                 "note": "with several streams brackets overlap kernels of other batches"},
+                "how": "CUDA events on the launching stream around the launch, kernel alone on the GPU "
+                       "(single-stream pass of this process, after the timed region)",
+                "paste_kernel_full_ms": iso.get("paste"), "paste_fill_ms": fill_ms, "paste_boxes_only_ms": box_ms,
                 "whole_step": {"algorithmic_bytes": step_bytes,
                                "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
-                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                               "frac_of_write_only_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / write_peak,
+                               "streams": S, "input_sets_per_stream": NSETS},
                 "cuda_graph_single_stream_ms_per_step": graph_ms,
-                "single_stream": ({"ms_per_step": iso.get("_step_ms"),
-                                   "stage_ms": {k_: v_ for k_, v_ in iso.items() if not k_.startswith("_")}}
-                                  if iso else None)}
+                "cuda_graph_single_stream_no_prefill_ms_per_step": graph_plain_ms,
+                "latency_us_per_frame_single_stream_graph": (1e3 * graph_ms / B) if isinstance(graph_ms, float) else None,
+                "single_stream": {"ms_per_step": iso.get("_step_ms"), "ms_per_step_prefill": iso.get("_step_prefill_ms"),
+                                  "stage_ms": {k_: v_ for k_, v_ in iso.items() if not k_.startswith("_")}}}
 
     # ---- end to end through the public API with host buffers
     e2e = e2e_bits = None
@@ -462,8 +548,9 @@ def run_ours(args, wl):
         e2e = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier)
         if PW % 8 == 0:
             # same path, masks delivered 1 bit per pixel (lossless, 8x fewer bytes over PCIe)
-            del pipes[1:]
-            cfg_b = ml.DetectionConfig(paste_output="bits", **kwargs_of(wl))
+            del graphs, sets, pipes[1:]
+            torch.cuda.empty_cache()
+            cfg_b = ml.DetectionConfig(paste_output="bits", prefill=bool(args.prefill), **kwargs_of(wl))
             pipe_b = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg_b, device=local,
                                             private_context=True)
             e2e_bits = run_e2e(args, wl, pipe_b, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=True)
@@ -477,7 +564,7 @@ def run_ours(args, wl):
         d_img = h_img.cuda()
 
         def serve():
-            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps)
+            r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps, prefill=False)       # no masks are written
             pipe.trim_and_summarize(r_, d_masks, d_seg)
             pipe.draw(r_, d_masks, d_img, INST_COLORS[:C], 0.3, seg_outs=d_seg, semantic_colors=SEM_COLORS,
                       semantic_alpha=0.3, boxes=True)
@@ -556,7 +643,11 @@ def run_ours(args, wl):
             summary_leg["cpu_port"] = cpu_serving_tail(wl, frames=2)
         line = {
             "metric": "frames/sec decode+NMS+RoIAlign+mask-paste", "value": fps, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "compute_ms": compute_ms, "gather_ms": gather_ms, "per_rank": per_rank,
+            "gather_verified": gather_verified, "gather_oracle_verified": oracle_verified,
+            "gather": (None if world == 1 else {"collective": "one all_gather_into_tensor (NCCL) of the packed records",
+                                                "bytes_per_rank": int(g_src.numel() * 4), "warmed": True}),
             "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.frames else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -617,6 +708,26 @@ def cpu_jpeg(frame):
         from oracle import jpeg_oracle as jo
         jo.encode_jpeg(frame)
         return "oracle/jpeg_oracle.py (NumPy restatement)"
+
+
+def verify_against_oracle(wl, gathered, B, K, world):
+    """Rank 0: frame 0 of EVERY rank's gathered detection records against the C restatement of the reference
+    path on that rank's own seeded inputs (regenerated here on the host)."""
+    from masklab_b200 import dist as mdist
+    from oracle import c_oracle as co
+    det, counts = mdist.unpack_records(gathered, B, K)
+    kw = {k: wl[k] for k in ("min_confidence", "nms_iou_threshold", "post_iou_threshold", "nms_max_output_size")}
+    ok = True
+    for r in range(world):
+        cfgp, N, loc, cls, _ = make_inputs(wl, B, seed=100 + r)
+        prior = co.prior_layer(cfgp, wl["H"], wl["W"])
+        boxes = co.restore_boxes(loc[:1], prior)
+        want = co.detection_proposal(cls[:1], boxes, **kw)               # [1,M0,6], -1 padded to its own count
+        n = int(counts[r * B])
+        got = det[r * B, :n].numpy()
+        m0 = int((want[0, :, 4] != -1).sum())
+        ok = ok and n == m0 and bool((got == want[0, :n]).all())
+    return bool(ok)
 
 
 def algorithmic_bytes(wl, N, M):
@@ -691,7 +802,7 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             s_cmp.wait_event(ev_in)
             if state["out_done"] is not None:
                 s_cmp.wait_event(state["out_done"])         # previous results copied out
-            r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"])
+            r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"], prefill=(None if not summary else False))
             vis = None
             if summary:
                 det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])

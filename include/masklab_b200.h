@@ -42,6 +42,7 @@ extern "C" {
 #define MLP_ENOMEM     -3        /* scratch allocation failed                        */
 #define MLP_EDLPACK    -4        /* DLPack tensor rejected (dtype/device/strides)    */
 #define MLP_EBATCH     -5        /* B > 32: tf.dynamic_partition(...,32), misc.py:275 */
+#define MLP_EFROZEN    -6        /* scratch would have to grow while a CUDA graph references it */
 
 #define MLP_MAX_LEVELS   8
 #define MLP_MAX_ANCHORS  32
@@ -62,6 +63,12 @@ int         mlp_ctx_sm_count(const mlp_ctx* ctx);
 int64_t     mlp_ctx_scratch_bytes(const mlp_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench `gpu_launches`). */
 int64_t     mlp_ctx_launch_count(const mlp_ctx* ctx);
+/* Scratch arenas are grow-only and regrowth frees the old block.  A captured CUDA graph keeps
+ * pointers into them, so whoever captures calls mlp_ctx_freeze_scratch(ctx, 1) after the warm-up
+ * run: from then on a call that would need more scratch returns MLP_EFROZEN (nothing is freed)
+ * until the graph is dropped and the ctx thawed with freeze = 0.  Growth attempted while a
+ * stream capture is active fails with MLP_ECUDA and a message that says so.                 */
+int         mlp_ctx_freeze_scratch(mlp_ctx* ctx, int freeze);
 
 /* ---- per-stage timing (bench.py roofline) -----------------------------------
  * When enabled, every stage function brackets its kernels with a pair of CUDA events on
@@ -224,6 +231,11 @@ int mlp_upsample_output(mlp_ctx* ctx, const float* det_dev, int64_t rows, float 
                              = pixel 8*i+k (numpy packbits bitorder='little'); PW % 8 == 0       */
 #define MLP_PASTE_NONE 3  /* mlp_trim_paste only: prepare the tail (int boxes, tile table), write no masks;
                            * out_dev may be NULL and M is left to mlp_tile_summary                    */
+/* flags OR-ed into mlp_trim_paste's out_mode */
+#define MLP_PASTE_PREFILLED 0x100 /* out_dev's [B,M,PH,PW] prefix was zeroed by mlp_paste_prefill: write the boxes only */
+#define MLP_MASKS_PLANAR    0x200 /* roi_masks_dev is [B,R,C,mh,mw] (one plane per class, what a channels-first mask
+                                   * head produces) instead of the reference's [B,R,mh,mw,C]: the tail then reads
+                                   * only the instance's own class plane (1/C of the bytes)                        */
 /* det_i32_dev [B,M,6], masks_i32_dev i32 [B,M,mh,mw] -> out_dev [B,M,PH,PW].
  * M is read from m_dev (i32 [1]) when not NULL, else m_rows; m_stride is the row
  * stride of det/masks per image.  A box clipped to zero area gives an all-zero mask
@@ -265,6 +277,22 @@ int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const float* roi_ma
                    float ratio_h, float ratio_w, int k_rows, int frame_h, int frame_w, int out_mode,
                    int32_t* det_i32_dev, int32_t* counts_dev, int32_t* m_dev, void* out_dev,
                    mlp_stream_t stream);
+/* mlp_detect_plan = mlp_detect_align without its last kernel (the RoIAlign run): a2-a9 and the RoIAlign
+ *   plan.  It exists so that the caller can fork after the NMS kernels: mlp_paste_prefill (below) on a
+ *   second stream beside mlp_roi_align_run / the mask head on the first.
+ * mlp_paste_prefill: CropAndPadMask's background ahead of time.  97 % of the [B,M,PH,PW] output is
+ *   zeros that depend on M only (engine/layers/misc.py:393-399 pads every resized mask to the frame);
+ *   this zeroes that prefix of out_dev with M = max(1, max_b counts_dev[b]) read on the device
+ *   (misc.py:235-236).  Join the stream before mlp_trim_paste(.., out_mode | MLP_PASTE_PREFILLED, ..),
+ *   which then writes only the 16-byte segments that intersect a box.  frame_w must be a multiple of
+ *   the store width (16 uint8 / 4 float32 / 128 bit-packed pixels).                              */
+int mlp_detect_plan(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                    const float* cls_dev, int batch, int height, int width, int num_classes,
+                    const mlp_detection_params* params, int max_k, float base_size, float* det_dev,
+                    int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev, float* dist_dev,
+                    int32_t* level_counts_dev, int32_t* level_m_dev, mlp_stream_t stream);
+int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* counts_dev, int batch, int k_rows, int frame_h,
+                      int frame_w, int out_mode, void* out_dev, mlp_stream_t stream);
 
 /* ---- a8: MoldBatch.call (engine/layers/misc.py:231-286) as a standalone operator ----
  * x_dev [K,row_elems] of 4-byte elements, batch_idx_dev i32 [K] (image id of each row).

@@ -21,6 +21,10 @@ struct mlp_ctx {
     // other's work space (cudaMalloc'd; regrown only between calls)
     void* arena[MLP_NUM_ARENAS];
     int64_t arena_bytes[MLP_NUM_ARENAS];
+    // frozen: a captured CUDA graph holds pointers into the arenas, so growth (= free + malloc) is
+    // refused with MLP_EFROZEN instead of pulling the memory from under the graph
+    bool frozen;
+    int tail_planar;       // mask layout of the last mlp_trim_paste (consumed by mlp_tile_summary / mlp_draw_tiles)
     // small device block for counters / dims (always allocated)
     int32_t* ctr;          // [MLP_CTR_WORDS]
     // optional per-stage CUDA-event timing (bench.py roofline): pairs recorded on the
@@ -35,7 +39,8 @@ struct mlp_ctx {
 enum {
     MLP_ST_THRESHOLD = 0, MLP_ST_NMS_CLASS, MLP_ST_NMS_CROSS, MLP_ST_DISTRIBUTE, MLP_ST_ROI_PLAN,
     MLP_ST_ROI_ALIGN, MLP_ST_TRIM, MLP_ST_UPSAMPLE, MLP_ST_PASTE_THR, MLP_ST_PASTE, MLP_ST_ELEMENTWISE,
-    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW, MLP_ST_RESIZE, MLP_ST_ASSIGN, MLP_ST_JPEG
+    MLP_ST_MOLD, MLP_ST_TAIL_FUSED, MLP_ST_ROAD_SCAN, MLP_ST_SUMMARY, MLP_ST_DRAW, MLP_ST_RESIZE, MLP_ST_ASSIGN, MLP_ST_JPEG,
+    MLP_ST_PASTE_FILL
 };
 
 // RAII: records a start event now and a stop event when it goes out of scope.
@@ -43,13 +48,28 @@ struct ProfScope {
     mlp_ctx* c; cudaStream_t st; int slot;
     ProfScope(mlp_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), st(stream), slot(-1) {
         if (c->prof_on && c->prof_used < MLP_PROF_CAP) {
-            slot = c->prof_used++;
+            // events recorded inside a stream capture become graph nodes and cannot be read with
+            // cudaEventElapsedTime: no brackets while the stream is capturing
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+                cudaGetLastError();
+                return;
+            }
+            slot = c->prof_used;
+            if (cudaEventRecord(c->prof_ev[2 * slot], st) != cudaSuccess) {
+                cudaGetLastError();
+                slot = -1;
+                return;
+            }
             c->prof_stage[slot] = stage;
-            cudaEventRecord(c->prof_ev[2 * slot], st);
+            c->prof_used++;
         }
     }
     ~ProfScope() {
-        if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], st);
+        if (slot >= 0 && cudaEventRecord(c->prof_ev[2 * slot + 1], st) != cudaSuccess) {
+            cudaGetLastError();
+            c->prof_stage[slot] = -1;          // unreadable bracket: skipped by mlp_ctx_profile_read
+        }
     }
 };
 

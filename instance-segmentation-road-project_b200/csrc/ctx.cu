@@ -36,6 +36,8 @@ extern "C" int mlp_ctx_create(int device, mlp_ctx** out) {
     c->launches = 0;
     for (int i = 0; i < MLP_NUM_ARENAS; ++i) { c->arena[i] = nullptr; c->arena_bytes[i] = 0; }
     c->ctr = nullptr;
+    c->frozen = false;
+    c->tail_planar = 0;
     c->prof_on = false;
     c->prof_used = 0;
     c->prof_ev = nullptr;
@@ -78,7 +80,7 @@ extern "C" int64_t mlp_ctx_launch_count(const mlp_ctx* ctx) { return ctx ? ctx->
 static const char* kStageNames[MLP_NUM_STAGES] = {
     "threshold_compact", "nms_per_class", "nms_cross_class", "mask_distribute", "roi_plan",
     "roi_align", "trim", "upsample", "paste_threshold", "paste", "elementwise", "mold_batch",
-    "tail_fused", "road_scan", "summary", "draw", "resize", "assign", "jpeg", "", "", "", "", ""};
+    "tail_fused", "road_scan", "summary", "draw", "resize", "assign", "jpeg", "paste_fill", "", "", "", ""};
 
 extern "C" const char* mlp_stage_name(int stage) {
     return (stage >= 0 && stage < MLP_NUM_STAGES) ? kStageNames[stage] : "";
@@ -104,6 +106,7 @@ extern "C" int mlp_ctx_profile_read(mlp_ctx* ctx, double* ms_out, int64_t* count
     MLP_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < ctx->prof_used; ++i) {
         float ms = 0.f;
+        if (ctx->prof_stage[i] < 0) continue;
         MLP_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
         ms_out[ctx->prof_stage[i]] += ms;
         count_out[ctx->prof_stage[i]] += 1;
@@ -111,15 +114,45 @@ extern "C" int mlp_ctx_profile_read(mlp_ctx* ctx, double* ms_out, int64_t* count
     return MLP_OK;
 }
 
-// Grow-only.  Regrowth frees the old arena after a device synchronise, so it must
-// not happen while earlier work of this ctx is still using it; callers size the
-// arena from (B,N,C) which is stable after the first call of a given shape.
+extern "C" int mlp_ctx_freeze_scratch(mlp_ctx* ctx, int freeze) {
+    MLP_CHECK_ARG(ctx != nullptr, "mlp_ctx_freeze_scratch: NULL ctx");
+    ctx->frozen = freeze != 0;
+    return MLP_OK;
+}
+
+// Grow-only.  Regrowth frees the old arena after a device synchronise, so it must not happen
+// while anything still references it: earlier work of this ctx (hence the synchronise) or a
+// captured CUDA graph (hence mlp_ctx_freeze_scratch, which PostProcessPipeline.capture sets: a
+// frozen ctx answers MLP_EFROZEN instead of freeing memory a graph replay would touch).  Callers
+// size the arena from the call's shapes, which are stable after the first call of a given shape.
 int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes) {
     if (bytes <= ctx->arena_bytes[which]) return MLP_OK;
+    if (ctx->frozen && ctx->arena[which]) {      // a first allocation frees nothing and stays allowed
+        mlp_set_error("scratch arena %d would have to grow from %lld to %lld bytes, but the ctx is frozen: a "
+                      "captured CUDA graph references its arenas.  Use a separate ctx for other shapes, or "
+                      "drop the graph and call mlp_ctx_freeze_scratch(ctx, 0).",
+                      which, (long long)ctx->arena_bytes[which], (long long)bytes);
+        return MLP_EFROZEN;
+    }
     DeviceGuard g(ctx->device);
     if (ctx->arena[which]) {
-        cudaDeviceSynchronize();
-        cudaFree(ctx->arena[which]);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            // cudaErrorStreamCaptureUnsupported lands here: growth was attempted inside a stream capture
+            mlp_set_error("scratch arena %d cannot grow now: cudaDeviceSynchronize failed: %s%s", which,
+                          cudaGetErrorString(e),
+                          e == cudaErrorStreamCaptureUnsupported
+                              ? " (a stream capture is active: run the call once with these shapes before capturing)"
+                              : "");
+            cudaGetLastError();
+            return MLP_ECUDA;
+        }
+        e = cudaFree(ctx->arena[which]);
+        if (e != cudaSuccess) {
+            mlp_set_error("scratch cudaFree failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return MLP_ECUDA;
+        }
         ctx->arena[which] = nullptr;
         ctx->arena_bytes[which] = 0;
     }
@@ -129,7 +162,7 @@ int mlp_ensure_scratch(mlp_ctx* ctx, int which, int64_t bytes) {
         mlp_set_error("scratch cudaMalloc(%lld bytes) failed: %s", (long long)want,
                       cudaGetErrorString(e));
         cudaGetLastError();
-        return MLP_ENOMEM;
+        return e == cudaErrorMemoryAllocation ? MLP_ENOMEM : MLP_ECUDA;
     }
     ctx->arena_bytes[which] = want;
     return MLP_OK;

@@ -22,6 +22,8 @@ constexpr int kClassThreads = 512;          // K2: several CTAs per SM (B*C CTAs
 constexpr int kCrossThreads = 1024;         // K3: one CTA per image
 constexpr int kChunk = 64;                  // candidates resolved per round (one 64-bit mask row each)
 constexpr int kMaskWords = kChunk / 32;
+constexpr int kBlock = 512;                 // candidates whose boxes are fetched at once (8 chunks): ONE memory round
+                                            // trip per block instead of one per chunk - the kernels are latency-bound
 constexpr uint64_t kKeyPad = ~0ull;
 
 struct BoxC { float ymin, xmin, ymax, xmax, area; };
@@ -244,6 +246,35 @@ __device__ void bitonic_sort_smem(uint64_t* s, int n_pow2) {
     }
 }
 
+// The same network with ONE key per thread held in a register (n_pow2 <= blockDim.x, the usual case: a few
+// hundred candidates per group): compare-exchange partners less than 32 apart meet by warp shuffle, only
+// the strides >= 32 go through shared memory - 10 block-wide exchanges for 512 keys instead of 45, which was
+// 40 % of the run time of both NMS kernels (profiles/ncu_summary_r02*.md).
+__device__ void bitonic_sort_reg(uint64_t* s, int n_pow2) {
+    const int t = threadIdx.x;
+    const bool in = t < n_pow2;
+    uint64_t v = in ? s[t] : kKeyPad;
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t o;
+            if (j >= 32) {
+                __syncthreads();                       // partners have read the previous exchange
+                if (in) s[t] = v;
+                __syncthreads();
+                o = in ? s[t ^ j] : kKeyPad;
+            } else {
+                o = __shfl_xor_sync(0xffffffffu, (unsigned long long)v, j);
+            }
+            const bool take_min = ((t & k) == 0) == ((t & j) == 0);
+            const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+            v = take_min ? mn : mx;
+        }
+    }
+    __syncthreads();
+    if (in) s[t] = v;
+    __syncthreads();
+}
+
 // Smallest pivot P such that #{key in gkeys : lo_excl < key <= P (or any key when
 // !have_lo)} == want.  Keys are unique, 1 <= want <= number of such keys.  MSB-first
 // 8-bit radix select; hist is a 256-int shared array, bcast a 2-word shared array.
@@ -284,8 +315,8 @@ __device__ uint64_t radix_select_pivot(const uint64_t* gkeys, int cnt, bool have
 struct NmsSmem {
     uint64_t* skeys;        // [sort_cap]
     float4* k_crn; float* k_area;   // [max_out] kept boxes (ymin,xmin,ymax,xmax) + area: one LDS.128 + one LDS.32 per test
-    float4* c_crn; float* c_area;   // [kChunk]  candidates of the current chunk
-    float4* c_box;          // [kChunk] cx,cy,w,h of the chunk's candidates
+    float4* c_crn; float* c_area;   // [kBlock]  candidates of the current block (chunks index into it)
+    float4* c_box;          // [kBlock] cx,cy,w,h of the block's candidates
     uint32_t* c_mask;       // [kChunk][kMaskWords]
     int* c_supp;            // [kChunk]
     uint32_t* keptw;        // [kMaskWords]
@@ -298,8 +329,8 @@ __host__ __device__ inline size_t nms_smem_bytes(int sort_cap, int max_out) {
     size_t b = 0;
     b += (size_t)sort_cap * 8;
     b += (size_t)max_out * 4 * 5;
-    b += (size_t)kChunk * 4 * 5;
-    b += (size_t)kChunk * 16;
+    b += (size_t)kBlock * 4 * 5;
+    b += (size_t)kBlock * 16;
     b += (size_t)kChunk * kMaskWords * 4;
     b += (size_t)kChunk * 4;
     b += kMaskWords * 4;
@@ -313,12 +344,12 @@ __device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_
     NmsSmem S;
     unsigned char* p = base;
     S.skeys = reinterpret_cast<uint64_t*>(p); p += (size_t)sort_cap * 8;
-    S.c_box = reinterpret_cast<float4*>(p);   p += (size_t)kChunk * 16;
+    S.c_box = reinterpret_cast<float4*>(p);   p += (size_t)kBlock * 16;
     S.bcast = reinterpret_cast<unsigned long long*>(p); p += 16;
     S.k_crn = reinterpret_cast<float4*>(p); p += (size_t)max_out * 16;     // 16-byte aligned (after c_box/bcast)
-    S.c_crn = reinterpret_cast<float4*>(p); p += (size_t)kChunk * 16;
+    S.c_crn = reinterpret_cast<float4*>(p); p += (size_t)kBlock * 16;
     S.k_area = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
-    S.c_area = reinterpret_cast<float*>(p); p += kChunk * 4;
+    S.c_area = reinterpret_cast<float*>(p); p += kBlock * 4;
     S.c_mask = reinterpret_cast<uint32_t*>(p); p += (size_t)kChunk * kMaskWords * 4;
     S.c_supp = reinterpret_cast<int*>(p); p += kChunk * 4;
     S.keptw = reinterpret_cast<uint32_t*>(p); p += kMaskWords * 4;
@@ -334,7 +365,7 @@ __device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_
 // box by exactly one thread.  Returns the kept count (block-uniform).
 template <int kThreads, class Fetch, class Emit>
 __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
-                        int max_out, const NmsSmem& S, Fetch fetch, Emit emit) {
+                        int max_out, const NmsSmem& S, Fetch fetch, Emit emit, bool staged = false) {
     constexpr int kLanesPerCand = kThreads / kChunk;   // threads that split the kept list
     static_assert(kThreads % kChunk == 0 && kChunk % kLanesPerCand == 0 && kChunk == 64, "bad NMS geometry");
     const int tid = threadIdx.x;
@@ -348,16 +379,23 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
         const int remaining = cnt - done;
         const int sc = remaining < sort_cap ? remaining : sort_cap;
         const bool have_lo = done > 0;
-        uint64_t pivot = kKeyPad;
-        if (remaining > sort_cap)
-            pivot = radix_select_pivot(gkeys, cnt, have_lo, lo, sc, S.hist, S.bcast);
-        if (tid == 0) S.misc[1] = 0;
-        __syncthreads();
-        for (int i = tid; i < cnt; i += blockDim.x) {
-            uint64_t k = gkeys[i];
-            if ((!have_lo || k > lo) && k <= pivot) {
-                int pos = atomicAdd(&S.misc[1], 1);
-                if (pos < sort_cap) S.skeys[pos] = k;
+        if (!have_lo && cnt <= sort_cap) {
+            // everything fits: plain copy (or already in S.skeys when the caller staged it), no
+            // selection pass and no shared-memory counter
+            if (!staged)
+                for (int i = tid; i < cnt; i += blockDim.x) S.skeys[i] = gkeys[i];
+        } else {
+            uint64_t pivot = kKeyPad;
+            if (remaining > sort_cap)
+                pivot = radix_select_pivot(gkeys, cnt, have_lo, lo, sc, S.hist, S.bcast);
+            if (tid == 0) S.misc[1] = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += blockDim.x) {
+                uint64_t k = gkeys[i];
+                if ((!have_lo || k > lo) && k <= pivot) {
+                    int pos = atomicAdd(&S.misc[1], 1);
+                    if (pos < sort_cap) S.skeys[pos] = k;
+                }
             }
         }
         int p2 = 1;
@@ -365,104 +403,108 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
         __syncthreads();
         for (int i = sc + tid; i < p2; i += blockDim.x) S.skeys[i] = kKeyPad;
         __syncthreads();
-        bitonic_sort_smem(S.skeys, p2);
+        if (p2 <= (int)blockDim.x) bitonic_sort_reg(S.skeys, p2);
+        else bitonic_sort_smem(S.skeys, p2);
         lo = S.skeys[sc - 1];
         done += sc;
 
-        // ---- chunks of kChunk (= 64) candidates ----
-        for (int base = 0; base < sc && kept < max_out; base += kChunk) {
-            const int m = (sc - base) < kChunk ? (sc - base) : kChunk;
-            if (tid < kChunk) {
+        // ---- blocks of kBlock candidates: all their boxes are fetched (decoded) in one round trip ----
+        for (int pb = 0; pb < sc && kept < max_out; pb += kBlock) {
+            const int pn = (sc - pb) < kBlock ? (sc - pb) : kBlock;
+            __syncthreads();                          // previous block's chunks are done with c_*
+            for (int i = tid; i < pn; i += blockDim.x) {
+                const float4 bx = fetch((uint32_t)S.skeys[pb + i]);
+                const BoxC c = corners_of(bx);
+                S.c_box[i] = bx;
+                S.c_crn[i] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+                S.c_area[i] = c.area;
+            }
+            // ---- chunks of kChunk (= 64) candidates ----
+            for (int base = 0; base < pn && kept < max_out; base += kChunk) {
+                const int m = (pn - base) < kChunk ? (pn - base) : kChunk;
+                if (tid < kChunk) {
+                    S.c_supp[tid] = tid < m ? 0 : 1;
+                    S.c_mask[tid * 2] = 0u;
+                    S.c_mask[tid * 2 + 1] = 0u;
+                }
+                __syncthreads();
+                const int t = tid % kChunk, r = tid / kChunk;
+                const float4 tc = S.c_crn[base + (t < m ? t : 0)];
+                const float tymin = tc.x, txmin = tc.y, tymax = tc.z, txmax = tc.w;
+                const float tarea = S.c_area[base + (t < m ? t : 0)];
+                // (b) against the kept list, split over kLanesPerCand threads per candidate
+                if (t < m) {
+                    for (int j = r; j < kept; j += kLanesPerCand) {
+                        const float4 kc = S.k_crn[j];
+                        if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, kc.x, kc.y, kc.z, kc.w, S.k_area[j],
+                                        thr)) {
+                            S.c_supp[t] = 1;
+                            break;
+                        }
+                    }
+                }
+                __syncthreads();
+                // (c) intra-chunk mask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
+                if (t < m && S.c_supp[t] == 0) {
+                    constexpr int kSlice = kChunk / kLanesPerCand;
+                    const int u0 = r * kSlice;
+                    const int u1 = (u0 + kSlice < t) ? (u0 + kSlice) : t;
+                    uint32_t lo = 0, hi = 0;
+                    for (int u = u0; u < u1; ++u) {
+                        const float4 uc = S.c_crn[base + u];
+                        if (S.c_supp[u] == 0 &&
+                            iou_exceeds(tymin, txmin, tymax, txmax, tarea, uc.x, uc.y, uc.z, uc.w,
+                                        S.c_area[base + u], thr)) {
+                            if (u < 32) lo |= 1u << u; else hi |= 1u << (u - 32);
+                        }
+                    }
+                    if (lo) atomicOr(&S.c_mask[t * 2], lo);
+                    if (hi) atomicOr(&S.c_mask[t * 2 + 1], hi);
+                }
+                __syncthreads();
+                // (d) sequential resolve by warp 0.  Rows live in registers (lane l: candidates l
+                // and l+32) and reach every lane by shuffle, so the loop-carried chain is two ANDs,
+                // a compare and an OR per candidate - no shared-memory latency on it.
+                if (tid < 32) {
+                    const uint32_t alive_lo = __ballot_sync(0xffffffffu, S.c_supp[tid] == 0);
+                    const uint32_t alive_hi = __ballot_sync(0xffffffffu, S.c_supp[tid + 32] == 0);
+                    const uint32_t rowA_lo = S.c_mask[tid * 2];
+                    const uint32_t rowB_lo = S.c_mask[(tid + 32) * 2];
+                    const uint32_t rowB_hi = S.c_mask[(tid + 32) * 2 + 1];
+                    uint32_t kept_lo = 0, kept_hi = 0;
+                    int k = kept;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const uint32_t rl = __shfl_sync(0xffffffffu, rowA_lo, q);
+                        const bool keep = ((alive_lo >> q) & 1u) && !(rl & kept_lo) && (k < max_out);
+                        if (keep) { kept_lo |= 1u << q; ++k; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const uint32_t rl = __shfl_sync(0xffffffffu, rowB_lo, q);
+                        const uint32_t rh = __shfl_sync(0xffffffffu, rowB_hi, q);
+                        const bool keep = ((alive_hi >> q) & 1u) && !((rl & kept_lo) | (rh & kept_hi)) &&
+                                          (k < max_out);
+                        if (keep) { kept_hi |= 1u << q; ++k; }
+                    }
+                    if (tid == 0) { S.keptw[0] = kept_lo; S.keptw[1] = kept_hi; S.misc[0] = k; }
+                }
+                __syncthreads();
+                // (e) append newly kept boxes in order and emit them
                 if (tid < m) {
-                    uint64_t key = S.skeys[base + tid];
-                    float4 bx = fetch((uint32_t)key);
-                    BoxC c = corners_of(bx);
-                    S.c_box[tid] = bx;
-                    S.c_crn[tid] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-                    S.c_area[tid] = c.area;
-                    S.c_supp[tid] = 0;
-                } else {
-                    S.c_supp[tid] = 1;
-                }
-                S.c_mask[tid * 2] = 0u;
-                S.c_mask[tid * 2 + 1] = 0u;
-            }
-            __syncthreads();
-            const int t = tid % kChunk, r = tid / kChunk;
-            const float4 tc = S.c_crn[t];
-            const float tymin = tc.x, txmin = tc.y, tymax = tc.z, txmax = tc.w, tarea = S.c_area[t];
-            // (b) against the kept list, split over kLanesPerCand threads per candidate
-            if (t < m) {
-                for (int j = r; j < kept; j += kLanesPerCand) {
-                    const float4 kc = S.k_crn[j];
-                    if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, kc.x, kc.y, kc.z, kc.w, S.k_area[j],
-                                    thr)) {
-                        S.c_supp[t] = 1;
-                        break;
+                    const uint32_t w0 = S.keptw[0], w1 = S.keptw[1];
+                    const uint32_t wv = (tid < 32) ? w0 : w1;
+                    if ((wv >> (tid & 31)) & 1u) {
+                        int rank = kept + ((tid < 32) ? 0 : __popc(w0));
+                        rank += __popc(wv & ((1u << (tid & 31)) - 1u));
+                        S.k_crn[rank] = S.c_crn[base + tid];
+                        S.k_area[rank] = S.c_area[base + tid];
+                        emit(rank, S.skeys[pb + base + tid], S.c_box[base + tid]);
                     }
                 }
+                kept = S.misc[0];
+                __syncthreads();
             }
-            __syncthreads();
-            // (c) intra-chunk mask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
-            if (t < m && S.c_supp[t] == 0) {
-                constexpr int kSlice = kChunk / kLanesPerCand;
-                const int u0 = r * kSlice;
-                const int u1 = (u0 + kSlice < t) ? (u0 + kSlice) : t;
-                uint32_t lo = 0, hi = 0;
-                for (int u = u0; u < u1; ++u) {
-                    const float4 uc = S.c_crn[u];
-                    if (S.c_supp[u] == 0 &&
-                        iou_exceeds(tymin, txmin, tymax, txmax, tarea, uc.x, uc.y, uc.z, uc.w, S.c_area[u],
-                                    thr)) {
-                        if (u < 32) lo |= 1u << u; else hi |= 1u << (u - 32);
-                    }
-                }
-                if (lo) atomicOr(&S.c_mask[t * 2], lo);
-                if (hi) atomicOr(&S.c_mask[t * 2 + 1], hi);
-            }
-            __syncthreads();
-            // (d) sequential resolve by warp 0.  Rows live in registers (lane l: candidates l
-            // and l+32) and reach every lane by shuffle, so the loop-carried chain is two ANDs,
-            // a compare and an OR per candidate - no shared-memory latency on it.
-            if (tid < 32) {
-                const uint32_t alive_lo = __ballot_sync(0xffffffffu, S.c_supp[tid] == 0);
-                const uint32_t alive_hi = __ballot_sync(0xffffffffu, S.c_supp[tid + 32] == 0);
-                const uint32_t rowA_lo = S.c_mask[tid * 2];
-                const uint32_t rowB_lo = S.c_mask[(tid + 32) * 2];
-                const uint32_t rowB_hi = S.c_mask[(tid + 32) * 2 + 1];
-                uint32_t kept_lo = 0, kept_hi = 0;
-                int k = kept;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const uint32_t rl = __shfl_sync(0xffffffffu, rowA_lo, q);
-                    const bool keep = ((alive_lo >> q) & 1u) && !(rl & kept_lo) && (k < max_out);
-                    if (keep) { kept_lo |= 1u << q; ++k; }
-                }
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const uint32_t rl = __shfl_sync(0xffffffffu, rowB_lo, q);
-                    const uint32_t rh = __shfl_sync(0xffffffffu, rowB_hi, q);
-                    const bool keep = ((alive_hi >> q) & 1u) && !((rl & kept_lo) | (rh & kept_hi)) &&
-                                      (k < max_out);
-                    if (keep) { kept_hi |= 1u << q; ++k; }
-                }
-                if (tid == 0) { S.keptw[0] = kept_lo; S.keptw[1] = kept_hi; S.misc[0] = k; }
-            }
-            __syncthreads();
-            // (e) append newly kept boxes in order and emit them
-            if (tid < m) {
-                const uint32_t w0 = S.keptw[0], w1 = S.keptw[1];
-                const uint32_t wv = (tid < 32) ? w0 : w1;
-                if ((wv >> (tid & 31)) & 1u) {
-                    int rank = kept + ((tid < 32) ? 0 : __popc(w0));
-                    rank += __popc(wv & ((1u << (tid & 31)) - 1u));
-                    S.k_crn[rank] = S.c_crn[tid];
-                    S.k_area[rank] = S.c_area[tid];
-                    emit(rank, S.skeys[base + tid], S.c_box[tid]);
-                }
-            }
-            kept = S.misc[0];
-            __syncthreads();
         }
     }
     return kept;
@@ -506,11 +548,15 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
     const uint64_t* gkeys = D.cand_keys + (int64_t)g * D.cap;
 
     // first anchor index at which this (image,class) appears: orders the groups like
-    // tf.unique does in the row-major (b,n,c) scan (detection.py:519-520)
+    // tf.unique does in the row-major (b,n,c) scan (detection.py:519-520).  When the group fits the
+    // sort buffer (the usual case) the same pass stages the keys, so they are read once.
+    const bool staged = cnt <= sort_cap;
     {
         int mn = 0x7fffffff;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-            int n = (int)(uint32_t)gkeys[i];
+            const uint64_t k = gkeys[i];
+            if (staged) S.skeys[i] = k;
+            int n = (int)(uint32_t)k;
             mn = n < mn ? n : mn;
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -537,10 +583,10 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
     int kept;
     if (kDecode) {
         FetchDecode f{&P, boxes_or_loc + (int64_t)b * N};
-        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit);
+        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
     } else {
         FetchBoxes f{boxes_or_loc + (int64_t)b * N};
-        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit);
+        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
     }
     if (threadIdx.x == 0) D.cls_kept[g] = kept;
 }
@@ -561,14 +607,22 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     __shared__ int s_off[257];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    // groups of this image in first-appearance order: sort by (min_n, c)
+    // groups of this image in first-appearance order: sort by (min_n, c).  The per-class scalars are
+    // fetched by C threads at once (one round trip), thread 0 orders them out of shared memory.
+    __shared__ int s_cnt[256], s_min[256], s_kept[256];
+    if (tid < C) {
+        s_cnt[tid] = D.cand_count[b * C + tid];
+        s_min[tid] = D.min_n[b * C + tid];
+        s_kept[tid] = D.cls_kept[b * C + tid];
+    }
+    __syncthreads();
     if (tid == 0) {
         int ng = 0;
         for (int c = 0; c < C; ++c) {
-            if (D.cand_count[b * C + c] > 0) {
-                int mn = D.min_n[b * C + c];
+            if (s_cnt[c] > 0) {
+                int mn = s_min[c];
                 int pos = ng++;
-                while (pos > 0 && D.min_n[b * C + s_order[pos - 1]] > mn) {
+                while (pos > 0 && s_min[s_order[pos - 1]] > mn) {
                     s_order[pos] = s_order[pos - 1];
                     --pos;
                 }
@@ -578,7 +632,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         int off = 0;
         for (int i = 0; i < ng; ++i) {
             s_off[i] = off;
-            off += D.cls_kept[b * C + s_order[i]];
+            off += s_kept[s_order[i]];
         }
         s_off[ng] = off;
         S.misc[2] = ng;
@@ -592,19 +646,21 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     float4* cat_box = D.cat_box + cat_base;
     int2* cat_sn = D.cat_sn + cat_base;
     int32_t* cat_c = D.cat_c + cat_base;
-    for (int gi = 0; gi < ng; ++gi) {
+    // concatenation, flat over the survivors (one round of loads): position p -> (group gi, rank i)
+    const bool staged = total <= sort_cap;
+    for (int p = tid; p < total; p += blockDim.x) {
+        int gi = 0;
+        while (gi + 1 < ng && p >= s_off[gi + 1]) ++gi;
         const int c = s_order[gi];
-        const int g = b * C + c;
-        const int n_g = s_off[gi + 1] - s_off[gi];
-        for (int i = tid; i < n_g; i += blockDim.x) {
-            const int p = s_off[gi] + i;
-            float4 bx = D.rec_box[(int64_t)g * max_out + i];
-            int2 sn = D.rec_sn[(int64_t)g * max_out + i];
-            cat_box[p] = bx;
-            cat_sn[p] = sn;
-            cat_c[p] = c;
-            cat_keys[p] = make_key(__int_as_float(sn.x), (uint32_t)p);
-        }
+        const int64_t src = (int64_t)(b * C + c) * max_out + (p - s_off[gi]);
+        const float4 bx = D.rec_box[src];
+        const int2 sn = D.rec_sn[src];
+        cat_box[p] = bx;
+        cat_sn[p] = sn;
+        cat_c[p] = c;
+        const uint64_t key = make_key(__int_as_float(sn.x), (uint32_t)p);
+        cat_keys[p] = key;
+        if (staged) S.skeys[p] = key;
     }
     __syncthreads();
     float* det_b = det + (int64_t)b * max_out * 6;
@@ -622,7 +678,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     int kept = 0;
     if (total > 0) {
         FetchCat f{cat_box};
-        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit);
+        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged);
     }
     // -1 padding of the unused rows (MoldBatch, misc.py:276-283)
     for (int i = kept * 6 + tid; i < max_out * 6; i += blockDim.x) det_b[i] = -1.0f;
@@ -779,7 +835,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     // B*C groups (160-192 at batch 32) are resident in a single wave on 148 SMs.
     {
         ProfScope prof(ctx, MLP_ST_NMS_CLASS, stream);
-        const int sort_cap = pick_sort_cap(4096, max_out, 72 * 1024);
+        const int sort_cap = pick_sort_cap(4096, max_out, 74 * 1024);
         const size_t smem = nms_smem_bytes(sort_cap, max_out);
         if (prior) {
             MLP_CUDA(cudaFuncSetAttribute(nms_per_class_kernel<true>,
@@ -844,22 +900,20 @@ extern "C" int mlp_detect_from_heads(mlp_ctx* ctx, const mlp_prior_config* prior
 }
 
 // Fused first half of the path (a2-a10): detection with MaskDistribute and the RoIAlign plan folded
-// into the cross-class NMS epilogue, then the RoIAlign run: 4 kernels for the whole half.
-extern "C" int mlp_detect_align(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
-                                const float* cls_dev, int batch, int height, int width, int num_classes,
-                                const mlp_detection_params* params, int max_k, float base_size,
-                                const float* const* fmaps_dev, const int32_t* fh, const int32_t* fw,
-                                int channels, int crop_h, int crop_w, float* det_dev, int32_t* keep_dev,
-                                int32_t* counts_dev, int32_t* m_dev, float* dist_dev,
-                                int32_t* level_counts_dev, int32_t* level_m_dev,
-                                float* const* crops_dev, float* roi_boxes_dev, mlp_stream_t stream) {
+// into the cross-class NMS epilogue (mlp_detect_plan, 3 kernels), then the RoIAlign run.
+extern "C" int mlp_detect_plan(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                               const float* cls_dev, int batch, int height, int width, int num_classes,
+                               const mlp_detection_params* params, int max_k, float base_size,
+                               float* det_dev, int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev,
+                               float* dist_dev, int32_t* level_counts_dev, int32_t* level_m_dev,
+                               mlp_stream_t stream) {
     if (!ctx || !prior || !params || !dist_dev || !level_counts_dev || !level_m_dev) {
-        mlp_set_error("mlp_detect_align: NULL argument");
+        mlp_set_error("mlp_detect_plan: NULL argument");
         return MLP_EINVAL;
     }
-    MLP_CHECK_ARG(max_k >= 0 && max_k + 1 <= MLP_MAX_LEVELS, "mlp_detect_align: max_k=%d out of range", max_k);
+    MLP_CHECK_ARG(max_k >= 0 && max_k + 1 <= MLP_MAX_LEVELS, "mlp_detect_plan: max_k=%d out of range", max_k);
     MLP_CHECK_ARG(params->nms_max_output_size >= 1 && params->nms_max_output_size <= MLP_MAX_KEEP,
-                  "mlp_detect_align: nms_max_output_size out of range");
+                  "mlp_detect_plan: nms_max_output_size out of range");
     int64_t N = mlp_prior_count(prior, height, width);
     if (N < 0) return (int)N;
     const int L = max_k + 1, K = params->nms_max_output_size;
@@ -877,10 +931,23 @@ extern "C" int mlp_detect_align(mlp_ctx* ctx, const mlp_prior_config* prior, con
     fp.roi_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_ROI]);
     fp.level_counts = level_counts_dev;
     fp.level_m = level_m_dev;
-    int rc = detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,
-                            det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream, "mlp_detect_align",
-                            fp);
+    return detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,
+                          det_dev, keep_dev, counts_dev, m_dev, (cudaStream_t)stream, "mlp_detect_plan", fp);
+}
+
+extern "C" int mlp_detect_align(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
+                                const float* cls_dev, int batch, int height, int width, int num_classes,
+                                const mlp_detection_params* params, int max_k, float base_size,
+                                const float* const* fmaps_dev, const int32_t* fh, const int32_t* fw,
+                                int channels, int crop_h, int crop_w, float* det_dev, int32_t* keep_dev,
+                                int32_t* counts_dev, int32_t* m_dev, float* dist_dev,
+                                int32_t* level_counts_dev, int32_t* level_m_dev,
+                                float* const* crops_dev, float* roi_boxes_dev, mlp_stream_t stream) {
+    int rc = mlp_detect_plan(ctx, prior, loc_dev, cls_dev, batch, height, width, num_classes, params, max_k,
+                             base_size, det_dev, keep_dev, counts_dev, m_dev, dist_dev, level_counts_dev,
+                             level_m_dev, stream);
     if (rc) return rc;
+    const int L = max_k + 1, K = params->nms_max_output_size;
     return mlp_roi_align_run(ctx, fmaps_dev, fh, fw, L, channels, dist_dev, batch, K, K, m_dev,
                              (float)height, (float)width, crop_h, crop_w, level_counts_dev, level_m_dev,
                              crops_dev, roi_boxes_dev, stream);

@@ -609,6 +609,7 @@ static int draw_tiles_impl(mlp_ctx* ctx, const void* images_dev, int image_dtype
         S.r_dev = r_dev;
         S.r_rows = r_rows;
         S.C = num_classes;
+        S.planar = ctx->tail_planar;
         S.counts = counts_dev;
         S.confmax = ft.confmax;
     }

@@ -20,6 +20,62 @@ namespace {
 constexpr int kPasteThreads = 256;
 constexpr int kTileRegs = 4;              // tile elements prefetched per thread (covers 32x32)
 
+// dynamic shared memory of the vector paste kernels: the mask tile as floats, then the column table
+__host__ __device__ inline int paste_tile_bytes(int px) { return (px * 4 + 15) & ~15; }
+inline size_t paste_smem_bytes(int mask_h, int mask_w, int frame_w) {
+    return (size_t)paste_tile_bytes(mask_h * mask_w) + (size_t)(frame_w < kMaxCols ? frame_w : kMaxCols) * sizeof(uint2);
+}
+
+// One 16-byte output segment (kVec pixels starting at x0) of frame row oy of an instance: the reference's
+// two-stage lerp from the mask tile in shared memory, > 0.5 fused for the binary modes.  s_col: the box's
+// column table (paste_fill_cols) or NULL for boxes wider than kMaxCols.
+template <int kMode>
+__device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile, const uint2* __restrict__ s_col,
+                                               const PasteGeom& g, int mh, int mw, int oy, int x0) {
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
+    const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
+    const float fl = floorf(p);
+    const int ylo = max((int)fl, 0);
+    const int yhi = min((int)ceilf(p), mh - 1);
+    const float ly = __fsub_rn(p, fl);
+    const float* row_lo = s_tile + ylo * mw;
+    const float* row_hi = s_tile + yhi * mw;
+    const int q0 = max(g.xmin - x0, 0), q1 = min(g.xmax - x0, kVec);       // pixels of the segment inside the box
+    const uint2* col = s_col ? s_col + (x0 - g.xmin) : nullptr;
+    auto value = [&](int q) -> float {
+        return col ? paste_value_cols(row_lo, row_hi, ly, col[q])
+                   : paste_value(s_tile, mh, mw, ylo, yhi, ly, x0 + q - g.xmin, g.sx);
+    };
+    uint4 v;
+    if (kMode == MLP_PASTE_U8) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (q0 == 0 && q1 == 16) {                                        // interior segment: no bounds tests
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (value(q) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q >= q0 && q < q1 && value(q) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (kMode == MLP_PASTE_BITS) {
+        // bit k of byte i = pixel 8*i + k  (numpy packbits, bitorder='little')
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int q = q0; q < q1; ++q)
+            if (value(q) > 0.5f) w[q >> 5] |= 1u << (q & 31);
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q >= q0 && q < q1) f[q] = value(q);
+        v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                       __float_as_uint(f[3]));
+    }
+    return v;
+}
+
 // One CTA per (instance, band) item, NOT a persistent grid: on B200 a write-only stream of many
 // short-lived CTAs, each owning one contiguous 64 KB band, reaches ~7.4 TB/s while persistent
 // CTAs top out near 6.3 TB/s (tools/write_bw.cu, profiles/write_bw_r01.txt).  The grid is sized
@@ -35,8 +91,9 @@ __global__ void __launch_bounds__(kPasteThreads)
 paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
              int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);   // pixels per 16-byte store
-    constexpr bool kU8 = kMode == MLP_PASTE_U8;
-    __shared__ float s_tile[kMaxTile];
+    extern __shared__ __align__(16) unsigned char s_dyn[];           // [tile floats][column table], paste_smem_bytes
+    float* s_tile = reinterpret_cast<float*>(s_dyn);
+    uint2* s_col_buf = reinterpret_cast<uint2*>(s_dyn + paste_tile_bytes(mh * mw));
     int M, thr;
     paste_scalars(S, B, m_rows, M, thr);
     if (m_stride == 0) m_stride = M;               // compact [B,M,..] input layout
@@ -69,7 +126,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         // memory after the zero rows have been streamed out
         int tile_regs[kTileRegs];
         TileRef tref;
-        tref.mi = nullptr; tref.mf = nullptr; tref.bits = nullptr; tref.C = 1; tref.mw = mw; tref.valid = false;
+        tref.mi = nullptr; tref.mf = nullptr; tref.bits = nullptr; tref.es = 1; tref.mw = mw; tref.valid = false;
         if (touches) {
             tref = tile_ref(S, b, j, m_stride, px, row[4], mh, mw);
 #pragma unroll
@@ -110,6 +167,8 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         }
         for (int i = tid + kTileRegs * kPasteThreads; i < px; i += kPasteThreads)
             s_tile[i] = (float)tref.at(i);
+        paste_fill_cols(s_col_buf, g, mw, tid, kPasteThreads);
+        const uint2* s_col = (g.xmax - g.xmin <= kMaxCols) ? s_col_buf : nullptr;
         const int sL = g.xmin / kVec;                       // first segment touching the box
         const int sR = (g.xmax + kVec - 1) / kVec;          // one past the last
         const int bw = sR - sL;
@@ -128,45 +187,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         for (int i = tid; i < nb; i += kPasteThreads) {
             const int r = i / bw;
             const int seg = sL + (i - r * bw);
-            const int oy = ya + r;
-            const int x0 = seg * kVec;
-            const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
-            const float fl = floorf(p);
-            const int ylo = max((int)fl, 0);
-            const int yhi = min((int)ceilf(p), mh - 1);
-            const float ly = __fsub_rn(p, fl);
-            uint4 v;
-            if (kU8) {
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int ox = x0 + q;
-                    if (ox >= g.xmin && ox < g.xmax) {
-                        const float val = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
-                        if (val > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
-                    }
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            } else if (kMode == MLP_PASTE_BITS) {
-                // bit k of byte i = pixel 8*i + k  (numpy packbits, bitorder='little')
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
-                const int q0 = max(g.xmin - x0, 0), q1 = min(g.xmax - x0, 128);
-                for (int q = q0; q < q1; ++q) {
-                    const float val = paste_value(s_tile, mh, mw, ylo, yhi, ly, x0 + q - g.xmin, g.sx);
-                    if (val > 0.5f) w[q >> 5] |= 1u << (q & 31);
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
-                float f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ox = x0 + q;
-                    if (ox >= g.xmin && ox < g.xmax)
-                        f[q] = paste_value(s_tile, mh, mw, ylo, yhi, ly, ox - g.xmin, g.sx);
-                }
-                v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                               __float_as_uint(f[3]));
-            }
+            const uint4 v = paste_segment<kMode>(s_tile, s_col, g, mh, mw, ya + r, seg * kVec);
             stg_stream_u4(box_rows + (int64_t)r * spr + seg, v);
         }
     }
@@ -223,6 +244,57 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
     }
 }
 
+// ---- work items of the boxes-only paste ---------------------------------------------------------
+// Behind a background fill (mlp_paste_prefill) only the 16-byte segments that intersect a box are left
+// to write: 18 M of 1,678 M pixels at cfg-2, very unevenly spread (a 45x45 box beside a frame-sized one).
+// The tail preparation therefore cuts every box into chunks of about kBoxSegs segments - (instance,
+// first row, rows) - and appends them to a list (one warp-aggregated atomicAdd per 32 instances); the
+// paste then walks the list with a grid-stride loop, every CTA doing equal work.
+constexpr int kBoxSegs = 2048;             // segments per work item (8 per thread)
+
+struct BoxItems {
+    uint2* items;            // x = b*K + slot, y = (first frame row << 16) | rows
+    int32_t* n_items;        // [1], zeroed before the tail preparation
+    int cap;
+    int PH, PW, vec;         // frame size, pixels per 16-byte segment; vec == 0: no list wanted
+};
+
+// rows of one chunk for a box of `bw` segments per row
+__device__ __forceinline__ int box_chunk_rows(int bw) { return max(1, kBoxSegs / max(bw, 1)); }
+
+// Called by all 32 lanes; lanes with `has` own a valid instance (int32 row o[6]).  Geometry as in
+// paste_geometry but without the confidence filter (unknown until every image is prepared): filtered
+// rows cost the paste one skipped item.
+__device__ __forceinline__ void box_items_append(const BoxItems& Q, bool has, const int32_t* o, int inst) {
+    int chunks = 0, ymin = 0, ymax = 0, rows = 1;
+    if (has) {
+        const PasteGeom g = paste_geometry(o, INT_MIN, 1, 1, Q.PH, Q.PW);
+        if (g.active) {
+            const int bw = (g.xmax + Q.vec - 1) / Q.vec - g.xmin / Q.vec;
+            rows = box_chunk_rows(bw);
+            ymin = g.ymin; ymax = g.ymax;
+            chunks = (ymax - ymin + rows - 1) / rows;
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    int incl = chunks;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(Q.n_items, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - chunks;
+    for (int k = 0; k < chunks; ++k) {
+        const int y0 = ymin + k * rows;
+        if (base + k < Q.cap)
+            Q.items[base + k] = make_uint2((uint32_t)inst, ((uint32_t)y0 << 16) | (uint32_t)min(rows, ymax - y0));
+    }
+}
+
 // ---- fused tail, step 1 -------------------------------------------------------------------
 // One CTA per image: ranks the rows of roi_boxes [B,R,6] whose class != -1 in order j
 // (TrimInstances), converts them to the int32 rows of UpSampleOutput, and records slot -> row so
@@ -231,19 +303,52 @@ paste_scalar_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, in
 constexpr int kPrepThreads = 256;
 constexpr int kPrepParts = 8;             // minimum CTAs per image (each repeats the cheap scan, owns 1/parts of the slots)
 
-__global__ void __launch_bounds__(kPrepThreads)
-tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ roi_masks, int r_rows,
-                 const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, float rh, float rw,
-                 int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
-                 uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ confmax) {
-    constexpr int kWarps = kPrepThreads / 32;
-    __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
-    const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+// ---- background fill --------------------------------------------------------------------------
+// Zeroes the valid prefix [B,M,PH,row] of the paste output: 97 % of CropAndPadMask's bytes do not
+// depend on the masks at all, only on M.  mlp_paste_prefill launches this right after the NMS
+// kernels on a parallel branch, so the stream of zeros overlaps RoIAlign, the mask head and the
+// tail preparation instead of waiting for them; the paste kernel then only writes the boxes
+// (paste_boxes_kernel).  One short-lived CTA per 64 KB, the launch shape that streams stores fastest on B200
+// (profiles/write_bw_r01.txt); CTAs past the device-side M exit at once.
+constexpr int kFillThreads = 256;
+constexpr int kFillVecs = 4096;           // uint4 per CTA = 64 KB
+
+__global__ void __launch_bounds__(kFillThreads)
+paste_fill_kernel(const int32_t* __restrict__ counts, int B, int m_rows, int64_t inst_vecs,
+                  uint4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int mx = 0;
+    for (int i = lane; i < B; i += 32) mx = max(mx, counts[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int M = min(max(mx, 1), m_rows);
+    const int64_t total = (int64_t)B * M * inst_vecs;
+    const int64_t start = (int64_t)blockIdx.x * kFillVecs;
+    if (start >= total) return;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4* p = out + start;
+    if (total - start >= kFillVecs) {
+#pragma unroll
+        for (int q = 0; q < kFillVecs / kFillThreads; ++q) stg_stream_u4(p + q * kFillThreads + threadIdx.x, zero4);
+    } else {
+        const int n = (int)(total - start);
+        for (int i = threadIdx.x; i < n; i += kFillThreads) stg_stream_u4(p + i, zero4);
+    }
+}
+
+// ---- fused tail, step 1, TMA form ---------------------------------------------------------------
+// Same contract as tail_prep_kernel; the bit tiles are built differently.  The mask head's output of
+// one RoI is ONE contiguous block ([mh*mw, C] interleaved: 15.7 KB at 28x28x5, or the 3 KB class
+// plane with the planar layout), so a warp fetches it with one cp.async.bulk into its own staging
+// slot (mbarrier completion, no registers held by loads in flight, full lines from DRAM) and then
+// thresholds its class channel out of shared memory with one ballot per mask row.
+constexpr int kPrepTmaWarps = 4;
+
+template <int kWarps>
+__device__ __forceinline__ int tail_scan(const float* __restrict__ rows, int R, int K, float rh, float rw,
+                                         int part, int parts, int32_t* __restrict__ drows,
+                                         int32_t* __restrict__ src, int* s_cnt, int* s_base, int* s_cm,
+                                         const BoxItems& Q, int b) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int R = r_dev ? *r_dev : r_rows;
-    if (R > r_rows) R = r_rows;
-    const float* rows = roi_boxes + (int64_t)b * R * 6;
     const int seg = (R + kWarps - 1) / kWarps;
     const int j0 = min(warp * seg, R), j1 = min(j0 + seg, R);
     int cnt = 0;
@@ -263,28 +368,30 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
     const int total = min(s_base[kWarps], K);
     int base = s_base[warp];
     int cm = INT_MIN;
-    int32_t* drows = det_i32 + (int64_t)b * K * 6;
-    int32_t* src = tail_src + (int64_t)b * K;
     for (int jb = j0; jb < j1; jb += 32) {
         const int j = jb + lane;
         const bool hit = (j < j1) && (rows[(int64_t)j * 6 + 4] != -1.0f);
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        int32_t o[6] = {0, 0, 0, 0, 0, 0};
+        int slot = -1;
+        bool mine = false;
         if (hit) {
-            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            slot = base + __popc(mask & ((1u << lane) - 1u));
             if (slot < K) {
                 float r[6];
 #pragma unroll
                 for (int q = 0; q < 6; ++q) r[q] = rows[(int64_t)j * 6 + q];
-                int32_t o[6];
                 upsample_row(r, rh, rw, o);
                 cm = max(cm, o[5]);
-                if (slot % parts == part) {
+                mine = slot % parts == part;
+                if (mine) {
 #pragma unroll
                     for (int q = 0; q < 6; ++q) drows[slot * 6 + q] = o[q];
                     src[slot] = j;
                 }
             }
         }
+        if (Q.vec && mask) box_items_append(Q, mine, o, b * K + slot);       // warp-uniform branch
         base += __popc(mask);
     }
     for (int o = 16; o > 0; o >>= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
@@ -294,13 +401,99 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
         const float m1[6] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
         int32_t o[6];
         upsample_row(m1, rh, rw, o);
-        for (int s = total + part + parts * (int)threadIdx.x; s < K; s += parts * kPrepThreads) {
+        for (int s = total + part + parts * (int)threadIdx.x; s < K; s += parts * kWarps * 32) {
 #pragma unroll
             for (int q = 0; q < 6; ++q) drows[s * 6 + q] = o[q];
             src[s] = -1;
         }
     }
     __syncthreads();                      // src[] / drows[] of this CTA's slots are written
+    return total;
+}
+
+__global__ void __launch_bounds__(kPrepTmaWarps * 32)
+tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ roi_masks, int r_rows,
+                     const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, int planar, float rh,
+                     float rw, int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
+                     uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
+                     int32_t* __restrict__ confmax, uint32_t slot_bytes, const BoxItems Q) {
+    constexpr int kWarps = kPrepTmaWarps;
+    extern __shared__ __align__(128) unsigned char s_stage[];     // [kWarps][slot_bytes]
+    __shared__ __align__(8) uint64_t s_bar[kWarps];
+    __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
+    const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    int R = r_dev ? *r_dev : r_rows;
+    if (R > r_rows) R = r_rows;
+    int32_t* drows = det_i32 + (int64_t)b * K * 6;
+    int32_t* src = tail_src + (int64_t)b * K;
+    const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
+                                        s_cnt, s_base, s_cm, Q, b);
+    if (threadIdx.x == 0 && part == 0) {
+        int m = INT_MIN;
+        for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
+        counts[b] = total;
+        confmax[b] = m;
+    }
+    const int px = mh * mw;
+    unsigned char* stage = s_stage + (size_t)warp * slot_bytes;
+    uint64_t* bar = &s_bar[warp];
+    uint32_t phase = 0;
+    const int es = planar ? 1 : C;
+    for (int s = part + parts * warp; s < total; s += parts * kWarps) {
+        const int j = src[s];
+        const int cls = drows[s * 6 + 4];
+        uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
+        if (cls < 0 || cls >= C) {                           // tf.gather_nd would raise: all-zero tile
+            for (int y = lane; y < mh; y += 32) out[y] = 0u;
+            continue;
+        }
+        const float* g = planar ? roi_masks + (((int64_t)b * R + j) * C + cls) * px
+                                : roi_masks + ((int64_t)b * R + j) * px * C;
+        if (lane == 0) {
+            mbar_expect_tx(bar, slot_bytes);
+            // the warp's generic-proxy reads of the previous tile (ordered by the __syncwarp below)
+            // come before the async proxy overwrites the slot
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_load_1d(stage, g, slot_bytes, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        const float* t = reinterpret_cast<const float*>(stage) + (planar ? 0 : cls);
+        for (int y0 = 0; y0 < mh; y0 += 32) {
+            uint32_t mine = 0u;
+            const int yn = min(32, mh - y0);
+            for (int u = 0; u < yn; ++u) {
+                const float v = (lane < mw) ? t[((y0 + u) * mw + lane) * es] : 0.0f;
+                const uint32_t w = __ballot_sync(0xffffffffu, v > 0.5f);
+                if (lane == u) mine = w;
+            }
+            if (lane < yn) out[y0 + lane] = mine;
+        }
+        __syncwarp();
+    }
+}
+
+// Register-gather form of the tail preparation (the fallback of tail_prep_tma_kernel: RoI blocks that are
+// not a multiple of 16 bytes or too large to stage, and the tile-less case K > 256).
+__global__ void __launch_bounds__(kPrepThreads)
+tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ roi_masks, int r_rows,
+                 const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, int planar, float rh, float rw,
+                 int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
+                 uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
+                 int32_t* __restrict__ confmax, const BoxItems Q) {
+    constexpr int kWarps = kPrepThreads / 32;
+    __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
+    const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int R = r_dev ? *r_dev : r_rows;
+    if (R > r_rows) R = r_rows;
+    int32_t* drows = det_i32 + (int64_t)b * K * 6;
+    int32_t* src = tail_src + (int64_t)b * K;
+    const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
+                                        s_cnt, s_base, s_cm, Q, b);
     if (threadIdx.x == 0 && part == 0) {
         int m = INT_MIN;
         for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
@@ -315,14 +508,16 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
         const int cls = drows[s * 6 + 4];
         uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
         const bool ok = cls >= 0 && cls < C;
-        const float* m = roi_masks + (((int64_t)b * R + j) * px) * C + (ok ? cls : 0);
+        const int es = planar ? 1 : C;
+        const float* m = planar ? roi_masks + (((int64_t)b * R + j) * C + (ok ? cls : 0)) * px
+                                : roi_masks + (((int64_t)b * R + j) * px) * C + (ok ? cls : 0);
         // all mask rows of the slot in flight at once (one DRAM round trip per 32 rows)
         for (int y0 = 0; y0 < mh; y0 += 32) {
             float v[32];
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
                 const int y = y0 + u;
-                v[u] = (ok && y < mh && lane < mw) ? __ldg(m + (int64_t)(y * mw + lane) * C) : 0.0f;
+                v[u] = (ok && y < mh && lane < mw) ? __ldg(m + (int64_t)(y * mw + lane) * es) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
@@ -333,16 +528,76 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
     }
 }
 
+// ---- boxes-only paste: walks the work items of the tail preparation behind a background fill --------
+template <int kMode>
+__global__ void __launch_bounds__(kPasteThreads)
+paste_boxes_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int K, int mh, int mw, int PH, int PW,
+                   const uint2* __restrict__ items, const int32_t* __restrict__ n_items, int item_cap,
+                   void* __restrict__ out) {
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
+    extern __shared__ __align__(16) unsigned char s_dyn[];           // [tile floats][column table], paste_smem_bytes
+    float* s_tile = reinterpret_cast<float*>(s_dyn);
+    uint2* s_col_buf = reinterpret_cast<uint2*>(s_dyn + paste_tile_bytes(mh * mw));
+    int M, thr;
+    paste_scalars(S, B, K, M, thr);
+    const int n = min(*n_items, item_cap);
+    const int spr = PW / kVec;
+    const int tid = threadIdx.x;
+    const int px = mh * mw;
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint2 q = __ldg(items + it);
+        const int b = (int)q.x / K, j = (int)q.x - b * K;
+        const int y0 = (int)(q.y >> 16), nrows = (int)(q.y & 0xffffu);
+        int row[6];
+        {
+            const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * K + j) * 6);
+            const int2 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+            row[0] = a0.x; row[1] = a0.y; row[2] = a1.x; row[3] = a1.y; row[4] = a2.x; row[5] = a2.y;
+        }
+        const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
+        if (!g.active || j >= M) continue;                  // filtered by the batch-wide confidence rule (block-uniform)
+        const TileRef tref = tile_ref(S, b, j, K, px, row[4], mh, mw);
+        __syncthreads();                                    // previous item done with s_tile / s_col
+        tref.fill(s_tile, mh, tid, kPasteThreads);
+        paste_fill_cols(s_col_buf, g, mw, tid, kPasteThreads);
+        const uint2* s_col = (g.xmax - g.xmin <= kMaxCols) ? s_col_buf : nullptr;
+        __syncthreads();
+        const int sL = g.xmin / kVec;
+        const int bw = (g.xmax + kVec - 1) / kVec - sL;
+        uint4* rows_out = reinterpret_cast<uint4*>(out) + (((int64_t)b * M + j) * PH + y0) * spr;
+        const int nb = nrows * bw;
+        for (int i = tid; i < nb; i += kPasteThreads) {
+            const int r = i / bw;
+            const int seg = sL + (i - r * bw);
+            const uint4 v = paste_segment<kMode>(s_tile, s_col, g, mh, mw, y0 + r, seg * kVec);
+            stg_stream_u4(rows_out + (int64_t)r * spr + seg, v);
+        }
+    }
+}
+
 int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, int batch, int m_rows,
                  int m_stride, int mask_h, int mask_w, int frame_h, int frame_w, int out_mode,
-                 void* out_dev, cudaStream_t st) {
+                 void* out_dev, cudaStream_t st, const BoxItems* boxes = nullptr) {
     ProfScope prof(ctx, MLP_ST_PASTE, st);
     const int vec = out_mode == MLP_PASTE_F32 ? 4 : (out_mode == MLP_PASTE_U8 ? 16 : 128);
     int band_kb = 64;                                  // tuning knobs (tools/bench_paste.py)
     int ctas_per_sm = 0;                               // 0: one CTA per item (default)
     if (const char* e = getenv("MLP_PASTE_CTAS_PER_SM")) ctas_per_sm = atoi(e);
     if (const char* e = getenv("MLP_PASTE_BAND_KB")) band_kb = atoi(e) > 0 ? atoi(e) : 64;
-    if (frame_w % vec == 0) {
+    if (boxes) {
+        // behind a background fill: only the box segments, from the work-item list of the tail preparation
+        MLP_CHECK_ARG(frame_w % vec == 0, "paste: a prefilled output needs a frame width that is a multiple of %d", vec);
+        const int grid = ctx->sm_count * 8;
+        const size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
+#define MLP_PASTE_LAUNCH(MODE)                                                                                 \
+    paste_boxes_kernel<MODE><<<grid, kPasteThreads, smem, st>>>(det_i32_dev, S, batch, m_rows, mask_h, mask_w,    \
+                                                            frame_h, frame_w, boxes->items, boxes->n_items,    \
+                                                            boxes->cap, out_dev)
+        if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
+        else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
+        else MLP_PASTE_LAUNCH(MLP_PASTE_F32);
+#undef MLP_PASTE_LAUNCH
+    } else if (frame_w % vec == 0) {
         const int row_bytes = frame_w / vec * 16;
         int band_rows = (band_kb * 1024) / row_bytes;
         if (band_rows < 1) band_rows = 1;
@@ -350,8 +605,9 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
         const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
         int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
         if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
+        const size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
 #define MLP_PASTE_LAUNCH(MODE)                                                                         \
-    paste_kernel<MODE><<<grid, kPasteThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
+    paste_kernel<MODE><<<grid, kPasteThreads, smem, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
                                                       mask_w, frame_h, frame_w, band_rows, out_dev)
         if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
         else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
@@ -421,11 +677,17 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
                               int num_classes, float ratio_h, float ratio_w, int k_rows, int frame_h,
                               int frame_w, int out_mode, int32_t* det_i32_dev, int32_t* counts_dev,
                               int32_t* m_dev, void* out_dev, mlp_stream_t stream) {
+    const int flags = out_mode & ~0xff;
+    out_mode &= 0xff;
+    const bool prefilled = (flags & MLP_PASTE_PREFILLED) != 0;
+    const int planar = (flags & MLP_MASKS_PLANAR) ? 1 : 0;
+    MLP_CHECK_ARG((flags & ~(MLP_PASTE_PREFILLED | MLP_MASKS_PLANAR)) == 0, "mlp_trim_paste: unknown flags 0x%x", flags);
     MLP_CHECK_ARG(ctx && roi_boxes_dev && roi_masks_dev && det_i32_dev && counts_dev && m_dev &&
                       (out_dev || out_mode == MLP_PASTE_NONE),
                   "mlp_trim_paste: NULL argument");
     MLP_CHECK_ARG(r_rows >= 1 && k_rows >= 1 && num_classes >= 1, "mlp_trim_paste: bad shape R=%d K=%d C=%d",
                   r_rows, k_rows, num_classes);
+    MLP_CHECK_ARG(mlp_aligned16(roi_masks_dev), "mlp_trim_paste: roi_masks_dev must be 16-byte aligned");
     int rc = check_paste_args("mlp_trim_paste", batch, mask_h, mask_w, frame_h, frame_w,
                               out_mode == MLP_PASTE_NONE ? MLP_PASTE_U8 : out_mode, out_dev);
     if (rc) return rc;
@@ -438,14 +700,53 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     int32_t* tail_src = ft.tail_src;
     int32_t* confmax = ft.confmax;
     uint32_t* tail_bits = ft.tail_bits;
+    ctx->tail_planar = planar;
+    BoxItems Q;
+    memset(&Q, 0, sizeof(Q));
+    if (prefilled && out_mode != MLP_PASTE_NONE) {
+        const int vec = out_mode == MLP_PASTE_F32 ? 4 : (out_mode == MLP_PASTE_U8 ? 16 : 128);
+        MLP_CHECK_ARG(frame_w % vec == 0, "mlp_trim_paste: a prefilled output needs a frame width that is a multiple of %d", vec);
+        MLP_CHECK_ARG(frame_h < 65536, "mlp_trim_paste: a prefilled output needs a frame height below 65536");
+        // worst case: every box spans the frame; a chunk holds at least max(1, kBoxSegs / segments per row) rows
+        const int spr = frame_w / vec;
+        const int rows_min = kBoxSegs / spr > 1 ? kBoxSegs / spr : 1;
+        const int64_t cap = (int64_t)batch * k_rows * ((frame_h + rows_min - 1) / rows_min);
+        MLP_CHECK_ARG(cap < (1ll << 28), "mlp_trim_paste: work-item list too large");
+        rc = mlp_ensure_scratch(ctx, MLP_ARENA_PASTE, 256 + cap * (int64_t)sizeof(uint2));
+        if (rc) return rc;
+        Q.n_items = static_cast<int32_t*>(ctx->arena[MLP_ARENA_PASTE]);
+        Q.items = reinterpret_cast<uint2*>(static_cast<char*>(ctx->arena[MLP_ARENA_PASTE]) + 256);
+        Q.cap = (int)cap;
+        Q.PH = frame_h; Q.PW = frame_w; Q.vec = vec;
+        MLP_CUDA(cudaMemsetAsync(Q.n_items, 0, 4, st));
+    }
     {
         ProfScope prof(ctx, MLP_ST_TAIL_FUSED, st);
-        // CTAs per image grow with the capacity so that each warp gathers at most ~2 tiles
-        int parts = k_rows / 16;
-        parts = parts < kPrepParts ? kPrepParts : (parts > 64 ? 64 : parts);
-        tail_prep_kernel<<<dim3(batch, parts), kPrepThreads, 0, st>>>(
-            roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, ratio_h,
-            ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax);
+        // One RoI's mask-head block is contiguous, so when bit tiles are built a warp stages it with one
+        // bulk copy (tail_prep_tma_kernel); the register-gather kernel remains for blocks that are not a
+        // multiple of 16 bytes or too large to stage, and for the tile-less case (many instances).
+        const int px = mask_h * mask_w;
+        const int64_t slot_bytes = (int64_t)px * (planar ? 1 : num_classes) * 4;
+        bool tma = tail_bits != nullptr && slot_bytes % 16 == 0 && slot_bytes * kPrepTmaWarps <= 200 * 1024;
+        if (const char* e = getenv("MLP_TAIL_TMA")) tma = tma && atoi(e) != 0;              // A/B knob
+        if (tma) {
+            // at most two tiles per warp: one wave of CTAs, enough bytes in flight per SM
+            int parts = (k_rows + 2 * kPrepTmaWarps - 1) / (2 * kPrepTmaWarps);
+            parts = parts < 1 ? 1 : (parts > 64 ? 64 : parts);
+            const size_t smem = (size_t)slot_bytes * kPrepTmaWarps;
+            MLP_CUDA(cudaFuncSetAttribute(tail_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            tail_prep_tma_kernel<<<dim3(batch, parts), kPrepTmaWarps * 32, smem, st>>>(
+                roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, (uint32_t)slot_bytes, Q);
+        } else {
+            // CTAs per image grow with the capacity so that each warp gathers at most ~2 tiles
+            int parts = k_rows / 16;
+            parts = parts < kPrepParts ? kPrepParts : (parts > 64 ? 64 : parts);
+            tail_prep_kernel<<<dim3(batch, parts), kPrepThreads, 0, st>>>(
+                roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, Q);
+        }
         MLP_LAUNCH_CHECK(ctx);
     }
     if (out_mode == MLP_PASTE_NONE) return MLP_OK;       // mlp_tile_summary consumes the prepared tail
@@ -458,9 +759,35 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     S.r_dev = r_dev;
     S.r_rows = r_rows;
     S.C = num_classes;
+    S.planar = planar;
     S.counts = counts_dev;
     S.confmax = confmax;
     S.m_out = m_dev;
     return paste_launch(ctx, det_i32_dev, S, batch, k_rows, k_rows, mask_h, mask_w, frame_h, frame_w,
-                        out_mode, out_dev, st);
+                        out_mode, out_dev, st, prefilled ? &Q : nullptr);
+}
+
+// Background of CropAndPadMask, ahead of time: zero the [B,M,PH,PW] prefix of out_dev with M taken from
+// the detection counts (M = max(1, max_b counts_b), engine/layers/misc.py:235-236).  Enqueue it on a
+// stream that runs beside RoIAlign / the mask head, join, then call mlp_trim_paste with
+// MLP_PASTE_PREFILLED.  TrimInstances can only drop rows, so the M of the tail never exceeds this one.
+extern "C" int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* counts_dev, int batch, int k_rows, int frame_h,
+                                 int frame_w, int out_mode, void* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && counts_dev && out_dev, "mlp_paste_prefill: NULL argument");
+    MLP_CHECK_ARG(batch >= 1 && k_rows >= 1 && frame_h >= 1 && frame_w >= 1, "mlp_paste_prefill: bad shape");
+    MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8 || out_mode == MLP_PASTE_BITS,
+                  "mlp_paste_prefill: unknown out_mode %d", out_mode);
+    const int vec = out_mode == MLP_PASTE_F32 ? 4 : (out_mode == MLP_PASTE_U8 ? 16 : 128);
+    MLP_CHECK_ARG(frame_w % vec == 0, "mlp_paste_prefill: frame width %d is not a multiple of %d", frame_w, vec);
+    MLP_CHECK_ARG(mlp_aligned16(out_dev), "mlp_paste_prefill: out_dev must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(ctx, MLP_ST_PASTE_FILL, st);
+    const int64_t inst_vecs = (int64_t)frame_h * (frame_w / vec);
+    const int64_t ctas = ((int64_t)batch * k_rows * inst_vecs + kFillVecs - 1) / kFillVecs;
+    MLP_CHECK_ARG(ctas < (1ll << 31), "mlp_paste_prefill: output too large");
+    paste_fill_kernel<<<(unsigned)ctas, kFillThreads, 0, st>>>(counts_dev, batch, k_rows, inst_vecs,
+                                                             static_cast<uint4*>(out_dev));
+    MLP_LAUNCH_CHECK(ctx);
+    return MLP_OK;
 }

@@ -31,6 +31,7 @@ struct PasteSrc {
     const int32_t* counts;        // [B] valid instances per image
     const int32_t* confmax;       // [B] max int confidence of the valid rows (INT_MIN if none)
     int32_t* m_out;               // [1] M written back for the host
+    int planar;                   // roi_masks is [B,R,C,mh*mw] (class planes) instead of [B,R,mh*mw,C]
 };
 
 struct PasteGeom {
@@ -73,6 +74,37 @@ __device__ __forceinline__ float paste_value(const float* __restrict__ tile, int
     return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
 }
 
+// Column table of one box: the x half of the resize depends on the column only, so a CTA that is about to
+// evaluate many rows of a box computes (xlo, xhi, lx) once per column (same three rounded operations as
+// paste_value) and every pixel then costs one 8-byte shared load instead of a multiply, floor, ceil, two
+// conversions, a clamp pair and a subtract.  Entry: x = xlo | xhi << 16, y = bits of lx.
+constexpr int kMaxCols = 2048;            // wider boxes fall back to paste_value
+
+__device__ __forceinline__ void paste_fill_cols(uint2* __restrict__ s_col, const PasteGeom& g, int mw, int tid,
+                                                int nthreads) {
+    const int ow = g.xmax - g.xmin;
+    if (ow > kMaxCols) return;
+    for (int c = tid; c < ow; c += nthreads) {
+        const float p = __fmul_rn((float)c, g.sx);
+        const float fl = floorf(p);
+        const int xlo = max((int)fl, 0);
+        const int xhi = min((int)ceilf(p), mw - 1);
+        s_col[c] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), __float_as_uint(__fsub_rn(p, fl)));
+    }
+}
+
+// paste_value with the x terms from the column table; row_lo / row_hi point at tile rows ylo / yhi
+__device__ __forceinline__ float paste_value_cols(const float* __restrict__ row_lo, const float* __restrict__ row_hi,
+                                                  float ly, const uint2 e) {
+    const int xlo = (int)(e.x & 0xffffu), xhi = (int)(e.x >> 16);
+    const float lx = __uint_as_float(e.y);
+    const float tl = row_lo[xlo], tr = row_lo[xhi];
+    const float bl = row_hi[xlo], br = row_hi[xhi];
+    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+    const float b = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+    return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
+}
+
 // M and the row-filter threshold for this launch (block-uniform, every warp computes it).
 __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_rows, int& M, int& thr) {
     if (!S.fused) {
@@ -102,9 +134,9 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
 // Tile element i of instance (b, j) as the int the reference's mask tensor would hold.
 struct TileRef {
     const int32_t* mi;     // standalone
-    const float* mf;       // fused (already offset to the class channel), stride C
+    const float* mf;       // fused (already offset to the class channel / plane), element stride es
     const uint32_t* bits;  // fused, pre-thresholded bit rows
-    int C, mw;
+    int es, mw;
     bool valid;
     __device__ __forceinline__ int at(int i) const {
         if (mi) return __ldg(mi + i);
@@ -112,14 +144,27 @@ struct TileRef {
             const int y = i / mw;
             return valid ? (int)((__ldg(bits + y) >> (i - y * mw)) & 1u) : 0;
         }
-        return valid ? (int)(__ldg(mf + (int64_t)i * C) > 0.5f) : 0;
+        return valid ? (int)(__ldg(mf + (int64_t)i * es) > 0.5f) : 0;
+    }
+    // whole tile -> shared memory as floats, all threads of the CTA (no per-element division on the bit path)
+    __device__ __forceinline__ void fill(float* __restrict__ s_tile, int mh, int tid, int nthreads) const {
+        if (bits && !mi) {
+            const int lane = tid & 31, nw = nthreads >> 5;
+            for (int y = tid >> 5; y < mh; y += nw) {
+                const uint32_t w = valid ? __ldg(bits + y) : 0u;
+                if (lane < mw) s_tile[y * mw + lane] = (float)((w >> lane) & 1u);
+            }
+            return;
+        }
+        const int px = mh * mw;
+        for (int i = tid; i < px; i += nthreads) s_tile[i] = (float)at(i);
     }
 };
 
 __device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int m_stride, int px, int cls,
                                             int mh, int mw) {
     TileRef t;
-    t.mi = nullptr; t.mf = nullptr; t.bits = nullptr; t.C = S.C; t.mw = mw; t.valid = false;
+    t.mi = nullptr; t.mf = nullptr; t.bits = nullptr; t.es = S.planar ? 1 : S.C; t.mw = mw; t.valid = false;
     if (!S.fused) {
         t.mi = S.masks_i32 + ((int64_t)b * m_stride + j) * px;
         return t;
@@ -128,7 +173,8 @@ __device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int
     const int jsrc = S.tail_src[(int64_t)b * m_stride + j];
     t.valid = jsrc >= 0 && cls >= 0 && cls < S.C;
     if (S.tail_bits) t.bits = S.tail_bits + ((int64_t)b * m_stride + j) * mh;
-    t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * px * S.C + cls) : 0);
+    if (S.planar) t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * S.C + cls) * px : 0);
+    else t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * px * S.C + cls) : 0);
     return t;
 }
 

@@ -914,6 +914,7 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
         T.src.r_dev = r_dev;
         T.src.r_rows = r_rows;
         T.src.C = num_classes;
+        T.src.planar = ctx->tail_planar;
         T.src.counts = counts_dev;
         T.src.confmax = ft.confmax;
         T.src.m_out = m_dev_out;

@@ -34,6 +34,13 @@ class DetectionConfig:
     strict_batch: bool = True
     paste_output: str = "uint8"          # 'uint8' (binary, > 0.5 fused), 'bits' (8 px/byte) or 'float32' (drop-in)
     fused: bool = True                   # fused halves (6 kernels) vs the chain of stage kernels (13)
+    # Zero the background of the [B,M,PH,PW] masks on a second stream right after the NMS kernels, beside
+    # RoIAlign / the mask head, and let the paste kernel write the boxes only (mlp_paste_prefill).  Only
+    # worth it when trim_and_paste follows; detect_and_align(prefill=...) overrides it per call.
+    prefill: bool = False
+    # layout of the mask head output handed to the tail: 'interleaved' = the reference's [B,R,mh,mw,C];
+    # 'planar' = [B,R,C,mh,mw] (channels-first head): the tail then reads 1/C of the bytes
+    mask_layout: str = "interleaved"
 
 
 @dataclass
@@ -89,6 +96,13 @@ class PostProcessPipeline:
         self.params = rt.DetectionParamsC(
             float(self.cfg.min_confidence), float(self.cfg.nms_iou_threshold),
             float(self.cfg.post_iou_threshold), self.K, 1 if self.cfg.strict_batch else 0)
+        if self.cfg.mask_layout not in ("interleaved", "planar"):
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"unknown mask_layout {self.cfg.mask_layout!r}")
+        if self.cfg.mask_layout == "planar" and not self.cfg.fused:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "mask_layout='planar' needs the fused tail (fused=True)")
+        self._tail_flags = rt.MLP_MASKS_PLANAR if self.cfg.mask_layout == "planar" else 0
+        self._side = None                # second stream for the background fill (created on first use)
+        self._fill_done = None           # event: the fill of the batch in flight has been enqueued / finished
         self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -97,9 +111,13 @@ class PostProcessPipeline:
         ch, cw = self.cfg.crop_size
         mh, mw = self.cfg.mask_size
         f32, i32 = torch.float32, torch.int32
-        self.det = c.empty((B, K, 6), f32)
+        # det + counts live in ONE buffer (masklab_b200.dist.record_*): the cross-class NMS kernel writes the
+        # multi-GPU gather's send buffer directly, no staging copy before the collective
+        from . import dist as mdist
+        self.record = c.empty((mdist.record_words(B, K)[1],), i32)
+        self.record.zero_()
+        self.det, self.counts = mdist.record_views(self.record, B, K)
         self.keep = c.empty((B, K, 2), i32)
-        self.counts = c.empty((B,), i32)
         self.m_dev = c.empty((1,), i32)
         self.dist = c.empty((B, K, 7), f32)
         self.level_counts = c.empty((L, B), i32)
@@ -131,11 +149,19 @@ class PostProcessPipeline:
         return sum(t.numel() * t.element_size() for t in ts) + self.ctx.scratch_bytes()
 
     # --------------------------------------------------------------- first half
-    def detect_and_align(self, loc_pred, cls_pred, fmaps):
+    def _can_prefill(self):
+        vec = {rt.MLP_PASTE_F32: 4, rt.MLP_PASTE_U8: 16, rt.MLP_PASTE_BITS: 128}[self.paste_mode]
+        return self.cfg.fused and self.frame_hw[1] % vec == 0
+
+    def detect_and_align(self, loc_pred, cls_pred, fmaps, prefill=None):
         """loc_pred [B,N,4], cls_pred [B,N,C], fmaps: L tensors [B,Hf,Wf,Cf] (NHWC), all f32
-        CUDA.  Enqueues a2-a10; returns AlignedRois (device tensors, no host sync)."""
+        CUDA.  Enqueues a2-a10; returns AlignedRois (device tensors, no host sync).  With prefill
+        (default: config.prefill) the zero background of the masks is streamed out on a second
+        stream from the moment the NMS kernels have produced M; trim_and_paste joins it."""
         c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
         st = c.stream()
+        prefill = (self.cfg.prefill if prefill is None else bool(prefill)) and self._can_prefill()
+        self._fill_done = None
         if tuple(loc_pred.shape) != (B, self.N, 4) or tuple(cls_pred.shape) != (B, self.N, self.C):
             raise rt.InvalidArgumentError(
                 rt.MLP_EINVAL, f"expected loc {(B, self.N, 4)} / cls {(B, self.N, self.C)}, got "
@@ -146,6 +172,37 @@ class PostProcessPipeline:
             if tuple(f.shape) != (B, h, w, self.Cf):
                 raise rt.InvalidArgumentError(
                     rt.MLP_EINVAL, f"FPN map {tuple(f.shape)} != {(B, h, w, self.Cf)}")
+        if self.cfg.fused and prefill:
+            fmap_ptrs = (ctypes.c_void_p * L)(*[c.view(f, torch.float32).value for f in fmaps[:L]])
+            ch, cw = self.cfg.crop_size
+            rt.check(lib.mlp_detect_plan(
+                c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
+                c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
+                ctypes.byref(self.params), int(self.cfg.max_k), float(self.cfg.base_size),
+                c.view(self.det), c.view(self.keep), c.view(self.counts), c.view(self.m_dev),
+                c.view(self.dist), c.view(self.level_counts), c.view(self.level_m), st))
+            # fork: the fill needs only counts (-> M); it runs beside RoIAlign, the mask head and the tail prep
+            cur = torch.cuda.current_stream(c.device)
+            if self._side is None:
+                # least priority: the fill's 64 KB CTAs take whatever SM slots the RoIAlign / mask-head kernels
+                # of the caller's (higher-priority) stream leave free, instead of queueing ahead of them
+                self._side = torch.cuda.Stream(device=c.device, priority=0)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(fork)
+                rt.check(lib.mlp_paste_prefill(
+                    c.handle, c.view(self.counts), B, K, self.frame_hw[0], self.frame_hw[1], self.paste_mode,
+                    c.view(self.pasted), ctypes.c_void_p(self._side.cuda_stream)))
+                self._fill_done = torch.cuda.Event()
+                self._fill_done.record(self._side)
+            rt.check(lib.mlp_roi_align_run(
+                c.handle, fmap_ptrs, self._fh, self._fw, L, self.Cf, c.view(self.dist), B, K, K,
+                c.view(self.m_dev), float(self.image_hw[0]), float(self.image_hw[1]), int(ch), int(cw),
+                c.view(self.level_counts), c.view(self.level_m), self._crop_ptrs, c.view(self.roi_boxes),
+                st))
+            return AlignedRois(self.det, self.keep, self.counts, self.m_dev, self.dist,
+                               self.level_counts, self.level_m, self.crops, self.roi_boxes)
         if self.cfg.fused:
             fmap_ptrs = (ctypes.c_void_p * L)(*[c.view(f, torch.float32).value for f in fmaps[:L]])
             ch, cw = self.cfg.crop_size
@@ -177,6 +234,13 @@ class PostProcessPipeline:
         return AlignedRois(self.det, self.keep, self.counts, self.m_dev, self.dist, self.level_counts,
                            self.level_m, self.crops, self.roi_boxes)
 
+    def prefill_background(self):
+        """Enqueue CropAndPadMask's zero background for the current detections on the CURRENT stream (no fork);
+        detect_and_align(prefill=True) does this on a second stream.  For measuring the fill alone."""
+        c = self.ctx
+        rt.check(self.lib.mlp_paste_prefill(c.handle, c.view(self.counts), self.B, self.K, self.frame_hw[0],
+                                            self.frame_hw[1], self.paste_mode, c.view(self.pasted), c.stream()))
+
     def roi_views(self, rois):
         """Reference-shaped views ([B,Mf,ch,cw,Cf] per level, [B,R,6]) — one small D2H."""
         mf, R = rois.shapes()
@@ -204,6 +268,11 @@ class PostProcessPipeline:
         mode = self.paste_mode
         self._compact_det = not self.cfg.fused
         if self.cfg.fused:
+            mode |= self._tail_flags
+            if self._fill_done is not None:                  # join the background fill of this batch
+                torch.cuda.current_stream(c.device).wait_event(self._fill_done)
+                self._fill_done = None
+                mode |= rt.MLP_PASTE_PREFILLED
             rt.check(lib.mlp_trim_paste(
                 c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
                 float(ratio[0]), float(ratio[1]), K, self.frame_hw[0], self.frame_hw[1], mode,
@@ -254,9 +323,15 @@ class PostProcessPipeline:
             self.crack_bits = c.empty((B, PH, (PW + 31) // 32), torch.int32)
             self.crack_box = c.empty((4 + 8 * B,), torch.int32)
         def tail():
+            flags = 0
+            if self._fill_done is not None:                  # a background fill of this batch is in flight: join it
+                torch.cuda.current_stream(c.device).wait_event(self._fill_done)
+                self._fill_done = None
+                flags = rt.MLP_PASTE_PREFILLED if paste else 0
             rt.check(lib.mlp_trim_paste(
                 c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C,
-                float(ratio[0]), float(ratio[1]), K, PH, PW, self.paste_mode if paste else rt.MLP_PASTE_NONE,
+                float(ratio[0]), float(ratio[1]), K, PH, PW,
+                (self.paste_mode if paste else rt.MLP_PASTE_NONE) | self._tail_flags | flags,
                 c.view(self.det_i32), c.view(self.trim_counts), c.view(self.trim_m),
                 c.view(self.pasted) if paste else ctypes.c_void_p(None), c.stream()))
 
@@ -341,25 +416,36 @@ class PostProcessPipeline:
         return self.summary[:self.B * Mo * 11].view(self.B, Mo, 11)
 
     # ---------------------------------------------------------------- CUDA graph
-    def capture(self, loc_pred, cls_pred, fmaps, roi_masks):
+    def _own_context(self):
+        """A captured graph bakes the ctx's scratch pointers in.  The per-device singleton ctx is shared
+        with every stand-alone layer call (which may regrow an arena for a larger shape), so a pipeline
+        that is about to be captured moves to a private ctx first; capture then freezes it."""
+        if self.ctx.shared:
+            self.ctx = rt.Context(self.ctx.device)
+
+    def capture(self, loc_pred, cls_pred, fmaps, roi_masks, prefill=None):
         """Capture one whole batch (detect_and_align + trim_and_paste over THESE buffers) into a CUDA
         graph: the path is sync-free - every data-dependent size stays on the device - so the six
         kernels and their memsets replay as one launch.  Refill the same input tensors and call
         `.replay()` on the returned graph; results land in the pipeline's buffers as usual.  The
         mask head is not part of the graph: roi_masks must already hold its output for the RoIs of
         this batch when the graph is replayed (for a real model capture the two halves separately)."""
+        self._own_context()
         torch.cuda.synchronize(self.ctx.device)
         side = torch.cuda.Stream(device=self.ctx.device)
         side.wait_stream(torch.cuda.current_stream(self.ctx.device))
         with torch.cuda.stream(side):                       # warm-up: scratch growth, function attributes
             for _ in range(2):
-                rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+                rois = self.detect_and_align(loc_pred, cls_pred, fmaps, prefill=prefill)
                 self.trim_and_paste(rois, roi_masks)
         torch.cuda.current_stream(self.ctx.device).wait_stream(side)
         torch.cuda.synchronize(self.ctx.device)
+        self.ctx.freeze(True)                               # the graph references the arenas from here on
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+        # captured on a high-priority stream: kernel nodes inherit it, the forked background fill stays at the
+        # least priority and only fills the SM slots the main chain leaves free
+        with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.ctx.device, priority=-1)):
+            rois = self.detect_and_align(loc_pred, cls_pred, fmaps, prefill=prefill)
             self.trim_and_paste(rois, roi_masks)
         return graph, rois
 
@@ -381,7 +467,7 @@ class PostProcessPipeline:
             if parallel_branches:
                 start = torch.cuda.Event()
                 start.record(cur)
-            rois = self.detect_and_align(loc_pred, cls_pred, fmaps)
+            rois = self.detect_and_align(loc_pred, cls_pred, fmaps, prefill=False)    # no masks are written
             tail, road, summarize = self.trim_and_summarize(rois, roi_masks, seg_outs, split=True)
             if parallel_branches:
                 with torch.cuda.stream(branch):             # the road scan only reads the semantic map: it runs beside
@@ -403,6 +489,7 @@ class PostProcessPipeline:
             if parallel_branches:
                 cur.wait_stream(branch)
             return rois
+        self._own_context()
         torch.cuda.synchronize(self.ctx.device)
         side = torch.cuda.Stream(device=self.ctx.device)
         side.wait_stream(torch.cuda.current_stream(self.ctx.device))
@@ -411,6 +498,7 @@ class PostProcessPipeline:
                 run()
         torch.cuda.current_stream(self.ctx.device).wait_stream(side)
         torch.cuda.synchronize(self.ctx.device)
+        self.ctx.freeze(True)                               # the graph references the arenas from here on
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             rois = run()

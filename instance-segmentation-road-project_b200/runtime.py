@@ -14,13 +14,14 @@ import torch.utils.dlpack
 
 from . import build as _build
 
-MLP_OK, MLP_EINVAL, MLP_ECUDA, MLP_ENOMEM, MLP_EDLPACK, MLP_EBATCH = 0, -1, -2, -3, -4, -5
+MLP_OK, MLP_EINVAL, MLP_ECUDA, MLP_ENOMEM, MLP_EDLPACK, MLP_EBATCH, MLP_EFROZEN = 0, -1, -2, -3, -4, -5, -6
 MLP_F32, MLP_I32, MLP_U8, MLP_I64 = 0, 1, 2, 3
 MLP_MAX_LEVELS, MLP_MAX_ANCHORS, MLP_MAX_BATCH, MLP_MAX_KEEP = 8, 32, 32, 2048
 MLP_PASTE_F32, MLP_PASTE_U8, MLP_PASTE_BITS, MLP_PASTE_NONE = 0, 1, 2, 3
+MLP_PASTE_PREFILLED, MLP_MASKS_PLANAR = 0x100, 0x200
 
 _ERRNAMES = {MLP_EINVAL: "MLP_EINVAL", MLP_ECUDA: "MLP_ECUDA", MLP_ENOMEM: "MLP_ENOMEM",
-             MLP_EDLPACK: "MLP_EDLPACK", MLP_EBATCH: "MLP_EBATCH"}
+             MLP_EDLPACK: "MLP_EDLPACK", MLP_EBATCH: "MLP_EBATCH", MLP_EFROZEN: "MLP_EFROZEN"}
 
 
 class MaskLabError(RuntimeError):
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mlp_ctx_sm_count": (_I, [_P]),
     "mlp_ctx_scratch_bytes": (_L, [_P]),
     "mlp_ctx_launch_count": (_L, [_P]),
+    "mlp_ctx_freeze_scratch": (_I, [_P, _I]),
     "mlp_stage_name": (ctypes.c_char_p, [_I]),
     "mlp_ctx_profile_enable": (_I, [_P, _I]),
     "mlp_ctx_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
@@ -113,6 +115,9 @@ SIGNATURES = {
                               ctypes.POINTER(DetectionParamsC), _I, _F, ctypes.POINTER(_P),
                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _I, _I, _I,
                               _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P]),
+    "mlp_detect_plan": (_I, [_P, ctypes.POINTER(PriorConfigC), _P, _P, _I, _I, _I, _I,
+                             ctypes.POINTER(DetectionParamsC), _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mlp_paste_prefill": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
@@ -200,6 +205,23 @@ class Context:
         h = ctypes.c_void_p()
         check(self.lib.mlp_ctx_create(self.device, ctypes.byref(h)))
         self.handle = h
+        self.shared = False          # True for the per-device singleton of Context.get()
+        self.frozen = False
+
+    def __del__(self):
+        # private contexts (pipelines that own their scratch) release it with the last reference
+        try:
+            if getattr(self, "handle", None) and not getattr(self, "shared", True):
+                self.lib.mlp_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:            # interpreter shutdown
+            pass
+
+    def freeze(self, on=True):
+        """A captured CUDA graph bakes this ctx's scratch pointers in: once frozen, a call that would
+        have to grow (= free and re-allocate) an arena raises MLP_EFROZEN instead."""
+        check(self.lib.mlp_ctx_freeze_scratch(self.handle, 1 if on else 0))
+        self.frozen = bool(on)
 
     @classmethod
     def get(cls, device=None):
@@ -213,6 +235,7 @@ class Context:
         inst = cls._instances.get(device)
         if inst is None:
             inst = cls._instances[device] = cls(device)
+            inst.shared = True
         return inst
 
     def close(self):

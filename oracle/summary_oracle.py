@@ -63,6 +63,38 @@ def fit_line(pos):
     return F32(t0), F32(t1)
 
 
+def fit_line_f32(pos, order="blas"):
+    """What TensorFlow itself computes in _calculate_theta (misc.py:706-718), emulated in float32 to QUANTIFY
+    how far the float64 contract above sits from the reference's own arithmetic (it is not the contract):
+    xs = [y, 1] and ys = x cast to float32, X^T X and X^T y as float32 matrix products, tf.linalg.det's sign
+    test, tf.linalg.inv as a float32 partial-pivoting LU (LAPACK sgetrf/sgetri here, Eigen PartialPivLU in TF),
+    then the float32 product inv @ (X^T y).  The accumulation order inside TF's matmul is an implementation
+    detail, so two orders are offered: "blas" (NumPy's sgemm) and "sequential" (one float32 add per row)."""
+    pos = np.asarray(pos, dtype=np.int64).reshape(-1, 2)
+    if pos.shape[0] == 0:
+        return F32(0), F32(0)
+    xs = np.stack([pos[:, 0].astype(F32), np.ones(pos.shape[0], F32)], axis=1)       # [n,2]
+    ys = pos[:, 1].astype(F32)[:, None]                                             # [n,1]
+    if order == "blas":
+        x_mat = (xs.T @ xs).astype(F32)
+        x_y = (xs.T @ ys).astype(F32)
+    else:
+        def seq(terms):
+            acc = F32(0)
+            for t in terms:
+                acc = F32(acc + t)
+            return acc
+        y = xs[:, 0]
+        x_mat = np.array([[seq(y * y), seq(y)], [seq(y), seq(np.ones_like(y))]], dtype=F32)
+        x_y = np.array([[seq(y * ys[:, 0])], [seq(ys[:, 0])]], dtype=F32)
+    det = F32(F32(x_mat[0, 0] * x_mat[1, 1]) - F32(x_mat[0, 1] * x_mat[1, 0]))
+    if not det > 0:
+        return F32(0), F32(0)
+    inv = np.linalg.inv(x_mat).astype(F32)                                         # float32 LU (sgesv)
+    theta = (inv @ x_y).astype(F32)
+    return F32(theta[0, 0]), F32(theta[1, 0])
+
+
 def road_marginals(road):
     """_calculate_marginal_x_by_y_axis, misc.py:680-704.  road: int [PH,PW].  tf.segment_min/max
     over the sorted row ids give one (x_min, x_max) per row up to the last road row, 0 for rows
@@ -87,13 +119,15 @@ def road_marginals(road):
     return left[drop:left.shape[0] - drop], right[drop:right.shape[0] - drop]
 
 
-def road_unit_lengths(road, default_road_size=3.25):
+def road_unit_lengths(road, default_road_size=3.25, fit=None):
     """_calculate_road_size_by_vertical_per_batch, misc.py:660-678 -> float32 [PH]: metres per
-    pixel on every frame row from the fitted left/right road borders."""
+    pixel on every frame row from the fitted left/right road borders.  `fit` swaps the line fit
+    (default: the float64 contract `fit_line`; `fit_line_f32` to measure the distance to TF's float32)."""
+    fit = fit or fit_line
     road = np.asarray(road)
     left, right = road_marginals(road)
-    l0, l1 = fit_line(left)
-    r0, r1 = fit_line(right)
+    l0, l1 = fit(left)
+    r0, r1 = fit(right)
     y = np.arange(road.shape[0], dtype=F32)
     pred_left = y * l0 + l1
     pred_right = y * r0 + r1

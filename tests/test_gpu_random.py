@@ -66,10 +66,15 @@ def test_random_configuration_matches_c_oracle(seed):
     want = co.full_path(loc, cls, fmaps, head, cfgp, (H, W), (c["PH"], c["PW"]), crop_size=c["crop"],
                         padding=c["padding"], binary=True, **c["kw"])
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    for fused in (True, False):
+    # fused / staged chain, then the round-2 variants of the fused tail: background fill on a second stream
+    # (prefill; silently off for widths the vector paste cannot take) and the planar mask-head layout
+    for fused, prefill, planar in ((True, False, False), (False, False, False), (True, True, False),
+                                   (True, False, True), (True, True, True)):
         cfg = ml.DetectionConfig(crop_size=c["crop"], mask_size=c["mask"], padding=c["padding"],
-                                 fused=fused, **c["kw"])
+                                 fused=fused, prefill=prefill, mask_layout="planar" if planar else "interleaved",
+                                 **c["kw"])
         pipe = ml.PostProcessPipeline(cfgp, (H, W), (c["PH"], c["PW"]), C, Cf, B, cfg)
+        pipe.pasted.fill_(7)                                           # stale bytes the paste (or the fill) has to clear
         rois = pipe.detect_and_align(d(loc), d(cls), [d(f) for f in fmaps])
         crops, roi_boxes = pipe.roi_views(rois)
         M = int(rois.m_dev.item())
@@ -77,10 +82,11 @@ def test_random_configuration_matches_c_oracle(seed):
         assert np.array_equal(roi_boxes.cpu().numpy(), want["roi_boxes"]), (seed, fused, c)
         for g, w in zip(crops, want["roi_fmaps"]):
             assert np.array_equal(g.cpu().numpy(), w), (seed, fused, c)
-        pipe.trim_and_paste(rois, d(probs["m"]))
+        masks = probs["m"].transpose(0, 1, 4, 2, 3) if planar else probs["m"]
+        pipe.trim_and_paste(rois, d(masks))
         det_i, pasted = pipe.result_views()
-        assert np.array_equal(det_i.cpu().numpy(), want["det_i"]), (seed, fused, c)
-        assert np.array_equal(pasted.cpu().numpy(), want["binary"]), (seed, fused, c)
+        assert np.array_equal(det_i.cpu().numpy(), want["det_i"]), (seed, fused, prefill, planar, c)
+        assert np.array_equal(pasted.cpu().numpy(), want["binary"]), (seed, fused, prefill, planar, c)
 
 
 def test_negative_and_nonfinite_scores_are_handled():
