@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--input-sets", type=int, default=3,
                     help="distinct input sets per stream, rotated step by step: no tensor is read by two batches in "
                          "flight and none is re-read before everything else has passed through L2")
-    ap.add_argument("--prefill", type=int, default=1,
+    ap.add_argument("--prefill", type=int, default=0,
                     help="1: CropAndPadMask's zero background is streamed out on a second stream from the moment "
                          "NMS has produced M (mlp_paste_prefill), the paste kernel writes the boxes only")
     ap.add_argument("--no-e2e", action="store_true")

@@ -282,17 +282,22 @@ int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const float* roi_ma
  *   second stream beside mlp_roi_align_run / the mask head on the first.
  * mlp_paste_prefill: CropAndPadMask's background ahead of time.  97 % of the [B,M,PH,PW] output is
  *   zeros that depend on M only (engine/layers/misc.py:393-399 pads every resized mask to the frame);
- *   this zeroes that prefix of out_dev with M = max(1, max_b counts_dev[b]) read on the device
- *   (misc.py:235-236).  Join the stream before mlp_trim_paste(.., out_mode | MLP_PASTE_PREFILLED, ..),
- *   which then writes only the 16-byte segments that intersect a box.  frame_w must be a multiple of
- *   the store width (16 uint8 / 4 float32 / 128 bit-packed pixels).                              */
+ *   this zeroes instance rows [m_from, m_to) of out_dev's flat prefix: m_to = max(1, max_b counts_dev[b])
+ *   (misc.py:235-236) when counts_dev is given, else *m_to_dev; m_from = *m_from_dev (0 when NULL); all
+ *   read on the device.  Zeroing a longer prefix than the final M needs is wasted work, never wrong, so a
+ *   first call may run BEFORE the NMS kernels with m_to_dev = the M of the previous batch and a second one
+ *   after them completes [that M, this batch's M).  Join the stream before
+ *   mlp_trim_paste(.., out_mode | MLP_PASTE_PREFILLED, ..), which then writes only the 16-byte segments
+ *   that intersect a box.  frame_w must be a multiple of the store width (16 uint8 / 4 float32 / 128
+ *   bit-packed pixels).                                                                          */
 int mlp_detect_plan(mlp_ctx* ctx, const mlp_prior_config* prior, const float* loc_dev,
                     const float* cls_dev, int batch, int height, int width, int num_classes,
                     const mlp_detection_params* params, int max_k, float base_size, float* det_dev,
                     int32_t* keep_dev, int32_t* counts_dev, int32_t* m_dev, float* dist_dev,
                     int32_t* level_counts_dev, int32_t* level_m_dev, mlp_stream_t stream);
-int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* counts_dev, int batch, int k_rows, int frame_h,
-                      int frame_w, int out_mode, void* out_dev, mlp_stream_t stream);
+int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* m_from_dev, const int32_t* counts_dev,
+                      const int32_t* m_to_dev, int batch, int k_rows, int frame_h, int frame_w, int out_mode,
+                      void* out_dev, mlp_stream_t stream);
 
 /* ---- a8: MoldBatch.call (engine/layers/misc.py:231-286) as a standalone operator ----
  * x_dev [K,row_elems] of 4-byte elements, batch_idx_dev i32 [K] (image id of each row).

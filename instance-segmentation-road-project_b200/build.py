@@ -66,5 +66,17 @@ def build_library(force=False, verbose=False, out=None, extra=()):
     return out
 
 
+DEBUG_LIB_PATH = os.path.join(HERE, "libmasklab_b200_dbg.so")
+
+
+def build_debug_bounds(verbose=False):
+    """The same sources with -DMLP_DEBUG_BOUNDS (common.cuh): every checked scratch / shared-memory index traps
+    with its source line when it leaves its extent.  Select it with MASKLAB_B200_LIB=<this path>."""
+    return build_library(force=True, verbose=verbose, out=DEBUG_LIB_PATH, extra=["-DMLP_DEBUG_BOUNDS"])
+
+
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug-bounds" in sys.argv:
+        print(build_debug_bounds(verbose="-v" in sys.argv))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

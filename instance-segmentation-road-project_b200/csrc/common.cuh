@@ -133,6 +133,24 @@ struct DeviceGuard {
     }
 };
 
+// ---- debug build: bounds checks on scratch / shared-memory indices ------------------------------
+// compute-sanitizer is closed on this GPU pool, so memory safety is checked by other means: building with
+// -DMLP_DEBUG_BOUNDS (python -m masklab_b200.build --debug-bounds -> libmasklab_b200_dbg.so) turns every
+// MLP_BOUND(index, extent) into a test that prints the site and traps; the small-shape GPU tests are then
+// run against that library (MASKLAB_B200_LIB=..., tools/run_debug_bounds.sh).  Release builds compile it away.
+#ifdef MLP_DEBUG_BOUNDS
+#define MLP_BOUND(i, n)                                                                                   \
+    do {                                                                                                  \
+        if (!((long long)(i) >= 0 && (long long)(i) < (long long)(n))) {                                  \
+            printf("MLP_BOUND violated at %s:%d: index %lld not in [0,%lld)\n", __FILE__, __LINE__,       \
+                   (long long)(i), (long long)(n));                                                       \
+            __trap();                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#else
+#define MLP_BOUND(i, n) do { } while (0)
+#endif
+
 // ------------------------------------------------------- device helpers ------
 // Streaming 128-bit global accesses: read-once inputs bypass L1, write-once
 // outputs do not allocate in L1 (guideline 13/14 of the Blackwell playbook).

@@ -92,6 +92,7 @@ __device__ __forceinline__ void k1_append(uint32_t e, float s, int N, int C, uin
     const uint32_t n = bn - b * (uint32_t)N;
     const int g = (int)b * C + c;
     const int pos = atomicAdd(cand_count + g, 1);
+    MLP_BOUND(n, N);
     if (pos < cap) cand_keys[(int64_t)g * cap + pos] = make_key(s, n);
 }
 
@@ -253,25 +254,32 @@ __device__ void bitonic_sort_smem(uint64_t* s, int n_pow2) {
 __device__ void bitonic_sort_reg(uint64_t* s, int n_pow2) {
     const int t = threadIdx.x;
     const bool in = t < n_pow2;
-    uint64_t v = in ? s[t] : kKeyPad;
+    const uint64_t v0 = in ? s[t] : kKeyPad;
+    uint32_t hi = (uint32_t)(v0 >> 32), lo = (uint32_t)v0;     // two 32-bit halves: shuffles and selects are 32-bit
     for (int k = 2; k <= n_pow2; k <<= 1) {
+        const bool asc = (t & k) == 0;
         for (int j = k >> 1; j > 0; j >>= 1) {
-            uint64_t o;
+            uint32_t ohi, olo;
             if (j >= 32) {
                 __syncthreads();                       // partners have read the previous exchange
-                if (in) s[t] = v;
+                if (in) s[t] = ((uint64_t)hi << 32) | lo;
                 __syncthreads();
-                o = in ? s[t ^ j] : kKeyPad;
+                const uint64_t o = in ? s[t ^ j] : kKeyPad;
+                ohi = (uint32_t)(o >> 32); olo = (uint32_t)o;
             } else {
-                o = __shfl_xor_sync(0xffffffffu, (unsigned long long)v, j);
+                ohi = __shfl_xor_sync(0xffffffffu, hi, j);
+                olo = __shfl_xor_sync(0xffffffffu, lo, j);
             }
-            const bool take_min = ((t & k) == 0) == ((t & j) == 0);
-            const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
-            v = take_min ? mn : mx;
+            // the lower index of a pair keeps the minimum in an ascending run, the maximum in a descending one
+            const bool take_min = asc == ((t & j) == 0);
+            const bool lt = hi < ohi || (hi == ohi && lo < olo);
+            const bool keep = lt == take_min;          // keys are unique: never equal
+            hi = keep ? hi : ohi;
+            lo = keep ? lo : olo;
         }
     }
     __syncthreads();
-    if (in) s[t] = v;
+    if (in) s[t] = ((uint64_t)hi << 32) | lo;
     __syncthreads();
 }
 
@@ -317,8 +325,8 @@ struct NmsSmem {
     float4* k_crn; float* k_area;   // [max_out] kept boxes (ymin,xmin,ymax,xmax) + area: one LDS.128 + one LDS.32 per test
     float4* c_crn; float* c_area;   // [kBlock]  candidates of the current block (chunks index into it)
     float4* c_box;          // [kBlock] cx,cy,w,h of the block's candidates
-    uint32_t* c_mask;       // [kChunk][kMaskWords]
-    int* c_supp;            // [kChunk]
+    uint32_t* c_mask;       // [2][kChunk][kMaskWords]  (double-buffered per chunk)
+    int* c_supp;            // [2][kChunk]
     uint32_t* keptw;        // [kMaskWords]
     int* hist;              // [256]
     unsigned long long* bcast;   // [2]
@@ -331,8 +339,8 @@ __host__ __device__ inline size_t nms_smem_bytes(int sort_cap, int max_out) {
     b += (size_t)max_out * 4 * 5;
     b += (size_t)kBlock * 4 * 5;
     b += (size_t)kBlock * 16;
-    b += (size_t)kChunk * kMaskWords * 4;
-    b += (size_t)kChunk * 4;
+    b += (size_t)2 * kChunk * kMaskWords * 4;
+    b += (size_t)2 * kChunk * 4;
     b += kMaskWords * 4;
     b += 256 * 4;
     b += 2 * 8;
@@ -350,8 +358,8 @@ __device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_
     S.c_crn = reinterpret_cast<float4*>(p); p += (size_t)kBlock * 16;
     S.k_area = reinterpret_cast<float*>(p); p += (size_t)max_out * 4;
     S.c_area = reinterpret_cast<float*>(p); p += kBlock * 4;
-    S.c_mask = reinterpret_cast<uint32_t*>(p); p += (size_t)kChunk * kMaskWords * 4;
-    S.c_supp = reinterpret_cast<int*>(p); p += kChunk * 4;
+    S.c_mask = reinterpret_cast<uint32_t*>(p); p += (size_t)2 * kChunk * kMaskWords * 4;
+    S.c_supp = reinterpret_cast<int*>(p); p += 2 * kChunk * 4;
     S.keptw = reinterpret_cast<uint32_t*>(p); p += kMaskWords * 4;
     S.hist = reinterpret_cast<int*>(p); p += 256 * 4;
     S.misc = reinterpret_cast<int*>(p); p += 16;
@@ -370,7 +378,9 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
     static_assert(kThreads % kChunk == 0 && kChunk % kLanesPerCand == 0 && kChunk == 64, "bad NMS geometry");
     const int tid = threadIdx.x;
     if (tid == 0) S.misc[0] = 0;
+    if (tid < 2 * kChunk) { S.c_supp[tid] = 0; S.c_mask[tid * 2] = 0u; S.c_mask[tid * 2 + 1] = 0u; }
     __syncthreads();
+    int buf = 0;                     // which half of c_supp / c_mask the current chunk uses
     int kept = 0;
     int done = 0;                    // keys consumed so far (in sorted order)
     uint64_t lo = 0;                 // largest key consumed so far
@@ -413,64 +423,62 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
             const int pn = (sc - pb) < kBlock ? (sc - pb) : kBlock;
             __syncthreads();                          // previous block's chunks are done with c_*
             for (int i = tid; i < pn; i += blockDim.x) {
+                MLP_BOUND(pb + i, sort_cap);
                 const float4 bx = fetch((uint32_t)S.skeys[pb + i]);
                 const BoxC c = corners_of(bx);
                 S.c_box[i] = bx;
                 S.c_crn[i] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
                 S.c_area[i] = c.area;
             }
-            // ---- chunks of kChunk (= 64) candidates ----
+            __syncthreads();                          // c_* of this block are in shared memory
+            // ---- chunks of kChunk (= 64) candidates, two barriers each ----
+            // phase 1 (all threads): candidate t against the kept list (its slice r of it) AND against the
+            //   earlier candidates of the chunk - the two do not depend on each other: a mask bit that
+            //   points at a candidate which turns out dead is never looked at by the resolve.
+            // phase 2: warp 0 resolves the chunk sequentially out of registers and appends the newly kept
+            //   boxes; two other warps clear the other half of c_supp / c_mask for the next chunk.
             for (int base = 0; base < pn && kept < max_out; base += kChunk) {
                 const int m = (pn - base) < kChunk ? (pn - base) : kChunk;
-                if (tid < kChunk) {
-                    S.c_supp[tid] = tid < m ? 0 : 1;
-                    S.c_mask[tid * 2] = 0u;
-                    S.c_mask[tid * 2 + 1] = 0u;
-                }
-                __syncthreads();
+                int* c_supp = S.c_supp + buf * kChunk;
+                uint32_t* c_mask = S.c_mask + buf * kChunk * kMaskWords;
                 const int t = tid % kChunk, r = tid / kChunk;
-                const float4 tc = S.c_crn[base + (t < m ? t : 0)];
-                const float tymin = tc.x, txmin = tc.y, tymax = tc.z, txmax = tc.w;
-                const float tarea = S.c_area[base + (t < m ? t : 0)];
-                // (b) against the kept list, split over kLanesPerCand threads per candidate
                 if (t < m) {
+                    const float4 tc = S.c_crn[base + t];
+                    const float tymin = tc.x, txmin = tc.y, tymax = tc.z, txmax = tc.w;
+                    const float tarea = S.c_area[base + t];
                     for (int j = r; j < kept; j += kLanesPerCand) {
                         const float4 kc = S.k_crn[j];
                         if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, kc.x, kc.y, kc.z, kc.w, S.k_area[j],
                                         thr)) {
-                            S.c_supp[t] = 1;
+                            c_supp[t] = 1;
                             break;
                         }
                     }
-                }
-                __syncthreads();
-                // (c) intra-chunk mask: bit u of row t set iff u < t, u alive, IoU(t,u) > thr
-                if (t < m && S.c_supp[t] == 0) {
+                    // bit u of row t set iff u < t and IoU(t,u) > thr
                     constexpr int kSlice = kChunk / kLanesPerCand;
                     const int u0 = r * kSlice;
                     const int u1 = (u0 + kSlice < t) ? (u0 + kSlice) : t;
                     uint32_t lo = 0, hi = 0;
                     for (int u = u0; u < u1; ++u) {
                         const float4 uc = S.c_crn[base + u];
-                        if (S.c_supp[u] == 0 &&
-                            iou_exceeds(tymin, txmin, tymax, txmax, tarea, uc.x, uc.y, uc.z, uc.w,
+                        if (iou_exceeds(tymin, txmin, tymax, txmax, tarea, uc.x, uc.y, uc.z, uc.w,
                                         S.c_area[base + u], thr)) {
                             if (u < 32) lo |= 1u << u; else hi |= 1u << (u - 32);
                         }
                     }
-                    if (lo) atomicOr(&S.c_mask[t * 2], lo);
-                    if (hi) atomicOr(&S.c_mask[t * 2 + 1], hi);
+                    if (lo) atomicOr(&c_mask[t * 2], lo);
+                    if (hi) atomicOr(&c_mask[t * 2 + 1], hi);
                 }
                 __syncthreads();
-                // (d) sequential resolve by warp 0.  Rows live in registers (lane l: candidates l
-                // and l+32) and reach every lane by shuffle, so the loop-carried chain is two ANDs,
-                // a compare and an OR per candidate - no shared-memory latency on it.
                 if (tid < 32) {
-                    const uint32_t alive_lo = __ballot_sync(0xffffffffu, S.c_supp[tid] == 0);
-                    const uint32_t alive_hi = __ballot_sync(0xffffffffu, S.c_supp[tid + 32] == 0);
-                    const uint32_t rowA_lo = S.c_mask[tid * 2];
-                    const uint32_t rowB_lo = S.c_mask[(tid + 32) * 2];
-                    const uint32_t rowB_hi = S.c_mask[(tid + 32) * 2 + 1];
+                    // sequential resolve.  Rows live in registers (lane l: candidates l and l+32) and reach
+                    // every lane by shuffle, so the loop-carried chain is two ANDs, a compare and an OR per
+                    // candidate - no shared-memory latency on it.
+                    const uint32_t alive_lo = __ballot_sync(0xffffffffu, tid < m && c_supp[tid] == 0);
+                    const uint32_t alive_hi = __ballot_sync(0xffffffffu, tid + 32 < m && c_supp[tid + 32] == 0);
+                    const uint32_t rowA_lo = c_mask[tid * 2];
+                    const uint32_t rowB_lo = c_mask[(tid + 32) * 2];
+                    const uint32_t rowB_hi = c_mask[(tid + 32) * 2 + 1];
                     uint32_t kept_lo = 0, kept_hi = 0;
                     int k = kept;
 #pragma unroll
@@ -487,23 +495,30 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                                           (k < max_out);
                         if (keep) { kept_hi |= 1u << q; ++k; }
                     }
-                    if (tid == 0) { S.keptw[0] = kept_lo; S.keptw[1] = kept_hi; S.misc[0] = k; }
-                }
-                __syncthreads();
-                // (e) append newly kept boxes in order and emit them
-                if (tid < m) {
-                    const uint32_t w0 = S.keptw[0], w1 = S.keptw[1];
-                    const uint32_t wv = (tid < 32) ? w0 : w1;
-                    if ((wv >> (tid & 31)) & 1u) {
-                        int rank = kept + ((tid < 32) ? 0 : __popc(w0));
-                        rank += __popc(wv & ((1u << (tid & 31)) - 1u));
-                        S.k_crn[rank] = S.c_crn[base + tid];
-                        S.k_area[rank] = S.c_area[base + tid];
-                        emit(rank, S.skeys[pb + base + tid], S.c_box[base + tid]);
+                    if (tid == 0) S.misc[0] = k;
+                    // append the newly kept boxes in order and emit them (lane l: candidates l and l+32)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t wv = h ? kept_hi : kept_lo;
+                        if ((wv >> tid) & 1u) {
+                            const int cand = tid + 32 * h;
+                            const int rank = kept + (h ? __popc(kept_lo) : 0) + __popc(wv & ((1u << tid) - 1u));
+                            MLP_BOUND(rank, max_out);
+                            MLP_BOUND(base + cand, kBlock);
+                            S.k_crn[rank] = S.c_crn[base + cand];
+                            S.k_area[rank] = S.c_area[base + cand];
+                            emit(rank, S.skeys[pb + base + cand], S.c_box[base + cand]);
+                        }
                     }
+                } else if (tid < 32 + kChunk) {
+                    const int i = tid - 32;            // clear the other half for the next chunk
+                    S.c_supp[(buf ^ 1) * kChunk + i] = 0;
+                    S.c_mask[((buf ^ 1) * kChunk + i) * 2] = 0u;
+                    S.c_mask[((buf ^ 1) * kChunk + i) * 2 + 1] = 0u;
                 }
-                kept = S.misc[0];
                 __syncthreads();
+                kept = S.misc[0];
+                buf ^= 1;
             }
         }
     }
@@ -518,7 +533,10 @@ struct FetchBoxes {
 struct FetchDecode {
     const PriorDev* P;
     const float4* loc;       // [N] of this image
-    __device__ float4 operator()(uint32_t n) const { return restore_box(loc[n], prior_anchor(*P, (int)n)); }
+    __device__ float4 operator()(uint32_t n) const {
+        MLP_BOUND(n, P->total);
+        return restore_box(loc[n], prior_anchor(*P, (int)n));
+    }
 };
 
 struct DetScratch {
@@ -653,6 +671,8 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         while (gi + 1 < ng && p >= s_off[gi + 1]) ++gi;
         const int c = s_order[gi];
         const int64_t src = (int64_t)(b * C + c) * max_out + (p - s_off[gi]);
+        MLP_BOUND(p, C * max_out);
+        MLP_BOUND(p - s_off[gi], max_out);
         const float4 bx = D.rec_box[src];
         const int2 sn = D.rec_sn[src];
         cat_box[p] = bx;
@@ -667,6 +687,8 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     int32_t* keep_b = keep ? keep + (int64_t)b * max_out * 2 : nullptr;
     auto emit = [&](int rank, uint64_t key, const float4& bx) {
         const uint32_t p = (uint32_t)key;
+        MLP_BOUND(p, C * max_out);
+        MLP_BOUND(rank, max_out);
         const int2 sn = cat_sn[p];
         const int c = cat_c[p];
         float* o = det_b + rank * 6;
@@ -718,7 +740,10 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
             const int r = r0 + lane;
             const bool hit = (r < kept) && (s_lvl[r] == f);
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (hit) src[base + __popc(mask & ((1u << lane) - 1u))] = r;
+            if (hit) {
+                MLP_BOUND(base + __popc(mask & ((1u << lane) - 1u)), max_out);
+                src[base + __popc(mask & ((1u << lane) - 1u))] = r;
+            }
             base += __popc(mask);
         }
         if (lane == 0) {

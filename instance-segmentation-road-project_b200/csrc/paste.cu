@@ -23,41 +23,38 @@ constexpr int kTileRegs = 4;              // tile elements prefetched per thread
 // dynamic shared memory of the vector paste kernels: the mask tile as floats, then the column table
 __host__ __device__ inline int paste_tile_bytes(int px) { return (px * 4 + 15) & ~15; }
 inline size_t paste_smem_bytes(int mask_h, int mask_w, int frame_w) {
-    return (size_t)paste_tile_bytes(mask_h * mask_w) + (size_t)(frame_w < kMaxCols ? frame_w : kMaxCols) * sizeof(uint2);
+    (void)frame_w;
+    return (size_t)paste_tile_bytes(mask_h * mask_w) + (size_t)kMaxCols * sizeof(uint2);
 }
 
-// One 16-byte output segment (kVec pixels starting at x0) of frame row oy of an instance: the reference's
-// two-stage lerp from the mask tile in shared memory, > 0.5 fused for the binary modes.  s_col: the box's
-// column table (paste_fill_cols) or NULL for boxes wider than kMaxCols.
-template <int kMode>
-__device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile, const uint2* __restrict__ s_col,
-                                               const PasteGeom& g, int mh, int mw, int oy, int x0) {
+// One 16-byte output segment (kVec pixels starting at x0 = seg * kVec) of frame row oy of an instance: the
+// reference's two-stage lerp from the mask tile in shared memory, > 0.5 fused for the binary modes.
+// kCols: x terms from the box's column table (paste_fill_cols; col points at entry (q = 0, this segment),
+// pitch = segments per box row); otherwise computed per pixel (boxes wider than the table).
+template <int kMode, bool kCols>
+__device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile, const uint2* __restrict__ col,
+                                               int pitch, const PasteGeom& g, int mh, int mw, int oy, int x0) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
     const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
     const float fl = floorf(p);
     const int ylo = max((int)fl, 0);
     const int yhi = min((int)ceilf(p), mh - 1);
     const float ly = __fsub_rn(p, fl);
-    const float* row_lo = s_tile + ylo * mw;
-    const float* row_hi = s_tile + yhi * mw;
+    const unsigned char* row_lo = reinterpret_cast<const unsigned char*>(s_tile + ylo * mw);
+    const unsigned char* row_hi = reinterpret_cast<const unsigned char*>(s_tile + yhi * mw);
     const int q0 = max(g.xmin - x0, 0), q1 = min(g.xmax - x0, kVec);       // pixels of the segment inside the box
-    const uint2* col = s_col ? s_col + (x0 - g.xmin) : nullptr;
     auto value = [&](int q) -> float {
-        return col ? paste_value_cols(row_lo, row_hi, ly, col[q])
-                   : paste_value(s_tile, mh, mw, ylo, yhi, ly, x0 + q - g.xmin, g.sx);
+        if (kCols) return paste_value_cols(row_lo, row_hi, ly, col[q * pitch]);
+        return paste_value(s_tile, mh, mw, ylo, yhi, ly, x0 + q - g.xmin, g.sx);
     };
     uint4 v;
     if (kMode == MLP_PASTE_U8) {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (q0 == 0 && q1 == 16) {                                        // interior segment: no bounds tests
+        // one loop for interior and edge segments alike: a warp holds both kinds, and two code paths would
+        // be executed one after the other by every warp (measured: 1.65x the pixel evaluations)
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (value(q) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q >= q0 && q < q1 && value(q) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
-        }
+        for (int q = 0; q < 16; ++q)
+            if (q >= q0 && q < q1 && value(q) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
         v = make_uint4(w[0], w[1], w[2], w[3]);
     } else if (kMode == MLP_PASTE_BITS) {
         // bit k of byte i = pixel 8*i + k  (numpy packbits, bitorder='little')
@@ -76,6 +73,28 @@ __device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile,
     return v;
 }
 
+// All segments [0, nb) of `nrows` box rows starting at frame row y_first, flattened over the CTA.
+template <int kMode>
+__device__ __forceinline__ void paste_box_rows(const float* __restrict__ s_tile, const uint2* __restrict__ s_col,
+                                               bool cols, const PasteGeom& g, int mh, int mw, int y_first, int nrows,
+                                               int sL, int bw, uint4* __restrict__ rows_out, int spr, int tid) {
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
+    const int nb = nrows * bw;
+    if (cols) {
+        for (int i = tid; i < nb; i += kPasteThreads) {
+            const int r = i / bw, s = i - r * bw;
+            const uint4 v = paste_segment<kMode, true>(s_tile, s_col + s, bw, g, mh, mw, y_first + r, (sL + s) * kVec);
+            stg_stream_u4(rows_out + (int64_t)r * spr + sL + s, v);
+        }
+    } else {
+        for (int i = tid; i < nb; i += kPasteThreads) {
+            const int r = i / bw, s = i - r * bw;
+            const uint4 v = paste_segment<kMode, false>(s_tile, nullptr, 0, g, mh, mw, y_first + r, (sL + s) * kVec);
+            stg_stream_u4(rows_out + (int64_t)r * spr + sL + s, v);
+        }
+    }
+}
+
 // One CTA per (instance, band) item, NOT a persistent grid: on B200 a write-only stream of many
 // short-lived CTAs, each owning one contiguous 64 KB band, reaches ~7.4 TB/s while persistent
 // CTAs top out near 6.3 TB/s (tools/write_bw.cu, profiles/write_bw_r01.txt).  The grid is sized
@@ -89,7 +108,7 @@ __device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile,
 template <int kMode>       // MLP_PASTE_F32 / MLP_PASTE_U8 / MLP_PASTE_BITS
 __global__ void __launch_bounds__(kPasteThreads)
 paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
-             int mw, int PH, int PW, int band_rows, void* __restrict__ out) {
+             int mw, int PH, int PW, int band_rows, int use_cols, void* __restrict__ out) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);   // pixels per 16-byte store
     extern __shared__ __align__(16) unsigned char s_dyn[];           // [tile floats][column table], paste_smem_bytes
     float* s_tile = reinterpret_cast<float*>(s_dyn);
@@ -167,8 +186,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         }
         for (int i = tid + kTileRegs * kPasteThreads; i < px; i += kPasteThreads)
             s_tile[i] = (float)tref.at(i);
-        paste_fill_cols(s_col_buf, g, mw, tid, kPasteThreads);
-        const uint2* s_col = (g.xmax - g.xmin <= kMaxCols) ? s_col_buf : nullptr;
+        const bool cols = use_cols && paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
         const int sL = g.xmin / kVec;                       // first segment touching the box
         const int sR = (g.xmax + kVec - 1) / kVec;          // one past the last
         const int bw = sR - sL;
@@ -181,15 +199,9 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
                 for (int k = lane; k < nz; k += 32) stg_stream_u4(rp + (k < sL ? k : k + bw), zero4);
             }
         }
-        __syncthreads();                           // s_tile ready
+        __syncthreads();                           // s_tile / column table ready
         // ---- phase B2: segments intersecting the box, flattened over the CTA
-        const int nb = (yb - ya) * bw;
-        for (int i = tid; i < nb; i += kPasteThreads) {
-            const int r = i / bw;
-            const int seg = sL + (i - r * bw);
-            const uint4 v = paste_segment<kMode>(s_tile, s_col, g, mh, mw, ya + r, seg * kVec);
-            stg_stream_u4(box_rows + (int64_t)r * spr + seg, v);
-        }
+        paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, ya, yb - ya, sL, bw, box_rows, spr, tid);
     }
 }
 
@@ -313,16 +325,29 @@ constexpr int kPrepParts = 8;             // minimum CTAs per image (each repeat
 constexpr int kFillThreads = 256;
 constexpr int kFillVecs = 4096;           // uint4 per CTA = 64 KB
 
+// Fills the instance rows [m_from, m_to) of every image's slab, i.e. the flat range
+// [B * m_from * inst_vecs, B * m_to * inst_vecs): m_from = *m_from_dev (0 when NULL); m_to = max(1, max counts)
+// when counts is given, else *m_to_dev; both clamped to the capacity m_rows.
 __global__ void __launch_bounds__(kFillThreads)
-paste_fill_kernel(const int32_t* __restrict__ counts, int B, int m_rows, int64_t inst_vecs,
+paste_fill_kernel(const int32_t* __restrict__ m_from_dev, const int32_t* __restrict__ counts,
+                  const int32_t* __restrict__ m_to_dev, int B, int m_rows, int64_t inst_vecs,
                   uint4* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    int mx = 0;
-    for (int i = lane; i < B; i += 32) mx = max(mx, counts[i]);
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const int M = min(max(mx, 1), m_rows);
-    const int64_t total = (int64_t)B * M * inst_vecs;
-    const int64_t start = (int64_t)blockIdx.x * kFillVecs;
+    int m_to;
+    if (counts) {
+        int mx = 0;
+        for (int i = lane; i < B; i += 32) mx = max(mx, counts[i]);
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        m_to = max(mx, 1);
+    } else {
+        m_to = *m_to_dev;
+    }
+    m_to = min(max(m_to, 0), m_rows);
+    const int m_from = m_from_dev ? min(max(*m_from_dev, 0), m_rows) : 0;
+    if (m_from >= m_to) return;
+    const int64_t first = (int64_t)B * m_from * inst_vecs;
+    const int64_t total = (int64_t)B * m_to * inst_vecs;
+    const int64_t start = first + (int64_t)blockIdx.x * kFillVecs;
     if (start >= total) return;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint4* p = out + start;
@@ -443,6 +468,8 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
     const int es = planar ? 1 : C;
     for (int s = part + parts * warp; s < total; s += parts * kWarps) {
         const int j = src[s];
+        MLP_BOUND(j, R);
+        MLP_BOUND(s, K);
         const int cls = drows[s * 6 + 4];
         uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
         if (cls < 0 || cls >= C) {                           // tf.gather_nd would raise: all-zero tile
@@ -548,6 +575,8 @@ paste_boxes_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int
         const uint2 q = __ldg(items + it);
         const int b = (int)q.x / K, j = (int)q.x - b * K;
         const int y0 = (int)(q.y >> 16), nrows = (int)(q.y & 0xffffu);
+        MLP_BOUND(b, B);
+        MLP_BOUND(y0 + nrows - 1, PH);
         int row[6];
         {
             const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * K + j) * 6);
@@ -559,19 +588,12 @@ paste_boxes_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int
         const TileRef tref = tile_ref(S, b, j, K, px, row[4], mh, mw);
         __syncthreads();                                    // previous item done with s_tile / s_col
         tref.fill(s_tile, mh, tid, kPasteThreads);
-        paste_fill_cols(s_col_buf, g, mw, tid, kPasteThreads);
-        const uint2* s_col = (g.xmax - g.xmin <= kMaxCols) ? s_col_buf : nullptr;
+        const bool cols = paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
         __syncthreads();
         const int sL = g.xmin / kVec;
         const int bw = (g.xmax + kVec - 1) / kVec - sL;
         uint4* rows_out = reinterpret_cast<uint4*>(out) + (((int64_t)b * M + j) * PH + y0) * spr;
-        const int nb = nrows * bw;
-        for (int i = tid; i < nb; i += kPasteThreads) {
-            const int r = i / bw;
-            const int seg = sL + (i - r * bw);
-            const uint4 v = paste_segment<kMode>(s_tile, s_col, g, mh, mw, y0 + r, seg * kVec);
-            stg_stream_u4(rows_out + (int64_t)r * spr + seg, v);
-        }
+        paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, y0, nrows, sL, bw, rows_out, spr, tid);
     }
 }
 
@@ -606,9 +628,11 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
         int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
         if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
         const size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
+        int use_cols = 1;
+        if (const char* e = getenv("MLP_PASTE_COLS")) use_cols = atoi(e);
 #define MLP_PASTE_LAUNCH(MODE)                                                                         \
     paste_kernel<MODE><<<grid, kPasteThreads, smem, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
-                                                      mask_w, frame_h, frame_w, band_rows, out_dev)
+                                                      mask_w, frame_h, frame_w, band_rows, use_cols, out_dev)
         if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
         else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
         else MLP_PASTE_LAUNCH(MLP_PASTE_F32);
@@ -767,13 +791,18 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
                         out_mode, out_dev, st, prefilled ? &Q : nullptr);
 }
 
-// Background of CropAndPadMask, ahead of time: zero the [B,M,PH,PW] prefix of out_dev with M taken from
-// the detection counts (M = max(1, max_b counts_b), engine/layers/misc.py:235-236).  Enqueue it on a
-// stream that runs beside RoIAlign / the mask head, join, then call mlp_trim_paste with
-// MLP_PASTE_PREFILLED.  TrimInstances can only drop rows, so the M of the tail never exceeds this one.
-extern "C" int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* counts_dev, int batch, int k_rows, int frame_h,
-                                 int frame_w, int out_mode, void* out_dev, mlp_stream_t stream) {
-    MLP_CHECK_ARG(ctx && counts_dev && out_dev, "mlp_paste_prefill: NULL argument");
+// Background of CropAndPadMask, ahead of time: zero instance rows [m_from, m_to) of out_dev's flat [B,M,PH,PW]
+// prefix.  m_to = max(1, max_b counts_dev[b]) (misc.py:235-236) when counts_dev is given, else *m_to_dev;
+// m_from = *m_from_dev, 0 when NULL.  Two calls make the overlapped fill of PostProcessPipeline: a SPECULATIVE one
+// before the NMS kernels with m_to_dev = the M of the previous batch (any prefix of the output is background
+// or box, so zeroing too much of it is only wasted work, never wrong), and a completing one after them with
+// m_from_dev = that same scalar and counts_dev = this batch's counts.  Join the stream, then call
+// mlp_trim_paste with MLP_PASTE_PREFILLED.  TrimInstances can only drop rows, so the M of the tail never
+// exceeds the one reduced from the detection counts.
+extern "C" int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* m_from_dev, const int32_t* counts_dev,
+                                 const int32_t* m_to_dev, int batch, int k_rows, int frame_h, int frame_w,
+                                 int out_mode, void* out_dev, mlp_stream_t stream) {
+    MLP_CHECK_ARG(ctx && out_dev && (counts_dev || m_to_dev), "mlp_paste_prefill: NULL argument");
     MLP_CHECK_ARG(batch >= 1 && k_rows >= 1 && frame_h >= 1 && frame_w >= 1, "mlp_paste_prefill: bad shape");
     MLP_CHECK_ARG(out_mode == MLP_PASTE_F32 || out_mode == MLP_PASTE_U8 || out_mode == MLP_PASTE_BITS,
                   "mlp_paste_prefill: unknown out_mode %d", out_mode);
@@ -786,8 +815,8 @@ extern "C" int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* counts_dev, int ba
     const int64_t inst_vecs = (int64_t)frame_h * (frame_w / vec);
     const int64_t ctas = ((int64_t)batch * k_rows * inst_vecs + kFillVecs - 1) / kFillVecs;
     MLP_CHECK_ARG(ctas < (1ll << 31), "mlp_paste_prefill: output too large");
-    paste_fill_kernel<<<(unsigned)ctas, kFillThreads, 0, st>>>(counts_dev, batch, k_rows, inst_vecs,
-                                                             static_cast<uint4*>(out_dev));
+    paste_fill_kernel<<<(unsigned)ctas, kFillThreads, 0, st>>>(m_from_dev, counts_dev, m_to_dev, batch, k_rows,
+                                                             inst_vecs, static_cast<uint4*>(out_dev));
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }

@@ -77,29 +77,39 @@ __device__ __forceinline__ float paste_value(const float* __restrict__ tile, int
 // Column table of one box: the x half of the resize depends on the column only, so a CTA that is about to
 // evaluate many rows of a box computes (xlo, xhi, lx) once per column (same three rounded operations as
 // paste_value) and every pixel then costs one 8-byte shared load instead of a multiply, floor, ceil, two
-// conversions, a clamp pair and a subtract.  Entry: x = xlo | xhi << 16, y = bits of lx.
-constexpr int kMaxCols = 2048;            // wider boxes fall back to paste_value
+// conversions, a clamp pair and a subtract.  Entry: x = byte offsets xlo*4 | xhi*4 << 16, y = bits of lx.
+// Layout: the table covers the frame-aligned segments [sL, sL+bw) of the box; pixel q of segment s lives at
+// q * bw + (s - sL), so the lanes of a warp (consecutive segments, same q) read consecutive entries -
+// no bank conflicts (the natural [column] order would put them 16 entries = 128 bytes apart: 16-way).
+constexpr int kMaxCols = 2048;            // table entries; wider boxes fall back to paste_value
 
-__device__ __forceinline__ void paste_fill_cols(uint2* __restrict__ s_col, const PasteGeom& g, int mw, int tid,
+template <int kVec>
+__device__ __forceinline__ bool paste_fill_cols(uint2* __restrict__ s_col, const PasteGeom& g, int mw, int tid,
                                                 int nthreads) {
-    const int ow = g.xmax - g.xmin;
-    if (ow > kMaxCols) return;
-    for (int c = tid; c < ow; c += nthreads) {
+    const int sL = g.xmin / kVec;
+    const int bw = (g.xmax + kVec - 1) / kVec - sL;
+    const int n = bw * kVec;
+    if (n > kMaxCols) return false;
+    for (int i = tid; i < n; i += nthreads) {
+        const int q = i / bw, s = i - q * bw;
+        const int c = (sL + s) * kVec + q - g.xmin;          // box column of that pixel (outside the box: unused)
         const float p = __fmul_rn((float)c, g.sx);
         const float fl = floorf(p);
-        const int xlo = max((int)fl, 0);
-        const int xhi = min((int)ceilf(p), mw - 1);
-        s_col[c] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), __float_as_uint(__fsub_rn(p, fl)));
+        const int xlo = min(max((int)fl, 0), mw - 1);
+        const int xhi = min(max((int)ceilf(p), 0), mw - 1);
+        MLP_BOUND(i, kMaxCols);
+        s_col[i] = make_uint2((uint32_t)(xlo * 4) | ((uint32_t)(xhi * 4) << 16), __float_as_uint(__fsub_rn(p, fl)));
     }
+    return true;
 }
 
 // paste_value with the x terms from the column table; row_lo / row_hi point at tile rows ylo / yhi
-__device__ __forceinline__ float paste_value_cols(const float* __restrict__ row_lo, const float* __restrict__ row_hi,
-                                                  float ly, const uint2 e) {
-    const int xlo = (int)(e.x & 0xffffu), xhi = (int)(e.x >> 16);
+__device__ __forceinline__ float paste_value_cols(const unsigned char* __restrict__ row_lo,
+                                                  const unsigned char* __restrict__ row_hi, float ly, const uint2 e) {
+    const uint32_t xlo = e.x & 0xffffu, xhi = e.x >> 16;
     const float lx = __uint_as_float(e.y);
-    const float tl = row_lo[xlo], tr = row_lo[xhi];
-    const float bl = row_hi[xlo], br = row_hi[xhi];
+    const float tl = *reinterpret_cast<const float*>(row_lo + xlo), tr = *reinterpret_cast<const float*>(row_lo + xhi);
+    const float bl = *reinterpret_cast<const float*>(row_hi + xlo), br = *reinterpret_cast<const float*>(row_hi + xhi);
     const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
     const float b = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
     return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
@@ -170,7 +180,9 @@ __device__ __forceinline__ TileRef tile_ref(const PasteSrc& S, int b, int j, int
         return t;
     }
     const int R = S.r_dev ? *S.r_dev : S.r_rows;
+    MLP_BOUND(j, m_stride);
     const int jsrc = S.tail_src[(int64_t)b * m_stride + j];
+    MLP_BOUND(jsrc + 1, R + 1);
     t.valid = jsrc >= 0 && cls >= 0 && cls < S.C;
     if (S.tail_bits) t.bits = S.tail_bits + ((int64_t)b * m_stride + j) * mh;
     if (S.planar) t.mf = S.roi_masks + (t.valid ? (((int64_t)b * R + jsrc) * S.C + cls) * px : 0);

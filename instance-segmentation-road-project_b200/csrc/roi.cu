@@ -147,7 +147,8 @@ __device__ __forceinline__ void roi_columns(const unsigned char* __restrict__ sr
     const uint32_t ystride = (uint32_t)(cw * Cf) * 4u;
 #pragma unroll 1
     for (int task = warp; task < cw * groups; task += nwarps) {
-        const int g = task / cw, x = task - g * cw;
+        int g = 0, x = task;
+        if (groups > 1) { g = task / cw; x = task - g * cw; }      // Cf <= 128: one group, no division
         const int c = (g << 5) + lane;
         if (c >= CV) continue;
         unsigned char* o = reinterpret_cast<unsigned char*>(out + (size_t)x * Cf + (size_t)c * V);
@@ -188,8 +189,8 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
     // every thread reads the device-side level sizes itself (one round trip, no barrier): CTAs
     // beyond the B * R real items exit at once
     int R = 0;
-#pragma unroll
-    for (int f = 0; f < MLP_MAX_LEVELS; ++f) R += (f < L ? level_m[f] : 0);
+#pragma unroll 1
+    for (int f = 0; f < L; ++f) R += level_m[f];
     if (blockIdx.x == 0 && threadIdx.x == 0) level_m[L] = R;   // R = sum of Mf, for TrimInstances
     const unsigned items = (unsigned)B * (unsigned)R;          // <= L * B * m_rows < 2^31 (host check)
     if (blockIdx.x >= items) return;
@@ -204,10 +205,10 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
         int f = 0, foff = 0, mf = 0;
         {
             int o = 0;
-#pragma unroll
-            for (int q = 0; q < MLP_MAX_LEVELS; ++q) {
-                const int m = q < L ? level_m[q] : 0;        // L1/L2 hits after the first read
-                if (q < L && r >= o) { f = q; foff = o; mf = m; }
+#pragma unroll 1
+            for (int q = 0; q < L; ++q) {
+                const int m = level_m[q];                    // L1/L2 hits after the first read
+                if (r >= o) { f = q; foff = o; mf = m; }
                 o += m;
             }
         }
@@ -234,6 +235,7 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
         if (warp == 0) {
             // ---- the whole per-RoI setup in one warp, one barrier for everybody else
             const int j = roi_src[((int64_t)f * B + b) * m_rows + slot];
+            MLP_BOUND(j, m_rows);
             const float* row = dist + ((int64_t)b * m_stride + j) * 7;
             const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
             if (lane < 6) rb[lane] = row[1 + lane];
@@ -285,6 +287,7 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                 // generic-proxy reads of the previous RoI's window (ordered by the barrier above)
                 // before the async proxy overwrites it
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                MLP_BOUND(row_bytes * rows - 1, window_cap);
                 for (int q = lane; q < rows; q += 32)
                     tma_load_1d(s_window + (size_t)q * row_bytes,
                                 img + ((int64_t)(ylo + q) * Wf + xlo) * Cf, (uint32_t)row_bytes, &s_bar);
@@ -318,6 +321,8 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                     if (prev == t && cur == bo) npush = 0;
                     else if (cur == t) npush = 1;
                     else { npush = 2; first = t; }
+                    MLP_BOUND(K + npush, kMaxRows + 1);
+                    MLP_BOUND(no, kMaxCrop);
                     if (npush == 2) {
                         S.obeg[K] = (unsigned short)no;
                         S.rowoff[K++] = (uint32_t)(first - top0) * pitch_bytes;
@@ -491,7 +496,14 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     }
     DeviceGuard g(ctx->device);
     ProfScope prof(ctx, MLP_ST_ROI_ALIGN, (cudaStream_t)stream);
-    const int64_t items = (int64_t)num_levels * batch * m_rows;
+    // The real item count B * R (R = sum over levels of max_b count, <= L * m_rows) is only known on the device.
+    // Every image's counts add up to <= m_rows, so R is typically a little above m_rows: the grid is sized
+    // for B * (m_rows + m_rows / 4 + L) items and the kernel's grid-stride loop covers the (rare) rest; a
+    // grid for the worst case would launch ~6,000 CTAs at cfg-2 that only read R and exit.
+    const int64_t worst = (int64_t)num_levels * batch * m_rows;
+    int64_t items = (int64_t)batch * (m_rows + m_rows / 4 + num_levels);
+    if (items > worst) items = worst;
+    if (const char* e = getenv("MLP_ROI_FULL_GRID")) { if (atoi(e)) items = worst; }
     const int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
     int window_cap = kRoiWindowBytes;
     if (const char* e = getenv("MLP_ROI_WINDOW_KB")) window_cap = atoi(e) * 1024;    // tuning knob; 0 = never stage

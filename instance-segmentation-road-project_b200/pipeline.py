@@ -101,7 +101,7 @@ class PostProcessPipeline:
         if self.cfg.mask_layout == "planar" and not self.cfg.fused:
             raise rt.InvalidArgumentError(rt.MLP_EINVAL, "mask_layout='planar' needs the fused tail (fused=True)")
         self._tail_flags = rt.MLP_MASKS_PLANAR if self.cfg.mask_layout == "planar" else 0
-        self._side = None                # second stream for the background fill (created on first use)
+        self._side = self._main = None   # internal streams of the overlapped background fill (created on first use)
         self._fill_done = None           # event: the fill of the batch in flight has been enqueued / finished
         self._alloc()
 
@@ -126,6 +126,7 @@ class PostProcessPipeline:
         self.roi_boxes = c.empty((B * L * K * 6,), f32)
         self.trim_counts = c.empty((B,), i32)
         self.trim_m = c.empty((1,), i32)
+        self.trim_m.zero_()              # M of the previous batch: sizes the speculative background fill
         self.trim_boxes = c.empty((B * K * 6,), f32)
         self.trim_masks = c.empty((B * K * mh * mw,), f32)
         self.det_i32 = c.empty((B * K * 6,), i32)
@@ -175,32 +176,51 @@ class PostProcessPipeline:
         if self.cfg.fused and prefill:
             fmap_ptrs = (ctypes.c_void_p * L)(*[c.view(f, torch.float32).value for f in fmaps[:L]])
             ch, cw = self.cfg.crop_size
-            rt.check(lib.mlp_detect_plan(
-                c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
-                c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
-                ctypes.byref(self.params), int(self.cfg.max_k), float(self.cfg.base_size),
-                c.view(self.det), c.view(self.keep), c.view(self.counts), c.view(self.m_dev),
-                c.view(self.dist), c.view(self.level_counts), c.view(self.level_m), st))
-            # fork: the fill needs only counts (-> M); it runs beside RoIAlign, the mask head and the tail prep
+            # Two internal streams.  `side` (least priority) streams the zero background of the masks out:
+            # first SPECULATIVELY, sized by the previous batch's M (a longer prefix than needed is only
+            # wasted work), beside the latency-bound NMS kernels, then the rest once this batch's counts
+            # exist.  `main` (high priority) runs the chain itself, so that its CTAs are placed ahead of the
+            # fill's 25,600 short ones whatever the priority of the caller's stream.
             cur = torch.cuda.current_stream(c.device)
             if self._side is None:
-                # least priority: the fill's 64 KB CTAs take whatever SM slots the RoIAlign / mask-head kernels
-                # of the caller's (higher-priority) stream leave free, instead of queueing ahead of them
                 self._side = torch.cuda.Stream(device=c.device, priority=0)
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(fork)
+                self._main = torch.cuda.Stream(device=c.device, priority=-1)
+            side, main = self._side, self._main
+            start = torch.cuda.Event()
+            start.record(cur)
+            side.wait_event(start)
+            main.wait_event(start)
+            null = ctypes.c_void_p(None)
+            with torch.cuda.stream(side):
                 rt.check(lib.mlp_paste_prefill(
-                    c.handle, c.view(self.counts), B, K, self.frame_hw[0], self.frame_hw[1], self.paste_mode,
-                    c.view(self.pasted), ctypes.c_void_p(self._side.cuda_stream)))
+                    c.handle, null, null, c.view(self.trim_m), B, K, self.frame_hw[0], self.frame_hw[1],
+                    self.paste_mode, c.view(self.pasted), ctypes.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(main):
+                rt.check(lib.mlp_detect_plan(
+                    c.handle, ctypes.byref(self.prior_c), c.view(loc_pred, torch.float32),
+                    c.view(cls_pred, torch.float32), B, self.image_hw[0], self.image_hw[1], self.C,
+                    ctypes.byref(self.params), int(self.cfg.max_k), float(self.cfg.base_size),
+                    c.view(self.det), c.view(self.keep), c.view(self.counts), c.view(self.m_dev),
+                    c.view(self.dist), c.view(self.level_counts), c.view(self.level_m),
+                    ctypes.c_void_p(main.cuda_stream)))
+                nms_done = torch.cuda.Event()
+                nms_done.record(main)
+            side.wait_event(nms_done)
+            with torch.cuda.stream(side):
+                rt.check(lib.mlp_paste_prefill(
+                    c.handle, c.view(self.trim_m), c.view(self.counts), null, B, K, self.frame_hw[0],
+                    self.frame_hw[1], self.paste_mode, c.view(self.pasted), ctypes.c_void_p(side.cuda_stream)))
                 self._fill_done = torch.cuda.Event()
-                self._fill_done.record(self._side)
-            rt.check(lib.mlp_roi_align_run(
-                c.handle, fmap_ptrs, self._fh, self._fw, L, self.Cf, c.view(self.dist), B, K, K,
-                c.view(self.m_dev), float(self.image_hw[0]), float(self.image_hw[1]), int(ch), int(cw),
-                c.view(self.level_counts), c.view(self.level_m), self._crop_ptrs, c.view(self.roi_boxes),
-                st))
+                self._fill_done.record(side)
+            with torch.cuda.stream(main):
+                rt.check(lib.mlp_roi_align_run(
+                    c.handle, fmap_ptrs, self._fh, self._fw, L, self.Cf, c.view(self.dist), B, K, K,
+                    c.view(self.m_dev), float(self.image_hw[0]), float(self.image_hw[1]), int(ch), int(cw),
+                    c.view(self.level_counts), c.view(self.level_m), self._crop_ptrs, c.view(self.roi_boxes),
+                    ctypes.c_void_p(main.cuda_stream)))
+                aligned = torch.cuda.Event()
+                aligned.record(main)
+            cur.wait_event(aligned)
             return AlignedRois(self.det, self.keep, self.counts, self.m_dev, self.dist,
                                self.level_counts, self.level_m, self.crops, self.roi_boxes)
         if self.cfg.fused:
@@ -238,8 +258,10 @@ class PostProcessPipeline:
         """Enqueue CropAndPadMask's zero background for the current detections on the CURRENT stream (no fork);
         detect_and_align(prefill=True) does this on a second stream.  For measuring the fill alone."""
         c = self.ctx
-        rt.check(self.lib.mlp_paste_prefill(c.handle, c.view(self.counts), self.B, self.K, self.frame_hw[0],
-                                            self.frame_hw[1], self.paste_mode, c.view(self.pasted), c.stream()))
+        null = ctypes.c_void_p(None)
+        rt.check(self.lib.mlp_paste_prefill(c.handle, null, c.view(self.counts), null, self.B, self.K,
+                                            self.frame_hw[0], self.frame_hw[1], self.paste_mode, c.view(self.pasted),
+                                            c.stream()))
 
     def roi_views(self, rois):
         """Reference-shaped views ([B,Mf,ch,cw,Cf] per level, [B,R,6]) — one small D2H."""

@@ -117,7 +117,7 @@ SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P]),
     "mlp_detect_plan": (_I, [_P, ctypes.POINTER(PriorConfigC), _P, _P, _I, _I, _I, _I,
                              ctypes.POINTER(DetectionParamsC), _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mlp_paste_prefill": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "mlp_paste_prefill": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),

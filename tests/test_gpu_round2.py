@@ -231,3 +231,34 @@ def test_atomic_finalisers_are_deterministic(cfg2):
             L = int(cur[2][b])
             assert torch.equal(cur[1][b, :L], ref[1][b, :L]), f"JPEG bytes of frame {b} differ at replay {i}"
         assert torch.equal(cur[3], ref[3])
+
+
+def test_speculative_fill_follows_a_changing_m():
+    """The background fill is sized by the PREVIOUS batch's M before this batch's counts exist, and completed after
+    the NMS kernels.  Batches whose M grows, shrinks, drops to 1 (no detections at all) and grows again must all
+    equal the plain pipeline bit for bit - stale boxes of earlier batches included (same output buffer)."""
+    import masklab_b200 as ml
+    B, H, W, C, Cf = 3, 96, 160, 4, 8
+    cfgp = synth.prior_config(strides=(8, 16, 32))
+    N = synth.num_anchors(cfgp, H, W)
+    kw = dict(min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65, nms_max_output_size=400,
+              max_k=2, base_size=36)
+    fmaps = [_d(f) for f in synth.fpn_maps(B, H, W, Cf, seed=51)]
+    plain = ml.PostProcessPipeline(cfgp, (H, W), (2 * H, 2 * W), C, Cf, B, ml.DetectionConfig(**kw))
+    fast = ml.PostProcessPipeline(cfgp, (H, W), (2 * H, 2 * W), C, Cf, B, ml.DetectionConfig(prefill=True, **kw))
+    fast.pasted.fill_(5)
+    seen = []
+    for step, mu in enumerate((-6.0, -3.0, -5.0, None, -4.0, -6.5)):
+        loc, cls = synth.head_tensors(B, N, C, mu=mu if mu is not None else -9.0, seed=60 + step)
+        if mu is None:
+            cls[:] = 0                                           # nothing passes the threshold: M = 1, all padding
+        outs = []
+        for pipe in (plain, fast):
+            rois = pipe.detect_and_align(_d(loc), _d(cls), fmaps)
+            _, R = rois.shapes()
+            pipe.trim_and_paste(rois, _d(synth.mask_probs(B, R, C, seed=70 + step)))
+            det_i, pasted = pipe.result_views()
+            outs.append((det_i.clone(), pasted.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (step, mu)
+        seen.append(int(fast.trim_m.item()))
+    assert len(set(seen)) >= 3 and min(seen) == 1, seen            # M really moved both ways

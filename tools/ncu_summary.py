@@ -36,6 +36,9 @@ def to_bytes(v, unit):
 
 
 def main():
+    """argv: report.ncu-rep launches.csv [traffic.json workload]; with the last two the DRAM bytes per launch are also
+    written as JSON together with the hash of the CUDA sources they were captured from (bench.py uses the file only
+    when that hash matches the sources it runs)."""
     rep, launches = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -72,6 +75,14 @@ def main():
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         print(f"| {k} | {len(v)} | {sum(v) / len(v) / 1000:.2f} | {sum(v) / tot * 100:.1f}% |")
     print("\n<!-- traffic-json: " + json.dumps(traffic) + " -->")
+    if len(sys.argv) > 4:
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        with open(sys.argv[3], "w") as f:
+            json.dump({"source": f"{os.path.basename(rep)} (ncu --set full --clock-control none, single stream)",
+                       "workload": sys.argv[4], "source_hash": bench.source_hash(),
+                       "dram_bytes_per_launch": traffic}, f, indent=1)
 
 
 if __name__ == "__main__":
