@@ -513,7 +513,7 @@ def run_ours(args, wl):
         with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
             tj = json.load(f)
         if tj.get("source_hash") == source_hash() and tj.get("workload") == args.workload:
-            traffic = tj["dram_bytes_per_launch"].get("paste_fill_kernel" if use_fill else "paste_kernel<1, 0>")
+            traffic = tj["dram_bytes_per_launch"].get("paste_fill_kernel" if use_fill else "paste_kernel<1>")
             traffic_src = tj.get("source")
     except Exception:
         pass

@@ -25,6 +25,8 @@ struct mlp_ctx {
     // refused with MLP_EFROZEN instead of pulling the memory from under the graph
     bool frozen;
     int tail_planar;       // mask layout of the last mlp_trim_paste (consumed by mlp_tile_summary / mlp_draw_tiles)
+    int64_t tail_layout_key;   // shapes / arena the fused tail's scratch was last laid out for (arrival counter zeroed)
+    void* tail_layout_base;
     // small device block for counters / dims (always allocated)
     int32_t* ctr;          // [MLP_CTR_WORDS]
     // optional per-stage CUDA-event timing (bench.py roofline): pairs recorded on the

@@ -38,6 +38,8 @@ extern "C" int mlp_ctx_create(int device, mlp_ctx** out) {
     c->ctr = nullptr;
     c->frozen = false;
     c->tail_planar = 0;
+    c->tail_layout_key = -1;
+    c->tail_layout_base = nullptr;
     c->prof_on = false;
     c->prof_used = 0;
     c->prof_ev = nullptr;

@@ -612,6 +612,7 @@ static int draw_tiles_impl(mlp_ctx* ctx, const void* images_dev, int image_dtype
         S.planar = ctx->tail_planar;
         S.counts = counts_dev;
         S.confmax = ft.confmax;
+        S.scalars = ft.scalars;
     }
     // scratch: geometry [B,m_rows] + bit rows [B,m_rows,mh] + M
     const int64_t n_inst = (int64_t)batch * m_rows;

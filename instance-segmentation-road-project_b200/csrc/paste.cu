@@ -125,8 +125,14 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int inst = (int)(item / bands);
-        const int band = (int)(item - (int64_t)inst * bands);
+        int inst, band;
+        if (items <= 0x7fffffffLL) {                // the usual case: 32-bit division
+            inst = (int)((uint32_t)item / (uint32_t)bands);
+            band = (int)((uint32_t)item - (uint32_t)inst * (uint32_t)bands);
+        } else {
+            inst = (int)(item / bands);
+            band = (int)(item - (int64_t)inst * bands);
+        }
         const int b = inst / M, j = inst - b * M;
         int row[6];
         {
@@ -441,7 +447,8 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
                      const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, int planar, float rh,
                      float rw, int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
                      uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
-                     int32_t* __restrict__ confmax, uint32_t slot_bytes, const BoxItems Q) {
+                     int32_t* __restrict__ confmax, uint32_t slot_bytes, const BoxItems Q,
+                     int32_t* __restrict__ scalars) {
     constexpr int kWarps = kPrepTmaWarps;
     extern __shared__ __align__(128) unsigned char s_stage[];     // [kWarps][slot_bytes]
     __shared__ __align__(8) uint64_t s_bar[kWarps];
@@ -501,6 +508,7 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
         }
         __syncwarp();
     }
+    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y);
 }
 
 // Register-gather form of the tail preparation (the fallback of tail_prep_tma_kernel: RoI blocks that are
@@ -510,7 +518,7 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
                  const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, int planar, float rh, float rw,
                  int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
                  uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ confmax, const BoxItems Q) {
+                 int32_t* __restrict__ confmax, const BoxItems Q, int32_t* __restrict__ scalars) {
     constexpr int kWarps = kPrepThreads / 32;
     __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
     const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
@@ -528,9 +536,8 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
         confmax[b] = m;
     }
     // bit tiles of this CTA's slots: one warp per slot, lane = mask column, ballot per mask row
-    if (tail_bits == nullptr) return;
     const int px = mh * mw;
-    for (int s = part + parts * warp; s < total; s += parts * kWarps) {
+    for (int s = part + parts * warp; tail_bits != nullptr && s < total; s += parts * kWarps) {
         const int j = src[s];
         const int cls = drows[s * 6 + 4];
         uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
@@ -553,6 +560,7 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
             }
         }
     }
+    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y);
 }
 
 // ---- boxes-only paste: walks the work items of the tail preparation behind a background fill --------
@@ -721,6 +729,14 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     rc = mlp_ensure_scratch(ctx, MLP_ARENA_FUSED, ft.bytes);
     if (rc) return rc;
     ft = fused_tail_layout(ctx->arena[MLP_ARENA_FUSED], batch, k_rows, mask_h, mask_w);
+    // arrival counter of tail_finish: zero it (stream-ordered, 16 bytes) whenever the layout in the arena changes;
+    // afterwards the last CTA of every launch leaves it at zero
+    if (ctx->tail_layout_key != ((int64_t)batch << 40 ^ (int64_t)k_rows << 16 ^ (int64_t)mask_h << 8 ^ mask_w) ||
+        ctx->tail_layout_base != ctx->arena[MLP_ARENA_FUSED]) {
+        MLP_CUDA(cudaMemsetAsync(ft.scalars, 0, 16, st));
+        ctx->tail_layout_key = (int64_t)batch << 40 ^ (int64_t)k_rows << 16 ^ (int64_t)mask_h << 8 ^ mask_w;
+        ctx->tail_layout_base = ctx->arena[MLP_ARENA_FUSED];
+    }
     int32_t* tail_src = ft.tail_src;
     int32_t* confmax = ft.confmax;
     uint32_t* tail_bits = ft.tail_bits;
@@ -762,14 +778,14 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
                                           (int)smem));
             tail_prep_tma_kernel<<<dim3(batch, parts), kPrepTmaWarps * 32, smem, st>>>(
                 roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
-                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, (uint32_t)slot_bytes, Q);
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, (uint32_t)slot_bytes, Q, ft.scalars);
         } else {
             // CTAs per image grow with the capacity so that each warp gathers at most ~2 tiles
             int parts = k_rows / 16;
             parts = parts < kPrepParts ? kPrepParts : (parts > 64 ? 64 : parts);
             tail_prep_kernel<<<dim3(batch, parts), kPrepThreads, 0, st>>>(
                 roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
-                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, Q);
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, Q, ft.scalars);
         }
         MLP_LAUNCH_CHECK(ctx);
     }
@@ -786,6 +802,7 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
     S.planar = planar;
     S.counts = counts_dev;
     S.confmax = confmax;
+    S.scalars = ft.scalars;
     S.m_out = m_dev;
     return paste_launch(ctx, det_i32_dev, S, batch, k_rows, k_rows, mask_h, mask_w, frame_h, frame_w,
                         out_mode, out_dev, st, prefilled ? &Q : nullptr);

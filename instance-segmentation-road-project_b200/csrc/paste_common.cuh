@@ -32,6 +32,7 @@ struct PasteSrc {
     const int32_t* confmax;       // [B] max int confidence of the valid rows (INT_MIN if none)
     int32_t* m_out;               // [1] M written back for the host
     int planar;                   // roi_masks is [B,R,C,mh*mw] (class planes) instead of [B,R,mh*mw,C]
+    const int32_t* scalars;       // [2] = (M, row-filter threshold), reduced once by the tail preparation's last CTA
 };
 
 struct PasteGeom {
@@ -47,7 +48,7 @@ __device__ __forceinline__ PasteGeom paste_geometry(const int32_t* row, int thr,
     const int conf = row[5];
     const float cx = (float)max(row[0], 1), cy = (float)max(row[1], 1);
     const float w = (float)max(row[2], 1), h = (float)max(row[3], 1);
-    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);        // w / 2, exactly
     g.xmin = min(max(__float2int_rz(ceilf(__fsub_rn(cx, hw))), 0), PW);
     g.xmax = min(max(__float2int_rz(ceilf(__fadd_rn(cx, hw))), 0), PW);
     g.ymin = min(max(__float2int_rz(ceilf(__fsub_rn(cy, hh))), 0), PH);
@@ -123,6 +124,13 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
         thr = *S.thr_dev;
         return;
     }
+    if (S.scalars) {                      // reduced once per batch (tail_finish): one 8-byte load per thread
+        const int2 v = __ldg(reinterpret_cast<const int2*>(S.scalars));
+        M = min(v.x, m_rows);
+        thr = v.y;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+        return;
+    }
     const int lane = threadIdx.x & 31;
     int mx = 0, mn = INT_MAX, cm = INT_MIN;
     for (int i = lane; i < B; i += 32) {
@@ -139,6 +147,40 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
     if (mn < M) cm = max(cm, -100);        // MoldBatch padding rows carry conf = int(-1*100)
     thr = (cm > 50) ? 50 : -100;
     if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+}
+
+// Last step of the tail preparation: the CTA that arrives last (all counts[] / confmax[] are written) reduces
+// M = max(1, max counts) and CropAndPadMask's row-filter threshold (misc.py:366-369) ONCE, so that the 25,600
+// short CTAs of the paste kernel read two words instead of repeating the reduction.  scalars[2] is the arrival
+// counter; the last CTA resets it for the next launch.  Every thread of the CTA calls this.
+__device__ __forceinline__ void tail_finish(int32_t* __restrict__ scalars, const int32_t* __restrict__ counts,
+                                            const int32_t* __restrict__ confmax, int B, int m_rows, int total_ctas) {
+    __shared__ int s_last;
+    __threadfence();                              // this CTA's counts / confmax are visible before it arrives
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(scalars + 2, 1) == total_ctas - 1;
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    const int lane = threadIdx.x;
+    int mx = 0, mn = INT_MAX, cm = INT_MIN;
+    for (int i = lane; i < B; i += 32) {
+        const int c = __ldcg(counts + i);
+        mx = max(mx, c); mn = min(mn, c); cm = max(cm, __ldcg(confmax + i));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    }
+    int M = max(mx, 1);
+    if (M > m_rows) M = m_rows;
+    if (mn < M) cm = max(cm, -100);        // MoldBatch padding rows carry conf = int(-1*100)
+    if (lane == 0) {
+        scalars[0] = M;
+        scalars[1] = (cm > 50) ? 50 : -100;
+        scalars[2] = 0;
+    }
 }
 
 // Tile element i of instance (b, j) as the int the reference's mask tensor would hold.
@@ -254,6 +296,7 @@ template <> struct MaskVec<uint8_t> {
 struct FusedTail {
     int32_t* tail_src;
     int32_t* confmax;
+    int32_t* scalars;         // [4]: M, row-filter threshold, arrival counter of the preparing CTAs, pad
     uint32_t* tail_bits;      // NULL when bit tiles are not used
     int64_t bytes;
 };
@@ -263,10 +306,12 @@ inline FusedTail fused_tail_layout(void* base, int batch, int k_rows, int mask_h
     // gather is better left inside the paste kernel, where its reads overlap the write stream.
     const bool use_bits = mask_w <= 32 && k_rows <= 256;
     FusedTail t;
-    t.bytes = ((int64_t)batch * k_rows + batch + (use_bits ? (int64_t)batch * k_rows * mask_h : 0)) * 4;
+    const int64_t head = ((int64_t)batch * k_rows + batch + 3) / 4 * 4;          // keeps `scalars` 16-byte aligned
+    t.bytes = (head + 4 + (use_bits ? (int64_t)batch * k_rows * mask_h : 0)) * 4;
     t.tail_src = static_cast<int32_t*>(base);
     t.confmax = t.tail_src + (int64_t)batch * k_rows;
-    t.tail_bits = use_bits ? reinterpret_cast<uint32_t*>(t.confmax + batch) : nullptr;
+    t.scalars = t.tail_src + head;
+    t.tail_bits = use_bits ? reinterpret_cast<uint32_t*>(t.scalars + 4) : nullptr;
     return t;
 }
 

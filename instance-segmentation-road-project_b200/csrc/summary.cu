@@ -917,6 +917,7 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
         T.src.planar = ctx->tail_planar;
         T.src.counts = counts_dev;
         T.src.confmax = ft.confmax;
+        T.src.scalars = ft.scalars;
         T.src.m_out = m_dev_out;
     }
     T.det = det_i32_dev; T.unit = unit_dev; T.road_bits = road_bits_dev;

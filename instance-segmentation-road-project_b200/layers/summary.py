@@ -22,7 +22,23 @@ def _seg_i32(ctx, seg_outs, what):
         raise rt.InvalidArgumentError(rt.MLP_EDLPACK, f"{what}: seg_outs must be a CUDA tensor (no CPU path)")
     if seg_outs.dim() != 4:
         raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"{what}: seg_outs must be [B,PH,PW,S]")
-    return seg_outs.to(torch.int32).contiguous()
+    return _integral_i32(seg_outs, what)
+
+
+def _integral_i32(x, what):
+    """The kernels take the semantic map as int32 and test `> 0` (road borders, misc.py:661), `> 0.5` after a
+    float cast (IncludeMyRoad, misc.py:605-611) and `!= 0` (tf.where in CrackToInstance, misc.py:516).  On the
+    integer map UpSampleOutput produces (misc.py:195) the three agree with the reference; on a FRACTIONAL float
+    map they would not (0.7 truncates to 0), so such an input is rejected instead of silently summarised."""
+    if x.dtype in (torch.int32, torch.int64, torch.int16, torch.int8, torch.uint8, torch.bool):
+        return x.to(torch.int32).contiguous()
+    if x.is_floating_point():
+        if bool((x != x.trunc()).any()):
+            raise rt.InvalidArgumentError(
+                rt.MLP_EINVAL, f"{what}: the semantic map holds fractional values; pass UpSampleOutput's int32 "
+                "{0,1} map (the reference thresholds it with > 0.5 first, engine/layers/misc.py:195)")
+        return x.to(torch.int32).contiguous()
+    raise rt.InvalidArgumentError(rt.MLP_EINVAL, f"{what}: unsupported semantic map dtype {x.dtype}")
 
 
 def _masks(ctx, masks, what):
@@ -101,7 +117,7 @@ class CrackToInstance(Layer):
 
     def call(self, inputs, **kwargs):
         ctx = ctx_of(inputs)
-        crack = inputs.to(torch.int32).contiguous()
+        crack = _integral_i32(inputs, "CrackToInstance")
         B, PH, PW = (int(d) for d in crack.shape)
         # the scan reads a [B,PH,PW,S] map: view the crack plane as S = 1 with both channels = 0
         unit = ctx.empty((B, PH), torch.float32)

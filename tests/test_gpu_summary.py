@@ -197,3 +197,23 @@ def test_serving_consumers_at_1080p():
     got_vis = ml.DrawInstance(colors, 0.3).from_tiles([boxed, dev(det), dev(ins)], seg_outs=dev(seg),
                                                       semantic_colors=sem_colors, semantic_alpha=0.3)
     assert np.array_equal(got_vis.cpu().numpy(), want_vis)
+
+
+def test_fractional_semantic_maps_are_rejected_integral_floats_accepted():
+    """the kernels read the semantic map as int32; a fractional float map (0.7 -> 0) would silently
+    differ from the reference's `> 0.5` / `> 0` / `!= 0` tests, so it is rejected; an integral float map is fine."""
+    import masklab_b200 as ml
+    from masklab_b200 import runtime as rt
+    B, PH, PW, M = 1, 64, 96, 3
+    seg = synth.semantic_map(B, PH, PW, seed=3)
+    det = synth.int_detections(B, M, 5, PH, PW, seed=4)
+    masks = (np.random.default_rng(5).random((B, M, PH, PW)) > 0.7).astype(np.float32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    want = ml.SummaryOutput()([d(det), d(seg), d(masks)])
+    same = ml.SummaryOutput()([d(det), d(seg.astype(np.float32)), d(masks)])
+    assert torch.equal(want, same)
+    soft = seg.astype(np.float32) * 0.7
+    with pytest.raises(rt.InvalidArgumentError):
+        ml.SummaryOutput()([d(det), d(soft), d(masks)])
+    with pytest.raises(rt.InvalidArgumentError):
+        ml.CrackToInstance()(d(soft[..., 2]))
