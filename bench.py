@@ -543,7 +543,7 @@ def run_ours(args, wl):
                                   "stage_ms": {k_: v_ for k_, v_ in iso.items() if not k_.startswith("_")}}}
 
     # ---- end to end through the public API with host buffers
-    e2e = e2e_bits = None
+    e2e = e2e_bits = e2e_clip = None
     if not args.no_e2e:
         e2e = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier)
         if PW % 8 == 0:
@@ -554,6 +554,12 @@ def run_ours(args, wl):
             pipe_b = ml.PostProcessPipeline(cfgp, (H, W), (PH, PW), C, wl["Cf"], B, cfg_b, device=local,
                                             private_context=True)
             e2e_bits = run_e2e(args, wl, pipe_b, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=True)
+            del pipe_b
+        # same path, masks delivered as box-clipped bit rows (a few MB per batch; lossless, expand_clipped on the host)
+        r_ = pipe.detect_and_align(d_loc, d_cls, d_fmaps, prefill=False)
+        used_ = pipe.trim_and_clip(r_, d_masks)[3]
+        e2e_clip = run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier,
+                           clip_cap=max(1, int(used_[0].item())))
 
     # ---- the consumer of the masks (SummaryOutput) fused behind the tail
     summary_leg = None
@@ -652,7 +658,7 @@ def run_ours(args, wl):
             "scaling": "strong" if args.frames else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl), "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "e2e_bitpacked": e2e_bits, "serving_tail": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_bitpacked": e2e_bits, "e2e_boxclip": e2e_clip, "serving_tail": summary_leg, "gpu_launches": int(launches), "clocks": clocks.summary(),
             "detections": {"M": M, "R": R, "Mf": mf, "kept_per_image_mean": float(counts.mean())},
             "device_bytes": pipe.device_bytes(),
         }
@@ -747,7 +753,7 @@ SEM_COLORS = [[64, 0, 128], [128, 96, 0], [128, 192, 0]]      # engine/config.py
 
 
 def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, bits=False, h_seg=None,
-            summary_rows=0, h_img=None, jpeg_cap=0):
+            summary_rows=0, h_img=None, jpeg_cap=0, clip_cap=0):
     """Same metric through PostProcessPipeline with HOST buffers: every step copies the inputs
     from pinned host memory, runs the path and reads detections + binary masks back into pinned
     host memory.  Three streams (copy-in, compute, copy-out) and two sets of device input buffers,
@@ -765,9 +771,17 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
                  img=(torch.empty_like(h_img, device="cuda") if h_img is not None else None),
                  free=None) for _ in range(NB)]
     summary = h_seg is not None
-    out_det = torch.empty((B * (pipe.K if summary else M) * 6,), dtype=torch.int32).pin_memory()
+    clip = clip_cap > 0
+    out_det = torch.empty((B * (pipe.K if (summary or clip) else M) * 6,), dtype=torch.int32).pin_memory()
     if summary:
         out_masks = torch.empty((B * summary_rows * 11,), dtype=torch.float32).pin_memory()
+    elif clip:
+        # box-clipped bit rows: a fixed pool bound (1.25 x what the warm-up batch needed, 64 KB granules) is copied
+        # without asking the device for the size first; the geometry records and the size travel with it
+        clip_cap = (int(clip_cap * 1.25) + 65535) // 65536 * 65536
+        out_masks = torch.empty((clip_cap,), dtype=torch.uint8).pin_memory()
+        out_geom = torch.empty((B * pipe.K * 8,), dtype=torch.int32).pin_memory()
+        out_used = torch.empty((2,), dtype=torch.int64).pin_memory()
     else:
         out_masks = torch.empty((B * M * PH * (PW // 8 if bits else PW),), dtype=torch.uint8).pin_memory()
     # the overlay leaves as JPEG files: a fixed per-frame bound (1.25 x the largest file of the warm-up step, 64 KB
@@ -778,6 +792,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
     h2d = sum(t.numel() * t.element_size() for t in [h_loc, h_cls, h_masks] + h_fmaps + ([h_seg] if summary else [])
               + ([h_img] if h_img is not None else []))
     d2h = out_det.numel() * 4 + out_masks.numel() * out_masks.element_size() + (out_vis.numel() + 4 * B if h_img is not None else 0)
+    if clip:
+        d2h += out_geom.numel() * 4 + 16
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     state = {"i": 0, "out_done": None}
 
@@ -802,7 +818,7 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             s_cmp.wait_event(ev_in)
             if state["out_done"] is not None:
                 s_cmp.wait_event(state["out_done"])         # previous results copied out
-            r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"], prefill=(None if not summary else False))
+            r = pipe.detect_and_align(buf["loc"], buf["cls"], buf["fmaps"], prefill=(False if (summary or clip) else None))
             vis = None
             if summary:
                 det_i32, pasted, _ = pipe.trim_and_summarize(r, buf["masks"], buf["seg"])
@@ -810,6 +826,8 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
                     pipe.draw(r, buf["masks"], buf["img"], INST_COLORS[:wl["C"]], 0.3, seg_outs=buf["seg"],
                               semantic_colors=SEM_COLORS, semantic_alpha=0.3, boxes=True)
                     vis, vis_len = pipe.encode()
+            elif clip:
+                det_i32, geom, pasted, used = pipe.trim_and_clip(r, buf["masks"], pool_bytes=clip_cap)
             else:
                 det_i32, pasted, _ = pipe.trim_and_paste(r, buf["masks"])
             cmp_done = torch.cuda.Event()
@@ -819,6 +837,9 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             s_out.wait_event(cmp_done)
             out_det.copy_(det_i32[:out_det.numel()], non_blocking=True)
             out_masks.copy_(pasted[:out_masks.numel()], non_blocking=True)
+            if clip:
+                out_geom.copy_(geom.view(-1), non_blocking=True)
+                out_used.copy_(used, non_blocking=True)
             if vis is not None:
                 out_vis.copy_(vis[:, :jpeg_cap], non_blocking=True)
                 out_len.copy_(vis_len, non_blocking=True)
@@ -847,7 +868,11 @@ def run_e2e(args, wl, pipe, h_loc, h_cls, h_fmaps, h_masks, world, M, barrier, b
             # both directions run concurrently (PCIe is full duplex): the busier one bounds the step
             "pcie_gbs_busier_direction": max(h2d, d2h) / (step_ms * 1e-3) / 1e9,
             "bound": "PCIe (host<->device copies of every step), not the kernels",
-            "api": ("PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw + encode" if h_img is not None else "")
+            "pool_bytes_used": (int(out_used[0]) if clip else None),
+            "api": ("PostProcessPipeline.detect_and_align + trim_and_clip; pinned host inputs in, int32 detections + "
+                    "box-clipped bit rows (geometry records + byte pool, expand_clipped rebuilds the dense masks) out"
+                    if clip else
+                    "PostProcessPipeline.detect_and_align + trim_and_summarize" + (" + draw + encode" if h_img is not None else "")
                     + "; pinned host inputs (heads, FPN maps, mask-head output, semantic map"
                     + (", frames" if h_img is not None else "") + ") in, int32 detections + [B,M',11] summary"
                     + (" + the JPEG files of the overlay (fixed per-frame bound)" if h_img is not None else "")

@@ -299,6 +299,19 @@ int mlp_paste_prefill(mlp_ctx* ctx, const int32_t* m_from_dev, const int32_t* co
                       const int32_t* m_to_dev, int batch, int k_rows, int frame_h, int frame_w, int out_mode,
                       void* out_dev, mlp_stream_t stream);
 
+/* ---- a13/a14 in box-clipped form: CropAndPadMask (engine/layers/misc.py:358-401) + the consumers' > 0.5 without
+ * the tf.pad zeros (misc.py:393-394), for clients on the far side of PCIe / NCCL.  Runs behind
+ * mlp_trim_paste(.., MLP_PASTE_NONE, ..) of the same batch.  geom_dev int32 [B,K,8]: per slot of the capacity grid
+ * { xmin, ymin, w, h, offset_lo, offset_hi, class, conf }; pool_dev: h rows of ceil(w/8) bytes per instance at
+ * `offset`, bit k of byte i of row r = pixel (ymin+r, xmin+8i+k) of the instance's frame-sized binary mask
+ * (w = h = 0: nothing pasted).  used_dev int64 [2] = bytes the batch needs (> pool_capacity: the pool was too small,
+ * rows past it were dropped) and the number of work items.  mlp_clip_pool_bound: a capacity that cannot overflow. */
+int64_t mlp_clip_pool_bound(int batch, int k_rows, int frame_h, int frame_w);
+int mlp_clip_masks(mlp_ctx* ctx, const int32_t* det_i32_dev, const float* roi_masks_dev, int r_rows,
+                   const int32_t* r_dev, int num_classes, const int32_t* counts_dev, int batch, int k_rows,
+                   int mask_h, int mask_w, int frame_h, int frame_w, int32_t* geom_dev, uint8_t* pool_dev,
+                   int64_t pool_capacity, int64_t* used_dev, mlp_stream_t stream);
+
 /* ---- a8: MoldBatch.call (engine/layers/misc.py:231-286) as a standalone operator ----
  * x_dev [K,row_elems] of 4-byte elements, batch_idx_dev i32 [K] (image id of each row).
  * Plan: counts_dev i32 [B], m_dev i32 [1] = max(1, max_b count).  Run: out_dev

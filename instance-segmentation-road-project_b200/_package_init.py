@@ -8,7 +8,7 @@ from .layers import (PriorLayer, RestoreBoxes, NormalizeBoxes, DetectionProposal
                      UpSampleOutput, CropAndPadMask, CrackToInstance, SummaryOutput, IncludeMyRoad,
                      CalculateInstanceSize, DrawBoxes, DrawSegmentation, DrawInstance, SemanticSmoothing,
                      CalculateIOU, AssignBoxes, AssignMasks, DetectionIOUMetric, EncodeImageContent, get_custom_objects)
-from .pipeline import PostProcessPipeline, DetectionConfig      # noqa: F401
+from .pipeline import PostProcessPipeline, DetectionConfig, expand_clipped      # noqa: F401
 from .serving import PostProcessConfig, serving_outputs        # noqa: F401
 from .runtime import Context, MaskLabError, InvalidArgumentError, load_library   # noqa: F401
 

@@ -15,7 +15,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_NAME = "libmasklab_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 
-SOURCES = ["ctx.cu", "elementwise.cu", "detect.cu", "roi.cu", "paste.cu", "mold.cu", "summary.cu", "draw.cu", "resize.cu", "assign.cu", "jpeg.cu"]
+SOURCES = ["ctx.cu", "elementwise.cu", "detect.cu", "roi.cu", "paste.cu", "mold.cu", "summary.cu", "draw.cu", "resize.cu", "assign.cu", "jpeg.cu", "clip.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -545,7 +545,7 @@ struct DetScratch {
     int32_t* cls_kept;       // [G]
     int32_t* min_n;          // [G]
     float4* rec_box;         // [G][max_out]
-    int2* rec_sn;            // [G][max_out] (score bits, n)
+    int4* rec_sn;            // [G][max_out] (score bits, n, 0, 0): 16-byte records, bulk-copyable per group
     uint64_t* cat_keys;      // [B][C*max_out]
     float4* cat_box;         // [B][C*max_out]
     int2* cat_sn;            // [B][C*max_out] (score bits, n)
@@ -593,10 +593,10 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
         return;
     }
     float4* rec_box = D.rec_box + (int64_t)g * max_out;
-    int2* rec_sn = D.rec_sn + (int64_t)g * max_out;
+    int4* rec_sn = D.rec_sn + (int64_t)g * max_out;
     auto emit = [&](int rank, uint64_t key, const float4& bx) {
         rec_box[rank] = bx;
-        rec_sn[rank] = make_int2(__float_as_int(key_score(key)), (int)(uint32_t)key);
+        rec_sn[rank] = make_int4(__float_as_int(key_score(key)), (int)(uint32_t)key, 0, 0);
     };
     int kept;
     if (kDecode) {
@@ -615,12 +615,21 @@ struct FetchCat {
     __device__ float4 operator()(uint32_t p) const { return box[p]; }
 };
 
+// Survivors staged in shared memory by bulk copies (the north star's "TMA-tiled IoU blocks", where a contiguous tile
+// exists: every class's survivors are one contiguous run of 16-byte records).  kStageCap survivors at most.
+constexpr int kStageCap = kBlock;
+
 __global__ void __launch_bounds__(kCrossThreads, 1)
 nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D,
                        float* __restrict__ det, int32_t* __restrict__ keep,
-                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan F) {
+                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan F, int use_tma) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
+    // behind the NMS work space: staging area of the bulk copies, boxes then (score, anchor) records
+    float4* t_box = reinterpret_cast<float4*>(smem_raw + ((nms_smem_bytes(sort_cap, max_out) + 127) & ~(size_t)127));
+    int4* t_sn = reinterpret_cast<int4*>(t_box + kStageCap);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned char s_cat_c[kStageCap];
     __shared__ int s_order[256];
     __shared__ int s_off[257];
     const int b = blockIdx.x;
@@ -664,8 +673,52 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     float4* cat_box = D.cat_box + cat_base;
     int2* cat_sn = D.cat_sn + cat_base;
     int32_t* cat_c = D.cat_c + cat_base;
-    // concatenation, flat over the survivors (one round of loads): position p -> (group gi, rank i)
     const bool staged = total <= sort_cap;
+    const bool tma = use_tma && staged && total > 0 && total <= kStageCap;      // CTA-uniform
+    float* det_b = det + (int64_t)b * max_out * 6;
+    int32_t* keep_b = keep ? keep + (int64_t)b * max_out * 2 : nullptr;
+    int kept = 0;
+    if (tma) {
+        // ---- one cp.async.bulk pair per class run: survivors land in shared memory, nothing is written back
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)total * 32u);
+        }
+        __syncthreads();
+        if (tid < ng) {
+            const int c = s_order[tid];
+            const int n_g = s_off[tid + 1] - s_off[tid];
+            if (n_g > 0) {
+                const int64_t src = (int64_t)(b * C + c) * max_out;
+                tma_load_1d(t_box + s_off[tid], D.rec_box + src, (uint32_t)n_g * 16u, &s_bar);
+                tma_load_1d(t_sn + s_off[tid], D.rec_sn + src, (uint32_t)n_g * 16u, &s_bar);
+            }
+        }
+        for (int p = tid; p < total; p += blockDim.x) {          // class of every position while the copies fly
+            int gi = 0;
+            while (gi + 1 < ng && p >= s_off[gi + 1]) ++gi;
+            s_cat_c[p] = (unsigned char)s_order[gi];
+        }
+        mbar_wait(&s_bar, 0);
+        for (int p = tid; p < total; p += blockDim.x)
+            S.skeys[p] = make_key(__int_as_float(t_sn[p].x), (uint32_t)p);
+        __syncthreads();
+        auto emit = [&](int rank, uint64_t key, const float4& bx) {
+            const uint32_t p = (uint32_t)key;
+            MLP_BOUND(p, kStageCap);
+            MLP_BOUND(rank, max_out);
+            const int4 sn = t_sn[p];
+            const int c = (int)s_cat_c[p];
+            float* o = det_b + rank * 6;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+            o[4] = (float)c;
+            o[5] = __int_as_float(sn.x);
+            if (keep_b) { keep_b[rank * 2] = sn.y; keep_b[rank * 2 + 1] = c; }
+        };
+        FetchCat f{t_box};
+        kept = nms_core<kCrossThreads>(nullptr, total, sort_cap, thr, max_out, S, f, emit, true);
+    } else {
+    // concatenation, flat over the survivors (one round of loads): position p -> (group gi, rank i)
     for (int p = tid; p < total; p += blockDim.x) {
         int gi = 0;
         while (gi + 1 < ng && p >= s_off[gi + 1]) ++gi;
@@ -674,7 +727,8 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         MLP_BOUND(p, C * max_out);
         MLP_BOUND(p - s_off[gi], max_out);
         const float4 bx = D.rec_box[src];
-        const int2 sn = D.rec_sn[src];
+        const int4 sn4 = D.rec_sn[src];
+        const int2 sn = make_int2(sn4.x, sn4.y);
         cat_box[p] = bx;
         cat_sn[p] = sn;
         cat_c[p] = c;
@@ -683,8 +737,6 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         if (staged) S.skeys[p] = key;
     }
     __syncthreads();
-    float* det_b = det + (int64_t)b * max_out * 6;
-    int32_t* keep_b = keep ? keep + (int64_t)b * max_out * 2 : nullptr;
     auto emit = [&](int rank, uint64_t key, const float4& bx) {
         const uint32_t p = (uint32_t)key;
         MLP_BOUND(p, C * max_out);
@@ -697,10 +749,10 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         o[5] = __int_as_float(sn.x);
         if (keep_b) { keep_b[rank * 2] = sn.y; keep_b[rank * 2 + 1] = c; }
     };
-    int kept = 0;
     if (total > 0) {
         FetchCat f{cat_box};
         kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged);
+    }
     }
     // -1 padding of the unused rows (MoldBatch, misc.py:276-283)
     for (int i = kept * 6 + tid; i < max_out * 6; i += blockDim.x) det_b[i] = -1.0f;
@@ -771,7 +823,7 @@ int plan_scratch(mlp_ctx* ctx, int B, int64_t N, int C, int max_out, DetScratch*
     const int64_t o_kept = take(G * 4);
     const int64_t o_minn = take(G * 4);
     const int64_t o_rbox = take(G * max_out * 16);
-    const int64_t o_rsn = take(G * max_out * 8);
+    const int64_t o_rsn = take(G * max_out * 16);
     const int64_t o_ckeys = take(G * max_out * 8);
     const int64_t o_cbox = take(G * max_out * 16);
     const int64_t o_csn = take(G * max_out * 8);
@@ -784,7 +836,7 @@ int plan_scratch(mlp_ctx* ctx, int B, int64_t N, int C, int max_out, DetScratch*
     out->cls_kept = reinterpret_cast<int32_t*>(base + o_kept);
     out->min_n = reinterpret_cast<int32_t*>(base + o_minn);
     out->rec_box = reinterpret_cast<float4*>(base + o_rbox);
-    out->rec_sn = reinterpret_cast<int2*>(base + o_rsn);
+    out->rec_sn = reinterpret_cast<int4*>(base + o_rsn);
     out->cat_keys = reinterpret_cast<uint64_t*>(base + o_ckeys);
     out->cat_box = reinterpret_cast<float4*>(base + o_cbox);
     out->cat_sn = reinterpret_cast<int2*>(base + o_csn);
@@ -880,13 +932,15 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     // K3: cross-class NMS per image; sort buffer sized for C*max_out survivors when it fits.
     {
         ProfScope prof(ctx, MLP_ST_NMS_CROSS, stream);
-        const int sort_cap = pick_sort_cap(C * max_out, max_out, 200 * 1024);
-        const size_t smem = nms_smem_bytes(sort_cap, max_out);
+        const int sort_cap = pick_sort_cap(C * max_out, max_out, 180 * 1024);
+        const size_t smem = ((nms_smem_bytes(sort_cap, max_out) + 127) & ~(size_t)127) + (size_t)kStageCap * 32;
+        int use_tma = 0;                               // measured: equal at cfg-2, 1.7 us slower at batch 1 (profiles/nms_tma_ab_r02.txt)
+        if (const char* e = getenv("MLP_NMS_TMA")) use_tma = atoi(e);
         MLP_CUDA(cudaFuncSetAttribute(nms_cross_class_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nms_cross_class_kernel<<<B, kCrossThreads, smem, stream>>>(C, p->post_iou_threshold, max_out,
                                                                 sort_cap, D, det_dev, keep_dev,
-                                                                counts_dev, m_dev, fp);
+                                                                counts_dev, m_dev, fp, use_tma);
         MLP_LAUNCH_CHECK(ctx);
     }
     return MLP_OK;

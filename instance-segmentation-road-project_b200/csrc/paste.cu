@@ -113,33 +113,42 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
     extern __shared__ __align__(16) unsigned char s_dyn[];           // [tile floats][column table], paste_smem_bytes
     float* s_tile = reinterpret_cast<float*>(s_dyn);
     uint2* s_col_buf = reinterpret_cast<uint2*>(s_dyn + paste_tile_bytes(mh * mw));
-    int M, thr;
-    paste_scalars(S, B, m_rows, M, thr);
-    if (m_stride == 0) m_stride = M;               // compact [B,M,..] input layout
+    // Items are numbered over the CAPACITY grid (image, slot < m_rows, band), so that a CTA knows its instance - and
+    // can fetch its detection row - without waiting for the device-side M; slots >= M leave once M has arrived.
     const int bands = (PH + band_rows - 1) / band_rows;
-    const int64_t items = (int64_t)B * M * bands;
+    const int64_t items = (int64_t)B * m_rows * bands;
     const int spr = PW / kVec;                     // 16-byte segments per frame row
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int px = mh * mw;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    int M = -1, thr = 0;
 
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        int inst, band;
+        int slot, band;
         if (items <= 0x7fffffffLL) {                // the usual case: 32-bit division
-            inst = (int)((uint32_t)item / (uint32_t)bands);
-            band = (int)((uint32_t)item - (uint32_t)inst * (uint32_t)bands);
+            slot = (int)((uint32_t)item / (uint32_t)bands);
+            band = (int)((uint32_t)item - (uint32_t)slot * (uint32_t)bands);
         } else {
-            inst = (int)(item / bands);
-            band = (int)(item - (int64_t)inst * bands);
+            slot = (int)(item / bands);
+            band = (int)(item - (int64_t)slot * bands);
         }
-        const int b = inst / M, j = inst - b * M;
+        const int b = slot / m_rows, j = slot - b * m_rows;
         int row[6];
-        {
+        if (m_stride != 0) {                        // capacity layout: the row does not depend on M - load it first
             const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * m_stride + j) * 6);
             const int2 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
             row[0] = a0.x; row[1] = a0.y; row[2] = a1.x; row[3] = a1.y; row[4] = a2.x; row[5] = a2.y;
         }
+        if (M < 0) paste_scalars(S, B, m_rows, M, thr);
+        if (j >= M) continue;                       // block-uniform
+        const int stride = m_stride ? m_stride : M; // compact [B,M,..] input layout
+        if (m_stride == 0) {
+            const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * stride + j) * 6);
+            const int2 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+            row[0] = a0.x; row[1] = a0.y; row[2] = a1.x; row[3] = a1.y; row[4] = a2.x; row[5] = a2.y;
+        }
+        const int inst = b * M + j;                 // position in the [B,M,PH,PW] output
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         const int y0 = band * band_rows;
         const int y1 = min(y0 + band_rows, PH);
@@ -153,7 +162,7 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         TileRef tref;
         tref.mi = nullptr; tref.mf = nullptr; tref.bits = nullptr; tref.es = 1; tref.mw = mw; tref.valid = false;
         if (touches) {
-            tref = tile_ref(S, b, j, m_stride, px, row[4], mh, mw);
+            tref = tile_ref(S, b, j, stride, px, row[4], mh, mw);
 #pragma unroll
             for (int q = 0; q < kTileRegs; ++q) {
                 const int i = tid + q * kPasteThreads;
@@ -448,7 +457,7 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
                      float rw, int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
                      uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
                      int32_t* __restrict__ confmax, uint32_t slot_bytes, const BoxItems Q,
-                     int32_t* __restrict__ scalars) {
+                     int32_t* __restrict__ scalars, int32_t* __restrict__ m_out) {
     constexpr int kWarps = kPrepTmaWarps;
     extern __shared__ __align__(128) unsigned char s_stage[];     // [kWarps][slot_bytes]
     __shared__ __align__(8) uint64_t s_bar[kWarps];
@@ -508,7 +517,7 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
         }
         __syncwarp();
     }
-    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y);
+    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y, m_out);
 }
 
 // Register-gather form of the tail preparation (the fallback of tail_prep_tma_kernel: RoI blocks that are
@@ -518,7 +527,8 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
                  const int32_t* __restrict__ r_dev, int K, int mh, int mw, int C, int planar, float rh, float rw,
                  int32_t* __restrict__ det_i32, int32_t* __restrict__ tail_src,
                  uint32_t* __restrict__ tail_bits, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ confmax, const BoxItems Q, int32_t* __restrict__ scalars) {
+                 int32_t* __restrict__ confmax, const BoxItems Q, int32_t* __restrict__ scalars,
+                 int32_t* __restrict__ m_out) {
     constexpr int kWarps = kPrepThreads / 32;
     __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
     const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
@@ -560,7 +570,7 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
             }
         }
     }
-    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y);
+    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y, m_out);
 }
 
 // ---- boxes-only paste: walks the work items of the tail preparation behind a background fill --------
@@ -778,14 +788,14 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
                                           (int)smem));
             tail_prep_tma_kernel<<<dim3(batch, parts), kPrepTmaWarps * 32, smem, st>>>(
                 roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
-                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, (uint32_t)slot_bytes, Q, ft.scalars);
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, (uint32_t)slot_bytes, Q, ft.scalars, m_dev);
         } else {
             // CTAs per image grow with the capacity so that each warp gathers at most ~2 tiles
             int parts = k_rows / 16;
             parts = parts < kPrepParts ? kPrepParts : (parts > 64 ? 64 : parts);
             tail_prep_kernel<<<dim3(batch, parts), kPrepThreads, 0, st>>>(
                 roi_boxes_dev, roi_masks_dev, r_rows, r_dev, k_rows, mask_h, mask_w, num_classes, planar, ratio_h,
-                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, Q, ft.scalars);
+                ratio_w, det_i32_dev, tail_src, tail_bits, counts_dev, confmax, Q, ft.scalars, m_dev);
         }
         MLP_LAUNCH_CHECK(ctx);
     }

@@ -154,7 +154,8 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
 // short CTAs of the paste kernel read two words instead of repeating the reduction.  scalars[2] is the arrival
 // counter; the last CTA resets it for the next launch.  Every thread of the CTA calls this.
 __device__ __forceinline__ void tail_finish(int32_t* __restrict__ scalars, const int32_t* __restrict__ counts,
-                                            const int32_t* __restrict__ confmax, int B, int m_rows, int total_ctas) {
+                                            const int32_t* __restrict__ confmax, int B, int m_rows, int total_ctas,
+                                            int32_t* __restrict__ m_out) {
     __shared__ int s_last;
     __threadfence();                              // this CTA's counts / confmax are visible before it arrives
     __syncthreads();
@@ -180,6 +181,7 @@ __device__ __forceinline__ void tail_finish(int32_t* __restrict__ scalars, const
         scalars[0] = M;
         scalars[1] = (cm > 50) ? 50 : -100;
         scalars[2] = 0;
+        if (m_out) *m_out = M;                 // M for the host / the next batch's speculative fill
     }
 }
 

@@ -539,7 +539,51 @@ struct BoxSummaryArgs {
     float threshold;
     float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
+    uint32_t* items;           // work items of box_plan_kernel: (b * m_rows + j) | chunk << 20
+    int32_t* n_items;          // [1]
+    int item_cap;
 };
+
+// One CTA per image, one thread per instance row (rounds of 256): which 128-column chunks of its clipped box exist.
+// Only those become work items (an atomicAdd per round and CTA), widest chunk index first within an instance; the
+// summary kernel walks the list instead of testing all B * M * ceil(PW / 128) combinations, 7 of 8 of which are empty.
+__global__ void __launch_bounds__(kReduceThreads)
+box_plan_kernel(const BoxSummaryArgs A) {
+    __shared__ int s_cnt[kReduceThreads / 32];
+    __shared__ int s_base;
+    int M, thr = 0;
+    paste_scalars(A.src, A.B, A.m_rows, M, thr);
+    const int m_stride = A.m_stride ? A.m_stride : M;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int j0 = 0; j0 < M; j0 += kReduceThreads) {
+        const int j = j0 + tid;
+        int n = 0;
+        if (j < M) {
+            const PasteGeom g = paste_geometry(A.det + ((int64_t)b * m_stride + j) * 6, thr, A.mh, A.mw, A.PH, A.PW);
+            n = g.active ? (g.xmax - g.xmin + kBoxCols - 1) / kBoxCols : 1;      // an all-zero mask still gets its row
+        }
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_cnt[warp] = incl;
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int q = 0; q < kReduceThreads / 32; ++q) {
+            if (q < warp) pre += s_cnt[q];
+            tot += s_cnt[q];
+        }
+        if (tid == 0) s_base = atomicAdd(A.n_items, tot);
+        __syncthreads();
+        int at = s_base + pre + incl - n;
+        for (int c = n - 1; c >= 0; --c, ++at)
+            if (at < A.item_cap) A.items[at] = (uint32_t)(b * A.m_rows + j) | ((uint32_t)c << 20);
+        __syncthreads();
+    }
+}
 
 struct BoxSmem {
     float tile[kMaxTile];
@@ -605,7 +649,7 @@ __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 d[q] = (double)v[q];
-                col[q] = __dadd_rn(col[q], __dmul_rn(du, d[q]));
+                col[q] = __fma_rn(du, d[q], col[q]);       // float32 x float32 is exact in float64: same bits as mul + add
                 on |= (v[q] > 0.5f ? 1u : 0u) << q;
             }
             const double rs = Q == 4 ? __dadd_rn(__dadd_rn(d[0], d[1]), __dadd_rn(d[Q / 2], d[Q - 1])) : d[0];
@@ -663,8 +707,9 @@ box_summary_kernel(const BoxSummaryArgs A) {
     const int PH = A.PH, PW = A.PW, mh = A.mh, mw = A.mw;
     const int words = (PW + 31) >> 5, ywords = (PH + 31) >> 5;
     const int n_crack = has_crack ? A.B : 0;
-    const int64_t items = n_crack + (A.has_tiles ? (int64_t)A.B * M * A.chunks : 0);
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int n_list = A.has_tiles ? min(*A.n_items, A.item_cap) : 0;
+    const int items = n_crack + n_list;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
         if (item < n_crack) {                               // reduced by mlp_road_scan already
             if (tid == 0) {
                 const int b = (int)item;
@@ -674,32 +719,11 @@ box_summary_kernel(const BoxSummaryArgs A) {
             }
             continue;
         }
-        // chunk-major, highest chunk first: the extra chunks of wide (= large) boxes start before the
-        // bulk of small boxes, so the longest CTAs are not the last ones
-        // (most items only get as far as the width test below, so the index arithmetic is kept 32-bit when it fits)
-        int chunk, b, j;
-        if (items <= 0x7fffffffLL) {
-            const uint32_t t = (uint32_t)(item - n_crack), n_inst = (uint32_t)A.B * (uint32_t)M;
-            const uint32_t cq = t / n_inst, inst = t - cq * n_inst;
-            chunk = A.chunks - 1 - (int)cq;
-            b = (int)(inst / (uint32_t)M);
-            j = (int)(inst - (uint32_t)b * (uint32_t)M);
-        } else {
-            const int64_t t = item - n_crack;
-            const int64_t n_inst = (int64_t)A.B * M;
-            chunk = A.chunks - 1 - (int)(t / n_inst);
-            const int64_t inst = t % n_inst;
-            b = (int)(inst / M);
-            j = (int)(inst - (int64_t)b * M);
-        }
+        const uint32_t code = __ldg(A.items + (item - n_crack));
+        const int chunk = (int)(code >> 20);
+        const int inst = (int)(code & 0xfffffu);
+        const int b = inst / A.m_rows, j = inst - b * A.m_rows;
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
-        if (chunk > 0) {                                    // most (instance, chunk) items do not exist: decide that
-            const float cx = (float)max(row[0], 1);         // from the box width alone (x part of paste_geometry)
-            const float hw = __fdiv_rn((float)max(row[2], 1), 2.0f);
-            const int x0 = min(max(__float2int_rz(ceilf(__fsub_rn(cx, hw))), 0), PW);
-            const int x1 = min(max(__float2int_rz(ceilf(__fadd_rn(cx, hw))), 0), PW);
-            if (chunk * 32 >= x1 - x0) continue;            // 32 = the narrowest chunk; CTA-uniform
-        }
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         const int cols = 32 * box_q(g);                     // columns per chunk of this box
         const int nchunks = g.active ? (g.xmax - g.xmin + cols - 1) / cols : 1;
@@ -713,7 +737,7 @@ box_summary_kernel(const BoxSummaryArgs A) {
         }
         __syncthreads();                                   // previous item done with shared memory
         const TileRef tref = tile_ref(A.src, b, j, m_stride, mh * mw, row[4], mh, mw);
-        for (int i = tid; i < mh * mw; i += kReduceThreads) S.tile[i] = (float)tref.at(i);
+        tref.fill(S.tile, mh, tid, kReduceThreads);
         for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) S.unit[y] = A.unit[(int64_t)b * PH + y];
         for (int i = (g.ymin >> 5) + tid; i <= ((g.ymax - 1) >> 5); i += kReduceThreads) S.rowany[i] = 0u;
         __syncthreads();
@@ -926,16 +950,26 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
     T.PH = frame_h; T.PW = frame_w; T.threshold = include_threshold; T.out = out_dev; T.m_out = m_out_dev;
     // per-instance accumulators for boxes split over several CTAs (zeroed every call)
     const int ywords = (frame_h + 31) / 32;
-    const int64_t acc_bytes = (int64_t)batch * m_rows * (sizeof(BoxAcc) + (int64_t)ywords * 4);
-    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_BOXACC, acc_bytes);
+    // ... then the work-item counter (zeroed with them) and the list
+    T.chunks = (frame_w + kBoxCols - 1) / kBoxCols;
+    MLP_CHECK_ARG((int64_t)batch * m_rows < (1 << 20) && T.chunks < (1 << 12), "mlp_tile_summary: too many instances / chunks");
+    const int64_t acc_bytes = ((int64_t)batch * m_rows * (sizeof(BoxAcc) + (int64_t)ywords * 4) + 15) / 16 * 16 + 16;
+    const int64_t item_cap = (int64_t)batch * m_rows * T.chunks;
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_BOXACC, acc_bytes + item_cap * 4);
     if (rc) return rc;
     MLP_CUDA(cudaMemsetAsync(ctx->arena[MLP_ARENA_BOXACC], 0, (size_t)acc_bytes, st));
     T.acc = static_cast<BoxAcc*>(ctx->arena[MLP_ARENA_BOXACC]);
     T.acc_rowany = reinterpret_cast<uint32_t*>(T.acc + (int64_t)batch * m_rows);
-    T.chunks = kBoxSmallArea == INT_MAX ? (frame_w + kBoxCols - 1) / kBoxCols : (frame_w + 31) / 32;
-    const int64_t items = (int64_t)batch * m_rows * T.chunks + batch;
-    const int64_t cap = (int64_t)ctx->sm_count * 64;       // idle (instance, chunk) items are skipped in a loop
-    const int grid = (int)(items < cap ? items : cap);
+    T.n_items = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->arena[MLP_ARENA_BOXACC]) + acc_bytes - 16);
+    T.items = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->arena[MLP_ARENA_BOXACC]) + acc_bytes);
+    T.item_cap = (int)item_cap;
+    box_plan_kernel<<<batch, kReduceThreads, 0, st>>>(T);
+    MLP_LAUNCH_CHECK(ctx);
+    // one CTA per work item for the usual load (about one item per instance, a few more for wide boxes); the
+    // grid-stride loop of the kernel takes whatever exceeds it
+    const int64_t want = (int64_t)batch * m_rows + (int64_t)batch * m_rows / 4 + batch;
+    const int64_t cap = item_cap + batch;
+    const int grid = (int)(want < cap ? want : cap);
     box_summary_kernel<<<grid, kReduceThreads, 0, st>>>(T);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;

@@ -314,6 +314,43 @@ class PostProcessPipeline:
             self.frame_hw[0], self.frame_hw[1], mode, c.view(self.pasted), st))
         return self.det_i32, self.pasted, self.trim_m
 
+    def trim_and_clip(self, rois, roi_masks, pool_bytes=None):
+        """The second half with the masks in box-clipped form (csrc/clip.cu): TrimInstances + UpSampleOutput,
+        then per instance its clipped box and the bit rows of (CropAndPadMask value > 0.5) INSIDE that box - the
+        tf.pad zeros of misc.py:393-394 are never materialised.  Returns (det_i32 [B,K,6], geom int32 [B,K,8],
+        pool uint8 [capacity], used int64 [2] on the device): cfg-2 needs 2.4 MB of pool where the dense masks
+        are 1.68 GB.  `expand_clipped` rebuilds the dense [B,M,PH,PW] uint8 tensor bit for bit.  pool_bytes:
+        capacity of the pool (default: a bound that cannot overflow, B*K*PH*ceil(PW/8)); used[0] > capacity
+        reports an overflow (rows past the capacity were dropped)."""
+        c, lib, B, K, L = self.ctx, self.lib, self.B, self.K, self.L
+        if not self.cfg.fused:
+            raise rt.InvalidArgumentError(rt.MLP_EINVAL, "trim_and_clip needs the fused tail (fused=True)")
+        mh, mw = self.cfg.mask_size
+        PH, PW = self.frame_hw
+        r_cap = L * K
+        r_dev = ctypes.c_void_p(c.view(rois.level_m).value + 4 * L)
+        masks_ptr = c.view(roi_masks, torch.float32)
+        ratio = (torch.tensor([float(PH), float(PW)], dtype=torch.float32)
+                 / torch.tensor([float(self.image_hw[0]), float(self.image_hw[1])], dtype=torch.float32))
+        cap = int(pool_bytes) if pool_bytes is not None else int(lib.mlp_clip_pool_bound(B, K, PH, PW))
+        if getattr(self, "clip_cap", None) != cap:
+            self.clip_pool = c.empty(((cap + 15) // 16 * 16,), torch.uint8)
+            self.clip_geom = c.empty((B, K, 8), torch.int32)
+            self.clip_used = c.empty((2,), torch.int64)
+            self.clip_cap = cap
+        if self._fill_done is not None:                      # a background fill of this batch is in flight: join it
+            torch.cuda.current_stream(c.device).wait_event(self._fill_done)
+            self._fill_done = None
+        rt.check(lib.mlp_trim_paste(
+            c.handle, c.view(rois.roi_boxes), masks_ptr, B, r_cap, r_dev, mh, mw, self.C, float(ratio[0]),
+            float(ratio[1]), K, PH, PW, rt.MLP_PASTE_NONE | self._tail_flags, c.view(self.det_i32),
+            c.view(self.trim_counts), c.view(self.trim_m), ctypes.c_void_p(None), c.stream()))
+        rt.check(lib.mlp_clip_masks(
+            c.handle, c.view(self.det_i32), masks_ptr, r_cap, r_dev, self.C, c.view(self.trim_counts), B, K, mh, mw,
+            PH, PW, c.view(self.clip_geom), c.view(self.clip_pool), cap, c.view(self.clip_used), c.stream()))
+        self._compact_det = False
+        return self.det_i32, self.clip_geom, self.clip_pool, self.clip_used
+
     def trim_and_summarize(self, rois, roi_masks, seg_outs, default_road_size=3.25, threshold=0.1,
                            paste=False, split=False):
         """SURVEY 8(f) rank 1 fused behind the tail: TrimInstances + UpSampleOutput, then
@@ -536,3 +573,26 @@ class PostProcessPipeline:
             det = self.det_i32.view(self.B, self.K, 6)[:, :M]
         masks = self.pasted[:self.B * M * PH * self.paste_row].view(self.B, M, PH, self.paste_row)
         return det, masks
+
+
+def expand_clipped(geom, pool, frame_hw, m_rows=None):
+    """Host-side inverse of PostProcessPipeline.trim_and_clip: geom int32 [B,K,8] and the byte pool (NumPy arrays
+    or CPU tensors, e.g. what a client received) -> the dense uint8 {0,1} masks [B,M,PH,PW] CropAndPadMask + `> 0.5`
+    define (M = m_rows, default K).  Zero-fill, then OR every instance's bit rows into its clipped box."""
+    import numpy as np
+    geom = np.asarray(geom)
+    pool = np.asarray(pool, dtype=np.uint8)
+    B, K = geom.shape[:2]
+    M = K if m_rows is None else int(m_rows)
+    PH, PW = frame_hw
+    out = np.zeros((B, M, PH, PW), dtype=np.uint8)
+    for b in range(B):
+        for j in range(M):
+            xmin, ymin, w, h, lo, hi = (int(v) for v in geom[b, j, :6])
+            if w <= 0 or h <= 0:
+                continue
+            off = (lo & 0xffffffff) | ((hi & 0xffffffff) << 32)
+            rb = (w + 7) // 8
+            rows = pool[off:off + h * rb].reshape(h, rb)
+            out[b, j, ymin:ymin + h, xmin:xmin + w] = np.unpackbits(rows, axis=1, bitorder="little")[:, :w]
+    return out

@@ -119,6 +119,8 @@ SIGNATURES = {
                              ctypes.POINTER(DetectionParamsC), _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mlp_paste_prefill": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mlp_trim_paste": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mlp_clip_pool_bound": (_L, [_I, _I, _I, _I]),
+    "mlp_clip_masks": (_I, [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P]),
     "mlp_road_scan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mlp_summary_output": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _F, _P, _P, _P]),
     "mlp_tile_summary": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _I, _I,
