@@ -16,6 +16,24 @@
 
 #include "common.cuh"
 
+#ifdef MLP_NMS_TIMING
+// tuning build only (-DMLP_NMS_TIMING): %globaltimer at the phase boundaries of the NMS kernels, CTA 0
+__device__ unsigned long long g_nms_t[2][32];
+__device__ __forceinline__ void nms_mark(int kernel, int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_nms_t[kernel][slot] = t;
+    }
+}
+extern "C" int mlp_debug_nms_timing(unsigned long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, g_nms_t, sizeof(g_nms_t)) == cudaSuccess ? 0 : -2;
+}
+#define NMS_MARK(k, s) nms_mark(k, s)
+#else
+#define NMS_MARK(k, s) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kClassThreads = 512;          // K2: several CTAs per SM (B*C CTAs in one wave)
@@ -41,7 +59,8 @@ __device__ __forceinline__ BoxC corners_of(const float4 b) {
     return c;
 }
 
-// IoU(a,b) > thr, TF operation order, true division.
+// IoU(a,b) > thr, TF operation order, true division.  (A fast approximate division with an exact fall-back near
+// the threshold was measured: no gain - the chunk phases are not bound by the division, profiles/nms_phases_r02.txt.)
 __device__ __forceinline__ bool iou_exceeds(float aymin, float axmin, float aymax, float axmax,
                                             float aarea, float bymin, float bxmin, float bymax,
                                             float bxmax, float barea, float thr) {
@@ -254,28 +273,33 @@ __device__ void bitonic_sort_smem(uint64_t* s, int n_pow2) {
 __device__ void bitonic_sort_reg(uint64_t* s, int n_pow2) {
     const int t = threadIdx.x;
     const bool in = t < n_pow2;
+    const bool warp_in = (t & ~31) < n_pow2;           // warps wholly past the keys only keep the barriers company
     const uint64_t v0 = in ? s[t] : kKeyPad;
     uint32_t hi = (uint32_t)(v0 >> 32), lo = (uint32_t)v0;     // two 32-bit halves: shuffles and selects are 32-bit
     for (int k = 2; k <= n_pow2; k <<= 1) {
         const bool asc = (t & k) == 0;
         for (int j = k >> 1; j > 0; j >>= 1) {
-            uint32_t ohi, olo;
+            uint32_t ohi = hi, olo = lo;
             if (j >= 32) {
                 __syncthreads();                       // partners have read the previous exchange
                 if (in) s[t] = ((uint64_t)hi << 32) | lo;
                 __syncthreads();
-                const uint64_t o = in ? s[t ^ j] : kKeyPad;
-                ohi = (uint32_t)(o >> 32); olo = (uint32_t)o;
-            } else {
+                if (in) {
+                    const uint64_t o = s[t ^ j];
+                    ohi = (uint32_t)(o >> 32); olo = (uint32_t)o;
+                }
+            } else if (warp_in) {
                 ohi = __shfl_xor_sync(0xffffffffu, hi, j);
                 olo = __shfl_xor_sync(0xffffffffu, lo, j);
             }
-            // the lower index of a pair keeps the minimum in an ascending run, the maximum in a descending one
-            const bool take_min = asc == ((t & j) == 0);
-            const bool lt = hi < ohi || (hi == ohi && lo < olo);
-            const bool keep = lt == take_min;          // keys are unique: never equal
-            hi = keep ? hi : ohi;
-            lo = keep ? lo : olo;
+            if (warp_in) {
+                // the lower index of a pair keeps the minimum in an ascending run, the maximum in a descending one
+                const bool take_min = asc == ((t & j) == 0);
+                const bool lt = hi < ohi || (hi == ohi && lo < olo);
+                const bool keep = lt == take_min;      // keys are unique: never equal (pad lanes: equal, keep either)
+                hi = keep ? hi : ohi;
+                lo = keep ? lo : olo;
+            }
         }
     }
     __syncthreads();
@@ -373,7 +397,9 @@ __device__ inline NmsSmem carve_smem(unsigned char* base, int sort_cap, int max_
 // box by exactly one thread.  Returns the kept count (block-uniform).
 template <int kThreads, class Fetch, class Emit>
 __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
-                        int max_out, const NmsSmem& S, Fetch fetch, Emit emit, bool staged = false) {
+                        int max_out, const NmsSmem& S, Fetch fetch, Emit emit, bool staged = false, int tk = 0) {
+    (void)tk;
+    int mark_chunk = 8;
     constexpr int kLanesPerCand = kThreads / kChunk;   // threads that split the kept list
     static_assert(kThreads % kChunk == 0 && kChunk % kLanesPerCand == 0 && kChunk == 64, "bad NMS geometry");
     const int tid = threadIdx.x;
@@ -413,8 +439,12 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
         __syncthreads();
         for (int i = sc + tid; i < p2; i += blockDim.x) S.skeys[i] = kKeyPad;
         __syncthreads();
+        NMS_MARK(tk, 2);
+        // (a rank sort - every key counts the smaller ones, one scatter - was measured at 7.4 us against the 4.9 us of
+        // the register network for 512 keys: profiles/nms_phases_r02.txt)
         if (p2 <= (int)blockDim.x) bitonic_sort_reg(S.skeys, p2);
         else bitonic_sort_smem(S.skeys, p2);
+        NMS_MARK(tk, 3);
         lo = S.skeys[sc - 1];
         done += sc;
 
@@ -431,6 +461,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 S.c_area[i] = c.area;
             }
             __syncthreads();                          // c_* of this block are in shared memory
+            NMS_MARK(tk, 4);
             // ---- chunks of kChunk (= 64) candidates, two barriers each ----
             // phase 1 (all threads): candidate t against the kept list (its slice r of it) AND against the
             //   earlier candidates of the chunk - the two do not depend on each other: a mask bit that
@@ -470,6 +501,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                     if (hi) atomicOr(&c_mask[t * 2 + 1], hi);
                 }
                 __syncthreads();
+                if (mark_chunk < 12) NMS_MARK(tk, 16 + 3 * (mark_chunk - 8));
                 if (tid < 32) {
                     // sequential resolve.  Rows live in registers (lane l: candidates l and l+32) and reach
                     // every lane by shuffle, so the loop-carried chain is two ANDs, a compare and an OR per
@@ -479,23 +511,29 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                     const uint32_t rowA_lo = c_mask[tid * 2];
                     const uint32_t rowB_lo = c_mask[(tid + 32) * 2];
                     const uint32_t rowB_hi = c_mask[(tid + 32) * 2 + 1];
+                    // the cap max_out stays off the loop-carried chain: resolve as if there were none, then keep only
+                    // the first (max_out - kept) winners - earlier decisions never depend on later candidates
                     uint32_t kept_lo = 0, kept_hi = 0;
-                    int k = kept;
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         const uint32_t rl = __shfl_sync(0xffffffffu, rowA_lo, q);
-                        const bool keep = ((alive_lo >> q) & 1u) && !(rl & kept_lo) && (k < max_out);
-                        if (keep) { kept_lo |= 1u << q; ++k; }
+                        const uint32_t bit = alive_lo & (1u << q);
+                        kept_lo |= (rl & kept_lo) ? 0u : bit;
                     }
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         const uint32_t rl = __shfl_sync(0xffffffffu, rowB_lo, q);
                         const uint32_t rh = __shfl_sync(0xffffffffu, rowB_hi, q);
-                        const bool keep = ((alive_hi >> q) & 1u) && !((rl & kept_lo) | (rh & kept_hi)) &&
-                                          (k < max_out);
-                        if (keep) { kept_hi |= 1u << q; ++k; }
+                        const uint32_t bit = alive_hi & (1u << q);
+                        kept_hi |= ((rl & kept_lo) | (rh & kept_hi)) ? 0u : bit;
                     }
+                    int room = max_out - kept;
+                    if (__popc(kept_lo) > room) kept_lo = room > 0 ? kept_lo & ((2u << __fns(kept_lo, 0, room)) - 1u) : 0u;
+                    room -= __popc(kept_lo);
+                    if (__popc(kept_hi) > room) kept_hi = room > 0 ? kept_hi & ((2u << __fns(kept_hi, 0, room)) - 1u) : 0u;
+                    const int k = kept + __popc(kept_lo) + __popc(kept_hi);
                     if (tid == 0) S.misc[0] = k;
+                    if (mark_chunk < 12) NMS_MARK(tk, 17 + 3 * (mark_chunk - 8));
                     // append the newly kept boxes in order and emit them (lane l: candidates l and l+32)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -510,6 +548,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                             emit(rank, S.skeys[pb + base + cand], S.c_box[base + cand]);
                         }
                     }
+                    if (mark_chunk < 12) NMS_MARK(tk, 18 + 3 * (mark_chunk - 8));
                 } else if (tid < 32 + kChunk) {
                     const int i = tid - 32;            // clear the other half for the next chunk
                     S.c_supp[(buf ^ 1) * kChunk + i] = 0;
@@ -519,6 +558,7 @@ __device__ int nms_core(const uint64_t* gkeys, int cnt, int sort_cap, float thr,
                 __syncthreads();
                 kept = S.misc[0];
                 buf ^= 1;
+                if (mark_chunk < 30) NMS_MARK(tk, mark_chunk++);
             }
         }
     }
@@ -559,6 +599,7 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
                      int N, int C, float thr, int max_out, int sort_cap, DetScratch D) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
+    NMS_MARK(0, 0);
     const int g = blockIdx.x;
     const int b = g / C;
     int cnt = D.cand_count[g];
@@ -592,6 +633,7 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
         if (threadIdx.x == 0) D.cls_kept[g] = 0;
         return;
     }
+    NMS_MARK(0, 1);
     float4* rec_box = D.rec_box + (int64_t)g * max_out;
     int4* rec_sn = D.rec_sn + (int64_t)g * max_out;
     auto emit = [&](int rank, uint64_t key, const float4& bx) {
@@ -607,6 +649,7 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
         kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
     }
     if (threadIdx.x == 0) D.cls_kept[g] = kept;
+    NMS_MARK(0, 31);
 }
 
 // ------------------------------------------------------------------ K3 -------
@@ -634,6 +677,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     __shared__ int s_off[257];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
+    NMS_MARK(1, 0);
     // groups of this image in first-appearance order: sort by (min_n, c).  The per-class scalars are
     // fetched by C threads at once (one round trip), thread 0 orders them out of shared memory.
     __shared__ int s_cnt[256], s_min[256], s_kept[256];
@@ -673,6 +717,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     float4* cat_box = D.cat_box + cat_base;
     int2* cat_sn = D.cat_sn + cat_base;
     int32_t* cat_c = D.cat_c + cat_base;
+    NMS_MARK(1, 1);
     const bool staged = total <= sort_cap;
     const bool tma = use_tma && staged && total > 0 && total <= kStageCap;      // CTA-uniform
     float* det_b = det + (int64_t)b * max_out * 6;
@@ -716,7 +761,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
             if (keep_b) { keep_b[rank * 2] = sn.y; keep_b[rank * 2 + 1] = c; }
         };
         FetchCat f{t_box};
-        kept = nms_core<kCrossThreads>(nullptr, total, sort_cap, thr, max_out, S, f, emit, true);
+        kept = nms_core<kCrossThreads>(nullptr, total, sort_cap, thr, max_out, S, f, emit, true, 1);
     } else {
     // concatenation, flat over the survivors (one round of loads): position p -> (group gi, rank i)
     for (int p = tid; p < total; p += blockDim.x) {
@@ -751,9 +796,10 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     };
     if (total > 0) {
         FetchCat f{cat_box};
-        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged);
+        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged, 1);
     }
     }
+    NMS_MARK(1, 30);
     // -1 padding of the unused rows (MoldBatch, misc.py:276-283)
     for (int i = kept * 6 + tid; i < max_out * 6; i += blockDim.x) det_b[i] = -1.0f;
     if (keep_b)

@@ -781,7 +781,9 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
         if (const char* e = getenv("MLP_TAIL_TMA")) tma = tma && atoi(e) != 0;              // A/B knob
         if (tma) {
             // at most two tiles per warp: one wave of CTAs, enough bytes in flight per SM
-            int parts = (k_rows + 2 * kPrepTmaWarps - 1) / (2 * kPrepTmaWarps);
+            int per_warp = 2;                                                             // tuning knob
+            if (const char* e = getenv("MLP_TAIL_SLOTS_PER_WARP")) per_warp = atoi(e) > 0 ? atoi(e) : 2;
+            int parts = (k_rows + per_warp * kPrepTmaWarps - 1) / (per_warp * kPrepTmaWarps);
             parts = parts < 1 ? 1 : (parts > 64 ? 64 : parts);
             const size_t smem = (size_t)slot_bytes * kPrepTmaWarps;
             MLP_CUDA(cudaFuncSetAttribute(tail_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
