@@ -471,11 +471,14 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
     int32_t* src = tail_src + (int64_t)b * K;
     const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
                                         s_cnt, s_base, s_cm, Q, b);
-    if (threadIdx.x == 0 && part == 0) {
-        int m = INT_MIN;
-        for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
-        counts[b] = total;
-        confmax[b] = m;
+    if (part == 0) {                                  // one CTA per image publishes its count / confidence maximum and
+        if (threadIdx.x == 0) {                       // arrives; the last image reduces M and the row-filter threshold
+            int m = INT_MIN;                          // while every CTA's tile copies are still in flight
+            for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
+            counts[b] = total;
+            confmax[b] = m;
+        }
+        tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x, m_out);
     }
     const int px = mh * mw;
     unsigned char* stage = s_stage + (size_t)warp * slot_bytes;
@@ -517,7 +520,6 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
         }
         __syncwarp();
     }
-    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y, m_out);
 }
 
 // Register-gather form of the tail preparation (the fallback of tail_prep_tma_kernel: RoI blocks that are
@@ -539,11 +541,14 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
     int32_t* src = tail_src + (int64_t)b * K;
     const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
                                         s_cnt, s_base, s_cm, Q, b);
-    if (threadIdx.x == 0 && part == 0) {
-        int m = INT_MIN;
-        for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
-        counts[b] = total;
-        confmax[b] = m;
+    if (part == 0) {
+        if (threadIdx.x == 0) {
+            int m = INT_MIN;
+            for (int w = 0; w < kWarps; ++w) m = max(m, s_cm[w]);
+            counts[b] = total;
+            confmax[b] = m;
+        }
+        tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x, m_out);
     }
     // bit tiles of this CTA's slots: one warp per slot, lane = mask column, ballot per mask row
     const int px = mh * mw;
@@ -570,7 +575,6 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
             }
         }
     }
-    tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x * gridDim.y, m_out);
 }
 
 // ---- boxes-only paste: walks the work items of the tail preparation behind a background fill --------

@@ -149,7 +149,8 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
     if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
 }
 
-// Last step of the tail preparation: the CTA that arrives last (all counts[] / confmax[] are written) reduces
+// Part of the tail preparation, called by ONE CTA per image right after it has published counts[b] / confmax[b]
+// (before its tile copies, so the reduction is off the kernel's critical path): the CTA that arrives last reduces
 // M = max(1, max counts) and CropAndPadMask's row-filter threshold (misc.py:366-369) ONCE, so that the 25,600
 // short CTAs of the paste kernel read two words instead of repeating the reduction.  scalars[2] is the arrival
 // counter; the last CTA resets it for the next launch.  Every thread of the CTA calls this.

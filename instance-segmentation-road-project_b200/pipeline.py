@@ -506,6 +506,7 @@ class PostProcessPipeline:
         with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.ctx.device, priority=-1)):
             rois = self.detect_and_align(loc_pred, cls_pred, fmaps, prefill=prefill)
             self.trim_and_paste(rois, roi_masks)
+        graph._mlp_owner = self                             # the graph replays into this pipeline's buffers and scratch
         return graph, rois
 
     def capture_serving(self, loc_pred, cls_pred, fmaps, roi_masks, seg_outs, images, instance_colors,
@@ -561,6 +562,7 @@ class PostProcessPipeline:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             rois = run()
+        graph._mlp_owner = self                             # the graph replays into this pipeline's buffers and scratch
         return graph, rois
 
     def result_views(self):
