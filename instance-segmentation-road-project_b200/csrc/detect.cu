@@ -590,13 +590,36 @@ struct DetScratch {
     float4* cat_box;         // [B][C*max_out]
     int2* cat_sn;            // [B][C*max_out] (score bits, n)
     int32_t* cat_c;          // [B][C*max_out]
+    int32_t* img_done;       // [B] arrival counters of the fused cross-class pass
+    int64_t zero_bytes;      // cand_count .. img_done: zeroed with one memset per call
     int64_t cap;
 };
+
+// Arguments of the cross-class pass when it is fused behind the per-class NMS: the class CTA of an image that
+// finishes last (arrival counter per image) runs the image's cross-class NMS itself, so the second kernel - its
+// launch, its drain and its 32-CTA grid - disappears and early images do not wait for late ones.
+struct CrossArgs {
+    int fuse;
+    float thr;
+    int sort_cap;
+    float* det;
+    int32_t* keep;
+    int32_t* counts;
+    int32_t* m_dev;
+    int32_t* img_done;       // [B] arrival counters, zero before the launch; the last CTA resets its image's
+    FusedPlan F;
+};
+
+template <int kThreads>
+__device__ void cross_class_body(unsigned char* smem_raw, int b, int B, int C, float thr, int max_out, int sort_cap,
+                                 const DetScratch& D, float* __restrict__ det, int32_t* __restrict__ keep,
+                                 int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan& F,
+                                 int use_tma);
 
 template <bool kDecode>
 __global__ void __launch_bounds__(kClassThreads, 2)
 nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restrict__ boxes_or_loc,
-                     int N, int C, float thr, int max_out, int sort_cap, DetScratch D) {
+                     int N, int C, float thr, int max_out, int sort_cap, DetScratch D, const CrossArgs X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
     NMS_MARK(0, 0);
@@ -631,25 +654,37 @@ nms_per_class_kernel(const __grid_constant__ PriorDev P, const float4* __restric
     }
     if (cnt == 0) {
         if (threadIdx.x == 0) D.cls_kept[g] = 0;
-        return;
-    }
-    NMS_MARK(0, 1);
-    float4* rec_box = D.rec_box + (int64_t)g * max_out;
-    int4* rec_sn = D.rec_sn + (int64_t)g * max_out;
-    auto emit = [&](int rank, uint64_t key, const float4& bx) {
-        rec_box[rank] = bx;
-        rec_sn[rank] = make_int4(__float_as_int(key_score(key)), (int)(uint32_t)key, 0, 0);
-    };
-    int kept;
-    if (kDecode) {
-        FetchDecode f{&P, boxes_or_loc + (int64_t)b * N};
-        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
     } else {
-        FetchBoxes f{boxes_or_loc + (int64_t)b * N};
-        kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
+        NMS_MARK(0, 1);
+        float4* rec_box = D.rec_box + (int64_t)g * max_out;
+        int4* rec_sn = D.rec_sn + (int64_t)g * max_out;
+        auto emit = [&](int rank, uint64_t key, const float4& bx) {
+            rec_box[rank] = bx;
+            rec_sn[rank] = make_int4(__float_as_int(key_score(key)), (int)(uint32_t)key, 0, 0);
+        };
+        int kept;
+        if (kDecode) {
+            FetchDecode f{&P, boxes_or_loc + (int64_t)b * N};
+            kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
+        } else {
+            FetchBoxes f{boxes_or_loc + (int64_t)b * N};
+            kept = nms_core<kClassThreads>(gkeys, cnt, sort_cap, thr, max_out, S, f, emit, staged);
+        }
+        if (threadIdx.x == 0) D.cls_kept[g] = kept;
     }
-    if (threadIdx.x == 0) D.cls_kept[g] = kept;
     NMS_MARK(0, 31);
+    if (!X.fuse) return;
+    // ---- arrival: the last class of image b to finish runs the image's cross-class pass (CTA-uniform branch)
+    __shared__ int s_is_last;
+    __threadfence();                                   // this group's records are visible before it arrives
+    __syncthreads();
+    if (threadIdx.x == 0) s_is_last = atomicAdd(X.img_done + b, 1) == C - 1;
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) X.img_done[b] = 0;           // ready for the next launch
+    cross_class_body<kClassThreads>(smem_raw, b, gridDim.x / C, C, X.thr, max_out, X.sort_cap, D, X.det, X.keep,
+                                    X.counts, X.m_dev, X.F, 0);
 }
 
 // ------------------------------------------------------------------ K3 -------
@@ -662,11 +697,11 @@ struct FetchCat {
 // exists: every class's survivors are one contiguous run of 16-byte records).  kStageCap survivors at most.
 constexpr int kStageCap = kBlock;
 
-__global__ void __launch_bounds__(kCrossThreads, 1)
-nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D,
-                       float* __restrict__ det, int32_t* __restrict__ keep,
-                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan F, int use_tma) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int kThreads>
+__device__ void cross_class_body(unsigned char* smem_raw, int b, int B, int C, float thr, int max_out, int sort_cap,
+                                 const DetScratch& D, float* __restrict__ det, int32_t* __restrict__ keep,
+                                 int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan& F,
+                                 int use_tma) {
     NmsSmem S = carve_smem(smem_raw, sort_cap, max_out);
     // behind the NMS work space: staging area of the bulk copies, boxes then (score, anchor) records
     float4* t_box = reinterpret_cast<float4*>(smem_raw + ((nms_smem_bytes(sort_cap, max_out) + 127) & ~(size_t)127));
@@ -675,16 +710,15 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     __shared__ unsigned char s_cat_c[kStageCap];
     __shared__ int s_order[256];
     __shared__ int s_off[257];
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
     NMS_MARK(1, 0);
     // groups of this image in first-appearance order: sort by (min_n, c).  The per-class scalars are
     // fetched by C threads at once (one round trip), thread 0 orders them out of shared memory.
     __shared__ int s_cnt[256], s_min[256], s_kept[256];
     if (tid < C) {
-        s_cnt[tid] = D.cand_count[b * C + tid];
-        s_min[tid] = D.min_n[b * C + tid];
-        s_kept[tid] = D.cls_kept[b * C + tid];
+        s_cnt[tid] = __ldcg(D.cand_count + b * C + tid);     // .cg: siblings of the same launch wrote these when fused
+        s_min[tid] = __ldcg(D.min_n + b * C + tid);
+        s_kept[tid] = __ldcg(D.cls_kept + b * C + tid);
     }
     __syncthreads();
     if (tid == 0) {
@@ -761,7 +795,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
             if (keep_b) { keep_b[rank * 2] = sn.y; keep_b[rank * 2 + 1] = c; }
         };
         FetchCat f{t_box};
-        kept = nms_core<kCrossThreads>(nullptr, total, sort_cap, thr, max_out, S, f, emit, true, 1);
+        kept = nms_core<kThreads>(nullptr, total, sort_cap, thr, max_out, S, f, emit, true, 1);
     } else {
     // concatenation, flat over the survivors (one round of loads): position p -> (group gi, rank i)
     for (int p = tid; p < total; p += blockDim.x) {
@@ -771,8 +805,8 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
         const int64_t src = (int64_t)(b * C + c) * max_out + (p - s_off[gi]);
         MLP_BOUND(p, C * max_out);
         MLP_BOUND(p - s_off[gi], max_out);
-        const float4 bx = D.rec_box[src];
-        const int4 sn4 = D.rec_sn[src];
+        const float4 bx = __ldcg(D.rec_box + src);
+        const int4 sn4 = __ldcg(D.rec_sn + src);
         const int2 sn = make_int2(sn4.x, sn4.y);
         cat_box[p] = bx;
         cat_sn[p] = sn;
@@ -796,7 +830,7 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     };
     if (total > 0) {
         FetchCat f{cat_box};
-        kept = nms_core<kCrossThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged, 1);
+        kept = nms_core<kThreads>(cat_keys, total, sort_cap, thr, max_out, S, f, emit, staged, 1);
     }
     }
     NMS_MARK(1, 30);
@@ -812,7 +846,6 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     // ---- fused MaskDistribute + RoIAlign plan for this image
     __shared__ int s_lvl[MLP_MAX_KEEP];
     __syncthreads();                               // det_b rows written by other threads
-    const int B = gridDim.x;
     for (int r = tid; r < max_out; r += blockDim.x) {
         float* drow = F.dist + ((int64_t)b * max_out + r) * 7;
         int lv = -1;
@@ -851,6 +884,17 @@ nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D
     }
 }
 
+// The cross-class pass as a kernel of its own: one CTA per image (used when it cannot ride behind the per-class
+// kernel: survivors that do not fit that kernel's shared memory, or MLP_NMS_FUSE=0).
+__global__ void __launch_bounds__(kCrossThreads, 1)
+nms_cross_class_kernel(int C, float thr, int max_out, int sort_cap, DetScratch D,
+                       float* __restrict__ det, int32_t* __restrict__ keep,
+                       int32_t* __restrict__ counts, int32_t* __restrict__ m_dev, const FusedPlan F, int use_tma) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cross_class_body<kCrossThreads>(smem_raw, blockIdx.x, gridDim.x, C, thr, max_out, sort_cap, D, det, keep, counts,
+                                    m_dev, F, use_tma);
+}
+
 // ------------------------------------------------------------ host side ------
 struct DetPlan {
     DetScratch D;
@@ -866,6 +910,7 @@ int plan_scratch(mlp_ctx* ctx, int B, int64_t N, int C, int max_out, DetScratch*
     auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 256); return o; };
     const int64_t o_keys = take(G * cap * 8);
     const int64_t o_count = take(G * 4);
+    const int64_t o_done = take((int64_t)B * 4);                  // directly behind cand_count: one memset covers both
     const int64_t o_kept = take(G * 4);
     const int64_t o_minn = take(G * 4);
     const int64_t o_rbox = take(G * max_out * 16);
@@ -879,6 +924,8 @@ int plan_scratch(mlp_ctx* ctx, int B, int64_t N, int C, int max_out, DetScratch*
     char* base = static_cast<char*>(ctx->arena[MLP_ARENA_DETECT]);
     out->cand_keys = reinterpret_cast<uint64_t*>(base + o_keys);
     out->cand_count = reinterpret_cast<int32_t*>(base + o_count);
+    out->img_done = reinterpret_cast<int32_t*>(base + o_done);
+    out->zero_bytes = o_done + (int64_t)B * 4 - o_count;
     out->cls_kept = reinterpret_cast<int32_t*>(base + o_kept);
     out->min_n = reinterpret_cast<int32_t*>(base + o_minn);
     out->rec_box = reinterpret_cast<float4*>(base + o_rbox);
@@ -932,7 +979,7 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
     int rc = plan_scratch(ctx, B, N, C, max_out, &D);
     if (rc) return rc;
     const int G = B * C;
-    MLP_CUDA(cudaMemsetAsync(D.cand_count, 0, (size_t)G * 4, stream));
+    MLP_CUDA(cudaMemsetAsync(D.cand_count, 0, (size_t)D.zero_bytes, stream));
 
     // K1: stream cls_pred once
     {
@@ -954,29 +1001,48 @@ int detection_impl(mlp_ctx* ctx, const mlp_prior_config* prior, int height, int 
                                                           fp.enabled ? fp.L + 1 : 0);
         MLP_LAUNCH_CHECK(ctx);
     }
-    // K2: per (image,class) NMS.  512-thread CTAs, <= 72 KB smem -> 3 CTAs per SM, so all
-    // B*C groups (160-192 at batch 32) are resident in a single wave on 148 SMs.
+    // K2: per (image,class) NMS.  512-thread CTAs, <= 74 KB smem -> 2-3 CTAs per SM, so all
+    // B*C groups (160-192 at batch 32) are resident in a single wave on 148 SMs.  When an image's survivors
+    // (<= C * max_out) fit the same shared memory, the cross-class pass rides behind it (CrossArgs).
+    const int sort_cap2 = pick_sort_cap(4096, max_out, 74 * 1024);
+    const size_t smem2 = nms_smem_bytes(sort_cap2, max_out);
+    int cross_cap = 256;
+    while (cross_cap < C * max_out) cross_cap <<= 1;
+    // Measured (profiles/nms_fuse_ab_r02.txt): eager launches save 3 us per batch, but inside a CUDA graph - where a
+    // kernel boundary costs next to nothing - the fused form is no faster (425 vs 422 us per batch alone at cfg-2,
+    // 108.9 vs 109.2 us at batch 1) because the cross-class pass then runs on 512 threads instead of 1024.  Off unless
+    // MLP_NMS_FUSE=1; both forms are covered by the GPU tests.
+    bool fuse = false;
+    if (const char* e = getenv("MLP_NMS_FUSE")) fuse = atoi(e) != 0;
+    fuse = fuse && nms_smem_bytes(cross_cap, max_out) <= smem2 && C <= 256;
     {
         ProfScope prof(ctx, MLP_ST_NMS_CLASS, stream);
-        const int sort_cap = pick_sort_cap(4096, max_out, 74 * 1024);
-        const size_t smem = nms_smem_bytes(sort_cap, max_out);
+        CrossArgs X;
+        memset(&X, 0, sizeof(X));
+        X.fuse = fuse ? 1 : 0;
+        X.thr = p->post_iou_threshold;
+        X.sort_cap = cross_cap;
+        X.det = det_dev; X.keep = keep_dev; X.counts = counts_dev; X.m_dev = m_dev;
+        X.img_done = D.img_done;
+        X.F = fp;
         if (prior) {
             MLP_CUDA(cudaFuncSetAttribute(nms_per_class_kernel<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            nms_per_class_kernel<true><<<G, kClassThreads, smem, stream>>>(
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            nms_per_class_kernel<true><<<G, kClassThreads, smem2, stream>>>(
                 P, reinterpret_cast<const float4*>(boxes_or_loc_dev), (int)N, C, p->nms_iou_threshold,
-                max_out, sort_cap, D);
+                max_out, sort_cap2, D, X);
         } else {
             MLP_CUDA(cudaFuncSetAttribute(nms_per_class_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            nms_per_class_kernel<false><<<G, kClassThreads, smem, stream>>>(
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            nms_per_class_kernel<false><<<G, kClassThreads, smem2, stream>>>(
                 P, reinterpret_cast<const float4*>(boxes_or_loc_dev), (int)N, C, p->nms_iou_threshold,
-                max_out, sort_cap, D);
+                max_out, sort_cap2, D, X);
         }
         MLP_LAUNCH_CHECK(ctx);
     }
-    // K3: cross-class NMS per image; sort buffer sized for C*max_out survivors when it fits.
-    {
+    // K3: cross-class NMS per image as its own kernel when it could not be fused; sort buffer sized for
+    // C*max_out survivors when it fits.
+    if (!fuse) {
         ProfScope prof(ctx, MLP_ST_NMS_CROSS, stream);
         const int sort_cap = pick_sort_cap(C * max_out, max_out, 180 * 1024);
         const size_t smem = ((nms_smem_bytes(sort_cap, max_out) + 127) & ~(size_t)127) + (size_t)kStageCap * 32;

@@ -262,3 +262,41 @@ def test_speculative_fill_follows_a_changing_m():
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (step, mu)
         seen.append(int(fast.trim_m.item()))
     assert len(set(seen)) >= 3 and min(seen) == 1, seen            # M really moved both ways
+
+
+@pytest.mark.parametrize("seed", [0, 3, 7, 11])
+def test_fused_cross_class_nms_equals_oracle(seed):
+    """MLP_NMS_FUSE=1: the last class CTA of an image to finish runs the image's cross-class NMS (no second kernel).
+    Same detections, RoIs and masks as the C oracle, incl. images without candidates and single-class images."""
+    import masklab_b200 as ml
+    rng = np.random.default_rng(seed)
+    B, H, W, C, Cf = int(rng.integers(1, 6)), 96, 160, int(rng.integers(1, 7)), 8
+    cfgp = synth.prior_config(strides=(8, 16, 32))
+    N = synth.num_anchors(cfgp, H, W)
+    loc, cls = synth.head_tensors(B, N, C, mu=float(rng.choice([-4.0, -3.0, -2.0])), seed=100 + seed)
+    if B > 1:
+        cls[0] = 0
+    if B > 2 and C > 1:
+        cls[2, :, 1:] = 0
+    fmaps = synth.fpn_maps(B, H, W, Cf, seed=200 + seed)
+    kw = dict(min_confidence=0.05, nms_iou_threshold=0.4, post_iou_threshold=0.65,
+              nms_max_output_size=int(rng.choice([5, 40, 300])), max_k=2, base_size=36)
+    os.environ["MLP_NMS_FUSE"] = "1"
+    try:
+        pipe = ml.PostProcessPipeline(cfgp, (H, W), (H, W), C, Cf, B, ml.DetectionConfig(**kw))
+        rois = pipe.detect_and_align(_d(loc), _d(cls), [_d(f) for f in fmaps])
+        _, R = rois.shapes()
+        probs = synth.mask_probs(B, R, C, seed=300 + seed)
+        pipe.trim_and_paste(rois, _d(probs))
+        det_i, pasted = pipe.result_views()
+        M = int(rois.m_dev.item())
+        got_det = rois.det[:, :M].cpu().numpy()
+        # stand-alone layer (boxes given, no prior decode) through the same kernels
+        boxes = co.restore_boxes(loc, np.broadcast_to(co.prior_layer(cfgp, H, W)[None], (B, N, 4)))
+        layer = ml.DetectionProposal(**{k: kw[k] for k in ("min_confidence", "nms_iou_threshold", "post_iou_threshold",
+                                                           "nms_max_output_size")})([_d(cls), _d(boxes), None])
+    finally:
+        os.environ.pop("MLP_NMS_FUSE", None)
+    want = co.full_path(loc, cls, fmaps, lambda f, b: probs, cfgp, (H, W), (H, W), binary=True, **kw)
+    assert np.array_equal(got_det, want["proposed"]) and np.array_equal(layer.cpu().numpy(), want["proposed"])
+    assert np.array_equal(det_i.cpu().numpy(), want["det_i"]) and np.array_equal(pasted.cpu().numpy(), want["binary"])
