@@ -93,6 +93,10 @@ class PostProcessPipeline:
         H, W = self.image_hw
         self.fmap_hw = [((H + s - 1) // s if same else H // s, (W + s - 1) // s if same else W // s)
                         for s, _ in groups[:self.L]]
+        if any(h < 1 or w < 1 for h, w in self.fmap_hw):
+            raise rt.InvalidArgumentError(
+                rt.MLP_EINVAL, f"pyramid level without a single cell for a {H}x{W} image with padding="
+                f"{self.cfg.padding!r}: {self.fmap_hw} (tf.image.crop_and_resize rejects an empty image too)")
         self.params = rt.DetectionParamsC(
             float(self.cfg.min_confidence), float(self.cfg.nms_iou_threshold),
             float(self.cfg.post_iou_threshold), self.K, 1 if self.cfg.strict_batch else 0)
