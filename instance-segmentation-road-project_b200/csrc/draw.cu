@@ -166,9 +166,16 @@ pack_tiles_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int 
     }
 }
 
-constexpr int kBlkH = 16, kBlkW = 64;     // pixel block of a CTA: 16 rows x 16 threads x 4 pixels
+#ifndef MLP_DRAW_MIN_CTAS
+#define MLP_DRAW_MIN_CTAS 4
+#endif
+#ifndef MLP_DRAW_ROWS
+#define MLP_DRAW_ROWS 4
+#endif
+constexpr int kRowsPT = MLP_DRAW_ROWS;    // adjacent frame rows per thread
+constexpr int kBlkH = 16 * kRowsPT, kBlkW = 64;     // pixel block of a CTA: 16 x 16 threads, kRowsPT rows x 4 pixels each
 constexpr int kMaxCand = 1024;            // instances touching one block kept in shared memory (indices)
-constexpr int kGeomCache = 32;            // ... of which the first ones with their geometry
+constexpr int kGeomCache = 64;            // ... of which the first ones with their geometry (the fast path)
 
 struct DrawTilesArgs {
     const void* images;
@@ -183,50 +190,85 @@ struct DrawTilesArgs {
     int line_words;
 };
 
-// 4 consecutive channel-interleaved pixels (12 values) of a frame row as float
-__device__ __forceinline__ void load_px12(const uint8_t* p, bool vec, int n, float* v) {
-    if (vec) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+// 4 consecutive channel-interleaved pixels (12 values) of a frame row: the raw words of the load (issued early) and
+// their float values (taken when the arithmetic starts)
+template <typename ImgT> struct PxRaw;
+template <> struct PxRaw<uint8_t> {
+    uint32_t u[3];
+    __device__ __forceinline__ void load(const uint8_t* p, bool vec, int n) {
+        if (vec) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t u = __ldg(w + k);
+            for (int k = 0; k < 3; ++k) u[k] = __ldg(reinterpret_cast<const uint32_t*>(p) + k);
+        } else {
+            u[0] = u[1] = u[2] = 0u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[k * 4 + i] = (float)((u >> (8 * i)) & 0xffu);
+            for (int i = 0; i < 12; ++i)
+                if (i < 3 * n) u[i >> 2] |= (uint32_t)__ldg(p + i) << (8 * (i & 3));
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = i < 3 * n ? (float)__ldg(p + i) : 0.0f;
     }
-}
-__device__ __forceinline__ void load_px12(const float* p, bool vec, int n, float* v) {
-    if (vec) {
+    __device__ __forceinline__ void pixels(float* v, bool) const {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(p) + k);
-            v[k * 4] = f.x; v[k * 4 + 1] = f.y; v[k * 4 + 2] = f.z; v[k * 4 + 3] = f.w;
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)                    // byte -> float as (2^23 + byte) - 2^23: no int->float conversion
+                v[k * 4 + i] = __fsub_rn(__uint_as_float(__byte_perm(u[k], 0x4B000000u, 0x7650u + i)), 8388608.0f);
+    }
+};
+template <> struct PxRaw<float> {
+    float f[12];
+    __device__ __forceinline__ void load(const float* p, bool vec, int n) {
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p) + k);
+                f[k * 4] = t.x; f[k * 4 + 1] = t.y; f[k * 4 + 2] = t.z; f[k * 4 + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) f[i] = i < 3 * n ? __ldg(p + i) : 0.0f;
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = i < 3 * n ? __ldg(p + i) : 0.0f;
     }
-}
+    __device__ __forceinline__ void pixels(float* v, bool) const {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = f[i];
+    }
+};
+template <typename T> __device__ __forceinline__ constexpr bool is_float_seg() { return false; }
+template <> __device__ __forceinline__ constexpr bool is_float_seg<float>() { return true; }
+__device__ __forceinline__ float clip255(float v) { return fminf(fmaxf(v, 0.0f), 255.0f); }   // clip_by_value(., 0, 255)
 __device__ __forceinline__ float seg_f32(const int32_t* p) { return (float)__ldg(p); }
 __device__ __forceinline__ float seg_f32(const float* p) { return __ldg(p); }
 template <typename T> __device__ __forceinline__ float seg_word(uint32_t w);          // one element of a 128-bit load
 template <> __device__ __forceinline__ float seg_word<float>(uint32_t w) { return __uint_as_float(w); }
 template <> __device__ __forceinline__ float seg_word<int32_t>(uint32_t w) { return (float)(int32_t)w; }
 
+// A value v in [0, 255] truncated toward zero, as the float 2^23 + trunc(v): an add with round-toward-zero against
+// 2^23 (ulp 1 there) drops the fraction.  Its low byte is the uint8 the reference's cast produces; subtracting 2^23
+// again gives that integer back as a float, exactly - both without a float<->int conversion.
+constexpr float kTwo23 = 8388608.0f;
+__device__ __forceinline__ float trunc_magic(float v) { return __fadd_rz(v, kTwo23); }
+
 // kCs: semantic classes known at compile time (0 = no semantic overlay, 3 = the serving graph's three
 // classes with their colours in registers and 128-bit map loads, -1 = any number, generic loop).
+//
+// One CTA per 64x64 pixel block; a thread owns 4 adjacent rows x 4 pixels.  The instances whose clipped box touches
+// the block are found once per CTA (ordered compaction) and grouped by class; for each of them a thread computes the
+// x half of the resize (source columns as single-bit masks, lx) once for its four pixels and walks its four rows with
+// it.  The tiles are {0,1} bit rows, so the x lerp tl + (tr - tl) * lx of a row is one of 0, lx, fadd(1, -lx), 1 -
+// picked by the two corner bits, bit-identical to the arithmetic.  What a thread keeps per pixel is only WHICH classes
+// passed sum > 0.5 (16 bits); the colour sums are rebuilt in class order at blend time.
 template <typename ImgT, typename SegT, int kCs>
-__global__ void __launch_bounds__(kDrawThreads)
+__global__ void __launch_bounds__(kDrawThreads, MLP_DRAW_MIN_CTAS)
 draw_tiles_kernel(const DrawTilesArgs A) {
     __shared__ unsigned short s_cand[kMaxCand];            // instances touching the block, instance order
     __shared__ signed char s_cls[kMaxCand];
     __shared__ DrawGeom s_geom[kGeomCache];
     __shared__ int s_wcnt[kDrawThreads / 32];
     __shared__ unsigned char s_ord[kGeomCache];
-    __shared__ int s_start[MLP_MAX_DRAW_CLASSES + 1];
+    __shared__ int s_start[MLP_MAX_DRAW_CLASSES], s_cnt[MLP_MAX_DRAW_CLASSES];      // a class's run in s_ord: [start, cnt)
+    __shared__ unsigned char s_pcls[MLP_MAX_DRAW_CLASSES];                           // classes present near the block
+    __shared__ int s_np;
+    __shared__ float4 s_ctab[16], s_stab[8];               // colour * alpha per class subset / per {0,1} map triple
     const int b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = min(*A.m_used, A.m_rows);
@@ -263,32 +305,132 @@ draw_tiles_kernel(const DrawTilesArgs A) {
         ncand += tot;
         __syncthreads();
     }
-    // At most 32 candidates (= the geometry cache): warp 0 groups them by class with ballots, order kept, so that
-    // the per-class loops below touch only their own candidates instead of scanning the list once per class.
-    const bool grouped = ncand > 0 && ncand <= kGeomCache && C <= MLP_MAX_DRAW_CLASSES;
-    if (grouped) {
-        if (warp == 0) {
-            const int mine = lane < ncand ? (int)s_cls[lane] : -1;
+    // At most 64 candidates (= the geometry cache): warp 0 groups them by class with ballots, order kept, so that
+    // the per-class loops below touch only their own candidates instead of scanning the list once per class; the
+    // classes that have a candidate at all (usually one to three) form the list the threads walk.  (Grouping the
+    // classes in parallel, one warp each, with per-warp colour tables was measured slower: 144 against 117 us.)
+    const bool grouped = ncand > 0 && ncand <= kGeomCache;
+    if (warp == 0) {
+        if (grouped) {
             int start = 0;
             for (int c = 0; c < C; ++c) {
-                const unsigned m = __ballot_sync(0xffffffffu, mine == c);
-                if (mine == c) s_ord[start + __popc(m & ((1u << lane) - 1u))] = (unsigned char)lane;
-                if (lane == 0) s_start[c] = start;
-                start += __popc(m);
-            }
-            if (lane == 0) s_start[C] = start;
-        }
-        __syncthreads();
-    }
-    const int oy = by0 + (tid >> 4), ox = bx0 + (tid & 15) * 4;
-    if (oy >= A.PH || ox >= A.PW) return;
-    const int mh = A.mh, mw = A.mw;
-    float cs[4][3];
+                if (lane == c) s_start[c] = start;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cs[q][0] = cs[q][1] = cs[q][2] = 0.0f;
-    if (ncand > 0) {
-        // the float32 value CropAndPadMask writes at (oy, ox+q) for instance j: two-stage lerp of the {0,1} tile
-        auto eval = [&](int j, const DrawGeom& d, float (&acc)[4]) {
+                for (int h = 0; h < kGeomCache; h += 32) {
+                    const int i = h + lane;
+                    const bool mine = i < ncand && (int)s_cls[i] == c;
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) s_ord[start + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
+                    start += __popc(m);
+                }
+                if (lane == c) s_cnt[c] = start;           // end of the class's run
+            }
+            __syncwarp();
+            const bool present = lane < C && s_cnt[lane] > s_start[lane];
+            const unsigned pm = __ballot_sync(0xffffffffu, present);
+            if (present) s_pcls[__popc(pm & ((1u << lane) - 1u))] = (unsigned char)lane;
+            if (lane == 0) s_np = __popc(pm);
+        } else {
+            if (lane < C) s_pcls[lane] = (unsigned char)lane;
+            if (lane == 0) s_np = ncand > 0 ? C : 0;
+        }
+        __syncwarp();
+        // Colour terms of the two blends, tabulated once per CTA with the operations a pixel would perform itself:
+        // lanes 0-15: csum * alpha of DrawInstance for every subset of (at most four) present classes, the colours
+        // added in class order; lanes 16-23: the same for DrawSegmentation over {0,1}-valued three-class maps.
+        if (lane < 16) {
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+            const int np = s_np;
+            for (int p = 0; p < 4 && p < np; ++p)
+                if ((lane >> p) & 1) {
+                    const int c = s_pcls[p];
+                    c0 = __fadd_rn(c0, A.inst.rgb[c][0]); c1 = __fadd_rn(c1, A.inst.rgb[c][1]); c2 = __fadd_rn(c2, A.inst.rgb[c][2]);
+                }
+            s_ctab[lane] = make_float4(__fmul_rn(c0, A.inst.alpha), __fmul_rn(c1, A.inst.alpha), __fmul_rn(c2, A.inst.alpha), 0.0f);
+        } else if (kCs == 3 && lane < 24) {
+            const float s0 = (float)(lane & 1), s1 = (float)((lane >> 1) & 1), s2 = (float)((lane >> 2) & 1);
+            float t[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float v = __fmul_rn(A.sem.rgb[0][k], s0);
+                v = __fadd_rn(v, __fmul_rn(A.sem.rgb[1][k], s1));
+                v = __fadd_rn(v, __fmul_rn(A.sem.rgb[2][k], s2));
+                t[k] = __fmul_rn(v, A.sem.alpha);
+            }
+            s_stab[lane - 16] = make_float4(t[0], t[1], t[2], 0.0f);
+        }
+    }
+    __syncthreads();
+    const int P = s_np;                                    // classes to walk, block-uniform; bit p of a pixel's mask
+    const float4* ctab = s_ctab;
+    const int oy0 = by0 + (tid >> 4) * kRowsPT, ox = bx0 + (tid & 15) * 4;
+    if (oy0 >= A.PH || ox >= A.PW) return;
+    const int mh = A.mh, mw = A.mw;
+    // classes whose summed masks exceed 0.5, 16 bits per pixel: cm[r][q >> 1] bits 16 * (q & 1) + c
+    uint32_t cm[kRowsPT][2];
+#pragma unroll
+    for (int r = 0; r < kRowsPT; ++r) cm[r][0] = cm[r][1] = 0u;
+    if (grouped) {
+        for (int p = 0; p < P; ++p) {
+            const int c = s_pcls[p];
+            const int k0 = s_start[c], k1 = s_cnt[c];
+            float acc[kRowsPT][4];                         // reduce_sum of the class's masks, order j
+#pragma unroll
+            for (int r = 0; r < kRowsPT; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] = 0.0f;
+            bool any = false;
+            for (int k = k0; k < k1; ++k) {
+                const int i = s_ord[k];
+                const DrawGeom d = s_geom[i];
+                if (oy0 + kRowsPT <= d.ymin || oy0 >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
+                any = true;
+                // x half of the resize, once for the four rows
+                uint32_t mlo[4], mhi[4];
+                float lx[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = ox + q;
+                    const bool in = x >= d.xmin && x < d.xmax;
+                    const float p = __fmul_rn((float)(x - d.xmin), d.sx);
+                    const float fl = floorf(p);
+                    const int xlo = max((int)fl, 0), xhi = min((int)ceilf(p), mw - 1);
+                    lx[q] = __fsub_rn(p, fl);
+                    mlo[q] = in ? 1u << (xlo & 31) : 0u;   // outside the box: no corner bit -> the value added is +0
+                    mhi[q] = in ? 1u << (xhi & 31) : 0u;
+                }
+                const uint32_t* tb = A.bits + ((int64_t)b * A.m_rows + (int)s_cand[i]) * mh;
+#pragma unroll
+                for (int r = 0; r < kRowsPT; ++r) {
+                    const int oy = oy0 + r;
+                    if (oy < d.ymin || oy >= d.ymax) continue;
+                    const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
+                    const float fy = floorf(py);
+                    const float ly = __fsub_rn(py, fy);
+                    const uint32_t w0 = __ldg(tb + max((int)fy, 0)), w1 = __ldg(tb + min((int)ceilf(py), mh - 1));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool tl = (w0 & mlo[q]) != 0u, tr = (w0 & mhi[q]) != 0u;
+                        const bool bl = (w1 & mlo[q]) != 0u, br = (w1 & mhi[q]) != 0u;
+                        const float oml = __fsub_rn(1.0f, lx[q]);              // fadd(1, (0 - 1) * lx)
+                        const float t = tl ? (tr ? 1.0f : oml) : (tr ? lx[q] : 0.0f);
+                        const float bo = bl ? (br ? 1.0f : oml) : (br ? lx[q] : 0.0f);
+                        acc[r][q] = __fadd_rn(acc[r][q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
+                    }
+                }
+            }
+            if (any) {
+#pragma unroll
+                for (int r = 0; r < kRowsPT; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (acc[r][q] > 0.5f) cm[r][q >> 1] |= 1u << (16 * (q & 1) + p);
+            }
+        }
+    } else if (ncand > 0) {
+        // list overflow (more than 64 boxes touch the block, or more than 1024): one row at a time, every class walks
+        // the candidate list (or all instances of the image) - same order, same result
+        auto eval = [&](int oy, int j, const DrawGeom& d, float (&acc)[4]) {
             const float py = __fmul_rn((float)(oy - d.ymin), d.sy);
             const float fy = floorf(py);
             const float ly = __fsub_rn(py, fy);
@@ -309,110 +451,161 @@ draw_tiles_kernel(const DrawTilesArgs A) {
                 acc[q] = __fadd_rn(acc[q], __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly)));
             }
         };
-        for (int c = 0; c < C; ++c) {
-            if (grouped && s_start[c] == s_start[c + 1]) continue;      // no instance of this class near the block
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};           // reduce_sum of the class's masks, order j
-            if (grouped) {
-                // the usual case (at most 32 candidates): only this class's candidates, still in instance order
-                for (int k = s_start[c]; k < s_start[c + 1]; ++k) {
-                    const int i = s_ord[k];
-                    const DrawGeom d = s_geom[i];
-                    if (oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
-                    eval((int)s_cand[i], d, acc);
-                }
-            } else {
-                // list overflow: walk all instances of the image instead (same order, same result)
-                const bool all = ncand > kMaxCand;
-                const int i1 = all ? M : ncand;
+        const bool all = ncand > kMaxCand;
+        const int i1 = all ? M : ncand;
+#pragma unroll 1
+        for (int r = 0; r < kRowsPT; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= A.PH) break;
+            uint32_t m0 = 0u, m1 = 0u;
+            for (int c = 0; c < C && c < MLP_MAX_DRAW_CLASSES; ++c) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int i = 0; i < i1; ++i) {
                     if (!all && s_cls[i] != c) continue;
                     const int j = all ? i : (int)s_cand[i];
                     const DrawGeom d = (!all && i < kGeomCache) ? s_geom[i] : G[j];
                     if (d.cls != c || oy < d.ymin || oy >= d.ymax || ox + 3 < d.xmin || ox >= d.xmax) continue;
-                    eval(j, d, acc);
+                    eval(oy, j, d, acc);
                 }
+                if (acc[0] > 0.5f) m0 |= 1u << c;
+                if (acc[1] > 0.5f) m0 |= 1u << (16 + c);
+                if (acc[2] > 0.5f) m1 |= 1u << c;
+                if (acc[3] > 0.5f) m1 |= 1u << (16 + c);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (acc[q] > 0.5f)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) cs[q][k] = __fadd_rn(cs[q][k], A.inst.rgb[c][k]);
+            for (int rr = 0; rr < kRowsPT; ++rr)
+                if (rr == r) { cm[rr][0] = m0; cm[rr][1] = m1; }
         }
     }
     // ---- blend: DrawInstance's uint8, then (optionally) DrawSegmentation over it (serving.py:38-40)
-    const int64_t pix0 = ((int64_t)b * A.PH + oy) * A.PW + ox;
     const int n = min(4, A.PW - ox);
     const bool vec = n == 4 && (A.PW & 3) == 0;            // 4-pixel groups are 12-byte / 48-byte aligned
-    float img[12];
-    load_px12(static_cast<const ImgT*>(A.images) + pix0 * 3, vec, n, img);
-    if (A.line_bits) {
-        // DrawBoxes in front of the overlays (serving.py:34): its uint8 canvas (clip + truncation for float frames)
-        // with the rectangles' pixels at 255; ox is a multiple of 4, so the four pixels share one word of the bitmap
-        if (sizeof(ImgT) != 1) {                           // uint8 frames are their own canvas
+    const float ia = A.inst.alpha, sa = A.sem.alpha;
+    const int nrows = min(kRowsPT, A.PH - oy0);
+#pragma unroll 1                                           // one copy of the row body: it has to stay in the instruction cache
+    for (int r = 0; r < nrows; ++r) {
+        const int oy = oy0 + r;
+        // every load of the row first (frame pixels, rectangle bits, semantic map): one round trip, not three
+        const int64_t pix0 = ((int64_t)b * A.PH + oy) * A.PW + ox;
+        PxRaw<ImgT> raw;
+        raw.load(static_cast<const ImgT*>(A.images) + pix0 * 3, vec, n);
+        uint32_t lw = 0u;
+        if (A.line_bits) lw = __ldg(A.line_bits + ((int64_t)b * A.PH + oy) * A.line_words + (ox >> 5));
+        uint32_t w[12];                                    // kCs == 3: the raw words of the map, 4 pixels x 3 classes
+        if (kCs == 3) {
+            const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * 3;
+            if (vec) {                                     // three 128-bit loads
 #pragma unroll
-            for (int i = 0; i < 12; ++i) img[i] = (float)__float2uint_rz(fminf(fmaxf(img[i], 0.0f), 255.0f));
+                for (int k = 0; k < 3; ++k) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(sp) + k);
+                    w[k * 4] = u.x; w[k * 4 + 1] = u.y; w[k * 4 + 2] = u.z; w[k * 4 + 3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) w[i] = i < 3 * n ? __ldg(reinterpret_cast<const uint32_t*>(sp) + i) : 0u;
+            }
         }
-        const uint32_t lw = __ldg(A.line_bits + ((int64_t)b * A.PH + oy) * A.line_words + (ox >> 5)) >> (ox & 31);
+        // csum * alpha of the classes that passed: from the subset table, or (more than four classes near the
+        // block) added up in class order here
+        float ca[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t m = (cm[0][q >> 1] >> (16 * (q & 1))) & 0xffffu;
+            if (P <= 4) {
+                const float4 t = ctab[m & 15u];
+                ca[q][0] = t.x; ca[q][1] = t.y; ca[q][2] = t.z;
+            } else {
+                float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+                for (int p = 0; p < P; ++p)
+                    if ((m >> p) & 1u) {
+                        const int c = s_pcls[p];
+                        c0 = __fadd_rn(c0, A.inst.rgb[c][0]); c1 = __fadd_rn(c1, A.inst.rgb[c][1]); c2 = __fadd_rn(c2, A.inst.rgb[c][2]);
+                    }
+                ca[q][0] = __fmul_rn(c0, ia); ca[q][1] = __fmul_rn(c1, ia); ca[q][2] = __fmul_rn(c2, ia);
+            }
+        }
+        float img[12];
+        raw.pixels(img, vec);
+        if (A.line_bits) {
+            // DrawBoxes in front of the overlays (serving.py:34): its uint8 canvas (clip + truncation for float frames)
+            // with the rectangles' pixels at 255; ox is a multiple of 4, so the four pixels share one word of the bitmap
+            if (sizeof(ImgT) != 1) {                       // uint8 frames are their own canvas
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                    img[i] = __fsub_rn(trunc_magic(fminf(fmaxf(img[i], 0.0f), 255.0f)), kTwo23);
+            }
+            lw >>= (ox & 31);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((lw >> q) & 1u) img[q * 3] = img[q * 3 + 1] = img[q * 3 + 2] = 255.0f;
+        }
+        // (sum_c colours[c] * seg[..., c]) * alpha of DrawSegmentation
+        float sc[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sc[q][0] = sc[q][1] = sc[q][2] = 0.0f;
+        if (kCs == 3) {
+            // an int32 map whose twelve values are all 0 or 1 (a one-hot semantic map): table lookup by the triple
+            bool binary = sizeof(SegT) == 4 && !is_float_seg<SegT>();
+            if (binary) {
+                uint32_t any = 0u;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) any |= w[i];
+                binary = __all_sync(__activemask(), (any & ~1u) == 0u);
+            }
+            if (binary) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = s_stab[w[q * 3] | (w[q * 3 + 1] << 1) | (w[q * 3 + 2] << 2)];
+                    sc[q][0] = t.x; sc[q][1] = t.y; sc[q][2] = t.z;
+                }
+            } else {
+                // reduce_sum over the classes, in order; the first term is added to +0, which changes nothing the
+                // blend can see (a -0 product survives only into v + (-0) = v)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float t = __fmul_rn(A.sem.rgb[0][k], seg_word<SegT>(w[q * 3]));
+                        t = __fadd_rn(t, __fmul_rn(A.sem.rgb[1][k], seg_word<SegT>(w[q * 3 + 1])));
+                        t = __fadd_rn(t, __fmul_rn(A.sem.rgb[2][k], seg_word<SegT>(w[q * 3 + 2])));
+                        sc[q][k] = __fmul_rn(t, sa);
+                    }
+            }
+        } else if (kCs != 0) {
+            const int Cs = A.sem.num_classes;
+            const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * Cs;
+            for (int q = 0; q < n; ++q) {
+                for (int c = 0; c < Cs; ++c) {
+                    const float v = seg_f32(sp + q * Cs + c);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sc[q][k] = __fadd_rn(sc[q][k], __fmul_rn(A.sem.rgb[c][k], v));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[q][k] = __fmul_rn(sc[q][k], sa);
+            }
+        }
+        uint32_t byte[12];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if ((lw >> q) & 1u) img[q * 3] = img[q * 3 + 1] = img[q * 3 + 2] = 255.0f;
-    }
-    float sc[4][3];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) sc[q][0] = sc[q][1] = sc[q][2] = 0.0f;
-    if (kCs == 3) {
-        float rgb[3][3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) rgb[c][k] = A.sem.rgb[c][k];
-        const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * 3;
-        float sv[12];
-        if (vec) {                                         // 4 pixels x 3 classes = three 128-bit loads
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(sp) + k);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    sv[k * 4 + e] = seg_word<SegT>(w[e]);
+                float m = trunc_magic(clip255(__fadd_rn(img[q * 3 + k], ca[q][k])));         // 2^23 + uint8
+                if (kCs != 0) m = trunc_magic(clip255(__fadd_rn(__fsub_rn(m, kTwo23), sc[q][k])));
+                byte[q * 3 + k] = __float_as_uint(m);          // the uint8 is the low byte
             }
+        uint8_t* op = A.out + pix0 * 3;
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                reinterpret_cast<uint32_t*>(op)[k] = __byte_perm(__byte_perm(byte[4 * k], byte[4 * k + 1], 0x0040),
+                                                                 __byte_perm(byte[4 * k + 2], byte[4 * k + 3], 0x0040), 0x5410);
         } else {
 #pragma unroll
-            for (int i = 0; i < 12; ++i) sv[i] = i < 3 * n ? seg_f32(sp + i) : 0.0f;
+            for (int i = 0; i < 12; ++i)
+                if (i < 3 * n) op[i] = (uint8_t)byte[i];
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sc[q][k] = __fadd_rn(sc[q][k], __fmul_rn(rgb[c][k], sv[q * 3 + c]));
-    } else if (kCs != 0) {
-        const int Cs = A.sem.num_classes;
-        const SegT* sp = static_cast<const SegT*>(A.seg) + pix0 * Cs;
-        for (int q = 0; q < n; ++q)
-            for (int c = 0; c < Cs; ++c) {
-                const float v = seg_f32(sp + q * Cs + c);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sc[q][k] = __fadd_rn(sc[q][k], __fmul_rn(A.sem.rgb[c][k], v));
-            }
-    }
-    uint32_t word[3] = {0u, 0u, 0u};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float v = (float)__float2uint_rz(blend(img[q * 3 + k], cs[q][k], A.inst.alpha));
-            if (kCs != 0) v = (float)__float2uint_rz(blend(v, sc[q][k], A.sem.alpha));
-            const int i = q * 3 + k;
-            word[i >> 2] |= __float2uint_rz(v) << (8 * (i & 3));
-        }
-    uint8_t* op = A.out + pix0 * 3;
-    if (vec) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) reinterpret_cast<uint32_t*>(op)[k] = word[k];
-    } else {
-        for (int i = 0; i < 3 * n; ++i) op[i] = (uint8_t)(word[i >> 2] >> (8 * (i & 3)));
+        for (int rr = 0; rr + 1 < kRowsPT; ++rr) { cm[rr][0] = cm[rr + 1][0]; cm[rr][1] = cm[rr + 1][1]; }   // next row's masks
     }
 }
 

@@ -105,8 +105,11 @@ __device__ __forceinline__ void paste_box_rows(const float* __restrict__ s_tile,
 //   B1 rows crossing the box: the 16-byte segments left and right of it (zeros);
 //   B2 the segments intersecting the box, flattened over ALL threads of the CTA: each evaluates
 //      the reference's two-stage lerp per pixel from the mask tile in shared memory.
+#ifndef MLP_PASTE_MIN_CTAS
+#define MLP_PASTE_MIN_CTAS 4
+#endif
 template <int kMode>       // MLP_PASTE_F32 / MLP_PASTE_U8 / MLP_PASTE_BITS
-__global__ void __launch_bounds__(kPasteThreads)
+__global__ void __launch_bounds__(kPasteThreads, MLP_PASTE_MIN_CTAS)
 paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
              int mw, int PH, int PW, int band_rows, int use_cols, void* __restrict__ out) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);   // pixels per 16-byte store
@@ -649,9 +652,21 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
         const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
         int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
         if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
-        const size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
+        size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
         int use_cols = 1;
         if (const char* e = getenv("MLP_PASTE_COLS")) use_cols = atoi(e);
+        if (const char* e = getenv("MLP_PASTE_SMEM_KB")) {           // tuning knob: fewer resident CTAs per SM
+            const size_t want = (size_t)atoi(e) * 1024;
+            if (want > smem && want <= 200 * 1024) {
+                smem = want;
+                if (out_mode == MLP_PASTE_U8)
+                    MLP_CUDA(cudaFuncSetAttribute(paste_kernel<MLP_PASTE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else if (out_mode == MLP_PASTE_BITS)
+                    MLP_CUDA(cudaFuncSetAttribute(paste_kernel<MLP_PASTE_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else
+                    MLP_CUDA(cudaFuncSetAttribute(paste_kernel<MLP_PASTE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+        }
 #define MLP_PASTE_LAUNCH(MODE)                                                                         \
     paste_kernel<MODE><<<grid, kPasteThreads, smem, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
                                                       mask_w, frame_h, frame_w, band_rows, use_cols, out_dev)

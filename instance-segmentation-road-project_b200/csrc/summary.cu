@@ -507,16 +507,23 @@ instance_reduce_kernel(const SummaryArgs A) {
 }
 
 // ---- the same reductions inside a box, without any [PH,PW] tensor ---------------------------
-// One CTA per (instance, column chunk of its clipped box: 128 columns, 32 for large boxes).  An instance's float32 paste values
-// exist only inside the box and are evaluated there from its tile (two-stage lerp, the values
-// CropAndPadMask would write).  The 8 warps take the box rows round-robin, lanes take 4 columns of
-// the chunk each (interleaved so that narrow boxes still fill the warp) and carry their column
-// sums; the warps' column sums meet in shared memory for the horizontal maximum.  Rows vote their
-// "any pixel > 0.5" flag.  Boxes wider than one chunk are split over several CTAs whose partial
-// results meet in a per-instance accumulator; the last CTA to arrive writes the row.  The crack
-// pseudo-instance of every image was reduced by mlp_road_scan and is only copied here.
+// One CTA per work item = (instance, chunk of 128 columns of its clipped box).  An instance's float32 paste values
+// exist only inside the box and are evaluated there from its tile (two-stage lerp, the values CropAndPadMask would
+// write).  Lane layout: a chunk of width <= 32 / <= 64 / <= 128 columns is walked with 8 / 16 / 32 lanes per row, so a
+// warp covers 4 / 2 / 1 box rows per step and every lane owns FOUR columns (c, c+cw, c+2cw, c+3cw) whose x terms it
+// computes once (median box of the benchmark: 47 columns - with a fixed 128-column layout 63 % of the lane slots were
+// idle).  The 8 warps take the row groups round-robin; lanes carry their column sums, which meet across the row
+// groups of a warp by shuffles and across the warps in shared memory for the horizontal maximum.  Row groups vote
+// their "any pixel > 0.5" flag.  Boxes wider than one chunk are split over several CTAs whose partial results meet
+// in a per-instance accumulator; the last CTA to arrive writes the row.  The crack pseudo-instance of every image
+// was reduced by mlp_road_scan and is only copied here.
+// Tiles that arrive as bit rows (the fused tail, mw <= 32) are {0,1} by construction: the x lerp of a row,
+// tl + (tr - tl) * lx, is then one of 0, lx, 1 - lx (rounded once, as fadd(1, -lx)) or 1 - selected by the two
+// corner bits with the same float32 results as the arithmetic, without the four shared-memory loads per pixel.
 constexpr int kBoxWarps = kReduceThreads / 32;
-constexpr int kBoxCols = 128;             // columns per chunk = 32 lanes x 4
+constexpr int kBoxCols = 128;             // columns per chunk = 4 per lane x 32 lanes at most
+constexpr int kBoxQ = 4;                  // columns per lane
+constexpr int kBitRows = 64;              // tile rows the bit path holds
 
 struct BoxAcc {                           // per-instance accumulator of a box split over several CTAs
     double pix, size;
@@ -524,6 +531,14 @@ struct BoxAcc {                           // per-instance accumulator of a box s
     int cnt, inter, done, pad;
 };
 static_assert(sizeof(BoxAcc) == 40, "BoxAcc layout");
+
+struct BoxItem {                          // one work item: instance, chunk and the instance's clipped box (32 bytes)
+    uint32_t code;                        // (b * m_rows + j) | chunk << 20
+    int xmin, xmax, ymin, ymax;
+    float sx, sy;
+    int active;
+};
+static_assert(sizeof(BoxItem) == 32, "BoxItem layout");
 
 struct BoxSummaryArgs {
     const int32_t* det;        // [B, m_stride, 6] int32 (UpSampleOutput rows)
@@ -535,11 +550,11 @@ struct BoxSummaryArgs {
     const int32_t* m_dev;      // M when there are no tiles
     BoxAcc* acc;               // [B * m_rows], zeroed before the launch
     uint32_t* acc_rowany;      // [B * m_rows, ceil(PH / 32)], zeroed before the launch
-    int B, m_rows, m_stride, mh, mw, PH, PW, chunks;      // chunks = ceil(PW / 32): most per instance
+    int B, m_rows, m_stride, mh, mw, PH, PW, chunks;      // chunks = ceil(PW / 128): most per instance
     float threshold;
     float* out;                // [B, M', 11]
     int32_t* m_out;            // [1] M'
-    uint32_t* items;           // work items of box_plan_kernel: (b * m_rows + j) | chunk << 20
+    BoxItem* items;            // work items of box_plan_kernel
     int32_t* n_items;          // [1]
     int item_cap;
 };
@@ -547,6 +562,7 @@ struct BoxSummaryArgs {
 // One CTA per image, one thread per instance row (rounds of 256): which 128-column chunks of its clipped box exist.
 // Only those become work items (an atomicAdd per round and CTA), widest chunk index first within an instance; the
 // summary kernel walks the list instead of testing all B * M * ceil(PW / 128) combinations, 7 of 8 of which are empty.
+// The box geometry (two float divisions, four ceils) is computed here once per instance and travels in the item.
 __global__ void __launch_bounds__(kReduceThreads)
 box_plan_kernel(const BoxSummaryArgs A) {
     __shared__ int s_cnt[kReduceThreads / 32];
@@ -558,9 +574,13 @@ box_plan_kernel(const BoxSummaryArgs A) {
     for (int j0 = 0; j0 < M; j0 += kReduceThreads) {
         const int j = j0 + tid;
         int n = 0;
+        BoxItem it;
+        it.active = 0;
         if (j < M) {
             const PasteGeom g = paste_geometry(A.det + ((int64_t)b * m_stride + j) * 6, thr, A.mh, A.mw, A.PH, A.PW);
             n = g.active ? (g.xmax - g.xmin + kBoxCols - 1) / kBoxCols : 1;      // an all-zero mask still gets its row
+            it.xmin = g.xmin; it.xmax = g.xmax; it.ymin = g.ymin; it.ymax = g.ymax; it.sx = g.sx; it.sy = g.sy;
+            it.active = g.active ? 1 : 0;
         }
         int incl = n;
 #pragma unroll
@@ -580,13 +600,17 @@ box_plan_kernel(const BoxSummaryArgs A) {
         __syncthreads();
         int at = s_base + pre + incl - n;
         for (int c = n - 1; c >= 0; --c, ++at)
-            if (at < A.item_cap) A.items[at] = (uint32_t)(b * A.m_rows + j) | ((uint32_t)c << 20);
+            if (at < A.item_cap) {
+                it.code = (uint32_t)(b * A.m_rows + j) | ((uint32_t)c << 20);
+                A.items[at] = it;
+            }
         __syncthreads();
     }
 }
 
 struct BoxSmem {
-    float tile[kMaxTile];
+    float tile[kMaxTile];                 // general path: the tile as floats
+    uint32_t rows[kBitRows];              // bit path: the tile's rows
     float unit[kMaxFrameRows];
     unsigned rowany[kMaxFrameRows / 32];
     double col[kBoxWarps][kBoxCols];
@@ -595,22 +619,23 @@ struct BoxSmem {
     int last;
 };
 
-// One chunk (columns [c0, c0 + 32*Q) of the box); every thread of the CTA calls it.  Q = 4 columns
-// per lane for small boxes (one CTA does the whole box), Q = 1 for large ones (more, shorter CTAs).
-template <int Q>
-__device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c0, int mh, int mw,
+// One chunk (columns [c0, c0 + 4 * cw) of the box, cw = 1 << cwl lanes per row); every thread of the CTA calls it.
+template <bool kBits>
+__device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c0, int cwl, int mh, int mw,
                                            const uint32_t* __restrict__ rbits, int words, double& pix,
                                            double& size, double& colmax, int& cnt, int& inter) {
+    constexpr int Q = kBoxQ;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cw = 1 << cwl, c = lane & (cw - 1), r = lane >> cwl, rpw = 32 >> cwl;
     const int bw = g.xmax - g.xmin;
     // this lane's Q columns of the chunk and their x lerp terms (paste_value, paste_common.cuh)
-    int xlo[Q], xhi[Q];
+    int xlo[Q], xhi[Q];                   // kBits: single-bit masks of the two source columns (0 outside the box)
     float lx[Q];
     bool live[Q];
     double col[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const int oxl = c0 + lane + 32 * q;
+        const int oxl = c0 + c + cw * q;
         live[q] = oxl < bw;
         const float p = __fmul_rn((float)oxl, g.sx);
         const float fl = floorf(p);
@@ -618,27 +643,49 @@ __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c
         xhi[q] = min((int)ceilf(p), mw - 1);
         lx[q] = __fsub_rn(p, fl);
         col[q] = 0.0;
+        if (kBits) {
+            xlo[q] = live[q] ? (int)(1u << xlo[q]) : 0;
+            xhi[q] = live[q] ? (int)(1u << xhi[q]) : 0;
+        }
     }
-    const int xw0 = g.xmin + c0 + lane;                      // frame column of q = 0; q adds 32 = one word
-    for (int oy = g.ymin + warp; oy < g.ymax; oy += kBoxWarps) {
+    const int xw0 = g.xmin + c0 + c;                        // frame column of q = 0; q adds cw
+    const unsigned gmask = (cw == 32 ? 0xffffffffu : ((1u << cw) - 1u)) << (r * cw);   // lanes of this row group
+    for (int oyb = g.ymin + warp * rpw; oyb < g.ymax; oyb += kBoxWarps * rpw) {        // warp-uniform
+        const int oy = oyb + r;
         float v[Q];
         bool nz = false;
-        {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) v[q] = 0.0f;
+        if (oy < g.ymax) {
             const float py = __fmul_rn((float)(oy - g.ymin), g.sy);
             const float fy = floorf(py);
-            const float* r0 = S.tile + max((int)fy, 0) * mw;
-            const float* r1 = S.tile + min((int)ceilf(py), mh - 1) * mw;
+            const int ylo = max((int)fy, 0), yhi = min((int)ceilf(py), mh - 1);
             const float ly = __fsub_rn(py, fy);
+            if (kBits) {
+                const uint32_t w0 = S.rows[ylo], w1 = S.rows[yhi];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                v[q] = 0.0f;
-                if (live[q]) {
-                    const float tl = r0[xlo[q]], tr = r0[xhi[q]], bl = r1[xlo[q]], br = r1[xhi[q]];
-                    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx[q]));
-                    const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx[q]));
+                for (int q = 0; q < Q; ++q) {
+                    const bool tl = (w0 & (uint32_t)xlo[q]) != 0u, tr = (w0 & (uint32_t)xhi[q]) != 0u;
+                    const bool bl = (w1 & (uint32_t)xlo[q]) != 0u, br = (w1 & (uint32_t)xhi[q]) != 0u;
+                    const float oml = __fsub_rn(1.0f, lx[q]);                  // fadd(1, (0 - 1) * lx)
+                    const float t = tl ? (tr ? 1.0f : oml) : (tr ? lx[q] : 0.0f);
+                    const float bo = bl ? (br ? 1.0f : oml) : (br ? lx[q] : 0.0f);
                     v[q] = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
+                    nz |= v[q] != 0.0f;
                 }
-                nz |= v[q] != 0.0f;
+            } else {
+                const float* r0 = S.tile + ylo * mw;
+                const float* r1 = S.tile + yhi * mw;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    if (live[q]) {
+                        const float tl = r0[xlo[q]], tr = r0[xhi[q]], bl = r1[xlo[q]], br = r1[xhi[q]];
+                        const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx[q]));
+                        const float bo = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx[q]));
+                        v[q] = __fadd_rn(t, __fmul_rn(__fsub_rn(bo, t), ly));
+                    }
+                    nz |= v[q] != 0.0f;
+                }
             }
         }
         unsigned on = 0u;
@@ -652,40 +699,40 @@ __device__ __forceinline__ void box_reduce(BoxSmem& S, const PasteGeom& g, int c
                 col[q] = __fma_rn(du, d[q], col[q]);       // float32 x float32 is exact in float64: same bits as mul + add
                 on |= (v[q] > 0.5f ? 1u : 0u) << q;
             }
-            const double rs = Q == 4 ? __dadd_rn(__dadd_rn(d[0], d[1]), __dadd_rn(d[Q / 2], d[Q - 1])) : d[0];
+            const double rs = __dadd_rn(__dadd_rn(d[0], d[1]), __dadd_rn(d[2], d[3]));
             pix = __dadd_rn(pix, rs);
             size = __dadd_rn(size, __dmul_rn((double)__fmul_rn(u, u), rs));          // unit ** 2 in float32
         }
-        if (__any_sync(0xffffffffu, on != 0u)) {             // warp-uniform: the row has a pixel > 0.5
-            if (lane == 0) atomicOr(&S.rowany[oy >> 5], 1u << (oy & 31));
-            cnt += __popc(on);
-            // my_road bits of the lane's columns: all loads in flight before the first use
-            unsigned rw[Q];
+        const unsigned vote = __ballot_sync(0xffffffffu, on != 0u);
+        if (vote) {                                          // warp-uniform: some row of the step has a pixel > 0.5
+            if ((vote & gmask) && c == 0) atomicOr(&S.rowany[oy >> 5], 1u << (oy & 31));
+            if (on) {
+                cnt += __popc(on);
+                // my_road bits of the lane's lit columns (a word-wise variant - ballots of the four column runs, one
+                // funnel-shifted AND per run - was measured slower: 135 against 108 us)
+                const uint32_t* rw = rbits + (int64_t)oy * words;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) rw[q] = __ldg(rbits + (int64_t)oy * words + min((xw0 + 32 * q) >> 5, words - 1));
-#pragma unroll
-            for (int q = 0; q < Q; ++q) inter += ((on >> q) & 1u) & (rw[q] >> ((xw0 + 32 * q) & 31));
+                for (int q = 0; q < Q; ++q)
+                    if ((on >> q) & 1u) {
+                        const int xw = xw0 + cw * q;
+                        inter += (int)((__ldg(rw + (xw >> 5)) >> (xw & 31)) & 1u);
+                    }
+            }
         }
     }
-    // horizontal size: column sums of the 8 warps meet in shared memory
+    // horizontal size: the row groups of a warp first (shuffles), then the 8 warps in shared memory
 #pragma unroll
-    for (int q = 0; q < Q; ++q) S.col[warp][lane + 32 * q] = col[q];
-    __syncthreads();
-    if (tid < 32 * Q) {
-        double c = S.col[0][tid];
-#pragma unroll
-        for (int w = 1; w < kBoxWarps; ++w) c = __dadd_rn(c, S.col[w][tid]);
-        colmax = fmax(colmax, c);
+    for (int q = 0; q < Q; ++q) {
+        for (int o = cw; o < 32; o <<= 1) col[q] = __dadd_rn(col[q], shfl_xor_d(col[q], o));
+        if (r == 0) S.col[warp][q * cw + c] = col[q];
     }
-}
-
-// Columns per lane for a box: 4 (one CTA per 128 columns) up to kBoxSmallArea pixels, else 1.
-// Measured on B200 (cfg-2 / stress): 32-column chunks for boxes > 16 K pixels made the kernel 1.8x /
-// 4x SLOWER (more CTAs, each paying the tile staging and the accumulator atomics), so the narrow
-// variant is disabled; the knob stays for frames much taller than 1080 rows.
-constexpr int kBoxSmallArea = INT_MAX;
-__device__ __forceinline__ int box_q(const PasteGeom& g) {
-    return (int64_t)(g.xmax - g.xmin) * (g.ymax - g.ymin) <= kBoxSmallArea ? 4 : 1;
+    __syncthreads();
+    if (tid < Q * cw) {
+        double t = S.col[0][tid];
+#pragma unroll
+        for (int w = 1; w < kBoxWarps; ++w) t = __dadd_rn(t, S.col[w][tid]);
+        colmax = fmax(colmax, t);
+    }
 }
 
 __global__ void __launch_bounds__(kReduceThreads, 4)
@@ -719,15 +766,18 @@ box_summary_kernel(const BoxSummaryArgs A) {
             }
             continue;
         }
-        const uint32_t code = __ldg(A.items + (item - n_crack));
-        const int chunk = (int)(code >> 20);
-        const int inst = (int)(code & 0xfffffu);
+        // the item: two 16-byte loads, the same address for the whole CTA
+        const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(A.items + (item - n_crack)));
+        const uint4 i1 = __ldg(reinterpret_cast<const uint4*>(A.items + (item - n_crack)) + 1);
+        PasteGeom g;
+        g.xmin = (int)i0.y; g.xmax = (int)i0.z; g.ymin = (int)i0.w; g.ymax = (int)i1.x;
+        g.sx = __uint_as_float(i1.y); g.sy = __uint_as_float(i1.z); g.active = i1.w != 0u;
+        const int chunk = (int)(i0.x >> 20);
+        const int inst = (int)(i0.x & 0xfffffu);
         const int b = inst / A.m_rows, j = inst - b * A.m_rows;
         const int32_t* row = A.det + ((int64_t)b * m_stride + j) * 6;
-        const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
-        const int cols = 32 * box_q(g);                     // columns per chunk of this box
-        const int nchunks = g.active ? (g.xmax - g.xmin + cols - 1) / cols : 1;
-        if (chunk >= nchunks) continue;                     // CTA-uniform
+        const int bw = g.xmax - g.xmin;
+        const int nchunks = g.active ? (bw + kBoxCols - 1) / kBoxCols : 1;
         float* o = A.out + ((int64_t)b * Mo + j) * 11;
         double pix = 0.0, size = 0.0, colmax = 0.0, vert = 0.0;
         int cnt = 0, inter = 0;
@@ -737,16 +787,21 @@ box_summary_kernel(const BoxSummaryArgs A) {
         }
         __syncthreads();                                   // previous item done with shared memory
         const TileRef tref = tile_ref(A.src, b, j, m_stride, mh * mw, row[4], mh, mw);
-        tref.fill(S.tile, mh, tid, kReduceThreads);
+        const bool bits = tref.bits && !tref.mi && mh <= kBitRows;          // CTA-uniform
+        if (bits) {
+            if (tid < mh) S.rows[tid] = tref.valid ? __ldg(tref.bits + tid) : 0u;
+        } else {
+            tref.fill(S.tile, mh, tid, kReduceThreads);
+        }
         for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads) S.unit[y] = A.unit[(int64_t)b * PH + y];
         for (int i = (g.ymin >> 5) + tid; i <= ((g.ymax - 1) >> 5); i += kReduceThreads) S.rowany[i] = 0u;
         __syncthreads();
-        if (cols == 32)
-            box_reduce<1>(S, g, chunk * cols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size,
-                          colmax, cnt, inter);
-        else
-            box_reduce<4>(S, g, chunk * cols, mh, mw, A.road_bits + (int64_t)b * PH * words, words, pix, size,
-                          colmax, cnt, inter);
+        const int c0 = chunk * kBoxCols;
+        const int width = min(kBoxCols, bw - c0);
+        const int cwl = width <= 32 ? 3 : (width <= 64 ? 4 : 5);            // 8 / 16 / 32 lanes per box row
+        const uint32_t* rbits = A.road_bits + (int64_t)b * PH * words;
+        if (bits) box_reduce<true>(S, g, c0, cwl, mh, mw, rbits, words, pix, size, colmax, cnt, inter);
+        else box_reduce<false>(S, g, c0, cwl, mh, mw, rbits, words, pix, size, colmax, cnt, inter);
         __syncthreads();                                   // row flags complete
         if (nchunks == 1) {                                 // the whole box: finish here
             for (int y = g.ymin + tid; y < g.ymax; y += kReduceThreads)
@@ -955,13 +1010,13 @@ extern "C" int mlp_tile_summary(mlp_ctx* ctx, const int32_t* det_i32_dev, const 
     MLP_CHECK_ARG((int64_t)batch * m_rows < (1 << 20) && T.chunks < (1 << 12), "mlp_tile_summary: too many instances / chunks");
     const int64_t acc_bytes = ((int64_t)batch * m_rows * (sizeof(BoxAcc) + (int64_t)ywords * 4) + 15) / 16 * 16 + 16;
     const int64_t item_cap = (int64_t)batch * m_rows * T.chunks;
-    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_BOXACC, acc_bytes + item_cap * 4);
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_BOXACC, acc_bytes + item_cap * (int64_t)sizeof(BoxItem));
     if (rc) return rc;
     MLP_CUDA(cudaMemsetAsync(ctx->arena[MLP_ARENA_BOXACC], 0, (size_t)acc_bytes, st));
     T.acc = static_cast<BoxAcc*>(ctx->arena[MLP_ARENA_BOXACC]);
     T.acc_rowany = reinterpret_cast<uint32_t*>(T.acc + (int64_t)batch * m_rows);
     T.n_items = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->arena[MLP_ARENA_BOXACC]) + acc_bytes - 16);
-    T.items = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->arena[MLP_ARENA_BOXACC]) + acc_bytes);
+    T.items = reinterpret_cast<BoxItem*>(static_cast<char*>(ctx->arena[MLP_ARENA_BOXACC]) + acc_bytes);
     T.item_cap = (int)item_cap;
     box_plan_kernel<<<batch, kReduceThreads, 0, st>>>(T);
     MLP_LAUNCH_CHECK(ctx);

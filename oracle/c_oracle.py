@@ -90,7 +90,9 @@ def prior_layer(prior_cfg, H, W, padding="same"):
 
 def restore_boxes(loc, prior):
     loc = np.ascontiguousarray(loc, F32)
-    prior = np.ascontiguousarray(prior, I32)
+    # the C loop walks loc and prior row by row: a [N,4] (or [1,N,4]) prior is broadcast over the batch here, the way
+    # RestoreBoxes' `loc * prior` broadcasts it (detection.py:325-344)
+    prior = np.ascontiguousarray(np.broadcast_to(np.asarray(prior, I32), loc.shape))
     out = np.empty_like(loc)
     lib().mlo_restore_boxes(_ptr(loc), _ptr(prior), loc.size // 4, _ptr(out))
     return out

@@ -92,6 +92,37 @@ def test_draw_from_tiles_equals_draw_of_pasted_masks(PH, PW, M):
     assert np.array_equal(got4, want4)
 
 
+@pytest.mark.parametrize("M,PH,PW", [(90, 70, 131), (40, 130, 200)])
+def test_draw_from_tiles_crowded_blocks(M, PH, PW):
+    """Many boxes over the same pixels: with 90 instances more than 64 boxes touch one 64x64 block (the per-block
+    geometry cache overflows and the kernel walks the whole candidate list), with 40 the grouped fast path runs with a
+    full list; overlapping instances of one class add up before the > 0.5 test.  Frame sizes that are no multiple of
+    the block or of 4 pixels."""
+    import masklab_b200 as ml
+    B, C = 2, 5
+    rng = np.random.default_rng(M + PW)
+    det = np.zeros((B, M, 6), np.int32)
+    det[..., 0] = rng.integers(0, PW, (B, M))
+    det[..., 1] = rng.integers(0, PH, (B, M))
+    det[..., 2] = rng.integers(PW // 3, 2 * PW, (B, M))             # wide boxes: every block sees most of them
+    det[..., 3] = rng.integers(PH // 3, 2 * PH, (B, M))
+    det[..., 4] = rng.integers(0, C, (B, M))
+    det[..., 5] = rng.integers(60, 100, (B, M))
+    det[1, M - 3:] = -1                                               # padding rows
+    ins = (rng.random((B, M, 28, 28)) > 0.8).astype(np.int32)         # sparse tiles: sums of fractions matter
+    masks = mo.crop_and_pad_mask((PH, PW), det, ins)
+    img = frames(B, PH, PW, 11)
+    seg = synth.semantic_map(B, PH, PW, seed=12)
+    layer = ml.DrawInstance(INST_COLORS, 0.3)
+    want = do.draw_instance(img, det, masks, INST_COLORS, 0.3)
+    got = layer.from_tiles([dev(img), dev(det), dev(ins)]).cpu().numpy()
+    assert np.array_equal(got, want)
+    want2 = do.draw_segmentation(do.draw_instance(do.draw_boxes(img, det), det, masks, INST_COLORS, 0.3), seg, SEM_COLORS, 0.3)
+    got2 = layer.from_tiles([dev(img), dev(det), dev(ins)], seg_outs=dev(seg), semantic_colors=SEM_COLORS,
+                            semantic_alpha=0.3, boxes=True).cpu().numpy()
+    assert np.array_equal(got2, want2)
+
+
 def test_pipeline_draw():
     import masklab_b200 as ml
     B, H, W, C, Cf = 2, 128, 256, 3, 16

@@ -136,6 +136,31 @@ def test_summary_from_tiles_equals_summary_of_pasted_masks(PH, PW, M):
     check_summary(got2, want)
 
 
+def test_summary_from_tiles_narrow_and_wide_boxes():
+    """Every lane layout of the box reduction: boxes 1..40 columns wide (8 lanes per row), 33..64 (16), wider (32),
+    more than one 128-column chunk, single-row and single-column boxes, boxes hanging over the frame edge."""
+    import masklab_b200 as ml
+    B, C, PH, PW, M = 2, 4, 150, 400, 24
+    rng = np.random.default_rng(77)
+    seg = synth.semantic_map(B, PH, PW, seed=78)
+    det = np.zeros((B, M, 6), np.int32)
+    widths = [1, 2, 7, 8, 9, 16, 17, 31, 32, 33, 47, 63, 64, 65, 100, 127, 128, 129, 200, 300, 5, 12, 40, 70]
+    for b in range(B):
+        det[b, :, 2] = widths if b == 0 else widths[::-1]
+        det[b, :, 3] = rng.integers(1, 140, M)
+        det[b, :, 0] = rng.integers(0, PW, M)
+        det[b, :, 1] = rng.integers(0, PH, M)
+        det[b, :, 4] = rng.integers(0, C, M)
+        det[b, :, 5] = rng.integers(55, 100, M)
+    det[0, 3, 3] = 1                                                  # one row
+    det[1, 5, :2] = [PW - 2, PH - 1]                                  # over the corner
+    ins = (rng.random((B, M, 28, 28)) > 0.4).astype(np.int32)
+    masks = mo.crop_and_pad_mask((PH, PW), det, ins)
+    want = so.summary_output(det, seg, masks)
+    got = ml.SummaryOutput().from_tiles([dev(det), dev(seg), dev(ins)]).cpu().numpy()
+    check_summary(got, want)
+
+
 def test_pipeline_trim_and_summarize():
     import masklab_b200 as ml
     B, H, W, C, Cf = 2, 128, 256, 3, 16
