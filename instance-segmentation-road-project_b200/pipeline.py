@@ -10,6 +10,7 @@ head (MaskSubNet, dense convolutions) is not part of this path: the caller runs 
 between `detect_and_align` and `trim_and_paste`.
 """
 import ctypes
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -522,7 +523,10 @@ class PostProcessPipeline:
         tail (road scan + summary beside overlays + JPEG).  Refill the same input tensors and call
         `.replay()`; summary, overlay and files land in the pipeline's buffers (summary_view(), vis, jpeg_files,
         jpeg_len).  As with capture(), the mask head is not part of the graph."""
-        branch = torch.cuda.Stream(device=self.ctx.device)
+        # the summary branch at the least priority, the graph itself captured on a high-priority stream (kernel nodes
+        # inherit it): the overlay -> JPEG chain is the critical path, the summary fills what it leaves free
+        prio = os.environ.get("MLP_SERVING_PRIORITIES", "1") != "0"
+        branch = torch.cuda.Stream(device=self.ctx.device, priority=0) if prio else torch.cuda.Stream(device=self.ctx.device)
 
         def run():
             # two branches (different scratch arenas, no shared state), joined at the end: road scan from the start and
@@ -564,7 +568,8 @@ class PostProcessPipeline:
         torch.cuda.synchronize(self.ctx.device)
         self.ctx.freeze(True)                               # the graph references the arenas from here on
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        cap = torch.cuda.Stream(device=self.ctx.device, priority=-1) if prio else None
+        with torch.cuda.graph(graph, stream=cap):
             rois = run()
         graph._mlp_owner = self                             # the graph replays into this pipeline's buffers and scratch
         return graph, rois
