@@ -153,6 +153,12 @@ struct DeviceGuard {
 #define MLP_BOUND(i, n) do { } while (0)
 #endif
 
+// PyramidRoiAlign's plan (roi.cu, and the fused tail of the cross-class NMS in detect.cu): the record of
+// (level, image, slot) = the source row j of the detection and its box, 32 bytes - what the RoIAlign kernel needs to
+// set a RoI up, in one load instead of the chain slot -> j -> row.
+struct RoiRec { int32_t j; float box[6]; int32_t pad; };   // box = (cx, cy, w, h, class, conf)
+static_assert(sizeof(RoiRec) == 32, "RoiRec layout");
+
 // ------------------------------------------------------- device helpers ------
 // Streaming 128-bit global accesses: read-once inputs bypass L1, write-once
 // outputs do not allocate in L1 (guideline 13/14 of the Blackwell playbook).

@@ -88,7 +88,7 @@ struct FusedPlan {
     float base_eps;         // base_size + K.epsilon()
     float max_k;
     float* dist;            // [B,K,7]
-    int32_t* roi_src;       // [L,B,K] slot -> row
+    RoiRec* roi_rec;        // [L,B,K] slot -> row and box (RoiRec, common.cuh)
     int32_t* level_counts;  // [L,B]
     int32_t* level_m;       // [L+1]
 };
@@ -865,7 +865,7 @@ __device__ void cross_class_body(unsigned char* smem_raw, int b, int B, int C, f
     __syncthreads();
     const int f = tid >> 5, lane = tid & 31;
     if (f < F.L) {
-        int32_t* src = F.roi_src + ((int64_t)f * B + b) * max_out;
+        RoiRec* rec = F.roi_rec + ((int64_t)f * B + b) * max_out;
         int base = 0;
         for (int r0 = 0; r0 < kept; r0 += 32) {
             const int r = r0 + lane;
@@ -873,7 +873,11 @@ __device__ void cross_class_body(unsigned char* smem_raw, int b, int B, int C, f
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (hit) {
                 MLP_BOUND(base + __popc(mask & ((1u << lane) - 1u)), max_out);
-                src[base + __popc(mask & ((1u << lane) - 1u))] = r;
+                RoiRec v;
+                v.j = r; v.pad = 0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) v.box[q] = det_b[r * 6 + q];
+                rec[base + __popc(mask & ((1u << lane) - 1u))] = v;
             }
             base += __popc(mask);
         }
@@ -1110,7 +1114,7 @@ extern "C" int mlp_detect_plan(mlp_ctx* ctx, const mlp_prior_config* prior, cons
     const int L = max_k + 1, K = params->nms_max_output_size;
     {
         DeviceGuard g(ctx->device);
-        int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)L * batch * K * 4);
+        int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)L * batch * K * (int64_t)sizeof(RoiRec));
         if (rc) return rc;
     }
     FusedPlan fp;
@@ -1119,7 +1123,7 @@ extern "C" int mlp_detect_plan(mlp_ctx* ctx, const mlp_prior_config* prior, cons
     fp.base_eps = (float)((double)base_size + 1e-7);
     fp.max_k = (float)max_k;
     fp.dist = dist_dev;
-    fp.roi_src = static_cast<int32_t*>(ctx->arena[MLP_ARENA_ROI]);
+    fp.roi_rec = static_cast<RoiRec*>(ctx->arena[MLP_ARENA_ROI]);
     fp.level_counts = level_counts_dev;
     fp.level_m = level_m_dev;
     return detection_impl(ctx, prior, height, width, cls_dev, loc_dev, batch, N, num_classes, params,

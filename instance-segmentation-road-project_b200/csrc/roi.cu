@@ -20,8 +20,11 @@
 
 namespace {
 
+#ifndef MLP_ROI_PAR_SCHED
+#define MLP_ROI_PAR_SCHED 1              // row schedule of a RoI by 32 lanes (0: one lane, serially)
+#endif
 #ifndef MLP_ROI_MAXNREG
-#define MLP_ROI_MAXNREG 56               // 5 CTAs x 7 warps per SM
+#define MLP_ROI_MAXNREG 64               // 4 CTAs x 7 warps per SM (56 / 5 CTAs spills since the row schedule went parallel; 64 and 72 measured equal)
 #endif
 constexpr int kRoiThreads = 224;         // upper bound (7 warps x 72 registers x 4 CTAs fill an SM); the launch uses 3..7 warps
 constexpr int kMaxCrop = 64;          // crop_h, crop_w <= 64
@@ -34,10 +37,12 @@ struct RoiLevels {
 };
 
 // ---- plan ---------------------------------------------------------------------
-// roi_src [L][B][m_rows] : source row j of (level, image, slot); counts [L][B]; level_m [L].
+// roi_rec [L][B][m_rows] : record of (level, image, slot) = the source row j and its box, 32 bytes - what the run
+// kernel needs to set a RoI up, in one load instead of the chain slot -> j -> row of dist (RoiRec, common.cuh);
+// counts [L][B]; level_m [L].
 __global__ void __launch_bounds__(32 * MLP_MAX_LEVELS)
 roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
-                const int32_t* __restrict__ m_dev, int L, int32_t* __restrict__ roi_src,
+                const int32_t* __restrict__ m_dev, int L, RoiRec* __restrict__ roi_rec,
                 int32_t* __restrict__ counts, int32_t* __restrict__ level_m) {
     const int b = blockIdx.x;
     const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -45,13 +50,19 @@ roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
     int M = m_dev ? *m_dev : m_rows;
     if (M > m_rows) M = m_rows;
     const float* rows = dist + (int64_t)b * m_stride * 7;
-    int32_t* src = roi_src + ((int64_t)f * B + b) * m_rows;
+    RoiRec* rec = roi_rec + ((int64_t)f * B + b) * m_rows;
     int base = 0;
     for (int j0 = 0; j0 < M; j0 += 32) {
         const int j = j0 + lane;
         const bool hit = (j < M) && (rows[(int64_t)j * 7] == (float)f);
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (hit) src[base + __popc(mask & ((1u << lane) - 1u))] = j;
+        if (hit) {
+            RoiRec r;
+            r.j = j; r.pad = 0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) r.box[q] = rows[(int64_t)j * 7 + 1 + q];
+            rec[base + __popc(mask & ((1u << lane) - 1u))] = r;
+        }
         base += __popc(mask);
     }
     if (lane == 0) {
@@ -70,7 +81,7 @@ roi_plan_kernel(const float* __restrict__ dist, int B, int m_rows, int m_stride,
 // Per RoI warp 0 builds the schedule once: the list of source rows to load, and after each row
 // the outputs (row offset, ly) that become computable as lerp(hp, hc, ly).
 constexpr int kMaxRows = 2 * kMaxCrop;       // worst case two new source rows per output row
-constexpr int kRoiWindowBytes = 40 * 1024;   // FPN window staged in shared memory per RoI (5 CTAs per SM)
+constexpr int kRoiWindowBytes = 48 * 1024;   // FPN window staged in shared memory per RoI (4 CTAs per SM)
 
 struct RoiOut { uint32_t yoff; float ly; };  // byte offset of the output row inside the crop, y weight
 struct RoiSched {                            // per-RoI tables, built once per CTA by warp 0
@@ -178,7 +189,7 @@ __device__ __forceinline__ void roi_columns(const unsigned char* __restrict__ sr
 __global__ void __maxnreg__(MLP_ROI_MAXNREG)
 roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ dist, int B,
                  int m_rows, int m_stride, float image_h, float image_w, int ch, int cw,
-                 const int32_t* __restrict__ roi_src, const int32_t* __restrict__ counts,
+                 const RoiRec* __restrict__ roi_rec, const int32_t* __restrict__ counts,
                  int32_t* __restrict__ level_m, float* __restrict__ roi_boxes, int window_cap) {
     extern __shared__ __align__(128) unsigned char s_window[];   // TMA-staged FPN window of this RoI
     __shared__ RoiSched S;
@@ -214,6 +225,11 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
         }
         const int slot = r - foff;
         const int cnt = counts[f * B + b];
+        // the slot's record travels beside the count (warp 0, eight lanes: one 32-byte sector); what it holds for a
+        // padded slot is never used
+        float recv = 0.0f;
+        if (warp == 0 && lane < 8)
+            recv = __ldg(reinterpret_cast<const float*>(roi_rec + ((int64_t)f * B + b) * m_rows + slot) + lane);
         float* out = lv.crops[f] + ((int64_t)b * mf + slot) * npix * Cf;
         float* rb = roi_boxes + (int64_t)item * 6;
 
@@ -234,18 +250,18 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
         __syncthreads();                                     // previous RoI done with tables + window
         if (warp == 0) {
             // ---- the whole per-RoI setup in one warp, one barrier for everybody else
-            const int j = roi_src[((int64_t)f * B + b) * m_rows + slot];
-            MLP_BOUND(j, m_rows);
-            const float* row = dist + ((int64_t)b * m_stride + j) * 7;
+            MLP_BOUND(__float_as_int(__shfl_sync(0xffffffffu, recv, 0)), m_rows);
+            const float bcx = __shfl_sync(0xffffffffu, recv, 1), bcy = __shfl_sync(0xffffffffu, recv, 2);
+            const float bw = __shfl_sync(0xffffffffu, recv, 3), bh = __shfl_sync(0xffffffffu, recv, 4);
             const float hm1 = (float)(Hf - 1), wm1 = (float)(Wf - 1);
-            if (lane < 6) rb[lane] = row[1 + lane];
+            if (lane >= 1 && lane < 7) rb[lane - 1] = recv;
             int ylo = INT_MAX, yhi = -1, xlo = INT_MAX, xhi = -1;
             for (int i = lane; i < ch + cw; i += 32) {
                 // NormalizeBoxes(shape=image) then crop_and_resize source coordinates
                 const bool is_y = i < ch;
                 const int idx = is_y ? i : i - ch;
-                const float c = is_y ? row[2] : row[1];          // cy : cx
-                const float s = is_y ? row[4] : row[3];          // h  : w
+                const float c = is_y ? bcy : bcx;
+                const float s = is_y ? bh : bw;
                 const float dim = is_y ? image_h : image_w;
                 const float half = __fdiv_rn(s, 2.0f);
                 const float lo = __fdiv_rn(__fsub_rn(c, half), dim);      // y1 : x1
@@ -306,9 +322,52 @@ roi_align_kernel(const RoiLevels lv, int L, int Cf, const float* __restrict__ di
                 }
                 S.xl[i] = xl; S.xr[i] = xr; S.lx[i] = lx;
             }
-            if (lane == 0) {                                 // row schedule (serial, ch steps)
-                const uint32_t pitch_bytes = (uint32_t)(pitch * Cf) * 4u;
-                const uint32_t ystride = (uint32_t)(cw * Cf) * 4u;
+            const uint32_t pitch_bytes = (uint32_t)(pitch * Cf) * 4u;
+            const uint32_t ystride = (uint32_t)(cw * Cf) * 4u;
+            if (MLP_ROI_PAR_SCHED && ch <= 32) {
+                // row schedule, one output row per lane: the source rows (t, bo) a row needs against those the previous
+                // valid row left in (hp, hc) decide how many new rows it pushes; positions by ballot prefix counts
+                const float v = lane < ch ? S.iny[lane] : -1.0f;
+                const bool inr = lane < ch;
+                const bool valid = inr && v >= 0.0f && v <= hm1;
+                const float fy = floorf(v);
+                const int t = (int)fy, bo = (int)ceilf(v);
+                const unsigned lt = (1u << lane) - 1u;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                const unsigned before = vmask & lt;
+                const int src = before ? 31 - __clz(before) : 0;      // the previous valid row, wherever it is
+                const int pt = __shfl_sync(0xffffffffu, t, src), pbo = __shfl_sync(0xffffffffu, bo, src);
+                int npush = 0;
+                if (valid) {
+                    if (before && pt == t && pbo == bo) npush = 0;
+                    else if (before && pbo == t) npush = 1;
+                    else npush = 2;
+                }
+                const unsigned m1 = __ballot_sync(0xffffffffu, npush >= 1), m2 = __ballot_sync(0xffffffffu, npush == 2);
+                const unsigned zmask = __ballot_sync(0xffffffffu, inr && !valid);
+                const int kb = __popc(m1 & lt) + __popc(m2 & lt), no = __popc(before);
+                MLP_BOUND(kb + npush, kMaxRows + 1);
+                if (npush == 2) {
+                    S.obeg[kb] = (unsigned short)no;
+                    S.rowoff[kb] = (uint32_t)(t - top0) * pitch_bytes;
+                    S.obeg[kb + 1] = (unsigned short)no;
+                    S.rowoff[kb + 1] = (uint32_t)(bo - top0) * pitch_bytes;
+                } else if (npush == 1) {
+                    S.obeg[kb] = (unsigned short)no;
+                    S.rowoff[kb] = (uint32_t)(bo - top0) * pitch_bytes;
+                }
+                if (valid) {
+                    S.out[no].yoff = (uint32_t)lane * ystride;
+                    S.out[no].ly = __fsub_rn(v, fy);
+                } else if (inr) {
+                    S.zoff[__popc(zmask & lt)] = (uint32_t)lane * ystride;
+                }
+                if (lane == 0) {
+                    const int K = __popc(m1) + __popc(m2);
+                    S.obeg[K] = (unsigned short)__popc(vmask);
+                    S.nrows = K; S.nzero = __popc(zmask); S.staged = staged;
+                }
+            } else if (lane == 0) {                          // crops taller than a warp: the same schedule, serially
                 int K = 0, no = 0, nz = 0;
                 int prev = INT_MIN, cur = INT_MIN;           // source rows held in hp / hc
                 for (int y = 0; y < ch; ++y) {
@@ -446,14 +505,14 @@ extern "C" int mlp_roi_align_plan(mlp_ctx* ctx, const float* dist_dev, int batch
     MLP_CHECK_ARG(num_levels >= 1 && num_levels <= MLP_MAX_LEVELS,
                   "mlp_roi_align_plan: num_levels=%d out of range", num_levels);
     DeviceGuard g(ctx->device);
-    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)num_levels * batch * m_rows * 4);
+    int rc = mlp_ensure_scratch(ctx, MLP_ARENA_ROI, (int64_t)num_levels * batch * m_rows * (int64_t)sizeof(RoiRec));
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(ctx, MLP_ST_ROI_PLAN, st);
     MLP_CUDA(cudaMemsetAsync(level_m_dev, 0, (size_t)(num_levels + 1) * 4, st));
     roi_plan_kernel<<<batch, 32 * MLP_MAX_LEVELS, 0, st>>>(
         dist_dev, batch, m_rows, m_stride, m_dev, num_levels,
-        static_cast<int32_t*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev, level_m_dev);
+        static_cast<RoiRec*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev, level_m_dev);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
 }
@@ -477,7 +536,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
                       crop_h + crop_w <= 2 * kMaxCrop,
                   "mlp_roi_align_run: crop size %dx%d out of range [1,%d]", crop_h, crop_w, kMaxCrop);
     MLP_CHECK_ARG(ctx->arena[MLP_ARENA_ROI] &&
-                      ctx->arena_bytes[MLP_ARENA_ROI] >= (int64_t)num_levels * batch * m_rows * 4,
+                      ctx->arena_bytes[MLP_ARENA_ROI] >= (int64_t)num_levels * batch * m_rows * (int64_t)sizeof(RoiRec),
                   "mlp_roi_align_run: call mlp_roi_align_plan with the same shapes first");
     RoiLevels lv;
     memset(&lv, 0, sizeof(lv));
@@ -527,7 +586,7 @@ extern "C" int mlp_roi_align_run(mlp_ctx* ctx, const float* const* fmaps_dev, co
     MLP_CUDA(cudaFuncSetAttribute(roi_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_kernel<<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
         lv, num_levels, channels, dist_dev, batch, m_rows, m_stride, image_h, image_w, crop_h, crop_w,
-        static_cast<const int32_t*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev,
+        static_cast<const RoiRec*>(ctx->arena[MLP_ARENA_ROI]), level_counts_dev,
         level_m_dev, roi_boxes_dev, window_cap);
     MLP_LAUNCH_CHECK(ctx);
     return MLP_OK;
