@@ -24,7 +24,7 @@ constexpr int kTileRegs = 4;              // tile elements prefetched per thread
 __host__ __device__ inline int paste_tile_bytes(int px) { return (px * 4 + 15) & ~15; }
 inline size_t paste_smem_bytes(int mask_h, int mask_w, int frame_w) {
     (void)frame_w;
-    return (size_t)paste_tile_bytes(mask_h * mask_w) + (size_t)kMaxCols * sizeof(uint2);
+    return (size_t)paste_tile_bytes(mask_h * mask_w) + (size_t)kMaxCols * sizeof(uint4);   // 16-byte entries on the bit path
 }
 
 // One 16-byte output segment (kVec pixels starting at x0 = seg * kVec) of frame row oy of an instance: the
@@ -73,6 +73,84 @@ __device__ __forceinline__ uint4 paste_segment(const float* __restrict__ s_tile,
     return v;
 }
 
+// ---- the same for tiles that arrive as bit rows (the fused tail: {0,1} by construction, mw <= 32) ----------------
+// Column table entry: single-bit masks of the two source columns, lx and fadd(1, -lx); columns of the table's
+// segments that lie outside the box carry empty masks, so their value is +0 without a range test.  The x lerp
+// tl + (tr - tl) * lx of a tile row is then one of 0, lx, 1 - lx, 1 - picked by the two corner bits with the same
+// float32 result as the arithmetic - and a pixel costs one 16-byte shared load instead of five loads.
+template <int kVec>
+__device__ __forceinline__ void paste_fill_cols_bits(uint4* __restrict__ s_col, const PasteGeom& g, int mw, int tid,
+                                                     int nthreads) {
+    const int sL = g.xmin / kVec;
+    const int bw = (g.xmax + kVec - 1) / kVec - sL;
+    const int n = bw * kVec;                                 // <= kMaxCols (the caller checked)
+    const int wpx = g.xmax - g.xmin;
+    for (int i = tid; i < n; i += nthreads) {
+        const int q = i / bw, sg = i - q * bw;
+        const int c = (sL + sg) * kVec + q - g.xmin;         // box column of that pixel
+        const float p = __fmul_rn((float)c, g.sx);
+        const float fl = floorf(p);
+        const int xlo = min(max((int)fl, 0), mw - 1);
+        const int xhi = min(max((int)ceilf(p), 0), mw - 1);
+        const float lx = __fsub_rn(p, fl);
+        const bool in = c >= 0 && c < wpx;
+        MLP_BOUND(i, kMaxCols);
+        s_col[i] = make_uint4(in ? 1u << xlo : 0u, in ? 1u << xhi : 0u, __float_as_uint(lx),
+                              __float_as_uint(__fsub_rn(1.0f, lx)));
+    }
+}
+
+__device__ __forceinline__ float paste_value_bits(uint32_t w0, uint32_t w1, float ly, const uint4 e) {
+    const float lx = __uint_as_float(e.z), oml = __uint_as_float(e.w);
+    const bool tl = (w0 & e.x) != 0u, tr = (w0 & e.y) != 0u, bl = (w1 & e.x) != 0u, br = (w1 & e.y) != 0u;
+    const float t = tl ? (tr ? 1.0f : oml) : (tr ? lx : 0.0f);
+    const float b = bl ? (br ? 1.0f : oml) : (br ? lx : 0.0f);
+    return __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), ly));
+}
+
+template <int kMode>
+__device__ __forceinline__ uint4 paste_segment_bits(const uint32_t* __restrict__ s_rows, const uint4* __restrict__ col,
+                                                    int pitch, const PasteGeom& g, int mh, int oy, int x0) {
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
+    const float p = __fmul_rn((float)(oy - g.ymin), g.sy);
+    const float fl = floorf(p);
+    const uint32_t w0 = s_rows[max((int)fl, 0)], w1 = s_rows[min((int)ceilf(p), mh - 1)];
+    const float ly = __fsub_rn(p, fl);
+    uint4 v;
+    if (kMode == MLP_PASTE_U8) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (paste_value_bits(w0, w1, ly, col[q * pitch]) > 0.5f) w[q >> 2] |= 1u << ((q & 3) * 8);
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (kMode == MLP_PASTE_BITS) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const int q0 = max(g.xmin - x0, 0), q1 = min(g.xmax - x0, kVec);   // pixels of the segment inside the box
+        for (int q = q0; q < q1; ++q)
+            if (paste_value_bits(w0, w1, ly, col[q * pitch]) > 0.5f) w[q >> 5] |= 1u << (q & 31);
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        float f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = paste_value_bits(w0, w1, ly, col[q * pitch]);
+        v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    return v;
+}
+
+template <int kMode>
+__device__ __forceinline__ void paste_box_rows_bits(const uint32_t* __restrict__ s_rows, const uint4* __restrict__ s_col,
+                                                    const PasteGeom& g, int mh, int y_first, int nrows, int sL, int bw,
+                                                    uint4* __restrict__ rows_out, int spr, int tid) {
+    constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
+    const int nb = nrows * bw;
+    for (int i = tid; i < nb; i += kPasteThreads) {
+        const int r = i / bw, sg = i - r * bw;
+        const uint4 v = paste_segment_bits<kMode>(s_rows, s_col + sg, bw, g, mh, y_first + r, (sL + sg) * kVec);
+        stg_stream_u4(rows_out + (int64_t)r * spr + sL + sg, v);
+    }
+}
+
 // All segments [0, nb) of `nrows` box rows starting at frame row y_first, flattened over the CTA.
 template <int kMode>
 __device__ __forceinline__ void paste_box_rows(const float* __restrict__ s_tile, const uint2* __restrict__ s_col,
@@ -111,15 +189,16 @@ __device__ __forceinline__ void paste_box_rows(const float* __restrict__ s_tile,
 template <int kMode>       // MLP_PASTE_F32 / MLP_PASTE_U8 / MLP_PASTE_BITS
 __global__ void __launch_bounds__(kPasteThreads, MLP_PASTE_MIN_CTAS)
 paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh,
-             int mw, int PH, int PW, int band_rows, int use_cols, void* __restrict__ out) {
+             int mw, int PH, int PW, int band_rows, int bands, int grid3, int use_cols, void* __restrict__ out) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);   // pixels per 16-byte store
     extern __shared__ __align__(16) unsigned char s_dyn[];           // [tile floats][column table], paste_smem_bytes
     float* s_tile = reinterpret_cast<float*>(s_dyn);
     uint2* s_col_buf = reinterpret_cast<uint2*>(s_dyn + paste_tile_bytes(mh * mw));
     // Items are numbered over the CAPACITY grid (image, slot < m_rows, band), so that a CTA knows its instance - and
     // can fetch its detection row - without waiting for the device-side M; slots >= M leave once M has arrived.
-    const int bands = (PH + band_rows - 1) / band_rows;
-    const int64_t items = (int64_t)B * m_rows * bands;
+    // grid3: the launch is (band, slot, image) - one item per CTA, its coordinates straight from blockIdx (no
+    // integer division on the way to the first store); else a 1-D grid-stride loop over the same numbering.
+    const int64_t items = grid3 ? 1 : (int64_t)B * m_rows * bands;
     const int spr = PW / kVec;                     // 16-byte segments per frame row
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -127,16 +206,21 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     int M = -1, thr = 0;
 
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        int slot, band;
-        if (items <= 0x7fffffffLL) {                // the usual case: 32-bit division
-            slot = (int)((uint32_t)item / (uint32_t)bands);
-            band = (int)((uint32_t)item - (uint32_t)slot * (uint32_t)bands);
+    for (int64_t item = grid3 ? 0 : blockIdx.x; item < items; item += gridDim.x) {
+        int band, b, j;
+        if (grid3) {
+            band = blockIdx.x; j = blockIdx.y; b = blockIdx.z;
         } else {
-            slot = (int)(item / bands);
-            band = (int)(item - (int64_t)slot * bands);
+            int slot;
+            if (items <= 0x7fffffffLL) {            // the usual case: 32-bit division
+                slot = (int)((uint32_t)item / (uint32_t)bands);
+                band = (int)((uint32_t)item - (uint32_t)slot * (uint32_t)bands);
+            } else {
+                slot = (int)(item / bands);
+                band = (int)(item - (int64_t)slot * bands);
+            }
+            b = slot / m_rows; j = slot - b * m_rows;
         }
-        const int b = slot / m_rows, j = slot - b * m_rows;
         int row[6];
         if (m_stride != 0) {                        // capacity layout: the row does not depend on M - load it first
             const int2* p = reinterpret_cast<const int2*>(det + ((int64_t)b * m_stride + j) * 6);
@@ -162,14 +246,23 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         // the mask tile is only needed by phase B2: issue its loads now, park them in shared
         // memory after the zero rows have been streamed out
         int tile_regs[kTileRegs];
+        uint32_t row_word = 0u;                     // bit path: tile row `tid`
+        bool bitp = false;                          // block-uniform
         TileRef tref;
         tref.mi = nullptr; tref.mf = nullptr; tref.bits = nullptr; tref.es = 1; tref.mw = mw; tref.valid = false;
         if (touches) {
             tref = tile_ref(S, b, j, stride, px, row[4], mh, mw);
+            // bit rows + a column table that fits: the bit path (one 4-byte load per tile row instead of the tile)
+            bitp = use_cols && tref.bits && !tref.mi && mh <= kPasteThreads &&
+                   ((g.xmax + kVec - 1) / kVec - g.xmin / kVec) * kVec <= kMaxCols;
+            if (bitp) {
+                if (tid < mh && tref.valid) row_word = __ldg(tref.bits + tid);
+            } else {
 #pragma unroll
-            for (int q = 0; q < kTileRegs; ++q) {
-                const int i = tid + q * kPasteThreads;
-                tile_regs[q] = (i < px) ? tref.at(i) : 0;
+                for (int q = 0; q < kTileRegs; ++q) {
+                    const int i = tid + q * kPasteThreads;
+                    tile_regs[q] = (i < px) ? tref.at(i) : 0;
+                }
             }
         }
         uint4* band_base = reinterpret_cast<uint4*>(out) + ((int64_t)inst * PH + y0) * spr;
@@ -197,14 +290,20 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         }
         if (!touches) continue;
         __syncthreads();                           // previous item's phase B2 done with s_tile
+        bool cols = false;
+        if (bitp) {
+            if (tid < mh) reinterpret_cast<uint32_t*>(s_tile)[tid] = row_word;
+            paste_fill_cols_bits<kVec>(reinterpret_cast<uint4*>(s_col_buf), g, mw, tid, kPasteThreads);
+        } else {
 #pragma unroll
-        for (int q = 0; q < kTileRegs; ++q) {
-            const int i = tid + q * kPasteThreads;
-            if (i < px) s_tile[i] = (float)tile_regs[q];
+            for (int q = 0; q < kTileRegs; ++q) {
+                const int i = tid + q * kPasteThreads;
+                if (i < px) s_tile[i] = (float)tile_regs[q];
+            }
+            for (int i = tid + kTileRegs * kPasteThreads; i < px; i += kPasteThreads)
+                s_tile[i] = (float)tref.at(i);
+            cols = use_cols && paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
         }
-        for (int i = tid + kTileRegs * kPasteThreads; i < px; i += kPasteThreads)
-            s_tile[i] = (float)tref.at(i);
-        const bool cols = use_cols && paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
         const int sL = g.xmin / kVec;                       // first segment touching the box
         const int sR = (g.xmax + kVec - 1) / kVec;          // one past the last
         const int bw = sR - sL;
@@ -219,7 +318,11 @@ paste_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_row
         }
         __syncthreads();                           // s_tile / column table ready
         // ---- phase B2: segments intersecting the box, flattened over the CTA
-        paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, ya, yb - ya, sL, bw, box_rows, spr, tid);
+        if (bitp)
+            paste_box_rows_bits<kMode>(reinterpret_cast<const uint32_t*>(s_tile), reinterpret_cast<const uint4*>(s_col_buf),
+                                       g, mh, ya, yb - ya, sL, bw, box_rows, spr, tid);
+        else
+            paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, ya, yb - ya, sL, bw, box_rows, spr, tid);
     }
 }
 
@@ -611,14 +714,25 @@ paste_boxes_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int
         const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
         if (!g.active || j >= M) continue;                  // filtered by the batch-wide confidence rule (block-uniform)
         const TileRef tref = tile_ref(S, b, j, K, px, row[4], mh, mw);
-        __syncthreads();                                    // previous item done with s_tile / s_col
-        tref.fill(s_tile, mh, tid, kPasteThreads);
-        const bool cols = paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
-        __syncthreads();
         const int sL = g.xmin / kVec;
         const int bw = (g.xmax + kVec - 1) / kVec - sL;
+        const bool bitp = tref.bits && !tref.mi && mh <= kPasteThreads && bw * kVec <= kMaxCols;   // block-uniform
+        __syncthreads();                                    // previous item done with s_tile / s_col
+        bool cols = false;
+        if (bitp) {
+            if (tid < mh) reinterpret_cast<uint32_t*>(s_tile)[tid] = tref.valid ? __ldg(tref.bits + tid) : 0u;
+            paste_fill_cols_bits<kVec>(reinterpret_cast<uint4*>(s_col_buf), g, mw, tid, kPasteThreads);
+        } else {
+            tref.fill(s_tile, mh, tid, kPasteThreads);
+            cols = paste_fill_cols<kVec>(s_col_buf, g, mw, tid, kPasteThreads);
+        }
+        __syncthreads();
         uint4* rows_out = reinterpret_cast<uint4*>(out) + (((int64_t)b * M + j) * PH + y0) * spr;
-        paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, y0, nrows, sL, bw, rows_out, spr, tid);
+        if (bitp)
+            paste_box_rows_bits<kMode>(reinterpret_cast<const uint32_t*>(s_tile), reinterpret_cast<const uint4*>(s_col_buf),
+                                       g, mh, y0, nrows, sL, bw, rows_out, spr, tid);
+        else
+            paste_box_rows<kMode>(s_tile, s_col_buf, cols, g, mh, mw, y0, nrows, sL, bw, rows_out, spr, tid);
     }
 }
 
@@ -649,9 +763,13 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
         int band_rows = (band_kb * 1024) / row_bytes;
         if (band_rows < 1) band_rows = 1;
         if (band_rows > frame_h) band_rows = frame_h;
-        const int64_t items = (int64_t)batch * m_rows * ((frame_h + band_rows - 1) / band_rows);
-        int grid = (int)(items < (1ll << 30) ? items : (1ll << 30));
-        if (ctas_per_sm > 0) grid = ctx->sm_count * ctas_per_sm;
+        const int bands = (frame_h + band_rows - 1) / band_rows;
+        const int64_t items = (int64_t)batch * m_rows * bands;
+        // one CTA per item, numbered (band, slot, image) by a 3-D grid; a 1-D grid-stride loop for the tuning knob and
+        // for shapes beyond the grid limits
+        const bool grid3 = ctas_per_sm <= 0 && m_rows <= 65535 && batch <= 65535;
+        dim3 grid(bands, m_rows, batch);
+        if (!grid3) grid = dim3((unsigned)(ctas_per_sm > 0 ? ctx->sm_count * ctas_per_sm : (items < (1ll << 30) ? items : (1ll << 30))));
         size_t smem = paste_smem_bytes(mask_h, mask_w, frame_w);
         int use_cols = 1;
         if (const char* e = getenv("MLP_PASTE_COLS")) use_cols = atoi(e);
@@ -669,7 +787,7 @@ int paste_launch(mlp_ctx* ctx, const int32_t* det_i32_dev, const PasteSrc& S, in
         }
 #define MLP_PASTE_LAUNCH(MODE)                                                                         \
     paste_kernel<MODE><<<grid, kPasteThreads, smem, st>>>(det_i32_dev, S, batch, m_rows, m_stride, mask_h, \
-                                                      mask_w, frame_h, frame_w, band_rows, use_cols, out_dev)
+                                                      mask_w, frame_h, frame_w, band_rows, bands, grid3 ? 1 : 0, use_cols, out_dev)
         if (out_mode == MLP_PASTE_U8) MLP_PASTE_LAUNCH(MLP_PASTE_U8);
         else if (out_mode == MLP_PASTE_BITS) MLP_PASTE_LAUNCH(MLP_PASTE_BITS);
         else MLP_PASTE_LAUNCH(MLP_PASTE_F32);

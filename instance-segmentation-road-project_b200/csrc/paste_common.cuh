@@ -128,7 +128,7 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
         const int2 v = __ldg(reinterpret_cast<const int2*>(S.scalars));
         M = min(v.x, m_rows);
         thr = v.y;
-        if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+        if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -146,7 +146,7 @@ __device__ __forceinline__ void paste_scalars(const PasteSrc& S, int B, int m_ro
     if (M > m_rows) M = m_rows;
     if (mn < M) cm = max(cm, -100);        // MoldBatch padding rows carry conf = int(-1*100)
     thr = (cm > 50) ? 50 : -100;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0 && S.m_out) *S.m_out = M;
 }
 
 // Part of the tail preparation, called by ONE CTA per image right after it has published counts[b] / confmax[b]
