@@ -144,10 +144,15 @@ __device__ __forceinline__ void paste_box_rows_bits(const uint32_t* __restrict__
                                                     uint4* __restrict__ rows_out, int spr, int tid) {
     constexpr int kVec = kMode == MLP_PASTE_F32 ? 4 : (kMode == MLP_PASTE_U8 ? 16 : 128);
     const int nb = nrows * bw;
+    // (sharing a segment between 2 or 4 threads for boxes with few segments was measured: no change)
+    // (row, segment) of item i = tid + k * 256, advanced without a division per item
+    int r = tid / bw, sg = tid - r * bw;
+    const int dr = kPasteThreads / bw, ds = kPasteThreads - dr * bw;
     for (int i = tid; i < nb; i += kPasteThreads) {
-        const int r = i / bw, sg = i - r * bw;
         const uint4 v = paste_segment_bits<kMode>(s_rows, s_col + sg, bw, g, mh, y_first + r, (sL + sg) * kVec);
         stg_stream_u4(rows_out + (int64_t)r * spr + sL + sg, v);
+        r += dr; sg += ds;
+        if (sg >= bw) { sg -= bw; ++r; }
     }
 }
 
