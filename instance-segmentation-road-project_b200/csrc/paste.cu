@@ -494,11 +494,17 @@ paste_fill_kernel(const int32_t* __restrict__ m_from_dev, const int32_t* __restr
 // thresholds its class channel out of shared memory with one ballot per mask row.
 constexpr int kPrepTmaWarps = 4;
 
-template <int kWarps>
+// kByRow: a valid row belongs to the CTA `j % parts` (its source row) instead of `slot % parts`, and s_slot[j]
+// receives the slot of every row (kNoSlot: not an instance, or beyond the capacity K) - the bulk-copy kernel starts
+// its copies by source row before the ranks are known.
+constexpr int kSlotMapCap = 4096;          // source rows per image the slot map holds
+constexpr unsigned short kNoSlot = 0xffffu;
+
+template <int kWarps, bool kByRow>
 __device__ __forceinline__ int tail_scan(const float* __restrict__ rows, int R, int K, float rh, float rw,
                                          int part, int parts, int32_t* __restrict__ drows,
                                          int32_t* __restrict__ src, int* s_cnt, int* s_base, int* s_cm,
-                                         const BoxItems& Q, int b) {
+                                         const BoxItems& Q, int b, unsigned short* s_slot = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg = (R + kWarps - 1) / kWarps;
     const int j0 = min(warp * seg, R), j1 = min(j0 + seg, R);
@@ -534,7 +540,7 @@ __device__ __forceinline__ int tail_scan(const float* __restrict__ rows, int R, 
                 for (int q = 0; q < 6; ++q) r[q] = rows[(int64_t)j * 6 + q];
                 upsample_row(r, rh, rw, o);
                 cm = max(cm, o[5]);
-                mine = slot % parts == part;
+                mine = kByRow ? (j % parts == part) : (slot % parts == part);
                 if (mine) {
 #pragma unroll
                     for (int q = 0; q < 6; ++q) drows[slot * 6 + q] = o[q];
@@ -542,6 +548,7 @@ __device__ __forceinline__ int tail_scan(const float* __restrict__ rows, int R, 
                 }
             }
         }
+        if (kByRow && j < j1) s_slot[j] = (hit && slot < K) ? (unsigned short)slot : kNoSlot;
         if (Q.vec && mask) box_items_append(Q, mine, o, b * K + slot);       // warp-uniform branch
         base += __popc(mask);
     }
@@ -573,15 +580,47 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
     extern __shared__ __align__(128) unsigned char s_stage[];     // [kWarps][slot_bytes]
     __shared__ __align__(8) uint64_t s_bar[kWarps];
     __shared__ int s_cnt[kWarps], s_base[kWarps + 1], s_cm[kWarps];
+    __shared__ unsigned short s_slot[kSlotMapCap];                // source row -> slot (R <= kSlotMapCap, host checks)
     const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) mbar_init(&s_bar[warp], 1);
     int R = r_dev ? *r_dev : r_rows;
     if (R > r_rows) R = r_rows;
+    const float* rows = roi_boxes + (int64_t)b * R * 6;
     int32_t* drows = det_i32 + (int64_t)b * K * 6;
     int32_t* src = tail_src + (int64_t)b * K;
-    const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
-                                        s_cnt, s_base, s_cm, Q, b);
+    const int px = mh * mw;
+    unsigned char* stage = s_stage + (size_t)warp * slot_bytes;
+    uint64_t* bar = &s_bar[warp];
+    uint32_t phase = 0;
+    const int es = planar ? 1 : C;
+    // The copy of a RoI's block depends on its SOURCE row only, its destination on the rank of that row: the warp
+    // starts the copy of its first row now and learns the ranks (tail_scan) while the bytes are in flight.
+    // Returns the class (>= 0) if a copy was started, -1 for a class outside the head's channels (all-zero tile, no
+    // copy), -2 for a row that is no instance.  Called by the whole warp.
+    auto start_copy = [&](int j) -> int {
+        const float cf = __ldg(rows + (int64_t)j * 6 + 4);
+        if (cf == -1.0f) return -2;
+        const int cls = __float2int_rz(cf);
+        if (cls < 0 || cls >= C) return -1;
+        const float* g = planar ? roi_masks + (((int64_t)b * R + j) * C + cls) * px
+                                : roi_masks + ((int64_t)b * R + j) * px * C;
+        if (lane == 0) {
+            mbar_expect_tx(bar, slot_bytes);
+            // the warp's generic-proxy reads of the previous tile (ordered by the __syncwarp before the call)
+            // come before the async proxy overwrites the slot
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_load_1d(stage, g, slot_bytes, bar);
+        }
+        __syncwarp();
+        return cls;
+    };
+    const int jstep = parts * kWarps;
+    int j = part + parts * warp;                      // the rows of this warp: j, j + jstep, ...
+    __syncwarp();                                     // mbarrier initialised before its first use
+    int st = j < R ? start_copy(j) : -2;
+    const int total = tail_scan<kWarps, true>(rows, R, K, rh, rw, part, parts, drows, src, s_cnt, s_base, s_cm, Q, b,
+                                              s_slot);
     if (part == 0) {                                  // one CTA per image publishes its count / confidence maximum and
         if (threadIdx.x == 0) {                       // arrives; the last image reduces M and the row-filter threshold
             int m = INT_MIN;                          // while every CTA's tile copies are still in flight
@@ -591,45 +630,34 @@ tail_prep_tma_kernel(const float* __restrict__ roi_boxes, const float* __restric
         }
         tail_finish(scalars, counts, confmax, gridDim.x, K, gridDim.x, m_out);
     }
-    const int px = mh * mw;
-    unsigned char* stage = s_stage + (size_t)warp * slot_bytes;
-    uint64_t* bar = &s_bar[warp];
-    uint32_t phase = 0;
-    const int es = planar ? 1 : C;
-    for (int s = part + parts * warp; s < total; s += parts * kWarps) {
-        const int j = src[s];
-        MLP_BOUND(j, R);
-        MLP_BOUND(s, K);
-        const int cls = drows[s * 6 + 4];
-        uint32_t* out = tail_bits + ((int64_t)b * K + s) * mh;
-        if (cls < 0 || cls >= C) {                           // tf.gather_nd would raise: all-zero tile
-            for (int y = lane; y < mh; y += 32) out[y] = 0u;
-            continue;
+    while (j < R) {
+        const unsigned slot = s_slot[j];
+        if (st >= 0) {                                // the copy of row j has landed (a row beyond K discards it)
+            mbar_wait(bar, phase);
+            phase ^= 1u;
         }
-        const float* g = planar ? roi_masks + (((int64_t)b * R + j) * C + cls) * px
-                                : roi_masks + ((int64_t)b * R + j) * px * C;
-        if (lane == 0) {
-            mbar_expect_tx(bar, slot_bytes);
-            // the warp's generic-proxy reads of the previous tile (ordered by the __syncwarp below)
-            // come before the async proxy overwrites the slot
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tma_load_1d(stage, g, slot_bytes, bar);
-        }
-        __syncwarp();
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        const float* t = reinterpret_cast<const float*>(stage) + (planar ? 0 : cls);
-        for (int y0 = 0; y0 < mh; y0 += 32) {
-            uint32_t mine = 0u;
-            const int yn = min(32, mh - y0);
-            for (int u = 0; u < yn; ++u) {
-                const float v = (lane < mw) ? t[((y0 + u) * mw + lane) * es] : 0.0f;
-                const uint32_t w = __ballot_sync(0xffffffffu, v > 0.5f);
-                if (lane == u) mine = w;
+        if (slot != kNoSlot) {
+            MLP_BOUND((int)slot, K);
+            uint32_t* out = tail_bits + ((int64_t)b * K + slot) * mh;
+            if (st < 0) {                             // tf.gather_nd would raise: all-zero tile
+                for (int y = lane; y < mh; y += 32) out[y] = 0u;
+            } else {
+                const float* t = reinterpret_cast<const float*>(stage) + (planar ? 0 : st);
+                for (int y0 = 0; y0 < mh; y0 += 32) {
+                    uint32_t mine = 0u;
+                    const int yn = min(32, mh - y0);
+                    for (int u = 0; u < yn; ++u) {
+                        const float v = (lane < mw) ? t[((y0 + u) * mw + lane) * es] : 0.0f;
+                        const uint32_t w = __ballot_sync(0xffffffffu, v > 0.5f);
+                        if (lane == u) mine = w;
+                    }
+                    if (lane < yn) out[y0 + lane] = mine;
+                }
             }
-            if (lane < yn) out[y0 + lane] = mine;
         }
         __syncwarp();
+        j += jstep;
+        st = j < R ? start_copy(j) : -2;
     }
 }
 
@@ -650,7 +678,7 @@ tail_prep_kernel(const float* __restrict__ roi_boxes, const float* __restrict__ 
     if (R > r_rows) R = r_rows;
     int32_t* drows = det_i32 + (int64_t)b * K * 6;
     int32_t* src = tail_src + (int64_t)b * K;
-    const int total = tail_scan<kWarps>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
+    const int total = tail_scan<kWarps, false>(roi_boxes + (int64_t)b * R * 6, R, K, rh, rw, part, parts, drows, src,
                                         s_cnt, s_base, s_cm, Q, b);
     if (part == 0) {
         if (threadIdx.x == 0) {
@@ -919,12 +947,13 @@ extern "C" int mlp_trim_paste(mlp_ctx* ctx, const float* roi_boxes_dev, const fl
         // multiple of 16 bytes or too large to stage, and for the tile-less case (many instances).
         const int px = mask_h * mask_w;
         const int64_t slot_bytes = (int64_t)px * (planar ? 1 : num_classes) * 4;
-        bool tma = tail_bits != nullptr && slot_bytes % 16 == 0 && slot_bytes * kPrepTmaWarps <= 200 * 1024;
+        bool tma = tail_bits != nullptr && slot_bytes % 16 == 0 && slot_bytes * kPrepTmaWarps <= 190 * 1024 &&
+                   r_rows <= kSlotMapCap;
         if (const char* e = getenv("MLP_TAIL_TMA")) tma = tma && atoi(e) != 0;              // A/B knob
         if (tma) {
-            // at most two tiles per warp: one wave of CTAs, enough bytes in flight per SM
-            int per_warp = 2;                                                             // tuning knob
-            if (const char* e = getenv("MLP_TAIL_SLOTS_PER_WARP")) per_warp = atoi(e) > 0 ? atoi(e) : 2;
+            // about one tile per warp (measured 1 / 2 / 3 with the copies started by source row: 19.1 / 20.9 / 21.8 us)
+            int per_warp = 1;                                                             // tuning knob
+            if (const char* e = getenv("MLP_TAIL_SLOTS_PER_WARP")) per_warp = atoi(e) > 0 ? atoi(e) : 1;
             int parts = (k_rows + per_warp * kPrepTmaWarps - 1) / (per_warp * kPrepTmaWarps);
             parts = parts < 1 ? 1 : (parts > 64 ? 64 : parts);
             const size_t smem = (size_t)slot_bytes * kPrepTmaWarps;
