@@ -123,6 +123,33 @@ def test_draw_from_tiles_crowded_blocks(M, PH, PW):
     assert np.array_equal(got2, want2)
 
 
+@pytest.mark.parametrize("kind", ["int_nonbinary", "float_fraction", "float_onehot"])
+def test_draw_from_tiles_semantic_map_values(kind):
+    """The overlay kernel looks DrawSegmentation's colour term up in a table when an int32 map holds only 0 / 1; every
+    other map - int32 values beyond 1 (also negative), float32 maps, fractional or not - takes the arithmetic path.
+    One frame mixes both kinds of warps (binary rows above, other values below)."""
+    import masklab_b200 as ml
+    B, M, PH, PW = 2, 6, 96, 128
+    img = frames(B, PH, PW, 21)
+    det, ins, masks = scene(B, M, PH, PW, seed=22)
+    seg = synth.semantic_map(B, PH, PW, seed=23)
+    rng = np.random.default_rng(24)
+    if kind == "int_nonbinary":
+        seg = seg.astype(np.int32)
+        seg[:, PH // 2:] = rng.integers(-2, 4, seg[:, PH // 2:].shape)
+        seg[0, 3, 5, 1] = 7
+    elif kind == "float_fraction":
+        seg = seg.astype(np.float32)
+        seg[:, PH // 2:] = rng.random(seg[:, PH // 2:].shape, dtype=np.float32)
+    else:
+        seg = seg.astype(np.float32)
+    layer = ml.DrawInstance(INST_COLORS, 0.3)
+    want = do.draw_segmentation(do.draw_instance(do.draw_boxes(img, det), det, masks, INST_COLORS, 0.3), seg, SEM_COLORS, 0.4)
+    got = layer.from_tiles([dev(img), dev(det), dev(ins)], seg_outs=dev(seg), semantic_colors=SEM_COLORS,
+                           semantic_alpha=0.4, boxes=True).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_pipeline_draw():
     import masklab_b200 as ml
     B, H, W, C, Cf = 2, 128, 256, 3, 16
