@@ -133,39 +133,6 @@ struct DrawGeom {                         // clipped box of an instance in the f
     int pad;
 };
 
-// One warp per instance: bit rows of its {0,1} tile (mask_w <= 32) and its geometry.
-__global__ void __launch_bounds__(kDrawThreads)
-pack_tiles_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh, int mw,
-                  int PH, int PW, int num_colors, DrawGeom* __restrict__ geom, uint32_t* __restrict__ bits,
-                  int32_t* __restrict__ m_used) {
-    int M, thr;
-    paste_scalars(S, B, m_rows, M, thr);
-    if (m_stride == 0) m_stride = M;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *m_used = M;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t inst = (int64_t)blockIdx.x * (kDrawThreads / 32) + warp;
-    if (inst >= (int64_t)B * M) return;
-    const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
-    const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
-    const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
-    const int cls = row[4];
-    const bool draw = g.active && cls >= 0 && cls < num_colors;
-    const int64_t slot = (int64_t)b * m_rows + j;
-    if (lane == 0) {
-        DrawGeom d;
-        d.xmin = g.xmin; d.xmax = g.xmax; d.ymin = g.ymin; d.ymax = g.ymax; d.sx = g.sx; d.sy = g.sy;
-        d.cls = draw ? cls : -1; d.pad = 0;
-        geom[slot] = d;
-    }
-    if (!draw) return;
-    const TileRef tref = tile_ref(S, b, j, m_stride, mh * mw, cls, mh, mw);
-    for (int y = 0; y < mh; ++y) {
-        const int v = lane < mw ? tref.at(y * mw + lane) : 0;
-        const unsigned w = __ballot_sync(0xffffffffu, v != 0);
-        if (lane == 0) bits[slot * mh + y] = w;
-    }
-}
-
 #ifndef MLP_DRAW_MIN_CTAS
 #define MLP_DRAW_MIN_CTAS 4
 #endif
@@ -662,19 +629,11 @@ draw_boxes_kernel(const int32_t* __restrict__ det, int B, int m_rows, int m_stri
 }
 
 // The same lines as one bit per pixel ([B, H, words], zeroed before the launch) for draw_tiles_kernel: the frame is
-// then neither copied nor written before the overlay pass.  Horizontal lines are word-wide ORs.
-__global__ void __launch_bounds__(kDrawThreads)
-box_lines_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int H, int W,
-                 int words, uint32_t* __restrict__ bits) {
-    int M, thr;
-    paste_scalars(S, B, m_rows, M, thr);                  // the rows the tail kept (M on the device)
-    if (m_stride == 0) m_stride = M;
-    const int lane = threadIdx.x & 31;
-    const int64_t box = (int64_t)blockIdx.x * (kDrawThreads / 32) + (threadIdx.x >> 5);
-    if (box >= (int64_t)B * M) return;
-    const int b = (int)(box / M), j = (int)(box - (int64_t)b * M);
+// then neither copied nor written before the overlay pass.  Horizontal lines are word-wide ORs.  One warp per box.
+__device__ __forceinline__ void box_lines_warp(const int32_t* __restrict__ row, int b, int H, int W, int words,
+                                               uint32_t* __restrict__ bits, int lane) {
     BoxRect r;
-    if (!box_rect(det + ((int64_t)b * m_stride + j) * 6, H, W, r)) return;
+    if (!box_rect(row, H, W, r)) return;
     const int y0c = max(r.y0, 0), y1c = min(r.y1, H - 1), x0c = max(r.x0, 0), x1c = min(r.x1, W - 1);
     uint32_t* img = bits + (int64_t)b * H * words;
     for (int wi = (x0c >> 5) + lane; wi <= (x1c >> 5); wi += 32) {
@@ -686,6 +645,46 @@ box_lines_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m
     for (int y = y0c + lane; y <= y1c; y += 32) {
         if (r.x0 >= 0) atomicOr(img + (int64_t)y * words + (r.x0 >> 5), 1u << (r.x0 & 31));
         if (r.x1 < W) atomicOr(img + (int64_t)y * words + (r.x1 >> 5), 1u << (r.x1 & 31));
+    }
+}
+
+// One warp per instance, ahead of draw_tiles_kernel: its clipped-box geometry, the bit rows of its {0,1} tile
+// (mask_w <= 32; a tail that already holds bit rows is copied word by word) and - with line_bits - the four
+// one-pixel lines of DrawBoxes' rectangle in the one-bit-per-pixel map (every row the tail kept, whatever its class).
+__global__ void __launch_bounds__(kDrawThreads)
+pack_tiles_kernel(const int32_t* __restrict__ det, const PasteSrc S, int B, int m_rows, int m_stride, int mh, int mw,
+                  int PH, int PW, int num_colors, DrawGeom* __restrict__ geom, uint32_t* __restrict__ bits,
+                  int32_t* __restrict__ m_used, uint32_t* __restrict__ line_bits, int line_words) {
+    int M, thr;
+    paste_scalars(S, B, m_rows, M, thr);
+    if (m_stride == 0) m_stride = M;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *m_used = M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t inst = (int64_t)blockIdx.x * (kDrawThreads / 32) + warp;
+    if (inst >= (int64_t)B * M) return;
+    const int b = (int)(inst / M), j = (int)(inst - (int64_t)b * M);
+    const int32_t* row = det + ((int64_t)b * m_stride + j) * 6;
+    if (line_bits) box_lines_warp(row, b, PH, PW, line_words, line_bits, lane);
+    const PasteGeom g = paste_geometry(row, thr, mh, mw, PH, PW);
+    const int cls = row[4];
+    const bool draw = g.active && cls >= 0 && cls < num_colors;
+    const int64_t slot = (int64_t)b * m_rows + j;
+    if (lane == 0) {
+        DrawGeom d;
+        d.xmin = g.xmin; d.xmax = g.xmax; d.ymin = g.ymin; d.ymax = g.ymax; d.sx = g.sx; d.sy = g.sy;
+        d.cls = draw ? cls : -1; d.pad = 0;
+        geom[slot] = d;
+    }
+    if (!draw) return;
+    const TileRef tref = tile_ref(S, b, j, m_stride, mh * mw, cls, mh, mw);
+    if (tref.bits && !tref.mi) {                            // the fused tail's bit rows: a copy
+        for (int y = lane; y < mh; y += 32) bits[slot * mh + y] = tref.valid ? __ldg(tref.bits + y) : 0u;
+        return;
+    }
+    for (int y = 0; y < mh; ++y) {
+        const int v = lane < mw ? tref.at(y * mw + lane) : 0;
+        const unsigned w = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) bits[slot * mh + y] = w;
     }
 }
 
@@ -820,15 +819,10 @@ static int draw_tiles_impl(mlp_ctx* ctx, const void* images_dev, int image_dtype
     int32_t* m_used = reinterpret_cast<int32_t*>(bits + n_inst * mask_h);
     uint32_t* line_bits = boxes ? reinterpret_cast<uint32_t*>(m_used + 4) : nullptr;
     const int wpc = kDrawThreads / 32;
-    if (boxes) {
-        MLP_CUDA(cudaMemsetAsync(line_bits, 0, (size_t)line_bytes, st));
-        box_lines_kernel<<<(int)((n_inst + wpc - 1) / wpc), kDrawThreads, 0, st>>>(det_i32_dev, S, batch, m_rows, m_stride,
-                                                                                  frame_h, frame_w, line_words, line_bits);
-        MLP_LAUNCH_CHECK(ctx);
-    }
+    if (boxes) MLP_CUDA(cudaMemsetAsync(line_bits, 0, (size_t)line_bytes, st));
     pack_tiles_kernel<<<(int)((n_inst + wpc - 1) / wpc), kDrawThreads, 0, st>>>(
         det_i32_dev, S, batch, m_rows, m_stride, mask_h, mask_w, frame_h, frame_w, inst_colors->num_classes, geom,
-        bits, m_used);
+        bits, m_used, line_bits, line_words);
     MLP_LAUNCH_CHECK(ctx);
     DrawTilesArgs A;
     memset(&A, 0, sizeof(A));
